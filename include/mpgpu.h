@@ -1,0 +1,148 @@
+/* mpgpu.h -- C-ABI of the B200-native parsimony hot path (libmpgpu.so).
+ *
+ * This is the drop-in boundary for MPBoot's data-parallel parsimony path.  The reference has
+ * no FFI; its "operator API" is the set of free functions of sprparsimony.h:13-54 that work on
+ * a pllInstance/partitionList pair plus the REPS block of IQTree::saveCurrentTree.  Every entry
+ * point below names the reference interface it replaces (file:line under the reference tree).
+ * INTEGRATION.md shows the shim a maintainer adds to sprparsimony.cpp / iqtree.cpp.
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; mpgpu_last_error() gives the text
+ *     (the host shim turns it into outError(), tools.cpp:91).  There is NO CPU fallback: if
+ *     no CUDA device is usable every compute call fails.
+ *   - the caller owns all host buffers; the context owns all device memory.  Calls are
+ *     synchronous on return unless stated otherwise.
+ *   - trees travel as PLL "ring tables": nodes 1..n are tips, n+1..2n-2 inner nodes; an inner
+ *     node has ring slots 0,1,2 (slot s+1 = ->next of slot s, pllrepo/src/pll.h:687-702), a
+ *     tip only slot 0.  back_node[3*i+s] / back_slot[3*i+s] = node number and slot hooked to
+ *     slot s of node i (->back), 0 = NULL.  Both arrays have 3*(2n-1) entries.  A "ref"
+ *     (pointer to one ring slot, i.e. a nodeptr) is encoded as 3*node+slot.
+ *   - alignment data are PLL codes exactly as in tr->yVector (after pllBaseSubstitute,
+ *     pllrepo/src/utils.c:2526) and pattern frequencies exactly as in tr->aliaswgt.
+ */
+#ifndef MPGPU_H
+#define MPGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpgpu_ctx mpgpu_ctx;
+
+/* PLL data types (pllrepo/src/pll.h:238-245) accepted by mpgpu_load_alignment */
+#define MPGPU_BINARY_DATA 0
+#define MPGPU_DNA_DATA    1
+#define MPGPU_AA_DATA     2
+#define MPGPU_GENERIC_32  6
+
+const char *mpgpu_last_error(void);
+
+/* Number of usable CUDA devices (0 when none / driver missing). */
+int mpgpu_device_count(void);
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to launch on
+ * (e.g. torch's current stream) or NULL for a private stream.  shard_rank/shard_count
+ * select the contiguous word slice of every bit plane this context holds (pattern sharding,
+ * SURVEY 8e); use 0/1 for a single GPU.  When shard_count > 1 the per-shard partial counts
+ * returned by the *_partial calls must be summed over shards by the caller (NCCL
+ * all-reduce of the int32 vector) before they are scores. */
+int mpgpu_create(mpgpu_ctx **out, int device, void *stream, int shard_rank, int shard_count);
+int mpgpu_destroy(mpgpu_ctx *ctx);
+/* The stream all kernels are launched on (cudaStream_t). */
+void *mpgpu_stream(mpgpu_ctx *ctx);
+int mpgpu_synchronize(mpgpu_ctx *ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t mpgpu_launch_count(mpgpu_ctx *ctx);
+
+/* ---- R1: _allocateParsimonyDataStructures / compressDNA (sprparsimony.cpp:3032, 2828) ----
+ * yvector: [ntaxa][npatterns] PLL codes (tr->yVector[1..n]); aliaswgt: [npatterns]
+ * (tr->aliaswgt).  sort_alignment mirrors Params::sort_alignment (isInformative returns TRUE
+ * for every site when it is 0, sprparsimony.cpp:2462).  Builds the tip bit planes on the
+ * device: pattern i expanded aliaswgt[i] times, padding bits set in every state. */
+int mpgpu_load_alignment(mpgpu_ctx *ctx, int ntaxa, int npatterns, int datatype,
+                         const uint8_t *yvector, const int32_t *aliaswgt, int sort_alignment);
+/* _updateInternalPllOnRatchet + re-compress (sprparsimony.cpp:3022, 3249-3252): new pattern
+ * frequencies over the same resident codes (ratchet / bootstrap-replicate re-weighting). */
+int mpgpu_set_weights(mpgpu_ctx *ctx, const int32_t *aliaswgt);
+/* states, reference parsimonyLength (words per plane padded to 8 as the AVX build,
+ * sprparsimony.cpp:2870-2879), device words per plane of THIS shard, informative patterns
+ * (numInformativePatterns :2862), expanded sites.  Any pointer may be NULL. */
+int mpgpu_get_layout(mpgpu_ctx *ctx, int *states, int *ref_words, int *shard_words,
+                     int *n_informative, int64_t *n_sites);
+/* Tip planes in the reference layout parsVect[tip][state][ref_words] (tip in 1..n);
+ * single-shard contexts only.  For parity tests of R1. */
+int mpgpu_get_tip_planes(mpgpu_ctx *ctx, int tip, uint32_t *out);
+
+/* ---- R2/R3: directed Fitch views of a tree (newviewParsimonyIterativeFast :554) ----
+ * Uploads the topology and recomputes every directed view: for each ring slot (node,slot)
+ * the Fitch state sets of the subtree that contains `node` when the edge at that slot is cut
+ * (what parsVect[node] holds when xPars sits on that slot, pll.h:622-640). */
+int mpgpu_set_tree(mpgpu_ctx *ctx, const int32_t *back_node, const int32_t *back_slot);
+/* Mismatch count of every directed view of this shard (popcount of t_N, :773), indexed by
+ * view id: tips 0..n-1 (always 0), inner (node,slot) -> n + 3*(node-n-1) + slot.
+ * 4n-6 entries.  Sum over shards, then hand back with mpgpu_set_view_counts. */
+int mpgpu_get_view_counts_partial(mpgpu_ctx *ctx, uint32_t *counts);
+int mpgpu_set_view_counts(mpgpu_ctx *ctx, const uint32_t *counts);
+/* tr->parsimonyScore[] equivalent: Fitch length of the subtree behind ref (node,slot). */
+int mpgpu_view_length(mpgpu_ctx *ctx, int node, int slot, uint32_t *length);
+/* The planes of one directed view in the reference layout [state][ref_words] (parity). */
+int mpgpu_get_view_planes(mpgpu_ctx *ctx, int node, int slot, uint32_t *out);
+
+/* ---- R4: evaluateParsimony(tr, pr, tr->start, full) (:1889, :965) ----
+ * Tree length evaluated across the edge at tip 1 (tr->start).  Single shard: *score is the
+ * score.  Sharded: *score is this shard's partial mismatch count of that edge and the caller
+ * adds the all-reduced value to mpgpu_view_length of tip 1's neighbour. */
+int mpgpu_tree_score(mpgpu_ctx *ctx, uint32_t *score);
+/* Mismatch count across an arbitrary edge given by one of its refs (partial if sharded). */
+int mpgpu_edge_mismatch_partial(mpgpu_ctx *ctx, int node, int slot, uint32_t *count);
+
+/* ---- R5: pllComputePatternParsimony(ushort) (:3363) ----
+ * Per-pattern Fitch score of the current tree, ptn_pars[0..upper) with upper =
+ * numInformativePatterns (sort_alignment) or npatterns, and *sum = sum ptn_pars*aliaswgt.
+ * Same site arithmetic as the reference (site += aliaswgt[ptn] over the prefix). */
+int mpgpu_pattern_parsimony(mpgpu_ctx *ctx, uint16_t *ptn_pars, int32_t *sum);
+
+/* ---- R6: SPR scan (rearrangeParsimony :2259, addTraverseParsimony :2208,
+ *          testInsertParsimony :2106) ----
+ * nodeRectifierPars (:2083): visit order of the sweep as refs, order[1..2n-2] (order[0]
+ * unused), computed for the tree last given to mpgpu_set_tree. */
+int mpgpu_visit_order(mpgpu_ctx *ctx, int32_t *order);
+/* Scores, in one batched launch, every insertion that rearrangeParsimony would test for the
+ * visits order[first..first+count) on the CURRENT tree.  Results are laid out per visit in
+ * the reference's visit order: visit_begin[k]..visit_begin[k+1] index mp[]; within a visit
+ * first the candidates of the p side then of the q side, each in addTraverseParsimony's
+ * pre-order.  cand_ref[j] = ref of the insertion branch q (tr->insertNode if chosen),
+ * cand_prune[j] = ref of the pruned node (tr->removeNode).  mp[j] is the full tree score
+ * the reference computes at :2160.  visit_begin needs count+1 entries; the candidate arrays
+ * `capacity` entries; *n_cand returns the number produced (error if capacity is too small).
+ * Single shard only (sharded callers use the _partial variant below). */
+int mpgpu_scan_visits(mpgpu_ctx *ctx, const int32_t *order, int first, int count,
+                      int mintrav, int maxtrav,
+                      int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune,
+                      int capacity, int *n_cand);
+/* Sharded form: plan on the host (identical on every rank), count on the device, finish
+ * after the all-reduce.  counts has n_cand + n_tasks entries (mpgpu_scan_plan returns both). */
+int mpgpu_scan_plan(mpgpu_ctx *ctx, const int32_t *order, int first, int count, int mintrav, int maxtrav,
+                    int *n_cand, int *n_tasks);
+/* Launches the scan of the planned batch; the int32 partial counts stay on the device at
+ * *dev_counts (n_cand+n_tasks entries) for an in-place NCCL all-reduce.  Asynchronous. */
+int mpgpu_scan_launch(mpgpu_ctx *ctx, void **dev_counts);
+int mpgpu_scan_finish(mpgpu_ctx *ctx, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref,
+                      int32_t *cand_prune, int capacity);
+
+/* ---- pllOptimizeSprParsimony (:3244) ----
+ * Hill-climbing SPR search on the tree given as ring tables (modified in place, like `tr`).
+ * rng is the host's random_double() (tools.cpp:3362); it is called exactly where and as often
+ * as the reference calls it.  Returns the reference's return value (startMP) in *best.
+ * n_insertions (nullable) returns how many insertions were scored on the device. */
+typedef double (*mpgpu_rng_fn)(void *user);
+int mpgpu_optimize_spr(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot,
+                       int mintrav, int maxtrav, mpgpu_rng_fn rng, void *rng_user,
+                       uint32_t *best, int64_t *n_insertions);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPGPU_H */

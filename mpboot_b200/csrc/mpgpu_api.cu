@@ -1,0 +1,620 @@
+// C-ABI layer of libmpgpu.so (include/mpgpu.h): context management, data movement and the
+// host-side orchestration of the kernels in fitch_kernels.cu.  No CPU fallback anywhere: every
+// compute entry point needs a CUDA device and fails loudly otherwise.
+#include "mpgpu_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace mpgpu {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return 2;
+}
+
+template <typename T>
+static int ensure(T *&ptr, size_t &cap, size_t need)
+{
+    if (need <= cap && ptr) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = need + need / 4 + 16;
+    MPGPU_CUDA(cudaMalloc((void **)&ptr, want * sizeof(T)));
+    cap = want;
+    return 0;
+}
+
+static int states_of(int datatype)
+{
+    switch (datatype) {
+    case MPGPU_BINARY_DATA: return 2;
+    case MPGPU_DNA_DATA:    return 4;
+    case MPGPU_AA_DATA:     return 20;
+    case MPGPU_GENERIC_32:  return 32;
+    default: return -1;
+    }
+}
+
+// isInformative (sprparsimony.cpp:2460-2499): at least two distinct codes below `undetermined`
+static void find_informative(Ctx *c, const uint8_t *yvec)
+{
+    int und = 0;
+    state_mask_table(c->datatype, nullptr, &und);
+    c->informative.assign(c->P, 1);
+    if (c->sort_alignment) {
+        std::vector<int32_t> first(c->P, -1);
+        std::fill(c->informative.begin(), c->informative.end(), 0);
+        for (int t = 0; t < c->n; t++) {
+            const uint8_t *row = yvec + (size_t)t * c->P;
+            for (int i = 0; i < c->P; i++) {
+                const int code = row[i];
+                if (code >= und) continue;
+                if (first[i] < 0) first[i] = code;
+                else if (first[i] != code) c->informative[i] = 1;
+            }
+        }
+    }
+    c->n_inf = 0;
+    for (int i = 0; i < c->P; i++) c->n_inf += c->informative[i];
+}
+
+static void free_alignment(Ctx *c)
+{
+    if (c->d_codes) cudaFree(c->d_codes);
+    if (c->d_site_start) cudaFree(c->d_site_start);
+    if (c->d_inf_ptn) cudaFree(c->d_inf_ptn);
+    if (c->d_views) cudaFree(c->d_views);
+    if (c->d_vcount) cudaFree(c->d_vcount);
+    c->d_codes = nullptr; c->d_site_start = nullptr; c->d_inf_ptn = nullptr; c->d_views = nullptr; c->d_vcount = nullptr;
+    c->tree_set = false; c->lens_valid = false;
+}
+
+// layout + tip planes for the current weights (compressDNA, sprparsimony.cpp:2864-2961)
+static int build_planes(Ctx *c, bool realloc_views)
+{
+    std::vector<int64_t> site_start(c->n_inf + 1);
+    std::vector<int32_t> inf_ptn(c->n_inf > 0 ? c->n_inf : 1);
+    int64_t sites = 0; int k = 0;
+    for (int i = 0; i < c->P; i++) {
+        if (!c->informative[i]) continue;
+        site_start[k] = sites; inf_ptn[k] = i; k++;
+        sites += c->weights[i];
+    }
+    site_start[k] = sites;
+    c->n_sites = sites;
+    int64_t words = (sites + 31) / 32;                       // compressedEntries :2870
+    int64_t refw = words % 8 ? words + (8 - words % 8) : words;   // padded to INTS_PER_VECTOR (AVX) :2876
+    c->ref_words = (int)refw;
+    const int64_t quantum = (int64_t)kWordPad * c->shard_count;
+    int64_t glob = (words + quantum - 1) / quantum * quantum;
+    if (glob == 0) glob = quantum;
+    const int newWl = (int)(glob / c->shard_count);
+    if (newWl != c->Wl || glob != c->glob_words) realloc_views = true;
+    c->glob_words = (int)glob; c->Wl = newWl; c->w0 = (int64_t)c->shard_rank * newWl;
+    c->view_stride = (size_t)c->S * c->Wl;
+
+    if (c->d_site_start) { cudaFree(c->d_site_start); c->d_site_start = nullptr; }
+    if (c->d_inf_ptn) { cudaFree(c->d_inf_ptn); c->d_inf_ptn = nullptr; }
+    MPGPU_CUDA(cudaMalloc((void **)&c->d_site_start, sizeof(int64_t) * (c->n_inf + 1)));
+    MPGPU_CUDA(cudaMalloc((void **)&c->d_inf_ptn, sizeof(int32_t) * inf_ptn.size()));
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_site_start, site_start.data(), sizeof(int64_t) * (c->n_inf + 1), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_inf_ptn, inf_ptn.data(), sizeof(int32_t) * inf_ptn.size(), cudaMemcpyHostToDevice, c->stream));
+
+    const size_t nviews = (size_t)(4 * c->n - 6);
+    if (realloc_views || !c->d_views) {
+        if (c->d_views) cudaFree(c->d_views);
+        if (c->d_vcount) cudaFree(c->d_vcount);
+        c->d_views = nullptr; c->d_vcount = nullptr;
+        MPGPU_CUDA(cudaMalloc((void **)&c->d_views, nviews * c->view_stride * sizeof(uint32_t)));
+        MPGPU_CUDA(cudaMalloc((void **)&c->d_vcount, nviews * sizeof(uint32_t)));
+    }
+    if (c->n_inf > 0) { if (int rc = launch_compress(c)) return rc; }
+    else MPGPU_CUDA(cudaMemsetAsync(c->d_views, 0xff, (size_t)c->n * c->view_stride * sizeof(uint32_t), c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // host staging vectors go out of scope
+    c->lens_valid = false;
+    return 0;
+}
+
+// level schedule of all directed views + launch (one kernel per level)
+static int compute_views(Ctx *c)
+{
+    const HostTree &t = c->tree;
+    const int n = t.n;
+    const int nviews = 4 * n - 6;
+    std::vector<int> level(nviews, -1);
+    for (int i = 0; i < n; i++) level[i] = 0;
+    c->levels.clear();
+    // iterative post-order over the dependency DAG
+    std::vector<int> stack;
+    for (int node = n + 1; node <= 2 * n - 2; node++) for (int s = 0; s < 3; s++) {
+        const int root = 3 * node + s;
+        if (!t.has_back(root)) continue;
+        if (level[t.vid(root)] >= 0) continue;
+        stack.push_back(root);
+        while (!stack.empty()) {
+            const int r = stack.back();
+            const int v = t.vid(r);
+            if (level[v] >= 0) { stack.pop_back(); continue; }
+            const int a = t.back(t.next(r)), b = t.back(t.next(t.next(r)));
+            const int la = level[t.vid(a)], lb = level[t.vid(b)];
+            if (la >= 0 && lb >= 0) {
+                const int l = std::max(la, lb) + 1;
+                level[v] = l;
+                if ((int)c->levels.size() < l) c->levels.resize(l);
+                Triple tr; tr.dst = v; tr.a = t.vid(a); tr.b = t.vid(b); tr.pad = 0;
+                c->levels[l - 1].push_back(tr);
+                stack.pop_back();
+            } else {
+                if (la < 0) stack.push_back(a);
+                if (lb < 0) stack.push_back(b);
+            }
+        }
+    }
+    size_t total = 0;
+    for (auto &lv : c->levels) total += lv.size();
+    if (int rc = ensure(c->d_triples, c->triples_cap, total)) return rc;
+    std::vector<Triple> flat; flat.reserve(total);
+    for (auto &lv : c->levels) flat.insert(flat.end(), lv.begin(), lv.end());
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_triples, flat.data(), total * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(c->d_vcount, 0, nviews * sizeof(uint32_t), c->stream));
+    size_t off = 0;
+    for (auto &lv : c->levels) {
+        if (int rc = launch_level(c, c->d_triples + off, (int)lv.size())) return rc;
+        off += lv.size();
+    }
+    c->vcount.assign(nviews, 0);
+    MPGPU_CUDA(cudaMemcpyAsync(c->vcount.data(), c->d_vcount, nviews * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// subtree lengths from (all-reduced) mismatch counts, in level order
+static void compute_lengths(Ctx *c)
+{
+    const int nviews = 4 * c->n - 6;
+    c->vlen.assign(nviews, 0);
+    for (auto &lv : c->levels)
+        for (const Triple &tr : lv) c->vlen[tr.dst] = c->vlen[tr.a] + c->vlen[tr.b] + c->vcount[tr.dst];
+    c->lens_valid = true;
+}
+
+static int need_tree(Ctx *c, bool lens)
+{
+    if (!c) { set_error("null context"); return 1; }
+    if (!c->d_views) { set_error("no alignment loaded"); return 1; }
+    if (!c->tree_set) { set_error("no tree set"); return 1; }
+    if (lens && !c->lens_valid) { set_error("view lengths not set (sharded context: call mpgpu_set_view_counts)"); return 1; }
+    return 0;
+}
+
+static int upload_plan(Ctx *c)
+{
+    ScanPlan &pl = c->plan;
+    if (int rc = ensure(c->d_ops, c->ops_cap, pl.ops.size() + 1)) return rc;
+    if (int rc = ensure(c->d_tasks, c->tasks_cap, pl.tasks.size() + 1)) return rc;
+    if (int rc = ensure(c->d_counts, c->counts_cap, (size_t)pl.n_cand + pl.tasks.size() + 1)) return rc;
+    if (!pl.ops.empty())
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_ops, pl.ops.data(), pl.ops.size() * sizeof(ScanOp), cudaMemcpyHostToDevice, c->stream));
+    if (!pl.tasks.empty())
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_tasks, pl.tasks.data(), pl.tasks.size() * sizeof(ScanTask), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static int run_scan(Ctx *c)
+{
+    ScanPlan &pl = c->plan;
+    const size_t nout = (size_t)pl.n_cand + pl.tasks.size();
+    MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, (nout + 1) * sizeof(int32_t), c->stream));
+    return launch_scan(c, (int)pl.tasks.size(), pl.max_slot);
+}
+
+static int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
+{
+    ScanPlan &pl = c->plan;
+    if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
+    const size_t nout = (size_t)pl.n_cand + pl.tasks.size();
+    c->h_counts.resize(nout + 1);
+    MPGPU_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->d_counts, nout * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < pl.n_cand; j++) {
+        const int ti = pl.cand_task[j];
+        mp[j] = pl.task_const[ti] + (uint32_t)c->h_counts[pl.n_cand + ti] + (uint32_t)c->h_counts[j];
+    }
+    if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
+    if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
+    if (cand_prune) memcpy(cand_prune, pl.cand_prune.data(), pl.n_cand * sizeof(int32_t));
+    return 0;
+}
+
+}  // namespace mpgpu
+
+using namespace mpgpu;
+
+struct mpgpu_ctx : public mpgpu::Ctx {};
+
+extern "C" {
+
+const char *mpgpu_last_error(void) { return g_error.c_str(); }
+
+int mpgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mpgpu_create(mpgpu_ctx **out, int device, void *stream, int shard_rank, int shard_count)
+{
+    if (!out) { set_error("null out pointer"); return 1; }
+    *out = nullptr;
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) { set_error("bad shard arguments"); return 1; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libmpgpu has no CPU fallback");
+        return 3;
+    }
+    if (device < 0 || device >= ndev) { set_error("bad device index"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(device));
+    mpgpu_ctx *c = new mpgpu_ctx();
+    c->device = device; c->shard_rank = shard_rank; c->shard_count = shard_count;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { MPGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    MPGPU_CUDA(cudaMalloc((void **)&c->d_scalar, 64 * sizeof(uint32_t)));
+    *out = c;
+    return 0;
+}
+
+int mpgpu_destroy(mpgpu_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_alignment(c);
+    if (c->d_triples) cudaFree(c->d_triples);
+    if (c->d_scalar) cudaFree(c->d_scalar);
+    if (c->d_ops) cudaFree(c->d_ops);
+    if (c->d_tasks) cudaFree(c->d_tasks);
+    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->d_bitcnt) cudaFree(c->d_bitcnt);
+    if (c->d_pairs) cudaFree(c->d_pairs);
+    if (c->d_ptn) cudaFree(c->d_ptn);
+    if (c->d_ptn_site) cudaFree(c->d_ptn_site);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+void *mpgpu_stream(mpgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int mpgpu_synchronize(mpgpu_ctx *c) { if (!c) return 1; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+int64_t mpgpu_launch_count(mpgpu_ctx *c) { return c ? c->launches : 0; }
+
+int mpgpu_load_alignment(mpgpu_ctx *c, int ntaxa, int npatterns, int datatype,
+                         const uint8_t *yvector, const int32_t *aliaswgt, int sort_alignment)
+{
+    if (!c || !yvector || !aliaswgt) { set_error("null argument"); return 1; }
+    const int S = states_of(datatype);
+    if (S < 0) { set_error("unsupported data type"); return 1; }
+    if (ntaxa < 4 || npatterns < 1) { set_error("need at least 4 taxa and 1 pattern"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    free_alignment(c);
+    c->n = ntaxa; c->P = npatterns; c->datatype = datatype; c->S = S; c->sort_alignment = sort_alignment;
+    c->weights.assign(aliaswgt, aliaswgt + npatterns);
+    for (int i = 0; i < npatterns; i++) if (aliaswgt[i] < 0) { set_error("negative pattern weight"); return 1; }
+    find_informative(c, yvector);
+    MPGPU_CUDA(cudaMalloc((void **)&c->d_codes, (size_t)ntaxa * npatterns));
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_codes, yvector, (size_t)ntaxa * npatterns, cudaMemcpyHostToDevice, c->stream));
+    c->Wl = 0; c->glob_words = 0;
+    return build_planes(c, true);
+}
+
+int mpgpu_set_weights(mpgpu_ctx *c, const int32_t *aliaswgt)
+{
+    if (!c || !aliaswgt) { set_error("null argument"); return 1; }
+    if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < c->P; i++) if (aliaswgt[i] < 0) { set_error("negative pattern weight"); return 1; }
+    c->weights.assign(aliaswgt, aliaswgt + c->P);
+    if (int rc = build_planes(c, false)) return rc;
+    if (c->tree_set) {                      // views depend on the planes
+        if (int rc = compute_views(c)) return rc;
+        if (c->shard_count == 1) compute_lengths(c);
+    }
+    return 0;
+}
+
+int mpgpu_get_layout(mpgpu_ctx *c, int *states, int *ref_words, int *shard_words, int *n_informative, int64_t *n_sites)
+{
+    if (!c || !c->d_views) { set_error("no alignment loaded"); return 1; }
+    if (states) *states = c->S;
+    if (ref_words) *ref_words = c->ref_words;
+    if (shard_words) *shard_words = c->Wl;
+    if (n_informative) *n_informative = c->n_inf;
+    if (n_sites) *n_sites = c->n_sites;
+    return 0;
+}
+
+static int copy_view_ref_layout(mpgpu_ctx *c, int vid, uint32_t *out)
+{
+    if (c->shard_count != 1) { set_error("plane read-back is single-shard only"); return 1; }
+    std::vector<uint32_t> tmp(c->view_stride);
+    MPGPU_CUDA(cudaMemcpyAsync(tmp.data(), c->d_views + (size_t)vid * c->view_stride, c->view_stride * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < c->S; s++)
+        for (int w = 0; w < c->ref_words; w++)
+            out[(size_t)s * c->ref_words + w] = w < c->Wl ? tmp[(size_t)s * c->Wl + w] : 0xFFFFFFFFu;
+    return 0;
+}
+
+int mpgpu_get_tip_planes(mpgpu_ctx *c, int tip, uint32_t *out)
+{
+    if (!c || !c->d_views || !out) { set_error("no alignment loaded"); return 1; }
+    if (tip < 1 || tip > c->n) { set_error("tip out of range"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    return copy_view_ref_layout(c, tip - 1, out);
+}
+
+int mpgpu_set_tree(mpgpu_ctx *c, const int32_t *back_node, const int32_t *back_slot)
+{
+    if (!c || !back_node || !back_slot) { set_error("null argument"); return 1; }
+    if (!c->d_views) { set_error("no alignment loaded"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    const int n = c->n, len = 3 * (2 * n - 1);
+    HostTree &t = c->tree;
+    t.n = n; t.bn.assign(back_node, back_node + len); t.bs.assign(back_slot, back_slot + len);
+    // validate: every slot of a complete unrooted binary tree is hooked symmetrically
+    for (int node = 1; node <= 2 * n - 2; node++) {
+        const int ns = node <= n ? 1 : 3;
+        for (int s = 0; s < ns; s++) {
+            const int r = 3 * node + s;
+            const int bnode = t.bn[r], bslot = t.bs[r];
+            if (bnode < 1 || bnode > 2 * n - 2 || bslot < 0 || bslot > (bnode <= n ? 0 : 2)) { set_error("ring table: dangling or out-of-range back pointer"); return 1; }
+            const int b = 3 * bnode + bslot;
+            if (t.bn[b] != node || t.bs[b] != s) { set_error("ring table: back pointers are not symmetric"); return 1; }
+        }
+    }
+    c->tree_set = true; c->lens_valid = false;
+    if (int rc = compute_views(c)) return rc;
+    if (c->shard_count == 1) compute_lengths(c);
+    return 0;
+}
+
+int mpgpu_get_view_counts_partial(mpgpu_ctx *c, uint32_t *counts)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    memcpy(counts, c->vcount.data(), c->vcount.size() * sizeof(uint32_t));
+    return 0;
+}
+
+int mpgpu_set_view_counts(mpgpu_ctx *c, const uint32_t *counts)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    c->vcount.assign(counts, counts + (4 * c->n - 6));
+    compute_lengths(c);
+    return 0;
+}
+
+static int check_ref(mpgpu_ctx *c, int node, int slot)
+{
+    if (node < 1 || node > 2 * c->n - 2 || slot < 0 || slot > (node <= c->n ? 0 : 2)) { set_error("bad (node,slot)"); return 1; }
+    return 0;
+}
+
+int mpgpu_view_length(mpgpu_ctx *c, int node, int slot, uint32_t *length)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (int rc = check_ref(c, node, slot)) return rc;
+    *length = c->vlen[c->tree.vid(3 * node + slot)];
+    return 0;
+}
+
+int mpgpu_get_view_planes(mpgpu_ctx *c, int node, int slot, uint32_t *out)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    if (int rc = check_ref(c, node, slot)) return rc;
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    return copy_view_ref_layout(c, c->tree.vid(3 * node + slot), out);
+}
+
+int mpgpu_edge_mismatch_partial(mpgpu_ctx *c, int node, int slot, uint32_t *count)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    if (int rc = check_ref(c, node, slot)) return rc;
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    const int r = 3 * node + slot;
+    MPGPU_CUDA(cudaMemsetAsync(c->d_scalar, 0, sizeof(uint32_t), c->stream));
+    if (int rc = launch_edge_mismatch(c, c->tree.vid(r), c->tree.vid(c->tree.back(r)), c->d_scalar)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(count, c->d_scalar, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mpgpu_tree_score(mpgpu_ctx *c, uint32_t *score)
+{
+    if (int rc = need_tree(c, c && c->shard_count == 1)) return rc;
+    uint32_t mis = 0;
+    if (int rc = mpgpu_edge_mismatch_partial(c, 1, 0, &mis)) return rc;
+    if (c->shard_count == 1) *score = mis + c->vlen[c->tree.vid(c->tree.back(3))];
+    else *score = mis;
+    return 0;
+}
+
+int mpgpu_pattern_parsimony(mpgpu_ctx *c, uint16_t *ptn_pars, int32_t *sum)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    if (!ptn_pars) { set_error("null argument"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    const HostTree &t = c->tree;
+    const int n = c->n;
+    // child-view pairs of the n-2 inner views facing tr->start, plus the start edge
+    std::vector<int32_t> order;
+    visit_order(t, order);
+    std::vector<int32_t> pairs;
+    for (int i = n + 1; i <= 2 * n - 2; i++) {
+        const int r = order[i];
+        pairs.push_back(t.vid(t.back(t.next(r))));
+        pairs.push_back(t.vid(t.back(t.next(t.next(r)))));
+    }
+    pairs.push_back(t.vid(3)); pairs.push_back(t.vid(t.back(3)));
+    const int npairs = (int)pairs.size() / 2;
+    const int nbits = 16;
+    if (int rc = ensure(c->d_pairs, c->pairs_cap, pairs.size())) return rc;
+    if (int rc = ensure(c->d_bitcnt, c->bitcnt_cap, (size_t)nbits * c->Wl)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_pairs, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_site_counters(c, npairs, nbits)) return rc;
+
+    // site of each reported pattern: the reference walks site += aliaswgt[ptn] over the prefix
+    const int upper = c->sort_alignment ? c->n_inf : c->P;                // :3380-3381
+    std::vector<int64_t> ptn_site(upper > 0 ? upper : 1);
+    int64_t site = 0;
+    for (int i = 0; i < upper; i++) { ptn_site[i] = site < (int64_t)c->ref_words * 32 ? site : -1; site += c->weights[i]; }
+    if (int rc = ensure(c->d_ptn_site, c->ptn_site_cap, ptn_site.size())) return rc;
+    if (int rc = ensure(c->d_ptn, c->ptn_cap, ptn_site.size())) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_ptn_site, ptn_site.data(), ptn_site.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_gather_patterns(c, nbits, upper)) return rc;
+    if (upper > 0)
+        MPGPU_CUDA(cudaMemcpyAsync(ptn_pars, c->d_ptn, (size_t)upper * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    if (sum) {
+        int s = 0;
+        for (int i = 0; i < upper; i++) s += (int)ptn_pars[i] * c->weights[i];
+        *sum = s;
+    }
+    return 0;
+}
+
+int mpgpu_visit_order(mpgpu_ctx *c, int32_t *order)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    std::vector<int32_t> o;
+    visit_order(c->tree, o);
+    memcpy(order, o.data(), o.size() * sizeof(int32_t));
+    return 0;
+}
+
+int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, int mintrav, int maxtrav,
+                    int *n_cand, int *n_tasks)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (!order || first < 1 || count < 0 || first + count > 2 * c->n - 1) { set_error("bad visit range"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    if (int rc = build_scan_plan(c->tree, c->vlen, order, first, count, mintrav, maxtrav, c->plan)) return rc;
+    if (int rc = upload_plan(c)) return rc;
+    if (n_cand) *n_cand = c->plan.n_cand;
+    if (n_tasks) *n_tasks = (int)c->plan.tasks.size();
+    return 0;
+}
+
+int mpgpu_scan_launch(mpgpu_ctx *c, void **dev_counts)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    if (int rc = run_scan(c)) return rc;
+    if (dev_counts) *dev_counts = (void *)c->d_counts;
+    return 0;
+}
+
+int mpgpu_scan_finish(mpgpu_ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (!mp) { set_error("null argument"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    return finish_scan(c, visit_begin, mp, cand_ref, cand_prune, capacity);
+}
+
+int mpgpu_scan_visits(mpgpu_ctx *c, const int32_t *order, int first, int count, int mintrav, int maxtrav,
+                      int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune,
+                      int capacity, int *n_cand)
+{
+    if (c && c->shard_count != 1) { set_error("mpgpu_scan_visits is single-shard; use plan/launch/finish"); return 1; }
+    int nc = 0, nt = 0;
+    if (int rc = mpgpu_scan_plan(c, order, first, count, mintrav, maxtrav, &nc, &nt)) return rc;
+    if (n_cand) *n_cand = nc;
+    if (nc > capacity) { set_error("candidate capacity too small"); return 1; }
+    if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
+    return mpgpu_scan_finish(c, visit_begin, mp, cand_ref, cand_prune, capacity);
+}
+
+// pllOptimizeSprParsimony (sprparsimony.cpp:3244-3319) with the node loop's scoring batched on
+// the device.  Speculation: the candidates of the next K visits are scored against the current
+// tree; the host replays testInsertParsimony's bookkeeping (:2168-2176) and the node loop's
+// acceptance test (:3306-3314) strictly in order, and throws the rest of a batch away as soon
+// as a move is applied (the only event that changes any score).
+int mpgpu_optimize_spr(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
+                       mpgpu_rng_fn rng, void *rng_user, uint32_t *best, int64_t *n_insertions)
+{
+    if (!c || !back_node || !back_slot || !rng || !best) { set_error("null argument"); return 1; }
+    if (c->shard_count != 1) { set_error("mpgpu_optimize_spr is single-shard in this version"); return 1; }
+    if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
+    if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
+    const int n = c->n, nvisit = 2 * n - 2;
+    uint32_t score = 0;
+    if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
+    uint32_t bestParsimony = score;
+    uint32_t randomMP = bestParsimony, startMP = 0;
+    unsigned int bestIterationScoreHits = 1;
+    int64_t scored = 0;
+    std::vector<int32_t> order, vbegin, cref, cprune;
+    std::vector<uint32_t> mp;
+    do {
+        startMP = randomMP;
+        visit_order(c->tree, order);                              // nodeRectifierPars :3297
+        int i = 1;
+        int batch = 16;
+        while (i <= nvisit) {
+            int count = std::min(batch, nvisit - i + 1);
+            int nc = 0, nt = 0;
+            if (int rc = mpgpu_scan_plan(c, order.data(), i, count, mintrav, maxtrav, &nc, &nt)) return rc;
+            vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
+            if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
+            if (int rc = mpgpu_scan_finish(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
+            bool moved = false;
+            int v = 0;
+            for (; v < count && !moved; v++) {
+                int insertNode = 0, removeNode = 0;
+                unsigned long bestTreeScoreHits = 1;              // :3303
+                for (int j = vbegin[v]; j < vbegin[v + 1]; j++) {
+                    const uint32_t m = mp[j];
+                    scored++;
+                    if (m < bestParsimony) bestTreeScoreHits = 1;                 // :2168
+                    else if (m == bestParsimony) bestTreeScoreHits++;
+                    if (m < bestParsimony || (m == bestParsimony && rng(rng_user) <= 1.0 / bestTreeScoreHits)) {
+                        bestParsimony = m; insertNode = cref[j]; removeNode = cprune[j];
+                    }
+                }
+                if (bestParsimony == randomMP) bestIterationScoreHits++;          // :3306
+                if (bestParsimony < randomMP) bestIterationScoreHits = 1;
+                if ((bestParsimony < randomMP ||
+                     (bestParsimony == randomMP && rng(rng_user) <= 1.0 / bestIterationScoreHits)) &&
+                    removeNode && insertNode) {
+                    apply_spr_move(c->tree, removeNode, insertNode);              // :3312
+                    randomMP = bestParsimony;
+                    moved = true;
+                }
+            }
+            i += v;
+            if (moved) {
+                c->tree_set = true; c->lens_valid = false;
+                if (int rc = compute_views(c)) return rc;
+                compute_lengths(c);
+                batch = 16;
+            } else {
+                batch = std::min(batch * 2, nvisit);
+            }
+        }
+    } while (randomMP < startMP);
+    memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
+    memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
+    *best = startMP;
+    if (n_insertions) *n_insertions = scored;
+    return 0;
+}
+
+}  // extern "C"

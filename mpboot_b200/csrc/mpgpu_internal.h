@@ -1,0 +1,138 @@
+// Internal declarations shared by the CUDA kernels, the C-ABI layer and the host-side SPR
+// driver of libmpgpu.so.  Nothing here is part of the public boundary (include/mpgpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mpgpu.h"
+
+namespace mpgpu {
+
+// Device words per plane are padded to a multiple of this (one warp-iteration of 128-bit lanes).
+static const int kWordPad = 128;
+// One unit of work of the scan kernel: 32 words (1024 expanded sites) of every plane.
+static const int kChunkWords = 32;
+static const int kMaxStates = 32;
+static const int kMaxTrav = 12;          // deepest SPR radius the scan kernel's stack supports
+
+// ---- host mirror of the PLL node rings (pllrepo/src/pll.h:687-702) ---------------------
+struct HostTree {
+    int n = 0;                            // tips
+    std::vector<int32_t> bn, bs;          // ring tables, 3*(2n-1) entries
+    int back(int ref) const { return 3 * bn[ref] + bs[ref]; }
+    bool has_back(int ref) const { return bn[ref] != 0; }
+    bool is_tip(int ref) const { return ref / 3 <= n; }
+    int next(int ref) const {
+        int node = ref / 3;
+        if (node <= n) return ref;
+        return 3 * node + (ref % 3 + 1) % 3;
+    }
+    int vid(int ref) const {              // directed-view id of the subtree behind `ref`
+        int node = ref / 3;
+        return node <= n ? node - 1 : n + 3 * (node - n - 1) + ref % 3;
+    }
+    int num_views() const { return 4 * n - 6 + 0 * n; }
+    void hookup(int a, int b) {           // hookupDefault (pllrepo/src/utils.c:456)
+        bn[a] = b / 3; bs[a] = b % 3;
+        bn[b] = a / 3; bs[b] = a % 3;
+    }
+};
+
+// One Fitch combine dst = fitch(a, b) of the level schedule
+struct Triple { int32_t dst, a, b, pad; };
+
+// ---- scan program (built on the host, interpreted by k_spr_scan) ------------------------
+struct ScanOp {
+    int32_t src;        // >= 0: stack slot holding U of the node being expanded; < 0: ~view id
+    int32_t c1, c2;     // view ids of the two children (pointing at the expanded node)
+    int32_t out1, out2; // output slot of the insertion into the child's branch (-1: not scored)
+    int32_t dst1, dst2; // stack slot receiving the child's up-view (-1: child is not expanded)
+    int32_t pad;
+};
+struct ScanTask {
+    int32_t s_vid;      // pruned subtree
+    int32_t d1, d2;     // the two views that become neighbours when the node is removed
+    int32_t op_begin, op_end;
+    int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge)
+    int32_t pad0, pad1;
+};
+
+struct ScanPlan {
+    std::vector<ScanOp> ops;
+    std::vector<ScanTask> tasks;
+    std::vector<int32_t> visit_begin;     // count+1
+    std::vector<int32_t> cand_ref, cand_prune, cand_task;
+    std::vector<uint32_t> task_const;     // len(S)+len(D1)+len(D2) per task
+    int n_cand = 0;
+    int max_slot = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int shard_rank = 0, shard_count = 1;
+    int64_t launches = 0;
+
+    // alignment
+    int n = 0, P = 0, datatype = 0, S = 0, sort_alignment = 1;
+    std::vector<int32_t> weights;
+    std::vector<uint8_t> informative;
+    int n_inf = 0;
+    int64_t n_sites = 0;
+    int ref_words = 0;                    // reference parsimonyLength (padded to 8)
+    int glob_words = 0;                   // padded words per plane over all shards
+    int Wl = 0;                           // words per plane of this shard
+    int64_t w0 = 0;                       // first global word of this shard
+    uint8_t *d_codes = nullptr;           // [n][P]
+    int64_t *d_site_start = nullptr;      // [n_inf+1] first expanded site of informative pattern k
+    int32_t *d_inf_ptn = nullptr;         // [n_inf] pattern index of informative pattern k
+
+    // views
+    uint32_t *d_views = nullptr;          // [4n-6][S][Wl]
+    size_t view_stride = 0;               // S*Wl
+    uint32_t *d_vcount = nullptr;         // [4n-6] mismatch count of each view (this shard)
+    std::vector<uint32_t> vcount;         // host copy (all-reduced when sharded)
+    std::vector<uint32_t> vlen;           // subtree length of each view
+    bool tree_set = false, lens_valid = false;
+    HostTree tree;
+    std::vector<std::vector<Triple>> levels;
+    Triple *d_triples = nullptr; size_t triples_cap = 0;
+    uint32_t *d_scalar = nullptr;         // small scratch for scalar results
+
+    // scan
+    ScanPlan plan;
+    ScanOp *d_ops = nullptr; size_t ops_cap = 0;
+    ScanTask *d_tasks = nullptr; size_t tasks_cap = 0;
+    int32_t *d_counts = nullptr; size_t counts_cap = 0;
+    std::vector<int32_t> h_counts;
+
+    // pattern scores
+    uint32_t *d_bitcnt = nullptr; size_t bitcnt_cap = 0;   // bit-sliced per-site counters
+    int32_t *d_pairs = nullptr; size_t pairs_cap = 0;
+    uint16_t *d_ptn = nullptr; size_t ptn_cap = 0;
+    int64_t *d_ptn_site = nullptr; size_t ptn_site_cap = 0;
+};
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define MPGPU_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return ::mpgpu::cuda_fail(e__, #expr); } while (0)
+
+// ---- kernel launchers (fitch_kernels.cu) -------------------------------------------------
+int launch_compress(Ctx *c);
+int launch_level(Ctx *c, const Triple *d_triples, int ntriples);
+int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out);
+int launch_scan(Ctx *c, int ntasks, int nslots);
+int launch_site_counters(Ctx *c, int npairs, int nbits);
+int launch_gather_patterns(Ctx *c, int nbits, int count);
+const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);
+
+// ---- host SPR logic (spr_host.cpp) ---------------------------------------------------------
+void visit_order(const HostTree &t, std::vector<int32_t> &order);
+int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
+                    int first, int count, int mintrav, int maxtrav, ScanPlan &plan);
+void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);
+
+}  // namespace mpgpu

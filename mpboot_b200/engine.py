@@ -1,0 +1,222 @@
+"""ctypes binding of the C-ABI (include/mpgpu.h) -- the same calls the reference-side shim
+makes from sprparsimony.cpp / iqtree.cpp.  Used by tests/ and bench.py.
+
+There is no CPU fallback: importing this module needs the built library, and creating an
+engine needs a CUDA device.  Nothing here touches oracle/."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libmpgpu.so")
+
+RNG_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)
+
+_lib = None
+
+
+class MpGpuError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libmpgpu.so (built in-tree by __graft_entry__.build() / mpboot_b200/csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpGpuError("libmpgpu.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                         "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
+    L.mpgpu_last_error.restype = C.c_char_p
+    L.mpgpu_device_count.restype = i32
+    L.mpgpu_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32]
+    L.mpgpu_destroy.argtypes = [vp]
+    L.mpgpu_stream.restype = vp
+    L.mpgpu_stream.argtypes = [vp]
+    L.mpgpu_synchronize.argtypes = [vp]
+    L.mpgpu_launch_count.restype = i64
+    L.mpgpu_launch_count.argtypes = [vp]
+    L.mpgpu_load_alignment.argtypes = [vp, i32, i32, i32, vp, vp, i32]
+    L.mpgpu_set_weights.argtypes = [vp, vp]
+    L.mpgpu_get_layout.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.mpgpu_get_tip_planes.argtypes = [vp, i32, vp]
+    L.mpgpu_set_tree.argtypes = [vp, vp, vp]
+    L.mpgpu_get_view_counts_partial.argtypes = [vp, vp]
+    L.mpgpu_set_view_counts.argtypes = [vp, vp]
+    L.mpgpu_view_length.argtypes = [vp, i32, i32, vp]
+    L.mpgpu_get_view_planes.argtypes = [vp, i32, i32, vp]
+    L.mpgpu_tree_score.argtypes = [vp, vp]
+    L.mpgpu_edge_mismatch_partial.argtypes = [vp, i32, i32, vp]
+    L.mpgpu_pattern_parsimony.argtypes = [vp, vp, vp]
+    L.mpgpu_visit_order.argtypes = [vp, vp]
+    L.mpgpu_scan_visits.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.mpgpu_scan_plan.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.mpgpu_scan_launch.argtypes = [vp, vp]
+    L.mpgpu_scan_finish.argtypes = [vp, vp, vp, vp, vp, i32]
+    L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().mpgpu_device_count()
+
+
+class Engine:
+    """One mpgpu context (one GPU, one word-slice of the alignment)."""
+
+    def __init__(self, device=0, stream=None, shard_rank=0, shard_count=1):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.mpgpu_create(C.byref(h), device, stream, shard_rank, shard_count)
+        if rc:
+            raise MpGpuError(self.L.mpgpu_last_error().decode())
+        self.h = h
+        self.n = self.P = 0
+        self.shard_count = shard_count
+
+    def _ck(self, rc):
+        if rc:
+            raise MpGpuError(self.L.mpgpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mpgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- R1
+    def load_alignment(self, codes, weights, datatype, sort_alignment=True):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        weights = np.ascontiguousarray(weights, dtype=np.int32)
+        self.n, self.P = codes.shape
+        self._ck(self.L.mpgpu_load_alignment(self.h, self.n, self.P, datatype, _p(codes), _p(weights), int(sort_alignment)))
+        lay = self.layout()
+        self.S, self.ref_words, self.shard_words, self.n_inf, self.n_sites = lay
+        return lay
+
+    def set_weights(self, weights):
+        weights = np.ascontiguousarray(weights, dtype=np.int32)
+        self._ck(self.L.mpgpu_set_weights(self.h, _p(weights)))
+        self.S, self.ref_words, self.shard_words, self.n_inf, self.n_sites = self.layout()
+
+    def layout(self):
+        s, rw, sw, ni = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ns = C.c_int64()
+        self._ck(self.L.mpgpu_get_layout(self.h, C.byref(s), C.byref(rw), C.byref(sw), C.byref(ni), C.byref(ns)))
+        return s.value, rw.value, sw.value, ni.value, ns.value
+
+    def tip_planes(self, tip):
+        out = np.zeros((self.S, self.ref_words), dtype=np.uint32)
+        self._ck(self.L.mpgpu_get_tip_planes(self.h, tip, _p(out)))
+        return out
+
+    # -- R2/R3/R4
+    def set_tree(self, bn, bs):
+        bn = np.ascontiguousarray(bn, dtype=np.int32); bs = np.ascontiguousarray(bs, dtype=np.int32)
+        self._ck(self.L.mpgpu_set_tree(self.h, _p(bn), _p(bs)))
+
+    def view_counts_partial(self):
+        out = np.zeros(4 * self.n - 6, dtype=np.uint32)
+        self._ck(self.L.mpgpu_get_view_counts_partial(self.h, _p(out)))
+        return out
+
+    def set_view_counts(self, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        self._ck(self.L.mpgpu_set_view_counts(self.h, _p(counts)))
+
+    def view_length(self, node, slot):
+        v = C.c_uint32()
+        self._ck(self.L.mpgpu_view_length(self.h, node, slot, C.byref(v)))
+        return v.value
+
+    def view_planes(self, node, slot):
+        out = np.zeros((self.S, self.ref_words), dtype=np.uint32)
+        self._ck(self.L.mpgpu_get_view_planes(self.h, node, slot, _p(out)))
+        return out
+
+    def tree_score(self):
+        v = C.c_uint32()
+        self._ck(self.L.mpgpu_tree_score(self.h, C.byref(v)))
+        return v.value
+
+    def edge_mismatch_partial(self, node, slot):
+        v = C.c_uint32()
+        self._ck(self.L.mpgpu_edge_mismatch_partial(self.h, node, slot, C.byref(v)))
+        return v.value
+
+    # -- R5
+    def pattern_parsimony(self):
+        upper = self.n_inf if getattr(self, "_sort", True) else self.P
+        out = np.zeros(max(self.P, 1) + 16, dtype=np.uint16)
+        s = C.c_int32()
+        self._ck(self.L.mpgpu_pattern_parsimony(self.h, _p(out), C.byref(s)))
+        return out, s.value
+
+    # -- R6
+    def visit_order(self):
+        out = np.zeros(2 * self.n - 1, dtype=np.int32)
+        self._ck(self.L.mpgpu_visit_order(self.h, _p(out)))
+        return out
+
+    def scan_visits(self, order, first, count, mintrav=1, maxtrav=6, capacity=None):
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        if capacity is None:
+            capacity = count * (8 << min(maxtrav, 10)) + 16
+        vb = np.zeros(count + 1, dtype=np.int32)
+        mp = np.zeros(capacity, dtype=np.uint32)
+        cr = np.zeros(capacity, dtype=np.int32)
+        cp = np.zeros(capacity, dtype=np.int32)
+        nc = C.c_int()
+        self._ck(self.L.mpgpu_scan_visits(self.h, _p(order), first, count, mintrav, maxtrav,
+                                          _p(vb), _p(mp), _p(cr), _p(cp), capacity, C.byref(nc)))
+        k = nc.value
+        return vb, mp[:k], cr[:k], cp[:k]
+
+    def scan_plan(self, order, first, count, mintrav=1, maxtrav=6):
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        nc, nt = C.c_int(), C.c_int()
+        self._ck(self.L.mpgpu_scan_plan(self.h, _p(order), first, count, mintrav, maxtrav, C.byref(nc), C.byref(nt)))
+        return nc.value, nt.value
+
+    def scan_launch(self):
+        ptr = C.c_void_p()
+        self._ck(self.L.mpgpu_scan_launch(self.h, C.byref(ptr)))
+        return ptr.value
+
+    def scan_finish(self, n_cand, count):
+        vb = np.zeros(count + 1, dtype=np.int32)
+        mp = np.zeros(n_cand + 1, dtype=np.uint32)
+        cr = np.zeros(n_cand + 1, dtype=np.int32)
+        cp = np.zeros(n_cand + 1, dtype=np.int32)
+        self._ck(self.L.mpgpu_scan_finish(self.h, _p(vb), _p(mp), _p(cr), _p(cp), n_cand + 1))
+        return vb, mp[:n_cand], cr[:n_cand], cp[:n_cand]
+
+    def optimize_spr(self, bn, bs, rng_fn_ptr, mintrav=1, maxtrav=6):
+        """pllOptimizeSprParsimony.  rng_fn_ptr: address of a `double f(void*)` (the host's
+        random_double).  Returns (startMP, back_node, back_slot, insertions scored)."""
+        bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
+        best = C.c_uint32(); nins = C.c_int64()
+        self._ck(self.L.mpgpu_optimize_spr(self.h, _p(bn), _p(bs), mintrav, maxtrav,
+                                           C.c_void_p(rng_fn_ptr), None, C.byref(best), C.byref(nins)))
+        return best.value, bn, bs, nins.value
+
+    def synchronize(self):
+        self._ck(self.L.mpgpu_synchronize(self.h))
+
+    def launch_count(self):
+        return self.L.mpgpu_launch_count(self.h)
+
+    def stream(self):
+        return self.L.mpgpu_stream(self.h)

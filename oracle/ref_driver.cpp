@@ -1,0 +1,468 @@
+/* TEST INFRASTRUCTURE -- not product code.  Built only into oracle/_ref/libmpref.so.
+ *
+ * Drives the UNMODIFIED reference parsimony engine: this translation unit textually
+ * includes /root/reference/sprparsimony.cpp (compiled where it lies, never copied), which
+ * gives the driver access to its file-static kernels (newviewParsimonyIterativeFast :554,
+ * evaluateParsimonyIterativeFast :965, rearrangeParsimony :2259, testInsertParsimony :2106,
+ * compressDNA :2828 ...) as well as the exported entry points (pllOptimizeSprParsimony
+ * :3244, _pllComputeRandomizedStepwiseAdditionParsimonyTree :3224,
+ * pllComputePatternParsimony :3363).  The PLL helpers it needs (hookupDefault, randum,
+ * getBitVector, pllBaseSubstitute, mask32 ...) come from /root/reference/pllrepo/src/utils.c,
+ * compiled separately by oracle/Makefile.
+ *
+ * What is NOT the reference here (and therefore stated explicitly):
+ *   - class IQTree is the stand-in of oracle/shim/mp_iqtree_shim.h; its saveCurrentTree()
+ *     forwards to a recorder instead of running iqtree.cpp:3271.
+ *   - random_double() (tools.cpp:3362, SPRNG) is replaced by a splitmix64 stream shared
+ *     with the product tests: parity is about *which* draws are made in *which* order.
+ *   - the REPS loop (iqtree.cpp:3411-3449) is re-typed below on the reference's own
+ *     vectorclass Vec16us so the 16-bit wrap semantics are the library's, not ours.
+ */
+#include "mp_iqtree_shim.h"
+#include "sprparsimony.cpp"          /* -I /root/reference */
+
+#include <stdint.h>
+#include <vector>
+
+extern "C" void pllBaseSubstitute(pllInstance *tr, partitionList *partitions);   /* utils.c:2526 */
+
+/* Sankoff-only helper (parstree.cpp:606) referenced from the -cost branch of
+ * _allocateParsimonyDataStructures; never reached because pllCostMatrix stays NULL. */
+int ParsTree::findMstScore(int) { fprintf(stderr, "mpref: Sankoff path not built\n"); abort(); return 0; }
+
+/* ---- globals the engine expects from iqtree.cpp / tools.cpp ------------------------- */
+Params *globalParam = NULL;                 /* iqtree.cpp:601 */
+parsimonyNumber *pllCostMatrix = NULL;      /* iqtree.cpp (Sankoff; unused: Fitch only) */
+int pllCostNstates = 0;
+parsimonyNumber *vectorCostMatrix = NULL;
+int pllRepsSegments = -1;
+int *pllSegmentUpper = NULL;
+
+static uint64_t g_rng_state = 0x9E3779B97F4A7C15ULL;
+static uint64_t g_rng_draws = 0;
+
+#define MPREF_API extern "C" __attribute__((visibility("default")))
+
+/* splitmix64 -> [0,1) ; the same generator is exported by the C port oracle */
+MPREF_API double mpref_random_double(void *unused)
+{
+    (void)unused;
+    uint64_t z = (g_rng_state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    g_rng_draws++;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+double random_double() { return mpref_random_double(NULL); }
+MPREF_API void mpref_seed_rng(uint64_t seed) { g_rng_state = seed; g_rng_draws = 0; }
+MPREF_API uint64_t mpref_rng_draws(void) { return g_rng_draws; }
+
+void outError(const char *error, bool quit) { fprintf(stderr, "mpref outError: %s\n", error); if (quit) exit(2); }
+
+/* ---- handle ------------------------------------------------------------------------- */
+struct mpref {
+    int n, P, datatype, states;
+    pllInstance *tr;
+    partitionList *pr;
+    pInfo *pinfo;
+    node *pool;
+    std::vector<nodeptr> base;            /* base[i] = ring slot 0 of node i (1..2n-2) */
+    std::vector<unsigned char> ybuf;
+    IQTree iq;
+    Alignment aln;
+    Params params;
+    /* recorder for the saveCurrentTree up-call */
+    std::vector<int> saved_mp;
+    std::vector<unsigned short> saved_ptn;   /* P per call when record_ptn */
+    int record_ptn;
+    bool allocated;
+};
+
+static void save_hook(void *user, double cur_logl)
+{
+    mpref *h = (mpref *)user;
+    h->saved_mp.push_back((int)(-cur_logl));
+    if (h->record_ptn) {
+        size_t off = h->saved_ptn.size();
+        h->saved_ptn.resize(off + h->P, 0);
+        int sum = 0;
+        /* what IQTree::saveCurrentTree does at iqtree.cpp:3365 */
+        pllComputePatternParsimony(h->tr, h->pr, &h->saved_ptn[off], &sum);
+    }
+}
+
+static int states_of(int datatype)
+{
+    switch (datatype) {
+    case PLL_BINARY_DATA: return 2;
+    case PLL_DNA_DATA:    return 4;
+    case PLL_AA_DATA:     return 20;
+    case PLL_GENERIC_32:  return 32;
+    default: return -1;
+    }
+}
+
+/* chars: [n][P] raw alignment characters (ASCII), mapped with the reference's own tables
+ * through pllBaseSubstitute (utils.c:2526). weights: pattern frequencies (tr->aliaswgt). */
+MPREF_API mpref *mpref_create(int n, int P, int datatype, const unsigned char *chars, const int *weights,
+                             int sort_alignment, int n_informative)
+{
+    int S = states_of(datatype);
+    if (S < 0 || n < 4 || P < 1) return NULL;
+    mpref *h = new mpref();
+    h->n = n; h->P = P; h->datatype = datatype; h->states = S;
+    h->record_ptn = 0; h->allocated = false;
+
+    pllInstance *tr = (pllInstance *)calloc(1, sizeof(pllInstance));
+    partitionList *pr = (partitionList *)calloc(1, sizeof(partitionList));
+    pInfo *pi = (pInfo *)calloc(1, sizeof(pInfo));
+    h->tr = tr; h->pr = pr; h->pinfo = pi;
+
+    pr->numberOfPartitions = 1;
+    pr->perGeneBranchLengths = PLL_FALSE;
+    pr->partitionData = (pInfo **)calloc(1, sizeof(pInfo *));
+    pr->partitionData[0] = pi;
+    pi->dataType = datatype;
+    pi->states = S;
+    pi->lower = 0; pi->upper = P; pi->width = P;
+    pi->parsVect = NULL; pi->perSitePartialPars = NULL;
+    pi->informativePtnWgt = NULL; pi->informativePtnScore = NULL;
+
+    tr->mxtips = n;
+    tr->originalCrunchedLength = P;
+    tr->aliaswgt = (int *)malloc(sizeof(int) * P);
+    memcpy(tr->aliaswgt, weights, sizeof(int) * P);
+    h->ybuf.assign(chars, chars + (size_t)n * P);
+    tr->yVector = (unsigned char **)calloc(n + 1, sizeof(unsigned char *));
+    for (int i = 1; i <= n; i++) tr->yVector[i] = &h->ybuf[(size_t)(i - 1) * P];
+    pllBaseSubstitute(tr, pr);
+
+    /* node rings laid out as pllTreeInitDefaults does (utils.c:1963-2041) */
+    int inner = n - 1;
+    h->pool = (node *)calloc(n + 3 * inner, sizeof(node));
+    tr->nodep = (nodeptr *)calloc(2 * n, sizeof(nodeptr));
+    tr->constraintVector = (int *)calloc(2 * n, sizeof(int));
+    h->base.assign(2 * n, (nodeptr)NULL);
+    node *p0 = h->pool;
+    for (int i = 1; i <= n; i++) {
+        node *p = p0++;
+        p->number = i; p->next = p; p->back = NULL;
+        tr->nodep[i] = p; h->base[i] = p;
+    }
+    for (int i = n + 1; i <= n + inner; i++) {
+        node *a = p0++, *b = p0++, *c = p0++;      /* slot 0, 1, 2 */
+        a->number = b->number = c->number = i;
+        a->next = b; b->next = c; c->next = a;
+        a->xPars = 1; a->x = 1; a->xBips = 1;
+        tr->nodep[i] = a; h->base[i] = a;
+    }
+    tr->start = tr->nodep[1];
+    tr->ntips = n;
+    tr->nextnode = 2 * n - 1;
+    tr->grouped = PLL_FALSE; tr->constrained = PLL_FALSE;
+    tr->parsimonyScore = NULL; tr->ti = NULL;
+    tr->bestParsimony = UINT_MAX;
+
+    /* Params: only the fields the engine reads */
+    memset((void *)&h->params, 0, sizeof(Params));
+    h->params.gbo_replicates = 0;
+    h->params.ratchet_iter = -1;
+    h->params.sort_alignment = sort_alignment ? true : false;
+    h->params.sankoff_short_int = true;
+    globalParam = &h->params;
+
+    h->aln.resize(P);
+    for (int i = 0; i < P; i++) { h->aln[i].frequency = weights[i]; h->aln[i].is_const = false; h->aln[i].ras_pars_score = 0; }
+    h->aln.n_informative_patterns = n_informative;
+    h->iq.aln = &h->aln; h->iq.pllInst = tr; h->iq.pllPartitions = pr;
+    h->iq.hook = save_hook; h->iq.hook_user = h;
+    iqtree = &h->iq;
+    first_call = true;
+    return h;
+}
+
+static void make_current(mpref *h) { globalParam = &h->params; iqtree = &h->iq; }
+
+MPREF_API void mpref_destroy(mpref *h)
+{
+    if (!h) return;
+    make_current(h);
+    if (h->allocated) _pllFreeParsimonyDataStructures(h->tr, h->pr);
+    free(h->tr->aliaswgt); free(h->tr->yVector); free(h->tr->nodep); free(h->tr->constraintVector);
+    free(h->pool); free(h->pr->partitionData); free(h->pinfo); free(h->pr); free(h->tr);
+    if (globalParam == &h->params) globalParam = NULL;
+    if (iqtree == &h->iq) iqtree = NULL;
+    delete h;
+}
+
+/* PLL code of every input byte for a data type (pins the char->code tables utils.c:98-157) */
+MPREF_API int mpref_char_map(int datatype, unsigned char out[256])
+{
+    if (states_of(datatype) < 0) return -1;
+    pllInstance tr; partitionList pr; pInfo pi; pInfo *pip = &pi;
+    memset(&tr, 0, sizeof tr); memset(&pr, 0, sizeof pr); memset(&pi, 0, sizeof pi);
+    unsigned char buf[256]; unsigned char *yv[2] = {NULL, buf};
+    for (int i = 0; i < 256; i++) buf[i] = (unsigned char)i;
+    tr.mxtips = 1; tr.yVector = yv;
+    pr.numberOfPartitions = 1; pr.partitionData = &pip;
+    pi.dataType = datatype; pi.lower = 0; pi.upper = 256;
+    pllBaseSubstitute(&tr, &pr);
+    memcpy(out, buf, 256);
+    return 0;
+}
+
+/* PLL state-set bit mask of every code (globalVariables.h:60-104) */
+MPREF_API int mpref_bitvector(int datatype, unsigned int *out, int ncodes)
+{
+    const unsigned int *bv = getBitVector(datatype);
+    for (int i = 0; i < ncodes; i++) out[i] = bv[i];
+    return getUndetermined(datatype);
+}
+
+static nodeptr slot_ptr(mpref *h, int number, int slot)
+{
+    nodeptr p = h->base[number];
+    for (int s = 0; s < slot; s++) p = p->next;
+    return p;
+}
+static int slot_of(mpref *h, nodeptr p)
+{
+    nodeptr b = h->base[p->number];
+    if (p == b) return 0;
+    if (p == b->next) return 1;
+    return 2;
+}
+
+/* ring tables: index (node*3 + slot), node in 1..2n-2; tips use slot 0 only.
+ * back_node = 0 means NULL. Resets orientation flags like _allocateParsimonyDataStructures. */
+MPREF_API void mpref_set_ring(mpref *h, const int *back_node, const int *back_slot)
+{
+    int n = h->n;
+    for (int i = 1; i <= 2 * n - 2; i++) {
+        int ns = (i <= n) ? 1 : 3;
+        for (int s = 0; s < ns; s++) {
+            nodeptr p = slot_ptr(h, i, s);
+            int bn = back_node[i * 3 + s];
+            p->back = bn ? slot_ptr(h, bn, back_slot[i * 3 + s]) : (nodeptr)NULL;
+            p->z[0] = PLL_DEFAULTZ;
+        }
+    }
+    for (int i = 1; i <= 2 * n - 2; i++) h->tr->nodep[i] = h->base[i];
+    for (int i = n + 1; i <= 2 * n - 2; i++) {
+        nodeptr p = h->base[i];
+        p->xPars = 1; p->next->xPars = 0; p->next->next->xPars = 0;
+    }
+    h->tr->start = h->tr->nodep[1];
+    h->tr->ntips = n;
+    h->tr->nextnode = 2 * n - 1;
+}
+
+MPREF_API void mpref_get_ring(mpref *h, int *back_node, int *back_slot)
+{
+    int n = h->n;
+    for (int i = 1; i <= 2 * n - 2; i++) {
+        int ns = (i <= n) ? 1 : 3;
+        for (int s = 0; s < 3; s++) { back_node[i * 3 + s] = 0; back_slot[i * 3 + s] = 0; }
+        for (int s = 0; s < ns; s++) {
+            nodeptr p = slot_ptr(h, i, s);
+            if (p->back) { back_node[i * 3 + s] = p->back->number; back_slot[i * 3 + s] = slot_of(h, p->back); }
+        }
+    }
+}
+
+/* current tr->nodep[] visit order as (node, slot) pairs, index 1..2n-2 */
+MPREF_API void mpref_get_nodep(mpref *h, int *node_out, int *slot_out)
+{
+    for (int i = 1; i <= 2 * h->n - 2; i++) {
+        node_out[i] = h->tr->nodep[i]->number;
+        slot_out[i] = slot_of(h, h->tr->nodep[i]);
+    }
+}
+
+MPREF_API void mpref_set_weights(mpref *h, const int *weights)
+{
+    memcpy(h->tr->aliaswgt, weights, sizeof(int) * h->P);
+    for (int i = 0; i < h->P; i++) h->aln[i].frequency = weights[i];
+}
+
+/* _allocateParsimonyDataStructures (sprparsimony.cpp:3032): returns parsimonyLength W */
+MPREF_API int mpref_allocate(mpref *h, int perSiteScores)
+{
+    make_current(h);
+    if (h->allocated) _pllFreeParsimonyDataStructures(h->tr, h->pr);
+    _allocateParsimonyDataStructures(h->tr, h->pr, perSiteScores);
+    h->allocated = true;
+    h->params.gbo_replicates = perSiteScores ? 1000 : 0;
+    return (int)h->pinfo->parsimonyLength;
+}
+
+MPREF_API int mpref_num_informative(mpref *h) { return h->pinfo->numInformativePatterns; }
+
+MPREF_API void mpref_get_parsvect(mpref *h, int node, unsigned int *out)
+{
+    size_t W = h->pinfo->parsimonyLength, S = h->states;
+    memcpy(out, &h->pinfo->parsVect[W * S * (size_t)node], W * S * sizeof(unsigned int));
+}
+MPREF_API unsigned int mpref_node_score(mpref *h, int node) { return h->tr->parsimonyScore[node]; }
+
+/* nodeRectifierPars + evaluateParsimony(start, full) as pllOptimizeSprParsimony :3275-3277 */
+MPREF_API unsigned int mpref_evaluate_full(mpref *h, int perSiteScores)
+{
+    make_current(h);
+    nodeRectifierPars(h->tr);
+    h->tr->bestParsimony = UINT_MAX;
+    return evaluateParsimony(h->tr, h->pr, h->tr->start, PLL_TRUE, perSiteScores);
+}
+
+/* evaluateParsimony at an arbitrary ring slot, lazily (full = FALSE) */
+MPREF_API unsigned int mpref_evaluate_at(mpref *h, int node, int slot, int full, int perSiteScores)
+{
+    make_current(h);
+    return evaluateParsimony(h->tr, h->pr, slot_ptr(h, node, slot), full ? PLL_TRUE : PLL_FALSE, perSiteScores);
+}
+
+MPREF_API void mpref_pattern_parsimony(mpref *h, unsigned short *out, int *sum)
+{
+    make_current(h);
+    pllComputePatternParsimony(h->tr, h->pr, out, sum);
+}
+
+MPREF_API int mpref_min_pars_pattern(mpref *h, int site)
+{
+    return pllCalcMinParsScorePattern(h->tr, h->datatype, site);
+}
+
+MPREF_API void mpref_record(mpref *h, int record_ptn) { h->record_ptn = record_ptn; h->saved_mp.clear(); h->saved_ptn.clear(); }
+MPREF_API int mpref_saved_count(mpref *h) { return (int)h->saved_mp.size(); }
+MPREF_API void mpref_saved_mp(mpref *h, int *out) { if (!h->saved_mp.empty()) memcpy(out, &h->saved_mp[0], h->saved_mp.size() * sizeof(int)); }
+MPREF_API void mpref_saved_ptn(mpref *h, unsigned short *out) { if (!h->saved_ptn.empty()) memcpy(out, &h->saved_ptn[0], h->saved_ptn.size() * sizeof(unsigned short)); }
+
+/* One node visit of the SPR sweep (sprparsimony.cpp:3301-3305) on visit index i of the
+ * current tr->nodep[] order.  best_in: value of tr->bestParsimony on entry.
+ * out[0]=bestParsimony after, out[1]=removeNode number (0 none), out[2]=its slot,
+ * out[3]=insertNode number, out[4]=its slot, out[5]=bestTreeScoreHits.
+ * With perSiteScores=1 every scored insertion is reported through the recorder. */
+MPREF_API int mpref_rearrange(mpref *h, int i, int mintrav, int maxtrav, int perSiteScores,
+                             unsigned int best_in, unsigned int *out)
+{
+    make_current(h);
+    pllInstance *tr = h->tr;
+    tr->insertNode = NULL; tr->removeNode = NULL;
+    bestTreeScoreHits = 1;
+    tr->bestParsimony = best_in;
+    tr->ntips = tr->mxtips;
+    int rc = rearrangeParsimony(tr, h->pr, tr->nodep[i], mintrav, maxtrav, PLL_FALSE, perSiteScores);
+    out[0] = tr->bestParsimony;
+    out[1] = tr->removeNode ? tr->removeNode->number : 0;
+    out[2] = tr->removeNode ? slot_of(h, tr->removeNode) : 0;
+    out[3] = tr->insertNode ? tr->insertNode->number : 0;
+    out[4] = tr->insertNode ? slot_of(h, tr->insertNode) : 0;
+    out[5] = (unsigned int)bestTreeScoreHits;
+    return rc;
+}
+
+/* restoreTreeRearrangeParsimony (sprparsimony.cpp:2379): apply the recorded move */
+MPREF_API void mpref_apply_move(mpref *h, int perSiteScores)
+{
+    make_current(h);
+    restoreTreeRearrangeParsimony(h->tr, h->pr, perSiteScores);
+}
+MPREF_API void mpref_node_rectifier(mpref *h) { nodeRectifierPars(h->tr); }
+
+/* The real search: pllOptimizeSprParsimony (sprparsimony.cpp:3244).
+ * cur_score must equal the tree's score (assert :3279). Returns startMP. */
+MPREF_API int mpref_optimize_spr(mpref *h, int mintrav, int maxtrav, int bb, int ratchet_realloc)
+{
+    make_current(h);
+    h->params.gbo_replicates = bb ? 1000 : 0;
+    h->params.ratchet_iter = ratchet_realloc ? 1 : -1;
+    h->iq.on_ratchet_hclimb1 = ratchet_realloc ? true : false;
+    h->iq.on_ratchet_hclimb2 = false;
+    h->iq.on_opt_btree = false;
+    if (!h->allocated || ratchet_realloc) {
+        first_call = true;
+    } else {
+        first_call = false;
+    }
+    /* the assert at :3279 needs iqtree->curScore; compute it with the same engine first */
+    if (first_call) {
+        if (h->allocated) { _pllFreeParsimonyDataStructures(h->tr, h->pr); h->allocated = false; }
+        _allocateParsimonyDataStructures(h->tr, h->pr, bb);
+        h->allocated = true;
+        first_call = false;
+        h->iq.on_ratchet_hclimb1 = false;
+        h->params.ratchet_iter = -1;
+    }
+    nodeRectifierPars(h->tr);
+    h->tr->bestParsimony = UINT_MAX;
+    size_t keep = h->saved_mp.size(), keepp = h->saved_ptn.size();
+    unsigned int s0 = evaluateParsimony(h->tr, h->pr, h->tr->start, PLL_TRUE, bb);
+    h->saved_mp.resize(keep); h->saved_ptn.resize(keepp);
+    h->iq.curScore = -(double)s0;
+    return pllOptimizeSprParsimony(h->tr, h->pr, mintrav, maxtrav, &h->iq);
+}
+
+/* _pllComputeRandomizedStepwiseAdditionParsimonyTree (sprparsimony.cpp:3224) */
+MPREF_API unsigned int mpref_ras(mpref *h, long seed, int sprDist)
+{
+    make_current(h);
+    if (h->allocated) { _pllFreeParsimonyDataStructures(h->tr, h->pr); h->allocated = false; }
+    for (int i = 1; i <= 2 * h->n - 2; i++) h->tr->nodep[i] = h->base[i];
+    for (int i = 1; i <= 2 * h->n - 2; i++) {
+        nodeptr p = h->base[i];
+        int ns = (i <= h->n) ? 1 : 3;
+        for (int s = 0; s < ns; s++, p = p->next) p->back = NULL;
+    }
+    h->tr->randomNumberSeed = seed;
+    h->params.gbo_replicates = 0;
+    _pllComputeRandomizedStepwiseAdditionParsimonyTree(h->tr, h->pr, sprDist, &h->iq);
+    return h->tr->bestParsimony;
+}
+
+/* ---- REPS (iqtree.cpp:3411-3449) on the reference's own Vec16us ------------------- */
+/* pars, w: u16 arrays padded to a multiple of 16 (zeros) and 32-byte aligned by the caller.
+ * res[b] = sum over segments of horizontal_add(sum_lanes u16(pars*w)) */
+MPREF_API void mpref_reps(const unsigned short *pars, const unsigned short *boot, int B, int stride,
+                         const int *segment_upper, int nseg, int *res_out)
+{
+    for (int b = 0; b < B; b++) {
+        const unsigned short *w = boot + (size_t)b * stride;
+        int ptn = 0, res = 0;
+        Vec16us vc_rell = 0;
+        for (int seg = 0; seg < nseg; seg++) {
+            for (; ptn < segment_upper[seg]; ptn += 16)
+                vc_rell = Vec16us().load(&pars[ptn]) * Vec16us().load(&w[ptn]) + vc_rell;
+            res += horizontal_add(vc_rell);
+            vc_rell = 0;
+        }
+        res_out[b] = res;
+    }
+}
+
+/* ---- timing helper for bench.py --impl reference ----------------------------------- */
+/* Runs the SPR sweep body (rearrangeParsimony over every node of the current tree, moves
+ * NOT applied) `reps` times and returns the number of insertions scored. */
+static unsigned long g_insert_counter = 0;
+MPREF_API unsigned long mpref_sweep_count_insertions(mpref *h, int mintrav, int maxtrav, int perSiteScores, int reps)
+{
+    make_current(h);
+    pllInstance *tr = h->tr;
+    unsigned long total = 0;
+    for (int r = 0; r < reps; r++) {
+        nodeRectifierPars(tr);
+        tr->bestParsimony = UINT_MAX;
+        unsigned int s0 = evaluateParsimony(tr, h->pr, tr->start, PLL_TRUE, perSiteScores);
+        tr->ntips = tr->mxtips;
+        size_t before = h->saved_mp.size();
+        for (int i = 1; i <= 2 * h->n - 2; i++) {
+            tr->insertNode = NULL; tr->removeNode = NULL;
+            bestTreeScoreHits = 1;
+            tr->bestParsimony = s0;
+            rearrangeParsimony(tr, h->pr, tr->nodep[i], mintrav, maxtrav, PLL_FALSE, perSiteScores);
+        }
+        total += (unsigned long)(h->saved_mp.size() - before);
+    }
+    (void)g_insert_counter;
+    return total;
+}

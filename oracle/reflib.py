@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/_ref/libmpref.so (the reference's own
+parsimony engine, see oracle/ref_driver.cpp).  Only tests/, the golden-vector generator and
+bench.py's reference/cpu_baseline legs may import this module."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PATH = os.path.join(HERE, "_ref", "libmpref.so")
+
+
+def available():
+    return os.path.exists(PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(PATH)
+        L.mpref_create.restype = C.c_void_p
+        L.mpref_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.mpref_destroy.argtypes = [C.c_void_p]
+        L.mpref_random_double.restype = C.c_double
+        L.mpref_random_double.argtypes = [C.c_void_p]
+        L.mpref_seed_rng.argtypes = [C.c_uint64]
+        L.mpref_rng_draws.restype = C.c_uint64
+        L.mpref_char_map.argtypes = [C.c_int, C.c_void_p]
+        L.mpref_bitvector.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.mpref_set_ring.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mpref_get_ring.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mpref_get_nodep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mpref_set_weights.argtypes = [C.c_void_p, C.c_void_p]
+        L.mpref_allocate.argtypes = [C.c_void_p, C.c_int]
+        L.mpref_num_informative.argtypes = [C.c_void_p]
+        L.mpref_get_parsvect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mpref_node_score.restype = C.c_uint
+        L.mpref_node_score.argtypes = [C.c_void_p, C.c_int]
+        L.mpref_evaluate_full.restype = C.c_uint
+        L.mpref_evaluate_full.argtypes = [C.c_void_p, C.c_int]
+        L.mpref_evaluate_at.restype = C.c_uint
+        L.mpref_evaluate_at.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mpref_pattern_parsimony.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mpref_min_pars_pattern.argtypes = [C.c_void_p, C.c_int]
+        L.mpref_record.argtypes = [C.c_void_p, C.c_int]
+        L.mpref_saved_count.argtypes = [C.c_void_p]
+        L.mpref_saved_mp.argtypes = [C.c_void_p, C.c_void_p]
+        L.mpref_saved_ptn.argtypes = [C.c_void_p, C.c_void_p]
+        L.mpref_rearrange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+        L.mpref_apply_move.argtypes = [C.c_void_p, C.c_int]
+        L.mpref_node_rectifier.argtypes = [C.c_void_p]
+        L.mpref_optimize_spr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mpref_ras.restype = C.c_uint
+        L.mpref_ras.argtypes = [C.c_void_p, C.c_long, C.c_int]
+        L.mpref_reps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.mpref_sweep_count_insertions.restype = C.c_ulong
+        L.mpref_sweep_count_insertions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def char_map(datatype):
+    out = np.zeros(256, dtype=np.uint8)
+    assert lib().mpref_char_map(datatype, _p(out)) == 0
+    return out
+
+
+def bitvector(datatype, ncodes):
+    out = np.zeros(ncodes, dtype=np.uint32)
+    und = lib().mpref_bitvector(datatype, _p(out), ncodes)
+    return out, und
+
+
+class RefEngine:
+    """One reference pllInstance + partitionList over an ASCII pattern matrix."""
+
+    def __init__(self, chars, weights, datatype, sort_alignment=True, n_informative=None):
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        weights = np.ascontiguousarray(weights, dtype=np.int32)
+        self.n, self.P = chars.shape
+        self.datatype = datatype
+        ninf = self.P if n_informative is None else n_informative
+        self.h = lib().mpref_create(self.n, self.P, datatype, _p(chars), _p(weights), int(sort_alignment), ninf)
+        assert self.h
+        self.W = None
+        self.S = {0: 2, 1: 4, 2: 20, 6: 32}[datatype]
+
+    def close(self):
+        if self.h:
+            lib().mpref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_ring(self, bn, bs):
+        bn = np.ascontiguousarray(bn, dtype=np.int32); bs = np.ascontiguousarray(bs, dtype=np.int32)
+        lib().mpref_set_ring(self.h, _p(bn), _p(bs))
+
+    def get_ring(self):
+        bn = np.zeros(3 * (2 * self.n - 1), dtype=np.int32); bs = np.zeros_like(bn)
+        lib().mpref_get_ring(self.h, _p(bn), _p(bs))
+        return bn, bs
+
+    def get_nodep(self):
+        a = np.zeros(2 * self.n - 1, dtype=np.int32); b = np.zeros_like(a)
+        lib().mpref_get_nodep(self.h, _p(a), _p(b))
+        return a, b
+
+    def set_weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.int32)
+        lib().mpref_set_weights(self.h, _p(w))
+
+    def allocate(self, per_site=False):
+        self.W = lib().mpref_allocate(self.h, int(per_site))
+        return self.W
+
+    def num_informative(self):
+        return lib().mpref_num_informative(self.h)
+
+    def parsvect(self, node):
+        out = np.zeros((self.S, self.W), dtype=np.uint32)
+        lib().mpref_get_parsvect(self.h, node, _p(out))
+        return out
+
+    def node_score(self, node):
+        return lib().mpref_node_score(self.h, node)
+
+    def evaluate_full(self, per_site=False):
+        return lib().mpref_evaluate_full(self.h, int(per_site))
+
+    def evaluate_at(self, node, slot, full=False, per_site=False):
+        return lib().mpref_evaluate_at(self.h, node, slot, int(full), int(per_site))
+
+    def pattern_parsimony(self, count=None):
+        out = np.zeros(self.P + 16, dtype=np.uint16)
+        s = C.c_int(0)
+        lib().mpref_pattern_parsimony(self.h, _p(out), C.byref(s))
+        return out[: (self.P if count is None else count)], s.value
+
+    def min_pars_pattern(self, site):
+        return lib().mpref_min_pars_pattern(self.h, site)
+
+    def record(self, ptn=False):
+        lib().mpref_record(self.h, int(ptn))
+
+    def saved(self, ptn=False):
+        k = lib().mpref_saved_count(self.h)
+        mp = np.zeros(k, dtype=np.int32)
+        lib().mpref_saved_mp(self.h, _p(mp))
+        if not ptn:
+            return mp
+        pt = np.zeros((k, self.P), dtype=np.uint16)
+        lib().mpref_saved_ptn(self.h, _p(pt))
+        return mp, pt
+
+    def rearrange(self, i, mintrav, maxtrav, per_site, best_in):
+        out = np.zeros(6, dtype=np.uint32)
+        rc = lib().mpref_rearrange(self.h, i, mintrav, maxtrav, int(per_site), int(best_in), _p(out))
+        return rc, out
+
+    def apply_move(self, per_site=False):
+        lib().mpref_apply_move(self.h, int(per_site))
+
+    def node_rectifier(self):
+        lib().mpref_node_rectifier(self.h)
+
+    def optimize_spr(self, mintrav=1, maxtrav=6, bb=False, ratchet_realloc=False):
+        return lib().mpref_optimize_spr(self.h, mintrav, maxtrav, int(bb), int(ratchet_realloc))
+
+    def ras(self, seed, spr_dist):
+        return lib().mpref_ras(self.h, seed, spr_dist)
+
+    def sweep_count(self, mintrav, maxtrav, per_site, reps=1):
+        return lib().mpref_sweep_count_insertions(self.h, mintrav, maxtrav, int(per_site), reps)
+
+
+def reps(pars, boot, segment_upper):
+    """REPS on the reference's Vec16us (iqtree.cpp:3424-3449). pars u16[P], boot u16[B][P]."""
+    P = len(pars)
+    Pp = (P + 15) // 16 * 16 + 16
+    B = boot.shape[0]
+    a = np.zeros(Pp, dtype=np.uint16); a[:P] = pars
+    w = np.zeros((B, Pp), dtype=np.uint16); w[:, :P] = boot
+    seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
+    out = np.zeros(B, dtype=np.int32)
+    lib().mpref_reps(_p(a), _p(w), B, Pp, _p(seg), len(seg), _p(out))
+    return out
