@@ -1,0 +1,111 @@
+"""Generates tests/golden/*.npz by running the REFERENCE ITSELF (oracle/_ref/libmpref.so =
+/root/reference/sprparsimony.cpp compiled in place, see oracle/ref_driver.cpp) on small seeded
+cases.  Run here (where /root/reference exists):  python tools/make_golden.py
+The fixtures are what pins oracle/mp_oracle.c and, through it, the CUDA path."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import reflib  # noqa: E402
+from tests.helpers import make_case  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# (name, n, sites, datatype, seed, maxtrav)
+CASES = [
+    ("dna12", 12, 300, 1, 7, 6),
+    ("dna40", 40, 1500, 1, 11, 6),
+    ("aa24", 24, 400, 2, 5, 6),
+    ("morph20", 20, 300, 6, 9, 5),
+    ("bin16", 16, 300, 0, 3, 4),
+    ("dna30w", 30, 800, 1, 21, 6),     # heavier pattern weights (low mu -> repeated columns)
+]
+
+
+def one_case(name, n, L, dt, seed, maxtrav):
+    mu = 0.01 if name.endswith("w") else 0.05
+    c = make_case(n, L, dt, seed, mu=mu)
+    ref = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    ref.set_ring(c["bn"], c["bs"])
+    W = ref.allocate(per_site=True)
+    g = dict(n=n, datatype=dt, maxtrav=maxtrav, chars=c["chars"], codes=c["codes"], weights=c["weights"],
+             n_inf=c["n_inf"], bn=c["bn"], bs=c["bs"], W=W, ref_n_inf=ref.num_informative())
+    g["tip_planes"] = np.stack([ref.parsvect(t) for t in range(1, n + 1)])
+    g["score"] = ref.evaluate_full(per_site=True)
+    pp, sm = ref.pattern_parsimony(c["n_inf"])
+    g["ptn_pars"] = pp.copy(); g["ptn_sum"] = sm
+    rn, rs = ref.get_nodep()
+    g["order"] = (3 * rn + rs).astype(np.int32)
+    g["min_pars"] = np.array([ref.min_pars_pattern(i) for i in range(c["n_inf"])], dtype=np.int32)
+    # every node visit of one sweep on the start tree, moves not applied
+    vb = [0]; mps = []; outs = []; ptn_first = None
+    reflib.lib().mpref_seed_rng(31337)               # ties inside a visit draw from the stream
+    for i in range(1, 2 * n - 1):
+        ref.record(i == 3)
+        rc, out = ref.rearrange(i, 1, maxtrav, True, g["score"])
+        if i == 3:
+            m, pt = ref.saved(True)
+            ptn_first = pt[:, : c["n_inf"]].copy()
+        else:
+            m = ref.saved()
+        assert m[0] == g["score"]
+        mps.append(m[1:]); vb.append(vb[-1] + len(m) - 1); outs.append(out)
+    g["visit_begin"] = np.array(vb, dtype=np.int32)
+    g["visit_mp"] = np.concatenate(mps).astype(np.int32)
+    g["visit_out"] = np.stack(outs).astype(np.uint32)
+    g["visit3_ptn"] = ptn_first                      # per-pattern vectors of every candidate of visit 3
+    # the real search, plain and -bb, with a fixed RNG stream
+    for tag, bb in (("plain", False), ("bb", True)):
+        reflib.lib().mpref_seed_rng(2024)
+        ref.set_ring(c["bn"], c["bs"])
+        ref.record(False)
+        g["opt_%s_ret" % tag] = ref.optimize_spr(1, maxtrav, bb=bb)
+        g["opt_%s_draws" % tag] = reflib.lib().mpref_rng_draws()
+        bn, bs = ref.get_ring()
+        g["opt_%s_bn" % tag] = bn; g["opt_%s_bs" % tag] = bs
+        g["opt_%s_score" % tag] = ref.evaluate_full(per_site=bb)
+        if bb:
+            g["opt_bb_saved"] = ref.saved().astype(np.int32)
+    # randomized stepwise addition
+    reflib.lib().mpref_seed_rng(77)
+    g["ras_ret"] = ref.ras(4242 + seed, maxtrav)
+    g["ras_draws"] = reflib.lib().mpref_rng_draws()
+    bn, bs = ref.get_ring()
+    g["ras_bn"] = bn; g["ras_bs"] = bs
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **g)
+    print(name, "W", W, "score", g["score"], "cands", len(g["visit_mp"]), "opt", g["opt_plain_ret"], g["opt_bb_ret"],
+          "saved", len(g["opt_bb_saved"]), "ras", g["ras_ret"])
+
+
+def tables():
+    g = {}
+    for dt in (0, 1, 2, 6):
+        g["char_map_%d" % dt] = reflib.char_map(dt)
+        nc = {0: 4, 1: 16, 2: 23, 6: 33}[dt]
+        bv, und = reflib.bitvector(dt, nc)
+        g["bitvector_%d" % dt] = bv; g["undetermined_%d" % dt] = und
+    # REPS on the reference's Vec16us, including products and sums that wrap at 16 bits
+    rng = np.random.default_rng(5)
+    P = 203
+    pars = rng.integers(0, 40, size=P).astype(np.uint16)
+    boot = rng.integers(0, 6, size=(37, P)).astype(np.uint16)
+    boot[3, 17] = 40000; pars[17] = 3          # lane product wraps
+    boot[5, :64] = 900                         # lane sums wrap
+    seg = np.array([64, 128, P], dtype=np.int32)
+    g["reps_pars"] = pars; g["reps_boot"] = boot; g["reps_seg"] = seg
+    g["reps_out"] = reflib.reps(pars, boot, seg)
+    g["reps_out_1seg"] = reflib.reps(pars, boot, np.array([P], dtype=np.int32))
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), **g)
+    print("tables ok; reps sample", g["reps_out"][:6])
+
+
+if __name__ == "__main__":
+    assert reflib.available(), "build oracle/_ref first: make -C oracle ref"
+    os.makedirs(OUT, exist_ok=True)
+    tables()
+    for c in CASES:
+        one_case(*c)
