@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the parsimony hot path (SPR insertion scoring) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch: every insertion that one SPR sweep
+(rearrangeParsimony for all 2n-2 node visits, radius 1..6) tests on a fixed random tree is
+scored by one launch of k_spr_scan.  Workload at N=1: BASELINE.json configs[1], synthetic DNA
+200 taxa x 100 000 sites (every site its own pattern).  At N>1 the alignment is pattern-sharded
+(SURVEY 8e): every rank holds a contiguous word slice of every bit plane, the slice has the
+same 100 000 sites per rank (weak scaling), and the per-insertion int32 counts are all-reduced
+over NCCL each step.
+
+metric = Fitch site-node ops/s (one insertion = one node combine + one edge evaluation over all
+expanded sites = 2*sites site-node ops); insertions/s is reported next to it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (taxa, sites per GPU, datatype, mu, seed, tree seed)
+    "c2": (200, 100000, 1, 0.05, 2, 102),
+    "c3": (500, 50000, 2, 0.08, 3, 103),
+    "c4": (1000, 1000000, 1, 0.03, 4, 104),
+    "c5": (300, 20000, 6, 0.05, 5, 105),
+    "tiny": (24, 2000, 1, 0.05, 6, 106),
+}
+METRIC = "fitch_site_node_ops_per_s"
+UNIT = "site-node ops/s"
+
+
+def build_case(name, nshards):
+    from mpboot_b200 import hostprep, synth
+    n, sites, dt, mu, seed, tseed = WORKLOADS[name]
+    chars = synth.evolve_alignment(n, sites * nshards, dt, mu, seed)
+    prep = hostprep.prepare(chars, dt, compress=False)     # every site its own pattern
+    bn, bs = synth.random_tree_rings(n, np.random.default_rng(tseed))
+    prep.update(n=n, datatype=dt, bn=bn, bs=bs, sites=sites * nshards)
+    return prep
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class DevCounts:
+    """Zero-copy torch view of the library's device count vector (for the NCCL all-reduce)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def cpu_baseline(case, maxtrav, budget_s=20.0):
+    """The reference's own engine (oracle/_ref) -- or the C port when it is not built -- timed on
+    one host core on a bounded sample of the same workload: as many whole node visits of the same
+    sweep as fit in ~budget_s."""
+    from oracle import portlib, reflib
+    if reflib.available():
+        eng = reflib.RefEngine(case["chars"], case["weights"], case["datatype"], n_informative=case["n_inf"])
+        kind = "reference"
+    else:
+        eng = portlib.OracleEngine(case["codes"], case["weights"], case["datatype"])
+        kind = "port"
+    eng.set_ring(case["bn"], case["bs"])
+    eng.allocate(per_site=True)                 # per-site mode only so that the recorder can count insertions
+    s0 = eng.evaluate_full(per_site=True)
+    n = case["n"]
+    # count insertions per visit first (untimed, recorder on) ...
+    counts = []
+    t0 = time.time()
+    for i in range(1, 2 * n - 1):
+        eng.record(False)
+        eng.rearrange(i, 1, maxtrav, True, s0)
+        counts.append(len(eng.saved()) - 1)
+        if time.time() - t0 > budget_s:
+            break
+    nvis = len(counts)
+    # ... then time the same visits in plain mode (perSiteScores = 0, the plain-search kernel)
+    eng.set_ring(case["bn"], case["bs"])
+    eng.allocate(per_site=False)
+    s0 = eng.evaluate_full(per_site=False)
+    t0 = time.time()
+    for i in range(1, nvis + 1):
+        eng.rearrange(i, 1, maxtrav, False, s0)
+    dt = time.time() - t0
+    ins = int(sum(counts))
+    return ins, dt, kind, "%d of %d node visits of the same sweep (%d insertions), plain mode" % (nvis, 2 * n - 2, ins)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle/_ref when built
+    here, else the C port) on the same workload; one process per host core, each running the
+    same bounded sample, because the reference path is single-threaded and not re-entrant."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    case = build_case(args.workload, 1)
+    ncores = max(1, len(os.sched_getaffinity(0)))
+    nproc = min(ncores, 64)
+    budget = 6.0
+    with mp.get_context("fork").Pool(nproc) as pool:
+        t0 = time.time()
+        res = pool.starmap(_ref_worker, [(case, args.maxtrav, budget, args.steps, args.warmup)] * nproc)
+        wall = time.time() - t0
+    ins = sum(r[0] for r in res)
+    elapsed = max(r[1] for r in res)
+    kind, sample = res[0][2], res[0][3]
+    sites = case["sites"]
+    ins_per_s = ins / elapsed
+    value = ins_per_s * 2.0 * sites
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "insertions_per_s": ins_per_s,
+        "config": {"workload": workload_name(args.workload, 1, case), "maxtrav": args.maxtrav, "processes": nproc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": kind, "sample": sample + " per step, x%d processes" % nproc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _ref_worker(case, maxtrav, budget_s, steps, warmup):
+    from oracle import portlib, reflib
+    if reflib.available():
+        eng = reflib.RefEngine(case["chars"], case["weights"], case["datatype"], n_informative=case["n_inf"]); kind = "reference"
+    else:
+        eng = portlib.OracleEngine(case["codes"], case["weights"], case["datatype"]); kind = "port"
+    n = case["n"]
+    eng.set_ring(case["bn"], case["bs"])
+    eng.allocate(per_site=True)
+    s0 = eng.evaluate_full(per_site=True)
+    counts = []
+    t0 = time.time()
+    for i in range(1, 2 * n - 1):               # untimed: size the bounded sample and count its insertions
+        eng.record(False)
+        eng.rearrange(i, 1, maxtrav, True, s0)
+        counts.append(len(eng.saved()) - 1)
+        if time.time() - t0 > budget_s:
+            break
+    nvis = len(counts)
+    eng.set_ring(case["bn"], case["bs"])
+    eng.allocate(per_site=False)
+    s0 = eng.evaluate_full(per_site=False)
+    for _ in range(min(warmup, 1)):
+        for i in range(1, nvis + 1):
+            eng.rearrange(i, 1, maxtrav, False, s0)
+    t0 = time.time()
+    for _ in range(steps):
+        for i in range(1, nvis + 1):
+            eng.rearrange(i, 1, maxtrav, False, s0)
+    dt = time.time() - t0
+    ins = int(sum(counts)) * steps
+    return ins, dt, kind, "%d of %d node visits of the sweep (%d insertions)" % (nvis, 2 * n - 2, int(sum(counts)))
+
+
+def workload_name(name, nshards, case):
+    n, sites, dt, mu, seed, tseed = WORKLOADS[name]
+    return "%s: synthetic %s %d taxa x %d sites (%d per GPU), SPR sweep radius 1..6 on a fixed random tree" % (
+        name, {0: "BIN", 1: "DNA", 2: "AA", 6: "MORPH32"}[dt], n, case["sites"], sites)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mpboot_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    case = build_case(args.workload, world)
+    n = case["n"]
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = engine.Engine(device=local, stream=stream, shard_rank=rank, shard_count=world)
+    eng.load_alignment(case["codes"], case["weights"], case["datatype"])
+    eng.set_tree(case["bn"], case["bs"])
+    if world > 1:
+        vc = torch.from_numpy(eng.view_counts_partial().astype(np.int32)).cuda()
+        dist.all_reduce(vc)
+        eng.set_view_counts(vc.cpu().numpy().astype(np.uint32))
+    order = eng.visit_order()
+    nvis = 2 * n - 2
+    n_cand, n_tasks = eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
+    S, W = eng.S, eng.shard_words
+    sites_total = eng.n_sites
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step_device():
+        ptr = eng.scan_launch()
+        if world > 1:
+            t = torch.as_tensor(DevCounts(ptr, n_cand + n_tasks), device="cuda")
+            dist.all_reduce(t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush.zero_()                            # L2 flush between timed iterations (outside the events)
+        ev[k][0].record()
+        kev[k][0].record()
+        ptr = eng.scan_launch()
+        kev[k][1].record()
+        if world > 1:
+            t = torch.as_tensor(DevCounts(ptr, n_cand + n_tasks), device="cuda")
+            dist.all_reduce(t)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.time() - t_wall0
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ker_ms = sum(a.elapsed_time(b) for a, b in kev)
+    if world > 1:
+        tt = torch.tensor([dev_ms, ker_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, ker_ms = float(tt[0]), float(tt[1])
+
+    # correctness of what was timed: finish the last step and compare with a fresh end-to-end call
+    vb, mp, cref, cprune = eng.scan_finish(n_cand, nvis) if world == 1 else (None, None, None, None)
+
+    # e2e: the reference-facing call with host buffers (plan on host, H2D, kernel, D2H, finish)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        if world == 1:
+            vb2, mp2, _, _ = eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
+        else:
+            eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
+            ptr = eng.scan_launch()
+            t = torch.as_tensor(DevCounts(ptr, n_cand + n_tasks), device="cuda")
+            dist.all_reduce(t)
+            vb2, mp2, _, _ = eng.scan_finish(n_cand, nvis)
+    barrier()
+    e2e_s = (time.time() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+    if world == 1:
+        assert np.array_equal(mp, mp2), "device-resident and end-to-end paths disagree"
+
+    if rank == 0:
+        ops_per_ins = 2.0 * sites_total
+        ms_per_step = dev_ms / args.steps
+        ins_per_s = n_cand / (ms_per_step * 1e-3)
+        value = ins_per_s * ops_per_ins
+        peak, peak_src = measured_peak()
+        alg_bytes = 8.0 * S * W * n_cand                       # canonical 8*S*W bytes per insertion (this shard)
+        ker_s = ker_ms * 1e-3 / args.steps
+        achieved = alg_bytes / ker_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "insertions_per_s": ins_per_s, "insertions_per_step": n_cand,
+            "config": {"workload": workload_name(args.workload, world, case), "maxtrav": args.maxtrav,
+                       "states": S, "words_per_plane_per_gpu": W, "prune_tasks": n_tasks, "bb": False,
+                       "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": "pattern-sharded x%d, NCCL all-reduce of int32 counts" % world if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_spr_scan", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker_s * 1e3},
+            "e2e": {"value": (n_cand / e2e_s) * ops_per_ins, "unit": UNIT, "insertions_per_s": n_cand / e2e_s,
+                    "h2d_bytes_per_step": None, "d2h_bytes_per_step": 4 * (n_cand + n_tasks), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
+        }
+        line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
+        if world == 1 and not args.no_cpu_baseline:
+            ins, dt, kind, sample = cpu_baseline(case, args.maxtrav, budget_s=args.cpu_budget)
+            line["cpu_baseline"] = {"value": ins / dt * ops_per_ins, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": sample, "insertions_per_s": ins / dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--maxtrav", type=int, default=6)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

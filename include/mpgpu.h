@@ -126,6 +126,8 @@ int mpgpu_scan_visits(mpgpu_ctx *ctx, const int32_t *order, int first, int count
  * after the all-reduce.  counts has n_cand + n_tasks entries (mpgpu_scan_plan returns both). */
 int mpgpu_scan_plan(mpgpu_ctx *ctx, const int32_t *order, int first, int count, int mintrav, int maxtrav,
                     int *n_cand, int *n_tasks);
+/* Bytes of scan program (ops + tasks) the last mpgpu_scan_plan uploaded host->device. */
+int64_t mpgpu_scan_plan_bytes(mpgpu_ctx *ctx);
 /* Launches the scan of the planned batch; the int32 partial counts stay on the device at
  * *dev_counts (n_cand+n_tasks entries) for an in-place NCCL all-reduce.  Asynchronous. */
 int mpgpu_scan_launch(mpgpu_ctx *ctx, void **dev_counts);

@@ -512,6 +512,12 @@ int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, in
     return 0;
 }
 
+int64_t mpgpu_scan_plan_bytes(mpgpu_ctx *c)
+{
+    if (!c) return 0;
+    return (int64_t)(c->plan.ops.size() * sizeof(ScanOp) + c->plan.tasks.size() * sizeof(ScanTask));
+}
+
 int mpgpu_scan_launch(mpgpu_ctx *c, void **dev_counts)
 {
     if (int rc = need_tree(c, true)) return rc;

@@ -54,6 +54,8 @@ def lib():
     L.mpgpu_scan_visits.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     L.mpgpu_scan_plan.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     L.mpgpu_scan_launch.argtypes = [vp, vp]
+    L.mpgpu_scan_plan_bytes.restype = i64
+    L.mpgpu_scan_plan_bytes.argtypes = [vp]
     L.mpgpu_scan_finish.argtypes = [vp, vp, vp, vp, vp, i32]
     L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     _lib = L
@@ -189,6 +191,9 @@ class Engine:
         nc, nt = C.c_int(), C.c_int()
         self._ck(self.L.mpgpu_scan_plan(self.h, _p(order), first, count, mintrav, maxtrav, C.byref(nc), C.byref(nt)))
         return nc.value, nt.value
+
+    def scan_plan_bytes(self):
+        return self.L.mpgpu_scan_plan_bytes(self.h)
 
     def scan_launch(self):
         ptr = C.c_void_p()
