@@ -244,7 +244,13 @@ def run_ours(args):
 
     case = build_case(args.workload, world)
     n = case["n"]
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream shared by torch and the library, so that torch.cuda.Event
+    # brackets exactly the library's launches (the legacy default stream's handle is NULL,
+    # which mpgpu_create takes as "make a private stream")
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     eng = engine.Engine(device=local, stream=stream, shard_rank=rank, shard_count=world)
     eng.load_alignment(case["codes"], case["weights"], case["datatype"])
     eng.set_tree(case["bn"], case["bs"])

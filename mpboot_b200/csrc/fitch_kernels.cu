@@ -1,11 +1,14 @@
 // Hand-written sm_100a kernels of the bit-plane Fitch path.
 //
 // Data layout in HBM: one "view" = the Fitch state sets of a directed
-// subtree, stored as S bit planes of Wl 32-bit words, views[vid][state][word]; bit j of word i
-// = "expanded site 32*(w0+i)+j may be in that state" (same meaning as the reference's
-// parsVect, sprparsimony.cpp:2870-2960; padding bits are 1 in every state so they never score).
-// Wl is a multiple of 128 words, so every plane row starts 512-byte aligned and a warp always
-// moves whole 128-byte lines (32-bit lanes) or 512-byte runs (128-bit lanes).
+// subtree: S bit planes of Wl 32-bit words; bit j of word i of plane k = "expanded site
+// 32*(w0+i)+j may be in state k" (same meaning as the reference's parsVect,
+// sprparsimony.cpp:2870-2960; padding bits are 1 in every state so they never score).
+// The planes are STATE-INTERLEAVED in groups of SG = min(S,4) states:
+//     views[vid][group g][word w][j]  holds plane k = 4*g + j,
+// so the 4 (or 2) state words of one site word are one aligned 128-bit (64-bit) vector: a lane
+// fetches all DNA states of its word with ONE LDG.128 and a warp moves 512 contiguous bytes per
+// group.  Wl is a multiple of 128 words.
 //
 // Kernels
 //   k_compress_tips   R1  compressDNA                    (sprparsimony.cpp:2898-2961)
@@ -56,6 +59,65 @@ const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined)
 }
 
 // ------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------
+template <int S> struct Lay {
+    static const int SG = S < 4 ? S : 4;          // states per interleave group
+    static const int G = (S + SG - 1) / SG;       // groups per view
+};
+
+// all S state words of site word `w` of a view: p = view base + w*SG, group stride gs = Wl*SG
+template <int S>
+__device__ __forceinline__ void load_states(const uint32_t *__restrict__ p, size_t gs, uint32_t (&r)[S])
+{
+    if (Lay<S>::SG == 4) {
+#pragma unroll
+        for (int g = 0; g < Lay<S>::G; g++) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + g * gs));
+            r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
+        }
+    } else {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        r[0] = v.x; r[S > 1 ? 1 : 0] = v.y;
+    }
+}
+template <int S>
+__device__ __forceinline__ void load_states_rw(const uint32_t *p, size_t gs, uint32_t (&r)[S])
+{
+    if (Lay<S>::SG == 4) {
+#pragma unroll
+        for (int g = 0; g < Lay<S>::G; g++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + g * gs);
+            r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
+        }
+    } else {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        r[0] = v.x; r[S > 1 ? 1 : 0] = v.y;
+    }
+}
+template <int S>
+__device__ __forceinline__ void store_states(uint32_t *p, size_t gs, const uint32_t (&r)[S])
+{
+    if (Lay<S>::SG == 4) {
+#pragma unroll
+        for (int g = 0; g < Lay<S>::G; g++)
+            *reinterpret_cast<uint4 *>(p + g * gs) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+    } else {
+        *reinterpret_cast<uint2 *>(p) = make_uint2(r[0], r[S > 1 ? 1 : 0]);
+    }
+}
+// (a & b) | (~n & (a | b)) : the Fitch set for one state given the "some state intersects" mask n
+__device__ __forceinline__ uint32_t fitch1(uint32_t a, uint32_t b, uint32_t n) { return (a & b) | (~n & (a | b)); }
+template <int S>
+__device__ __forceinline__ uint32_t any_and(const uint32_t (&a)[S], const uint32_t (&b)[S])
+{
+    uint32_t n = 0;
+#pragma unroll
+    for (int k = 0; k < S; k++) n |= a[k] & b[k];
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
 // R1: tip planes from codes + pattern frequencies
 // ------------------------------------------------------------------------------------------
 // One thread per (tip, word of this shard).  site_start[k] = first expanded site of the k-th
@@ -97,12 +159,13 @@ __global__ void k_compress_tips(const uint8_t *__restrict__ codes, int P, int nt
             mask[j] = cur;
         }
     }
-    uint32_t *dst = views + (size_t)tip * view_stride + w;       // tips are views 0..n-1
+    const int SG = S < 4 ? S : 4;
+    uint32_t *dst = views + (size_t)tip * view_stride;            // tips are views 0..n-1
     for (int s = 0; s < S; s++) {
         uint32_t word = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) word |= ((mask[j] >> s) & 1u) << j;
-        dst[(size_t)s * Wl] = word;
+        dst[(size_t)(s / SG) * Wl * SG + (size_t)w * SG + (s % SG)] = word;
     }
 }
 
@@ -120,63 +183,34 @@ int launch_compress(Ctx *c)
 }
 
 // ------------------------------------------------------------------------------------------
-// 128-bit helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ld4(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ void st4(uint32_t *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
-__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
-__device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
-// (a & b) | (~n & (a | b)) : the Fitch set for one state given the "some state intersects" mask n
-__device__ __forceinline__ uint32_t fitch1(uint32_t a, uint32_t b, uint32_t n) { return (a & b) | (~n & (a | b)); }
-__device__ __forceinline__ uint4 fitch4(uint4 a, uint4 b, uint4 n)
-{
-    return make_uint4(fitch1(a.x, b.x, n.x), fitch1(a.y, b.y, n.y), fitch1(a.z, b.z, n.z), fitch1(a.w, b.w, n.w));
-}
-__device__ __forceinline__ int popc_not4(uint4 n) { return __popc(~n.x) + __popc(~n.y) + __popc(~n.z) + __popc(~n.w); }
-
-// ------------------------------------------------------------------------------------------
-// R3: one level of the directed-view schedule.  One warp per (triple, 128-word chunk);
-// lanes hold 128 bits of every plane.  dst = fitch(a, b), count[dst] += popc(t_N).
+// R3: one level of the directed-view schedule.  One thread per (triple, site word): all states
+// of the word in registers (one LDG.128 per group and operand).  dst = fitch(a, b),
+// count[dst] += popc(t_N).
 // ------------------------------------------------------------------------------------------
 template <int S>
-__global__ void __launch_bounds__(128) k_fitch_level(uint32_t *__restrict__ views, size_t view_stride, int Wl,
+__global__ void __launch_bounds__(128) k_fitch_level(uint32_t *views, size_t view_stride, int Wl,
                                                      const Triple *__restrict__ triples, uint32_t *__restrict__ vcount)
 {
     const int lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (chunk * kWordPad >= Wl) return;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;          // Wl is a multiple of 128
     const Triple t = triples[blockIdx.y];
-    const size_t off = (size_t)chunk * kWordPad + lane * 4;
-    const uint32_t *A = views + (size_t)t.a * view_stride + off;
-    const uint32_t *B = views + (size_t)t.b * view_stride + off;
-    uint32_t *D = views + (size_t)t.dst * view_stride + off;
-
-    uint4 any = make_uint4(0, 0, 0, 0);
-    if (S <= 4) {
-        uint4 a[S <= 4 ? S : 1], b[S <= 4 ? S : 1];
+    const size_t gs = (size_t)Wl * Lay<S>::SG;
+    const size_t off = (size_t)w * Lay<S>::SG;
+    uint32_t a[S], b[S];
+    load_states_rw<S>(views + (size_t)t.a * view_stride + off, gs, a);
+    load_states_rw<S>(views + (size_t)t.b * view_stride + off, gs, b);
+    const uint32_t n = any_and<S>(a, b);
 #pragma unroll
-        for (int k = 0; k < S; k++) { a[k] = ld4(A + (size_t)k * Wl); b[k] = ld4(B + (size_t)k * Wl); }
-#pragma unroll
-        for (int k = 0; k < S; k++) any = or4(any, and4(a[k], b[k]));
-#pragma unroll
-        for (int k = 0; k < S; k++) st4(D + (size_t)k * Wl, fitch4(a[k], b[k], any));
-    } else {
-#pragma unroll 4
-        for (int k = 0; k < S; k++) any = or4(any, and4(ld4(A + (size_t)k * Wl), ld4(B + (size_t)k * Wl)));
-#pragma unroll 4
-        for (int k = 0; k < S; k++)
-            st4(D + (size_t)k * Wl, fitch4(ld4(A + (size_t)k * Wl), ld4(B + (size_t)k * Wl), any));
-    }
-    int cnt = popc_not4(any);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    for (int k = 0; k < S; k++) a[k] = fitch1(a[k], b[k], n);
+    store_states<S>(views + (size_t)t.dst * view_stride + off, gs, a);
+    int cnt = __reduce_add_sync(0xffffffffu, __popc(~n));
     if (lane == 0 && cnt) atomicAdd(&vcount[t.dst], (uint32_t)cnt);
 }
 
 int launch_level(Ctx *c, const Triple *d_triples, int ntriples)
 {
     if (ntriples == 0) return 0;
-    int chunks = c->Wl / kWordPad;
-    dim3 grid((chunks + 3) / 4, ntriples);
+    dim3 grid(c->Wl / 128, ntriples);
     switch (c->S) {
     case 2:  k_fitch_level<2><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_triples, c->d_vcount); break;
     case 4:  k_fitch_level<4><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_triples, c->d_vcount); break;
@@ -197,23 +231,19 @@ __global__ void __launch_bounds__(128) k_edge_mismatch(const uint32_t *__restric
                                                        int vidA, int vidB, uint32_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (chunk * kWordPad >= Wl) return;
-    const size_t off = (size_t)chunk * kWordPad + lane * 4;
-    const uint32_t *A = views + (size_t)vidA * view_stride + off;
-    const uint32_t *B = views + (size_t)vidB * view_stride + off;
-    uint4 any = make_uint4(0, 0, 0, 0);
-#pragma unroll 4
-    for (int k = 0; k < S; k++) any = or4(any, and4(ld4(A + (size_t)k * Wl), ld4(B + (size_t)k * Wl)));
-    int cnt = popc_not4(any);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t gs = (size_t)Wl * Lay<S>::SG;
+    const size_t off = (size_t)w * Lay<S>::SG;
+    uint32_t a[S], b[S];
+    load_states<S>(views + (size_t)vidA * view_stride + off, gs, a);
+    load_states<S>(views + (size_t)vidB * view_stride + off, gs, b);
+    int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(a, b)));
     if (lane == 0 && cnt) atomicAdd(out, (uint32_t)cnt);
 }
 
 int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out)
 {
-    int chunks = c->Wl / kWordPad;
-    dim3 grid((chunks + 3) / 4);
+    dim3 grid(c->Wl / 128);
     switch (c->S) {
     case 2:  k_edge_mismatch<2><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, vidA, vidB, d_out); break;
     case 4:  k_edge_mismatch<4><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, vidA, vidB, d_out); break;
@@ -242,123 +272,173 @@ int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out)
 // which the task accumulates once into base_out.  Each child view is read once per task
 // (4*S*W bytes per insertion instead of the canonical 8*S*W), the up-views never leave the SM.
 //
-// One warp owns (task, chunk of 32 words); lane l owns word l of the chunk for every plane
+// One warp owns (task, chunk of 32 words); lane l owns word l of the chunk for every state
 // and every stack slot, so the stack needs no synchronisation at all.
 // Work order: all tasks of chunk 0, then chunk 1, ... so that concurrently resident warps
-// touch the same few word columns of every view and the views are served from L2.
+// touch the same few word columns of every view and the views are served from L1/L2.
 // ------------------------------------------------------------------------------------------
-template <int S>
-__device__ __forceinline__ uint32_t any_and(const uint32_t (&a)[S], const uint32_t (&b)[S])
+// shared-memory stack access by 32-bit shared address (keeps address arithmetic to one IMAD)
+__device__ __forceinline__ void lds_vec(uint32_t addr, uint4 &v)
 {
-    uint32_t n = 0;
-#pragma unroll
-    for (int k = 0; k < S; k++) n |= a[k] & b[k];
-    return n;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+}
+__device__ __forceinline__ void sts_vec(uint32_t addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void lds_vec(uint32_t addr, uint2 &v)
+{
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+}
+__device__ __forceinline__ void sts_vec(uint32_t addr, const uint2 &v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+template <int S> struct VecOf { typedef uint4 T; };
+template <> struct VecOf<2> { typedef uint2 T; };
+
+// A view operand held as G vectors of SG states
+template <int S> struct StateVec {
+    typedef typename VecOf<S>::T V;
+    V g[Lay<S>::G];
+    __device__ __forceinline__ void load(const V *__restrict__ p, uint32_t gstride)
+    {
+#pragma unroll
+        for (int i = 0; i < Lay<S>::G; i++) g[i] = __ldg(p + (size_t)i * gstride);
+    }
+    __device__ __forceinline__ void load_shared(uint32_t addr)
+    {
+#pragma unroll
+        for (int i = 0; i < Lay<S>::G; i++) lds_vec(addr + i * 32 * (int)sizeof(V), g[i]);
+    }
+    __device__ __forceinline__ void store_shared(uint32_t addr) const
+    {
+#pragma unroll
+        for (int i = 0; i < Lay<S>::G; i++) sts_vec(addr + i * 32 * (int)sizeof(V), g[i]);
+    }
+    __device__ __forceinline__ void unpack(uint32_t (&r)[S]) const
+    {
+#pragma unroll
+        for (int i = 0; i < Lay<S>::G; i++) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(&g[i]);
+#pragma unroll
+            for (int j = 0; j < Lay<S>::SG; j++) r[Lay<S>::SG * i + j] = w[j];
+        }
+    }
+    __device__ __forceinline__ void pack(const uint32_t (&r)[S])
+    {
+#pragma unroll
+        for (int i = 0; i < Lay<S>::G; i++) {
+            uint32_t *w = reinterpret_cast<uint32_t *>(&g[i]);
+#pragma unroll
+            for (int j = 0; j < Lay<S>::SG; j++) w[j] = r[Lay<S>::SG * i + j];
+        }
+    }
+};
+
+// Scores one child: Uc = fitch(U, X) (X = sibling view), optional store of Uc, optional count.
 template <int S>
-__global__ void k_spr_scan(const uint32_t *__restrict__ views, size_t view_stride, int Wl,
+__device__ __forceinline__ void scan_child(const uint32_t (&U)[S], const uint32_t (&X)[S], const uint32_t (&C)[S],
+                                           const uint32_t (&Sv)[S], int outi, int dsti, uint32_t sstack,
+                                           int lane, int32_t *__restrict__ out)
+{
+    const uint32_t n = any_and<S>(U, X);
+    uint32_t Uc[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) Uc[k] = fitch1(U[k], X[k], n);
+    if (dsti >= 0) {
+        StateVec<S> sv; sv.pack(Uc);
+        sv.store_shared(sstack + (uint32_t)dsti * (Lay<S>::G * 32 * (int)sizeof(typename VecOf<S>::T)));
+    }
+    if (outi >= 0) {
+        const uint32_t m = any_and<S>(Uc, C);
+        uint32_t z = 0;
+#pragma unroll
+        for (int k = 0; k < S; k++) z |= fitch1(Uc[k], C[k], m) & Sv[k];
+        const int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
+        if (lane == 0) atomicAdd(&out[outi], cnt);
+    }
+}
+
+// PF = software-prefetch the next op's child views while the current op computes.
+template <int S, bool PF>
+__global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int Wl,
                            const ScanTask *__restrict__ tasks, int ntasks,
                            const ScanOp *__restrict__ ops, int nslots, int32_t *__restrict__ out)
 {
-    extern __shared__ uint32_t smem[];
+    typedef typename VecOf<S>::T V;
+    extern __shared__ uint4 smem4[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int wpb = blockDim.x >> 5;
-    const long long gw = (long long)blockIdx.x * wpb + warp;
-    const int nchunks = Wl / kChunkWords;
-    if (gw >= (long long)ntasks * nchunks) return;
-    const int chunk = (int)(gw / ntasks);
-    const int ti = (int)(gw % ntasks);
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    const unsigned nchunks = Wl / kChunkWords;
+    if (gw >= (unsigned)ntasks * nchunks) return;
+    const unsigned chunk = gw / (unsigned)ntasks;
+    const unsigned ti = gw - chunk * (unsigned)ntasks;
     const ScanTask task = tasks[ti];
-    const size_t off = (size_t)chunk * kChunkWords + lane;
-    uint32_t *stack = smem + (size_t)warp * nslots * S * 32 + lane;     // [slot][k][lane]
+    const uint32_t gsv = (uint32_t)Wl;                                   // group stride in vectors
+    const V *vbase = views + (size_t)chunk * kChunkWords + lane;
+    constexpr uint32_t kSlotBytes = Lay<S>::G * 32 * sizeof(V);          // [group][lane] vectors
+    const uint32_t sstack = (uint32_t)__cvta_generic_to_shared(smem4) +
+                            (uint32_t)warp * (uint32_t)nslots * kSlotBytes + lane * (uint32_t)sizeof(V);
 
     uint32_t Sv[S];
     {
-        const uint32_t *p = views + (size_t)task.s_vid * view_stride + off;
-#pragma unroll
-        for (int k = 0; k < S; k++) Sv[k] = __ldg(p + (size_t)k * Wl);
-    }
-    if (task.base_out >= 0) {
-        const uint32_t *p1 = views + (size_t)task.d1 * view_stride + off;
-        const uint32_t *p2 = views + (size_t)task.d2 * view_stride + off;
-        uint32_t n = 0;
-#pragma unroll
-        for (int k = 0; k < S; k++) n |= __ldg(p1 + (size_t)k * Wl) & __ldg(p2 + (size_t)k * Wl);
-        int cnt = __reduce_add_sync(0xffffffffu, __popc(~n));
-        if (lane == 0 && cnt) atomicAdd(&out[task.base_out], cnt);
+        StateVec<S> t0, t1, t2;
+        t0.load(vbase + (uint32_t)task.s_vid, gsv);
+        t1.load(vbase + (uint32_t)task.d1, gsv);
+        t2.load(vbase + (uint32_t)task.d2, gsv);
+        t0.unpack(Sv);
+        uint32_t d1[S], d2[S];
+        t1.unpack(d1); t2.unpack(d2);
+        const int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(d1, d2)));
+        if (lane == 0) atomicAdd(&out[task.base_out], cnt);
     }
 
-    for (int oi = task.op_begin; oi < task.op_end; oi++) {
-        const int4 o0 = __ldg(reinterpret_cast<const int4 *>(ops + oi));
-        const int4 o1 = __ldg(reinterpret_cast<const int4 *>(ops + oi) + 1);
-        const int src = o0.x, c1 = o0.y, c2 = o0.z, out1 = o0.w;
-        const int out2 = o1.x, dst1 = o1.y, dst2 = o1.z;
+    int oi = task.op_begin;
+    const int oe = task.op_end;
+    if (oi >= oe) return;
+    const int4 *opv = reinterpret_cast<const int4 *>(ops);
+    int4 q0 = __ldg(opv + 2 * oi), q1 = __ldg(opv + 2 * oi + 1);         // current op
+    int4 p0 = q0, p1 = q1;                                               // next op
+    if (oi + 1 < oe) { p0 = __ldg(opv + 2 * oi + 2); p1 = __ldg(opv + 2 * oi + 3); }
+    StateVec<S> Av, Bv;
+    Av.load(vbase + (uint32_t)q0.y, gsv);
+    Bv.load(vbase + (uint32_t)q0.z, gsv);
 
+    for (; oi < oe; oi++) {
+        StateVec<S> An, Bn;
+        int4 r0 = p0, r1 = p1;
+        if (PF) {
+            if (oi + 1 < oe) { An.load(vbase + (uint32_t)p0.y, gsv); Bn.load(vbase + (uint32_t)p0.z, gsv); }
+            if (oi + 2 < oe) { r0 = __ldg(opv + 2 * oi + 4); r1 = __ldg(opv + 2 * oi + 5); }
+        }
+        const int src = q0.x, out1 = q0.w, out2 = q1.x, dst1 = q1.y, dst2 = q1.z;
+        StateVec<S> Uv;
+        if (src >= 0) Uv.load_shared(sstack + (uint32_t)src * kSlotBytes);
+        else Uv.load(vbase + (uint32_t)(~src), gsv);
         uint32_t U[S], A[S], B[S];
-        {
-            const uint32_t *pa = views + (size_t)c1 * view_stride + off;
-            const uint32_t *pb = views + (size_t)c2 * view_stride + off;
-#pragma unroll
-            for (int k = 0; k < S; k++) { A[k] = __ldg(pa + (size_t)k * Wl); B[k] = __ldg(pb + (size_t)k * Wl); }
-            if (src >= 0) {
-                const uint32_t *ps = stack + (size_t)src * S * 32;
-#pragma unroll
-                for (int k = 0; k < S; k++) U[k] = ps[k * 32];
-            } else {
-                const uint32_t *pu = views + (size_t)(~src) * view_stride + off;
-#pragma unroll
-                for (int k = 0; k < S; k++) U[k] = __ldg(pu + (size_t)k * Wl);
-            }
+        Uv.unpack(U); Av.unpack(A); Bv.unpack(B);
+        if ((out1 & dst1) >= 0) scan_child<S>(U, B, A, Sv, out1, dst1, sstack, lane, out);   // child 1, sibling B
+        if ((out2 & dst2) >= 0) scan_child<S>(U, A, B, Sv, out2, dst2, sstack, lane, out);   // child 2, sibling A
+        if (PF) {
+            Av = An; Bv = Bn;
+        } else if (oi + 1 < oe) {
+            if (oi + 2 < oe) { r0 = __ldg(opv + 2 * oi + 4); r1 = __ldg(opv + 2 * oi + 5); }
+            Av.load(vbase + (uint32_t)p0.y, gsv);
+            Bv.load(vbase + (uint32_t)p0.z, gsv);
         }
-        // child 1 (sibling view B)
-        if (out1 >= 0 || dst1 >= 0) {
-            const uint32_t n = any_and<S>(U, B);
-            uint32_t U1[S];
-#pragma unroll
-            for (int k = 0; k < S; k++) U1[k] = fitch1(U[k], B[k], n);
-            if (dst1 >= 0) {
-                uint32_t *pd = stack + (size_t)dst1 * S * 32;
-#pragma unroll
-                for (int k = 0; k < S; k++) pd[k * 32] = U1[k];
-            }
-            if (out1 >= 0) {
-                const uint32_t m = any_and<S>(U1, A);
-                uint32_t z = 0;
-#pragma unroll
-                for (int k = 0; k < S; k++) z |= fitch1(U1[k], A[k], m) & Sv[k];
-                int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
-                if (lane == 0 && cnt) atomicAdd(&out[out1], cnt);
-            }
-        }
-        // child 2 (sibling view A)
-        if (out2 >= 0 || dst2 >= 0) {
-            const uint32_t n = any_and<S>(U, A);
-            uint32_t U2[S];
-#pragma unroll
-            for (int k = 0; k < S; k++) U2[k] = fitch1(U[k], A[k], n);
-            if (dst2 >= 0) {
-                uint32_t *pd = stack + (size_t)dst2 * S * 32;
-#pragma unroll
-                for (int k = 0; k < S; k++) pd[k * 32] = U2[k];
-            }
-            if (out2 >= 0) {
-                const uint32_t m = any_and<S>(U2, B);
-                uint32_t z = 0;
-#pragma unroll
-                for (int k = 0; k < S; k++) z |= fitch1(U2[k], B[k], m) & Sv[k];
-                int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
-                if (lane == 0 && cnt) atomicAdd(&out[out2], cnt);
-            }
-        }
+        q0 = p0; q1 = p1; p0 = r0; p1 = r1;
     }
 }
 
 template <int S>
 static int launch_scan_t(Ctx *c, int ntasks, int nslots)
 {
-    const size_t per_warp = (size_t)(nslots > 0 ? nslots : 1) * S * 32 * sizeof(uint32_t);
+    typedef typename VecOf<S>::T V;
+    constexpr bool PF = S <= 4;
+    const size_t per_warp = (size_t)(nslots > 0 ? nslots : 1) * Lay<S>::G * 32 * sizeof(V);
     int wpb = 8;
     const size_t budget = 96 * 1024;
     while (wpb > 1 && per_warp * wpb > budget) wpb >>= 1;
@@ -366,14 +446,15 @@ static int launch_scan_t(Ctx *c, int ntasks, int nslots)
     if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         configured = 200 * 1024;
     }
     const long long warps = (long long)ntasks * (c->Wl / kChunkWords);
     const long long blocks = (warps + wpb - 1) / wpb;
-    if (blocks > 0x7fffffffLL) { set_error("scan grid too large"); return 1; }
-    k_spr_scan<S><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(c->d_views, c->view_stride, c->Wl, c->d_tasks, ntasks,
-                                                                   c->d_ops, nslots > 0 ? nslots : 1, c->d_counts);
+    if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
+    k_spr_scan<S, PF><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const V *>(c->d_views), c->Wl,
+                                                                       c->d_tasks, ntasks, c->d_ops,
+                                                                       nslots > 0 ? nslots : 1, c->d_counts);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;
@@ -405,16 +486,16 @@ __global__ void k_site_counters(const uint32_t *__restrict__ views, size_t view_
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= Wl) return;
+    const size_t gs = (size_t)Wl * Lay<S>::SG;
+    const size_t off = (size_t)w * Lay<S>::SG;
     uint32_t cnt[16];
 #pragma unroll
     for (int b = 0; b < 16; b++) cnt[b] = 0;
     for (int i = 0; i < npairs; i++) {
-        const uint32_t *A = views + (size_t)pairs[2 * i] * view_stride + w;
-        const uint32_t *B = views + (size_t)pairs[2 * i + 1] * view_stride + w;
-        uint32_t n = 0;
-#pragma unroll 4
-        for (int k = 0; k < S; k++) n |= __ldg(A + (size_t)k * Wl) & __ldg(B + (size_t)k * Wl);
-        uint32_t carry = ~n;
+        uint32_t a[S], bb[S];
+        load_states<S>(views + (size_t)pairs[2 * i] * view_stride + off, gs, a);
+        load_states<S>(views + (size_t)pairs[2 * i + 1] * view_stride + off, gs, bb);
+        uint32_t carry = ~any_and<S>(a, bb);
 #pragma unroll
         for (int b = 0; b < 16; b++) {
             const uint32_t t = cnt[b] & carry;
@@ -422,7 +503,8 @@ __global__ void k_site_counters(const uint32_t *__restrict__ views, size_t view_
             carry = t;
         }
     }
-    for (int b = 0; b < nbits; b++) bitcnt[(size_t)b * Wl + w] = cnt[b];
+#pragma unroll
+    for (int b = 0; b < 16; b++) if (b < nbits) bitcnt[(size_t)b * Wl + w] = cnt[b];
 }
 
 int launch_site_counters(Ctx *c, int npairs, int nbits)

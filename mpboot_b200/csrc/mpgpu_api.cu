@@ -96,7 +96,10 @@ static int build_planes(Ctx *c, bool realloc_views)
     const int newWl = (int)(glob / c->shard_count);
     if (newWl != c->Wl || glob != c->glob_words) realloc_views = true;
     c->glob_words = (int)glob; c->Wl = newWl; c->w0 = (int64_t)c->shard_rank * newWl;
-    c->view_stride = (size_t)c->S * c->Wl;
+    {
+        const int SG = c->S < 4 ? c->S : 4, G = (c->S + SG - 1) / SG;
+        c->view_stride = (size_t)G * SG * c->Wl;      // state-interleaved groups, see fitch_kernels.cu
+    }
 
     if (c->d_site_start) { cudaFree(c->d_site_start); c->d_site_start = nullptr; }
     if (c->d_inf_ptn) { cudaFree(c->d_inf_ptn); c->d_inf_ptn = nullptr; }
@@ -347,9 +350,10 @@ static int copy_view_ref_layout(mpgpu_ctx *c, int vid, uint32_t *out)
     MPGPU_CUDA(cudaMemcpyAsync(tmp.data(), c->d_views + (size_t)vid * c->view_stride, c->view_stride * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    const int SG = c->S < 4 ? c->S : 4;
     for (int s = 0; s < c->S; s++)
         for (int w = 0; w < c->ref_words; w++)
-            out[(size_t)s * c->ref_words + w] = w < c->Wl ? tmp[(size_t)s * c->Wl + w] : 0xFFFFFFFFu;
+            out[(size_t)s * c->ref_words + w] = w < c->Wl ? tmp[(size_t)(s / SG) * c->Wl * SG + (size_t)w * SG + (s % SG)] : 0xFFFFFFFFu;
     return 0;
 }
 
@@ -505,7 +509,8 @@ int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, in
     if (int rc = need_tree(c, true)) return rc;
     if (!order || first < 1 || count < 0 || first + count > 2 * c->n - 1) { set_error("bad visit range"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
-    if (int rc = build_scan_plan(c->tree, c->vlen, order, first, count, mintrav, maxtrav, c->plan)) return rc;
+    const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
+    if (int rc = build_scan_plan(c->tree, c->vlen, order, first, count, mintrav, maxtrav, vstride_vec, c->plan)) return rc;
     if (int rc = upload_plan(c)) return rc;
     if (n_cand) *n_cand = c->plan.n_cand;
     if (n_tasks) *n_tasks = (int)c->plan.tasks.size();

@@ -45,15 +45,16 @@ struct Triple { int32_t dst, a, b, pad; };
 
 // ---- scan program (built on the host, interpreted by k_spr_scan) ------------------------
 struct ScanOp {
-    int32_t src;        // >= 0: stack slot holding U of the node being expanded; < 0: ~view id
-    int32_t c1, c2;     // view ids of the two children (pointing at the expanded node)
+    int32_t src;        // >= 0: stack slot holding U of the node being expanded; < 0: ~view offset
+    int32_t c1, c2;     // views of the two children (pointing at the expanded node), as offsets
+                        // in vector units (vid * view_stride / SG) so the kernel adds, not multiplies
     int32_t out1, out2; // output slot of the insertion into the child's branch (-1: not scored)
     int32_t dst1, dst2; // stack slot receiving the child's up-view (-1: child is not expanded)
     int32_t pad;
 };
 struct ScanTask {
-    int32_t s_vid;      // pruned subtree
-    int32_t d1, d2;     // the two views that become neighbours when the node is removed
+    int32_t s_vid;      // pruned subtree (view offset in vector units, like ScanOp::c1)
+    int32_t d1, d2;     // the two views that become neighbours when the node is removed (offsets)
     int32_t op_begin, op_end;
     int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge)
     int32_t pad0, pad1;
@@ -132,7 +133,7 @@ const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);
 // ---- host SPR logic (spr_host.cpp) ---------------------------------------------------------
 void visit_order(const HostTree &t, std::vector<int32_t> &order);
 int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
-                    int first, int count, int mintrav, int maxtrav, ScanPlan &plan);
+                    int first, int count, int mintrav, int maxtrav, uint32_t vstride_vec, ScanPlan &plan);
 void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);
 
 }  // namespace mpgpu

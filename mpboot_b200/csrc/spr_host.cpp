@@ -37,7 +37,9 @@ struct Builder {
     ScanPlan &plan;
     int prune_ref;
     int task_index;
-    Builder(const HostTree &tt, ScanPlan &pp) : t(tt), plan(pp), prune_ref(0), task_index(0) {}
+    uint32_t vstride;                                               // view stride in vector units
+    Builder(const HostTree &tt, ScanPlan &pp, uint32_t vs) : t(tt), plan(pp), prune_ref(0), task_index(0), vstride(vs) {}
+    int32_t voff(int ref) const { return (int32_t)((uint32_t)t.vid(ref) * vstride); }
 
     // addTraverseParsimony(tr, pr, p, q, mintrav, maxtrav, doAll = FALSE) for q = x.
     // parent_op/which identify the expand op that scores x; depth is x's distance (1-based).
@@ -56,7 +58,7 @@ struct Builder {
             if (slot + 1 > plan.max_slot) plan.max_slot = slot + 1;
             const int c1 = t.back(t.next(x)), c2 = t.back(t.next(t.next(x)));
             ScanOp op;
-            op.src = slot; op.c1 = t.vid(c1); op.c2 = t.vid(c2);
+            op.src = slot; op.c1 = voff(c1); op.c2 = voff(c2);
             op.out1 = op.out2 = op.dst1 = op.dst2 = -1; op.pad = 0;
             const int me = (int)plan.ops.size();
             plan.ops.push_back(op);
@@ -67,11 +69,11 @@ struct Builder {
 
     // the two addTraverseParsimony calls made for one inner neighbour `nb` of the removed node:
     // candidates are the branches to nb's children; the far side of nb is the view `far_vid`.
-    void expand_top(int nb, int far_vid, int mintrav, int maxtrav)
+    void expand_top(int nb, int far_ref, int mintrav, int maxtrav)
     {
         const int c1 = t.back(t.next(nb)), c2 = t.back(t.next(t.next(nb)));
         ScanOp op;
-        op.src = ~far_vid; op.c1 = t.vid(c1); op.c2 = t.vid(c2);
+        op.src = ~voff(far_ref); op.c1 = voff(c1); op.c2 = voff(c2);
         op.out1 = op.out2 = op.dst1 = op.dst2 = -1; op.pad = 0;
         const int me = (int)plan.ops.size();
         plan.ops.push_back(op);
@@ -85,7 +87,7 @@ struct Builder {
 // Enumerates what rearrangeParsimony(tr, pr, tr->nodep[i], mintrav, maxtrav, doAll=FALSE) tests
 // for i in [first, first+count).  Returns 0, or 1 if maxtrav exceeds the kernel's stack.
 int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
-                    int first, int count, int mintrav, int maxtrav_in, ScanPlan &plan)
+                    int first, int count, int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan)
 {
     plan.ops.clear(); plan.tasks.clear(); plan.visit_begin.clear();
     plan.cand_ref.clear(); plan.cand_prune.clear(); plan.cand_task.clear(); plan.task_const.clear();
@@ -94,7 +96,8 @@ int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const 
     int maxtrav = maxtrav_in;
     if (maxtrav > n - 3) maxtrav = n - 3;                       // :2275 (tr->ntips == mxtips during the search)
     if (maxtrav > kMaxTrav) { set_error("maxtrav exceeds the scan kernel's stack depth"); return 1; }
-    Builder b(t, plan);
+    if ((uint64_t)(4 * n - 6) * vstride >= 0x7fffffffULL) { set_error("view array too large for 32-bit scan offsets"); return 1; }
+    Builder b(t, plan, vstride);
 
     for (int v = 0; v < count; v++) {
         plan.visit_begin.push_back(plan.n_cand);
@@ -106,14 +109,14 @@ int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const 
             const int p1 = t.back(t.next(p)), p2 = t.back(t.next(t.next(p)));
             if (!t.is_tip(p1) || !t.is_tip(p2)) {
                 ScanTask task;
-                task.s_vid = t.vid(q); task.d1 = t.vid(p1); task.d2 = t.vid(p2);
+                task.s_vid = b.voff(q); task.d1 = b.voff(p1); task.d2 = b.voff(p2);
                 task.op_begin = (int)plan.ops.size(); task.base_out = 0; task.pad0 = task.pad1 = 0;
                 b.prune_ref = p; b.task_index = (int)plan.tasks.size();
-                if (!t.is_tip(p1)) b.expand_top(p1, task.d2, mintrav, maxtrav);
-                if (!t.is_tip(p2)) b.expand_top(p2, task.d1, mintrav, maxtrav);
+                if (!t.is_tip(p1)) b.expand_top(p1, p2, mintrav, maxtrav);
+                if (!t.is_tip(p2)) b.expand_top(p2, p1, mintrav, maxtrav);
                 task.op_end = (int)plan.ops.size();
                 plan.tasks.push_back(task);
-                plan.task_const.push_back(vlen[task.s_vid] + vlen[task.d1] + vlen[task.d2]);
+                plan.task_const.push_back(vlen[t.vid(q)] + vlen[t.vid(p1)] + vlen[t.vid(p2)]);
             }
         }
         if (!t.is_tip(q) && maxtrav > 0) {                      // :2333
@@ -123,14 +126,14 @@ int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const 
             if (ok1 || ok2) {
                 const int mintrav2 = mintrav > 2 ? mintrav : 2;
                 ScanTask task;
-                task.s_vid = t.vid(p); task.d1 = t.vid(q1); task.d2 = t.vid(q2);
+                task.s_vid = b.voff(p); task.d1 = b.voff(q1); task.d2 = b.voff(q2);
                 task.op_begin = (int)plan.ops.size(); task.base_out = 0; task.pad0 = task.pad1 = 0;
                 b.prune_ref = q; b.task_index = (int)plan.tasks.size();
-                if (!t.is_tip(q1)) b.expand_top(q1, task.d2, mintrav2, maxtrav);
-                if (!t.is_tip(q2)) b.expand_top(q2, task.d1, mintrav2, maxtrav);
+                if (!t.is_tip(q1)) b.expand_top(q1, q2, mintrav2, maxtrav);
+                if (!t.is_tip(q2)) b.expand_top(q2, q1, mintrav2, maxtrav);
                 task.op_end = (int)plan.ops.size();
                 plan.tasks.push_back(task);
-                plan.task_const.push_back(vlen[task.s_vid] + vlen[task.d1] + vlen[task.d2]);
+                plan.task_const.push_back(vlen[t.vid(p)] + vlen[t.vid(q1)] + vlen[t.vid(q2)]);
             }
         }
     }
