@@ -21,6 +21,8 @@
 //                         (sprparsimony.cpp:294-343, 3363-3392)
 #include "mpgpu_internal.h"
 
+#include <cstdlib>
+
 namespace mpgpu {
 
 // ------------------------------------------------------------------------------------------
@@ -340,32 +342,44 @@ template <int S> struct StateVec {
 // Scores one child: Uc = fitch(U, X) (X = sibling view), optional store of Uc, optional count.
 template <int S>
 __device__ __forceinline__ void scan_child(const uint32_t (&U)[S], const uint32_t (&X)[S], const uint32_t (&C)[S],
-                                           const uint32_t (&Sv)[S], int outi, int dsti, uint32_t sstack,
-                                           int lane, int32_t *__restrict__ out)
+                                           const uint32_t (&Sv)[S], bool do_out, int32_t *__restrict__ outp,
+                                           bool do_dst, uint32_t dst_addr, bool lane0)
 {
     const uint32_t n = any_and<S>(U, X);
     uint32_t Uc[S];
 #pragma unroll
     for (int k = 0; k < S; k++) Uc[k] = fitch1(U[k], X[k], n);
-    if (dsti >= 0) {
+    if (do_dst) {
         StateVec<S> sv; sv.pack(Uc);
-        sv.store_shared(sstack + (uint32_t)dsti * (Lay<S>::G * 32 * (int)sizeof(typename VecOf<S>::T)));
+        sv.store_shared(dst_addr);
     }
-    if (outi >= 0) {
+    if (do_out) {
         const uint32_t m = any_and<S>(Uc, C);
         uint32_t z = 0;
 #pragma unroll
         for (int k = 0; k < S; k++) z |= fitch1(Uc[k], C[k], m) & Sv[k];
         const int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
-        if (lane == 0) atomicAdd(&out[outi], cnt);
+        if (lane0) atomicAdd(outp, cnt);
     }
 }
 
-// PF = software-prefetch the next op's child views while the current op computes.
+// keep a value in its register: stops ptxas from re-deriving it from special registers /
+// kernel parameters at every use (it did, ~8 instructions per shared or global address)
+__device__ __forceinline__ void pin(uint32_t &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(const void *&x) { asm volatile("" : "+l"(x)); }
+
+// The program arrives as two streams so that the loads of op i+1's child views can be issued
+// while op i computes without rotating whole op records through registers:
+//   offs[i] = (c1, c2) view offsets in vector units
+//   ctl[i]  = x: out1 | out2 << 16, each relative to the task's first candidate, 0xFFFF = none
+//             y: src | dst1 << 8 | dst2 << 16   (stack slots; 0xFF = none;
+//                src 0xFF / 0xFE = the task's D2 / D1 view for the two top-level expansions)
+// PF = also software-prefetch op i+1's child views into a second register set (small S only).
 template <int S, bool PF>
 __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int Wl,
                            const ScanTask *__restrict__ tasks, int ntasks,
-                           const ScanOp *__restrict__ ops, int nslots, int32_t *__restrict__ out)
+                           const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
+                           int nslots, int32_t *__restrict__ out)
 {
     typedef typename VecOf<S>::T V;
     extern __shared__ uint4 smem4[];
@@ -376,61 +390,72 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     if (gw >= (unsigned)ntasks * nchunks) return;
     const unsigned chunk = gw / (unsigned)ntasks;
     const unsigned ti = gw - chunk * (unsigned)ntasks;
-    const ScanTask task = tasks[ti];
-    const uint32_t gsv = (uint32_t)Wl;                                   // group stride in vectors
-    const V *vbase = views + (size_t)chunk * kChunkWords + lane;
-    constexpr uint32_t kSlotBytes = Lay<S>::G * 32 * sizeof(V);          // [group][lane] vectors
-    const uint32_t sstack = (uint32_t)__cvta_generic_to_shared(smem4) +
-                            (uint32_t)warp * (uint32_t)nslots * kSlotBytes + lane * (uint32_t)sizeof(V);
+    const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
+    const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
+    const uint32_t gsv = (uint32_t)Wl;                                       // group stride in vectors
+    const void *vb_ = views + (size_t)chunk * kChunkWords + lane;
+    pin(vb_);
+    const V *vbase = static_cast<const V *>(vb_);
+    constexpr uint32_t kSlotBytes = Lay<S>::G * 32 * sizeof(V);              // [group][lane] vectors
+    uint32_t sstack = (uint32_t)__cvta_generic_to_shared(smem4) +
+                      (uint32_t)warp * (uint32_t)nslots * kSlotBytes + lane * (uint32_t)sizeof(V);
+    pin(sstack);
+    const bool lane0 = lane == 0;
+    int32_t *outc = out + t1.z;                                              // candidates of this task
 
     uint32_t Sv[S];
     {
-        StateVec<S> t0, t1, t2;
-        t0.load(vbase + (uint32_t)task.s_vid, gsv);
-        t1.load(vbase + (uint32_t)task.d1, gsv);
-        t2.load(vbase + (uint32_t)task.d2, gsv);
-        t0.unpack(Sv);
+        StateVec<S> a, b, c;
+        a.load(vbase + (uint32_t)t0.x, gsv);
+        b.load(vbase + (uint32_t)t0.y, gsv);
+        c.load(vbase + (uint32_t)t0.z, gsv);
+        a.unpack(Sv);
         uint32_t d1[S], d2[S];
-        t1.unpack(d1); t2.unpack(d2);
+        b.unpack(d1); c.unpack(d2);
         const int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(d1, d2)));
-        if (lane == 0) atomicAdd(&out[task.base_out], cnt);
+        if (lane0) atomicAdd(&out[t1.y], cnt);
     }
 
-    int oi = task.op_begin;
-    const int oe = task.op_end;
+    int oi = t0.w;
+    const int oe = t1.x;
     if (oi >= oe) return;
-    const int4 *opv = reinterpret_cast<const int4 *>(ops);
-    int4 q0 = __ldg(opv + 2 * oi), q1 = __ldg(opv + 2 * oi + 1);         // current op
-    int4 p0 = q0, p1 = q1;                                               // next op
-    if (oi + 1 < oe) { p0 = __ldg(opv + 2 * oi + 2); p1 = __ldg(opv + 2 * oi + 3); }
-    StateVec<S> Av, Bv;
-    Av.load(vbase + (uint32_t)q0.y, gsv);
-    Bv.load(vbase + (uint32_t)q0.z, gsv);
 
-    for (; oi < oe; oi++) {
-        StateVec<S> An, Bn;
-        int4 r0 = p0, r1 = p1;
-        if (PF) {
-            if (oi + 1 < oe) { An.load(vbase + (uint32_t)p0.y, gsv); Bn.load(vbase + (uint32_t)p0.z, gsv); }
-            if (oi + 2 < oe) { r0 = __ldg(opv + 2 * oi + 4); r1 = __ldg(opv + 2 * oi + 5); }
-        }
-        const int src = q0.x, out1 = q0.w, out2 = q1.x, dst1 = q1.y, dst2 = q1.z;
-        StateVec<S> Uv;
-        if (src >= 0) Uv.load_shared(sstack + (uint32_t)src * kSlotBytes);
-        else Uv.load(vbase + (uint32_t)(~src), gsv);
-        uint32_t U[S], A[S], B[S];
-        Uv.unpack(U); Av.unpack(A); Bv.unpack(B);
-        if ((out1 & dst1) >= 0) scan_child<S>(U, B, A, Sv, out1, dst1, sstack, lane, out);   // child 1, sibling B
-        if ((out2 & dst2) >= 0) scan_child<S>(U, A, B, Sv, out2, dst2, sstack, lane, out);   // child 2, sibling A
-        if (PF) {
-            Av = An; Bv = Bn;
-        } else if (oi + 1 < oe) {
-            if (oi + 2 < oe) { r0 = __ldg(opv + 2 * oi + 4); r1 = __ldg(opv + 2 * oi + 5); }
-            Av.load(vbase + (uint32_t)p0.y, gsv);
-            Bv.load(vbase + (uint32_t)p0.z, gsv);
-        }
-        q0 = p0; q1 = p1; p0 = r0; p1 = r1;
+    int2 f0 = __ldg(offs + oi);
+    int2 f1 = f0;
+    if (oi + 1 < oe) f1 = __ldg(offs + oi + 1);
+    StateVec<S> A0, B0, A1, B1;
+    A0.load(vbase + (uint32_t)f0.x, gsv);
+    B0.load(vbase + (uint32_t)f0.y, gsv);
+
+#define MPGPU_SCAN_STEP(AC, BC, AN, BN, FCUR, FNEXT, FLOAD)                                            \
+    {                                                                                                  \
+        if (PF) {                                                                                      \
+            if (oi + 1 < oe) { AN.load(vbase + (uint32_t)FNEXT.x, gsv); BN.load(vbase + (uint32_t)FNEXT.y, gsv); } \
+        } else {                                                                                       \
+            AC.load(vbase + (uint32_t)FCUR.x, gsv); BC.load(vbase + (uint32_t)FCUR.y, gsv);            \
+        }                                                                                              \
+        if (oi + 2 < oe) FLOAD = __ldg(offs + oi + 2);                                                 \
+        const int2 cw = __ldg(ctl + oi);                                                               \
+        const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;       \
+        const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;                                  \
+        StateVec<S> Uv;                                                                                \
+        if (src < 0xfe) Uv.load_shared(sstack + src * kSlotBytes);                                     \
+        else Uv.load(vbase + (uint32_t)(src == 0xff ? t0.z : t0.y), gsv);                              \
+        uint32_t U[S], A[S], B[S];                                                                     \
+        Uv.unpack(U); AC.unpack(A); BC.unpack(B);                                                      \
+        if (o1 != 0xffff || dst1 != 0xff)                                                              \
+            scan_child<S>(U, B, A, Sv, o1 != 0xffff, outc + o1, dst1 != 0xff, sstack + dst1 * kSlotBytes, lane0); \
+        if (o2 != 0xffff || dst2 != 0xff)                                                              \
+            scan_child<S>(U, A, B, Sv, o2 != 0xffff, outc + o2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0); \
     }
+
+    for (;;) {
+        MPGPU_SCAN_STEP(A0, B0, A1, B1, f0, f1, f0)
+        if (++oi >= oe) break;
+        MPGPU_SCAN_STEP(A1, B1, A0, B0, f1, f0, f1)
+        if (++oi >= oe) break;
+    }
+#undef MPGPU_SCAN_STEP
 }
 
 template <int S>
@@ -439,7 +464,8 @@ static int launch_scan_t(Ctx *c, int ntasks, int nslots)
     typedef typename VecOf<S>::T V;
     constexpr bool PF = S <= 4;
     const size_t per_warp = (size_t)(nslots > 0 ? nslots : 1) * Lay<S>::G * 32 * sizeof(V);
-    int wpb = 8;
+    int wpb = 4;           // small CTAs: ragged task lengths retire early, measured best on B200 (profiles/)
+    if (const char *e = getenv("MPGPU_SCAN_WPB")) { int v = atoi(e); if (v >= 1 && v <= 32) wpb = v; }   // tuning knob
     const size_t budget = 96 * 1024;
     while (wpb > 1 && per_warp * wpb > budget) wpb >>= 1;
     const size_t smem = per_warp * wpb;
@@ -453,7 +479,8 @@ static int launch_scan_t(Ctx *c, int ntasks, int nslots)
     const long long blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
     k_spr_scan<S, PF><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const V *>(c->d_views), c->Wl,
-                                                                       c->d_tasks, ntasks, c->d_ops,
+                                                                       c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs),
+                                                                       reinterpret_cast<const int2 *>(c->d_ctl),
                                                                        nslots > 0 ? nslots : 1, c->d_counts);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());

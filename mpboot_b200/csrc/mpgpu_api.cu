@@ -198,11 +198,14 @@ static int need_tree(Ctx *c, bool lens)
 static int upload_plan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
-    if (int rc = ensure(c->d_ops, c->ops_cap, pl.ops.size() + 1)) return rc;
+    if (int rc = ensure(c->d_offs, c->offs_cap, pl.offs.size() + 1)) return rc;
+    if (int rc = ensure(c->d_ctl, c->ctl_cap, pl.ctl.size() + 1)) return rc;
     if (int rc = ensure(c->d_tasks, c->tasks_cap, pl.tasks.size() + 1)) return rc;
     if (int rc = ensure(c->d_counts, c->counts_cap, (size_t)pl.n_cand + pl.tasks.size() + 1)) return rc;
-    if (!pl.ops.empty())
-        MPGPU_CUDA(cudaMemcpyAsync(c->d_ops, pl.ops.data(), pl.ops.size() * sizeof(ScanOp), cudaMemcpyHostToDevice, c->stream));
+    if (!pl.offs.empty()) {
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_offs, pl.offs.data(), pl.offs.size() * sizeof(ScanOffs), cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_ctl, pl.ctl.data(), pl.ctl.size() * sizeof(ScanCtl), cudaMemcpyHostToDevice, c->stream));
+    }
     if (!pl.tasks.empty())
         MPGPU_CUDA(cudaMemcpyAsync(c->d_tasks, pl.tasks.data(), pl.tasks.size() * sizeof(ScanTask), cudaMemcpyHostToDevice, c->stream));
     return 0;
@@ -282,7 +285,8 @@ int mpgpu_destroy(mpgpu_ctx *c)
     free_alignment(c);
     if (c->d_triples) cudaFree(c->d_triples);
     if (c->d_scalar) cudaFree(c->d_scalar);
-    if (c->d_ops) cudaFree(c->d_ops);
+    if (c->d_offs) cudaFree(c->d_offs);
+    if (c->d_ctl) cudaFree(c->d_ctl);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->d_bitcnt) cudaFree(c->d_bitcnt);
@@ -520,7 +524,7 @@ int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, in
 int64_t mpgpu_scan_plan_bytes(mpgpu_ctx *c)
 {
     if (!c) return 0;
-    return (int64_t)(c->plan.ops.size() * sizeof(ScanOp) + c->plan.tasks.size() * sizeof(ScanTask));
+    return (int64_t)(c->plan.offs.size() * (sizeof(ScanOffs) + sizeof(ScanCtl)) + c->plan.tasks.size() * sizeof(ScanTask));
 }
 
 int mpgpu_scan_launch(mpgpu_ctx *c, void **dev_counts)

@@ -44,24 +44,26 @@ struct HostTree {
 struct Triple { int32_t dst, a, b, pad; };
 
 // ---- scan program (built on the host, interpreted by k_spr_scan) ------------------------
-struct ScanOp {
-    int32_t src;        // >= 0: stack slot holding U of the node being expanded; < 0: ~view offset
-    int32_t c1, c2;     // views of the two children (pointing at the expanded node), as offsets
-                        // in vector units (vid * view_stride / SG) so the kernel adds, not multiplies
-    int32_t out1, out2; // output slot of the insertion into the child's branch (-1: not scored)
-    int32_t dst1, dst2; // stack slot receiving the child's up-view (-1: child is not expanded)
-    int32_t pad;
+// One "expand" op per expanded node, as two parallel streams (see k_spr_scan):
+struct ScanOffs { int32_t c1, c2; };   // views of the two children (pointing at the expanded node) as
+                                       // offsets in vector units (vid * view_stride / SG): the kernel adds
+struct ScanCtl {
+    uint32_t outs;      // out1 | out2 << 16: candidate index relative to the task's first (0xFFFF: not scored)
+    uint32_t meta;      // src | dst1 << 8 | dst2 << 16: stack slots (0xFF none); src 0xFF / 0xFE = the
+                        // task's D2 / D1 view (top-level expansions)
 };
 struct ScanTask {
-    int32_t s_vid;      // pruned subtree (view offset in vector units, like ScanOp::c1)
+    int32_t s_vid;      // pruned subtree (view offset in vector units)
     int32_t d1, d2;     // the two views that become neighbours when the node is removed (offsets)
     int32_t op_begin, op_end;
     int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge)
-    int32_t pad0, pad1;
+    int32_t cand_base;  // first candidate (output slot) of this task
+    int32_t pad;
 };
 
 struct ScanPlan {
-    std::vector<ScanOp> ops;
+    std::vector<ScanOffs> offs;
+    std::vector<ScanCtl> ctl;
     std::vector<ScanTask> tasks;
     std::vector<int32_t> visit_begin;     // count+1
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
@@ -105,7 +107,8 @@ struct Ctx {
 
     // scan
     ScanPlan plan;
-    ScanOp *d_ops = nullptr; size_t ops_cap = 0;
+    ScanOffs *d_offs = nullptr; size_t offs_cap = 0;
+    ScanCtl *d_ctl = nullptr; size_t ctl_cap = 0;
     ScanTask *d_tasks = nullptr; size_t tasks_cap = 0;
     int32_t *d_counts = nullptr; size_t counts_cap = 0;
     std::vector<int32_t> h_counts;

@@ -159,7 +159,7 @@ def test_full_size_properties_c2_slice():
     assert o.evaluate_full(False) == s
     order = eng.visit_order()
     vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, 6)
-    assert len(mp) > 10000 and mp.min() >= s - 3000
+    assert len(mp) > 10000 and mp.min() >= 0.9 * s
     # spot-check three visits against the oracle (needs per-site mode for the recorder)
     o2 = portlib.OracleEngine(c["codes"], c["weights"], 1); o2.set_ring(c["bn"], c["bs"]); o2.allocate(True)
     s2 = o2.evaluate_full(True)
