@@ -144,6 +144,76 @@ int mpgpu_optimize_spr(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot,
                        int mintrav, int maxtrav, mpgpu_rng_fn rng, void *rng_user,
                        uint32_t *best, int64_t *n_insertions);
 
+/* ---- R8: replicate scoring, the REPS block of IQTree::saveCurrentTree (iqtree.cpp:3356-3449) ----
+ * boot_samples: [B][stride] u16, boot_samples_pars exactly as IQTree::setParams fills it
+ * (iqtree.cpp:220-233, 285-313; stride >= number of reported patterns); segment_upper/nseg
+ * from IQTree::doSegmenting (iqtree.cpp:3793).  The weights stay resident on the device.
+ * Results are the reference's integers, including the 16-bit wrap of each segment sum
+ * (vectorclass/vectori256.h:1726-1740): segments that provably cannot reach 2^16 on any tree
+ * and weights <= 255 run on the int8 tensor cores, everything else through an exact
+ * CUDA-core path (mpgpu_reps_info reports the split). */
+int mpgpu_load_replicates(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples, int stride,
+                          const int32_t *segment_upper, int nseg);
+/* groups = 1 + wrap-prone segments, exceptions = patterns on the exact CUDA-core path,
+ * tensor = 1 when the tcgen05 path is enabled.  Any pointer may be NULL. */
+int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
+/* Options: "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests). */
+int mpgpu_set_option(mpgpu_ctx *ctx, const char *name, int value);
+/* res[b] = -rell[b] of the CURRENT tree for b < B (what the loop at :3424-3449 leaves in `res`
+ * when no replicate is skipped).  Single shard. */
+int mpgpu_reps_current_tree(mpgpu_ctx *ctx, int32_t *res);
+/* The same for candidates of the last mpgpu_scan_visits / mpgpu_scan_plan batch: cand_idx[i]
+ * indexes mp[] of that batch (-1 = the current tree); res is [m][B].  This is the REPS vector
+ * saveCurrentTree would compute inside testInsertParsimony (:2163-2166) for that insertion.
+ * Single shard. */
+int mpgpu_reps_candidates(mpgpu_ctx *ctx, const int32_t *cand_idx, int m, int32_t *res);
+
+/* ---- pllOptimizeSprParsimony under -bb: search + saveCurrentTree, default policy ----
+ * Replaces the pair pllOptimizeSprParsimony (sprparsimony.cpp:3244) / IQTree::saveCurrentTree
+ * (iqtree.cpp:3271-3760) for maximum_parsimony && spr_parsimony with !store_candidate_trees,
+ * !multiple_hits, distinct_iter_top_boot < 1, outside ratchet iterations.  Every scored
+ * insertion and, once per node visit, the current tree (:2286-2289) goes through the cutoff
+ * filter (:3343), is appended to treels_logl (push_tree_logl), gets its REPS vector from the
+ * device and updates boot_logl / boot_counts / boot_trees exactly as :3687-3731, drawing
+ * random_double() for ties in the reference's order.  When a candidate wins its first
+ * replicate the host materialises it (`materialize`, :3692-3708): it receives the current
+ * ring tables and the move (remove_ref regrafted on insert_ref; 0,0 = the current tree)
+ * and returns the tree index to store in boot_trees (the treels lookup is the host's). */
+typedef struct mpgpu_bb_hooks {
+    void *user;
+    double (*random_double)(void *user);
+    int32_t (*push_tree_logl)(void *user, double cur_logl);
+    int32_t (*materialize)(void *user, const int32_t *back_node, const int32_t *back_slot,
+                           int32_t remove_ref, int32_t insert_ref, int32_t tree_index);
+} mpgpu_bb_hooks;
+typedef struct mpgpu_bb_state {
+    int32_t B;
+    double *boot_logl;        /* [B] in/out */
+    int32_t *boot_counts;     /* [B] in/out */
+    int32_t *boot_trees;      /* [B] in/out */
+    double logl_cutoff;       /* IQTree::logl_cutoff (0.0 = no filter) */
+    double ufboot_epsilon;    /* Params::ufboot_epsilon (0.5) */
+    int64_t n_calls;          /* out: saveCurrentTree calls */
+    int64_t n_reps;           /* out: calls that passed the cutoff (REPS vectors computed and used) */
+} mpgpu_bb_state;
+int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
+                          const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,
+                          uint32_t *best, int64_t *n_insertions);
+
+/* ---- host-side helper: a minimal treels / treels_logl container (iqtree.h) ----
+ * For hosts that do not bring their own (tests, bench.py): collects treels_logl, keys
+ * materialised trees by a canonical topology hash like the treels map (iqtree.cpp:3299-3312,
+ * 3701-3708), forwards random_double to `rng`.  mpgpu_treels_materialized returns
+ * [k][4] = remove_ref, insert_ref, tree_index, topology hash per materialised tree. */
+typedef struct mpgpu_treels mpgpu_treels;
+mpgpu_treels *mpgpu_treels_create(int ntaxa);
+void mpgpu_treels_destroy(mpgpu_treels *t);
+int64_t mpgpu_treels_size(const mpgpu_treels *t);
+void mpgpu_treels_logl(const mpgpu_treels *t, double *out);
+int64_t mpgpu_treels_num_materialized(const mpgpu_treels *t);
+void mpgpu_treels_materialized(const mpgpu_treels *t, int64_t *out);
+void mpgpu_treels_hooks(mpgpu_treels *t, mpgpu_rng_fn rng, void *rng_user, mpgpu_bb_hooks *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -340,9 +340,12 @@ template <int S> struct StateVec {
 };
 
 // Scores one child: Uc = fitch(U, X) (X = sibling view), optional store of Uc, optional count.
-template <int S>
+// ROWS: instead of counting, the mismatch bits of the insertion (the candidate's per-site
+// delta row under -bb) go to rowp[0] when rowp is not null.
+template <int S, bool ROWS>
 __device__ __forceinline__ void scan_child(const uint32_t (&U)[S], const uint32_t (&X)[S], const uint32_t (&C)[S],
                                            const uint32_t (&Sv)[S], bool do_out, int32_t *__restrict__ outp,
+                                           uint32_t *__restrict__ rowp,
                                            bool do_dst, uint32_t dst_addr, bool lane0)
 {
     const uint32_t n = any_and<S>(U, X);
@@ -358,8 +361,12 @@ __device__ __forceinline__ void scan_child(const uint32_t (&U)[S], const uint32_
         uint32_t z = 0;
 #pragma unroll
         for (int k = 0; k < S; k++) z |= fitch1(Uc[k], C[k], m) & Sv[k];
-        const int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
-        if (lane0) atomicAdd(outp, cnt);
+        if (ROWS) {
+            if (rowp) *rowp = ~z;
+        } else {
+            const int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
+            if (lane0) atomicAdd(outp, cnt);
+        }
     }
 }
 
@@ -375,11 +382,16 @@ __device__ __forceinline__ void pin(const void *&x) { asm volatile("" : "+l"(x))
 //             y: src | dst1 << 8 | dst2 << 16   (stack slots; 0xFF = none;
 //                src 0xFF / 0xFE = the task's D2 / D1 view for the two top-level expansions)
 // PF = also software-prefetch op i+1's child views into a second register set (small S only).
-template <int S, bool PF>
+// ROWS = the -bb second pass: for the candidates with row_of[candidate] >= 0 the per-site
+// mismatch row is written to rows[row_of][Wl] instead of counting (tasks = only those that
+// have such a candidate; task_ids maps the dense task index to the plan's task).
+template <int S, bool PF, bool ROWS>
 __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int Wl,
                            const ScanTask *__restrict__ tasks, int ntasks,
                            const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
-                           int nslots, int32_t *__restrict__ out)
+                           int nslots, int32_t *__restrict__ out,
+                           const int32_t *__restrict__ task_ids, const int32_t *__restrict__ row_of,
+                           uint32_t *__restrict__ rows)
 {
     typedef typename VecOf<S>::T V;
     extern __shared__ uint4 smem4[];
@@ -389,7 +401,8 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     const unsigned nchunks = Wl / kChunkWords;
     if (gw >= (unsigned)ntasks * nchunks) return;
     const unsigned chunk = gw / (unsigned)ntasks;
-    const unsigned ti = gw - chunk * (unsigned)ntasks;
+    unsigned ti = gw - chunk * (unsigned)ntasks;
+    if (ROWS) ti = (unsigned)__ldg(task_ids + ti);
     const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
     const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
     const uint32_t gsv = (uint32_t)Wl;                                       // group stride in vectors
@@ -402,6 +415,8 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     pin(sstack);
     const bool lane0 = lane == 0;
     int32_t *outc = out + t1.z;                                              // candidates of this task
+    const int32_t *rowc = ROWS ? row_of + t1.z : nullptr;
+    uint32_t *rowbase = ROWS ? rows + (size_t)chunk * kChunkWords + lane : nullptr;
 
     uint32_t Sv[S];
     {
@@ -412,8 +427,10 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
         a.unpack(Sv);
         uint32_t d1[S], d2[S];
         b.unpack(d1); c.unpack(d2);
-        const int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(d1, d2)));
-        if (lane0) atomicAdd(&out[t1.y], cnt);
+        if (!ROWS) {
+            const int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(d1, d2)));
+            if (lane0) atomicAdd(&out[t1.y], cnt);
+        }
     }
 
     int oi = t0.w;
@@ -443,10 +460,15 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
         else Uv.load(vbase + (uint32_t)(src == 0xff ? t0.z : t0.y), gsv);                              \
         uint32_t U[S], A[S], B[S];                                                                     \
         Uv.unpack(U); AC.unpack(A); BC.unpack(B);                                                      \
+        uint32_t *rp1 = nullptr, *rp2 = nullptr;                                                       \
+        if (ROWS) {                                                                                    \
+            if (o1 != 0xffff) { const int r = __ldg(rowc + o1); if (r >= 0) rp1 = rowbase + (size_t)r * Wl; } \
+            if (o2 != 0xffff) { const int r = __ldg(rowc + o2); if (r >= 0) rp2 = rowbase + (size_t)r * Wl; } \
+        }                                                                                              \
         if (o1 != 0xffff || dst1 != 0xff)                                                              \
-            scan_child<S>(U, B, A, Sv, o1 != 0xffff, outc + o1, dst1 != 0xff, sstack + dst1 * kSlotBytes, lane0); \
+            scan_child<S, ROWS>(U, B, A, Sv, o1 != 0xffff, outc + o1, rp1, dst1 != 0xff, sstack + dst1 * kSlotBytes, lane0); \
         if (o2 != 0xffff || dst2 != 0xff)                                                              \
-            scan_child<S>(U, A, B, Sv, o2 != 0xffff, outc + o2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0); \
+            scan_child<S, ROWS>(U, A, B, Sv, o2 != 0xffff, outc + o2, rp2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0); \
     }
 
     for (;;) {
@@ -458,7 +480,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
 #undef MPGPU_SCAN_STEP
 }
 
-template <int S>
+template <int S, bool ROWS>
 static int launch_scan_t(Ctx *c, int ntasks, int nslots)
 {
     typedef typename VecOf<S>::T V;
@@ -472,16 +494,16 @@ static int launch_scan_t(Ctx *c, int ntasks, int nslots)
     if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         configured = 200 * 1024;
     }
     const long long warps = (long long)ntasks * (c->Wl / kChunkWords);
     const long long blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
-    k_spr_scan<S, PF><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const V *>(c->d_views), c->Wl,
-                                                                       c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs),
-                                                                       reinterpret_cast<const int2 *>(c->d_ctl),
-                                                                       nslots > 0 ? nslots : 1, c->d_counts);
+    k_spr_scan<S, PF, ROWS><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
+        reinterpret_cast<const V *>(c->d_views), c->Wl, c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs),
+        reinterpret_cast<const int2 *>(c->d_ctl), nslots > 0 ? nslots : 1, c->d_counts,
+        ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, ROWS ? c->d_rows_site : nullptr);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;
@@ -491,10 +513,23 @@ int launch_scan(Ctx *c, int ntasks, int nslots)
 {
     if (ntasks == 0) return 0;
     switch (c->S) {
-    case 2:  return launch_scan_t<2>(c, ntasks, nslots);
-    case 4:  return launch_scan_t<4>(c, ntasks, nslots);
-    case 20: return launch_scan_t<20>(c, ntasks, nslots);
-    case 32: return launch_scan_t<32>(c, ntasks, nslots);
+    case 2:  return launch_scan_t<2, false>(c, ntasks, nslots);
+    case 4:  return launch_scan_t<4, false>(c, ntasks, nslots);
+    case 20: return launch_scan_t<20, false>(c, ntasks, nslots);
+    case 32: return launch_scan_t<32, false>(c, ntasks, nslots);
+    default: set_error("unsupported state count"); return 1;
+    }
+}
+
+// -bb second pass over the tasks listed in d_row_tasks (see k_spr_scan<ROWS>)
+int launch_scan_rows(Ctx *c, int ntasks, int nslots)
+{
+    if (ntasks == 0) return 0;
+    switch (c->S) {
+    case 2:  return launch_scan_t<2, true>(c, ntasks, nslots);
+    case 4:  return launch_scan_t<4, true>(c, ntasks, nslots);
+    case 20: return launch_scan_t<20, true>(c, ntasks, nslots);
+    case 32: return launch_scan_t<32, true>(c, ntasks, nslots);
     default: set_error("unsupported state count"); return 1;
     }
 }

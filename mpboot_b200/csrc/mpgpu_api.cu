@@ -17,18 +17,6 @@ int cuda_fail(cudaError_t e, const char *what)
     return 2;
 }
 
-template <typename T>
-static int ensure(T *&ptr, size_t &cap, size_t need)
-{
-    if (need <= cap && ptr) return 0;
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr; cap = 0;
-    size_t want = need + need / 4 + 16;
-    MPGPU_CUDA(cudaMalloc((void **)&ptr, want * sizeof(T)));
-    cap = want;
-    return 0;
-}
-
 static int states_of(int datatype)
 {
     switch (datatype) {
@@ -120,11 +108,13 @@ static int build_planes(Ctx *c, bool realloc_views)
     else MPGPU_CUDA(cudaMemsetAsync(c->d_views, 0xff, (size_t)c->n * c->view_stride * sizeof(uint32_t), c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // host staging vectors go out of scope
     c->lens_valid = false;
+    c->ptn_site_valid = false;
+    c->reps.tree_valid = false;
     return 0;
 }
 
 // level schedule of all directed views + launch (one kernel per level)
-static int compute_views(Ctx *c)
+int compute_views(Ctx *c)
 {
     const HostTree &t = c->tree;
     const int n = t.n;
@@ -170,6 +160,7 @@ static int compute_views(Ctx *c)
         if (int rc = launch_level(c, c->d_triples + off, (int)lv.size())) return rc;
         off += lv.size();
     }
+    c->reps.tree_valid = false;
     c->vcount.assign(nviews, 0);
     MPGPU_CUDA(cudaMemcpyAsync(c->vcount.data(), c->d_vcount, nviews * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -177,7 +168,7 @@ static int compute_views(Ctx *c)
 }
 
 // subtree lengths from (all-reduced) mismatch counts, in level order
-static void compute_lengths(Ctx *c)
+void compute_lengths(Ctx *c)
 {
     const int nviews = 4 * c->n - 6;
     c->vlen.assign(nviews, 0);
@@ -186,7 +177,7 @@ static void compute_lengths(Ctx *c)
     c->lens_valid = true;
 }
 
-static int need_tree(Ctx *c, bool lens)
+int need_tree(Ctx *c, bool lens)
 {
     if (!c) { set_error("null context"); return 1; }
     if (!c->d_views) { set_error("no alignment loaded"); return 1; }
@@ -195,7 +186,7 @@ static int need_tree(Ctx *c, bool lens)
     return 0;
 }
 
-static int upload_plan(Ctx *c)
+int upload_plan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
     if (int rc = ensure(c->d_offs, c->offs_cap, pl.offs.size() + 1)) return rc;
@@ -211,7 +202,7 @@ static int upload_plan(Ctx *c)
     return 0;
 }
 
-static int run_scan(Ctx *c)
+int run_scan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
     const size_t nout = (size_t)pl.n_cand + pl.tasks.size();
@@ -219,7 +210,7 @@ static int run_scan(Ctx *c)
     return launch_scan(c, (int)pl.tasks.size(), pl.max_slot);
 }
 
-static int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
+int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
 {
     ScanPlan &pl = c->plan;
     if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
@@ -237,11 +228,51 @@ static int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand
     return 0;
 }
 
+
+// Per-site mismatch counters of the current tree, bit-sliced, in d_bitcnt[nbits][Wl]: child-view
+// pairs of the n-2 inner views facing tr->start, plus the start edge (storePerSiteNodeScores :294).
+int compute_site_counters(Ctx *c, int nbits)
+{
+    const HostTree &t = c->tree;
+    const int n = c->n;
+    std::vector<int32_t> order;
+    visit_order(t, order);
+    std::vector<int32_t> pairs;
+    for (int i = n + 1; i <= 2 * n - 2; i++) {
+        const int r = order[i];
+        pairs.push_back(t.vid(t.back(t.next(r))));
+        pairs.push_back(t.vid(t.back(t.next(t.next(r)))));
+    }
+    pairs.push_back(t.vid(3)); pairs.push_back(t.vid(t.back(3)));
+    const int npairs = (int)pairs.size() / 2;
+    if (int rc = ensure(c->d_pairs, c->pairs_cap, pairs.size())) return rc;
+    if (int rc = ensure(c->d_bitcnt, c->bitcnt_cap, (size_t)16 * c->Wl)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_pairs, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_site_counters(c, npairs, nbits)) return rc;
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // `pairs` goes out of scope
+    return 0;
+}
+
+// Site of each reported pattern: the reference walks site += aliaswgt[ptn] over the prefix
+// (pllComputePatternParsimony :3380-3390); -1 = beyond the reference's padded plane.
+int ensure_ptn_site(Ctx *c)
+{
+    if (c->ptn_site_valid) return 0;
+    const int upper = c->sort_alignment ? c->n_inf : c->P;
+    std::vector<int64_t> ptn_site(upper > 0 ? upper : 1);
+    int64_t site = 0;
+    for (int i = 0; i < upper; i++) { ptn_site[i] = site < (int64_t)c->ref_words * 32 ? site : -1; site += c->weights[i]; }
+    if (int rc = ensure(c->d_ptn_site, c->ptn_site_cap, ptn_site.size())) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_ptn_site, ptn_site.data(), ptn_site.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->ptn_site_valid = true;
+    return 0;
+}
+
 }  // namespace mpgpu
 
 using namespace mpgpu;
 
-struct mpgpu_ctx : public mpgpu::Ctx {};
 
 extern "C" {
 
@@ -293,6 +324,7 @@ int mpgpu_destroy(mpgpu_ctx *c)
     if (c->d_pairs) cudaFree(c->d_pairs);
     if (c->d_ptn) cudaFree(c->d_ptn);
     if (c->d_ptn_site) cudaFree(c->d_ptn_site);
+    free_reps(c);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -311,6 +343,7 @@ int mpgpu_load_alignment(mpgpu_ctx *c, int ntaxa, int npatterns, int datatype,
     if (ntaxa < 4 || npatterns < 1) { set_error("need at least 4 taxa and 1 pattern"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     free_alignment(c);
+    free_reps(c);
     c->n = ntaxa; c->P = npatterns; c->datatype = datatype; c->S = S; c->sort_alignment = sort_alignment;
     c->weights.assign(aliaswgt, aliaswgt + npatterns);
     for (int i = 0; i < npatterns; i++) if (aliaswgt[i] < 0) { set_error("negative pattern weight"); return 1; }
@@ -459,33 +492,11 @@ int mpgpu_pattern_parsimony(mpgpu_ctx *c, uint16_t *ptn_pars, int32_t *sum)
     if (int rc = need_tree(c, false)) return rc;
     if (!ptn_pars) { set_error("null argument"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
-    const HostTree &t = c->tree;
-    const int n = c->n;
-    // child-view pairs of the n-2 inner views facing tr->start, plus the start edge
-    std::vector<int32_t> order;
-    visit_order(t, order);
-    std::vector<int32_t> pairs;
-    for (int i = n + 1; i <= 2 * n - 2; i++) {
-        const int r = order[i];
-        pairs.push_back(t.vid(t.back(t.next(r))));
-        pairs.push_back(t.vid(t.back(t.next(t.next(r)))));
-    }
-    pairs.push_back(t.vid(3)); pairs.push_back(t.vid(t.back(3)));
-    const int npairs = (int)pairs.size() / 2;
     const int nbits = 16;
-    if (int rc = ensure(c->d_pairs, c->pairs_cap, pairs.size())) return rc;
-    if (int rc = ensure(c->d_bitcnt, c->bitcnt_cap, (size_t)nbits * c->Wl)) return rc;
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_pairs, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    if (int rc = launch_site_counters(c, npairs, nbits)) return rc;
-
-    // site of each reported pattern: the reference walks site += aliaswgt[ptn] over the prefix
+    if (int rc = compute_site_counters(c, nbits)) return rc;
+    if (int rc = ensure_ptn_site(c)) return rc;
     const int upper = c->sort_alignment ? c->n_inf : c->P;                // :3380-3381
-    std::vector<int64_t> ptn_site(upper > 0 ? upper : 1);
-    int64_t site = 0;
-    for (int i = 0; i < upper; i++) { ptn_site[i] = site < (int64_t)c->ref_words * 32 ? site : -1; site += c->weights[i]; }
-    if (int rc = ensure(c->d_ptn_site, c->ptn_site_cap, ptn_site.size())) return rc;
-    if (int rc = ensure(c->d_ptn, c->ptn_cap, ptn_site.size())) return rc;
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_ptn_site, ptn_site.data(), ptn_site.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper > 0 ? upper : 1))) return rc;
     if (int rc = launch_gather_patterns(c, nbits, upper)) return rc;
     if (upper > 0)
         MPGPU_CUDA(cudaMemcpyAsync(ptn_pars, c->d_ptn, (size_t)upper * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
@@ -555,81 +566,6 @@ int mpgpu_scan_visits(mpgpu_ctx *c, const int32_t *order, int first, int count, 
     if (nc > capacity) { set_error("candidate capacity too small"); return 1; }
     if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
     return mpgpu_scan_finish(c, visit_begin, mp, cand_ref, cand_prune, capacity);
-}
-
-// pllOptimizeSprParsimony (sprparsimony.cpp:3244-3319) with the node loop's scoring batched on
-// the device.  Speculation: the candidates of the next K visits are scored against the current
-// tree; the host replays testInsertParsimony's bookkeeping (:2168-2176) and the node loop's
-// acceptance test (:3306-3314) strictly in order, and throws the rest of a batch away as soon
-// as a move is applied (the only event that changes any score).
-int mpgpu_optimize_spr(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
-                       mpgpu_rng_fn rng, void *rng_user, uint32_t *best, int64_t *n_insertions)
-{
-    if (!c || !back_node || !back_slot || !rng || !best) { set_error("null argument"); return 1; }
-    if (c->shard_count != 1) { set_error("mpgpu_optimize_spr is single-shard in this version"); return 1; }
-    if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
-    if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
-    const int n = c->n, nvisit = 2 * n - 2;
-    uint32_t score = 0;
-    if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
-    uint32_t bestParsimony = score;
-    uint32_t randomMP = bestParsimony, startMP = 0;
-    unsigned int bestIterationScoreHits = 1;
-    int64_t scored = 0;
-    std::vector<int32_t> order, vbegin, cref, cprune;
-    std::vector<uint32_t> mp;
-    do {
-        startMP = randomMP;
-        visit_order(c->tree, order);                              // nodeRectifierPars :3297
-        int i = 1;
-        int batch = 16;
-        while (i <= nvisit) {
-            int count = std::min(batch, nvisit - i + 1);
-            int nc = 0, nt = 0;
-            if (int rc = mpgpu_scan_plan(c, order.data(), i, count, mintrav, maxtrav, &nc, &nt)) return rc;
-            vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
-            if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
-            if (int rc = mpgpu_scan_finish(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
-            bool moved = false;
-            int v = 0;
-            for (; v < count && !moved; v++) {
-                int insertNode = 0, removeNode = 0;
-                unsigned long bestTreeScoreHits = 1;              // :3303
-                for (int j = vbegin[v]; j < vbegin[v + 1]; j++) {
-                    const uint32_t m = mp[j];
-                    scored++;
-                    if (m < bestParsimony) bestTreeScoreHits = 1;                 // :2168
-                    else if (m == bestParsimony) bestTreeScoreHits++;
-                    if (m < bestParsimony || (m == bestParsimony && rng(rng_user) <= 1.0 / bestTreeScoreHits)) {
-                        bestParsimony = m; insertNode = cref[j]; removeNode = cprune[j];
-                    }
-                }
-                if (bestParsimony == randomMP) bestIterationScoreHits++;          // :3306
-                if (bestParsimony < randomMP) bestIterationScoreHits = 1;
-                if ((bestParsimony < randomMP ||
-                     (bestParsimony == randomMP && rng(rng_user) <= 1.0 / bestIterationScoreHits)) &&
-                    removeNode && insertNode) {
-                    apply_spr_move(c->tree, removeNode, insertNode);              // :3312
-                    randomMP = bestParsimony;
-                    moved = true;
-                }
-            }
-            i += v;
-            if (moved) {
-                c->tree_set = true; c->lens_valid = false;
-                if (int rc = compute_views(c)) return rc;
-                compute_lengths(c);
-                batch = 16;
-            } else {
-                batch = std::min(batch * 2, nvisit);
-            }
-        }
-    } while (randomMP < startMP);
-    memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
-    memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
-    *best = startMP;
-    if (n_insertions) *n_insertions = scored;
-    return 0;
 }
 
 }  // extern "C"

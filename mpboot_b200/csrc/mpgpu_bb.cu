@@ -1,0 +1,537 @@
+// C-ABI layer, part 2: replicate scoring (R8) and pllOptimizeSprParsimony under -bb.
+//
+//   mpgpu_load_replicates      boot_samples_pars + segments -> resident tensor operand, exception lists
+//   mpgpu_reps_current_tree    REPS of the current tree
+//   mpgpu_reps_candidates      REPS of candidates of the last scan batch
+//   mpgpu_optimize_spr(_bb)    the SPR hill-climb; with hooks/state = IQTree::saveCurrentTree's
+//                              default policy replayed on the host in the reference's order
+// No CPU fallback: every number a decision is based on comes from the device kernels.
+#include "mpgpu_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace mpgpu {
+
+void free_reps(Ctx *c)
+{
+    Reps &r = c->reps;
+    void *ptrs[] = {r.d_w8, r.d_w16e, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
+                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_hit_count, r.d_hits};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    const bool use_tensor = r.use_tensor;
+    r = Reps();
+    r.use_tensor = use_tensor;
+    c->d_row_of = nullptr; c->d_row_tasks = nullptr; c->d_rows_site = nullptr;
+}
+
+// K-blocks (128 patterns) whose first expanded site can fall into this shard's word slice
+static void update_kb_range(Ctx *c)
+{
+    Reps &r = c->reps;
+    if (c->shard_count == 1) { r.kb_lo = 0; r.kb_hi = r.Kpad / 128; return; }
+    const int64_t s_lo = c->w0 * 32, s_hi = (c->w0 + c->Wl) * 32;
+    int p_lo = r.upper, p_hi = 0;
+    int64_t site = 0;
+    for (int i = 0; i < r.upper; i++) {
+        if (site >= s_lo && site < s_hi) { if (i < p_lo) p_lo = i; p_hi = i + 1; }
+        site += c->weights[i];
+    }
+    if (p_hi <= p_lo) { r.kb_lo = r.kb_hi = 0; return; }
+    r.kb_lo = p_lo / 128; r.kb_hi = (p_hi + 127) / 128;
+}
+
+static int ensure_rows(Ctx *c, int rows)
+{
+    Reps &r = c->reps;
+    if (rows <= r.row_cap) return 0;
+    const size_t per_row = (size_t)c->Wl * 4 + (size_t)r.Pw * 4 + (size_t)r.G * r.Bpad * 4;
+    size_t budget = (size_t)4 << 30;
+    if (const char *e = getenv("MPGPU_REPS_ROW_BYTES")) { long long v = atoll(e); if (v > 0) budget = (size_t)v; }
+    int limit = (int)std::min<size_t>(budget / per_row, (size_t)1 << 20);
+    if (limit < kTreeRows + 64) limit = kTreeRows + 64;
+    int want = std::max(rows + rows / 2, 1024);
+    if (want > limit) want = limit;
+    if (want <= r.row_cap) return 0;                       // already at the limit: callers chunk
+    if (r.d_rows_site) cudaFree(r.d_rows_site);
+    if (r.d_rows_ptn) cudaFree(r.d_rows_ptn);
+    if (r.d_X) cudaFree(r.d_X);
+    r.d_rows_site = nullptr; r.d_rows_ptn = nullptr; r.d_X = nullptr; r.row_cap = 0; r.tree_valid = false;
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_rows_site, (size_t)want * c->Wl * 4));
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_rows_ptn, (size_t)want * r.Pw * 4));
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_X, (size_t)want * r.G * r.Bpad * 4));
+    r.row_cap = want;
+    c->d_rows_site = r.d_rows_site;
+    return 0;
+}
+
+// rows [row0, row0+nrows) of d_rows_ptn -> X (all groups)
+static int contract_rows(Ctx *c, int row0, int nrows)
+{
+    Reps &r = c->reps;
+    if (nrows == 0) return 0;
+    MPGPU_CUDA(cudaMemsetAsync(r.d_X + (size_t)row0 * r.G * r.Bpad, 0, (size_t)nrows * r.G * r.Bpad * 4, c->stream));
+    if (int rc = launch_reps_exc(c, row0, nrows)) return rc;
+    if (r.use_tensor) { if (int rc = launch_reps_tc(c, row0, nrows)) return rc; }
+    r.rows_scored += nrows;
+    return 0;
+}
+
+// rows 0..15 = bit planes of the per-site counters of the current tree, row 16 = sum_bit 2^bit * plane
+static int refresh_tree_rows(Ctx *c)
+{
+    Reps &r = c->reps;
+    if (int rc = ensure_rows(c, kTreeRows + 64)) return rc;
+    if (r.tree_valid) return 0;
+    const int nbits = 16;
+    if (int rc = compute_site_counters(c, nbits)) return rc;
+    if (int rc = ensure_ptn_site(c)) return rc;
+    update_kb_range(c);
+    if (int rc = launch_gather_rows(c, c->d_bitcnt, r.d_rows_ptn, nbits)) return rc;
+    if (int rc = contract_rows(c, 0, nbits)) return rc;
+    if (int rc = launch_reps_tree_row(c, 0, nbits, kTreeRows - 1)) return rc;
+    r.tree_valid = true;
+    return 0;
+}
+
+// Result of one REPS batch on the host: per call either a dense row or a hit list
+struct RepsOut {
+    int Bpad = 0;
+    std::vector<int32_t> dense;                   // concatenated dense rows [Bpad]
+    std::vector<int64_t> dense_off;               // per call: offset into dense, -1 = hit list
+    std::vector<int32_t> hit_begin;               // per call: [begin, end) into hit_b / hit_res (when dense_off < 0)
+    std::vector<int32_t> hit_end;
+    std::vector<int32_t> hit_b, hit_res;
+};
+
+// REPS vectors for the calls cands[0..m) of the last planned scan batch (-1 = the current tree),
+// in order.  thr (host, [B], nullable): only entries with res <= thr[b] are needed by the caller.
+static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, RepsOut &out)
+{
+    Reps &r = c->reps;
+    const ScanPlan &pl = c->plan;
+    const HostTree &t = c->tree;
+    out.Bpad = r.Bpad;
+    out.dense.clear(); out.hit_b.clear(); out.hit_res.clear();
+    out.dense_off.assign(m, -1); out.hit_begin.assign(m, 0); out.hit_end.assign(m, 0);
+    if (m == 0) return 0;
+    if (int rc = refresh_tree_rows(c)) return rc;
+    // rows the whole list would like to have; ensure_rows clamps to the memory budget
+    {
+        int want = kTreeRows;
+        for (int i = 0; i < m; i++) if (cands[i] >= 0) want += 2;
+        if (int rc = ensure_rows(c, want)) return rc;
+        if (int rc = refresh_tree_rows(c)) return rc;        // a reallocation drops the tree rows
+    }
+    const int max_rows = r.row_cap - kTreeRows;
+    if (thr) {
+        if (!r.d_thr) MPGPU_CUDA(cudaMalloc((void **)&r.d_thr, (size_t)r.Bpad * 4));
+        if (!r.d_hit_count) MPGPU_CUDA(cudaMalloc((void **)&r.d_hit_count, 4));
+        if (!r.d_hits) { r.hit_cap = 1u << 20; MPGPU_CUDA(cudaMalloc((void **)&r.d_hits, (size_t)r.hit_cap * sizeof(int4))); }
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.B * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    std::vector<int32_t> row_of(pl.n_cand > 0 ? pl.n_cand : 1);
+    std::vector<int32_t> task_row(pl.tasks.size()), row_tasks;
+    std::vector<int4> edges;
+    std::vector<int2> calls;
+    std::vector<int4> hits;
+    int done = 0;
+    while (done < m) {
+        // ---- carve a chunk that fits the row buffers ----
+        std::fill(row_of.begin(), row_of.end(), -1);
+        std::fill(task_row.begin(), task_row.end(), -1);
+        row_tasks.clear(); edges.clear(); calls.clear();
+        int nrows = 0, k = done;
+        for (; k < m; k++) {
+            const int j = cands[k];
+            if (j < 0) { calls.push_back(make_int2(-1, -1)); continue; }
+            if (j >= pl.n_cand) { set_error("candidate index out of range"); return 1; }
+            const int ti = pl.cand_task[j];
+            const int need = (task_row[ti] < 0 ? 1 : 0) + (row_of[j] < 0 ? 1 : 0);
+            if (nrows + need > max_rows) break;
+            if (task_row[ti] < 0) {
+                const int pr = pl.cand_prune[j];
+                task_row[ti] = kTreeRows + nrows++;
+                edges.push_back(make_int4(t.vid(pr), t.vid(t.back(pr)), task_row[ti], 0));
+                row_tasks.push_back(ti);
+            }
+            if (row_of[j] < 0) row_of[j] = nrows++;          // relative to the first batch row
+            calls.push_back(make_int2(task_row[ti], kTreeRows + row_of[j]));
+        }
+        if (k == done) { set_error("REPS row buffers too small for a single candidate"); return 1; }
+        const int ncalls = k - done;
+        // ---- upload the chunk ----
+        if (int rc = ensure(r.d_row_of, r.row_of_cap, row_of.size())) return rc;
+        if (int rc = ensure(r.d_row_tasks, r.row_tasks_cap, row_tasks.size() + 1)) return rc;
+        if (int rc = ensure(r.d_edges, r.edges_cap, edges.size() + 1)) return rc;
+        if (int rc = ensure(r.d_calls, r.calls_cap, calls.size())) return rc;
+        if (int rc = ensure(r.d_res, r.res_cap, (size_t)ncalls * r.Bpad)) return rc;
+        c->d_row_of = r.d_row_of; c->d_row_tasks = r.d_row_tasks; c->d_rows_site = r.d_rows_site + (size_t)kTreeRows * c->Wl;
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_calls, calls.data(), calls.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+        if (nrows > 0) {
+            MPGPU_CUDA(cudaMemcpyAsync(r.d_row_of, row_of.data(), row_of.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            MPGPU_CUDA(cudaMemcpyAsync(r.d_row_tasks, row_tasks.data(), row_tasks.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            MPGPU_CUDA(cudaMemcpyAsync(r.d_edges, edges.data(), edges.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+            // ---- rows: edge rows, delta rows (second pass of the scan), site -> pattern space ----
+            if (int rc = launch_edge_rows(c, r.d_edges, (int)edges.size(), r.d_rows_site)) return rc;
+            if (int rc = launch_scan_rows(c, (int)row_tasks.size(), pl.max_slot)) return rc;
+            if (int rc = launch_gather_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl,
+                                            r.d_rows_ptn + (size_t)kTreeRows * r.Pw, nrows)) return rc;
+            if (int rc = contract_rows(c, kTreeRows, nrows)) return rc;
+        }
+        // ---- combine ----
+        if (thr) MPGPU_CUDA(cudaMemsetAsync(r.d_hit_count, 0, 4, c->stream));
+        if (int rc = launch_reps_combine(c, kTreeRows - 1, r.d_calls, ncalls, r.d_res, thr ? r.d_thr : nullptr,
+                                         r.d_hit_count, r.d_hits, r.hit_cap)) return rc;
+        bool dense = true;
+        if (thr) {
+            uint32_t nh = 0;
+            MPGPU_CUDA(cudaMemcpyAsync(&nh, r.d_hit_count, 4, cudaMemcpyDeviceToHost, c->stream));
+            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+            if (nh <= r.hit_cap) {
+                dense = false;
+                hits.resize(nh);
+                if (nh) MPGPU_CUDA(cudaMemcpyAsync(hits.data(), r.d_hits, (size_t)nh * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+                MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+                std::sort(hits.begin(), hits.end(), [](const int4 &a, const int4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+                size_t h = 0;
+                for (int i = 0; i < ncalls; i++) {
+                    out.hit_begin[done + i] = (int32_t)out.hit_b.size();
+                    while (h < hits.size() && hits[h].x == i) { out.hit_b.push_back(hits[h].y); out.hit_res.push_back(hits[h].z); h++; }
+                    out.hit_end[done + i] = (int32_t)out.hit_b.size();
+                }
+            }
+        }
+        if (dense) {
+            const size_t off = out.dense.size();
+            out.dense.resize(off + (size_t)ncalls * r.Bpad);
+            MPGPU_CUDA(cudaMemcpyAsync(out.dense.data() + off, r.d_res, (size_t)ncalls * r.Bpad * 4, cudaMemcpyDeviceToHost, c->stream));
+            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < ncalls; i++) out.dense_off[done + i] = (int64_t)(off + (size_t)i * r.Bpad);
+        }
+        done = k;
+    }
+    return 0;
+}
+
+// ---- the search --------------------------------------------------------------------------------
+struct BBRun {
+    const mpgpu_bb_hooks *hooks;
+    mpgpu_bb_state *st;
+};
+
+static inline bool bb_passes(const mpgpu_bb_state *st, uint32_t mp)
+{
+    const double cur_logl = -(double)mp;
+    return !(st->logl_cutoff != 0.0 && cur_logl <= st->logl_cutoff - 1e-4);          // iqtree.cpp:3343
+}
+
+// IQTree::saveCurrentTree for one call that passed the cutoff (iqtree.cpp:3345-3348, 3687-3731)
+static void bb_save(BBRun *bb, Ctx *c, uint32_t mp, const RepsOut &ro, int call, int remove_ref, int insert_ref)
+{
+    mpgpu_bb_state *st = bb->st;
+    const mpgpu_bb_hooks *hk = bb->hooks;
+    const double cur_logl = -(double)mp, eps = st->ufboot_epsilon;
+    int32_t tree_index = hk->push_tree_logl(hk->user, cur_logl);
+    bool have = false;
+    auto one = [&](int b, int32_t res) {
+        const double rell = -(double)res;
+        const double bl = st->boot_logl[b];
+        if (rell > bl + eps || (rell > bl - eps && hk->random_double(hk->user) <= 1.0 / (st->boot_counts[b] + 1))) {
+            if (!have) {
+                have = true;
+                tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
+            }
+            if (rell > bl) st->boot_counts[b] = 1;
+            st->boot_logl[b] = std::max(bl, rell);
+            st->boot_trees[b] = tree_index;
+        }
+        if (rell == st->boot_logl[b]) st->boot_counts[b]++;
+    };
+    if (ro.dense_off[call] >= 0) {
+        const int32_t *row = ro.dense.data() + ro.dense_off[call];
+        for (int b = 0; b < st->B; b++) one(b, row[b]);
+    } else {
+        for (int h = ro.hit_begin[call]; h < ro.hit_end[call]; h++) one(ro.hit_b[h], ro.hit_res[h]);
+    }
+    st->n_reps++;
+}
+
+}  // namespace mpgpu
+
+using namespace mpgpu;
+
+// pllOptimizeSprParsimony (sprparsimony.cpp:3244-3319) with the node loop's scoring batched on
+// the device.  Speculation: the candidates of the next K visits are scored against the current
+// tree; the host replays testInsertParsimony's bookkeeping (:2168-2176), the saveCurrentTree
+// up-calls (:2163-2166, :2286-2289) and the node loop's acceptance test (:3306-3314) strictly in
+// order, and throws the rest of a batch away as soon as a move is applied (the only event that
+// changes any score).
+static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
+                         mpgpu_rng_fn rng, void *rng_user, BBRun *bb, uint32_t *best, int64_t *n_insertions)
+{
+    if (c->shard_count != 1) { set_error("mpgpu_optimize_spr is single-shard in this version"); return 1; }
+    if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
+    if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
+    const int n = c->n, nvisit = 2 * n - 2;
+    uint32_t score = 0;
+    if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
+    uint32_t bestParsimony = score;
+    uint32_t randomMP = bestParsimony, startMP = 0;
+    uint32_t cur_score = score;                                     // score of the tree in c->tree
+    unsigned int bestIterationScoreHits = 1;
+    int64_t scored = 0;
+    std::vector<int32_t> order, vbegin, cref, cprune, pass_cands, call_of;
+    std::vector<uint32_t> mp;
+    std::vector<int32_t> thr;
+    RepsOut ro;
+    do {
+        startMP = randomMP;
+        visit_order(c->tree, order);                              // nodeRectifierPars :3297
+        int i = 1;
+        int batch = 16;
+        while (i <= nvisit) {
+            int count = std::min(batch, nvisit - i + 1);
+            int nc = 0, nt = 0;
+            if (int rc = mpgpu_scan_plan(c, order.data(), i, count, mintrav, maxtrav, &nc, &nt)) return rc;
+            vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
+            if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
+            if (int rc = mpgpu_scan_finish(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
+            if (bb) {
+                // every saveCurrentTree call of the batch, in order; call_of[] = index into the REPS results
+                mpgpu_bb_state *st = bb->st;
+                pass_cands.clear();
+                call_of.assign((size_t)count + nc, -1);
+                for (int v = 0; v < count; v++) {
+                    if (bb_passes(st, cur_score)) { call_of[(size_t)v + vbegin[v]] = (int32_t)pass_cands.size(); pass_cands.push_back(-1); }
+                    for (int j = vbegin[v]; j < vbegin[v + 1]; j++)
+                        if (bb_passes(st, mp[j])) { call_of[(size_t)v + 1 + j] = (int32_t)pass_cands.size(); pass_cands.push_back(j); }
+                }
+                thr.resize(st->B);
+                for (int b = 0; b < st->B; b++) {
+                    const double lim = std::floor(-st->boot_logl[b] + st->ufboot_epsilon);
+                    thr[b] = lim >= 2147483647.0 ? 2147483647 : (lim <= -2147483648.0 ? (int32_t)-2147483647 - 1 : (int32_t)lim);
+                }
+                if (int rc = reps_run(c, pass_cands.data(), (int)pass_cands.size(), thr.data(), ro)) return rc;
+            }
+            bool moved = false;
+            int v = 0;
+            for (; v < count && !moved; v++) {
+                int insertNode = 0, removeNode = 0;
+                unsigned long bestTreeScoreHits = 1;              // :3303
+                if (bb) {                                         // rearrangeParsimony :2286-2289
+                    bb->st->n_calls++;
+                    const int k = call_of[(size_t)v + vbegin[v]];
+                    if (k >= 0) bb_save(bb, c, cur_score, ro, k, 0, 0);
+                }
+                for (int j = vbegin[v]; j < vbegin[v + 1]; j++) {
+                    const uint32_t m = mp[j];
+                    scored++;
+                    if (bb) {                                     // testInsertParsimony :2163-2166
+                        bb->st->n_calls++;
+                        const int k = call_of[(size_t)v + 1 + j];
+                        if (k >= 0) bb_save(bb, c, m, ro, k, cprune[j], cref[j]);
+                    }
+                    if (m < bestParsimony) bestTreeScoreHits = 1;                 // :2168
+                    else if (m == bestParsimony) bestTreeScoreHits++;
+                    if (m < bestParsimony || (m == bestParsimony && rng(rng_user) <= 1.0 / bestTreeScoreHits)) {
+                        bestParsimony = m; insertNode = cref[j]; removeNode = cprune[j];
+                    }
+                }
+                if (bestParsimony == randomMP) bestIterationScoreHits++;          // :3306
+                if (bestParsimony < randomMP) bestIterationScoreHits = 1;
+                if ((bestParsimony < randomMP ||
+                     (bestParsimony == randomMP && rng(rng_user) <= 1.0 / bestIterationScoreHits)) &&
+                    removeNode && insertNode) {
+                    apply_spr_move(c->tree, removeNode, insertNode);              // :3312
+                    randomMP = bestParsimony;
+                    cur_score = bestParsimony;
+                    moved = true;
+                }
+            }
+            i += v;
+            if (moved) {
+                c->tree_set = true; c->lens_valid = false;
+                if (int rc = compute_views(c)) return rc;
+                compute_lengths(c);
+                batch = 16;
+            } else {
+                batch = std::min(batch * 2, nvisit);
+            }
+        }
+    } while (randomMP < startMP);
+    memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
+    memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
+    *best = startMP;
+    if (n_insertions) *n_insertions = scored;
+    return 0;
+}
+
+extern "C" {
+
+int mpgpu_optimize_spr(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
+                       mpgpu_rng_fn rng, void *rng_user, uint32_t *best, int64_t *n_insertions)
+{
+    if (!c || !back_node || !back_slot || !rng || !best) { set_error("null argument"); return 1; }
+    return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, rng, rng_user, nullptr, best, n_insertions);
+}
+
+int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
+                          const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state, uint32_t *best, int64_t *n_insertions)
+{
+    if (!c || !back_node || !back_slot || !hooks || !state || !best) { set_error("null argument"); return 1; }
+    if (!hooks->random_double || !hooks->push_tree_logl || !hooks->materialize) { set_error("incomplete -bb hooks"); return 1; }
+    if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
+    if (state->B != c->reps.B || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
+    state->n_calls = 0; state->n_reps = 0;
+    BBRun bb{hooks, state};
+    return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, hooks->random_double, hooks->user, &bb, best, n_insertions);
+}
+
+int mpgpu_set_option(mpgpu_ctx *c, const char *name, int value)
+{
+    if (!c || !name) { set_error("null argument"); return 1; }
+    if (!strcmp(name, "reps_tensor")) {
+        if (c->reps.loaded) { set_error("reps_tensor must be set before mpgpu_load_replicates"); return 1; }
+        c->reps.use_tensor = value != 0;
+        return 0;
+    }
+    set_error(std::string("unknown option: ") + name);
+    return 1;
+}
+
+int mpgpu_reps_info(mpgpu_ctx *c, int *groups, int *exceptions, int *tensor)
+{
+    if (!c || !c->reps.loaded) { set_error("no replicates loaded"); return 1; }
+    if (groups) *groups = c->reps.G;
+    if (exceptions) *exceptions = c->reps.n_exc;
+    if (tensor) *tensor = c->reps.use_tensor ? 1 : 0;
+    return 0;
+}
+
+int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride, const int32_t *segment_upper, int nseg)
+{
+    if (!c || !boot || !segment_upper) { set_error("null argument"); return 1; }
+    if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
+    if (B < 1 || nseg < 1) { set_error("need at least one replicate and one segment"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    free_reps(c);
+    Reps &r = c->reps;
+    const int upper0 = c->sort_alignment ? c->n_inf : c->P;
+    if (stride < upper0) { set_error("boot_samples stride is smaller than the number of reported patterns"); return 1; }
+    for (int s = 0; s < nseg; s++) {
+        if (segment_upper[s] <= (s ? segment_upper[s - 1] : 0)) { set_error("segment_upper must be increasing"); return 1; }
+        if (s < nseg - 1 && segment_upper[s] % 16) { set_error("inner segment bounds must be multiples of 16 (iqtree.cpp:3806)"); return 1; }
+    }
+    r.B = B; r.Bpad = (B + 255) / 256 * 256;
+    r.upper = std::min(upper0, (int)segment_upper[nseg - 1]);       // the loop at :3424 stops at the last bound
+    r.Kpad = (std::max(r.upper, 1) + 127) / 128 * 128; r.Pw = r.Kpad / 32;
+    r.seg_upper.assign(segment_upper, segment_upper + nseg);
+
+    // ---- which segments can wrap at 16 bits on some tree, which patterns are too heavy for u8 ----
+    std::vector<uint16_t> ub(std::max(r.upper, 1));
+    {
+        uint16_t *d_ub = nullptr;
+        MPGPU_CUDA(cudaMalloc((void **)&d_ub, ub.size() * sizeof(uint16_t)));
+        int rc = launch_pattern_ub(c, r.upper, d_ub);
+        if (!rc && r.upper > 0) {
+            cudaError_t e = cudaMemcpyAsync(ub.data(), d_ub, (size_t)r.upper * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "pattern upper bounds");
+        }
+        cudaFree(d_ub);
+        if (rc) return rc;
+    }
+    std::vector<int> seg_of(std::max(r.upper, 1), 0);
+    std::vector<uint8_t> flagged(nseg, 0), heavy(std::max(r.upper, 1), 0);
+    {
+        int s = 0;
+        for (int p = 0; p < r.upper; p++) { while (p >= segment_upper[s]) s++; seg_of[p] = s; }
+        std::vector<uint64_t> sum(nseg);
+        for (int b = 0; b < B; b++) {
+            const uint16_t *w = boot + (size_t)b * stride;
+            std::fill(sum.begin(), sum.end(), 0);
+            for (int p = 0; p < r.upper; p++) { sum[seg_of[p]] += (uint64_t)ub[p] * w[p]; if (w[p] > 255) heavy[p] = 1; }
+            for (int g = 0; g < nseg; g++) if (sum[g] >= 65536) flagged[g] = 1;
+        }
+    }
+    std::vector<int> group_of_seg(nseg, 0);
+    r.G = 1;
+    for (int g = 0; g < nseg; g++) if (flagged[g]) group_of_seg[g] = r.G++;
+    std::vector<int32_t> exc_ptn, exc_group;
+    std::vector<uint8_t> is_exc(r.Kpad, 0);
+    r.n_heavy = 0;
+    for (int pass = 0; pass < 2; pass++)                                       // group 0 first, then the wrap-prone segments in order
+        for (int p = 0; p < r.upper; p++) {
+            const int g = group_of_seg[seg_of[p]];
+            if (pass == 0 ? (g == 0 && (heavy[p] || !r.use_tensor)) : g > 0) {
+                exc_ptn.push_back(p); exc_group.push_back(g); is_exc[p] = 1;
+                if (g == 0 && heavy[p]) r.n_heavy++;
+            }
+        }
+    if (r.G > 1) {                                                             // keep groups contiguous and ascending
+        std::vector<int> idx(exc_ptn.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return exc_group[a] < exc_group[b]; });
+        std::vector<int32_t> p2(idx.size()), g2(idx.size());
+        for (size_t i = 0; i < idx.size(); i++) { p2[i] = exc_ptn[idx[i]]; g2[i] = exc_group[idx[i]]; }
+        exc_ptn.swap(p2); exc_group.swap(g2);
+    }
+    r.n_exc = (int)exc_ptn.size();
+
+    // ---- device copies ----
+    uint16_t *d_boot16 = nullptr; uint8_t *d_is_exc = nullptr;
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_w8, (size_t)r.Bpad * r.Kpad));
+    if (r.n_exc) {
+        MPGPU_CUDA(cudaMalloc((void **)&r.d_w16e, (size_t)r.n_exc * r.Bpad * sizeof(uint16_t)));
+        MPGPU_CUDA(cudaMalloc((void **)&r.d_exc_ptn, (size_t)r.n_exc * 4));
+        MPGPU_CUDA(cudaMalloc((void **)&r.d_exc_group, (size_t)r.n_exc * 4));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_exc_ptn, exc_ptn.data(), (size_t)r.n_exc * 4, cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_exc_group, exc_group.data(), (size_t)r.n_exc * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    MPGPU_CUDA(cudaMalloc((void **)&d_boot16, (size_t)B * stride * sizeof(uint16_t)));
+    MPGPU_CUDA(cudaMalloc((void **)&d_is_exc, (size_t)r.Kpad));
+    MPGPU_CUDA(cudaMemcpyAsync(d_boot16, boot, (size_t)B * stride * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemcpyAsync(d_is_exc, is_exc.data(), (size_t)r.Kpad, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_build_weights(c, d_boot16, stride, d_is_exc);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_boot16); cudaFree(d_is_exc);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "building replicate weights");
+    if (r.use_tensor) { if (int rc2 = make_w8_tensor_map(c)) return rc2; }
+    r.loaded = true;
+    r.tree_valid = false;
+    return 0;
+}
+
+int mpgpu_reps_current_tree(mpgpu_ctx *c, int32_t *res)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (!res) { set_error("null argument"); return 1; }
+    if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
+    if (c->shard_count != 1) { set_error("mpgpu_reps_current_tree is single-shard in this version"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    // the current tree needs no scan plan: a one-call batch with an empty plan
+    const int32_t cand = -1;
+    RepsOut ro;
+    if (int rc = reps_run(c, &cand, 1, nullptr, ro)) return rc;
+    memcpy(res, ro.dense.data() + ro.dense_off[0], (size_t)c->reps.B * 4);
+    return 0;
+}
+
+int mpgpu_reps_candidates(mpgpu_ctx *c, const int32_t *cand_idx, int m, int32_t *res)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (!cand_idx || !res || m < 0) { set_error("bad argument"); return 1; }
+    if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
+    if (c->shard_count != 1) { set_error("mpgpu_reps_candidates is single-shard in this version"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    RepsOut ro;
+    if (int rc = reps_run(c, cand_idx, m, nullptr, ro)) return rc;
+    for (int i = 0; i < m; i++) memcpy(res + (size_t)i * c->reps.B, ro.dense.data() + ro.dense_off[i], (size_t)c->reps.B * 4);
+    return 0;
+}
+
+}  // extern "C"

@@ -72,6 +72,41 @@ struct ScanPlan {
     int max_slot = 0;
 };
 
+// ---- replicate scoring state (R8; reps_kernels.cu, mpgpu_bb.cu) -------------------------------
+static const int kTreeRows = 17;          // rows 0..15: bit planes of the tree's per-site counters, row 16: their weighted sum
+struct Reps {
+    bool loaded = false;
+    int B = 0, Bpad = 0;                  // replicates, padded to the tensor tile (256)
+    int upper = 0;                        // patterns that take part: min(numInformative or P, last segment_upper)
+    int Kpad = 0, Pw = 0;                 // patterns padded to 128; words per pattern row
+    std::vector<int32_t> seg_upper;
+    int G = 1;                            // column groups: 0 = wrap-free bulk, g >= 1 = one wrap-prone segment each
+    int n_exc = 0, n_heavy = 0;           // exception patterns (all of groups >= 1, plus weights > 255 of group 0)
+    int kb_lo = 0, kb_hi = 0;             // 128-pattern K-blocks that can have bits on this shard
+    bool use_tensor = true;
+    uint8_t *d_w8 = nullptr;              // [Bpad][Kpad]
+    uint16_t *d_w16e = nullptr;           // [n_exc][Bpad]
+    int32_t *d_exc_ptn = nullptr, *d_exc_group = nullptr;
+    alignas(64) unsigned char tmap_w8[128];
+    bool tmap_valid = false;
+    // rows (one index space for the three buffers)
+    int row_cap = 0;
+    uint32_t *d_rows_site = nullptr;      // [row_cap][Wl]   mismatch rows in expanded-site space
+    uint32_t *d_rows_ptn = nullptr;       // [row_cap][Pw]   the same rows in pattern space
+    int32_t *d_X = nullptr;               // [row_cap][G][Bpad]
+    bool tree_valid = false;              // rows 0..16 describe the current tree and weights
+    // per batch
+    int32_t *d_row_of = nullptr; size_t row_of_cap = 0;
+    int32_t *d_row_tasks = nullptr; size_t row_tasks_cap = 0;
+    int4 *d_edges = nullptr; size_t edges_cap = 0;
+    int2 *d_calls = nullptr; size_t calls_cap = 0;
+    int32_t *d_res = nullptr; size_t res_cap = 0;          // [calls][Bpad]
+    int32_t *d_thr = nullptr;                              // [Bpad]
+    uint32_t *d_hit_count = nullptr;
+    int4 *d_hits = nullptr; uint32_t hit_cap = 0;
+    int64_t rows_scored = 0;              // statistics: rows pushed through the contraction
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -118,20 +153,63 @@ struct Ctx {
     int32_t *d_pairs = nullptr; size_t pairs_cap = 0;
     uint16_t *d_ptn = nullptr; size_t ptn_cap = 0;
     int64_t *d_ptn_site = nullptr; size_t ptn_site_cap = 0;
+    bool ptn_site_valid = false;
+
+    // replicate scoring
+    Reps reps;
+    // aliases the scan kernel's ROWS mode reads (owned by reps)
+    int32_t *d_row_of = nullptr, *d_row_tasks = nullptr;
+    uint32_t *d_rows_site = nullptr;
 };
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 #define MPGPU_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return ::mpgpu::cuda_fail(e__, #expr); } while (0)
 
+template <typename T>
+static inline int ensure(T *&ptr, size_t &cap, size_t need)
+{
+    if (need <= cap && ptr) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = need + need / 4 + 16;
+    MPGPU_CUDA(cudaMalloc((void **)&ptr, want * sizeof(T)));
+    cap = want;
+    return 0;
+}
+
+// ---- shared host helpers (mpgpu_api.cu) -----------------------------------------------------
+int compute_views(Ctx *c);
+void compute_lengths(Ctx *c);
+int need_tree(Ctx *c, bool lens);
+int run_scan(Ctx *c);
+int upload_plan(Ctx *c);
+int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity);
+int compute_site_counters(Ctx *c, int nbits);       // bit-sliced per-site counters of the current tree -> d_bitcnt
+int ensure_ptn_site(Ctx *c);                        // first expanded site of every reported pattern -> d_ptn_site
+void free_reps(Ctx *c);
+
 // ---- kernel launchers (fitch_kernels.cu) -------------------------------------------------
 int launch_compress(Ctx *c);
 int launch_level(Ctx *c, const Triple *d_triples, int ntriples);
 int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out);
 int launch_scan(Ctx *c, int ntasks, int nslots);
+int launch_scan_rows(Ctx *c, int ntasks, int nslots);
 int launch_site_counters(Ctx *c, int npairs, int nbits);
 int launch_gather_patterns(Ctx *c, int nbits, int count);
 const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);
+
+// ---- kernel launchers (reps_kernels.cu) ----------------------------------------------------
+int launch_pattern_ub(Ctx *c, int count, uint16_t *d_ub);
+int launch_build_weights(Ctx *c, const uint16_t *d_boot16, int stride, const uint8_t *d_is_exc);
+int launch_edge_rows(Ctx *c, const int4 *d_edges, int nedges, uint32_t *d_rows);
+int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows);
+int launch_reps_exc(Ctx *c, int row0, int nrows);
+int make_w8_tensor_map(Ctx *c);
+int launch_reps_tc(Ctx *c, int row0, int nrows);
+int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row);
+int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr,
+                        uint32_t *d_hit_count, int4 *d_hits, uint32_t hit_cap);
 
 // ---- host SPR logic (spr_host.cpp) ---------------------------------------------------------
 void visit_order(const HostTree &t, std::vector<int32_t> &order);
@@ -140,3 +218,5 @@ int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const 
 void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);
 
 }  // namespace mpgpu
+
+struct mpgpu_ctx : public mpgpu::Ctx {};

@@ -1,0 +1,585 @@
+// Replicate scoring (REPS) kernels of the -bb path: R8 of DESIGN.md.
+//
+// Reference: IQTree::saveCurrentTree, iqtree.cpp:3411-3449 --
+//     rell[b] = - sum_seg ( ( sum_{ptn in seg} pattern_pars[ptn] * boot_sample[b][ptn] ) mod 2^16 )
+// on u16 SIMD lanes (vectorclass/vectori256.h:1726-1740: lane products, lane sums and the
+// horizontal add all wrap at 16 bits).
+//
+// Here every per-pattern score vector is a signed sum of 1-bit rows:
+//   current tree      c_T   = sum_bit 2^bit * plane_bit            (bit-sliced site counters)
+//   candidate (p->e)  c     = c_T - mis(edge p|q) + delta_e        (Fitch length is root-invariant per site)
+// so REPS is  X[row][b] = sum_ptn bit[row][ptn] * w[b][ptn]  -- a dense {0,1} x u8 -> s32 contraction
+// (rows x patterns x replicates) -- followed by a tiny linear combine.  The contraction runs on
+// the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM, replicate weights staged by
+// TMA); patterns whose arithmetic the u8 tensor path cannot represent exactly -- a replicate
+// weight above 255, or a segment whose 16-bit wrap cannot be ruled out -- are "exceptions" and
+// go through an exact CUDA-core kernel into their own column group, where the mod-2^16 is
+// applied after the combine.
+#include "mpgpu_internal.h"
+
+#include <cuda.h>
+
+namespace mpgpu {
+
+__host__ __device__ inline uint32_t reps_code_mask(int datatype, uint32_t code)
+{
+    switch (datatype) {
+    case MPGPU_AA_DATA:
+        if (code < 20) return 1u << code;
+        if (code == 20) return 12u;
+        if (code == 21) return 96u;
+        return 0xFFFFFu;
+    case MPGPU_GENERIC_32:
+        return code < 32 ? (1u << code) : 0xFFFFFFFFu;
+    default:
+        return code;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Upper bound of a pattern's Fitch score on ANY tree: n - (largest number of tips compatible
+// with one state).  Used to prove that a REPS segment cannot reach 2^16 (wrap-free).
+// ------------------------------------------------------------------------------------------
+template <int S>
+__global__ void k_pattern_ub(const uint8_t *__restrict__ codes, int P, int n, int datatype, int count,
+                             uint16_t *__restrict__ ub)
+{
+    const int ptn = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ptn >= count) return;
+    int cnt[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) cnt[s] = 0;
+    for (int t = 0; t < n; t++) {
+        const uint32_t m = reps_code_mask(datatype, codes[(size_t)t * P + ptn]);
+#pragma unroll
+        for (int s = 0; s < S; s++) cnt[s] += (m >> s) & 1u;
+    }
+    int best = 0;
+#pragma unroll
+    for (int s = 0; s < S; s++) best = cnt[s] > best ? cnt[s] : best;
+    ub[ptn] = (uint16_t)(n - best);
+}
+
+int launch_pattern_ub(Ctx *c, int count, uint16_t *d_ub)
+{
+    if (count == 0) return 0;
+    const int threads = 128, blocks = (count + threads - 1) / threads;
+    switch (c->S) {
+    case 2:  k_pattern_ub<2><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
+    case 4:  k_pattern_ub<4><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
+    case 20: k_pattern_ub<20><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
+    case 32: k_pattern_ub<32><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
+    default: set_error("unsupported state count"); return 1;
+    }
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Replicate weights: boot16 [B][stride] u16 (as boot_samples_pars, iqtree.cpp:220-233) ->
+//   w8  [Bpad][Kpad] u8, K-major (the tensor kernel's B operand); exception patterns and padding = 0
+//   w16e[n_exc][Bpad] u16, the exact weights of the exception patterns
+// ------------------------------------------------------------------------------------------
+__global__ void k_build_w8(const uint16_t *__restrict__ boot16, int B, int stride, int upper,
+                           const uint8_t *__restrict__ is_exc, int Bpad, int Kpad, uint8_t *__restrict__ w8)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (k >= Kpad) return;
+    uint32_t v = 0;
+    if (b < B && k < upper && !is_exc[k]) v = boot16[(size_t)b * stride + k];
+    w8[(size_t)b * Kpad + k] = (uint8_t)v;            // v <= 255 by construction (heavier patterns are exceptions)
+}
+
+__global__ void k_build_w16e(const uint16_t *__restrict__ boot16, int B, int stride,
+                             const int32_t *__restrict__ exc_ptn, int n_exc, int Bpad, uint16_t *__restrict__ w16e)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.y;
+    if (b >= Bpad || e >= n_exc) return;
+    w16e[(size_t)e * Bpad + b] = b < B ? boot16[(size_t)b * stride + exc_ptn[e]] : (uint16_t)0;
+}
+
+int launch_build_weights(Ctx *c, const uint16_t *d_boot16, int stride, const uint8_t *d_is_exc)
+{
+    Reps &r = c->reps;
+    {
+        dim3 grid((r.Kpad + 255) / 256, r.Bpad);
+        k_build_w8<<<grid, 256, 0, c->stream>>>(d_boot16, r.B, stride, r.upper, d_is_exc, r.Bpad, r.Kpad, r.d_w8);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    if (r.n_exc > 0) {
+        dim3 grid((r.Bpad + 255) / 256, r.n_exc);
+        k_build_w16e<<<grid, 256, 0, c->stream>>>(d_boot16, r.B, stride, r.d_exc_ptn, r.n_exc, r.Bpad, r.d_w16e);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Rows.  Site space: one bit per expanded site of this shard (Wl words per row).
+// ------------------------------------------------------------------------------------------
+// mismatch row across an edge: ~OR_k(A_k & B_k)   (the bits evaluateParsimony counts, :1096-1125)
+template <int S>
+__global__ void __launch_bounds__(128) k_edge_rows(const uint32_t *__restrict__ views, size_t view_stride, int Wl,
+                                                   const int4 *__restrict__ edges, uint32_t *__restrict__ rows)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int4 e = edges[blockIdx.y];                            // vidA, vidB, row
+    constexpr int SG = S < 4 ? S : 4;
+    const size_t gs = (size_t)Wl * SG, off = (size_t)w * SG;
+    uint32_t n = 0;
+#pragma unroll
+    for (int g = 0; g < (S + SG - 1) / SG; g++) {
+        if (SG == 4) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(views + (size_t)e.x * view_stride + off + g * gs));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(views + (size_t)e.y * view_stride + off + g * gs));
+            n |= (a.x & b.x) | (a.y & b.y) | (a.z & b.z) | (a.w & b.w);
+        } else {
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(views + (size_t)e.x * view_stride + off));
+            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(views + (size_t)e.y * view_stride + off));
+            n |= (a.x & b.x) | (a.y & b.y);
+        }
+    }
+    rows[(size_t)e.z * Wl + w] = ~n;
+}
+
+int launch_edge_rows(Ctx *c, const int4 *d_edges, int nedges, uint32_t *d_rows)
+{
+    if (nedges == 0) return 0;
+    dim3 grid(c->Wl / 128, nedges);
+    switch (c->S) {
+    case 2:  k_edge_rows<2><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_rows); break;
+    case 4:  k_edge_rows<4><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_rows); break;
+    case 20: k_edge_rows<20><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_rows); break;
+    case 32: k_edge_rows<32><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_rows); break;
+    default: set_error("unsupported state count"); return 1;
+    }
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Site rows -> pattern rows: bit ptn of the output = bit at the FIRST expanded site of pattern
+// ptn (what pllComputePatternParsimony reads, :3384).  One warp per (row, 32 patterns).
+__global__ void k_gather_rows(const uint32_t *__restrict__ src, int Wl, int64_t w0,
+                              const int64_t *__restrict__ ptn_site, int upper, int Pw,
+                              uint32_t *__restrict__ dst, int nrows)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= (long long)nrows * Pw) return;
+    const int row = (int)(gw / Pw), pw = (int)(gw % Pw);
+    const int ptn = 32 * pw + lane;
+    uint32_t bit = 0;
+    if (ptn < upper) {
+        const int64_t site = ptn_site[ptn];
+        const int64_t w = (site >> 5) - w0;
+        if (site >= 0 && w >= 0 && w < Wl) bit = (src[(size_t)row * Wl + w] >> (site & 31)) & 1u;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) dst[(size_t)row * Pw + pw] = word;
+}
+
+int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows)
+{
+    if (nrows == 0) return 0;
+    Reps &r = c->reps;
+    const long long warps = (long long)nrows * r.Pw;
+    const int wpb = 8;
+    const long long blocks = (warps + wpb - 1) / wpb;
+    if (blocks > 0x7fffffffLL) { set_error("gather grid too large"); return 1; }
+    k_gather_rows<<<(unsigned)blocks, wpb * 32, 0, c->stream>>>(d_src, c->Wl, c->w0, c->d_ptn_site, r.upper, r.Pw, d_dst, nrows);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact CUDA-core contraction over the exception patterns.
+//   X[row][group(e)][b] += bit[row][ptn(e)] * w16e[e][b]
+// exceptions are sorted by group; one thread per (row, b).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ rows_ptn, int Pw, int row0,
+                                                  const int32_t *__restrict__ exc_ptn, const int32_t *__restrict__ exc_group,
+                                                  int n_exc, const uint16_t *__restrict__ w16e, int Bpad, int G,
+                                                  int32_t *__restrict__ X)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = row0 + blockIdx.y;
+    if (b >= Bpad) return;
+    const uint32_t *bits = rows_ptn + (size_t)row * Pw;
+    int32_t *xrow = X + (size_t)row * G * Bpad;
+    int acc = 0, cur = -1;
+    for (int e = 0; e < n_exc; e++) {
+        const int g = __ldg(exc_group + e);
+        if (g != cur) {
+            if (cur >= 0 && acc) atomicAdd(&xrow[(size_t)cur * Bpad + b], acc);
+            cur = g; acc = 0;
+        }
+        const int p = __ldg(exc_ptn + e);
+        if ((__ldg(bits + (p >> 5)) >> (p & 31)) & 1u) acc += (int)__ldg(w16e + (size_t)e * Bpad + b);
+    }
+    if (cur >= 0 && acc) atomicAdd(&xrow[(size_t)cur * Bpad + b], acc);
+}
+
+int launch_reps_exc(Ctx *c, int row0, int nrows)
+{
+    Reps &r = c->reps;
+    if (nrows == 0 || r.n_exc == 0) return 0;
+    for (int done = 0; done < nrows; done += 65535) {
+        const int chunk = nrows - done < 65535 ? nrows - done : 65535;
+        dim3 grid((r.Bpad + 255) / 256, chunk);
+        k_reps_exc<<<grid, 256, 0, c->stream>>>(r.d_rows_ptn, r.Pw, row0 + done, r.d_exc_ptn, r.d_exc_group, r.n_exc,
+                                                 r.d_w16e, r.Bpad, r.G, r.d_X);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core contraction:  X[row][0][b] += sum_k bit[row][k] * w8[b][k]
+//
+// tcgen05.mma.cta_group::1.kind::i8, M = 128 rows, N = 256 replicates, K = 32 per instruction.
+// CTA tile 128 x 256, K-block = 128 patterns (= one 128-byte swizzle row of u8).
+//   warps 0-3  A producers: read 128 bits per row, expand to 0/1 bytes, write the K-major
+//              SWIZZLE_128B tile by hand (generic proxy -> fence.proxy.async), then epilogue
+//   warp 4     B producer: one TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) per K-block
+//   warp 5     TMEM owner + MMA issuer (one elected lane)
+// 4-stage mbarrier ring (full/empty), accumulator 128 lanes x 256 columns of TMEM (s32).
+// Split-K over blockIdx.z; partial tiles are added with integer atomics (exact, order-free).
+// ------------------------------------------------------------------------------------------
+namespace tc {
+
+constexpr int M = 128, N = 256, KB = 128, STAGES = 4;
+constexpr int A_BYTES = M * KB, B_BYTES = N * KB, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);           // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B, bits [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = s32, A = B = u8, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc()
+{
+    return (2u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// 4 bits -> 4 bytes of 0/1 (bit j -> byte j)
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_ptn, int Pw,
+          int row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));            // generic pointer to the aligned base
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * M, n0 = blockIdx.y * N;
+    const int kb_begin = kb_lo + blockIdx.z * kb_per_split;
+    int kb_end = kb_begin + kb_per_split;
+    if (kb_end > kb_hi) kb_end = kb_hi;
+    const int nkb = kb_end - kb_begin;
+    if (nkb <= 0) return;                                                  // uniform over the CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < 4) {
+        // ---- A producers: thread r owns tile row r ----
+        const int r = threadIdx.x;
+        const int row = row0 + m0 + r;
+        const bool live = (m0 + r) < nrows;
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows_ptn + (size_t)row * Pw);
+        const uint32_t sw = (uint32_t)(r & 7);
+        for (int it = 0; it < nkb; it++) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            uint4 bits = make_uint4(0, 0, 0, 0);
+            if (live) bits = __ldg(src + (kb_begin + it));                 // 128 patterns of this row
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            uint8_t *arow = smem_gen + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+            const uint32_t wv[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+            for (int cidx = 0; cidx < 8; cidx++) {
+                const uint32_t h = (wv[cidx >> 1] >> ((cidx & 1) * 16)) & 0xFFFFu;
+                uint4 v;
+                v.x = spread4(h & 0xF); v.y = spread4((h >> 4) & 0xF); v.z = spread4((h >> 8) & 0xF); v.w = spread4(h >> 12);
+                *reinterpret_cast<uint4 *>(arow + ((cidx ^ sw) << 4)) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+        }
+    } else if (warp == 4) {
+        // ---- B producer (TMA) ----
+        if (lane == 0) {
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), B_BYTES);
+                tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmap_w8, (kb_begin + it) * KB, n0, full_bar(s));
+            }
+        }
+    } else {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc();
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t ad = umma_desc(base + s * STAGE_BYTES);
+                const uint64_t bd = umma_desc(base + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < KB / 32; k++)                           // +32 bytes along K inside the swizzle row
+                    umma_i8(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                umma_commit(empty_bar(s));                                   // frees the stage when these MMAs retire
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+
+    if (warp < 4) {
+        // ---- epilogue: TMEM -> registers -> (transpose through smem) -> coalesced integer atomics ----
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t *tile = reinterpret_cast<uint32_t *>(smem_gen) + warp * (32 * 33);   // stage memory is free now
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int cb = 0; cb < N / 32; cb++) {
+            uint32_t v[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr + (uint32_t)(cb * 32)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j++) tile[lane * 33 + j] = v[j];
+            __syncwarp();
+            const int col = n0 + cb * 32 + lane;
+            for (int i = 0; i < 32; i++) {
+                const int mrow = m0 + warp * 32 + i;
+                const int val = (int)tile[i * 33 + lane];
+                if (mrow < nrows && col < B && val != 0)
+                    atomicAdd(&X[(size_t)(row0 + mrow) * x_pitch + col], val);
+            }
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(N) : "memory");
+}
+
+}  // namespace tc
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_w8_tensor_map(Ctx *c)
+{
+    Reps &r = c->reps;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MPGPU_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return 1; }
+        encode = (EncodeTiledFn)fn;
+    }
+    static_assert(sizeof(CUtensorMap) <= sizeof(r.tmap_w8), "tensor map storage too small");
+    const cuuint64_t dims[2] = {(cuuint64_t)r.Kpad, (cuuint64_t)r.Bpad};
+    const cuuint64_t strides[1] = {(cuuint64_t)r.Kpad};                   // bytes between replicate rows
+    const cuuint32_t box[2] = {(cuuint32_t)tc::KB, (cuuint32_t)tc::N};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult res = encode(reinterpret_cast<CUtensorMap *>(r.tmap_w8), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, r.d_w8, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed for the replicate-weight matrix"); return 1; }
+    r.tmap_valid = true;
+    return 0;
+}
+
+// X[row0 .. row0+nrows)[group 0] += rows_ptn x w8   (this shard's K-blocks [kb_lo, kb_hi))
+int launch_reps_tc(Ctx *c, int row0, int nrows)
+{
+    Reps &r = c->reps;
+    if (nrows == 0) return 0;
+    if (!r.tmap_valid) { set_error("replicate weights not loaded"); return 1; }
+    const int kb_lo = r.kb_lo, kb_hi = r.kb_hi;
+    if (kb_hi <= kb_lo) return 0;
+    static bool configured = false;
+    if (!configured) {
+        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        configured = true;
+    }
+    const int mt = (nrows + tc::M - 1) / tc::M, nt = r.Bpad / tc::N;
+    const int nkb = kb_hi - kb_lo;
+    // split K so that the grid fills the GPU (148 SMs, one CTA each) without making splits tiny
+    int splits = 1;
+    const int ctas = mt * nt;
+    if (ctas < 148) splits = (148 + ctas - 1) / ctas;
+    if (splits > nkb / 8) splits = nkb / 8;
+    if (splits < 1) splits = 1;
+    if (const char *e = getenv("MPGPU_REPS_SPLITS")) { int v = atoi(e); if (v >= 1) splits = v; }
+    const int per = (nkb + splits - 1) / splits;
+    splits = (nkb + per - 1) / per;
+    dim3 grid(mt, nt, splits);
+    tc::k_reps_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), r.d_rows_ptn, r.Pw,
+                                                                    row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Combine.
+//   tree row:  X[t][g][b] = sum_bit X[plane_bit][g][b] << bit
+//   call j:    res[j][b]  = sum_g mask_g( X[t][g][b] - X[e_j][g][b] + X[d_j][g][b] ),  mask_0 = id, else & 0xFFFF
+// A hit (res <= thr[b], i.e. rell >= boot_logl[b] at the start of the batch) is appended to a
+// compact list so that the host only has to read what can change a replicate.
+// ------------------------------------------------------------------------------------------
+__global__ void k_reps_tree_row(int32_t *__restrict__ X, int plane_row0, int nbits, int t_row, int pitch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pitch) return;
+    int acc = 0;
+    for (int b = 0; b < nbits; b++) acc += X[(size_t)(plane_row0 + b) * pitch + i] << b;
+    X[(size_t)t_row * pitch + i] = acc;
+}
+
+__global__ void k_reps_combine(const int32_t *__restrict__ X, int G, int Bpad, int B, int t_row,
+                               const int2 *__restrict__ calls, int call0, int ncalls, int32_t *__restrict__ res,
+                               const int32_t *__restrict__ thr, uint32_t *__restrict__ hit_count,
+                               int4 *__restrict__ hits, uint32_t hit_cap)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = call0 + blockIdx.y;
+    if (b >= Bpad || j >= ncalls) return;
+    const int2 cd = calls[j];                                   // x = edge row (-1 none), y = delta row (-1 none)
+    const size_t pitch = (size_t)G * Bpad;
+    int total = 0;
+    for (int g = 0; g < G; g++) {
+        int v = X[(size_t)t_row * pitch + (size_t)g * Bpad + b];
+        if (cd.x >= 0) v -= X[(size_t)cd.x * pitch + (size_t)g * Bpad + b];
+        if (cd.y >= 0) v += X[(size_t)cd.y * pitch + (size_t)g * Bpad + b];
+        total += g == 0 ? v : (v & 0xFFFF);
+    }
+    res[(size_t)j * Bpad + b] = total;
+    if (thr && b < B && total <= thr[b]) {
+        const uint32_t slot = atomicAdd(hit_count, 1u);
+        if (slot < hit_cap) hits[slot] = make_int4(j, b, total, 0);
+    }
+}
+
+int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row)
+{
+    Reps &r = c->reps;
+    const int pitch = r.G * r.Bpad;
+    k_reps_tree_row<<<(pitch + 255) / 256, 256, 0, c->stream>>>(r.d_X, plane_row0, nbits, t_row, pitch);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr,
+                        uint32_t *d_hit_count, int4 *d_hits, uint32_t hit_cap)
+{
+    Reps &r = c->reps;
+    if (ncalls == 0) return 0;
+    for (int done = 0; done < ncalls; done += 65535) {
+        const int chunk = ncalls - done < 65535 ? ncalls - done : 65535;
+        dim3 grid((r.Bpad + 255) / 256, chunk);
+        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.B, t_row, d_calls, done, ncalls,
+                                                     d_res, d_thr, d_hit_count, d_hits, hit_cap);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace mpgpu

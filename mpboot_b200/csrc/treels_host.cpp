@@ -1,0 +1,104 @@
+// A minimal host-side stand-in for the pieces of class IQTree that mpgpu_optimize_spr_bb calls
+// back into: treels_logl (iqtree.h, vector<double>), the treels map keyed by the tree's
+// canonical form (iqtree.cpp:3299-3312, 3701-3708) and the random_double() stream.  The real
+// host wires the hooks to IQTree's own members instead; tests and bench.py
+// use this container so that no Python sits between the device and the bookkeeping.
+// The canonical form here is a 64-bit order-independent hash of the unrooted topology (the
+// reference uses the sorted-taxa newick string; both identify the topology).
+#include "mpgpu_internal.h"
+
+#include <cstring>
+#include <unordered_map>
+
+struct mpgpu_treels {
+    int n = 0;
+    std::vector<double> logl;                              // treels_logl
+    std::unordered_map<uint64_t, int32_t> index;           // treels
+    std::vector<int64_t> mats;                             // 4 per materialised tree: remove_ref, insert_ref, tree_index, fingerprint
+    mpgpu_rng_fn rng = nullptr; void *rng_user = nullptr;
+};
+
+namespace {
+
+uint64_t fin64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+uint64_t subtree_hash(const mpgpu::HostTree &t, int ref)
+{
+    // iterative post-order: hash of the subtree that holds ref's node, entered through ref
+    struct Frame { int ref; int state; uint64_t a; };
+    std::vector<Frame> st;
+    st.push_back({ref, 0, 0});
+    uint64_t ret = 0;
+    while (!st.empty()) {
+        Frame &f = st.back();
+        if (t.is_tip(f.ref)) { ret = fin64((uint64_t)(f.ref / 3)); st.pop_back(); continue; }
+        if (f.state == 0) { f.state = 1; st.push_back({t.back(t.next(f.ref)), 0, 0}); continue; }
+        if (f.state == 1) { f.a = ret; f.state = 2; st.push_back({t.back(t.next(t.next(f.ref))), 0, 0}); continue; }
+        uint64_t a = f.a, b = ret;
+        if (a > b) std::swap(a, b);
+        ret = fin64(a * 0x9E3779B97F4A7C15ULL + b + 0x632BE59BD9B4E019ULL);
+        st.pop_back();
+    }
+    return ret;
+}
+
+double hook_rng(void *user)
+{
+    mpgpu_treels *h = (mpgpu_treels *)user;
+    return h->rng(h->rng_user);
+}
+
+int32_t hook_push(void *user, double cur_logl)
+{
+    mpgpu_treels *h = (mpgpu_treels *)user;
+    h->logl.push_back(cur_logl);                           // iqtree.cpp:3345-3348
+    return (int32_t)h->logl.size() - 1;
+}
+
+int32_t hook_materialize(void *user, const int32_t *bn, const int32_t *bs, int32_t remove_ref, int32_t insert_ref, int32_t tree_index)
+{
+    mpgpu_treels *h = (mpgpu_treels *)user;
+    mpgpu::HostTree t;
+    t.n = h->n;
+    const int len = 3 * (2 * h->n - 1);
+    t.bn.assign(bn, bn + len); t.bs.assign(bs, bs + len);
+    if (remove_ref) mpgpu::apply_spr_move(t, remove_ref, insert_ref);
+    const uint64_t fp = fin64(subtree_hash(t, t.back(3)) ^ 0x1234567ULL);
+    auto it = h->index.find(fp);                           // treels.find(tree_str), iqtree.cpp:3701-3706
+    if (it != h->index.end()) tree_index = it->second;
+    else h->index[fp] = tree_index;
+    const int64_t rec[4] = {remove_ref, insert_ref, tree_index, (int64_t)fp};
+    h->mats.insert(h->mats.end(), rec, rec + 4);
+    return tree_index;
+}
+
+}  // namespace
+
+extern "C" {
+
+mpgpu_treels *mpgpu_treels_create(int ntaxa)
+{
+    mpgpu_treels *h = new mpgpu_treels();
+    h->n = ntaxa;
+    return h;
+}
+void mpgpu_treels_destroy(mpgpu_treels *h) { delete h; }
+int64_t mpgpu_treels_size(const mpgpu_treels *h) { return h ? (int64_t)h->logl.size() : 0; }
+void mpgpu_treels_logl(const mpgpu_treels *h, double *out) { if (h && !h->logl.empty()) memcpy(out, h->logl.data(), h->logl.size() * sizeof(double)); }
+int64_t mpgpu_treels_num_materialized(const mpgpu_treels *h) { return h ? (int64_t)h->mats.size() / 4 : 0; }
+void mpgpu_treels_materialized(const mpgpu_treels *h, int64_t *out) { if (h && !h->mats.empty()) memcpy(out, h->mats.data(), h->mats.size() * sizeof(int64_t)); }
+void mpgpu_treels_hooks(mpgpu_treels *h, mpgpu_rng_fn rng, void *rng_user, mpgpu_bb_hooks *out)
+{
+    h->rng = rng; h->rng_user = rng_user;
+    out->user = h;
+    out->random_double = hook_rng;
+    out->push_tree_logl = hook_push;
+    out->materialize = hook_materialize;
+}
+
+}  // extern "C"

@@ -58,12 +58,73 @@ def lib():
     L.mpgpu_scan_plan_bytes.argtypes = [vp]
     L.mpgpu_scan_finish.argtypes = [vp, vp, vp, vp, vp, i32]
     L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.mpgpu_load_replicates.argtypes = [vp, i32, vp, i32, vp, i32]
+    L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
+    L.mpgpu_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.mpgpu_reps_current_tree.argtypes = [vp, vp]
+    L.mpgpu_reps_candidates.argtypes = [vp, vp, i32, vp]
+    L.mpgpu_optimize_spr_bb.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.mpgpu_treels_create.restype = vp
+    L.mpgpu_treels_create.argtypes = [i32]
+    L.mpgpu_treels_destroy.argtypes = [vp]
+    L.mpgpu_treels_size.restype = i64
+    L.mpgpu_treels_size.argtypes = [vp]
+    L.mpgpu_treels_logl.argtypes = [vp, vp]
+    L.mpgpu_treels_num_materialized.restype = i64
+    L.mpgpu_treels_num_materialized.argtypes = [vp]
+    L.mpgpu_treels_materialized.argtypes = [vp, vp]
+    L.mpgpu_treels_hooks.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class BBHooks(C.Structure):
+    """mpgpu_bb_hooks (include/mpgpu.h)"""
+    _fields_ = [("user", C.c_void_p), ("random_double", C.c_void_p), ("push_tree_logl", C.c_void_p),
+                ("materialize", C.c_void_p)]
+
+
+class BBState(C.Structure):
+    """mpgpu_bb_state (include/mpgpu.h)"""
+    _fields_ = [("B", C.c_int32), ("boot_logl", C.c_void_p), ("boot_counts", C.c_void_p), ("boot_trees", C.c_void_p),
+                ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64)]
+
+
+class Treels:
+    """mpgpu_treels: the host-side treels / treels_logl container of include/mpgpu.h."""
+
+    def __init__(self, ntaxa):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.mpgpu_treels_create(ntaxa))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.mpgpu_treels_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def hooks(self, rng_fn_ptr):
+        hk = BBHooks()
+        self.L.mpgpu_treels_hooks(self.h, C.c_void_p(rng_fn_ptr), None, C.byref(hk))
+        return hk
+
+    def logl(self):
+        k = self.L.mpgpu_treels_size(self.h)
+        out = np.zeros(max(k, 1), dtype=np.float64)
+        self.L.mpgpu_treels_logl(self.h, _p(out))
+        return out[:k]
+
+    def materialized(self):
+        k = self.L.mpgpu_treels_num_materialized(self.h)
+        out = np.zeros((max(k, 1), 4), dtype=np.int64)
+        self.L.mpgpu_treels_materialized(self.h, _p(out))
+        return out[:k]
 
 
 def device_count():
@@ -216,6 +277,46 @@ class Engine:
         self._ck(self.L.mpgpu_optimize_spr(self.h, _p(bn), _p(bs), mintrav, maxtrav,
                                            C.c_void_p(rng_fn_ptr), None, C.byref(best), C.byref(nins)))
         return best.value, bn, bs, nins.value
+
+    # -- R8 / -bb
+    def set_option(self, name, value):
+        self._ck(self.L.mpgpu_set_option(self.h, name.encode(), int(value)))
+
+    def load_replicates(self, boot, segment_upper):
+        boot = np.ascontiguousarray(boot, dtype=np.uint16)
+        seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
+        self.B = boot.shape[0]
+        self._ck(self.L.mpgpu_load_replicates(self.h, boot.shape[0], _p(boot), boot.shape[1], _p(seg), len(seg)))
+
+    def reps_info(self):
+        g, e, t = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.mpgpu_reps_info(self.h, C.byref(g), C.byref(e), C.byref(t)))
+        return g.value, e.value, t.value
+
+    def reps_current_tree(self):
+        out = np.zeros(self.B, dtype=np.int32)
+        self._ck(self.L.mpgpu_reps_current_tree(self.h, _p(out)))
+        return out
+
+    def reps_candidates(self, cand_idx):
+        idx = np.ascontiguousarray(cand_idx, dtype=np.int32)
+        out = np.zeros((len(idx), self.B), dtype=np.int32)
+        self._ck(self.L.mpgpu_reps_candidates(self.h, _p(idx), len(idx), _p(out)))
+        return out
+
+    def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
+                        mintrav=1, maxtrav=6):
+        """pllOptimizeSprParsimony + saveCurrentTree (default policy).  hooks: BBHooks (e.g.
+        Treels.hooks(rng)); boot_* arrays are updated in place.  Returns (startMP, back_node,
+        back_slot, insertions scored, saveCurrentTree calls, REPS vectors used)."""
+        bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
+        assert boot_logl.dtype == np.float64 and boot_counts.dtype == np.int32 and boot_trees.dtype == np.int32
+        st = BBState(len(boot_logl), boot_logl.ctypes.data, boot_counts.ctypes.data, boot_trees.ctypes.data,
+                     float(logl_cutoff), float(eps), 0, 0)
+        best = C.c_uint32(); nins = C.c_int64()
+        self._ck(self.L.mpgpu_optimize_spr_bb(self.h, _p(bn), _p(bs), mintrav, maxtrav, C.byref(hooks), C.byref(st),
+                                              C.byref(best), C.byref(nins)))
+        return best.value, bn, bs, nins.value, st.n_calls, st.n_reps
 
     def synchronize(self):
         self._ck(self.L.mpgpu_synchronize(self.h))

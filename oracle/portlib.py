@@ -62,6 +62,8 @@ def lib():
         L.mporacle_undetermined.argtypes = [i]
         L.mporacle_reps.argtypes = [vp, vp, i, i, vp, i, vp]
         L.mporacle_segments.argtypes = [vp, vp, i, i, vp]
+        from .reflib import _boot_protos
+        _boot_protos(L, "mporacle")
         _lib = L
     return _lib
 
@@ -83,7 +85,15 @@ def rng_fn_address():
     return C.cast(lib().mporacle_random_double, C.c_void_p).value
 
 
-class OracleEngine:
+from .reflib import BootMixin  # noqa: E402  (pure-Python mixin, loads no library)
+
+
+class OracleEngine(BootMixin):
+    _pre = "mporacle"
+
+    def _L(self):
+        return lib()
+
     def __init__(self, codes, weights, datatype, sort_alignment=True):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         weights = np.ascontiguousarray(weights, dtype=np.int32)

@@ -77,11 +77,16 @@ struct mpref {
     std::vector<unsigned short> saved_ptn;   /* P per call when record_ptn */
     int record_ptn;
     bool allocated;
+    struct BootSim *boot;                 /* -bb bookkeeping of IQTree::saveCurrentTree (re-typed below) */
 };
+
+static void boot_save_current_tree(mpref *h, double cur_logl);
+
 
 static void save_hook(void *user, double cur_logl)
 {
     mpref *h = (mpref *)user;
+    if (h->boot) boot_save_current_tree(h, cur_logl);
     h->saved_mp.push_back((int)(-cur_logl));
     if (h->record_ptn) {
         size_t off = h->saved_ptn.size();
@@ -112,7 +117,7 @@ MPREF_API mpref *mpref_create(int n, int P, int datatype, const unsigned char *c
     if (S < 0 || n < 4 || P < 1) return NULL;
     mpref *h = new mpref();
     h->n = n; h->P = P; h->datatype = datatype; h->states = S;
-    h->record_ptn = 0; h->allocated = false;
+    h->record_ptn = 0; h->allocated = false; h->boot = NULL;
 
     pllInstance *tr = (pllInstance *)calloc(1, sizeof(pllInstance));
     partitionList *pr = (partitionList *)calloc(1, sizeof(partitionList));
@@ -184,6 +189,7 @@ MPREF_API mpref *mpref_create(int n, int P, int datatype, const unsigned char *c
 
 static void make_current(mpref *h) { globalParam = &h->params; iqtree = &h->iq; }
 
+MPREF_API void mpref_boot_free(mpref *h);
 MPREF_API void mpref_destroy(mpref *h)
 {
     if (!h) return;
@@ -193,6 +199,7 @@ MPREF_API void mpref_destroy(mpref *h)
     free(h->pool); free(h->pr->partitionData); free(h->pinfo); free(h->pr); free(h->tr);
     if (globalParam == &h->params) globalParam = NULL;
     if (iqtree == &h->iq) iqtree = NULL;
+    mpref_boot_free(h);
     delete h;
 }
 
@@ -465,4 +472,167 @@ MPREF_API unsigned long mpref_sweep_count_insertions(mpref *h, int mintrav, int 
     }
     (void)g_insert_counter;
     return total;
+}
+
+/* ---- -bb bookkeeping: IQTree::saveCurrentTree (iqtree.cpp:3271-3760), default policy ------
+ * Re-typed (class IQTree cannot be linked, see the header of this file) for maximum_parsimony,
+ * spr_parsimony, !store_candidate_trees, !multiple_hits, distinct_iter_top_boot < 1,
+ * !auto_vectorize, !do_first_rell, outside ratchet iterations.  The REPS loop runs on the
+ * reference's own Vec16us (load_a on 32-byte aligned buffers, as iqtree.cpp:3428); pattern
+ * scores come from the reference's pllComputePatternParsimony; the skip bound is
+ * pllComputeRellRemainBound (:3821-3858) over pllCalcMinParsScorePattern and ras_pars_score. */
+#include <map>
+struct BootSim {
+    int B, stride, nseg;
+    std::vector<unsigned short *> boot_samples_pars;          /* aligned, P+16, zero padded (:220-233) */
+    std::vector<int> segment_upper;
+    std::vector<std::vector<int> > remain;                   /* boot_samples_pars_remain_bounds */
+    bool use_skip;
+    std::vector<double> boot_logl, treels_logl;
+    std::vector<int> boot_counts, boot_trees;
+    double logl_cutoff, eps;
+    unsigned short *pattern_pars;                            /* _pattern_pars */
+    long calls, reps_rows, skipped, bad_sum;
+    std::map<unsigned long long, int> treels;                /* topology fingerprint -> tree_index */
+    std::vector<long long> mat;                              /* 5 per materialised tree */
+};
+
+static void *aligned32(size_t bytes) { void *p = NULL; if (posix_memalign(&p, 32, bytes)) return NULL; memset(p, 0, bytes); return p; }
+
+static unsigned long long fin64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static unsigned long long topo_hash(pllInstance *tr, nodeptr p)
+{
+    if (p->number <= tr->mxtips) return fin64((unsigned long long)p->number);
+    unsigned long long a = topo_hash(tr, p->next->back), b = topo_hash(tr, p->next->next->back);
+    if (a > b) std::swap(a, b);
+    return fin64(a * 0x9E3779B97F4A7C15ULL + b + 0x632BE59BD9B4E019ULL);
+}
+MPREF_API unsigned long long mpref_tree_fingerprint(mpref *h) { return fin64(topo_hash(h->tr, h->base[1]->back) ^ 0x1234567ULL); }
+
+MPREF_API void mpref_boot_free(mpref *h)
+{
+    BootSim *b = h->boot;
+    if (!b) return;
+    for (size_t i = 0; i < b->boot_samples_pars.size(); i++) free(b->boot_samples_pars[i]);
+    free(b->pattern_pars);
+    delete b;
+    h->boot = NULL;
+}
+
+MPREF_API void mpref_boot_init(mpref *h, int B, const unsigned short *boot, int stride, const int *seg_upper, int nseg,
+                              double logl_cutoff, double eps, const int *ras_pars_score)
+{
+    mpref_boot_free(h);
+    BootSim *b = new BootSim();
+    b->B = B; b->nseg = nseg; b->stride = h->P + 16;
+    b->boot_samples_pars.resize(B);
+    for (int s = 0; s < B; s++) {
+        b->boot_samples_pars[s] = (unsigned short *)aligned32(sizeof(unsigned short) * (b->stride + 16));
+        memcpy(b->boot_samples_pars[s], boot + (size_t)s * stride, sizeof(unsigned short) * (stride < h->P ? stride : h->P));
+    }
+    b->segment_upper.assign(seg_upper, seg_upper + nseg);
+    b->use_skip = ras_pars_score != NULL && nseg > 1;
+    if (b->use_skip) {                                   /* pllComputeRellRemainBound(nptn), iqtree.cpp:3821 */
+        int nunit = h->params.sort_alignment ? h->aln.n_informative_patterns : h->P;
+        std::vector<int> min_unit_pars(nunit);
+        for (int i = 0; i < nunit; i++) {
+            int pll_min = pllCalcMinParsScorePattern(h->tr, h->datatype, i);
+            int cur_min = ras_pars_score[i];
+            min_unit_pars[i] = (pll_min < cur_min) ? pll_min : cur_min;
+        }
+        b->remain.resize(B);
+        for (int s = 0; s < B; s++) {
+            b->remain[s].resize(nseg - 1);
+            for (int g = 0; g < nseg - 1; g++) {
+                int remain = 0;
+                for (int pos = seg_upper[g]; pos < nunit; pos++) remain += min_unit_pars[pos] * b->boot_samples_pars[s][pos];
+                b->remain[s][g] = remain;
+            }
+        }
+    }
+    b->boot_logl.assign(B, -(double)LONG_MAX);           /* iqtree.cpp:248 */
+    b->boot_trees.assign(B, -1); b->boot_counts.assign(B, 0);
+    b->logl_cutoff = logl_cutoff; b->eps = eps;
+    b->pattern_pars = (unsigned short *)aligned32(sizeof(unsigned short) * (b->stride + 16));
+    b->calls = b->reps_rows = b->skipped = b->bad_sum = 0;
+    h->boot = b;
+}
+
+MPREF_API void mpref_boot_set_cutoff(mpref *h, double c) { if (h->boot) h->boot->logl_cutoff = c; }
+MPREF_API void mpref_boot_set_state(mpref *h, const double *bl, const int *bc, const int *bt)
+{
+    BootSim *b = h->boot;
+    b->boot_logl.assign(bl, bl + b->B); b->boot_counts.assign(bc, bc + b->B); b->boot_trees.assign(bt, bt + b->B);
+}
+MPREF_API void mpref_boot_get_state(mpref *h, double *bl, int *bc, int *bt)
+{
+    BootSim *b = h->boot;
+    memcpy(bl, &b->boot_logl[0], sizeof(double) * b->B);
+    memcpy(bc, &b->boot_counts[0], sizeof(int) * b->B);
+    memcpy(bt, &b->boot_trees[0], sizeof(int) * b->B);
+}
+MPREF_API long mpref_boot_counters(mpref *h, long *out4)
+{
+    BootSim *b = h->boot;
+    out4[0] = b->calls; out4[1] = (long)b->treels_logl.size(); out4[2] = b->reps_rows; out4[3] = b->skipped;
+    return b->bad_sum;
+}
+MPREF_API void mpref_boot_treels(mpref *h, double *out) { if (!h->boot->treels_logl.empty()) memcpy(out, &h->boot->treels_logl[0], sizeof(double) * h->boot->treels_logl.size()); }
+MPREF_API int mpref_boot_nmat(mpref *h) { return (int)(h->boot->mat.size() / 5); }
+MPREF_API void mpref_boot_mats(mpref *h, long long *out) { if (!h->boot->mat.empty()) memcpy(out, &h->boot->mat[0], sizeof(long long) * h->boot->mat.size()); }
+
+static void boot_save_current_tree(mpref *h, double cur_logl)
+{
+    BootSim *b = h->boot;
+    long call = b->calls++;
+    if (b->logl_cutoff != 0.0 && cur_logl <= b->logl_cutoff - 1e-4) return;              /* :3343 */
+    int tree_index = (int)b->treels_logl.size();                                          /* :3345 */
+    b->treels_logl.push_back(cur_logl);
+    int test_pars = 0;
+    pllComputePatternParsimony(h->tr, h->pr, b->pattern_pars, &test_pars);                 /* :3365 */
+    if (test_pars != -int(cur_logl)) b->bad_sum++;                                         /* :3366 */
+    b->reps_rows++;
+    bool have_str = false;
+    unsigned short *_pattern_pars = b->pattern_pars;
+    int reps_segments = b->nseg;
+    for (int sample = 0; sample < b->B; sample++) {                                        /* :3405 */
+        double rell = 0.0;
+        bool skipped = false;
+        unsigned short *boot_sample = b->boot_samples_pars[sample];
+        int ptn = 0, segment_id = 0, res = 0;
+        Vec16us vc_rell = 0;
+        for (; segment_id < reps_segments; segment_id++) {                                 /* :3424 */
+            for (; ptn < b->segment_upper[segment_id]; ptn += 16)
+                vc_rell = Vec16us().load_a(&_pattern_pars[ptn]) * Vec16us().load_a(&boot_sample[ptn]) + vc_rell;
+            res += horizontal_add(vc_rell);
+            vc_rell = 0;
+            if ((!skipped) && b->use_skip && (reps_segments > 1) && (segment_id > reps_segments / 4) && (segment_id < reps_segments - 1)) {
+                int reps_total = res + b->remain[sample][segment_id];
+                if ((double)(-reps_total) < b->boot_logl[sample] - b->eps) { skipped = true; break; }
+            }
+        }
+        rell = -(double)res;
+        if (skipped) { b->skipped++; continue; }                                           /* :3484 */
+        if (rell > b->boot_logl[sample] + b->eps
+            || (rell > b->boot_logl[sample] - b->eps && random_double() <= 1.0 / (b->boot_counts[sample] + 1))) {   /* :3689 */
+            if (!have_str) {                                                               /* :3692-3708 */
+                have_str = true;
+                unsigned long long fp = mpref_tree_fingerprint(h);
+                std::map<unsigned long long, int>::iterator it = b->treels.find(fp);
+                if (it != b->treels.end()) tree_index = it->second;
+                else { tree_index = (int)b->treels_logl.size() - 1; b->treels[fp] = tree_index; }
+                long long m[5] = { call, 0, 0, tree_index, (long long)fp };
+                b->mat.insert(b->mat.end(), m, m + 5);
+            }
+            if (rell > b->boot_logl[sample]) b->boot_counts[sample] = 1;                   /* :3712 */
+            b->boot_logl[sample] = std::max(b->boot_logl[sample], rell);                   /* :3720 */
+            b->boot_trees[sample] = tree_index;
+        }
+        if (rell == b->boot_logl[sample]) b->boot_counts[sample]++;                        /* :3729 */
+    }
 }

@@ -57,12 +57,89 @@ def lib():
         L.mpref_reps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.mpref_sweep_count_insertions.restype = C.c_ulong
         L.mpref_sweep_count_insertions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        _boot_protos(L, "mpref")
         _lib = L
     return _lib
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def _boot_protos(L, pre):
+    vp, i = C.c_void_p, C.c_int
+    getattr(L, pre + "_tree_fingerprint").restype = C.c_uint64
+    getattr(L, pre + "_tree_fingerprint").argtypes = [vp]
+    getattr(L, pre + "_boot_init").argtypes = [vp, i, vp, i, vp, i, C.c_double, C.c_double, vp]
+    getattr(L, pre + "_boot_free").argtypes = [vp]
+    getattr(L, pre + "_boot_set_cutoff").argtypes = [vp, C.c_double]
+    getattr(L, pre + "_boot_set_state").argtypes = [vp, vp, vp, vp]
+    getattr(L, pre + "_boot_get_state").argtypes = [vp, vp, vp, vp]
+    getattr(L, pre + "_boot_counters").restype = C.c_long
+    getattr(L, pre + "_boot_counters").argtypes = [vp, vp]
+    getattr(L, pre + "_boot_treels").argtypes = [vp, vp]
+    getattr(L, pre + "_boot_nmat").argtypes = [vp]
+    getattr(L, pre + "_boot_mats").argtypes = [vp, vp]
+
+
+class BootMixin:
+    """-bb bookkeeping of IQTree::saveCurrentTree (default policy) attached to an engine: every
+    saveCurrentTree up-call of the search then runs cutoff filter, REPS and the per-replicate
+    best-tree update.  `bound` = per-pattern lower bound for the skip test (reference driver:
+    ras_pars_score, combined with pllCalcMinParsScorePattern inside; C port: the final
+    min_unit_pars) or None to run without the skip test."""
+    _pre = None
+
+    def _f(self, name):
+        return getattr(self._L(), self._pre + name)
+
+    def boot_init(self, boot, segment_upper, logl_cutoff=0.0, eps=0.5, bound=None):
+        boot = np.ascontiguousarray(boot, dtype=np.uint16)
+        seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
+        self._B = boot.shape[0]
+        b = None if bound is None else np.ascontiguousarray(bound, dtype=np.int32)
+        self._f("_boot_init")(self.h, boot.shape[0], _p(boot), boot.shape[1], _p(seg), len(seg),
+                              float(logl_cutoff), float(eps), None if b is None else _p(b))
+
+    def boot_free(self):
+        self._f("_boot_free")(self.h)
+
+    def boot_set_cutoff(self, c):
+        self._f("_boot_set_cutoff")(self.h, float(c))
+
+    def boot_set_state(self, boot_logl, boot_counts, boot_trees):
+        a = np.ascontiguousarray(boot_logl, dtype=np.float64)
+        b = np.ascontiguousarray(boot_counts, dtype=np.int32)
+        c = np.ascontiguousarray(boot_trees, dtype=np.int32)
+        self._f("_boot_set_state")(self.h, _p(a), _p(b), _p(c))
+
+    def boot_state(self):
+        a = np.zeros(self._B, dtype=np.float64); b = np.zeros(self._B, dtype=np.int32); c = np.zeros(self._B, dtype=np.int32)
+        self._f("_boot_get_state")(self.h, _p(a), _p(b), _p(c))
+        return a, b, c
+
+    def boot_counters(self):
+        """(saveCurrentTree calls, treels_logl size, REPS rows, skipped replicates, bad pattern sums)"""
+        out = np.zeros(4, dtype=np.int64)
+        bad = self._f("_boot_counters")(self.h, _p(out))
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3]), int(bad)
+
+    def boot_treels(self):
+        out = np.zeros(max(self.boot_counters()[1], 1), dtype=np.float64)
+        self._f("_boot_treels")(self.h, _p(out))
+        return out[: self.boot_counters()[1]]
+
+    def boot_mats(self):
+        """rows (call index, pruned ref, insertion ref, tree_index, topology fingerprint) of every tree
+        materialised because it won a replicate (iqtree.cpp:3692-3708); refs are 0 for the reference
+        driver (it sees only the tree)."""
+        k = self._f("_boot_nmat")(self.h)
+        out = np.zeros((max(k, 1), 5), dtype=np.int64)
+        self._f("_boot_mats")(self.h, _p(out))
+        return out[:k]
+
+    def fingerprint(self):
+        return int(self._f("_tree_fingerprint")(self.h))
 
 
 def char_map(datatype):
@@ -77,8 +154,12 @@ def bitvector(datatype, ncodes):
     return out, und
 
 
-class RefEngine:
+class RefEngine(BootMixin):
     """One reference pllInstance + partitionList over an ASCII pattern matrix."""
+    _pre = "mpref"
+
+    def _L(self):
+        return lib()
 
     def __init__(self, chars, weights, datatype, sort_alignment=True, n_informative=None):
         chars = np.ascontiguousarray(chars, dtype=np.uint8)

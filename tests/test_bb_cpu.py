@@ -1,0 +1,84 @@
+"""CPU suite for the -bb bookkeeping oracle: the C port's restatement of IQTree::saveCurrentTree
+(default policy) against the reference driver's re-typed copy (which runs the reference's own
+search, pattern-score and Vec16us code), on whole -bb SPR searches: same treels_logl, same
+per-replicate best trees/scores/counts, same RNG draws, same materialised topologies."""
+import numpy as np
+import pytest
+
+from oracle import portlib, reflib
+from tests.helpers import make_case, make_boot, segments_for, fingerprint_ring
+
+needs_ref = pytest.mark.skipif(not reflib.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def bb_setup(n, L, dt, seed, B, mu=0.05, art_segments=True, heavy=True):
+    c = make_case(n, L, dt, seed, mu=mu)
+    o = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    o.set_ring(c["bn"], c["bs"]); o.allocate(True)
+    s0 = o.evaluate_full(True)
+    pp, _ = o.pattern_parsimony(c["n_inf"])
+    ninf = c["n_inf"]
+    if art_segments and ninf > 64:          # several segments (multiples of 16, last = n_inf)
+        seg = np.array([16, 48, 16 * (ninf // 32), ninf], dtype=np.int32)
+        seg = np.unique(seg)
+    else:
+        seg = segments_for(pp, c["weights"], ninf)
+    hv = None
+    if heavy:                               # u16 lane products / sums that wrap, weights > 255
+        hv = [(1, 3, 40000), (2, 5, 300), (2, 6, 65535)] + [(3, k, 900) for k in range(0, min(ninf, 40))]
+    boot = make_boot(c, B, seed, heavy=hv)
+    minp = np.array([o.min_pars_pattern(i) for i in range(ninf)], dtype=np.int32)
+    P = c["codes"].shape[1]
+    ras = np.zeros(P, dtype=np.int32); ras[:ninf] = pp
+    bound = np.zeros(P, dtype=np.int32); bound[:ninf] = np.minimum(minp, pp)
+    return c, o, s0, pp, seg, boot, ras, bound
+
+
+def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6):
+    eng.set_ring(c["bn"], c["bs"])
+    eng.allocate(per_site=True)
+    eng.boot_init(boot, seg, cutoff, 0.5, bound)
+    (reflib.lib().mpref_seed_rng if is_ref else portlib.seed_rng)(seed)
+    eng.record(False)
+    ret = eng.optimize_spr(1, mt, bb=True)
+    draws = reflib.lib().mpref_rng_draws() if is_ref else portlib.rng_draws()
+    return dict(ret=ret, draws=draws, ring=eng.get_ring(), state=eng.boot_state(), counters=eng.boot_counters(),
+                treels=eng.boot_treels(), mats=eng.boot_mats(), saved=eng.saved())
+
+
+def same(a, b):
+    assert a["ret"] == b["ret"] and a["draws"] == b["draws"]
+    assert all(np.array_equal(x, y) for x, y in zip(a["ring"], b["ring"]))
+    assert all(np.array_equal(x, y) for x, y in zip(a["state"], b["state"]))
+    assert a["counters"] == b["counters"] and a["counters"][4] == 0
+    assert np.array_equal(a["treels"], b["treels"]) and np.array_equal(a["saved"], b["saved"])
+    assert np.array_equal(a["mats"][:, [0, 3, 4]], b["mats"][:, [0, 3, 4]])
+
+
+@needs_ref
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05),
+                                               (30, 800, 1, 21, 64, 0.01), (20, 300, 6, 9, 30, 0.05)])
+def test_port_bb_equals_reference(n, L, dt, seed, B, mu):
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    plain = run_bb(o, c, boot, seg, 0.0, None, False)
+    same(plain, run_bb(r, c, boot, seg, 0.0, None, True))
+    cutoff = -(plain["ret"] + 4.0)                      # keeps roughly the best candidates only
+    a = run_bb(o, c, boot, seg, cutoff, bound, False)
+    same(a, run_bb(r, c, boot, seg, cutoff, ras, True))
+    assert a["counters"][1] < a["counters"][0]          # the cutoff dropped candidates
+    # the skip test is decision-neutral
+    b = run_bb(o, c, boot, seg, cutoff, None, False)
+    for k in ("ret", "draws"):
+        assert a[k] == b[k]
+    assert all(np.array_equal(x, y) for x, y in zip(a["state"], b["state"]))
+    assert np.array_equal(a["mats"], b["mats"])
+
+
+def test_fingerprint_matches_python_helper():
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(16, 300, 1, 3, 8)
+    res = run_bb(o, c, boot, seg, 0.0, None, False)
+    bn, bs = res["ring"]
+    assert fingerprint_ring(bn, bs, 16) == o.fingerprint() % (1 << 64)
+    m = res["mats"]
+    assert len(m) > 0 and (m[:, 3] >= 0).all()

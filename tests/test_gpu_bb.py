@@ -1,0 +1,90 @@
+"""GPU parity tests of the -bb path (R8 + the -bb search): replicate scores from the device
+(int8 tensor-core contraction + exact exception path) against the oracle's u16-lane REPS on the
+same pattern vectors, and whole -bb SPR searches against the oracle's restatement of
+IQTree::saveCurrentTree (itself pinned to the reference driver by tests/test_bb_cpu.py).
+Bit-exact: integers only."""
+import numpy as np
+import pytest
+
+from oracle import portlib
+from tests.helpers import fingerprint_ring
+from tests.test_bb_cpu import bb_setup, run_bb
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05), (30, 800, 1, 21, 64, 0.01), (20, 300, 6, 9, 30, 0.05),
+         (40, 1500, 1, 11, 300, 0.05), (16, 300, 0, 3, 20, 0.05)]
+
+
+def _engine(c, boot, seg, tensor):
+    from mpboot_b200.engine import Engine
+    eng = Engine()
+    eng.set_option("reps_tensor", tensor)
+    eng.load_alignment(c["codes"], c["weights"], c["datatype"])
+    eng.set_tree(c["bn"], c["bs"])
+    eng.load_replicates(boot, seg)
+    return eng
+
+
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES)
+def test_reps_current_tree_and_candidates(n, L, dt, seed, B, mu, tensor):
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    eng = _engine(c, boot, seg, tensor)
+    groups, exc, t = eng.reps_info()
+    assert t == tensor and groups >= 2 and exc > 0            # the heavy replicates force wrap-prone segments
+    want = portlib.reps(pp, boot[:, : c["n_inf"]], seg)
+    assert np.array_equal(eng.reps_current_tree(), want)
+    # every saveCurrentTree call of three node visits: current tree first, then each insertion
+    order = eng.visit_order()
+    for i in (1, n + 1, 2 * n - 2):
+        o.set_ring(c["bn"], c["bs"]); o.allocate(True); o.evaluate_full(True)
+        o.record(True)
+        o.rearrange(i, 1, 6, True, s0)
+        mps, ptn = o.saved(True)
+        vb, mp, cref, cprune = eng.scan_visits(order, i, 1, 1, 6)
+        assert np.array_equal(mps[1:], mp.astype(np.int32))
+        got = eng.reps_candidates(np.arange(-1, len(mp), dtype=np.int32))
+        for k in range(len(mps)):
+            assert np.array_equal(got[k], portlib.reps(ptn[k, : c["n_inf"]], boot[:, : c["n_inf"]], seg)), (i, k)
+
+
+def test_reps_wrap_free_bulk_uses_no_exceptions():
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(40, 1500, 1, 11, 100, heavy=False)
+    eng = _engine(c, boot, seg, 1)
+    groups, exc, t = eng.reps_info()
+    assert groups == 1 and exc == 0 and t == 1                # everything on the tensor path
+    assert np.array_equal(eng.reps_current_tree(), portlib.reps(pp, boot[:, : c["n_inf"]], seg))
+
+
+def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6):
+    from mpboot_b200.engine import Treels
+    eng = _engine(c, boot, seg, tensor)
+    B = boot.shape[0]
+    bl = np.full(B, -float(np.iinfo(np.int64).max), dtype=np.float64)   # -LONG_MAX, iqtree.cpp:248
+    bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
+    tl = Treels(c["n"])
+    portlib.seed_rng(seed)
+    ret, bn, bs, nins, ncalls, nreps = eng.optimize_spr_bb(c["bn"], c["bs"], tl.hooks(portlib.rng_fn_address()),
+                                                           bl, bc, bt, cutoff, 0.5, 1, mt)
+    return dict(ret=ret, draws=portlib.rng_draws(), ring=(bn, bs), state=(bl, bc, bt), ncalls=ncalls, nreps=nreps,
+                treels=tl.logl(), mats=tl.materialized(), nins=nins)
+
+
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES[:5])
+def test_bb_search_matches_oracle(n, L, dt, seed, B, mu, tensor):
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    want = run_bb(o, c, boot, seg, 0.0, None, False)
+    for cutoff in (0.0, -(want["ret"] + 4.0)):
+        w = run_bb(o, c, boot, seg, cutoff, None, False)
+        g = _run_gpu_bb(c, boot, seg, cutoff, tensor)
+        assert g["ret"] == w["ret"] and g["draws"] == w["draws"]
+        assert np.array_equal(g["ring"][0][3:], w["ring"][0][3:]) and np.array_equal(g["ring"][1][3:], w["ring"][1][3:])
+        assert all(np.array_equal(x, y) for x, y in zip(g["state"], w["state"]))          # boot_logl, boot_counts, boot_trees
+        assert g["ncalls"] == w["counters"][0] and g["nreps"] == w["counters"][2]
+        assert np.array_equal(g["treels"], w["treels"])
+        wm = w["mats"]
+        assert len(g["mats"]) == len(wm)
+        assert np.array_equal(g["mats"][:, :3], wm[:, 1:4])                              # pruned ref, insertion ref, tree_index
+        assert np.array_equal(g["mats"][:, 3], wm[:, 4])                                 # topology fingerprint
