@@ -50,6 +50,21 @@ def build_case(name, nshards):
     return prep
 
 
+def do_segmenting(scores, weights, n_informative):
+    """IQTree::doSegmenting (iqtree.cpp:3793-3819): a new REPS segment every time the running
+    sum of ras_pars_score * frequency exceeds USHRT_MAX / 16 at a multiple of 16 patterns."""
+    seg, run = [], 0
+    prod = np.zeros(len(weights), dtype=np.int64)
+    prod[: len(scores)] = np.asarray(scores, dtype=np.int64) * np.asarray(weights[: len(scores)], dtype=np.int64)
+    for i in range(len(weights)):
+        run += int(prod[i])
+        if (i + 1) % 16 == 0 and run > 65535 // 16:
+            seg.append(i + 1); run = 0
+    if run:
+        seg.append(n_informative)
+    return np.array(seg, dtype=np.int32)
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"

@@ -157,8 +157,12 @@ int mpgpu_load_replicates(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples, i
 /* groups = 1 + wrap-prone segments, exceptions = patterns on the exact CUDA-core path,
  * tensor = 1 when the tcgen05 path is enabled.  Any pointer may be NULL. */
 int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
-/* Options: "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests). */
+/* Options: "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests);
+ * "reps_timing" 0/1 (CUDA events around the largest tensor-kernel launch, read by mpgpu_reps_timing). */
 int mpgpu_set_option(mpgpu_ctx *ctx, const char *name, int value);
+/* Device time (ms, CUDA events on the context's stream) of the largest tensor-kernel launch since the
+ * last call, with its shape: rows x patterns (K, padded to 128) x replicates, and the K splits used. */
+int mpgpu_reps_timing(mpgpu_ctx *ctx, float *tc_ms, int *rows, int *patterns, int *splits);
 /* res[b] = -rell[b] of the CURRENT tree for b < B (what the loop at :3424-3449 leaves in `res`
  * when no replicate is skipped).  Single shard. */
 int mpgpu_reps_current_tree(mpgpu_ctx *ctx, int32_t *res);
@@ -167,6 +171,10 @@ int mpgpu_reps_current_tree(mpgpu_ctx *ctx, int32_t *res);
  * saveCurrentTree would compute inside testInsertParsimony (:2163-2166) for that insertion.
  * Single shard. */
 int mpgpu_reps_candidates(mpgpu_ctx *ctx, const int32_t *cand_idx, int m, int32_t *res);
+/* Asynchronous form: the vectors stay on the device, *dev_res = int32 [m][*pitch] (valid until
+ * the next REPS call on this context, ordered on the context's stream).  The batch must fit the
+ * row buffers in one piece. */
+int mpgpu_reps_candidates_device(mpgpu_ctx *ctx, const int32_t *cand_idx, int m, void **dev_res, int *pitch);
 
 /* ---- pllOptimizeSprParsimony under -bb: search + saveCurrentTree, default policy ----
  * Replaces the pair pllOptimizeSprParsimony (sprparsimony.cpp:3244) / IQTree::saveCurrentTree

@@ -261,7 +261,13 @@ int ensure_ptn_site(Ctx *c)
     const int upper = c->sort_alignment ? c->n_inf : c->P;
     std::vector<int64_t> ptn_site(upper > 0 ? upper : 1);
     int64_t site = 0;
-    for (int i = 0; i < upper; i++) { ptn_site[i] = site < (int64_t)c->ref_words * 32 ? site : -1; site += c->weights[i]; }
+    bool ident = c->shard_count == 1;
+    for (int i = 0; i < upper; i++) {
+        ptn_site[i] = site < (int64_t)c->ref_words * 32 ? site : -1;
+        if (ptn_site[i] != i) ident = false;
+        site += c->weights[i];
+    }
+    c->ptn_identity = ident;
     if (int rc = ensure(c->d_ptn_site, c->ptn_site_cap, ptn_site.size())) return rc;
     MPGPU_CUDA(cudaMemcpyAsync(c->d_ptn_site, ptn_site.data(), ptn_site.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));

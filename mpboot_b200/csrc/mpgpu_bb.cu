@@ -9,21 +9,43 @@
 #include "mpgpu_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 namespace mpgpu {
 
+// wall-clock breakdown of the search loop, printed when MPGPU_PROFILE=1 (development aid)
+struct Prof {
+    bool on = getenv("MPGPU_PROFILE") != nullptr;
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::chrono::steady_clock::time_point t0;
+    void start() { if (on) t0 = std::chrono::steady_clock::now(); }
+    void stop(int k) { if (on) { t[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); n[k]++; } }
+    void report(const char *const *names, int cnt) {
+        if (!on) return;
+        for (int k = 0; k < cnt; k++) fprintf(stderr, "[mpgpu profile] %-12s %9.3f ms  (%ld)\n", names[k], t[k] * 1e3, n[k]);
+    }
+};
+
+static Prof g_rp;      // REPS internals (sections are closed with a stream synchronize when profiling is on)
+static const char *const g_rp_names[] = {"tree:counters", "tree:check", "tree:contract", "chunk:build", "chunk:rows", "chunk:contract", "chunk:combine", "chunk:readback"};
+static inline void rp_stop(Ctx *c, int k) { if (g_rp.on) { cudaStreamSynchronize(c->stream); g_rp.stop(k); g_rp.start(); } }
+
 void free_reps(Ctx *c)
 {
     Reps &r = c->reps;
-    void *ptrs[] = {r.d_w8, r.d_w16e, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
-                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_hit_count, r.d_hits};
+    void *ptrs[] = {r.d_w8, r.d_w16T, r.d_seg_upper, r.d_seg_flags, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
+                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_call_hit, r.d_hit_list, r.d_res_hit};
     for (void *p : ptrs) if (p) cudaFree(p);
-    const bool use_tensor = r.use_tensor;
+    if (r.ev0) { cudaEventDestroy(r.ev0); cudaEventDestroy(r.ev1); }
+    if (r.h_pin) cudaFreeHost(r.h_pin);
+    const bool use_tensor = r.use_tensor, timing = r.timing;
     r = Reps();
-    r.use_tensor = use_tensor;
+    r.use_tensor = use_tensor; r.timing = timing;
     c->d_row_of = nullptr; c->d_row_tasks = nullptr; c->d_rows_site = nullptr;
 }
 
@@ -46,8 +68,10 @@ static void update_kb_range(Ctx *c)
 static int ensure_rows(Ctx *c, int rows)
 {
     Reps &r = c->reps;
+    const bool ident = c->ptn_identity;                    // site rows double as pattern rows: no gather, no second buffer
+    if (!ident && !r.d_rows_ptn) r.row_cap = 0;            // weights changed under us: the pattern-space buffer is needed now
     if (rows <= r.row_cap) return 0;
-    const size_t per_row = (size_t)c->Wl * 4 + (size_t)r.Pw * 4 + (size_t)r.G * r.Bpad * 4;
+    const size_t per_row = (size_t)c->Wl * 4 + (ident ? 0 : (size_t)r.Pw * 4) + (size_t)r.G * r.Bpad * 4;
     size_t budget = (size_t)4 << 30;
     if (const char *e = getenv("MPGPU_REPS_ROW_BYTES")) { long long v = atoll(e); if (v > 0) budget = (size_t)v; }
     int limit = (int)std::min<size_t>(budget / per_row, (size_t)1 << 20);
@@ -60,62 +84,138 @@ static int ensure_rows(Ctx *c, int rows)
     if (r.d_X) cudaFree(r.d_X);
     r.d_rows_site = nullptr; r.d_rows_ptn = nullptr; r.d_X = nullptr; r.row_cap = 0; r.tree_valid = false;
     MPGPU_CUDA(cudaMalloc((void **)&r.d_rows_site, (size_t)want * c->Wl * 4));
-    MPGPU_CUDA(cudaMalloc((void **)&r.d_rows_ptn, (size_t)want * r.Pw * 4));
+    if (!ident) MPGPU_CUDA(cudaMalloc((void **)&r.d_rows_ptn, (size_t)want * r.Pw * 4));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_X, (size_t)want * r.G * r.Bpad * 4));
     r.row_cap = want;
     c->d_rows_site = r.d_rows_site;
     return 0;
 }
 
-// rows [row0, row0+nrows) of d_rows_ptn -> X (all groups)
-static int contract_rows(Ctx *c, int row0, int nrows)
+// pattern-indexed bit rows a_base[0..nrows) -> X[x_row0 ..) (all groups)
+static int contract_rows(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows)
 {
     Reps &r = c->reps;
     if (nrows == 0) return 0;
-    MPGPU_CUDA(cudaMemsetAsync(r.d_X + (size_t)row0 * r.G * r.Bpad, 0, (size_t)nrows * r.G * r.Bpad * 4, c->stream));
-    if (int rc = launch_reps_exc(c, row0, nrows)) return rc;
-    if (r.use_tensor) { if (int rc = launch_reps_tc(c, row0, nrows)) return rc; }
+    MPGPU_CUDA(cudaMemsetAsync(r.d_X + (size_t)x_row0 * r.G * r.Bpad, 0, (size_t)nrows * r.G * r.Bpad * 4, c->stream));
+    if (int rc = launch_reps_exc(c, a_base, a_pitch, x_row0, nrows)) return rc;
+    if (r.use_tensor) { if (int rc = launch_reps_tc(c, a_base, a_pitch, x_row0, nrows)) return rc; }
     r.rows_scored += nrows;
     return 0;
 }
 
-// rows 0..15 = bit planes of the per-site counters of the current tree, row 16 = sum_bit 2^bit * plane
+// Exception lists + tensor operand for the current classification (seg_flagged, heavy):
+// group 0 = everything wrap-free, group g >= 1 = the g-th flagged segment.  Exceptions = all
+// patterns of flagged segments plus, in group 0, the patterns with a weight above 255 (or every
+// pattern when the tensor path is switched off).
+static int build_classification(Ctx *c)
+{
+    Reps &r = c->reps;
+    const int nseg = (int)r.seg_upper.size();
+    std::vector<int> group_of_seg(nseg, 0);
+    int G = 1;
+    for (int g = 0; g < nseg; g++) if (r.seg_flagged[g]) group_of_seg[g] = G++;
+    std::vector<int32_t> exc_ptn, exc_group;
+    std::vector<uint8_t> is_exc(r.Kpad, 0);
+    r.n_heavy = 0;
+    for (int pass = 0; pass < 2; pass++) {                         // group 0 first, then the flagged segments in order
+        int s = 0;
+        for (int p = 0; p < r.upper; p++) {
+            while (p >= r.seg_upper[s]) s++;
+            const int g = group_of_seg[s];
+            if (pass == 0 ? (g == 0 && (r.heavy[p] || !r.use_tensor)) : g > 0) {
+                exc_ptn.push_back(p); exc_group.push_back(g); is_exc[p] = 1;
+                if (g == 0 && r.heavy[p]) r.n_heavy++;
+            }
+        }
+    }
+    if (G != r.G) {                                                 // X changes shape: drop the row buffers
+        if (r.d_rows_site) cudaFree(r.d_rows_site);
+        if (r.d_rows_ptn) cudaFree(r.d_rows_ptn);
+        if (r.d_X) cudaFree(r.d_X);
+        r.d_rows_site = nullptr; r.d_rows_ptn = nullptr; r.d_X = nullptr; r.row_cap = 0;
+        c->d_rows_site = nullptr;
+    }
+    r.G = G;
+    r.n_exc = (int)exc_ptn.size();
+    r.tree_valid = false;
+    if (int rc = ensure(r.d_exc_ptn, r.exc_cap, exc_ptn.size() + 1)) return rc;
+    if (int rc = ensure(r.d_exc_group, r.exc_group_cap, exc_group.size() + 1)) return rc;
+    uint8_t *d_is_exc = nullptr;
+    MPGPU_CUDA(cudaMalloc((void **)&d_is_exc, (size_t)r.Kpad));
+    if (r.n_exc) {
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_exc_ptn, exc_ptn.data(), (size_t)r.n_exc * 4, cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_exc_group, exc_group.data(), (size_t)r.n_exc * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    MPGPU_CUDA(cudaMemcpyAsync(d_is_exc, is_exc.data(), (size_t)r.Kpad, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_build_w8(c, d_is_exc);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_is_exc);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "building the tensor operand");
+    r.reclassifications++;
+    return 0;
+}
+
+// rows 0..15 = bit planes of the per-site counters of the current tree, row 16 = sum_bit 2^bit * plane.
+// Also the wrap check of this tree (k_seg_check): segments that might wrap move to a group of
+// their own before anything is contracted.
 static int refresh_tree_rows(Ctx *c)
 {
     Reps &r = c->reps;
-    if (int rc = ensure_rows(c, kTreeRows + 64)) return rc;
-    if (r.tree_valid) return 0;
+    if (r.tree_valid && r.row_cap > 0) return 0;
     const int nbits = 16;
+    const int nseg = (int)r.seg_upper.size();
+    g_rp.start();
     if (int rc = compute_site_counters(c, nbits)) return rc;
     if (int rc = ensure_ptn_site(c)) return rc;
     update_kb_range(c);
-    if (int rc = launch_gather_rows(c, c->d_bitcnt, r.d_rows_ptn, nbits)) return rc;
-    if (int rc = contract_rows(c, 0, nbits)) return rc;
+    rp_stop(c, 0);
+    // per-pattern scores of the tree -> wrap check
+    const int upper0 = c->sort_alignment ? c->n_inf : c->P;
+    if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper0 > 0 ? upper0 : 1))) return rc;
+    if (int rc = launch_gather_patterns(c, nbits, upper0)) return rc;
+    MPGPU_CUDA(cudaMemsetAsync(r.d_seg_flags, 0, (size_t)nseg, c->stream));
+    if (int rc = launch_seg_check(c, r.d_seg_flags)) return rc;
+    std::vector<uint8_t> flags(nseg);
+    MPGPU_CUDA(cudaMemcpyAsync(flags.data(), r.d_seg_flags, (size_t)nseg, cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    bool grew = false;
+    for (int g = 0; g < nseg; g++) if (flags[g] && !r.seg_flagged[g]) { r.seg_flagged[g] = 1; grew = true; }
+    if (grew) { if (int rc = build_classification(c)) return rc; }
+    rp_stop(c, 1);
+    if (int rc = ensure_rows(c, kTreeRows + 64)) return rc;
+    if (c->ptn_identity) {
+        if (int rc = contract_rows(c, c->d_bitcnt, c->Wl, 0, nbits)) return rc;
+    } else {
+        if (int rc = launch_gather_rows(c, c->d_bitcnt, r.d_rows_ptn, nbits)) return rc;
+        if (int rc = contract_rows(c, r.d_rows_ptn, r.Pw, 0, nbits)) return rc;
+    }
     if (int rc = launch_reps_tree_row(c, 0, nbits, kTreeRows - 1)) return rc;
+    rp_stop(c, 2);
     r.tree_valid = true;
     return 0;
 }
 
-// Result of one REPS batch on the host: per call either a dense row or a hit list
+// Result of one REPS batch on the host: per call its row of B results, or nothing when no
+// replicate of the call can pass its threshold
 struct RepsOut {
     int Bpad = 0;
-    std::vector<int32_t> dense;                   // concatenated dense rows [Bpad]
-    std::vector<int64_t> dense_off;               // per call: offset into dense, -1 = hit list
-    std::vector<int32_t> hit_begin;               // per call: [begin, end) into hit_b / hit_res (when dense_off < 0)
-    std::vector<int32_t> hit_end;
-    std::vector<int32_t> hit_b, hit_res;
+    std::vector<int32_t> dense;                   // concatenated rows [Bpad]
+    std::vector<int64_t> dense_off;               // per call: offset into dense, -1 = no replicate can be affected
 };
 
 // REPS vectors for the calls cands[0..m) of the last planned scan batch (-1 = the current tree),
 // in order.  thr (host, [B], nullable): only entries with res <= thr[b] are needed by the caller.
-static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, RepsOut &out)
+// device_only: enqueue the work of a single chunk and return without reading anything back (d_res holds
+// [m][Bpad] when the stream reaches this point).
+static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, RepsOut &out, bool device_only = false)
 {
     Reps &r = c->reps;
     const ScanPlan &pl = c->plan;
     const HostTree &t = c->tree;
     out.Bpad = r.Bpad;
-    out.dense.clear(); out.hit_b.clear(); out.hit_res.clear();
-    out.dense_off.assign(m, -1); out.hit_begin.assign(m, 0); out.hit_end.assign(m, 0);
+    out.dense.clear();
+    out.dense_off.assign(m, -1);
     if (m == 0) return 0;
     if (int rc = refresh_tree_rows(c)) return rc;
     // rows the whole list would like to have; ensure_rows clamps to the memory budget
@@ -128,17 +228,19 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     const int max_rows = r.row_cap - kTreeRows;
     if (thr) {
         if (!r.d_thr) MPGPU_CUDA(cudaMalloc((void **)&r.d_thr, (size_t)r.Bpad * 4));
-        if (!r.d_hit_count) MPGPU_CUDA(cudaMalloc((void **)&r.d_hit_count, 4));
-        if (!r.d_hits) { r.hit_cap = 1u << 20; MPGPU_CUDA(cudaMalloc((void **)&r.d_hits, (size_t)r.hit_cap * sizeof(int4))); }
         MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.B * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    std::vector<int32_t> row_of(pl.n_cand > 0 ? pl.n_cand : 1);
-    std::vector<int32_t> task_row(pl.tasks.size()), row_tasks;
-    std::vector<int4> edges;
-    std::vector<int2> calls;
-    std::vector<int4> hits;
+    // staging vectors live in the context: asynchronous uploads may still read them after we return
+    std::vector<int32_t> &row_of = r.h_row_of, &row_tasks = r.h_row_tasks;
+    std::vector<int4> &edges = r.h_edges;
+    std::vector<int2> &calls = r.h_calls;
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));             // previous batch's uploads are done with them
+    row_of.assign(pl.n_cand > 0 ? pl.n_cand : 1, -1);
+    std::vector<int32_t> task_row(pl.tasks.size());
+    std::vector<int32_t> hit_list;
     int done = 0;
     while (done < m) {
+        g_rp.start();
         // ---- carve a chunk that fits the row buffers ----
         std::fill(row_of.begin(), row_of.end(), -1);
         std::fill(task_row.begin(), task_row.end(), -1);
@@ -161,7 +263,9 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
             calls.push_back(make_int2(task_row[ti], kTreeRows + row_of[j]));
         }
         if (k == done) { set_error("REPS row buffers too small for a single candidate"); return 1; }
+        if (device_only && k < m) { set_error("REPS batch does not fit the row buffers in one piece (raise MPGPU_REPS_ROW_BYTES)"); return 1; }
         const int ncalls = k - done;
+        rp_stop(c, 3);
         // ---- upload the chunk ----
         if (int rc = ensure(r.d_row_of, r.row_of_cap, row_of.size())) return rc;
         if (int rc = ensure(r.d_row_tasks, r.row_tasks_cap, row_tasks.size() + 1)) return rc;
@@ -177,40 +281,63 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
             // ---- rows: edge rows, delta rows (second pass of the scan), site -> pattern space ----
             if (int rc = launch_edge_rows(c, r.d_edges, (int)edges.size(), r.d_rows_site)) return rc;
             if (int rc = launch_scan_rows(c, (int)row_tasks.size(), pl.max_slot)) return rc;
-            if (int rc = launch_gather_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl,
-                                            r.d_rows_ptn + (size_t)kTreeRows * r.Pw, nrows)) return rc;
-            if (int rc = contract_rows(c, kTreeRows, nrows)) return rc;
+            rp_stop(c, 4);
+            if (c->ptn_identity) {
+                if (int rc = contract_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl, c->Wl, kTreeRows, nrows)) return rc;
+            } else {
+                if (int rc = launch_gather_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl,
+                                                r.d_rows_ptn + (size_t)kTreeRows * r.Pw, nrows)) return rc;
+                if (int rc = contract_rows(c, r.d_rows_ptn + (size_t)kTreeRows * r.Pw, r.Pw, kTreeRows, nrows)) return rc;
+            }
         }
+        rp_stop(c, 5);
         // ---- combine ----
-        if (thr) MPGPU_CUDA(cudaMemsetAsync(r.d_hit_count, 0, 4, c->stream));
-        if (int rc = launch_reps_combine(c, kTreeRows - 1, r.d_calls, ncalls, r.d_res, thr ? r.d_thr : nullptr,
-                                         r.d_hit_count, r.d_hits, r.hit_cap)) return rc;
-        bool dense = true;
         if (thr) {
-            uint32_t nh = 0;
-            MPGPU_CUDA(cudaMemcpyAsync(&nh, r.d_hit_count, 4, cudaMemcpyDeviceToHost, c->stream));
+            if (int rc = ensure(r.d_call_hit, r.call_hit_cap, (size_t)ncalls)) return rc;
+            MPGPU_CUDA(cudaMemsetAsync(r.d_call_hit, 0, (size_t)ncalls * 4, c->stream));
+        }
+        if (int rc = launch_reps_combine(c, kTreeRows - 1, r.d_calls, ncalls, r.d_res, thr ? r.d_thr : nullptr, r.d_call_hit)) return rc;
+        rp_stop(c, 6);
+        if (device_only) return 0;
+        // ---- read back: only the rows of calls that can change a replicate ----
+        bool all_rows = true;
+        if (thr) {
+            int32_t *fl = (int32_t *)r.pinned((size_t)ncalls * 4);
+            if (!fl) { set_error("pinned host allocation failed"); return 2; }
+            MPGPU_CUDA(cudaMemcpyAsync(fl, r.d_call_hit, (size_t)ncalls * 4, cudaMemcpyDeviceToHost, c->stream));
             MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-            if (nh <= r.hit_cap) {
-                dense = false;
-                hits.resize(nh);
-                if (nh) MPGPU_CUDA(cudaMemcpyAsync(hits.data(), r.d_hits, (size_t)nh * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
-                MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-                std::sort(hits.begin(), hits.end(), [](const int4 &a, const int4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
-                size_t h = 0;
-                for (int i = 0; i < ncalls; i++) {
-                    out.hit_begin[done + i] = (int32_t)out.hit_b.size();
-                    while (h < hits.size() && hits[h].x == i) { out.hit_b.push_back(hits[h].y); out.hit_res.push_back(hits[h].z); h++; }
-                    out.hit_end[done + i] = (int32_t)out.hit_b.size();
+            hit_list.clear();
+            for (int i = 0; i < ncalls; i++) if (fl[i]) hit_list.push_back(i);
+            if ((int)hit_list.size() * 2 < ncalls) {
+                all_rows = false;
+                const int nl = (int)hit_list.size();
+                if (nl) {
+                    if (int rc = ensure(r.d_hit_list, r.hit_list_cap, (size_t)nl)) return rc;
+                    if (int rc = ensure(r.d_res_hit, r.res_hit_cap, (size_t)nl * r.Bpad)) return rc;
+                    MPGPU_CUDA(cudaMemcpyAsync(r.d_hit_list, hit_list.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
+                    if (int rc = launch_gather_res_rows(c, r.d_res, r.d_hit_list, nl, r.d_res_hit)) return rc;
+                    const size_t off = out.dense.size(), bytes = (size_t)nl * r.Bpad * 4;
+                    void *hp = r.pinned(bytes);
+                    if (!hp) { set_error("pinned host allocation failed"); return 2; }
+                    MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res_hit, bytes, cudaMemcpyDeviceToHost, c->stream));
+                    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+                    out.dense.resize(off + (size_t)nl * r.Bpad);
+                    memcpy(out.dense.data() + off, hp, bytes);
+                    for (int i = 0; i < nl; i++) out.dense_off[done + hit_list[i]] = (int64_t)(off + (size_t)i * r.Bpad);
                 }
             }
         }
-        if (dense) {
-            const size_t off = out.dense.size();
-            out.dense.resize(off + (size_t)ncalls * r.Bpad);
-            MPGPU_CUDA(cudaMemcpyAsync(out.dense.data() + off, r.d_res, (size_t)ncalls * r.Bpad * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (all_rows) {
+            const size_t off = out.dense.size(), bytes = (size_t)ncalls * r.Bpad * 4;
+            void *hp = r.pinned(bytes);
+            if (!hp) { set_error("pinned host allocation failed"); return 2; }
+            MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res, bytes, cudaMemcpyDeviceToHost, c->stream));
             MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+            out.dense.resize(off + (size_t)ncalls * r.Bpad);
+            memcpy(out.dense.data() + off, hp, bytes);
             for (int i = 0; i < ncalls; i++) out.dense_off[done + i] = (int64_t)(off + (size_t)i * r.Bpad);
         }
+        rp_stop(c, 7);
         done = k;
     }
     return 0;
@@ -250,11 +377,9 @@ static void bb_save(BBRun *bb, Ctx *c, uint32_t mp, const RepsOut &ro, int call,
         }
         if (rell == st->boot_logl[b]) st->boot_counts[b]++;
     };
-    if (ro.dense_off[call] >= 0) {
+    if (ro.dense_off[call] >= 0) {                      // else: no replicate of this call reaches its threshold
         const int32_t *row = ro.dense.data() + ro.dense_off[call];
         for (int b = 0; b < st->B; b++) one(b, row[b]);
-    } else {
-        for (int h = ro.hit_begin[call]; h < ro.hit_end[call]; h++) one(ro.hit_b[h], ro.hit_res[h]);
     }
     st->n_reps++;
 }
@@ -287,6 +412,8 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     std::vector<uint32_t> mp;
     std::vector<int32_t> thr;
     RepsOut ro;
+    Prof prof;
+    static const char *const prof_names[] = {"plan+upload", "scan", "reps", "replay", "views", "moves"};
     do {
         startMP = randomMP;
         visit_order(c->tree, order);                              // nodeRectifierPars :3297
@@ -295,10 +422,13 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
         while (i <= nvisit) {
             int count = std::min(batch, nvisit - i + 1);
             int nc = 0, nt = 0;
+            prof.start();
             if (int rc = mpgpu_scan_plan(c, order.data(), i, count, mintrav, maxtrav, &nc, &nt)) return rc;
+            prof.stop(0); prof.start();
             vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
             if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
             if (int rc = mpgpu_scan_finish(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
+            prof.stop(1); prof.start();
             if (bb) {
                 // every saveCurrentTree call of the batch, in order; call_of[] = index into the REPS results
                 mpgpu_bb_state *st = bb->st;
@@ -316,6 +446,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 }
                 if (int rc = reps_run(c, pass_cands.data(), (int)pass_cands.size(), thr.data(), ro)) return rc;
             }
+            prof.stop(2); prof.start();
             bool moved = false;
             int v = 0;
             for (; v < count && !moved; v++) {
@@ -352,16 +483,22 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 }
             }
             i += v;
+            prof.stop(3);
             if (moved) {
+                prof.start();
                 c->tree_set = true; c->lens_valid = false;
                 if (int rc = compute_views(c)) return rc;
                 compute_lengths(c);
                 batch = 16;
+                prof.stop(4);
             } else {
                 batch = std::min(batch * 2, nvisit);
             }
         }
     } while (randomMP < startMP);
+    prof.report(prof_names, 5);
+    g_rp.report(g_rp_names, 8);
+    for (int k = 0; k < 8; k++) { g_rp.t[k] = 0; g_rp.n[k] = 0; }
     memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
     memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
     *best = startMP;
@@ -398,8 +535,23 @@ int mpgpu_set_option(mpgpu_ctx *c, const char *name, int value)
         c->reps.use_tensor = value != 0;
         return 0;
     }
+    if (!strcmp(name, "reps_timing")) { c->reps.timing = value != 0; c->reps.timed_rows = 0; return 0; }
     set_error(std::string("unknown option: ") + name);
     return 1;
+}
+
+int mpgpu_reps_timing(mpgpu_ctx *c, float *tc_ms, int *rows, int *patterns, int *splits)
+{
+    if (!c || !c->reps.loaded || !c->reps.ev1 || c->reps.timed_rows == 0) { set_error("no timed k_reps_tc launch (option reps_timing)"); return 1; }
+    MPGPU_CUDA(cudaEventSynchronize(c->reps.ev1));
+    float ms = 0;
+    MPGPU_CUDA(cudaEventElapsedTime(&ms, c->reps.ev0, c->reps.ev1));
+    if (tc_ms) *tc_ms = ms;
+    if (rows) *rows = c->reps.timed_rows;
+    if (patterns) *patterns = c->reps.timed_kblocks * 128;
+    if (splits) *splits = c->reps.timed_splits;
+    c->reps.timed_rows = 0;
+    return 0;
 }
 
 int mpgpu_reps_info(mpgpu_ctx *c, int *groups, int *exceptions, int *tensor)
@@ -430,76 +582,29 @@ int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride,
     r.Kpad = (std::max(r.upper, 1) + 127) / 128 * 128; r.Pw = r.Kpad / 32;
     r.seg_upper.assign(segment_upper, segment_upper + nseg);
 
-    // ---- which segments can wrap at 16 bits on some tree, which patterns are too heavy for u8 ----
-    std::vector<uint16_t> ub(std::max(r.upper, 1));
-    {
-        uint16_t *d_ub = nullptr;
-        MPGPU_CUDA(cudaMalloc((void **)&d_ub, ub.size() * sizeof(uint16_t)));
-        int rc = launch_pattern_ub(c, r.upper, d_ub);
-        if (!rc && r.upper > 0) {
-            cudaError_t e = cudaMemcpyAsync(ub.data(), d_ub, (size_t)r.upper * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) rc = cuda_fail(e, "pattern upper bounds");
-        }
-        cudaFree(d_ub);
-        if (rc) return rc;
-    }
-    std::vector<int> seg_of(std::max(r.upper, 1), 0);
-    std::vector<uint8_t> flagged(nseg, 0), heavy(std::max(r.upper, 1), 0);
-    {
-        int s = 0;
-        for (int p = 0; p < r.upper; p++) { while (p >= segment_upper[s]) s++; seg_of[p] = s; }
-        std::vector<uint64_t> sum(nseg);
-        for (int b = 0; b < B; b++) {
-            const uint16_t *w = boot + (size_t)b * stride;
-            std::fill(sum.begin(), sum.end(), 0);
-            for (int p = 0; p < r.upper; p++) { sum[seg_of[p]] += (uint64_t)ub[p] * w[p]; if (w[p] > 255) heavy[p] = 1; }
-            for (int g = 0; g < nseg; g++) if (sum[g] >= 65536) flagged[g] = 1;
-        }
-    }
-    std::vector<int> group_of_seg(nseg, 0);
-    r.G = 1;
-    for (int g = 0; g < nseg; g++) if (flagged[g]) group_of_seg[g] = r.G++;
-    std::vector<int32_t> exc_ptn, exc_group;
-    std::vector<uint8_t> is_exc(r.Kpad, 0);
-    r.n_heavy = 0;
-    for (int pass = 0; pass < 2; pass++)                                       // group 0 first, then the wrap-prone segments in order
-        for (int p = 0; p < r.upper; p++) {
-            const int g = group_of_seg[seg_of[p]];
-            if (pass == 0 ? (g == 0 && (heavy[p] || !r.use_tensor)) : g > 0) {
-                exc_ptn.push_back(p); exc_group.push_back(g); is_exc[p] = 1;
-                if (g == 0 && heavy[p]) r.n_heavy++;
-            }
-        }
-    if (r.G > 1) {                                                             // keep groups contiguous and ascending
-        std::vector<int> idx(exc_ptn.size());
-        for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return exc_group[a] < exc_group[b]; });
-        std::vector<int32_t> p2(idx.size()), g2(idx.size());
-        for (size_t i = 0; i < idx.size(); i++) { p2[i] = exc_ptn[idx[i]]; g2[i] = exc_group[idx[i]]; }
-        exc_ptn.swap(p2); exc_group.swap(g2);
-    }
-    r.n_exc = (int)exc_ptn.size();
-
-    // ---- device copies ----
-    uint16_t *d_boot16 = nullptr; uint8_t *d_is_exc = nullptr;
+    // ---- device copies: exact weights pattern-major, heavy flags, segment bounds ----
+    const int nseg_ = nseg;
+    r.seg_flagged.assign(nseg_, 0);
+    r.heavy.assign(std::max(r.upper, 1), 0);
+    uint16_t *d_boot16 = nullptr; uint8_t *d_heavy = nullptr;
     MPGPU_CUDA(cudaMalloc((void **)&r.d_w8, (size_t)r.Bpad * r.Kpad));
-    if (r.n_exc) {
-        MPGPU_CUDA(cudaMalloc((void **)&r.d_w16e, (size_t)r.n_exc * r.Bpad * sizeof(uint16_t)));
-        MPGPU_CUDA(cudaMalloc((void **)&r.d_exc_ptn, (size_t)r.n_exc * 4));
-        MPGPU_CUDA(cudaMalloc((void **)&r.d_exc_group, (size_t)r.n_exc * 4));
-        MPGPU_CUDA(cudaMemcpyAsync(r.d_exc_ptn, exc_ptn.data(), (size_t)r.n_exc * 4, cudaMemcpyHostToDevice, c->stream));
-        MPGPU_CUDA(cudaMemcpyAsync(r.d_exc_group, exc_group.data(), (size_t)r.n_exc * 4, cudaMemcpyHostToDevice, c->stream));
-    }
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_w16T, (size_t)std::max(r.upper, 1) * r.Bpad * sizeof(uint16_t)));
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_seg_upper, (size_t)nseg_ * 4));
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_seg_flags, (size_t)nseg_));
     MPGPU_CUDA(cudaMalloc((void **)&d_boot16, (size_t)B * stride * sizeof(uint16_t)));
-    MPGPU_CUDA(cudaMalloc((void **)&d_is_exc, (size_t)r.Kpad));
+    MPGPU_CUDA(cudaMalloc((void **)&d_heavy, r.heavy.size()));
+    MPGPU_CUDA(cudaMemcpyAsync(r.d_seg_upper, segment_upper, (size_t)nseg_ * 4, cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaMemcpyAsync(d_boot16, boot, (size_t)B * stride * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-    MPGPU_CUDA(cudaMemcpyAsync(d_is_exc, is_exc.data(), (size_t)r.Kpad, cudaMemcpyHostToDevice, c->stream));
-    int rc = launch_build_weights(c, d_boot16, stride, d_is_exc);
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_boot16); cudaFree(d_is_exc);
+    MPGPU_CUDA(cudaMemsetAsync(d_heavy, 0, r.heavy.size(), c->stream));
+    int rc = launch_transpose_boot(c, d_boot16, stride, d_heavy);
+    cudaError_t e = cudaMemcpyAsync(r.heavy.data(), d_heavy, r.heavy.size(), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_boot16); cudaFree(d_heavy);
     if (rc) return rc;
-    if (e != cudaSuccess) return cuda_fail(e, "building replicate weights");
+    if (e != cudaSuccess) return cuda_fail(e, "uploading replicate weights");
+    r.G = 1;
+    if (int rc2 = build_classification(c)) return rc2;
+    r.reclassifications = 0;
     if (r.use_tensor) { if (int rc2 = make_w8_tensor_map(c)) return rc2; }
     r.loaded = true;
     r.tree_valid = false;
@@ -518,6 +623,20 @@ int mpgpu_reps_current_tree(mpgpu_ctx *c, int32_t *res)
     RepsOut ro;
     if (int rc = reps_run(c, &cand, 1, nullptr, ro)) return rc;
     memcpy(res, ro.dense.data() + ro.dense_off[0], (size_t)c->reps.B * 4);
+    return 0;
+}
+
+int mpgpu_reps_candidates_device(mpgpu_ctx *c, const int32_t *cand_idx, int m, void **dev_res, int *pitch)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (!cand_idx || m < 0) { set_error("bad argument"); return 1; }
+    if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
+    if (c->shard_count != 1) { set_error("mpgpu_reps_candidates_device is single-shard in this version"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    RepsOut ro;
+    if (int rc = reps_run(c, cand_idx, m, nullptr, ro, true)) return rc;
+    if (dev_res) *dev_res = (void *)c->reps.d_res;
+    if (pitch) *pitch = c->reps.Bpad;
     return 0;
 }
 

@@ -84,9 +84,13 @@ struct Reps {
     int n_exc = 0, n_heavy = 0;           // exception patterns (all of groups >= 1, plus weights > 255 of group 0)
     int kb_lo = 0, kb_hi = 0;             // 128-pattern K-blocks that can have bits on this shard
     bool use_tensor = true;
-    uint8_t *d_w8 = nullptr;              // [Bpad][Kpad]
-    uint16_t *d_w16e = nullptr;           // [n_exc][Bpad]
-    int32_t *d_exc_ptn = nullptr, *d_exc_group = nullptr;
+    uint8_t *d_w8 = nullptr;              // [Bpad][Kpad] u8, K-major: the tensor kernel's B operand
+    uint16_t *d_w16T = nullptr;           // [upper][Bpad] u16, pattern-major: the exact weights
+    int32_t *d_seg_upper = nullptr;       // [nseg]
+    uint8_t *d_seg_flags = nullptr;       // [nseg] scratch of the wrap check
+    std::vector<uint8_t> heavy;           // [upper] some replicate weight > 255
+    std::vector<uint8_t> seg_flagged;     // [nseg] segment is in a group of its own (can wrap)
+    int32_t *d_exc_ptn = nullptr, *d_exc_group = nullptr; size_t exc_cap = 0, exc_group_cap = 0;
     alignas(64) unsigned char tmap_w8[128];
     bool tmap_valid = false;
     // rows (one index space for the three buffers)
@@ -95,16 +99,34 @@ struct Reps {
     uint32_t *d_rows_ptn = nullptr;       // [row_cap][Pw]   the same rows in pattern space
     int32_t *d_X = nullptr;               // [row_cap][G][Bpad]
     bool tree_valid = false;              // rows 0..16 describe the current tree and weights
-    // per batch
+    // per batch (host staging + device copies)
+    std::vector<int32_t> h_row_of, h_row_tasks;
+    std::vector<int4> h_edges;
+    std::vector<int2> h_calls;
     int32_t *d_row_of = nullptr; size_t row_of_cap = 0;
     int32_t *d_row_tasks = nullptr; size_t row_tasks_cap = 0;
     int4 *d_edges = nullptr; size_t edges_cap = 0;
     int2 *d_calls = nullptr; size_t calls_cap = 0;
     int32_t *d_res = nullptr; size_t res_cap = 0;          // [calls][Bpad]
     int32_t *d_thr = nullptr;                              // [Bpad]
-    uint32_t *d_hit_count = nullptr;
-    int4 *d_hits = nullptr; uint32_t hit_cap = 0;
+    int32_t *d_call_hit = nullptr; size_t call_hit_cap = 0;   // [calls] some replicate of the call passes its threshold
+    int32_t *d_hit_list = nullptr; size_t hit_list_cap = 0;   // calls to read back
+    int32_t *d_res_hit = nullptr; size_t res_hit_cap = 0;     // their rows, compacted
+    void *h_pin = nullptr; size_t pin_cap = 0;              // pinned staging for the read-backs
+    void *pinned(size_t bytes) {
+        if (bytes <= pin_cap && h_pin) return h_pin;
+        if (h_pin) cudaFreeHost(h_pin);
+        h_pin = nullptr; pin_cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        if (cudaHostAlloc(&h_pin, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h_pin = nullptr; return nullptr; }
+        pin_cap = want;
+        return h_pin;
+    }
     int64_t rows_scored = 0;              // statistics: rows pushed through the contraction
+    bool timing = false;                  // option "reps_timing": CUDA events around the largest k_reps_tc launch
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int timed_rows = 0, timed_kblocks = 0, timed_splits = 0;
+    int reclassifications = 0;            // times a wrap check moved a segment out of the tensor path's bulk group
 };
 
 struct Ctx {
@@ -154,6 +176,7 @@ struct Ctx {
     uint16_t *d_ptn = nullptr; size_t ptn_cap = 0;
     int64_t *d_ptn_site = nullptr; size_t ptn_site_cap = 0;
     bool ptn_site_valid = false;
+    bool ptn_identity = false;            // pattern i sits at expanded site i (all reported weights are 1, single shard)
 
     // replicate scoring
     Reps reps;
@@ -200,16 +223,17 @@ int launch_gather_patterns(Ctx *c, int nbits, int count);
 const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);
 
 // ---- kernel launchers (reps_kernels.cu) ----------------------------------------------------
-int launch_pattern_ub(Ctx *c, int count, uint16_t *d_ub);
-int launch_build_weights(Ctx *c, const uint16_t *d_boot16, int stride, const uint8_t *d_is_exc);
+int launch_transpose_boot(Ctx *c, const uint16_t *d_boot16, int stride, uint8_t *d_heavy);
+int launch_build_w8(Ctx *c, const uint8_t *d_is_exc);
+int launch_seg_check(Ctx *c, uint8_t *d_flags);
 int launch_edge_rows(Ctx *c, const int4 *d_edges, int nedges, uint32_t *d_rows);
 int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows);
-int launch_reps_exc(Ctx *c, int row0, int nrows);
+int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows);
 int make_w8_tensor_map(Ctx *c);
-int launch_reps_tc(Ctx *c, int row0, int nrows);
+int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows);
 int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row);
-int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr,
-                        uint32_t *d_hit_count, int4 *d_hits, uint32_t hit_cap);
+int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr, int32_t *d_call_hit);
+int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, int nlist, int32_t *d_out);
 
 // ---- host SPR logic (spr_host.cpp) ---------------------------------------------------------
 void visit_order(const HostTree &t, std::vector<int32_t> &order);

@@ -21,98 +21,100 @@
 
 namespace mpgpu {
 
-__host__ __device__ inline uint32_t reps_code_mask(int datatype, uint32_t code)
+// ------------------------------------------------------------------------------------------
+// Replicate weights.  boot16 [B][stride] u16 (boot_samples_pars, iqtree.cpp:220-233) is kept on
+// the device pattern-major:   w16T[ptn][Bpad]   (exact weights; exception path, wrap check)
+// and, for the tensor kernel: w8[Bpad][Kpad] u8, K-major, exception patterns and padding = 0.
+// ------------------------------------------------------------------------------------------
+// 32x32 tile transpose; heavy[ptn] = 1 when some replicate weight of the pattern exceeds 255
+__global__ void k_transpose_boot(const uint16_t *__restrict__ boot16, int B, int stride, int upper, int Bpad,
+                                 uint16_t *__restrict__ w16T, uint8_t *__restrict__ heavy)
 {
-    switch (datatype) {
-    case MPGPU_AA_DATA:
-        if (code < 20) return 1u << code;
-        if (code == 20) return 12u;
-        if (code == 21) return 96u;
-        return 0xFFFFFu;
-    case MPGPU_GENERIC_32:
-        return code < 32 ? (1u << code) : 0xFFFFFFFFu;
-    default:
-        return code;
+    __shared__ uint16_t tile[32][33];
+    const int p0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int b = b0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (b < B && p < upper) ? boot16[(size_t)b * stride + p] : (uint16_t)0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, b = b0 + threadIdx.x;
+        if (p < upper && b < Bpad) {
+            const uint16_t v = tile[threadIdx.x][i];
+            w16T[(size_t)p * Bpad + b] = v;
+            if (v > 255) heavy[p] = 1;
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Upper bound of a pattern's Fitch score on ANY tree: n - (largest number of tips compatible
-// with one state).  Used to prove that a REPS segment cannot reach 2^16 (wrap-free).
-// ------------------------------------------------------------------------------------------
-template <int S>
-__global__ void k_pattern_ub(const uint8_t *__restrict__ codes, int P, int n, int datatype, int count,
-                             uint16_t *__restrict__ ub)
+__global__ void k_build_w8(const uint16_t *__restrict__ w16T, int upper, const uint8_t *__restrict__ is_exc,
+                           int Bpad, int Kpad, uint8_t *__restrict__ w8)
 {
-    const int ptn = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ptn >= count) return;
-    int cnt[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) cnt[s] = 0;
-    for (int t = 0; t < n; t++) {
-        const uint32_t m = reps_code_mask(datatype, codes[(size_t)t * P + ptn]);
-#pragma unroll
-        for (int s = 0; s < S; s++) cnt[s] += (m >> s) & 1u;
+    __shared__ uint8_t tile[32][33];
+    const int p0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, b = b0 + threadIdx.x;
+        uint32_t v = 0;
+        if (p < upper && !is_exc[p]) v = w16T[(size_t)p * Bpad + b];
+        tile[i][threadIdx.x] = (uint8_t)v;              // <= 255 by construction: heavier patterns are exceptions
     }
-    int best = 0;
-#pragma unroll
-    for (int s = 0; s < S; s++) best = cnt[s] > best ? cnt[s] : best;
-    ub[ptn] = (uint16_t)(n - best);
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int b = b0 + i, p = p0 + threadIdx.x;
+        if (p < Kpad) w8[(size_t)b * Kpad + p] = tile[threadIdx.x][i];
+    }
 }
 
-int launch_pattern_ub(Ctx *c, int count, uint16_t *d_ub)
+int launch_transpose_boot(Ctx *c, const uint16_t *d_boot16, int stride, uint8_t *d_heavy)
 {
-    if (count == 0) return 0;
-    const int threads = 128, blocks = (count + threads - 1) / threads;
-    switch (c->S) {
-    case 2:  k_pattern_ub<2><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
-    case 4:  k_pattern_ub<4><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
-    case 20: k_pattern_ub<20><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
-    case 32: k_pattern_ub<32><<<blocks, threads, 0, c->stream>>>(c->d_codes, c->P, c->n, c->datatype, count, d_ub); break;
-    default: set_error("unsupported state count"); return 1;
-    }
+    Reps &r = c->reps;
+    dim3 grid((r.upper + 31) / 32, r.Bpad / 32), block(32, 8);
+    if (r.upper == 0) return 0;
+    k_transpose_boot<<<grid, block, 0, c->stream>>>(d_boot16, r.B, stride, r.upper, r.Bpad, r.d_w16T, d_heavy);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Replicate weights: boot16 [B][stride] u16 (as boot_samples_pars, iqtree.cpp:220-233) ->
-//   w8  [Bpad][Kpad] u8, K-major (the tensor kernel's B operand); exception patterns and padding = 0
-//   w16e[n_exc][Bpad] u16, the exact weights of the exception patterns
-// ------------------------------------------------------------------------------------------
-__global__ void k_build_w8(const uint16_t *__restrict__ boot16, int B, int stride, int upper,
-                           const uint8_t *__restrict__ is_exc, int Bpad, int Kpad, uint8_t *__restrict__ w8)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (k >= Kpad) return;
-    uint32_t v = 0;
-    if (b < B && k < upper && !is_exc[k]) v = boot16[(size_t)b * stride + k];
-    w8[(size_t)b * Kpad + k] = (uint8_t)v;            // v <= 255 by construction (heavier patterns are exceptions)
-}
-
-__global__ void k_build_w16e(const uint16_t *__restrict__ boot16, int B, int stride,
-                             const int32_t *__restrict__ exc_ptn, int n_exc, int Bpad, uint16_t *__restrict__ w16e)
-{
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int e = blockIdx.y;
-    if (b >= Bpad || e >= n_exc) return;
-    w16e[(size_t)e * Bpad + b] = b < B ? boot16[(size_t)b * stride + exc_ptn[e]] : (uint16_t)0;
-}
-
-int launch_build_weights(Ctx *c, const uint16_t *d_boot16, int stride, const uint8_t *d_is_exc)
+int launch_build_w8(Ctx *c, const uint8_t *d_is_exc)
 {
     Reps &r = c->reps;
-    {
-        dim3 grid((r.Kpad + 255) / 256, r.Bpad);
-        k_build_w8<<<grid, 256, 0, c->stream>>>(d_boot16, r.B, stride, r.upper, d_is_exc, r.Bpad, r.Kpad, r.d_w8);
-        c->launches++;
-        MPGPU_CUDA(cudaGetLastError());
-    }
-    if (r.n_exc > 0) {
-        dim3 grid((r.Bpad + 255) / 256, r.n_exc);
-        k_build_w16e<<<grid, 256, 0, c->stream>>>(d_boot16, r.B, stride, r.d_exc_ptn, r.n_exc, r.Bpad, r.d_w16e);
+    dim3 grid(r.Kpad / 32, r.Bpad / 32), block(32, 8);
+    k_build_w8<<<grid, block, 0, c->stream>>>(r.d_w16T, r.upper, d_is_exc, r.Bpad, r.Kpad, r.d_w8);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Wrap check for the tree the rows are built from.  Every candidate scored against tree T has
+// per-pattern score <= c_T + 1 (one SPR adds at most one step per site), so a segment whose
+//     sum_{ptn in seg} (c_T[ptn] + 1) * w[b][ptn]  <  2^16   for every replicate b
+// cannot wrap in the reference's u16 lanes for T or any of its candidates: its mod-2^16 is the
+// identity and it may stay in the tensor path's bulk group.  flags[seg] = 1 otherwise.
+__global__ void __launch_bounds__(256) k_seg_check(const uint16_t *__restrict__ ptn_pars, const uint16_t *__restrict__ w16T,
+                                                   const int32_t *__restrict__ seg_upper, int seg0, int upper, int B, int Bpad,
+                                                   uint8_t *__restrict__ flags)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = seg0 + blockIdx.y;
+    if (b >= B) return;
+    const int lo = seg ? seg_upper[seg - 1] : 0;
+    int hi = seg_upper[seg];
+    if (hi > upper) hi = upper;
+    unsigned long long sum = 0;
+    for (int p = lo; p < hi; p++) sum += (unsigned long long)(__ldg(ptn_pars + p) + 1u) * __ldg(w16T + (size_t)p * Bpad + b);
+    if (sum >= 65536ull) flags[seg] = 1;
+}
+
+int launch_seg_check(Ctx *c, uint8_t *d_flags)
+{
+    Reps &r = c->reps;
+    const int nseg = (int)r.seg_upper.size();
+    if (r.upper == 0) return 0;
+    for (int done = 0; done < nseg; done += 65535) {
+        const int chunk = nseg - done < 65535 ? nseg - done : 65535;
+        dim3 grid((r.B + 255) / 256, chunk);
+        k_seg_check<<<grid, 256, 0, c->stream>>>(c->d_ptn, r.d_w16T, r.d_seg_upper, done, r.upper, r.B, r.Bpad, d_flags);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }
@@ -164,37 +166,45 @@ int launch_edge_rows(Ctx *c, const int4 *d_edges, int nedges, uint32_t *d_rows)
 }
 
 // Site rows -> pattern rows: bit ptn of the output = bit at the FIRST expanded site of pattern
-// ptn (what pllComputePatternParsimony reads, :3384).  One warp per (row, 32 patterns).
-__global__ void k_gather_rows(const uint32_t *__restrict__ src, int Wl, int64_t w0,
-                              const int64_t *__restrict__ ptn_site, int upper, int Pw,
-                              uint32_t *__restrict__ dst, int nrows)
+// ptn (what pllComputePatternParsimony reads, :3384).  One warp per 32 patterns x kGatherRows
+// rows: the site of each pattern is looked up once and reused for every row of the block.
+static const int kGatherRows = 32;
+__global__ void __launch_bounds__(256) k_gather_rows(const uint32_t *__restrict__ src, int Wl, int64_t w0,
+                                                     const int64_t *__restrict__ ptn_site, int upper, int Pw,
+                                                     uint32_t *__restrict__ dst, int nrows)
 {
     const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= (long long)nrows * Pw) return;
-    const int row = (int)(gw / Pw), pw = (int)(gw % Pw);
+    const int pw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pw >= Pw) return;
     const int ptn = 32 * pw + lane;
-    uint32_t bit = 0;
+    int word = -1, sh = 0;
     if (ptn < upper) {
         const int64_t site = ptn_site[ptn];
         const int64_t w = (site >> 5) - w0;
-        if (site >= 0 && w >= 0 && w < Wl) bit = (src[(size_t)row * Wl + w] >> (site & 31)) & 1u;
+        if (site >= 0 && w >= 0 && w < Wl) { word = (int)w; sh = (int)(site & 31); }
     }
-    const uint32_t word = __ballot_sync(0xffffffffu, bit);
-    if (lane == 0) dst[(size_t)row * Pw + pw] = word;
+    const int r0 = blockIdx.y * kGatherRows;
+    const int r1 = r0 + kGatherRows < nrows ? r0 + kGatherRows : nrows;
+    for (int row = r0; row < r1; row++) {
+        uint32_t bit = 0;
+        if (word >= 0) bit = (__ldg(src + (size_t)row * Wl + word) >> sh) & 1u;
+        const uint32_t packed = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) dst[(size_t)row * Pw + pw] = packed;
+    }
 }
 
 int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows)
 {
     if (nrows == 0) return 0;
     Reps &r = c->reps;
-    const long long warps = (long long)nrows * r.Pw;
-    const int wpb = 8;
-    const long long blocks = (warps + wpb - 1) / wpb;
-    if (blocks > 0x7fffffffLL) { set_error("gather grid too large"); return 1; }
-    k_gather_rows<<<(unsigned)blocks, wpb * 32, 0, c->stream>>>(d_src, c->Wl, c->w0, c->d_ptn_site, r.upper, r.Pw, d_dst, nrows);
-    c->launches++;
-    MPGPU_CUDA(cudaGetLastError());
+    for (int done = 0; done < nrows; done += 65535 * kGatherRows) {
+        const int chunk = nrows - done < 65535 * kGatherRows ? nrows - done : 65535 * kGatherRows;
+        dim3 grid((r.Pw + 7) / 8, (chunk + kGatherRows - 1) / kGatherRows);
+        k_gather_rows<<<grid, 256, 0, c->stream>>>(d_src + (size_t)done * c->Wl, c->Wl, c->w0, c->d_ptn_site, r.upper, r.Pw,
+                                                    d_dst + (size_t)done * r.Pw, chunk);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -203,16 +213,16 @@ int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows
 //   X[row][group(e)][b] += bit[row][ptn(e)] * w16e[e][b]
 // exceptions are sorted by group; one thread per (row, b).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ rows_ptn, int Pw, int row0,
+__global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ rows_a, int a_pitch, int row0, int x_row0,
                                                   const int32_t *__restrict__ exc_ptn, const int32_t *__restrict__ exc_group,
-                                                  int n_exc, const uint16_t *__restrict__ w16e, int Bpad, int G,
+                                                  int n_exc, const uint16_t *__restrict__ w16T, int Bpad, int G,
                                                   int32_t *__restrict__ X)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = row0 + blockIdx.y;
     if (b >= Bpad) return;
-    const uint32_t *bits = rows_ptn + (size_t)row * Pw;
-    int32_t *xrow = X + (size_t)row * G * Bpad;
+    const uint32_t *bits = rows_a + (size_t)row * a_pitch;
+    int32_t *xrow = X + (size_t)(x_row0 + row) * G * Bpad;
     int acc = 0, cur = -1;
     for (int e = 0; e < n_exc; e++) {
         const int g = __ldg(exc_group + e);
@@ -221,20 +231,21 @@ __global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ r
             cur = g; acc = 0;
         }
         const int p = __ldg(exc_ptn + e);
-        if ((__ldg(bits + (p >> 5)) >> (p & 31)) & 1u) acc += (int)__ldg(w16e + (size_t)e * Bpad + b);
+        if ((__ldg(bits + (p >> 5)) >> (p & 31)) & 1u) acc += (int)__ldg(w16T + (size_t)p * Bpad + b);
     }
     if (cur >= 0 && acc) atomicAdd(&xrow[(size_t)cur * Bpad + b], acc);
 }
 
-int launch_reps_exc(Ctx *c, int row0, int nrows)
+// rows a_base[0..nrows) (pitch a_pitch words, pattern-indexed bits) -> X[x_row0 ..][group][b]
+int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows)
 {
     Reps &r = c->reps;
     if (nrows == 0 || r.n_exc == 0) return 0;
     for (int done = 0; done < nrows; done += 65535) {
         const int chunk = nrows - done < 65535 ? nrows - done : 65535;
         dim3 grid((r.Bpad + 255) / 256, chunk);
-        k_reps_exc<<<grid, 256, 0, c->stream>>>(r.d_rows_ptn, r.Pw, row0 + done, r.d_exc_ptn, r.d_exc_group, r.n_exc,
-                                                 r.d_w16e, r.Bpad, r.G, r.d_X);
+        k_reps_exc<<<grid, 256, 0, c->stream>>>(a_base, a_pitch, done, x_row0, r.d_exc_ptn, r.d_exc_group, r.n_exc,
+                                                 r.d_w16T, r.Bpad, r.G, r.d_X);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }
@@ -323,8 +334,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
 __global__ void __launch_bounds__(THREADS, 1)
-k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_ptn, int Pw,
-          int row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
+k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_a, int a_pitch,
+          int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -361,9 +372,8 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
     if (warp < 4) {
         // ---- A producers: thread r owns tile row r ----
         const int r = threadIdx.x;
-        const int row = row0 + m0 + r;
         const bool live = (m0 + r) < nrows;
-        const uint4 *src = reinterpret_cast<const uint4 *>(rows_ptn + (size_t)row * Pw);
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch);
         const uint32_t sw = (uint32_t)(r & 7);
         for (int it = 0; it < nkb; it++) {
             const int s = it % STAGES;
@@ -442,7 +452,7 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
                 const int mrow = m0 + warp * 32 + i;
                 const int val = (int)tile[i * 33 + lane];
                 if (mrow < nrows && col < B && val != 0)
-                    atomicAdd(&X[(size_t)(row0 + mrow) * x_pitch + col], val);
+                    atomicAdd(&X[(size_t)(x_row0 + mrow) * x_pitch + col], val);
             }
             __syncwarp();
         }
@@ -484,8 +494,9 @@ int make_w8_tensor_map(Ctx *c)
     return 0;
 }
 
-// X[row0 .. row0+nrows)[group 0] += rows_ptn x w8   (this shard's K-blocks [kb_lo, kb_hi))
-int launch_reps_tc(Ctx *c, int row0, int nrows)
+// X[x_row0 .. x_row0+nrows)[group 0] += rows x w8   (this shard's K-blocks [kb_lo, kb_hi));
+// rows = a_base[0..nrows), pitch a_pitch words (a multiple of 4), pattern-indexed bits
+int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows)
 {
     Reps &r = c->reps;
     if (nrows == 0) return 0;
@@ -509,8 +520,14 @@ int launch_reps_tc(Ctx *c, int row0, int nrows)
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
     dim3 grid(mt, nt, splits);
-    tc::k_reps_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), r.d_rows_ptn, r.Pw,
-                                                                    row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
+    const bool timed = r.timing && nrows >= r.timed_rows;      // keep the events of the largest launch
+    if (timed) {
+        if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
+        MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
+    }
+    tc::k_reps_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch,
+                                                                    x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
+    if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;
@@ -520,8 +537,8 @@ int launch_reps_tc(Ctx *c, int row0, int nrows)
 // Combine.
 //   tree row:  X[t][g][b] = sum_bit X[plane_bit][g][b] << bit
 //   call j:    res[j][b]  = sum_g mask_g( X[t][g][b] - X[e_j][g][b] + X[d_j][g][b] ),  mask_0 = id, else & 0xFFFF
-// A hit (res <= thr[b], i.e. rell >= boot_logl[b] at the start of the batch) is appended to a
-// compact list so that the host only has to read what can change a replicate.
+// A call with a hit (res <= thr[b] for some b, i.e. rell >= boot_logl[b] at the start of the batch)
+// is flagged so that the host only reads back the rows that can change a replicate.
 // ------------------------------------------------------------------------------------------
 __global__ void k_reps_tree_row(int32_t *__restrict__ X, int plane_row0, int nbits, int t_row, int pitch)
 {
@@ -532,28 +549,35 @@ __global__ void k_reps_tree_row(int32_t *__restrict__ X, int plane_row0, int nbi
     X[(size_t)t_row * pitch + i] = acc;
 }
 
-__global__ void k_reps_combine(const int32_t *__restrict__ X, int G, int Bpad, int B, int t_row,
-                               const int2 *__restrict__ calls, int call0, int ncalls, int32_t *__restrict__ res,
-                               const int32_t *__restrict__ thr, uint32_t *__restrict__ hit_count,
-                               int4 *__restrict__ hits, uint32_t hit_cap)
+__global__ void __launch_bounds__(256) k_reps_combine(const int32_t *__restrict__ X, int G, int Bpad, int B, int t_row,
+                                                      const int2 *__restrict__ calls, int call0, int ncalls, int32_t *__restrict__ res,
+                                                      const int32_t *__restrict__ thr, int32_t *__restrict__ call_hit)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = call0 + blockIdx.y;
-    if (b >= Bpad || j >= ncalls) return;
-    const int2 cd = calls[j];                                   // x = edge row (-1 none), y = delta row (-1 none)
-    const size_t pitch = (size_t)G * Bpad;
-    int total = 0;
-    for (int g = 0; g < G; g++) {
-        int v = X[(size_t)t_row * pitch + (size_t)g * Bpad + b];
-        if (cd.x >= 0) v -= X[(size_t)cd.x * pitch + (size_t)g * Bpad + b];
-        if (cd.y >= 0) v += X[(size_t)cd.y * pitch + (size_t)g * Bpad + b];
-        total += g == 0 ? v : (v & 0xFFFF);
+    const int j = call0 + blockIdx.y;                           // uniform over the block
+    if (j >= ncalls) return;
+    int hit = 0;
+    if (b < Bpad) {
+        const int2 cd = calls[j];                               // x = edge row (-1 none), y = delta row (-1 none)
+        const size_t pitch = (size_t)G * Bpad;
+        int total = 0;
+        for (int g = 0; g < G; g++) {
+            int v = X[(size_t)t_row * pitch + (size_t)g * Bpad + b];
+            if (cd.x >= 0) v -= X[(size_t)cd.x * pitch + (size_t)g * Bpad + b];
+            if (cd.y >= 0) v += X[(size_t)cd.y * pitch + (size_t)g * Bpad + b];
+            total += g == 0 ? v : (v & 0xFFFF);
+        }
+        res[(size_t)j * Bpad + b] = total;
+        hit = thr && b < B && total <= thr[b];
     }
-    res[(size_t)j * Bpad + b] = total;
-    if (thr && b < B && total <= thr[b]) {
-        const uint32_t slot = atomicAdd(hit_count, 1u);
-        if (slot < hit_cap) hits[slot] = make_int4(j, b, total, 0);
-    }
+    if (thr && __syncthreads_or(hit) && threadIdx.x == 0) call_hit[j] = 1;
+}
+
+// rows of res listed in `list` -> contiguous rows of `out`
+__global__ void k_gather_res_rows(const int32_t *__restrict__ res, int Bpad, const int32_t *__restrict__ list, int32_t *__restrict__ out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < Bpad) out[(size_t)blockIdx.y * Bpad + b] = res[(size_t)list[blockIdx.y] * Bpad + b];
 }
 
 int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row)
@@ -566,16 +590,27 @@ int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row)
     return 0;
 }
 
-int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr,
-                        uint32_t *d_hit_count, int4 *d_hits, uint32_t hit_cap)
+int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr, int32_t *d_call_hit)
 {
     Reps &r = c->reps;
     if (ncalls == 0) return 0;
     for (int done = 0; done < ncalls; done += 65535) {
         const int chunk = ncalls - done < 65535 ? ncalls - done : 65535;
         dim3 grid((r.Bpad + 255) / 256, chunk);
-        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.B, t_row, d_calls, done, ncalls,
-                                                     d_res, d_thr, d_hit_count, d_hits, hit_cap);
+        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.B, t_row, d_calls, done, ncalls, d_res, d_thr, d_call_hit);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, int nlist, int32_t *d_out)
+{
+    Reps &r = c->reps;
+    for (int done = 0; done < nlist; done += 65535) {
+        const int chunk = nlist - done < 65535 ? nlist - done : 65535;
+        dim3 grid((r.Bpad + 255) / 256, chunk);
+        k_gather_res_rows<<<grid, 256, 0, c->stream>>>(d_res, r.Bpad, d_list + done, d_out + (size_t)done * r.Bpad);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }

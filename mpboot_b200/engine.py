@@ -60,9 +60,11 @@ def lib():
     L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.mpgpu_load_replicates.argtypes = [vp, i32, vp, i32, vp, i32]
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
+    L.mpgpu_reps_timing.argtypes = [vp, vp, vp, vp, vp]
     L.mpgpu_set_option.argtypes = [vp, C.c_char_p, i32]
     L.mpgpu_reps_current_tree.argtypes = [vp, vp]
     L.mpgpu_reps_candidates.argtypes = [vp, vp, i32, vp]
+    L.mpgpu_reps_candidates_device.argtypes = [vp, vp, i32, vp, vp]
     L.mpgpu_optimize_spr_bb.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.mpgpu_treels_create.restype = vp
     L.mpgpu_treels_create.argtypes = [i32]
@@ -293,6 +295,11 @@ class Engine:
         self._ck(self.L.mpgpu_reps_info(self.h, C.byref(g), C.byref(e), C.byref(t)))
         return g.value, e.value, t.value
 
+    def reps_timing(self):
+        ms, rows, pat, sp = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.mpgpu_reps_timing(self.h, C.byref(ms), C.byref(rows), C.byref(pat), C.byref(sp)))
+        return ms.value, rows.value, pat.value, sp.value
+
     def reps_current_tree(self):
         out = np.zeros(self.B, dtype=np.int32)
         self._ck(self.L.mpgpu_reps_current_tree(self.h, _p(out)))
@@ -303,6 +310,14 @@ class Engine:
         out = np.zeros((len(idx), self.B), dtype=np.int32)
         self._ck(self.L.mpgpu_reps_candidates(self.h, _p(idx), len(idx), _p(out)))
         return out
+
+    def reps_candidates_device(self, cand_idx):
+        """Asynchronous: returns (device pointer, pitch) of the int32 [m][pitch] result."""
+        idx = np.ascontiguousarray(cand_idx, dtype=np.int32)
+        self._keep = idx
+        ptr, pitch = C.c_void_p(), C.c_int()
+        self._ck(self.L.mpgpu_reps_candidates_device(self.h, _p(idx), len(idx), C.byref(ptr), C.byref(pitch)))
+        return ptr.value, pitch.value
 
     def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
                         mintrav=1, maxtrav=6):

@@ -82,3 +82,37 @@ def test_fingerprint_matches_python_helper():
     assert fingerprint_ring(bn, bs, 16) == o.fingerprint() % (1 << 64)
     m = res["mats"]
     assert len(m) > 0 and (m[:, 3] >= 0).all()
+
+
+# ---- committed golden vectors (produced by the reference driver, tools/make_golden.py) ----------
+import glob
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASE_FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz")) if not f.endswith("tables.npz"))
+IDS = [os.path.basename(p)[:-4] for p in CASE_FILES]
+
+
+def check_against_golden(g, tag, res):
+    """res: dict(ret, draws, ring, state, counters=(calls, trees, reps rows), treels, mats[call?, tree_index, fp])"""
+    assert res["ret"] == int(g["bb_%s_ret" % tag]) and res["draws"] == int(g["bb_%s_draws" % tag])
+    assert np.array_equal(res["ring"][0][3:], g["bb_%s_bn" % tag][3:]) and np.array_equal(res["ring"][1][3:], g["bb_%s_bs" % tag][3:])
+    assert np.array_equal(res["state"][0], g["bb_%s_boot_logl" % tag])
+    assert np.array_equal(res["state"][1], g["bb_%s_boot_counts" % tag])
+    assert np.array_equal(res["state"][2], g["bb_%s_boot_trees" % tag])
+    assert np.array_equal(res["treels"], g["bb_%s_treels" % tag])
+    cnt = g["bb_%s_counters" % tag]
+    assert res["counters"][0] == int(cnt[0]) and res["counters"][1] == int(cnt[1]) and res["counters"][2] == int(cnt[2])
+    assert np.array_equal(res["mats"], g["bb_%s_mats" % tag][:, 1:])       # tree_index, topology fingerprint
+
+
+@pytest.mark.parametrize("path", CASE_FILES, ids=IDS)
+def test_port_bb_equals_golden(path):
+    g = dict(np.load(path))
+    n, dt, mt = int(g["n"]), int(g["datatype"]), int(g["maxtrav"])
+    c = dict(n=n, datatype=dt, codes=g["codes"], weights=g["weights"], n_inf=int(g["n_inf"]), bn=g["bn"], bs=g["bs"])
+    o = portlib.OracleEngine(g["codes"], g["weights"], dt)
+    for tag in ("all", "cut"):
+        r = run_bb(o, c, g["bb_boot"], g["bb_seg"], float(g["bb_%s_cutoff" % tag]), None, False, mt=mt)
+        r["mats"] = r["mats"][:, [3, 4]]
+        check_against_golden(g, tag, r)

@@ -31,10 +31,10 @@ def _engine(c, boot, seg, tensor):
 def test_reps_current_tree_and_candidates(n, L, dt, seed, B, mu, tensor):
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
     eng = _engine(c, boot, seg, tensor)
-    groups, exc, t = eng.reps_info()
-    assert t == tensor and groups >= 2 and exc > 0            # the heavy replicates force wrap-prone segments
     want = portlib.reps(pp, boot[:, : c["n_inf"]], seg)
     assert np.array_equal(eng.reps_current_tree(), want)
+    groups, exc, t = eng.reps_info()
+    assert t == tensor and groups >= 2 and exc > 0            # the heavy replicates make segments wrap-prone
     # every saveCurrentTree call of three node visits: current tree first, then each insertion
     order = eng.visit_order()
     for i in (1, n + 1, 2 * n - 2):
@@ -52,9 +52,9 @@ def test_reps_current_tree_and_candidates(n, L, dt, seed, B, mu, tensor):
 def test_reps_wrap_free_bulk_uses_no_exceptions():
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(40, 1500, 1, 11, 100, heavy=False)
     eng = _engine(c, boot, seg, 1)
+    assert np.array_equal(eng.reps_current_tree(), portlib.reps(pp, boot[:, : c["n_inf"]], seg))
     groups, exc, t = eng.reps_info()
     assert groups == 1 and exc == 0 and t == 1                # everything on the tensor path
-    assert np.array_equal(eng.reps_current_tree(), portlib.reps(pp, boot[:, : c["n_inf"]], seg))
 
 
 def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6):
@@ -88,3 +88,19 @@ def test_bb_search_matches_oracle(n, L, dt, seed, B, mu, tensor):
         assert len(g["mats"]) == len(wm)
         assert np.array_equal(g["mats"][:, :3], wm[:, 1:4])                              # pruned ref, insertion ref, tree_index
         assert np.array_equal(g["mats"][:, 3], wm[:, 4])                                 # topology fingerprint
+
+
+# ---- the committed golden vectors: what the reference driver produced for the same -bb search ----
+from tests.test_bb_cpu import CASE_FILES, IDS, check_against_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("path", CASE_FILES, ids=IDS)
+def test_bb_search_matches_golden(path):
+    g = dict(np.load(path))
+    n, dt, mt = int(g["n"]), int(g["datatype"]), int(g["maxtrav"])
+    c = dict(n=n, datatype=dt, codes=g["codes"], weights=g["weights"], n_inf=int(g["n_inf"]), bn=g["bn"], bs=g["bs"])
+    for tag in ("all", "cut"):
+        r = _run_gpu_bb(c, g["bb_boot"], g["bb_seg"], float(g["bb_%s_cutoff" % tag]), 1, mt=mt)
+        r["counters"] = (r["ncalls"], len(r["treels"]), r["nreps"])
+        r["mats"] = r["mats"][:, [2, 3]]
+        check_against_golden(g, tag, r)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import reflib  # noqa: E402
-from tests.helpers import make_case  # noqa: E402
+from tests.helpers import make_case, make_boot  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -70,6 +70,33 @@ def one_case(name, n, L, dt, seed, maxtrav):
         g["opt_%s_score" % tag] = ref.evaluate_full(per_site=bb)
         if bb:
             g["opt_bb_saved"] = ref.saved().astype(np.int32)
+    # the -bb search with the whole saveCurrentTree bookkeeping (re-typed default policy on top of the
+    # reference's own search, pattern scores and Vec16us REPS, oracle/ref_driver.cpp): 40 replicates, a few
+    # of them forced to wrap at 16 bits / exceed 255, artificial segment bounds, with and without cutoff
+    ninf = c["n_inf"]
+    seg = np.unique(np.array([16, 48, 16 * max(ninf // 32, 4), ninf], dtype=np.int32))
+    seg = seg[seg <= ninf]
+    hv = [(1, 3, 40000), (2, 5, 300), (2, 6, 65535)] + [(3, k, 900) for k in range(0, min(ninf, 40))]
+    boot = make_boot(c, 40, seed, heavy=hv)
+    g["bb_boot"] = boot; g["bb_seg"] = seg
+    ras = np.zeros(len(c["weights"]), dtype=np.int32); ras[:ninf] = g["ptn_pars"]
+    for tag, cutoff in (("all", 0.0), ("cut", -(float(g["opt_bb_ret"]) + 4.0))):
+        ref.set_ring(c["bn"], c["bs"])
+        ref.allocate(per_site=True)
+        ref.boot_init(boot, seg, cutoff, 0.5, ras)
+        reflib.lib().mpref_seed_rng(2024)
+        ref.record(False)
+        g["bb_%s_cutoff" % tag] = cutoff
+        g["bb_%s_ret" % tag] = ref.optimize_spr(1, maxtrav, bb=True)
+        g["bb_%s_draws" % tag] = reflib.lib().mpref_rng_draws()
+        bn, bs = ref.get_ring()
+        g["bb_%s_bn" % tag] = bn; g["bb_%s_bs" % tag] = bs
+        bl, bc, bt = ref.boot_state()
+        g["bb_%s_boot_logl" % tag] = bl; g["bb_%s_boot_counts" % tag] = bc; g["bb_%s_boot_trees" % tag] = bt
+        g["bb_%s_counters" % tag] = np.array(ref.boot_counters(), dtype=np.int64)
+        g["bb_%s_treels" % tag] = ref.boot_treels()
+        g["bb_%s_mats" % tag] = ref.boot_mats()[:, [0, 3, 4]]          # call index, tree_index, topology fingerprint
+    ref.boot_free()
     # randomized stepwise addition
     reflib.lib().mpref_seed_rng(77)
     g["ras_ret"] = ref.ras(4242 + seed, maxtrav)
