@@ -165,6 +165,112 @@ def cpu_baseline(case, maxtrav, budget_s=20.0):
     return ins, dt, kind, "%d of %d node visits of the same sweep (%d insertions), plain mode" % (nvis, 2 * n - 2, ins)
 
 
+def make_replicates(case, B, seed=5):
+    """boot_samples_pars as MPBoot draws them: multinomial resampling of the sites, counted per pattern
+    (alignment.cpp:1985-1990, iqtree.cpp:285-313)."""
+    rng = np.random.default_rng(seed)
+    w = case["weights"].astype(np.float64)
+    return rng.multinomial(int(w.sum()), w / w.sum(), size=B).astype(np.uint16)
+
+
+def bench_bb(eng, case, order, vb, n_cand, args, flush):
+    """The same sweep under -bb with the cutoff off: every scored insertion and, once per node visit, the
+    current tree go through REPS against B = 1000 replicates (iqtree.cpp:3411-3449) -- the worst case for the
+    replicate contraction.  Device-timed step = k_spr_scan + delta rows + tcgen05 contraction + combine;
+    search = one whole mpgpu_optimize_spr_bb call (host bookkeeping, RNG replay and moves included)."""
+    import torch
+    from mpboot_b200 import engine
+    n, B, ninf = case["n"], args.replicates, case["n_inf"]
+    boot = make_replicates(case, B)
+    seg = do_segmenting(eng.pattern_parsimony()[0][:ninf], case["weights"], ninf)
+    eng.set_option("reps_timing", 1)
+    eng.load_replicates(boot, seg)
+    calls = []
+    for v in range(2 * n - 2):
+        calls.append(-1); calls.extend(range(vb[v], vb[v + 1]))
+    calls = np.array(calls, dtype=np.int32)
+    eng.scan_plan(order, 1, 2 * n - 2, 1, args.maxtrav)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        eng.scan_launch(); eng.reps_candidates_device(calls)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    tc_ms = []
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record()
+        eng.scan_launch(); eng.reps_candidates_device(calls)
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        ms, rows, pat, splits = eng.reps_timing()
+        tc_ms.append(ms)
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    tc = float(np.median(tc_ms))
+    ops = 2.0 * rows * ninf * B                                   # algorithmic int8 ops of the contraction
+    peak_bf16 = None
+    try:
+        peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    peak = 2.0 * (peak_bf16 if peak_bf16 else 1590.0)
+    groups, exc, tensor = eng.reps_info()
+    out = {
+        "replicates": B, "patterns": ninf, "segments": int(len(seg)), "calls_per_step": int(len(calls)),
+        "rows_per_step": int(rows), "ms_per_step": step_ms, "insertions_per_s": n_cand / (step_ms * 1e-3),
+        "reps_vectors_per_s": len(calls) / (step_ms * 1e-3),
+        "exact_path": {"column_groups": groups, "exception_patterns": exc, "tensor": tensor},
+        "roofline": {"bound": "tensor", "kernel": "k_reps_tc", "achieved": ops / (tc * 1e-3) / 1e12, "peak": peak,
+                     "unit": "TOP/s (int8, s32 accumulate)", "frac": ops / (tc * 1e-3) / 1e12 / peak,
+                     "peak_source": "2 x %s bf16_tflops (no int8 figure is measured; nominal dense int8 is 4500)"
+                                    % ("MEASURED_PEAKS.json" if peak_bf16 else "fallback"),
+                     "kernel_ms": tc, "shape": "%d rows x %d patterns x %d replicates, K splits %d" % (rows, pat, B, splits),
+                     "algorithmic_ops_per_launch": ops, "traffic": None},
+    }
+    # the whole -bb SPR search from the same random tree, cutoff off
+    from mpboot_b200.engine import HostRng, Treels
+    rs = HostRng(11)
+    bl = np.full(B, -float(np.iinfo(np.int64).max)); bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
+    tl = Treels(n)
+    t0 = time.time()
+    ret, bn2, bs2, nins, ncalls, nreps = eng.optimize_spr_bb(case["bn"], case["bs"], tl.hooks(rs.fn, rs.user), bl, bc, bt, 0.0, 0.5, 1, args.maxtrav)
+    dt = time.time() - t0
+    out["search"] = {"what": "mpgpu_optimize_spr_bb from the random tree, cutoff off, host buffers (e2e)", "wall_s": dt,
+                     "insertions": int(nins), "savecurrenttree_calls": int(ncalls), "reps_vectors": int(nreps),
+                     "insertions_per_s": nins / dt, "reps_vectors_per_s": nreps / dt, "final_score": int(ret),
+                     "replicates_won": int((bt >= 0).sum()), "trees_materialised": int(len(tl.materialized()))}
+    return out, boot, seg
+
+
+def cpu_baseline_bb(case, boot, seg, maxtrav, budget_s=20.0):
+    """Reference arm of the -bb step: rearrangeParsimony with per-site scores, every saveCurrentTree call
+    through pllComputePatternParsimony + the Vec16us REPS loop + the default bookkeeping (oracle/_ref), on as
+    many node visits of the same sweep as fit in ~budget_s on one core."""
+    from oracle import portlib, reflib
+    if reflib.available():
+        eng = reflib.RefEngine(case["chars"], case["weights"], case["datatype"], n_informative=case["n_inf"]); kind = "reference"
+    else:
+        eng = portlib.OracleEngine(case["codes"], case["weights"], case["datatype"]); kind = "port"
+    eng.set_ring(case["bn"], case["bs"])
+    eng.allocate(per_site=True)
+    s0 = eng.evaluate_full(per_site=True)
+    eng.boot_init(boot, seg, 0.0, 0.5, None)
+    n = case["n"]
+    eng.record(False)
+    t0 = time.time()
+    nvis = 0
+    for i in range(1, 2 * n - 1):
+        eng.rearrange(i, 1, maxtrav, True, s0)
+        nvis += 1
+        if time.time() - t0 > budget_s:
+            break
+    dt = time.time() - t0
+    calls = eng.boot_counters()[0]
+    ins = calls - nvis
+    return {"insertions_per_s": ins / dt, "reps_vectors_per_s": calls / dt, "cores": 1, "kind": kind,
+            "sample": "%d of %d node visits of the same sweep (%d insertions, %d REPS vectors x %d replicates) in %.1f s"
+                      % (nvis, 2 * n - 2, ins, calls, boot.shape[0], dt)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle/_ref when built
     here, else the C port) on the same workload; one process per host core, each running the
@@ -375,6 +481,11 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
         }
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
+        if world == 1 and not args.no_bb:
+            bb, boot, seg = bench_bb(eng, case, order, vb, n_cand, args, flush)
+            if not args.no_cpu_baseline:
+                bb["cpu_baseline"] = cpu_baseline_bb(case, boot, seg, args.maxtrav, budget_s=args.cpu_budget)
+            line["bb"] = bb
         if world == 1 and not args.no_cpu_baseline:
             ins, dt, kind, sample = cpu_baseline(case, args.maxtrav, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": ins / dt * ops_per_ins, "unit": UNIT, "cores": 1, "kind": kind,
@@ -395,6 +506,8 @@ def main():
     ap.add_argument("--maxtrav", type=int, default=6)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bb", action="store_true", help="skip the -bb (replicate scoring) section")
+    ap.add_argument("--replicates", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

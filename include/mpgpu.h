@@ -213,6 +213,9 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot
  * materialised trees by a canonical topology hash like the treels map (iqtree.cpp:3299-3312,
  * 3701-3708), forwards random_double to `rng`.  mpgpu_treels_materialized returns
  * [k][4] = remove_ref, insert_ref, tree_index, topology hash per materialised tree. */
+/* random_double() for hosts without their own stream: splitmix64 on the uint64_t `user` points to
+ * (an mpgpu_rng_fn). */
+double mpgpu_splitmix64_double(void *user);
 typedef struct mpgpu_treels mpgpu_treels;
 mpgpu_treels *mpgpu_treels_create(int ntaxa);
 void mpgpu_treels_destroy(mpgpu_treels *t);

@@ -375,24 +375,38 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
         const bool live = (m0 + r) < nrows;
         const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch);
         const uint32_t sw = (uint32_t)(r & 7);
-        for (int it = 0; it < nkb; it++) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            uint4 bits = make_uint4(0, 0, 0, 0);
-            if (live) bits = __ldg(src + (kb_begin + it));                 // 128 patterns of this row
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            uint8_t *arow = smem_gen + (size_t)s * STAGE_BYTES + (size_t)r * 128;
-            const uint32_t wv[4] = {bits.x, bits.y, bits.z, bits.w};
+        // the 128 bits of K-block it+PF are requested while K-block it is expanded: the L2 latency of
+        // the row loads is off the critical path of the MMA pipeline
+        constexpr int PF = 4;
+        uint4 pre[PF];
 #pragma unroll
-            for (int cidx = 0; cidx < 8; cidx++) {
-                const uint32_t h = (wv[cidx >> 1] >> ((cidx & 1) * 16)) & 0xFFFFu;
-                uint4 v;
-                v.x = spread4(h & 0xF); v.y = spread4((h >> 4) & 0xF); v.z = spread4((h >> 8) & 0xF); v.w = spread4(h >> 12);
-                *reinterpret_cast<uint4 *>(arow + ((cidx ^ sw) << 4)) = v;
+        for (int d = 0; d < PF; d++) {
+            pre[d] = make_uint4(0, 0, 0, 0);
+            if (live && d < nkb) pre[d] = __ldg(src + (kb_begin + d));
+        }
+        for (int it0 = 0; it0 < nkb; it0 += PF) {
+#pragma unroll
+            for (int d = 0; d < PF; d++) {
+                const int it = it0 + d;
+                if (it >= nkb) break;
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                const uint4 bits = pre[d];
+                if (live && it + PF < nkb) pre[d] = __ldg(src + (kb_begin + it + PF));
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                uint8_t *arow = smem_gen + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+                const uint32_t wv[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+                for (int cidx = 0; cidx < 8; cidx++) {
+                    const uint32_t h = (wv[cidx >> 1] >> ((cidx & 1) * 16)) & 0xFFFFu;
+                    uint4 v;
+                    v.x = spread4(h & 0xF); v.y = spread4((h >> 4) & 0xF); v.z = spread4((h >> 8) & 0xF); v.w = spread4(h >> 12);
+                    *reinterpret_cast<uint4 *>(arow + ((cidx ^ sw) << 4)) = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
         }
     } else if (warp == 4) {
         // ---- B producer (TMA) ----
@@ -510,12 +524,18 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int 
     }
     const int mt = (nrows + tc::M - 1) / tc::M, nt = r.Bpad / tc::N;
     const int nkb = kb_hi - kb_lo;
-    // split K so that the grid fills the GPU (148 SMs, one CTA each) without making splits tiny
+    // Split K so that the grid comes out in full waves of 148 CTAs (one per SM): cost model
+    // waves x (K-blocks per CTA + epilogue), the epilogue (TMEM -> atomics) ~ 24 K-blocks of MMA time.
     int splits = 1;
-    const int ctas = mt * nt;
-    if (ctas < 148) splits = (148 + ctas - 1) / ctas;
-    if (splits > nkb / 8) splits = nkb / 8;
-    if (splits < 1) splits = 1;
+    {
+        const int ctas = mt * nt, sms = 148, epi = 24;
+        long best = -1;
+        for (int sp = 1; sp <= 32 && sp * 8 <= nkb; sp++) {
+            const long waves = ((long)ctas * sp + sms - 1) / sms;
+            const long cost = waves * ((nkb + sp - 1) / sp + epi);
+            if (best < 0 || cost < best) { best = cost; splits = sp; }
+        }
+    }
     if (const char *e = getenv("MPGPU_REPS_SPLITS")) { int v = atoi(e); if (v >= 1) splits = v; }
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;

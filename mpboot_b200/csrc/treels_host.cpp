@@ -81,6 +81,18 @@ int32_t hook_materialize(void *user, const int32_t *bn, const int32_t *bs, int32
 
 extern "C" {
 
+// A self-contained random_double() for hosts without their own stream (tests, bench.py):
+// splitmix64 on the uint64_t state `user` points to.  MPBoot proper passes its SPRNG stream.
+double mpgpu_splitmix64_double(void *user)
+{
+    uint64_t *state = (uint64_t *)user;
+    uint64_t z = (*state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
 mpgpu_treels *mpgpu_treels_create(int ntaxa)
 {
     mpgpu_treels *h = new mpgpu_treels();

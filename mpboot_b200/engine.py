@@ -66,6 +66,8 @@ def lib():
     L.mpgpu_reps_candidates.argtypes = [vp, vp, i32, vp]
     L.mpgpu_reps_candidates_device.argtypes = [vp, vp, i32, vp, vp]
     L.mpgpu_optimize_spr_bb.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.mpgpu_splitmix64_double.restype = C.c_double
+    L.mpgpu_splitmix64_double.argtypes = [vp]
     L.mpgpu_treels_create.restype = vp
     L.mpgpu_treels_create.argtypes = [i32]
     L.mpgpu_treels_destroy.argtypes = [vp]
@@ -96,6 +98,16 @@ class BBState(C.Structure):
                 ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64)]
 
 
+class HostRng:
+    """The library's splitmix64 random_double (mpgpu_splitmix64_double) with its state: pass .fn and
+    .user wherever an mpgpu_rng_fn / user pair is expected."""
+
+    def __init__(self, seed):
+        self.state = C.c_uint64(seed)
+        self.fn = C.cast(lib().mpgpu_splitmix64_double, C.c_void_p).value
+        self.user = C.addressof(self.state)
+
+
 class Treels:
     """mpgpu_treels: the host-side treels / treels_logl container of include/mpgpu.h."""
 
@@ -111,9 +123,9 @@ class Treels:
         except Exception:
             pass
 
-    def hooks(self, rng_fn_ptr):
+    def hooks(self, rng_fn_ptr, rng_user=None):
         hk = BBHooks()
-        self.L.mpgpu_treels_hooks(self.h, C.c_void_p(rng_fn_ptr), None, C.byref(hk))
+        self.L.mpgpu_treels_hooks(self.h, C.c_void_p(rng_fn_ptr), C.c_void_p(rng_user) if rng_user else None, C.byref(hk))
         return hk
 
     def logl(self):
@@ -271,13 +283,14 @@ class Engine:
         self._ck(self.L.mpgpu_scan_finish(self.h, _p(vb), _p(mp), _p(cr), _p(cp), n_cand + 1))
         return vb, mp[:n_cand], cr[:n_cand], cp[:n_cand]
 
-    def optimize_spr(self, bn, bs, rng_fn_ptr, mintrav=1, maxtrav=6):
+    def optimize_spr(self, bn, bs, rng_fn_ptr, mintrav=1, maxtrav=6, rng_user=None):
         """pllOptimizeSprParsimony.  rng_fn_ptr: address of a `double f(void*)` (the host's
         random_double).  Returns (startMP, back_node, back_slot, insertions scored)."""
         bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
         best = C.c_uint32(); nins = C.c_int64()
         self._ck(self.L.mpgpu_optimize_spr(self.h, _p(bn), _p(bs), mintrav, maxtrav,
-                                           C.c_void_p(rng_fn_ptr), None, C.byref(best), C.byref(nins)))
+                                           C.c_void_p(rng_fn_ptr), C.c_void_p(rng_user) if rng_user else None,
+                                           C.byref(best), C.byref(nins)))
         return best.value, bn, bs, nins.value
 
     # -- R8 / -bb

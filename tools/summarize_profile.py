@@ -27,31 +27,49 @@ if os.path.exists(lp):
     for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         out.append("%-72s n=%3d avg=%9.2f us total=%9.3f ms share=%5.1f%%" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e6, 100 * sum(v) / tot))
 
-rp = os.path.join(go, "prof_scan_%s.ncu-rep" % tag)
-if os.path.exists(rp):
-    txt = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "l1tex__throughput.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_registers", "sm__cycles_elapsed.max"]
+
+
+def full_capture(rep, title):
+    if not os.path.exists(rep):
+        return
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr = rows[0]
-    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-            "l1tex__throughput.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
-            "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
-            "launch__occupancy_limit_registers", "sm__cycles_elapsed.max"]
     out.append("")
-    out.append("== ncu --set full, kernel k_spr_scan (2 launches captured) ==")
-    for w in want:
+    out.append("== ncu --set full, %s (%d launch(es) captured) ==" % (title, len(rows) - 2))
+    for w in WANT:
         if w in hdr:
             i = hdr.index(w)
-            out.append("%-70s %s" % (w, " | ".join(r[i] for r in rows[1:])))
-    out.append("-- warp stall reasons (warps per issue-active cycle, launch 1) --")
+            out.append("%-70s %s | %s" % (w, rows[1][i], " | ".join(r[i] for r in rows[2:])))
+    tens = [h for h in hdr if ("tensor" in h or "tmem" in h.lower()) and ".avg." in h]
+    for h in tens:
+        if h not in WANT:
+            i = hdr.index(h)
+            vals = [r[i] for r in rows[2:]]
+            if any(v not in ("0", "0.0", "", "n/a") for v in vals):
+                out.append("%-70s %s | %s" % (h, rows[1][i], " | ".join(vals)))
+    out.append("-- warp stall reasons (warps per issue-active cycle, first launch) --")
     for i, h in enumerate(hdr):
         if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:
-            v = float(rows[2][i])
+            try:
+                v = float(rows[2][i])
+            except ValueError:
+                continue
             if v > 0.05:
                 out.append("   %-28s %.3f" % (h.split("issue_stalled_")[1].split("_per_")[0], v))
+
+
+full_capture(os.path.join(go, "prof_scan_%s.ncu-rep" % tag), "kernel k_spr_scan")
+full_capture(os.path.join(go, "prof_reps_%s.ncu-rep" % tag), "kernel k_reps_tc (tcgen05 kind::i8 replicate contraction)")
 
 for name in ("bench_%s.json" % tag, "bench_ref_%s.json" % tag):
     bp = os.path.join(go, name)
