@@ -50,6 +50,16 @@ int mpgpu_device_count(void);
  * all-reduce of the int32 vector) before they are scores. */
 int mpgpu_create(mpgpu_ctx **out, int device, void *stream, int shard_rank, int shard_count);
 int mpgpu_destroy(mpgpu_ctx *ctx);
+/* Pattern-sharded contexts (shard_count > 1): the one exchange step of the path is an
+ * in-place int32 SUM all-reduce over the shards of a small device vector.  The host supplies it
+ * (ncclAllReduce on its communicator, or torch.distributed): `fn` must enqueue the reduction of
+ * dev_buf[0..count) on `stream` (the context's stream) and return 0.  With a callback installed
+ * every call of this header returns complete results on every shard -- view lengths, scores,
+ * per-insertion scores, pattern scores, replicate scores, and the SPR searches run replicated
+ * (same host decisions on every rank, same RNG stream required).  Without one, sharded contexts
+ * only offer the *_partial calls and the caller reduces. */
+typedef int (*mpgpu_allreduce_fn)(void *user, void *dev_buf, int64_t count, void *stream);
+int mpgpu_set_allreduce(mpgpu_ctx *ctx, mpgpu_allreduce_fn fn, void *user);
 /* The stream all kernels are launched on (cudaStream_t). */
 void *mpgpu_stream(mpgpu_ctx *ctx);
 int mpgpu_synchronize(mpgpu_ctx *ctx);

@@ -62,6 +62,14 @@ static void free_alignment(Ctx *c)
     c->tree_set = false; c->lens_valid = false;
 }
 
+int shard_sum(Ctx *c, void *dev_i32, int64_t count)
+{
+    if (c->shard_count == 1 || count <= 0) return 0;
+    if (!c->allreduce) { set_error("sharded context: this call needs mpgpu_set_allreduce (or use the *_partial calls)"); return 1; }
+    if (c->allreduce(c->allreduce_user, dev_i32, count, (void *)c->stream)) { set_error("the all-reduce callback failed"); return 1; }
+    return 0;
+}
+
 // layout + tip planes for the current weights (compressDNA, sprparsimony.cpp:2864-2961)
 static int build_planes(Ctx *c, bool realloc_views)
 {
@@ -161,6 +169,7 @@ int compute_views(Ctx *c)
         off += lv.size();
     }
     c->reps.tree_valid = false;
+    if (c->shard_count > 1 && c->allreduce) { if (int rc = shard_sum(c, c->d_vcount, nviews)) return rc; }
     c->vcount.assign(nviews, 0);
     MPGPU_CUDA(cudaMemcpyAsync(c->vcount.data(), c->d_vcount, nviews * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -207,7 +216,9 @@ int run_scan(Ctx *c)
     ScanPlan &pl = c->plan;
     const size_t nout = (size_t)pl.n_cand + pl.tasks.size();
     MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, (nout + 1) * sizeof(int32_t), c->stream));
-    return launch_scan(c, (int)pl.tasks.size(), pl.max_slot);
+    if (int rc = launch_scan(c, (int)pl.tasks.size(), pl.max_slot)) return rc;
+    if (c->shard_count > 1 && c->allreduce) return shard_sum(c, c->d_counts, (int64_t)nout);
+    return 0;
 }
 
 int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
@@ -261,7 +272,7 @@ int ensure_ptn_site(Ctx *c)
     const int upper = c->sort_alignment ? c->n_inf : c->P;
     std::vector<int64_t> ptn_site(upper > 0 ? upper : 1);
     int64_t site = 0;
-    bool ident = c->shard_count == 1;
+    bool ident = true;
     for (int i = 0; i < upper; i++) {
         ptn_site[i] = site < (int64_t)c->ref_words * 32 ? site : -1;
         if (ptn_site[i] != i) ident = false;
@@ -336,6 +347,18 @@ int mpgpu_destroy(mpgpu_ctx *c)
     return 0;
 }
 
+int mpgpu_set_allreduce(mpgpu_ctx *c, mpgpu_allreduce_fn fn, void *user)
+{
+    if (!c) { set_error("null context"); return 1; }
+    c->allreduce = fn; c->allreduce_user = user;
+    if (fn && c->tree_set && !c->lens_valid) {            // the partial counts of the resident tree can be completed now
+        MPGPU_CUDA(cudaSetDevice(c->device));
+        if (int rc = compute_views(c)) return rc;
+        compute_lengths(c);
+    }
+    return 0;
+}
+
 void *mpgpu_stream(mpgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int mpgpu_synchronize(mpgpu_ctx *c) { if (!c) return 1; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 int64_t mpgpu_launch_count(mpgpu_ctx *c) { return c ? c->launches : 0; }
@@ -370,7 +393,7 @@ int mpgpu_set_weights(mpgpu_ctx *c, const int32_t *aliaswgt)
     if (int rc = build_planes(c, false)) return rc;
     if (c->tree_set) {                      // views depend on the planes
         if (int rc = compute_views(c)) return rc;
-        if (c->shard_count == 1) compute_lengths(c);
+        if (c->reduces()) compute_lengths(c);
     }
     return 0;
 }
@@ -429,7 +452,7 @@ int mpgpu_set_tree(mpgpu_ctx *c, const int32_t *back_node, const int32_t *back_s
     }
     c->tree_set = true; c->lens_valid = false;
     if (int rc = compute_views(c)) return rc;
-    if (c->shard_count == 1) compute_lengths(c);
+    if (c->reduces()) compute_lengths(c);
     return 0;
 }
 
@@ -470,7 +493,7 @@ int mpgpu_get_view_planes(mpgpu_ctx *c, int node, int slot, uint32_t *out)
     return copy_view_ref_layout(c, c->tree.vid(3 * node + slot), out);
 }
 
-int mpgpu_edge_mismatch_partial(mpgpu_ctx *c, int node, int slot, uint32_t *count)
+static int edge_mismatch(mpgpu_ctx *c, int node, int slot, uint32_t *count, bool reduce)
 {
     if (int rc = need_tree(c, false)) return rc;
     if (int rc = check_ref(c, node, slot)) return rc;
@@ -478,17 +501,23 @@ int mpgpu_edge_mismatch_partial(mpgpu_ctx *c, int node, int slot, uint32_t *coun
     const int r = 3 * node + slot;
     MPGPU_CUDA(cudaMemsetAsync(c->d_scalar, 0, sizeof(uint32_t), c->stream));
     if (int rc = launch_edge_mismatch(c, c->tree.vid(r), c->tree.vid(c->tree.back(r)), c->d_scalar)) return rc;
+    if (reduce) { if (int rc = shard_sum(c, c->d_scalar, 1)) return rc; }
     MPGPU_CUDA(cudaMemcpyAsync(count, c->d_scalar, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
+int mpgpu_edge_mismatch_partial(mpgpu_ctx *c, int node, int slot, uint32_t *count)
+{
+    return edge_mismatch(c, node, slot, count, false);
+}
+
 int mpgpu_tree_score(mpgpu_ctx *c, uint32_t *score)
 {
-    if (int rc = need_tree(c, c && c->shard_count == 1)) return rc;
+    if (int rc = need_tree(c, c && c->reduces())) return rc;
     uint32_t mis = 0;
-    if (int rc = mpgpu_edge_mismatch_partial(c, 1, 0, &mis)) return rc;
-    if (c->shard_count == 1) *score = mis + c->vlen[c->tree.vid(c->tree.back(3))];
+    if (int rc = edge_mismatch(c, 1, 0, &mis, c->shard_count > 1 && c->allreduce)) return rc;
+    if (c->reduces()) *score = mis + c->vlen[c->tree.vid(c->tree.back(3))];
     else *score = mis;
     return 0;
 }
@@ -502,8 +531,13 @@ int mpgpu_pattern_parsimony(mpgpu_ctx *c, uint16_t *ptn_pars, int32_t *sum)
     if (int rc = compute_site_counters(c, nbits)) return rc;
     if (int rc = ensure_ptn_site(c)) return rc;
     const int upper = c->sort_alignment ? c->n_inf : c->P;                // :3380-3381
-    if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper > 0 ? upper : 1))) return rc;
+    if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)upper + 2)) return rc;
     if (int rc = launch_gather_patterns(c, nbits, upper)) return rc;
+    if (c->shard_count > 1 && c->allreduce) {
+        // every pattern is non-zero on exactly one shard: summing u16 pairs as int32 cannot carry
+        MPGPU_CUDA(cudaMemsetAsync(c->d_ptn + upper, 0, 2 * sizeof(uint16_t), c->stream));
+        if (int rc = shard_sum(c, c->d_ptn, (upper + 1) / 2)) return rc;
+    }
     if (upper > 0)
         MPGPU_CUDA(cudaMemcpyAsync(ptn_pars, c->d_ptn, (size_t)upper * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -565,7 +599,7 @@ int mpgpu_scan_visits(mpgpu_ctx *c, const int32_t *order, int first, int count, 
                       int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune,
                       int capacity, int *n_cand)
 {
-    if (c && c->shard_count != 1) { set_error("mpgpu_scan_visits is single-shard; use plan/launch/finish"); return 1; }
+    if (c && !c->reduces()) { set_error("mpgpu_scan_visits on a sharded context needs mpgpu_set_allreduce (or use plan/launch/finish)"); return 1; }
     int nc = 0, nt = 0;
     if (int rc = mpgpu_scan_plan(c, order, first, count, mintrav, maxtrav, &nc, &nt)) return rc;
     if (n_cand) *n_cand = nc;

@@ -38,7 +38,7 @@ static inline void rp_stop(Ctx *c, int k) { if (g_rp.on) { cudaStreamSynchronize
 void free_reps(Ctx *c)
 {
     Reps &r = c->reps;
-    void *ptrs[] = {r.d_w8, r.d_w16T, r.d_seg_upper, r.d_seg_flags, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
+    void *ptrs[] = {r.d_w8, r.d_w16T, r.d_seg_upper, r.d_segmax, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
                     r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_call_hit, r.d_hit_list, r.d_res_hit};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (r.ev0) { cudaEventDestroy(r.ev0); cudaEventDestroy(r.ev1); }
@@ -49,19 +49,25 @@ void free_reps(Ctx *c)
     c->d_row_of = nullptr; c->d_row_tasks = nullptr; c->d_rows_site = nullptr;
 }
 
-// K-blocks (128 patterns) whose first expanded site can fall into this shard's word slice
+// Patterns [p_lo, p_hi) whose first expanded site falls into this shard's word slice, and the
+// 128-pattern K-blocks [kb_lo, kb_hi) the tensor kernel has to visit for them.
 static void update_kb_range(Ctx *c)
 {
     Reps &r = c->reps;
-    if (c->shard_count == 1) { r.kb_lo = 0; r.kb_hi = r.Kpad / 128; return; }
+    if (c->shard_count == 1) { r.p_lo = 0; r.p_hi = r.upper; r.kb_lo = 0; r.kb_hi = r.Kpad / 128; return; }
     const int64_t s_lo = c->w0 * 32, s_hi = (c->w0 + c->Wl) * 32;
     int p_lo = r.upper, p_hi = 0;
-    int64_t site = 0;
-    for (int i = 0; i < r.upper; i++) {
-        if (site >= s_lo && site < s_hi) { if (i < p_lo) p_lo = i; p_hi = i + 1; }
-        site += c->weights[i];
+    if (c->ptn_identity) {
+        p_lo = (int)std::min<int64_t>(s_lo, r.upper); p_hi = (int)std::min<int64_t>(s_hi, r.upper);
+    } else {
+        int64_t site = 0;
+        for (int i = 0; i < r.upper; i++) {
+            if (site >= s_lo && site < s_hi) { if (i < p_lo) p_lo = i; p_hi = i + 1; }
+            site += c->weights[i];
+        }
     }
-    if (p_hi <= p_lo) { r.kb_lo = r.kb_hi = 0; return; }
+    if (p_hi <= p_lo) { r.p_lo = r.p_hi = 0; r.kb_lo = r.kb_hi = 0; return; }
+    r.p_lo = p_lo; r.p_hi = p_hi;
     r.kb_lo = p_lo / 128; r.kb_hi = (p_hi + 127) / 128;
 }
 
@@ -92,13 +98,14 @@ static int ensure_rows(Ctx *c, int rows)
 }
 
 // pattern-indexed bit rows a_base[0..nrows) -> X[x_row0 ..) (all groups)
-static int contract_rows(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows)
+// (bit i of a row = pattern 32 * a_word0 + i: site rows of a shard start at its first word)
+static int contract_rows(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows)
 {
     Reps &r = c->reps;
     if (nrows == 0) return 0;
     MPGPU_CUDA(cudaMemsetAsync(r.d_X + (size_t)x_row0 * r.G * r.Bpad, 0, (size_t)nrows * r.G * r.Bpad * 4, c->stream));
-    if (int rc = launch_reps_exc(c, a_base, a_pitch, x_row0, nrows)) return rc;
-    if (r.use_tensor) { if (int rc = launch_reps_tc(c, a_base, a_pitch, x_row0, nrows)) return rc; }
+    if (int rc = launch_reps_exc(c, a_base, a_pitch, a_word0, x_row0, nrows)) return rc;
+    if (r.use_tensor) { if (int rc = launch_reps_tc(c, a_base, a_pitch, a_word0, x_row0, nrows)) return rc; }
     r.rows_scored += nrows;
     return 0;
 }
@@ -174,23 +181,25 @@ static int refresh_tree_rows(Ctx *c)
     const int upper0 = c->sort_alignment ? c->n_inf : c->P;
     if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper0 > 0 ? upper0 : 1))) return rc;
     if (int rc = launch_gather_patterns(c, nbits, upper0)) return rc;
-    MPGPU_CUDA(cudaMemsetAsync(r.d_seg_flags, 0, (size_t)nseg, c->stream));
-    if (int rc = launch_seg_check(c, r.d_seg_flags)) return rc;
-    std::vector<uint8_t> flags(nseg);
-    MPGPU_CUDA(cudaMemcpyAsync(flags.data(), r.d_seg_flags, (size_t)nseg, cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(r.d_segmax, 0, (size_t)nseg * 4, c->stream));
+    if (int rc = launch_seg_check(c, r.d_segmax)) return rc;
+    if (int rc = shard_sum(c, r.d_segmax, nseg)) return rc;
+    std::vector<int32_t> segmax(nseg);
+    MPGPU_CUDA(cudaMemcpyAsync(segmax.data(), r.d_segmax, (size_t)nseg * 4, cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     bool grew = false;
-    for (int g = 0; g < nseg; g++) if (flags[g] && !r.seg_flagged[g]) { r.seg_flagged[g] = 1; grew = true; }
+    for (int g = 0; g < nseg; g++) if (segmax[g] >= 65536 && !r.seg_flagged[g]) { r.seg_flagged[g] = 1; grew = true; }
     if (grew) { if (int rc = build_classification(c)) return rc; }
     rp_stop(c, 1);
     if (int rc = ensure_rows(c, kTreeRows + 64)) return rc;
     if (c->ptn_identity) {
-        if (int rc = contract_rows(c, c->d_bitcnt, c->Wl, 0, nbits)) return rc;
+        if (int rc = contract_rows(c, c->d_bitcnt, c->Wl, (int)c->w0, 0, nbits)) return rc;
     } else {
         if (int rc = launch_gather_rows(c, c->d_bitcnt, r.d_rows_ptn, nbits)) return rc;
-        if (int rc = contract_rows(c, r.d_rows_ptn, r.Pw, 0, nbits)) return rc;
+        if (int rc = contract_rows(c, r.d_rows_ptn, r.Pw, 0, 0, nbits)) return rc;
     }
     if (int rc = launch_reps_tree_row(c, 0, nbits, kTreeRows - 1)) return rc;
+    if (int rc = shard_sum(c, r.d_X + (size_t)(kTreeRows - 1) * r.G * r.Bpad, (int64_t)r.G * r.Bpad)) return rc;
     rp_stop(c, 2);
     r.tree_valid = true;
     return 0;
@@ -283,13 +292,14 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
             if (int rc = launch_scan_rows(c, (int)row_tasks.size(), pl.max_slot)) return rc;
             rp_stop(c, 4);
             if (c->ptn_identity) {
-                if (int rc = contract_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl, c->Wl, kTreeRows, nrows)) return rc;
+                if (int rc = contract_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl, c->Wl, (int)c->w0, kTreeRows, nrows)) return rc;
             } else {
                 if (int rc = launch_gather_rows(c, r.d_rows_site + (size_t)kTreeRows * c->Wl,
                                                 r.d_rows_ptn + (size_t)kTreeRows * r.Pw, nrows)) return rc;
-                if (int rc = contract_rows(c, r.d_rows_ptn + (size_t)kTreeRows * r.Pw, r.Pw, kTreeRows, nrows)) return rc;
+                if (int rc = contract_rows(c, r.d_rows_ptn + (size_t)kTreeRows * r.Pw, r.Pw, 0, kTreeRows, nrows)) return rc;
             }
         }
+        if (nrows > 0) { if (int rc = shard_sum(c, r.d_X + (size_t)kTreeRows * r.G * r.Bpad, (int64_t)nrows * r.G * r.Bpad)) return rc; }
         rp_stop(c, 5);
         // ---- combine ----
         if (thr) {
@@ -397,7 +407,7 @@ using namespace mpgpu;
 static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                          mpgpu_rng_fn rng, void *rng_user, BBRun *bb, uint32_t *best, int64_t *n_insertions)
 {
-    if (c->shard_count != 1) { set_error("mpgpu_optimize_spr is single-shard in this version"); return 1; }
+    if (!c->reduces()) { set_error("the SPR search on a sharded context needs mpgpu_set_allreduce"); return 1; }
     if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
     if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
     const int n = c->n, nvisit = 2 * n - 2;
@@ -590,7 +600,7 @@ int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride,
     MPGPU_CUDA(cudaMalloc((void **)&r.d_w8, (size_t)r.Bpad * r.Kpad));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_w16T, (size_t)std::max(r.upper, 1) * r.Bpad * sizeof(uint16_t)));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_seg_upper, (size_t)nseg_ * 4));
-    MPGPU_CUDA(cudaMalloc((void **)&r.d_seg_flags, (size_t)nseg_));
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_segmax, (size_t)nseg_ * 4));
     MPGPU_CUDA(cudaMalloc((void **)&d_boot16, (size_t)B * stride * sizeof(uint16_t)));
     MPGPU_CUDA(cudaMalloc((void **)&d_heavy, r.heavy.size()));
     MPGPU_CUDA(cudaMemcpyAsync(r.d_seg_upper, segment_upper, (size_t)nseg_ * 4, cudaMemcpyHostToDevice, c->stream));
@@ -616,7 +626,7 @@ int mpgpu_reps_current_tree(mpgpu_ctx *c, int32_t *res)
     if (int rc = need_tree(c, true)) return rc;
     if (!res) { set_error("null argument"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
-    if (c->shard_count != 1) { set_error("mpgpu_reps_current_tree is single-shard in this version"); return 1; }
+    if (!c->reduces()) { set_error("mpgpu_reps_current_tree on a sharded context needs mpgpu_set_allreduce"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     // the current tree needs no scan plan: a one-call batch with an empty plan
     const int32_t cand = -1;
@@ -631,7 +641,7 @@ int mpgpu_reps_candidates_device(mpgpu_ctx *c, const int32_t *cand_idx, int m, v
     if (int rc = need_tree(c, true)) return rc;
     if (!cand_idx || m < 0) { set_error("bad argument"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
-    if (c->shard_count != 1) { set_error("mpgpu_reps_candidates_device is single-shard in this version"); return 1; }
+    if (!c->reduces()) { set_error("mpgpu_reps_candidates_device on a sharded context needs mpgpu_set_allreduce"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     RepsOut ro;
     if (int rc = reps_run(c, cand_idx, m, nullptr, ro, true)) return rc;
@@ -645,7 +655,7 @@ int mpgpu_reps_candidates(mpgpu_ctx *c, const int32_t *cand_idx, int m, int32_t 
     if (int rc = need_tree(c, true)) return rc;
     if (!cand_idx || !res || m < 0) { set_error("bad argument"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
-    if (c->shard_count != 1) { set_error("mpgpu_reps_candidates is single-shard in this version"); return 1; }
+    if (!c->reduces()) { set_error("mpgpu_reps_candidates on a sharded context needs mpgpu_set_allreduce"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     RepsOut ro;
     if (int rc = reps_run(c, cand_idx, m, nullptr, ro)) return rc;

@@ -83,11 +83,12 @@ struct Reps {
     int G = 1;                            // column groups: 0 = wrap-free bulk, g >= 1 = one wrap-prone segment each
     int n_exc = 0, n_heavy = 0;           // exception patterns (all of groups >= 1, plus weights > 255 of group 0)
     int kb_lo = 0, kb_hi = 0;             // 128-pattern K-blocks that can have bits on this shard
+    int p_lo = 0, p_hi = 0;               // patterns whose first expanded site lies in this shard's word slice
+    int32_t *d_segmax = nullptr;          // [nseg] wrap check: max over replicates of the segment bound
     bool use_tensor = true;
     uint8_t *d_w8 = nullptr;              // [Bpad][Kpad] u8, K-major: the tensor kernel's B operand
     uint16_t *d_w16T = nullptr;           // [upper][Bpad] u16, pattern-major: the exact weights
     int32_t *d_seg_upper = nullptr;       // [nseg]
-    uint8_t *d_seg_flags = nullptr;       // [nseg] scratch of the wrap check
     std::vector<uint8_t> heavy;           // [upper] some replicate weight > 255
     std::vector<uint8_t> seg_flagged;     // [nseg] segment is in a group of its own (can wrap)
     int32_t *d_exc_ptn = nullptr, *d_exc_group = nullptr; size_t exc_cap = 0, exc_group_cap = 0;
@@ -134,6 +135,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int shard_rank = 0, shard_count = 1;
+    mpgpu_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
+    bool reduces() const { return shard_count == 1 || allreduce != nullptr; }   // results are complete on this shard
     int64_t launches = 0;
 
     // alignment
@@ -202,6 +205,7 @@ static inline int ensure(T *&ptr, size_t &cap, size_t need)
 }
 
 // ---- shared host helpers (mpgpu_api.cu) -----------------------------------------------------
+int shard_sum(Ctx *c, void *dev_i32, int64_t count);   // in-place int32 all-reduce over the shards (no-op for one shard)
 int compute_views(Ctx *c);
 void compute_lengths(Ctx *c);
 int need_tree(Ctx *c, bool lens);
@@ -225,12 +229,12 @@ const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);
 // ---- kernel launchers (reps_kernels.cu) ----------------------------------------------------
 int launch_transpose_boot(Ctx *c, const uint16_t *d_boot16, int stride, uint8_t *d_heavy);
 int launch_build_w8(Ctx *c, const uint8_t *d_is_exc);
-int launch_seg_check(Ctx *c, uint8_t *d_flags);
+int launch_seg_check(Ctx *c, int32_t *d_segmax);
 int launch_edge_rows(Ctx *c, const int4 *d_edges, int nedges, uint32_t *d_rows);
 int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows);
-int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows);
+int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows);
 int make_w8_tensor_map(Ctx *c);
-int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows);
+int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows);
 int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row);
 int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr, int32_t *d_call_hit);
 int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, int nlist, int32_t *d_out);

@@ -90,31 +90,36 @@ int launch_build_w8(Ctx *c, const uint8_t *d_is_exc)
 // per-pattern score <= c_T + 1 (one SPR adds at most one step per site), so a segment whose
 //     sum_{ptn in seg} (c_T[ptn] + 1) * w[b][ptn]  <  2^16   for every replicate b
 // cannot wrap in the reference's u16 lanes for T or any of its candidates: its mod-2^16 is the
-// identity and it may stay in the tensor path's bulk group.  flags[seg] = 1 otherwise.
+// identity and it may stay in the tensor path's bulk group.  segmax[seg] = max over b of that
+// sum over THIS shard's patterns [p_lo, p_hi) (clipped); shards add their maxima (an upper bound
+// of the true maximum) and a segment is wrap-prone when the total reaches 2^16.
 __global__ void __launch_bounds__(256) k_seg_check(const uint16_t *__restrict__ ptn_pars, const uint16_t *__restrict__ w16T,
-                                                   const int32_t *__restrict__ seg_upper, int seg0, int upper, int B, int Bpad,
-                                                   uint8_t *__restrict__ flags)
+                                                   const int32_t *__restrict__ seg_upper, int seg0, int p_lo, int p_hi, int B, int Bpad,
+                                                   int32_t *__restrict__ segmax)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int seg = seg0 + blockIdx.y;
-    if (b >= B) return;
-    const int lo = seg ? seg_upper[seg - 1] : 0;
+    int lo = seg ? seg_upper[seg - 1] : 0;
     int hi = seg_upper[seg];
-    if (hi > upper) hi = upper;
+    if (lo < p_lo) lo = p_lo;
+    if (hi > p_hi) hi = p_hi;
     unsigned long long sum = 0;
-    for (int p = lo; p < hi; p++) sum += (unsigned long long)(__ldg(ptn_pars + p) + 1u) * __ldg(w16T + (size_t)p * Bpad + b);
-    if (sum >= 65536ull) flags[seg] = 1;
+    if (b < B)
+        for (int p = lo; p < hi; p++) sum += (unsigned long long)(__ldg(ptn_pars + p) + 1u) * __ldg(w16T + (size_t)p * Bpad + b);
+    int v = sum > (1ull << 28) ? (1 << 28) : (int)sum;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(&segmax[seg], v);
 }
 
-int launch_seg_check(Ctx *c, uint8_t *d_flags)
+int launch_seg_check(Ctx *c, int32_t *d_segmax)
 {
     Reps &r = c->reps;
     const int nseg = (int)r.seg_upper.size();
-    if (r.upper == 0) return 0;
+    if (r.upper == 0 || r.p_hi <= r.p_lo) return 0;
     for (int done = 0; done < nseg; done += 65535) {
         const int chunk = nseg - done < 65535 ? nseg - done : 65535;
         dim3 grid((r.B + 255) / 256, chunk);
-        k_seg_check<<<grid, 256, 0, c->stream>>>(c->d_ptn, r.d_w16T, r.d_seg_upper, done, r.upper, r.B, r.Bpad, d_flags);
+        k_seg_check<<<grid, 256, 0, c->stream>>>(c->d_ptn, r.d_w16T, r.d_seg_upper, done, r.p_lo, r.p_hi, r.B, r.Bpad, d_segmax);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }
@@ -213,7 +218,7 @@ int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows
 //   X[row][group(e)][b] += bit[row][ptn(e)] * w16e[e][b]
 // exceptions are sorted by group; one thread per (row, b).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ rows_a, int a_pitch, int row0, int x_row0,
+__global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ rows_a, int a_pitch, int a_word0, int a_words, int row0, int x_row0,
                                                   const int32_t *__restrict__ exc_ptn, const int32_t *__restrict__ exc_group,
                                                   int n_exc, const uint16_t *__restrict__ w16T, int Bpad, int G,
                                                   int32_t *__restrict__ X)
@@ -231,20 +236,21 @@ __global__ void __launch_bounds__(256) k_reps_exc(const uint32_t *__restrict__ r
             cur = g; acc = 0;
         }
         const int p = __ldg(exc_ptn + e);
-        if ((__ldg(bits + (p >> 5)) >> (p & 31)) & 1u) acc += (int)__ldg(w16T + (size_t)p * Bpad + b);
+        const int w = (p >> 5) - a_word0;                      // the row starts at pattern 32 * a_word0
+        if (w >= 0 && w < a_words && ((__ldg(bits + w) >> (p & 31)) & 1u)) acc += (int)__ldg(w16T + (size_t)p * Bpad + b);
     }
     if (cur >= 0 && acc) atomicAdd(&xrow[(size_t)cur * Bpad + b], acc);
 }
 
-// rows a_base[0..nrows) (pitch a_pitch words, pattern-indexed bits) -> X[x_row0 ..][group][b]
-int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows)
+// rows a_base[0..nrows) (pitch a_pitch words; bit i of a row = pattern 32 * a_word0 + i) -> X[x_row0 ..][group][b]
+int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows)
 {
     Reps &r = c->reps;
     if (nrows == 0 || r.n_exc == 0) return 0;
     for (int done = 0; done < nrows; done += 65535) {
         const int chunk = nrows - done < 65535 ? nrows - done : 65535;
         dim3 grid((r.Bpad + 255) / 256, chunk);
-        k_reps_exc<<<grid, 256, 0, c->stream>>>(a_base, a_pitch, done, x_row0, r.d_exc_ptn, r.d_exc_group, r.n_exc,
+        k_reps_exc<<<grid, 256, 0, c->stream>>>(a_base, a_pitch, a_word0, a_pitch, done, x_row0, r.d_exc_ptn, r.d_exc_group, r.n_exc,
                                                  r.d_w16T, r.Bpad, r.G, r.d_X);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
@@ -334,7 +340,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
 __global__ void __launch_bounds__(THREADS, 1)
-k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_a, int a_pitch,
+k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_a, int a_pitch, int a_kb0,
           int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -373,7 +379,7 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
         // ---- A producers: thread r owns tile row r ----
         const int r = threadIdx.x;
         const bool live = (m0 + r) < nrows;
-        const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch);
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch) - a_kb0;   // row starts at K-block a_kb0
         const uint32_t sw = (uint32_t)(r & 7);
         // the 128 bits of K-block it+PF are requested while K-block it is expanded: the L2 latency of
         // the row loads is off the critical path of the MMA pipeline
@@ -509,8 +515,9 @@ int make_w8_tensor_map(Ctx *c)
 }
 
 // X[x_row0 .. x_row0+nrows)[group 0] += rows x w8   (this shard's K-blocks [kb_lo, kb_hi));
-// rows = a_base[0..nrows), pitch a_pitch words (a multiple of 4), pattern-indexed bits
-int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int nrows)
+// rows = a_base[0..nrows), pitch a_pitch words (a multiple of 4); bit i of a row = pattern 32 * a_word0 + i
+// (a_word0 a multiple of 4: rows start on a K-block boundary)
+int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows)
 {
     Reps &r = c->reps;
     if (nrows == 0) return 0;
@@ -545,7 +552,7 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int x_row0, int 
         if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
         MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
     }
-    tc::k_reps_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch,
+    tc::k_reps_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
                                                                     x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
     if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
     c->launches++;

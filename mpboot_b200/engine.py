@@ -33,6 +33,7 @@ def lib():
     L.mpgpu_device_count.restype = i32
     L.mpgpu_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32]
     L.mpgpu_destroy.argtypes = [vp]
+    L.mpgpu_set_allreduce.argtypes = [vp, vp, vp]
     L.mpgpu_stream.restype = vp
     L.mpgpu_stream.argtypes = [vp]
     L.mpgpu_synchronize.argtypes = [vp]
@@ -157,6 +158,11 @@ class Engine:
         self.h = h
         self.n = self.P = 0
         self.shard_count = shard_count
+
+    def set_allreduce(self, callback):
+        """callback: a ctypes function object of type mpgpu_allreduce_fn (see mpboot_b200.sharded)."""
+        self._allreduce_cb = callback                    # keep it alive
+        self._ck(self.L.mpgpu_set_allreduce(self.h, C.cast(callback, C.c_void_p), None))
 
     def _ck(self, rc):
         if rc:
