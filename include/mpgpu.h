@@ -154,6 +154,16 @@ int mpgpu_optimize_spr(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot,
                        int mintrav, int maxtrav, mpgpu_rng_fn rng, void *rng_user,
                        uint32_t *best, int64_t *n_insertions);
 
+/* ---- R7: _pllComputeRandomizedStepwiseAdditionParsimonyTree (sprparsimony.cpp:3224, 3107, 2977) ----
+ * Builds a randomized-stepwise-addition tree over the loaded alignment and runs the SPR rounds
+ * of _pllMakeParsimonyTreeFast on it (radius spr_dist).  *random_seed is tr->randomNumberSeed
+ * (PLL's private generator for the taxon order, pllrepo/src/utils.c:335; updated like the
+ * reference does); rng is the host's random_double() for the tie-breaks (:3004, :3199).  The tree
+ * comes back as ring tables with the reference's node numbering (inner nodes n+1.. in insertion
+ * order), *best = tr->bestParsimony. */
+int mpgpu_stepwise_addition(mpgpu_ctx *ctx, int64_t *random_seed, int spr_dist, mpgpu_rng_fn rng, void *rng_user,
+                            int32_t *back_node, int32_t *back_slot, uint32_t *best, int64_t *n_insertions);
+
 /* ---- R8: replicate scoring, the REPS block of IQTree::saveCurrentTree (iqtree.cpp:3356-3449) ----
  * boot_samples: [B][stride] u16, boot_samples_pars exactly as IQTree::setParams fills it
  * (iqtree.cpp:220-233, 285-313; stride >= number of reported patterns); segment_upper/nseg

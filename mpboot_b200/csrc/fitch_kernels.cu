@@ -259,6 +259,47 @@ int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out)
 }
 
 // ------------------------------------------------------------------------------------------
+// R7: stepwise addition (stepwiseAddition, sprparsimony.cpp:2977-3019): the extra steps of
+// hanging tip T on the branch between the views A and B: popc(~OR_k(fitch(A,B)_k & T_k)).
+// One thread per (branch, site word); the tree's own length is added on the host.
+// ------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(128) k_tip_insert(const uint32_t *__restrict__ views, size_t view_stride, int Wl,
+                                                    const int4 *__restrict__ edges, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int4 e = edges[blockIdx.y];                              // vidA, vidB, vidT
+    const size_t gs = (size_t)Wl * Lay<S>::SG;
+    const size_t off = (size_t)w * Lay<S>::SG;
+    uint32_t a[S], b[S];
+    load_states<S>(views + (size_t)e.x * view_stride + off, gs, a);
+    load_states<S>(views + (size_t)e.y * view_stride + off, gs, b);
+    const uint32_t n = any_and<S>(a, b);
+#pragma unroll
+    for (int k = 0; k < S; k++) a[k] = fitch1(a[k], b[k], n);
+    load_states<S>(views + (size_t)e.z * view_stride + off, gs, b);
+    const int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(a, b)));
+    if (lane == 0 && cnt) atomicAdd(&out[blockIdx.y], cnt);
+}
+
+int launch_tip_insert(Ctx *c, const int4 *d_edges, int nedges, int32_t *d_out)
+{
+    if (nedges == 0) return 0;
+    dim3 grid(c->Wl / 128, nedges);
+    switch (c->S) {
+    case 2:  k_tip_insert<2><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_out); break;
+    case 4:  k_tip_insert<4><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_out); break;
+    case 20: k_tip_insert<20><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_out); break;
+    case 32: k_tip_insert<32><<<grid, 128, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_edges, d_out); break;
+    default: set_error("unsupported state count"); return 1;
+    }
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // R6: the SPR scan.
 //
 // A task is one pruned subtree S with the two views D1, D2 that become neighbours once the

@@ -516,7 +516,142 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     return 0;
 }
 
+// PLL's private generator (pllrepo/src/utils.c:335-357): a 28-bit multiplicative congruential
+// generator worked in 12-bit limbs; returns a double in [0,1) and advances *seed.
+static double pll_randum(int64_t *seed)
+{
+    const int64_t s0 = *seed & 4095, s1 = (*seed >> 12) & 4095, s2 = (*seed >> 24) & 255;
+    int64_t acc = 1549 * s0;
+    const int64_t n0 = acc & 4095;
+    acc = (acc >> 12) + 1549 * s1 + 406 * s0;
+    const int64_t n1 = acc & 4095;
+    acc = (acc >> 12) + 1549 * s2 + 406 * s1;
+    const int64_t n2 = acc & 255;
+    *seed = (n2 << 24) | (n1 << 12) | n0;
+    return 0.00390625 * ((double)n2 + 0.000244140625 * ((double)n1 + 0.000244140625 * (double)n0));
+}
+
+// _pllMakeParsimonyTreeFast (sprparsimony.cpp:3107-3209), stepwise phase on the device:
+// for each new taxon every branch of the partial tree is scored in one launch (k_tip_insert),
+// the host walks stepwiseAddition's DFS (:2977-3019, recursion below q only while the subtree
+// behind q has a positive length) over those numbers with the reference's tie-break draws.
+static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *rng_user, uint32_t *best_out, int64_t *scored)
+{
+    const int n = c->n;
+    HostTree &t = c->tree;
+    t.n = n;
+    t.bn.assign(3 * (2 * n - 1), 0); t.bs.assign(3 * (2 * n - 1), 0);
+    std::vector<int> perm(n + 2);
+    for (int i = 1; i <= n; i++) perm[i] = i;                                   // makePermutationFast :2221
+    for (int i = 1; i <= n; i++) {
+        const int k = (int)((double)(n + 1 - i) * pll_randum(seed));
+        std::swap(perm[i], perm[i + k]);
+    }
+    int nextnode = n + 1;
+    // buildSimpleTree :1968: tips ip, iq joined, the first inner node hangs ir and is inserted between them
+    const int ip = perm[1], iq = perm[2], ir = perm[3];
+    const int f = 3 * std::min(ip, std::min(iq, ir));                            // tr->start
+    {
+        const int s = 3 * nextnode++;
+        t.hookup(3 * ir, s);
+        t.hookup(s + 1, 3 * ip);
+        t.hookup(s + 2, 3 * iq);
+    }
+    c->tree_set = true; c->lens_valid = false;
+    if (int rc = compute_views(c)) return rc;
+    if (!c->reduces()) { set_error("stepwise addition on a sharded context needs mpgpu_set_allreduce"); return 1; }
+    compute_lengths(c);
+    uint32_t treelen = 0;
+    {
+        uint32_t mis = 0;
+        MPGPU_CUDA(cudaMemsetAsync(c->d_scalar, 0, sizeof(uint32_t), c->stream));
+        if (int rc = launch_edge_mismatch(c, t.vid(f), t.vid(t.back(f)), c->d_scalar)) return rc;
+        if (int rc = shard_sum(c, c->d_scalar, 1)) return rc;
+        MPGPU_CUDA(cudaMemcpyAsync(&mis, c->d_scalar, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        treelen = mis + c->vlen[t.vid(f)] + c->vlen[t.vid(t.back(f))];
+    }
+    std::vector<int4> edges;
+    std::vector<int32_t> edge_of_ref(3 * (2 * n - 1)), ins;
+    std::vector<int> stack;
+    int4 *d_edges = nullptr; size_t edges_cap = 0;
+    int32_t *d_ins = nullptr; size_t ins_cap = 0;
+    unsigned long hits = 1;
+    uint32_t best = treelen;
+    int rc = 0;
+    for (int ntips = 4; ntips <= n && !rc; ntips++) {
+        const int p = 3 * perm[ntips];                                           // the new tip
+        const int q = 3 * nextnode++;                                            // its inner node, slot 0 on the tip
+        // every branch of the current tree, keyed by the ref on the far side from tr->start
+        edges.clear(); stack.clear();
+        stack.push_back(t.back(f));
+        while (!stack.empty()) {
+            const int x = stack.back(); stack.pop_back();
+            edge_of_ref[x] = (int)edges.size();
+            edges.push_back(make_int4(t.vid(x), t.vid(t.back(x)), t.vid(p), 0));
+            if (!t.is_tip(x)) { stack.push_back(t.back(t.next(t.next(x)))); stack.push_back(t.back(t.next(x))); }
+        }
+        const int ne = (int)edges.size();
+        if ((rc = ensure(d_edges, edges_cap, (size_t)ne))) break;
+        if ((rc = ensure(d_ins, ins_cap, (size_t)ne))) break;
+        ins.resize(ne);
+        cudaError_t e = cudaMemcpyAsync(d_edges, edges.data(), (size_t)ne * sizeof(int4), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_ins, 0, (size_t)ne * 4, c->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "stepwise addition upload"); break; }
+        if ((rc = launch_tip_insert(c, d_edges, ne, d_ins))) break;
+        if ((rc = shard_sum(c, d_ins, ne))) break;
+        e = cudaMemcpyAsync(ins.data(), d_ins, (size_t)ne * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "stepwise addition read-back"); break; }
+        // stepwiseAddition(tr, pr, q, f->back): pre-order, children only below a subtree of positive length
+        best = 2147483647u;                                                       // tr->bestParsimony = INT_MAX :3141
+        int insert_ref = 0;
+        stack.clear(); stack.push_back(t.back(f));
+        while (!stack.empty()) {
+            const int x = stack.back(); stack.pop_back();
+            const uint32_t mp = treelen + (uint32_t)ins[edge_of_ref[x]];
+            (*scored)++;
+            if (mp < best) hits = 1;
+            else if (mp == best) hits++;
+            if (mp < best || (mp == best && rng(rng_user) <= 1.0 / hits)) { best = mp; insert_ref = x; }
+            if (!t.is_tip(x) && c->vlen[t.vid(x)] > 0) {                          // :3014
+                stack.push_back(t.back(t.next(t.next(x))));
+                stack.push_back(t.back(t.next(x)));
+            }
+        }
+        const int r = t.back(insert_ref);                                         // :3156-3162
+        t.hookup(p, q);
+        t.hookup(q + 1, insert_ref);
+        t.hookup(q + 2, r);
+        treelen = best;
+        c->lens_valid = false;
+        if ((rc = compute_views(c))) break;
+        compute_lengths(c);
+    }
+    if (d_edges) cudaFree(d_edges);
+    if (d_ins) cudaFree(d_ins);
+    *best_out = best;
+    return rc;
+}
+
 extern "C" {
+
+int mpgpu_stepwise_addition(mpgpu_ctx *c, int64_t *random_seed, int spr_dist, mpgpu_rng_fn rng, void *rng_user,
+                            int32_t *back_node, int32_t *back_slot, uint32_t *best, int64_t *n_insertions)
+{
+    if (!c || !random_seed || !rng || !back_node || !back_slot || !best) { set_error("null argument"); return 1; }
+    if (!c->d_views) { set_error("no alignment loaded"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    int64_t scored = 0;
+    uint32_t b0 = 0;
+    if (int rc = stepwise_phase(c, random_seed, rng, rng_user, &b0, &scored)) { c->tree_set = false; return rc; }
+    memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
+    memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
+    int64_t more = 0;
+    if (int rc = optimize_impl(c, back_node, back_slot, 1, spr_dist, rng, rng_user, nullptr, best, &more)) return rc;
+    if (n_insertions) *n_insertions = scored + more;
+    return 0;
+}
 
 int mpgpu_optimize_spr(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                        mpgpu_rng_fn rng, void *rng_user, uint32_t *best, int64_t *n_insertions)

@@ -222,6 +222,7 @@ int launch_level(Ctx *c, const Triple *d_triples, int ntriples);
 int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out);
 int launch_scan(Ctx *c, int ntasks, int nslots);
 int launch_scan_rows(Ctx *c, int ntasks, int nslots);
+int launch_tip_insert(Ctx *c, const int4 *d_edges, int nedges, int32_t *d_out);
 int launch_site_counters(Ctx *c, int npairs, int nbits);
 int launch_gather_patterns(Ctx *c, int nbits, int count);
 const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);

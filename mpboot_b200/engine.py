@@ -59,6 +59,7 @@ def lib():
     L.mpgpu_scan_plan_bytes.argtypes = [vp]
     L.mpgpu_scan_finish.argtypes = [vp, vp, vp, vp, vp, i32]
     L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.mpgpu_stepwise_addition.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.mpgpu_load_replicates.argtypes = [vp, i32, vp, i32, vp, i32]
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
     L.mpgpu_reps_timing.argtypes = [vp, vp, vp, vp, vp]
@@ -298,6 +299,17 @@ class Engine:
                                            C.c_void_p(rng_fn_ptr), C.c_void_p(rng_user) if rng_user else None,
                                            C.byref(best), C.byref(nins)))
         return best.value, bn, bs, nins.value
+
+    # -- R7
+    def stepwise_addition(self, seed, spr_dist, rng_fn_ptr, rng_user=None):
+        """_pllComputeRandomizedStepwiseAdditionParsimonyTree.  Returns (bestParsimony, back_node,
+        back_slot, insertions scored, updated seed)."""
+        bn = np.zeros(3 * (2 * self.n - 1), dtype=np.int32); bs = np.zeros_like(bn)
+        sd = C.c_int64(seed); best = C.c_uint32(); nins = C.c_int64()
+        self._ck(self.L.mpgpu_stepwise_addition(self.h, C.byref(sd), spr_dist, C.c_void_p(rng_fn_ptr),
+                                                C.c_void_p(rng_user) if rng_user else None, _p(bn), _p(bs),
+                                                C.byref(best), C.byref(nins)))
+        return best.value, bn, bs, nins.value, sd.value
 
     # -- R8 / -bb
     def set_option(self, name, value):

@@ -166,3 +166,34 @@ def test_full_size_properties_c2_slice():
     for i in (2, 250, 397):
         o2.record(False); o2.rearrange(i, 1, 6, True, s2)
         assert np.array_equal(o2.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32))
+
+
+@pytest.mark.parametrize("path", CASE_FILES, ids=IDS)
+def test_golden_stepwise_addition(path):
+    """R7: _pllComputeRandomizedStepwiseAdditionParsimonyTree -- same taxon order (PLL's randum), same
+    insertion branches, same tie-break draws, same SPR rounds, same tree in the reference's numbering."""
+    g = dict(np.load(path))
+    dt, mt = int(g["datatype"]), int(g["maxtrav"])
+    eng = _engine(g["codes"], g["weights"], dt)
+    portlib.seed_rng(77)
+    ret, bn, bs, nins, seed_after = eng.stepwise_addition(int(g["ras_seed"]), mt, portlib.rng_fn_address())
+    assert ret == int(g["ras_ret"]) and portlib.rng_draws() == int(g["ras_draws"])
+    assert np.array_equal(bn[3:], g["ras_bn"][3:]) and np.array_equal(bs[3:], g["ras_bs"][3:])
+    eng.set_tree(bn, bs)
+    assert eng.tree_score() == ret and nins > 0
+
+
+@pytest.mark.parametrize("n,L,dt,seed", [(50, 3000, 1, 71), (30, 600, 2, 72), (18, 400, 6, 73), (5, 200, 1, 74), (4, 100, 1, 75)])
+def test_stepwise_addition_matches_oracle(n, L, dt, seed):
+    c = make_case(n, L, dt, seed)
+    o = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    for ras_seed in (12345, 987):
+        portlib.seed_rng(5)
+        want = o.ras(ras_seed, 6)
+        draws = portlib.rng_draws()
+        wbn, wbs = o.get_ring()
+        eng = _engine(c["codes"], c["weights"], dt)
+        portlib.seed_rng(5)
+        ret, bn, bs, nins, _ = eng.stepwise_addition(ras_seed, 6, portlib.rng_fn_address())
+        assert ret == want and portlib.rng_draws() == draws
+        assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])

@@ -99,6 +99,7 @@ def one_case(name, n, L, dt, seed, maxtrav):
     ref.boot_free()
     # randomized stepwise addition
     reflib.lib().mpref_seed_rng(77)
+    g["ras_seed"] = 4242 + seed
     g["ras_ret"] = ref.ras(4242 + seed, maxtrav)
     g["ras_draws"] = reflib.lib().mpref_rng_draws()
     bn, bs = ref.get_ring()
