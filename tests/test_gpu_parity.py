@@ -197,3 +197,27 @@ def test_stepwise_addition_matches_oracle(n, L, dt, seed):
         ret, bn, bs, nins, _ = eng.stepwise_addition(ras_seed, 6, portlib.rng_fn_address())
         assert ret == want and portlib.rng_draws() == draws
         assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+
+
+def test_replicate_reweighting_search_matches_oracle():
+    """R12 building block (IQTree::optimizeBootTrees, iqtree.cpp:2475-2915): a bootstrap replicate is the
+    same resident codes under new pattern frequencies -- mpgpu_set_weights + mpgpu_optimize_spr must
+    give what the reference gets after re-creating its data structures for the re-weighted alignment
+    (zero-weight patterns included)."""
+    c = make_case(36, 2500, 1, 81)
+    eng = _engine(c["codes"], c["weights"], 1)
+    o = portlib.OracleEngine(c["codes"], c["weights"], 1)
+    rng = np.random.default_rng(8)
+    L = int(c["weights"].sum())
+    for rep in range(3):
+        w = rng.multinomial(L, c["weights"] / L).astype(np.int32)
+        o.set_weights(w); o.set_ring(c["bn"], c["bs"]); o.allocate(False)
+        portlib.seed_rng(100 + rep)
+        want = o.optimize_spr(1, 6, bb=False)
+        draws = portlib.rng_draws()
+        wring = o.get_ring()
+        eng.set_weights(w)
+        portlib.seed_rng(100 + rep)
+        ret, bn, bs, nins = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, 6)
+        assert ret == want and portlib.rng_draws() == draws
+        assert np.array_equal(bn[3:], wring[0][3:]) and np.array_equal(bs[3:], wring[1][3:])
