@@ -390,7 +390,7 @@ def run_ours(args):
     def step_device():
         ptr = eng.scan_launch()
         if world > 1:
-            t = torch.as_tensor(DevCounts(ptr, n_cand + n_tasks), device="cuda")
+            t = torch.as_tensor(DevCounts(ptr, n_cand + 2 * nvis), device="cuda")
             dist.all_reduce(t)
 
     def barrier():
@@ -416,7 +416,7 @@ def run_ours(args):
         ptr = eng.scan_launch()
         kev[k][1].record()
         if world > 1:
-            t = torch.as_tensor(DevCounts(ptr, n_cand + n_tasks), device="cuda")
+            t = torch.as_tensor(DevCounts(ptr, n_cand + 2 * nvis), device="cuda")
             dist.all_reduce(t)
         ev[k][1].record()
     barrier()
@@ -443,7 +443,7 @@ def run_ours(args):
         else:
             eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
             ptr = eng.scan_launch()
-            t = torch.as_tensor(DevCounts(ptr, n_cand + n_tasks), device="cuda")
+            t = torch.as_tensor(DevCounts(ptr, n_cand + 2 * nvis), device="cuda")
             dist.all_reduce(t)
             vb2, mp2, _, _ = eng.scan_finish(n_cand, nvis)
     barrier()
@@ -477,7 +477,7 @@ def run_ours(args):
                          "traffic": None, "kernel": "k_spr_scan", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker_s * 1e3},
             "e2e": {"value": (n_cand / e2e_s) * ops_per_ins, "unit": UNIT, "insertions_per_s": n_cand / e2e_s,
-                    "h2d_bytes_per_step": None, "d2h_bytes_per_step": 4 * (n_cand + n_tasks), "ms_per_step": e2e_s * 1e3},
+                    "h2d_bytes_per_step": None, "d2h_bytes_per_step": 4 * (n_cand + 2 * nvis), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
         }
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())

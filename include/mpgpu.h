@@ -132,14 +132,16 @@ int mpgpu_scan_visits(mpgpu_ctx *ctx, const int32_t *order, int first, int count
                       int mintrav, int maxtrav,
                       int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune,
                       int capacity, int *n_cand);
-/* Sharded form: plan on the host (identical on every rank), count on the device, finish
- * after the all-reduce.  counts has n_cand + n_tasks entries (mpgpu_scan_plan returns both). */
+/* Split form: plan on the host (identical on every rank), count on the device, finish after the
+ * caller's all-reduce.  The device count vector has 2*count + n_cand int32 entries (one slot per
+ * possible prune task of the planned visits, then one per candidate); n_tasks returns the tasks
+ * actually planned. */
 int mpgpu_scan_plan(mpgpu_ctx *ctx, const int32_t *order, int first, int count, int mintrav, int maxtrav,
                     int *n_cand, int *n_tasks);
 /* Bytes of scan program (ops + tasks) the last mpgpu_scan_plan uploaded host->device. */
 int64_t mpgpu_scan_plan_bytes(mpgpu_ctx *ctx);
 /* Launches the scan of the planned batch; the int32 partial counts stay on the device at
- * *dev_counts (n_cand+n_tasks entries) for an in-place NCCL all-reduce.  Asynchronous. */
+ * *dev_counts (2*count + n_cand entries) for an in-place NCCL all-reduce.  Asynchronous. */
 int mpgpu_scan_launch(mpgpu_ctx *ctx, void **dev_counts);
 int mpgpu_scan_finish(mpgpu_ctx *ctx, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref,
                       int32_t *cand_prune, int capacity);

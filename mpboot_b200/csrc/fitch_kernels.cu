@@ -431,7 +431,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
                            const ScanTask *__restrict__ tasks, int ntasks,
                            const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
                            int nslots, int32_t *__restrict__ out,
-                           const int32_t *__restrict__ task_ids, const int32_t *__restrict__ row_of,
+                           const int32_t *__restrict__ task_ids, const int32_t *__restrict__ row_of, int row_bias,
                            uint32_t *__restrict__ rows)
 {
     typedef typename VecOf<S>::T V;
@@ -456,7 +456,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     pin(sstack);
     const bool lane0 = lane == 0;
     int32_t *outc = out + t1.z;                                              // candidates of this task
-    const int32_t *rowc = ROWS ? row_of + t1.z : nullptr;
+    const int32_t *rowc = ROWS ? row_of + (t1.z - row_bias) : nullptr;   // cand_base counts from the base slots
     uint32_t *rowbase = ROWS ? rows + (size_t)chunk * kChunkWords + lane : nullptr;
 
     uint32_t Sv[S];
@@ -522,7 +522,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
 }
 
 template <int S, bool ROWS>
-static int launch_scan_t(Ctx *c, int ntasks, int nslots)
+static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
 {
     typedef typename VecOf<S>::T V;
     constexpr bool PF = S <= 4;
@@ -542,22 +542,23 @@ static int launch_scan_t(Ctx *c, int ntasks, int nslots)
     const long long blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
     k_spr_scan<S, PF, ROWS><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
-        reinterpret_cast<const V *>(c->d_views), c->Wl, c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs),
+        reinterpret_cast<const V *>(c->d_views), c->Wl, c->d_tasks + (ROWS ? 0 : task0), ntasks, reinterpret_cast<const int2 *>(c->d_offs),
         reinterpret_cast<const int2 *>(c->d_ctl), nslots > 0 ? nslots : 1, c->d_counts,
-        ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, ROWS ? c->d_rows_site : nullptr);
+        ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, c->plan.task_cap, ROWS ? c->d_rows_site : nullptr);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_scan(Ctx *c, int ntasks, int nslots)
+// tasks [task0, task0 + ntasks) of the uploaded plan
+int launch_scan(Ctx *c, int task0, int ntasks, int nslots)
 {
     if (ntasks == 0) return 0;
     switch (c->S) {
-    case 2:  return launch_scan_t<2, false>(c, ntasks, nslots);
-    case 4:  return launch_scan_t<4, false>(c, ntasks, nslots);
-    case 20: return launch_scan_t<20, false>(c, ntasks, nslots);
-    case 32: return launch_scan_t<32, false>(c, ntasks, nslots);
+    case 2:  return launch_scan_t<2, false>(c, task0, ntasks, nslots);
+    case 4:  return launch_scan_t<4, false>(c, task0, ntasks, nslots);
+    case 20: return launch_scan_t<20, false>(c, task0, ntasks, nslots);
+    case 32: return launch_scan_t<32, false>(c, task0, ntasks, nslots);
     default: set_error("unsupported state count"); return 1;
     }
 }
@@ -567,10 +568,10 @@ int launch_scan_rows(Ctx *c, int ntasks, int nslots)
 {
     if (ntasks == 0) return 0;
     switch (c->S) {
-    case 2:  return launch_scan_t<2, true>(c, ntasks, nslots);
-    case 4:  return launch_scan_t<4, true>(c, ntasks, nslots);
-    case 20: return launch_scan_t<20, true>(c, ntasks, nslots);
-    case 32: return launch_scan_t<32, true>(c, ntasks, nslots);
+    case 2:  return launch_scan_t<2, true>(c, 0, ntasks, nslots);
+    case 4:  return launch_scan_t<4, true>(c, 0, ntasks, nslots);
+    case 20: return launch_scan_t<20, true>(c, 0, ntasks, nslots);
+    case 32: return launch_scan_t<32, true>(c, 0, ntasks, nslots);
     default: set_error("unsupported state count"); return 1;
     }
 }

@@ -195,28 +195,46 @@ int need_tree(Ctx *c, bool lens)
     return 0;
 }
 
-int upload_plan(Ctx *c)
+// device copies of the plan ranges [ops0, n_ops) and [task0, ntasks): the whole plan, or one more piece
+static int upload_plan_range(Ctx *c, int ops0, int task0)
+{
+    ScanPlan &pl = c->plan;
+    const int nops = pl.n_ops - ops0, nt = (int)pl.tasks.size() - task0;
+    if (nops > 0) {
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_offs + ops0, pl.offs.data() + ops0, (size_t)nops * sizeof(ScanOffs), cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_ctl + ops0, pl.ctl.data() + ops0, (size_t)nops * sizeof(ScanCtl), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (nt > 0) {
+        memcpy(pl.tasks_pin.data() + task0, pl.tasks.data() + task0, (size_t)nt * sizeof(ScanTask));
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_tasks + task0, pl.tasks_pin.data() + task0, (size_t)nt * sizeof(ScanTask), cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+// device buffers for a plan whose arrays were sized by ScanPlanner::begin (upper bounds)
+static int reserve_plan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
     if (int rc = ensure(c->d_offs, c->offs_cap, pl.offs.size() + 1)) return rc;
     if (int rc = ensure(c->d_ctl, c->ctl_cap, pl.ctl.size() + 1)) return rc;
-    if (int rc = ensure(c->d_tasks, c->tasks_cap, pl.tasks.size() + 1)) return rc;
-    if (int rc = ensure(c->d_counts, c->counts_cap, (size_t)pl.n_cand + pl.tasks.size() + 1)) return rc;
-    if (!pl.offs.empty()) {
-        MPGPU_CUDA(cudaMemcpyAsync(c->d_offs, pl.offs.data(), pl.offs.size() * sizeof(ScanOffs), cudaMemcpyHostToDevice, c->stream));
-        MPGPU_CUDA(cudaMemcpyAsync(c->d_ctl, pl.ctl.data(), pl.ctl.size() * sizeof(ScanCtl), cudaMemcpyHostToDevice, c->stream));
-    }
-    if (!pl.tasks.empty())
-        MPGPU_CUDA(cudaMemcpyAsync(c->d_tasks, pl.tasks.data(), pl.tasks.size() * sizeof(ScanTask), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = ensure(c->d_tasks, c->tasks_cap, (size_t)pl.task_cap + 1)) return rc;
+    if (int rc = ensure(c->d_counts, c->counts_cap, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     return 0;
 }
 
+int upload_plan(Ctx *c)
+{
+    if (int rc = reserve_plan(c)) return rc;
+    return upload_plan_range(c, 0, 0);
+}
+
+// counts layout: [0, task_cap) joined-edge counts per task slot, then one count per candidate
 int run_scan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
-    const size_t nout = (size_t)pl.n_cand + pl.tasks.size();
+    const size_t nout = (size_t)pl.task_cap + pl.n_cand;
     MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, (nout + 1) * sizeof(int32_t), c->stream));
-    if (int rc = launch_scan(c, (int)pl.tasks.size(), pl.max_slot)) return rc;
+    if (int rc = launch_scan(c, 0, (int)pl.tasks.size(), pl.max_slot)) return rc;
     if (c->shard_count > 1 && c->allreduce) return shard_sum(c, c->d_counts, (int64_t)nout);
     return 0;
 }
@@ -225,13 +243,22 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
 {
     ScanPlan &pl = c->plan;
     if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
-    const size_t nout = (size_t)pl.n_cand + pl.tasks.size();
-    c->h_counts.resize(nout + 1);
-    MPGPU_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->d_counts, nout * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    const size_t nout = (size_t)pl.task_cap + pl.n_cand;
+    if (nout * sizeof(int32_t) > c->h_counts_cap) {
+        if (c->h_counts) cudaFreeHost(c->h_counts);
+        c->h_counts = nullptr; c->h_counts_cap = 0;
+        const size_t want = (nout + nout / 2 + 1024) * sizeof(int32_t);
+        MPGPU_CUDA(cudaHostAlloc((void **)&c->h_counts, want, cudaHostAllocDefault));        // pinned: the read-back is on the e2e path
+        c->h_counts_cap = want;
+    }
+    MPGPU_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counts, nout * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    const int32_t *base = c->h_counts, *cnt = c->h_counts + pl.task_cap;
+    const int32_t *ctask = pl.cand_task.data();
+    const uint32_t *tconst = pl.task_const.data();
     for (int j = 0; j < pl.n_cand; j++) {
-        const int ti = pl.cand_task[j];
-        mp[j] = pl.task_const[ti] + (uint32_t)c->h_counts[pl.n_cand + ti] + (uint32_t)c->h_counts[j];
+        const int ti = ctask[j];
+        mp[j] = tconst[ti] + (uint32_t)base[ti] + (uint32_t)cnt[j];
     }
     if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
     if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
@@ -239,6 +266,33 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
     return 0;
 }
 
+// Plan, upload and launch a batch of visits in pieces: while the device scores the first visits
+// the host enumerates the next ones (the enumeration is the largest host term of the e2e path).
+int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int mintrav, int maxtrav)
+{
+    ScanPlan &pl = c->plan;
+    const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
+    ScanPlanner planner;
+    if (int rc = planner.begin(c->tree, c->vlen, order, first, count, mintrav, maxtrav, vstride_vec, pl)) return rc;
+    if (int rc = reserve_plan(c)) return rc;
+    MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, ((size_t)pl.task_cap + pl.cand_ref.size() + 1) * sizeof(int32_t), c->stream));
+    int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep): 1: 0.338 ms, 2: 0.316 ms, 4: 0.337 ms, 6: 0.390 ms e2e
+    if (const char *e = getenv("MPGPU_SCAN_PIECES")) { int v = atoi(e); if (v >= 1) pieces = v; }
+    int v0 = 0;
+    for (int k = 0; k < pieces; k++) {
+        // early pieces are smaller: the device should get going as soon as possible
+        const int v1 = k == pieces - 1 ? count : std::min(count, v0 + std::max(1, (int)((long long)count * (k + 1) / (pieces * (pieces + 1) / 2))));
+        const int ops0 = pl.n_ops, task0 = (int)pl.tasks.size();
+        planner.add(v0, v1);
+        if (int rc = upload_plan_range(c, ops0, task0)) return rc;
+        if (int rc = launch_scan(c, task0, (int)pl.tasks.size() - task0, pl.max_slot)) return rc;
+        v0 = v1;
+        if (v0 >= count) break;
+    }
+    planner.finish();
+    if (c->shard_count > 1 && c->allreduce) return shard_sum(c, c->d_counts, (int64_t)pl.task_cap + pl.n_cand);
+    return 0;
+}
 
 // Per-site mismatch counters of the current tree, bit-sliced, in d_bitcnt[nbits][Wl]: child-view
 // pairs of the n-2 inner views facing tr->start, plus the start edge (storePerSiteNodeScores :294).
@@ -337,6 +391,7 @@ int mpgpu_destroy(mpgpu_ctx *c)
     if (c->d_ctl) cudaFree(c->d_ctl);
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_counts) cudaFree(c->d_counts);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->d_bitcnt) cudaFree(c->d_bitcnt);
     if (c->d_pairs) cudaFree(c->d_pairs);
     if (c->d_ptn) cudaFree(c->d_ptn);
@@ -575,7 +630,7 @@ int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, in
 int64_t mpgpu_scan_plan_bytes(mpgpu_ctx *c)
 {
     if (!c) return 0;
-    return (int64_t)(c->plan.offs.size() * (sizeof(ScanOffs) + sizeof(ScanCtl)) + c->plan.tasks.size() * sizeof(ScanTask));
+    return (int64_t)((size_t)c->plan.n_ops * (sizeof(ScanOffs) + sizeof(ScanCtl)) + c->plan.tasks.size() * sizeof(ScanTask));
 }
 
 int mpgpu_scan_launch(mpgpu_ctx *c, void **dev_counts)
@@ -600,12 +655,13 @@ int mpgpu_scan_visits(mpgpu_ctx *c, const int32_t *order, int first, int count, 
                       int capacity, int *n_cand)
 {
     if (c && !c->reduces()) { set_error("mpgpu_scan_visits on a sharded context needs mpgpu_set_allreduce (or use plan/launch/finish)"); return 1; }
-    int nc = 0, nt = 0;
-    if (int rc = mpgpu_scan_plan(c, order, first, count, mintrav, maxtrav, &nc, &nt)) return rc;
-    if (n_cand) *n_cand = nc;
-    if (nc > capacity) { set_error("candidate capacity too small"); return 1; }
-    if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
-    return mpgpu_scan_finish(c, visit_begin, mp, cand_ref, cand_prune, capacity);
+    if (int rc = need_tree(c, true)) return rc;
+    if (!order || !mp || first < 1 || count < 0 || first + count > 2 * c->n - 1) { set_error("bad visit range"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    if (int rc = scan_batch_pipelined(c, order, first, count, mintrav, maxtrav)) return rc;
+    if (n_cand) *n_cand = c->plan.n_cand;
+    if (c->plan.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
+    return finish_scan(c, visit_begin, mp, cand_ref, cand_prune, capacity);
 }
 
 }  // extern "C"

@@ -423,7 +423,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     std::vector<int32_t> thr;
     RepsOut ro;
     Prof prof;
-    static const char *const prof_names[] = {"plan+upload", "scan", "reps", "replay", "views", "moves"};
+    static const char *const prof_names[] = {"plan+launch", "scan wait", "reps", "replay", "views", "moves"};
     do {
         startMP = randomMP;
         visit_order(c->tree, order);                              // nodeRectifierPars :3297
@@ -431,13 +431,12 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
         int batch = 16;
         while (i <= nvisit) {
             int count = std::min(batch, nvisit - i + 1);
-            int nc = 0, nt = 0;
             prof.start();
-            if (int rc = mpgpu_scan_plan(c, order.data(), i, count, mintrav, maxtrav, &nc, &nt)) return rc;
+            if (int rc = scan_batch_pipelined(c, order.data(), i, count, mintrav, maxtrav)) return rc;
             prof.stop(0); prof.start();
+            const int nc = c->plan.n_cand;
             vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
-            if (int rc = mpgpu_scan_launch(c, nullptr)) return rc;
-            if (int rc = mpgpu_scan_finish(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
+            if (int rc = finish_scan(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
             prof.stop(1); prof.start();
             if (bb) {
                 // every saveCurrentTree call of the batch, in order; call_of[] = index into the REPS results

@@ -56,20 +56,44 @@ struct ScanTask {
     int32_t s_vid;      // pruned subtree (view offset in vector units)
     int32_t d1, d2;     // the two views that become neighbours when the node is removed (offsets)
     int32_t op_begin, op_end;
-    int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge)
-    int32_t cand_base;  // first candidate (output slot) of this task
+    int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge) = the task's index
+    int32_t cand_base;  // output slot of the task's first candidate = task_cap + its candidate index
     int32_t pad;
 };
 
+// Page-locked host array: the plan streams are uploaded piece by piece while the host keeps
+// appending, so the copies must be truly asynchronous (pageable memory is staged synchronously).
+template <typename T> struct PinnedArray {
+    T *p = nullptr; size_t cap = 0;
+    PinnedArray() {}
+    ~PinnedArray() { if (p) cudaFreeHost(p); }
+    size_t size() const { return cap; }
+    T *data() { return p; }
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+        cap = n;
+        return true;
+    }
+private:
+    PinnedArray(const PinnedArray &);
+    PinnedArray &operator=(const PinnedArray &);
+};
+
 struct ScanPlan {
-    std::vector<ScanOffs> offs;
-    std::vector<ScanCtl> ctl;
+    PinnedArray<ScanOffs> offs;
+    PinnedArray<ScanCtl> ctl;
+    PinnedArray<ScanTask> tasks_pin;      // upload copy of `tasks`
     std::vector<ScanTask> tasks;
     std::vector<int32_t> visit_begin;     // count+1
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
     std::vector<uint32_t> task_const;     // len(S)+len(D1)+len(D2) per task
-    int n_cand = 0;
+    int n_cand = 0;                      // candidates / ops actually used (the vectors are sized to an upper bound)
+    int n_ops = 0;
     int max_slot = 0;
+    int task_cap = 0;                    // base slots in front of the candidate counts (2 per planned visit)
 };
 
 // ---- replicate scoring state (R8; reps_kernels.cu, mpgpu_bb.cu) -------------------------------
@@ -171,7 +195,7 @@ struct Ctx {
     ScanCtl *d_ctl = nullptr; size_t ctl_cap = 0;
     ScanTask *d_tasks = nullptr; size_t tasks_cap = 0;
     int32_t *d_counts = nullptr; size_t counts_cap = 0;
-    std::vector<int32_t> h_counts;
+    int32_t *h_counts = nullptr; size_t h_counts_cap = 0;   // pinned read-back buffer (bytes)
 
     // pattern scores
     uint32_t *d_bitcnt = nullptr; size_t bitcnt_cap = 0;   // bit-sliced per-site counters
@@ -210,6 +234,7 @@ int compute_views(Ctx *c);
 void compute_lengths(Ctx *c);
 int need_tree(Ctx *c, bool lens);
 int run_scan(Ctx *c);
+int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int mintrav, int maxtrav);
 int upload_plan(Ctx *c);
 int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity);
 int compute_site_counters(Ctx *c, int nbits);       // bit-sliced per-site counters of the current tree -> d_bitcnt
@@ -220,7 +245,7 @@ void free_reps(Ctx *c);
 int launch_compress(Ctx *c);
 int launch_level(Ctx *c, const Triple *d_triples, int ntriples);
 int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out);
-int launch_scan(Ctx *c, int ntasks, int nslots);
+int launch_scan(Ctx *c, int task0, int ntasks, int nslots);
 int launch_scan_rows(Ctx *c, int ntasks, int nslots);
 int launch_tip_insert(Ctx *c, const int4 *d_edges, int nedges, int32_t *d_out);
 int launch_site_counters(Ctx *c, int npairs, int nbits);
@@ -242,6 +267,20 @@ int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, 
 
 // ---- host SPR logic (spr_host.cpp) ---------------------------------------------------------
 void visit_order(const HostTree &t, std::vector<int32_t> &order);
+class ScanPlanner {                      // incremental form of build_scan_plan (pieces of consecutive visits)
+public:
+    ScanPlanner();
+    ~ScanPlanner();
+    int begin(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order, int first, int count,
+              int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan);
+    void add(int v0, int v1);
+    void finish();
+private:
+    struct Impl;
+    Impl *impl;
+    ScanPlanner(const ScanPlanner &);
+    ScanPlanner &operator=(const ScanPlanner &);
+};
 int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
                     int first, int count, int mintrav, int maxtrav, uint32_t vstride_vec, ScanPlan &plan);
 void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);

@@ -8,6 +8,8 @@
 //   apply_spr_move     restoreTreeRearrangeParsimony         (sprparsimony.cpp:2379-2384, 2191-2205)
 #include "mpgpu_internal.h"
 
+#include <algorithm>
+
 namespace mpgpu {
 
 // tr->nodep[1..2n-2] after nodeRectifierPars: tips in number order, then the inner nodes in
@@ -32,34 +34,44 @@ void visit_order(const HostTree &t, std::vector<int32_t> &order)
 
 namespace {
 
+// Flat per-ref tables of the tree for the enumeration (built once per plan): the two refs
+// behind an inner ref, tip flags and view offsets, so that the hot recursion touches no
+// division and no ring arithmetic.
 struct Builder {
-    const HostTree &t;
+    const int n;
     ScanPlan &plan;
-    int prune_ref;
-    int task_index;
-    uint32_t vstride;                                               // view stride in vector units
-    Builder(const HostTree &tt, ScanPlan &pp, uint32_t vs) : t(tt), plan(pp), prune_ref(0), task_index(0), vstride(vs) {}
-    int32_t voff(int ref) const { return (int32_t)((uint32_t)t.vid(ref) * vstride); }
+    std::vector<int32_t> c1, c2, voff_;     // per ref: back(next(ref)), back(next(next(ref))), view offset
+    std::vector<uint8_t> tip;
+    int prune_ref = 0, task_index = 0, cand_base = 0;
+    // raw cursors into the plan's arrays (sized up front)
+    ScanOffs *offs = nullptr; ScanCtl *ctl = nullptr;
+    int32_t *cand_ref = nullptr, *cand_prune = nullptr, *cand_task = nullptr;
+    int nops = 0, ncand = 0, max_slot = 0;
 
-    int cand_base = 0;
+    Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride) : n(t.n), plan(pp)
+    {
+        const int nref = 3 * (2 * n - 1);
+        c1.assign(nref, 0); c2.assign(nref, 0); voff_.assign(nref, 0); tip.assign(nref, 1);
+        for (int node = 1; node <= 2 * n - 2; node++) {
+            const int ns = node <= n ? 1 : 3;
+            for (int sl = 0; sl < ns; sl++) {
+                const int r = 3 * node + sl;
+                voff_[r] = (int32_t)((uint32_t)t.vid(r) * vstride);
+                if (node > n) {
+                    tip[r] = 0;
+                    const int a = 3 * node + (sl + 1) % 3, b = 3 * node + (sl + 2) % 3;
+                    c1[r] = t.back(a); c2[r] = t.back(b);
+                }
+            }
+        }
+    }
+    int32_t voff(int ref) const { return voff_[ref]; }
 
-    int new_op(uint32_t src, int c1, int c2)
+    int new_op(uint32_t src, int a, int b)
     {
-        ScanOffs o; o.c1 = voff(c1); o.c2 = voff(c2);
-        ScanCtl c; c.outs = 0xFFFFFFFFu; c.meta = src | 0xFF00u | 0xFF0000u;
-        plan.offs.push_back(o); plan.ctl.push_back(c);
-        return (int)plan.offs.size() - 1;
-    }
-    void set_out(int op, int which, int idx)
-    {
-        const uint32_t rel = (uint32_t)(idx - cand_base);
-        uint32_t &w = plan.ctl[op].outs;
-        w = which == 0 ? ((w & 0xFFFF0000u) | rel) : ((w & 0x0000FFFFu) | (rel << 16));
-    }
-    void set_dst(int op, int which, int slot)
-    {
-        uint32_t &w = plan.ctl[op].meta;
-        w = which == 0 ? ((w & ~0xFF00u) | ((uint32_t)slot << 8)) : ((w & ~0xFF0000u) | ((uint32_t)slot << 16));
+        offs[nops].c1 = voff_[a]; offs[nops].c2 = voff_[b];
+        ctl[nops].outs = 0xFFFFFFFFu; ctl[nops].meta = src | 0xFF00u | 0xFF0000u;
+        return nops++;
     }
 
     // addTraverseParsimony(tr, pr, p, q, mintrav, maxtrav, doAll = FALSE) for q = x.
@@ -67,20 +79,21 @@ struct Builder {
     void traverse(int x, int mintrav, int maxtrav, int parent_op, int which, int depth)
     {
         if (--mintrav <= 0) {                                   // testInsertParsimony(p, x)
-            int idx = plan.n_cand++;
-            plan.cand_ref.push_back(x);
-            plan.cand_prune.push_back(prune_ref);
-            plan.cand_task.push_back(task_index);
-            set_out(parent_op, which, idx);
+            const int idx = ncand++;
+            cand_ref[idx] = x; cand_prune[idx] = prune_ref; cand_task[idx] = task_index;
+            const uint32_t rel = (uint32_t)(idx - cand_base);
+            uint32_t &w = ctl[parent_op].outs;
+            w = which == 0 ? ((w & 0xFFFF0000u) | rel) : ((w & 0x0000FFFFu) | (rel << 16));
         }
-        if (!t.is_tip(x) && (--maxtrav > 0)) {
+        if (!tip[x] && (--maxtrav > 0)) {
             const int slot = 2 * (depth - 1) + which;           // U_x goes here
-            set_dst(parent_op, which, slot);
-            if (slot + 1 > plan.max_slot) plan.max_slot = slot + 1;
-            const int c1 = t.back(t.next(x)), c2 = t.back(t.next(t.next(x)));
-            const int me = new_op((uint32_t)slot, c1, c2);
-            traverse(c1, mintrav, maxtrav, me, 0, depth + 1);
-            traverse(c2, mintrav, maxtrav, me, 1, depth + 1);
+            uint32_t &w = ctl[parent_op].meta;
+            w = which == 0 ? ((w & ~0xFF00u) | ((uint32_t)slot << 8)) : ((w & ~0xFF0000u) | ((uint32_t)slot << 16));
+            if (slot + 1 > max_slot) max_slot = slot + 1;
+            const int a = c1[x], b = c2[x];
+            const int me = new_op((uint32_t)slot, a, b);
+            traverse(a, mintrav, maxtrav, me, 0, depth + 1);
+            traverse(b, mintrav, maxtrav, me, 1, depth + 1);
         }
     }
 
@@ -89,71 +102,124 @@ struct Builder {
     // is the D1 neighbour, src code 0xFF) or D1 (src code 0xFE).
     void expand_top(int nb, uint32_t src_code, int mintrav, int maxtrav)
     {
-        const int c1 = t.back(t.next(nb)), c2 = t.back(t.next(t.next(nb)));
-        const int me = new_op(src_code, c1, c2);
-        traverse(c1, mintrav, maxtrav, me, 0, 1);
-        traverse(c2, mintrav, maxtrav, me, 1, 1);
+        const int a = c1[nb], b = c2[nb];
+        const int me = new_op(src_code, a, b);
+        traverse(a, mintrav, maxtrav, me, 0, 1);
+        traverse(b, mintrav, maxtrav, me, 1, 1);
     }
 };
 
 }  // namespace
 
 // Enumerates what rearrangeParsimony(tr, pr, tr->nodep[i], mintrav, maxtrav, doAll=FALSE) tests
-// for i in [first, first+count).  Returns 0, or 1 if maxtrav exceeds the kernel's stack.
-int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
-                    int first, int count, int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan)
+// for i in [first, first+count).  The plan can be built in pieces (scan_plan_begin, then
+// scan_plan_add for consecutive visit ranges) so that the device can start on the first piece
+// while the host enumerates the next.  Output layout of the device count vector: slots
+// [0, task_cap) hold the joined-edge count of each task, candidate j sits at task_cap + j.
+struct ScanPlanner::Impl {
+    Builder b;
+    const HostTree &t;
+    const std::vector<uint32_t> &vlen;
+    const int32_t *order;
+    int first, mintrav, maxtrav;
+    Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const std::vector<uint32_t> &vl, const int32_t *ord,
+         int f, int mi, int ma) : b(tt, plan, vstride), t(tt), vlen(vl), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
+};
+
+ScanPlanner::ScanPlanner() : impl(nullptr) {}
+ScanPlanner::~ScanPlanner() { delete impl; }
+
+int ScanPlanner::begin(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order, int first, int count,
+                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan)
 {
-    plan.offs.clear(); plan.ctl.clear(); plan.tasks.clear(); plan.visit_begin.clear();
-    plan.cand_ref.clear(); plan.cand_prune.clear(); plan.cand_task.clear(); plan.task_const.clear();
-    plan.n_cand = 0; plan.max_slot = 0;
+    delete impl; impl = nullptr;
+    plan.tasks.clear(); plan.visit_begin.clear(); plan.task_const.clear();
+    plan.n_cand = 0; plan.n_ops = 0; plan.max_slot = 0;
+    plan.task_cap = 2 * count;
     const int n = t.n;
     int maxtrav = maxtrav_in;
     if (maxtrav > n - 3) maxtrav = n - 3;                       // :2275 (tr->ntips == mxtips during the search)
     if (maxtrav > kMaxTrav) { set_error("maxtrav exceeds the scan kernel's stack depth"); return 1; }   // slots < 0xFE
     if ((uint64_t)(4 * n - 6) * vstride >= 0x7fffffffULL) { set_error("view array too large for 32-bit scan offsets"); return 1; }
-    Builder b(t, plan, vstride);
+    impl = new Impl(t, plan, vstride, vlen, order, first, mintrav, maxtrav);
+    Builder &b = impl->b;
+    // upper bounds: one side of a visit reaches at most 4 * (2^maxtrav - 1) branches, never more than the tree has
+    const size_t per_side = std::min<size_t>((size_t)4 << std::max(maxtrav, 0), (size_t)2 * n);
+    const size_t cap = (size_t)count * 2 * per_side + 16;
+    if (!plan.offs.reserve(cap + cap / 4) || !plan.ctl.reserve(cap + cap / 4) || !plan.tasks_pin.reserve((size_t)plan.task_cap + 16)) {
+        set_error("page-locked host allocation for the scan plan failed"); return 1;
+    }
+    if (plan.cand_ref.size() < cap) { plan.cand_ref.resize(cap); plan.cand_prune.resize(cap); plan.cand_task.resize(cap); }
+    b.offs = plan.offs.data(); b.ctl = plan.ctl.data();
+    b.cand_ref = plan.cand_ref.data(); b.cand_prune = plan.cand_prune.data(); b.cand_task = plan.cand_task.data();
+    plan.tasks.reserve((size_t)plan.task_cap);
+    return 0;
+}
 
-    for (int v = 0; v < count; v++) {
-        plan.visit_begin.push_back(plan.n_cand);
+// visits [v0, v1) relative to `first`; must be called with consecutive ranges
+void ScanPlanner::add(int v0, int v1)
+{
+    Builder &b = impl->b;
+    ScanPlan &plan = b.plan;
+    const HostTree &t = impl->t;
+    const std::vector<uint32_t> &vlen = impl->vlen;
+    const int mintrav = impl->mintrav, maxtrav = impl->maxtrav;
+    for (int v = v0; v < v1; v++) {
+        plan.visit_begin.push_back(b.ncand);
         if (maxtrav < mintrav) continue;                        // :2280
-        const int p = order[first + v];
+        const int p = impl->order[impl->first + v];
         const int q = t.back(p);
 
-        if (!t.is_tip(p)) {                                     // :2303
-            const int p1 = t.back(t.next(p)), p2 = t.back(t.next(t.next(p)));
-            if (!t.is_tip(p1) || !t.is_tip(p2)) {
+        if (!b.tip[p]) {                                        // :2303
+            const int p1 = b.c1[p], p2 = b.c2[p];
+            if (!b.tip[p1] || !b.tip[p2]) {
                 ScanTask task;
                 task.s_vid = b.voff(q); task.d1 = b.voff(p1); task.d2 = b.voff(p2);
-                task.op_begin = (int)plan.offs.size(); task.base_out = 0; task.cand_base = plan.n_cand; task.pad = 0; b.cand_base = plan.n_cand;
+                task.op_begin = b.nops; task.base_out = (int)plan.tasks.size(); task.cand_base = plan.task_cap + b.ncand; task.pad = 0;
+                b.cand_base = b.ncand;
                 b.prune_ref = p; b.task_index = (int)plan.tasks.size();
-                if (!t.is_tip(p1)) b.expand_top(p1, 0xFFu, mintrav, maxtrav);
-                if (!t.is_tip(p2)) b.expand_top(p2, 0xFEu, mintrav, maxtrav);
-                task.op_end = (int)plan.offs.size();
+                if (!b.tip[p1]) b.expand_top(p1, 0xFFu, mintrav, maxtrav);
+                if (!b.tip[p2]) b.expand_top(p2, 0xFEu, mintrav, maxtrav);
+                task.op_end = b.nops;
                 plan.tasks.push_back(task);
                 plan.task_const.push_back(vlen[t.vid(q)] + vlen[t.vid(p1)] + vlen[t.vid(p2)]);
             }
         }
-        if (!t.is_tip(q) && maxtrav > 0) {                      // :2333
-            const int q1 = t.back(t.next(q)), q2 = t.back(t.next(t.next(q)));
-            const bool ok1 = !t.is_tip(q1) && (!t.is_tip(t.back(t.next(q1))) || !t.is_tip(t.back(t.next(t.next(q1)))));
-            const bool ok2 = !t.is_tip(q2) && (!t.is_tip(t.back(t.next(q2))) || !t.is_tip(t.back(t.next(t.next(q2)))));
+        if (!b.tip[q] && maxtrav > 0) {                         // :2333
+            const int q1 = b.c1[q], q2 = b.c2[q];
+            const bool ok1 = !b.tip[q1] && (!b.tip[b.c1[q1]] || !b.tip[b.c2[q1]]);
+            const bool ok2 = !b.tip[q2] && (!b.tip[b.c1[q2]] || !b.tip[b.c2[q2]]);
             if (ok1 || ok2) {
                 const int mintrav2 = mintrav > 2 ? mintrav : 2;
                 ScanTask task;
                 task.s_vid = b.voff(p); task.d1 = b.voff(q1); task.d2 = b.voff(q2);
-                task.op_begin = (int)plan.offs.size(); task.base_out = 0; task.cand_base = plan.n_cand; task.pad = 0; b.cand_base = plan.n_cand;
+                task.op_begin = b.nops; task.base_out = (int)plan.tasks.size(); task.cand_base = plan.task_cap + b.ncand; task.pad = 0;
+                b.cand_base = b.ncand;
                 b.prune_ref = q; b.task_index = (int)plan.tasks.size();
-                if (!t.is_tip(q1)) b.expand_top(q1, 0xFFu, mintrav2, maxtrav);
-                if (!t.is_tip(q2)) b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
-                task.op_end = (int)plan.offs.size();
+                if (!b.tip[q1]) b.expand_top(q1, 0xFFu, mintrav2, maxtrav);
+                if (!b.tip[q2]) b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
+                task.op_end = b.nops;
                 plan.tasks.push_back(task);
                 plan.task_const.push_back(vlen[t.vid(p)] + vlen[t.vid(q1)] + vlen[t.vid(q2)]);
             }
         }
     }
+    plan.n_cand = b.ncand; plan.n_ops = b.nops; plan.max_slot = b.max_slot;
+}
+
+void ScanPlanner::finish()
+{
+    ScanPlan &plan = impl->b.plan;
     plan.visit_begin.push_back(plan.n_cand);
-    // base counters live after the candidate counters in the device output vector
-    for (size_t i = 0; i < plan.tasks.size(); i++) plan.tasks[i].base_out = plan.n_cand + (int)i;
+}
+
+int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
+                    int first, int count, int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan)
+{
+    ScanPlanner pl;
+    if (int rc = pl.begin(t, vlen, order, first, count, mintrav, maxtrav, vstride, plan)) return rc;
+    pl.add(0, count);
+    pl.finish();
     return 0;
 }
 
