@@ -176,6 +176,12 @@ int mpgpu_stepwise_addition(mpgpu_ctx *ctx, int64_t *random_seed, int spr_dist, 
  * CUDA-core path (mpgpu_reps_info reports the split). */
 int mpgpu_load_replicates(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples, int stride,
                           const int32_t *segment_upper, int nseg);
+/* The same plus IQTree::original_sample (u16, the ORIGINAL pattern frequencies, at least as many
+ * entries as reported patterns): needed for ratchet iterations, where saveCurrentTree re-scores
+ * cur_logl on the original frequencies (iqtree.cpp:3283-3294).  It rides along as one more
+ * column of the replicate contraction. */
+int mpgpu_load_replicates2(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples, int stride,
+                           const int32_t *segment_upper, int nseg, const uint16_t *original_sample);
 /* groups = 1 + wrap-prone segments, exceptions = patterns on the exact CUDA-core path,
  * tensor = 1 when the tcgen05 path is enabled.  Any pointer may be NULL. */
 int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
@@ -225,6 +231,15 @@ typedef struct mpgpu_bb_state {
     double ufboot_epsilon;    /* Params::ufboot_epsilon (0.5) */
     int64_t n_calls;          /* out: saveCurrentTree calls */
     int64_t n_reps;           /* out: calls that passed the cutoff (REPS vectors computed and used) */
+    /* Ratchet iteration (IQTree::on_ratchet_hclimb1, iqtree.cpp:3283-3294): the search runs on the
+     * perturbed frequencies (mpgpu_set_weights) and every call's cur_logl is minus the score, on the
+     * ORIGINAL frequencies (mpgpu_load_replicates2), of whatever _pattern_pars holds on entry -- the
+     * vector of the previous call that reached pllComputePatternParsimony.  ratchet_pattern_pars =
+     * the host's _pattern_pars before the search (u16, reported patterns); ratchet_last_score
+     * returns the score the next call would see. */
+    int32_t ratchet;                          /* 0 = normal iteration */
+    const uint16_t *ratchet_pattern_pars;     /* in, when ratchet */
+    int32_t ratchet_last_score;               /* out */
 } mpgpu_bb_state;
 int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,

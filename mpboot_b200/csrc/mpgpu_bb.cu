@@ -211,6 +211,7 @@ struct RepsOut {
     int Bpad = 0;
     std::vector<int32_t> dense;                   // concatenated rows [Bpad]
     std::vector<int64_t> dense_off;               // per call: offset into dense, -1 = no replicate can be affected
+    std::vector<int32_t> orig;                    // per call: score on original_sample (column Buser), when loaded
 };
 
 // REPS vectors for the calls cands[0..m) of the last planned scan batch (-1 = the current tree),
@@ -225,6 +226,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     out.Bpad = r.Bpad;
     out.dense.clear();
     out.dense_off.assign(m, -1);
+    out.orig.assign(r.has_orig ? m : 0, 0);
     if (m == 0) return 0;
     if (int rc = refresh_tree_rows(c)) return rc;
     // rows the whole list would like to have; ensure_rows clamps to the memory budget
@@ -237,7 +239,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     const int max_rows = r.row_cap - kTreeRows;
     if (thr) {
         if (!r.d_thr) MPGPU_CUDA(cudaMalloc((void **)&r.d_thr, (size_t)r.Bpad * 4));
-        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.B * 4, cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.Buser * 4, cudaMemcpyHostToDevice, c->stream));
     }
     // staging vectors live in the context: asynchronous uploads may still read them after we return
     std::vector<int32_t> &row_of = r.h_row_of, &row_tasks = r.h_row_tasks;
@@ -309,6 +311,12 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
         if (int rc = launch_reps_combine(c, kTreeRows - 1, r.d_calls, ncalls, r.d_res, thr ? r.d_thr : nullptr, r.d_call_hit)) return rc;
         rp_stop(c, 6);
         if (device_only) return 0;
+        // ---- read back: the original-frequency score of every call (ratchet iterations) ----
+        if (r.has_orig) {
+            MPGPU_CUDA(cudaMemcpy2DAsync(out.orig.data() + done, 4, r.d_res + r.Buser, (size_t)r.Bpad * 4, 4, (size_t)ncalls,
+                                         cudaMemcpyDeviceToHost, c->stream));
+            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        }
         // ---- read back: only the rows of calls that can change a replicate ----
         bool all_rows = true;
         if (thr) {
@@ -359,18 +367,32 @@ struct BBRun {
     mpgpu_bb_state *st;
 };
 
-static inline bool bb_passes(const mpgpu_bb_state *st, uint32_t mp)
+static inline bool bb_passes_logl(const mpgpu_bb_state *st, double cur_logl)
 {
-    const double cur_logl = -(double)mp;
     return !(st->logl_cutoff != 0.0 && cur_logl <= st->logl_cutoff - 1e-4);          // iqtree.cpp:3343
+}
+static inline bool bb_passes(const mpgpu_bb_state *st, uint32_t mp) { return bb_passes_logl(st, -(double)mp); }
+
+// Sum over segments of the 16-bit-wrapped lane sums of a * b (iqtree.cpp:3285-3292)
+static int32_t segmented_u16_dot(const uint16_t *a, const uint16_t *b, const std::vector<int32_t> &seg_upper, int upper)
+{
+    int32_t total = 0;
+    int p = 0;
+    for (size_t s = 0; s < seg_upper.size(); s++) {
+        uint32_t acc = 0;
+        const int hi = std::min(upper, (int)seg_upper[s]);
+        for (; p < hi; p++) acc += (uint32_t)a[p] * b[p];
+        total += (int32_t)(acc & 0xFFFFu);
+    }
+    return total;
 }
 
 // IQTree::saveCurrentTree for one call that passed the cutoff (iqtree.cpp:3345-3348, 3687-3731)
-static void bb_save(BBRun *bb, Ctx *c, uint32_t mp, const RepsOut &ro, int call, int remove_ref, int insert_ref)
+static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int call, int remove_ref, int insert_ref)
 {
     mpgpu_bb_state *st = bb->st;
     const mpgpu_bb_hooks *hk = bb->hooks;
-    const double cur_logl = -(double)mp, eps = st->ufboot_epsilon;
+    const double eps = st->ufboot_epsilon;
     int32_t tree_index = hk->push_tree_logl(hk->user, cur_logl);
     bool have = false;
     auto one = [&](int b, int32_t res) {
@@ -422,6 +444,12 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     std::vector<uint32_t> mp;
     std::vector<int32_t> thr;
     RepsOut ro;
+    int32_t ratchet_stale = 0;
+    if (bb && bb->st->ratchet) {
+        if (!c->reps.has_orig) { set_error("ratchet iteration: load the replicates with mpgpu_load_replicates2 (original_sample)"); return 1; }
+        if (!bb->st->ratchet_pattern_pars) { set_error("ratchet iteration: ratchet_pattern_pars is null"); return 1; }
+        ratchet_stale = segmented_u16_dot(bb->st->ratchet_pattern_pars, c->reps.original_sample.data(), c->reps.seg_upper, c->reps.upper);
+    }
     Prof prof;
     static const char *const prof_names[] = {"plan+launch", "scan wait", "reps", "replay", "views", "moves"};
     do {
@@ -443,10 +471,13 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 mpgpu_bb_state *st = bb->st;
                 pass_cands.clear();
                 call_of.assign((size_t)count + nc, -1);
+                // ratchet iteration: whether a call passes depends on the previous passing call's vector, so
+                // every call of the batch is scored as long as the chain is alive (and none once it broke)
+                const bool all = st->ratchet && bb_passes_logl(st, -(double)ratchet_stale);
                 for (int v = 0; v < count; v++) {
-                    if (bb_passes(st, cur_score)) { call_of[(size_t)v + vbegin[v]] = (int32_t)pass_cands.size(); pass_cands.push_back(-1); }
+                    if (st->ratchet ? all : bb_passes(st, cur_score)) { call_of[(size_t)v + vbegin[v]] = (int32_t)pass_cands.size(); pass_cands.push_back(-1); }
                     for (int j = vbegin[v]; j < vbegin[v + 1]; j++)
-                        if (bb_passes(st, mp[j])) { call_of[(size_t)v + 1 + j] = (int32_t)pass_cands.size(); pass_cands.push_back(j); }
+                        if (st->ratchet ? all : bb_passes(st, mp[j])) { call_of[(size_t)v + 1 + j] = (int32_t)pass_cands.size(); pass_cands.push_back(j); }
                 }
                 thr.resize(st->B);
                 for (int b = 0; b < st->B; b++) {
@@ -461,19 +492,19 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             for (; v < count && !moved; v++) {
                 int insertNode = 0, removeNode = 0;
                 unsigned long bestTreeScoreHits = 1;              // :3303
-                if (bb) {                                         // rearrangeParsimony :2286-2289
+                auto save_call = [&](int k, uint32_t m, int remove_ref, int insert_ref) {
                     bb->st->n_calls++;
-                    const int k = call_of[(size_t)v + vbegin[v]];
-                    if (k >= 0) bb_save(bb, c, cur_score, ro, k, 0, 0);
-                }
+                    if (!bb->st->ratchet) { if (k >= 0) bb_save(bb, c, -(double)m, ro, k, remove_ref, insert_ref); return; }
+                    const double cur_logl = -(double)ratchet_stale;               // iqtree.cpp:3283-3294
+                    if (k < 0 || !bb_passes_logl(bb->st, cur_logl)) return;
+                    bb_save(bb, c, cur_logl, ro, k, remove_ref, insert_ref);
+                    ratchet_stale = ro.orig[k];                                   // _pattern_pars now holds this tree's vector
+                };
+                if (bb) save_call(call_of[(size_t)v + vbegin[v]], cur_score, 0, 0);           // rearrangeParsimony :2286-2289
                 for (int j = vbegin[v]; j < vbegin[v + 1]; j++) {
                     const uint32_t m = mp[j];
                     scored++;
-                    if (bb) {                                     // testInsertParsimony :2163-2166
-                        bb->st->n_calls++;
-                        const int k = call_of[(size_t)v + 1 + j];
-                        if (k >= 0) bb_save(bb, c, m, ro, k, cprune[j], cref[j]);
-                    }
+                    if (bb) save_call(call_of[(size_t)v + 1 + j], m, cprune[j], cref[j]);        // testInsertParsimony :2163-2166
                     if (m < bestParsimony) bestTreeScoreHits = 1;                 // :2168
                     else if (m == bestParsimony) bestTreeScoreHits++;
                     if (m < bestParsimony || (m == bestParsimony && rng(rng_user) <= 1.0 / bestTreeScoreHits)) {
@@ -512,6 +543,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
     *best = startMP;
     if (n_insertions) *n_insertions = scored;
+    if (bb) bb->st->ratchet_last_score = ratchet_stale;
     return 0;
 }
 
@@ -665,7 +697,7 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, 
     if (!c || !back_node || !back_slot || !hooks || !state || !best) { set_error("null argument"); return 1; }
     if (!hooks->random_double || !hooks->push_tree_logl || !hooks->materialize) { set_error("incomplete -bb hooks"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
-    if (state->B != c->reps.B || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
+    if (state->B != c->reps.Buser || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
     state->n_calls = 0; state->n_reps = 0;
     BBRun bb{hooks, state};
     return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, hooks->random_double, hooks->user, &bb, best, n_insertions);
@@ -709,6 +741,12 @@ int mpgpu_reps_info(mpgpu_ctx *c, int *groups, int *exceptions, int *tensor)
 
 int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride, const int32_t *segment_upper, int nseg)
 {
+    return mpgpu_load_replicates2(c, B, boot, stride, segment_upper, nseg, nullptr);
+}
+
+int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride, const int32_t *segment_upper, int nseg,
+                           const uint16_t *original_sample)
+{
     if (!c || !boot || !segment_upper) { set_error("null argument"); return 1; }
     if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
     if (B < 1 || nseg < 1) { set_error("need at least one replicate and one segment"); return 1; }
@@ -721,7 +759,8 @@ int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride,
         if (segment_upper[s] <= (s ? segment_upper[s - 1] : 0)) { set_error("segment_upper must be increasing"); return 1; }
         if (s < nseg - 1 && segment_upper[s] % 16) { set_error("inner segment bounds must be multiples of 16 (iqtree.cpp:3806)"); return 1; }
     }
-    r.B = B; r.Bpad = (B + 255) / 256 * 256;
+    r.Buser = B; r.has_orig = original_sample != nullptr;
+    r.B = B + (r.has_orig ? 1 : 0); r.Bpad = (r.B + 255) / 256 * 256;
     r.upper = std::min(upper0, (int)segment_upper[nseg - 1]);       // the loop at :3424 stops at the last bound
     r.Kpad = (std::max(r.upper, 1) + 127) / 128 * 128; r.Pw = r.Kpad / 32;
     r.seg_upper.assign(segment_upper, segment_upper + nseg);
@@ -735,10 +774,15 @@ int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride,
     MPGPU_CUDA(cudaMalloc((void **)&r.d_w16T, (size_t)std::max(r.upper, 1) * r.Bpad * sizeof(uint16_t)));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_seg_upper, (size_t)nseg_ * 4));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_segmax, (size_t)nseg_ * 4));
-    MPGPU_CUDA(cudaMalloc((void **)&d_boot16, (size_t)B * stride * sizeof(uint16_t)));
+    MPGPU_CUDA(cudaMalloc((void **)&d_boot16, (size_t)r.B * stride * sizeof(uint16_t)));
     MPGPU_CUDA(cudaMalloc((void **)&d_heavy, r.heavy.size()));
     MPGPU_CUDA(cudaMemcpyAsync(r.d_seg_upper, segment_upper, (size_t)nseg_ * 4, cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaMemcpyAsync(d_boot16, boot, (size_t)B * stride * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    if (r.has_orig) {                                     // one more "replicate": the original frequencies
+        r.original_sample.assign(original_sample, original_sample + std::max(r.upper, 1));
+        MPGPU_CUDA(cudaMemsetAsync(d_boot16 + (size_t)B * stride, 0, (size_t)stride * sizeof(uint16_t), c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(d_boot16 + (size_t)B * stride, original_sample, (size_t)r.upper * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    }
     MPGPU_CUDA(cudaMemsetAsync(d_heavy, 0, r.heavy.size(), c->stream));
     int rc = launch_transpose_boot(c, d_boot16, stride, d_heavy);
     cudaError_t e = cudaMemcpyAsync(r.heavy.data(), d_heavy, r.heavy.size(), cudaMemcpyDeviceToHost, c->stream);
@@ -766,7 +810,7 @@ int mpgpu_reps_current_tree(mpgpu_ctx *c, int32_t *res)
     const int32_t cand = -1;
     RepsOut ro;
     if (int rc = reps_run(c, &cand, 1, nullptr, ro)) return rc;
-    memcpy(res, ro.dense.data() + ro.dense_off[0], (size_t)c->reps.B * 4);
+    memcpy(res, ro.dense.data() + ro.dense_off[0], (size_t)c->reps.Buser * 4);
     return 0;
 }
 
@@ -793,7 +837,7 @@ int mpgpu_reps_candidates(mpgpu_ctx *c, const int32_t *cand_idx, int m, int32_t 
     MPGPU_CUDA(cudaSetDevice(c->device));
     RepsOut ro;
     if (int rc = reps_run(c, cand_idx, m, nullptr, ro)) return rc;
-    for (int i = 0; i < m; i++) memcpy(res + (size_t)i * c->reps.B, ro.dense.data() + ro.dense_off[i], (size_t)c->reps.B * 4);
+    for (int i = 0; i < m; i++) memcpy(res + (size_t)i * c->reps.Buser, ro.dense.data() + ro.dense_off[i], (size_t)c->reps.Buser * 4);
     return 0;
 }
 

@@ -100,7 +100,10 @@ struct ScanPlan {
 static const int kTreeRows = 17;          // rows 0..15: bit planes of the tree's per-site counters, row 16: their weighted sum
 struct Reps {
     bool loaded = false;
-    int B = 0, Bpad = 0;                  // replicates, padded to the tensor tile (256)
+    int B = 0, Bpad = 0;                  // weight columns (replicates, + 1 for original_sample), padded to the tensor tile (256)
+    int Buser = 0;                        // replicates proper: columns [0, Buser); column Buser = original_sample when has_orig
+    bool has_orig = false;
+    std::vector<uint16_t> original_sample; // host copy [upper] (ratchet: score of the host's initial _pattern_pars)
     int upper = 0;                        // patterns that take part: min(numInformative or P, last segment_upper)
     int Kpad = 0, Pw = 0;                 // patterns padded to 128; words per pattern row
     std::vector<int32_t> seg_upper;

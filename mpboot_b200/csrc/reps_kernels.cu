@@ -624,7 +624,7 @@ int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int3
     for (int done = 0; done < ncalls; done += 65535) {
         const int chunk = ncalls - done < 65535 ? ncalls - done : 65535;
         dim3 grid((r.Bpad + 255) / 256, chunk);
-        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.B, t_row, d_calls, done, ncalls, d_res, d_thr, d_call_hit);
+        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.Buser, t_row, d_calls, done, ncalls, d_res, d_thr, d_call_hit);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }

@@ -61,6 +61,7 @@ def lib():
     L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.mpgpu_stepwise_addition.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.mpgpu_load_replicates.argtypes = [vp, i32, vp, i32, vp, i32]
+    L.mpgpu_load_replicates2.argtypes = [vp, i32, vp, i32, vp, i32, vp]
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
     L.mpgpu_reps_timing.argtypes = [vp, vp, vp, vp, vp]
     L.mpgpu_set_option.argtypes = [vp, C.c_char_p, i32]
@@ -97,7 +98,8 @@ class BBHooks(C.Structure):
 class BBState(C.Structure):
     """mpgpu_bb_state (include/mpgpu.h)"""
     _fields_ = [("B", C.c_int32), ("boot_logl", C.c_void_p), ("boot_counts", C.c_void_p), ("boot_trees", C.c_void_p),
-                ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64)]
+                ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64),
+                ("ratchet", C.c_int32), ("ratchet_pattern_pars", C.c_void_p), ("ratchet_last_score", C.c_int32)]
 
 
 class HostRng:
@@ -315,11 +317,16 @@ class Engine:
     def set_option(self, name, value):
         self._ck(self.L.mpgpu_set_option(self.h, name.encode(), int(value)))
 
-    def load_replicates(self, boot, segment_upper):
+    def load_replicates(self, boot, segment_upper, original_sample=None):
         boot = np.ascontiguousarray(boot, dtype=np.uint16)
         seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
         self.B = boot.shape[0]
-        self._ck(self.L.mpgpu_load_replicates(self.h, boot.shape[0], _p(boot), boot.shape[1], _p(seg), len(seg)))
+        if original_sample is None:
+            self._ck(self.L.mpgpu_load_replicates(self.h, boot.shape[0], _p(boot), boot.shape[1], _p(seg), len(seg)))
+        else:
+            orig = np.zeros(max(self.P, len(original_sample)), dtype=np.uint16)
+            orig[: len(original_sample)] = original_sample
+            self._ck(self.L.mpgpu_load_replicates2(self.h, boot.shape[0], _p(boot), boot.shape[1], _p(seg), len(seg), _p(orig)))
 
     def reps_info(self):
         g, e, t = C.c_int(), C.c_int(), C.c_int()
@@ -351,14 +358,19 @@ class Engine:
         return ptr.value, pitch.value
 
     def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
-                        mintrav=1, maxtrav=6):
+                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None):
         """pllOptimizeSprParsimony + saveCurrentTree (default policy).  hooks: BBHooks (e.g.
         Treels.hooks(rng)); boot_* arrays are updated in place.  Returns (startMP, back_node,
         back_slot, insertions scored, saveCurrentTree calls, REPS vectors used)."""
         bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
         assert boot_logl.dtype == np.float64 and boot_counts.dtype == np.int32 and boot_trees.dtype == np.int32
         st = BBState(len(boot_logl), boot_logl.ctypes.data, boot_counts.ctypes.data, boot_trees.ctypes.data,
-                     float(logl_cutoff), float(eps), 0, 0)
+                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0)
+        if ratchet_pattern_pars is not None:            # ratchet iteration (iqtree.cpp:3283-3294)
+            rp = np.zeros(max(self.P, len(ratchet_pattern_pars)), dtype=np.uint16)
+            rp[: len(ratchet_pattern_pars)] = ratchet_pattern_pars
+            st.ratchet = 1; st.ratchet_pattern_pars = rp.ctypes.data
+        self.last_bb_state = st
         best = C.c_uint32(); nins = C.c_int64()
         self._ck(self.L.mpgpu_optimize_spr_bb(self.h, _p(bn), _p(bs), mintrav, maxtrav, C.byref(hooks), C.byref(st),
                                               C.byref(best), C.byref(nins)))

@@ -495,6 +495,8 @@ struct BootSim {
     long calls, reps_rows, skipped, bad_sum;
     std::map<unsigned long long, int> treels;                /* topology fingerprint -> tree_index */
     std::vector<long long> mat;                              /* 5 per materialised tree */
+    bool on_ratchet_hclimb1;                                 /* iqtree.cpp:3283: cur_logl from original_sample */
+    unsigned short *original_sample;
 };
 
 static void *aligned32(size_t bytes) { void *p = NULL; if (posix_memalign(&p, 32, bytes)) return NULL; memset(p, 0, bytes); return p; }
@@ -519,7 +521,7 @@ MPREF_API void mpref_boot_free(mpref *h)
     BootSim *b = h->boot;
     if (!b) return;
     for (size_t i = 0; i < b->boot_samples_pars.size(); i++) free(b->boot_samples_pars[i]);
-    free(b->pattern_pars);
+    free(b->pattern_pars); free(b->original_sample);
     delete b;
     h->boot = NULL;
 }
@@ -560,7 +562,19 @@ MPREF_API void mpref_boot_init(mpref *h, int B, const unsigned short *boot, int 
     b->logl_cutoff = logl_cutoff; b->eps = eps;
     b->pattern_pars = (unsigned short *)aligned32(sizeof(unsigned short) * (b->stride + 16));
     b->calls = b->reps_rows = b->skipped = b->bad_sum = 0;
+    b->on_ratchet_hclimb1 = false; b->original_sample = NULL;
     h->boot = b;
+}
+
+MPREF_API void mpref_boot_set_ratchet(mpref *h, const unsigned short *original_sample, const unsigned short *initial_ptn)
+{
+    BootSim *b = h->boot;
+    b->on_ratchet_hclimb1 = true;
+    free(b->original_sample);
+    b->original_sample = (unsigned short *)aligned32(sizeof(unsigned short) * (b->stride + 16));
+    memcpy(b->original_sample, original_sample, sizeof(unsigned short) * h->P);
+    memset(b->pattern_pars, 0, sizeof(unsigned short) * (b->stride + 16));
+    memcpy(b->pattern_pars, initial_ptn, sizeof(unsigned short) * h->P);
 }
 
 MPREF_API void mpref_boot_set_cutoff(mpref *h, double c) { if (h->boot) h->boot->logl_cutoff = c; }
@@ -590,12 +604,23 @@ static void boot_save_current_tree(mpref *h, double cur_logl)
 {
     BootSim *b = h->boot;
     long call = b->calls++;
+    if (b->on_ratchet_hclimb1) {                                                           /* :3283-3294 */
+        int ptn = 0, segment_id = 0, score = 0;
+        Vec16us vc_score = 0;
+        for (; segment_id < b->nseg; segment_id++) {
+            for (; ptn < b->segment_upper[segment_id]; ptn += 16)
+                vc_score = Vec16us().load_a(&b->pattern_pars[ptn]) * Vec16us().load_a(&b->original_sample[ptn]) + vc_score;
+            score += horizontal_add(vc_score);
+            vc_score = 0;
+        }
+        cur_logl = -score;
+    }
     if (b->logl_cutoff != 0.0 && cur_logl <= b->logl_cutoff - 1e-4) return;              /* :3343 */
     int tree_index = (int)b->treels_logl.size();                                          /* :3345 */
     b->treels_logl.push_back(cur_logl);
     int test_pars = 0;
     pllComputePatternParsimony(h->tr, h->pr, b->pattern_pars, &test_pars);                 /* :3365 */
-    if (test_pars != -int(cur_logl)) b->bad_sum++;                                         /* :3366 */
+    if (!b->on_ratchet_hclimb1 && test_pars != -int(cur_logl)) b->bad_sum++;               /* :3366 */
     b->reps_rows++;
     bool have_str = false;
     unsigned short *_pattern_pars = b->pattern_pars;

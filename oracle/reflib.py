@@ -73,6 +73,7 @@ def _boot_protos(L, pre):
     getattr(L, pre + "_boot_init").argtypes = [vp, i, vp, i, vp, i, C.c_double, C.c_double, vp]
     getattr(L, pre + "_boot_free").argtypes = [vp]
     getattr(L, pre + "_boot_set_cutoff").argtypes = [vp, C.c_double]
+    getattr(L, pre + "_boot_set_ratchet").argtypes = [vp, vp, vp]
     getattr(L, pre + "_boot_set_state").argtypes = [vp, vp, vp, vp]
     getattr(L, pre + "_boot_get_state").argtypes = [vp, vp, vp, vp]
     getattr(L, pre + "_boot_counters").restype = C.c_long
@@ -100,6 +101,13 @@ class BootMixin:
         b = None if bound is None else np.ascontiguousarray(bound, dtype=np.int32)
         self._f("_boot_init")(self.h, boot.shape[0], _p(boot), boot.shape[1], _p(seg), len(seg),
                               float(logl_cutoff), float(eps), None if b is None else _p(b))
+
+    def boot_set_ratchet(self, original_sample, initial_ptn):
+        """Ratchet-iteration semantics (iqtree.cpp:3283-3294): cur_logl of every call is recomputed on the
+        original frequencies from the previous call's pattern vector (initial_ptn before the first)."""
+        a = np.zeros(self.P, dtype=np.uint16); a[: len(original_sample)] = original_sample
+        b = np.zeros(self.P, dtype=np.uint16); b[: len(initial_ptn)] = initial_ptn
+        self._f("_boot_set_ratchet")(self.h, _p(a), _p(b))
 
     def boot_free(self):
         self._f("_boot_free")(self.h)

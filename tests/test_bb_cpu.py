@@ -34,10 +34,28 @@ def bb_setup(n, L, dt, seed, B, mu=0.05, art_segments=True, heavy=True):
     return c, o, s0, pp, seg, boot, ras, bound
 
 
-def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6):
+def ratchet_setup(c, pp, seed):
+    """What a ratchet iteration changes (alignment.cpp:1940-1963): half of the informative patterns get
+    frequency + 1 for the search; saveCurrentTree still scores cur_logl on the original frequencies."""
+    rng = np.random.default_rng(700 + seed)
+    w2 = c["weights"].copy()
+    w2[: c["n_inf"]] += (rng.random(c["n_inf"]) < 0.5).astype(w2.dtype)
+    P = len(w2)
+    orig = np.zeros(P, dtype=np.uint16); orig[: c["n_inf"]] = c["weights"][: c["n_inf"]]
+    init = np.zeros(P, dtype=np.uint16); init[: c["n_inf"]] = pp
+    return w2, orig, init
+
+
+def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None):
+    if ratchet is not None:
+        eng.set_weights(ratchet[0])
+    else:
+        eng.set_weights(c["weights"])
     eng.set_ring(c["bn"], c["bs"])
     eng.allocate(per_site=True)
     eng.boot_init(boot, seg, cutoff, 0.5, bound)
+    if ratchet is not None:
+        eng.boot_set_ratchet(ratchet[1], ratchet[2])
     (reflib.lib().mpref_seed_rng if is_ref else portlib.seed_rng)(seed)
     eng.record(False)
     ret = eng.optimize_spr(1, mt, bb=True)
@@ -73,6 +91,23 @@ def test_port_bb_equals_reference(n, L, dt, seed, B, mu):
         assert a[k] == b[k]
     assert all(np.array_equal(x, y) for x, y in zip(a["state"], b["state"]))
     assert np.array_equal(a["mats"], b["mats"])
+
+
+@needs_ref
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05), (30, 800, 1, 21, 64, 0.01)])
+def test_port_bb_ratchet_iteration_equals_reference(n, L, dt, seed, B, mu):
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    rt = ratchet_setup(c, pp, seed)
+    a = run_bb(o, c, boot, seg, 0.0, None, False, ratchet=rt)
+    same(a, run_bb(r, c, boot, seg, 0.0, None, True, ratchet=rt))
+    # with a cutoff the chain of stale scores breaks at some call and nothing passes afterwards
+    top = np.unique(-a["treels"])[::-1]               # original-frequency scores of the unfiltered run, worst first
+    for worst in top[:2]:                             # the chain breaks right after the first call that scores `worst`
+        cutoff = -(worst - 0.5)
+        x = run_bb(o, c, boot, seg, cutoff, None, False, ratchet=rt)
+        same(x, run_bb(r, c, boot, seg, cutoff, None, True, ratchet=rt))
+        assert x["counters"][1] < a["counters"][1]
 
 
 def test_fingerprint_matches_python_helper():
@@ -112,7 +147,8 @@ def test_port_bb_equals_golden(path):
     n, dt, mt = int(g["n"]), int(g["datatype"]), int(g["maxtrav"])
     c = dict(n=n, datatype=dt, codes=g["codes"], weights=g["weights"], n_inf=int(g["n_inf"]), bn=g["bn"], bs=g["bs"])
     o = portlib.OracleEngine(g["codes"], g["weights"], dt)
-    for tag in ("all", "cut"):
-        r = run_bb(o, c, g["bb_boot"], g["bb_seg"], float(g["bb_%s_cutoff" % tag]), None, False, mt=mt)
+    for tag in ("all", "cut", "rall", "rcut"):
+        rt = (g["bb_ratchet_weights"], g["bb_ratchet_orig"], g["bb_ratchet_init"]) if tag[0] == "r" else None
+        r = run_bb(o, c, g["bb_boot"], g["bb_seg"], float(g["bb_%s_cutoff" % tag]), None, False, mt=mt, ratchet=rt)
         r["mats"] = r["mats"][:, [3, 4]]
         check_against_golden(g, tag, r)

@@ -16,13 +16,15 @@ CASES = [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05), (30, 800, 1, 21, 
          (40, 1500, 1, 11, 300, 0.05), (16, 300, 0, 3, 20, 0.05)]
 
 
-def _engine(c, boot, seg, tensor):
+def _engine(c, boot, seg, tensor, ratchet=None):
     from mpboot_b200.engine import Engine
     eng = Engine()
     eng.set_option("reps_tensor", tensor)
     eng.load_alignment(c["codes"], c["weights"], c["datatype"])
+    if ratchet is not None:
+        eng.set_weights(ratchet[0])                 # the search runs on the perturbed frequencies
     eng.set_tree(c["bn"], c["bs"])
-    eng.load_replicates(boot, seg)
+    eng.load_replicates(boot, seg, original_sample=None if ratchet is None else ratchet[1])
     return eng
 
 
@@ -49,6 +51,33 @@ def test_reps_current_tree_and_candidates(n, L, dt, seed, B, mu, tensor):
             assert np.array_equal(got[k], portlib.reps(ptn[k, : c["n_inf"]], boot[:, : c["n_inf"]], seg)), (i, k)
 
 
+def _same_as_oracle(g, w):
+    assert g["ret"] == w["ret"] and g["draws"] == w["draws"]
+    assert np.array_equal(g["ring"][0][3:], w["ring"][0][3:]) and np.array_equal(g["ring"][1][3:], w["ring"][1][3:])
+    assert all(np.array_equal(x, y) for x, y in zip(g["state"], w["state"]))
+    assert g["ncalls"] == w["counters"][0] and g["nreps"] == w["counters"][2]
+    assert np.array_equal(g["treels"], w["treels"])
+    assert np.array_equal(g["mats"][:, :3], w["mats"][:, 1:4]) and np.array_equal(g["mats"][:, 3], w["mats"][:, 4])
+
+
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES[:4])
+def test_bb_search_ratchet_iteration_matches_oracle(n, L, dt, seed, B, mu, tensor):
+    """on_ratchet_hclimb1 (iqtree.cpp:3283-3294): search on perturbed frequencies, cur_logl of every call =
+    original-frequency score of the previous passing call's tree; the chain breaks for good once such a
+    score fails the cutoff."""
+    from tests.test_bb_cpu import ratchet_setup
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    rt = ratchet_setup(c, pp, seed)
+    a = run_bb(o, c, boot, seg, 0.0, None, False, ratchet=rt)
+    _same_as_oracle(_run_gpu_bb(c, boot, seg, 0.0, tensor, ratchet=rt), a)
+    top = np.unique(-a["treels"])[::-1]
+    for worst in top[:2]:
+        cutoff = -(worst - 0.5)
+        w = run_bb(o, c, boot, seg, cutoff, None, False, ratchet=rt)
+        _same_as_oracle(_run_gpu_bb(c, boot, seg, cutoff, tensor, ratchet=rt), w)
+
+
 def test_reps_wrap_free_bulk_uses_no_exceptions():
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(40, 1500, 1, 11, 100, heavy=False)
     eng = _engine(c, boot, seg, 1)
@@ -57,16 +86,17 @@ def test_reps_wrap_free_bulk_uses_no_exceptions():
     assert groups == 1 and exc == 0 and t == 1                # everything on the tensor path
 
 
-def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6):
+def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None):
     from mpboot_b200.engine import Treels
-    eng = _engine(c, boot, seg, tensor)
+    eng = _engine(c, boot, seg, tensor, ratchet)
     B = boot.shape[0]
     bl = np.full(B, -float(np.iinfo(np.int64).max), dtype=np.float64)   # -LONG_MAX, iqtree.cpp:248
     bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
     tl = Treels(c["n"])
     portlib.seed_rng(seed)
     ret, bn, bs, nins, ncalls, nreps = eng.optimize_spr_bb(c["bn"], c["bs"], tl.hooks(portlib.rng_fn_address()),
-                                                           bl, bc, bt, cutoff, 0.5, 1, mt)
+                                                           bl, bc, bt, cutoff, 0.5, 1, mt,
+                                                           ratchet_pattern_pars=None if ratchet is None else ratchet[2])
     return dict(ret=ret, draws=portlib.rng_draws(), ring=(bn, bs), state=(bl, bc, bt), ncalls=ncalls, nreps=nreps,
                 treels=tl.logl(), mats=tl.materialized(), nins=nins)
 
@@ -99,8 +129,9 @@ def test_bb_search_matches_golden(path):
     g = dict(np.load(path))
     n, dt, mt = int(g["n"]), int(g["datatype"]), int(g["maxtrav"])
     c = dict(n=n, datatype=dt, codes=g["codes"], weights=g["weights"], n_inf=int(g["n_inf"]), bn=g["bn"], bs=g["bs"])
-    for tag in ("all", "cut"):
-        r = _run_gpu_bb(c, g["bb_boot"], g["bb_seg"], float(g["bb_%s_cutoff" % tag]), 1, mt=mt)
+    for tag in ("all", "cut", "rall", "rcut"):
+        rt = (g["bb_ratchet_weights"], g["bb_ratchet_orig"], g["bb_ratchet_init"]) if tag[0] == "r" else None
+        r = _run_gpu_bb(c, g["bb_boot"], g["bb_seg"], float(g["bb_%s_cutoff" % tag]), 1, mt=mt, ratchet=rt)
         r["counters"] = (r["ncalls"], len(r["treels"]), r["nreps"])
         r["mats"] = r["mats"][:, [2, 3]]
         check_against_golden(g, tag, r)

@@ -96,6 +96,34 @@ def one_case(name, n, L, dt, seed, maxtrav):
         g["bb_%s_counters" % tag] = np.array(ref.boot_counters(), dtype=np.int64)
         g["bb_%s_treels" % tag] = ref.boot_treels()
         g["bb_%s_mats" % tag] = ref.boot_mats()[:, [0, 3, 4]]          # call index, tree_index, topology fingerprint
+    # a ratchet iteration (on_ratchet_hclimb1): search on perturbed frequencies, cur_logl re-scored on the
+    # original ones from the previous call's vector (iqtree.cpp:3283-3294); cutoff chosen so that the chain of
+    # passing calls breaks somewhere inside the search
+    from tests.test_bb_cpu import ratchet_setup
+    rt = ratchet_setup(c, g["ptn_pars"], seed)
+    g["bb_ratchet_weights"] = rt[0]; g["bb_ratchet_orig"] = rt[1]; g["bb_ratchet_init"] = rt[2]
+    cut = 0.0
+    for tag in ("rall", "rcut"):
+        ref.set_weights(rt[0])
+        ref.set_ring(c["bn"], c["bs"])
+        ref.allocate(per_site=True)
+        ref.boot_init(boot, seg, cut, 0.5, None)
+        ref.boot_set_ratchet(rt[1], rt[2])
+        reflib.lib().mpref_seed_rng(2024)
+        ref.record(False)
+        g["bb_%s_cutoff" % tag] = cut
+        g["bb_%s_ret" % tag] = ref.optimize_spr(1, maxtrav, bb=True)
+        g["bb_%s_draws" % tag] = reflib.lib().mpref_rng_draws()
+        bn, bs = ref.get_ring()
+        g["bb_%s_bn" % tag] = bn; g["bb_%s_bs" % tag] = bs
+        bl, bc, bt = ref.boot_state()
+        g["bb_%s_boot_logl" % tag] = bl; g["bb_%s_boot_counts" % tag] = bc; g["bb_%s_boot_trees" % tag] = bt
+        g["bb_%s_counters" % tag] = np.array(ref.boot_counters(), dtype=np.int64)
+        g["bb_%s_treels" % tag] = ref.boot_treels()
+        g["bb_%s_mats" % tag] = ref.boot_mats()[:, [0, 3, 4]]
+        top = np.unique(-g["bb_rall_treels"])[::-1]
+        cut = -(float(top[min(1, len(top) - 1)]) - 0.5)
+    ref.set_weights(c["weights"])
     ref.boot_free()
     # randomized stepwise addition
     reflib.lib().mpref_seed_rng(77)
