@@ -226,6 +226,125 @@ int launch_level(Ctx *c, const Triple *d_triples, int ntriples)
 }
 
 // ------------------------------------------------------------------------------------------
+// R3, latency path: every stale view after an SPR move in ONE launch.  The stale views form a
+// dependency forest as deep as the tree (each needs one stale and, mostly, one clean child): far
+// too little work per level for a launch each, and a chain of L2 round trips if done naively.
+// Fitch is word-local, so a CTA owns a 32-word column of ALL views and walks the levels alone:
+//   * the triple list is staged in shared memory once,
+//   * NW warps share the triples of a level; each warp prefetches the CLEAN operand of its next
+//     triple (any level ahead) into registers while it works on the current one,
+//   * a fresh view is written to global memory and to a two-generation shared-memory cache, so
+//     the stale operand of the next level comes from shared memory, not from L2,
+//   * __syncthreads() between levels; no CTA ever reads a word another CTA writes.
+// Triple.pad = a_slot | dst_slot << 8 | b_clean << 16 (slots 0xFF: not cached).  list = hdr
+// Triples reinterpreted as int32 level ends, then the triples; wcount[k] += popc(t_N) of triple k.
+// ------------------------------------------------------------------------------------------
+template <int S> struct WaveCfg { static const int CAP = S <= 4 ? 32 : (S <= 20 ? 16 : 12); };
+
+template <int S, int NW>
+__global__ void __launch_bounds__(32 * NW) k_fitch_wave(uint32_t *views, size_t view_stride, int Wl,
+                                                        const Triple *__restrict__ list, int nlevels, int hdr, int total,
+                                                        uint32_t *__restrict__ wcount)
+{
+    extern __shared__ uint4 wave_smem[];
+    const int CAP = WaveCfg<S>::CAP;
+    int4 *sl = reinterpret_cast<int4 *>(wave_smem);
+    uint32_t *cache = reinterpret_cast<uint32_t *>(sl + hdr + total);
+    for (int i = threadIdx.x; i < hdr + total; i += 32 * NW) sl[i] = __ldg(reinterpret_cast<const int4 *>(list) + i);
+    __syncthreads();
+    const int32_t *level_end = reinterpret_cast<const int32_t *>(sl);
+    const int4 *tri = sl + hdr;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * 32 + lane;
+    const size_t gs = (size_t)Wl * Lay<S>::SG;
+    const size_t off = (size_t)w * Lay<S>::SG;
+
+    // this warp's next triple: index nt, in level nl
+    int nt = -1, nl = 0;
+    {
+        int s0 = 0;
+        for (nl = 0; nl < nlevels; nl++) { const int e = level_end[nl]; if (s0 + warp < e) { nt = s0 + warp; break; } s0 = e; }
+    }
+    uint32_t bp[S];
+    if (nt >= 0) { const int4 d = tri[nt]; if (d.w & 0x10000) load_states_rw<S>(views + (size_t)d.z * view_stride + off, gs, bp); }
+
+    for (int l = 0; l < nlevels; l++) {
+        const int t1 = level_end[l];
+        while (nt >= 0 && nl == l) {
+            const int cur = nt;
+            const int4 d = tri[cur];
+            uint32_t a[S], b[S];
+#pragma unroll
+            for (int k = 0; k < S; k++) b[k] = bp[k];
+            // next triple of this warp and its clean operand
+            if (cur + NW < t1) nt = cur + NW;
+            else {
+                nt = -1;
+                int s0 = t1;
+                for (nl = l + 1; nl < nlevels; nl++) { const int e = level_end[nl]; if (s0 + warp < e) { nt = s0 + warp; break; } s0 = e; }
+            }
+            if (nt >= 0) { const int4 dn = tri[nt]; if (dn.w & 0x10000) load_states_rw<S>(views + (size_t)dn.z * view_stride + off, gs, bp); }
+            if (!(d.w & 0x10000)) load_states_rw<S>(views + (size_t)d.z * view_stride + off, gs, b);
+            const int a_slot = d.w & 0xFF, d_slot = (d.w >> 8) & 0xFF;
+            if (a_slot != 0xFF) {
+                const uint32_t *src = cache + ((size_t)(((l + 1) & 1) * CAP + a_slot) * S) * 32 + lane;
+#pragma unroll
+                for (int k = 0; k < S; k++) a[k] = src[k * 32];
+            } else {
+                load_states_rw<S>(views + (size_t)d.y * view_stride + off, gs, a);
+            }
+            const uint32_t n = any_and<S>(a, b);
+#pragma unroll
+            for (int k = 0; k < S; k++) a[k] = fitch1(a[k], b[k], n);
+            store_states<S>(views + (size_t)d.x * view_stride + off, gs, a);
+            if (d_slot != 0xFF) {
+                uint32_t *dstc = cache + ((size_t)((l & 1) * CAP + d_slot) * S) * 32 + lane;
+#pragma unroll
+                for (int k = 0; k < S; k++) dstc[k * 32] = a[k];
+            }
+            const int cnt = __reduce_add_sync(0xffffffffu, __popc(~n));
+            if (lane == 0 && cnt) atomicAdd(&wcount[cur], (uint32_t)cnt);
+        }
+        __syncthreads();
+    }
+}
+
+int wave_slot_cap(int S) { return S <= 4 ? 32 : (S <= 20 ? 16 : 12); }
+size_t wave_smem_bytes(int S, int entries) { return (size_t)entries * sizeof(Triple) + (size_t)2 * wave_slot_cap(S) * S * 128; }
+
+template <int S, int NW>
+static int launch_wave_t(Ctx *c, const Triple *d_list, int nlevels, int hdr, int total, uint32_t *d_wcount)
+{
+    const size_t smem = wave_smem_bytes(S, hdr + total);
+    static size_t opted = 0;
+    if (smem > opted) {
+        MPGPU_CUDA(cudaFuncSetAttribute(k_fitch_wave<S, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted = smem;
+    }
+    k_fitch_wave<S, NW><<<c->Wl / 32, 32 * NW, smem, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_list, nlevels, hdr, total, d_wcount);
+    return 0;
+}
+
+int launch_wave(Ctx *c, const Triple *d_list, int nlevels, int hdr, int total, uint32_t *d_wcount)
+{
+    if (nlevels == 0) return 0;
+    const int NW = 16;
+    int rc = 0;
+    switch (c->S) {
+    case 2:  rc = launch_wave_t<2, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+    case 4:  rc = launch_wave_t<4, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+    case 20: rc = launch_wave_t<20, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+    case 32: rc = launch_wave_t<32, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+    default: set_error("unsupported state count"); return 1;
+    }
+    if (rc) return rc;
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // R4: mismatch count across one edge: popc(~OR_k(A_k & B_k))
 // ------------------------------------------------------------------------------------------
 template <int S>

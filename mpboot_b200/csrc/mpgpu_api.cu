@@ -3,6 +3,9 @@
 // compute entry point needs a CUDA device and fails loudly otherwise.
 #include "mpgpu_internal.h"
 
+#include <chrono>
+#include <cstdio>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -116,22 +119,24 @@ static int build_planes(Ctx *c, bool realloc_views)
     else MPGPU_CUDA(cudaMemsetAsync(c->d_views, 0xff, (size_t)c->n * c->view_stride * sizeof(uint32_t), c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // host staging vectors go out of scope
     c->lens_valid = false;
+    c->kids_valid = false;
     c->ptn_site_valid = false;
     c->reps.tree_valid = false;
     return 0;
 }
 
-// level schedule of all directed views + launch (one kernel per level)
-int compute_views(Ctx *c)
+// dependency schedule of all directed views of c->tree -> c->sched (post-order: children first)
+static void build_schedule(Ctx *c)
 {
     const HostTree &t = c->tree;
     const int n = t.n;
     const int nviews = 4 * n - 6;
-    std::vector<int> level(nviews, -1);
+    std::vector<int32_t> &level = c->sc_level, &stack = c->sc_stack;
+    level.assign(nviews, -1);
     for (int i = 0; i < n; i++) level[i] = 0;
-    c->levels.clear();
-    // iterative post-order over the dependency DAG
-    std::vector<int> stack;
+    c->sched.clear();
+    c->sched_levels = 0;
+    stack.clear();
     for (int node = n + 1; node <= 2 * n - 2; node++) for (int s = 0; s < 3; s++) {
         const int root = 3 * node + s;
         if (!t.has_back(root)) continue;
@@ -146,9 +151,9 @@ int compute_views(Ctx *c)
             if (la >= 0 && lb >= 0) {
                 const int l = std::max(la, lb) + 1;
                 level[v] = l;
-                if ((int)c->levels.size() < l) c->levels.resize(l);
-                Triple tr; tr.dst = v; tr.a = t.vid(a); tr.b = t.vid(b); tr.pad = 0;
-                c->levels[l - 1].push_back(tr);
+                if (l > c->sched_levels) c->sched_levels = l;
+                Triple tr; tr.dst = v; tr.a = t.vid(a); tr.b = t.vid(b); tr.pad = l;
+                c->sched.push_back(tr);
                 stack.pop_back();
             } else {
                 if (la < 0) stack.push_back(a);
@@ -156,33 +161,131 @@ int compute_views(Ctx *c)
             }
         }
     }
-    size_t total = 0;
-    for (auto &lv : c->levels) total += lv.size();
+}
+
+static inline int2 kid_pair(const Triple &tr) { return tr.a < tr.b ? make_int2(tr.a, tr.b) : make_int2(tr.b, tr.a); }
+
+// all directed views of c->tree: level schedule + one launch per level (throughput path)
+int compute_views(Ctx *c)
+{
+    const int nviews = 4 * c->n - 6;
+    build_schedule(c);
+    const size_t total = c->sched.size();
+    const int nl = c->sched_levels;
     if (int rc = ensure(c->d_triples, c->triples_cap, total)) return rc;
-    std::vector<Triple> flat; flat.reserve(total);
-    for (auto &lv : c->levels) flat.insert(flat.end(), lv.begin(), lv.end());
+    std::vector<int32_t> start(nl + 2, 0);
+    for (const Triple &tr : c->sched) start[tr.pad + 1]++;
+    for (int l = 1; l <= nl + 1; l++) start[l] += start[l - 1];          // level l occupies [start[l], start[l+1])
+    std::vector<Triple> flat(total);
+    {
+        std::vector<int32_t> fill(start.begin(), start.end());
+        for (const Triple &tr : c->sched) { Triple x = tr; x.pad = 0; flat[fill[tr.pad]++] = x; }
+    }
     MPGPU_CUDA(cudaMemcpyAsync(c->d_triples, flat.data(), total * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaMemsetAsync(c->d_vcount, 0, nviews * sizeof(uint32_t), c->stream));
-    size_t off = 0;
-    for (auto &lv : c->levels) {
-        if (int rc = launch_level(c, c->d_triples + off, (int)lv.size())) return rc;
-        off += lv.size();
-    }
+    for (int l = 1; l <= nl; l++)
+        if (int rc = launch_level(c, c->d_triples + start[l], start[l + 1] - start[l])) return rc;
     c->reps.tree_valid = false;
     if (c->shard_count > 1 && c->allreduce) { if (int rc = shard_sum(c, c->d_vcount, nviews)) return rc; }
     c->vcount.assign(nviews, 0);
     MPGPU_CUDA(cudaMemcpyAsync(c->vcount.data(), c->d_vcount, nviews * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->view_kids.assign(nviews, make_int2(-1, -1));
+    for (const Triple &tr : c->sched) c->view_kids[tr.dst] = kid_pair(tr);
+    c->kids_valid = true;
     return 0;
 }
 
-// subtree lengths from (all-reduced) mismatch counts, in level order
+// After a move on c->tree (latency path): a view is stale iff its children changed or one of
+// them is stale -- about half of the views, in a forest as deep as the tree.  They are
+// recomputed by ONE k_fitch_wave launch; the mismatch counts of the stale views come back
+// compact.  Needs complete counts on every shard (all-reduce callback) like compute_lengths.
+int update_views(Ctx *c)
+{
+    const int nviews = 4 * c->n - 6;
+    if (!c->kids_valid || (int)c->view_kids.size() != nviews || (int)c->vcount.size() != nviews ||
+        (c->shard_count > 1 && !c->allreduce) || getenv("MPGPU_NO_WAVE"))
+        return compute_views(c);
+    static const bool prof = getenv("MPGPU_PROFILE") != nullptr;
+    static double t_host = 0, t_dev = 0; static long n_calls = 0, n_triples = 0, n_levels = 0;
+    std::chrono::steady_clock::time_point p0, p1;
+    if (prof) p0 = std::chrono::steady_clock::now();
+    build_schedule(c);
+    std::vector<int32_t> &dl = c->sc_dl, &slot = c->sc_slot, &fill = c->sc_fill;
+    std::vector<Triple> &stale = c->sc_stale;
+    dl.assign(nviews, 0);                               // stale level (0 = clean)
+    stale.clear();
+    int nlevels = 0;
+    for (const Triple &tr0 : c->sched) {
+        const int2 k = kid_pair(tr0), o = c->view_kids[tr0.dst];
+        if (dl[tr0.a] == 0 && dl[tr0.b] == 0 && k.x == o.x && k.y == o.y) continue;
+        Triple tr = tr0;
+        const int l = std::max(dl[tr.a], dl[tr.b]) + 1;
+        // b = the clean operand when there is one (prefetched); a = the stale one of the previous level (cached)
+        const bool sa = dl[tr.a] != 0, sb = dl[tr.b] != 0;
+        if (!sa && sb) std::swap(tr.a, tr.b);
+        else if (sa && sb && dl[tr.a] != l - 1) std::swap(tr.a, tr.b);
+        tr.pad = l;
+        dl[tr.dst] = l;
+        if (l > nlevels) nlevels = l;
+        stale.push_back(tr);
+        c->view_kids[tr.dst] = k;
+    }
+    const size_t total = stale.size();
+    if (total == 0) return 0;
+    const int hdr = (nlevels + 3) / 4;
+    if (wave_smem_bytes(c->S, hdr + (int)total) > 200 * 1024) { c->kids_valid = false; return compute_views(c); }   // list does not fit in shared memory
+    if (!c->wave_pin.reserve(2 * (hdr + total) + 64) || !c->wcount_pin.reserve(2 * total + 64)) { set_error("pinned allocation failed"); return 1; }
+    if (int rc = ensure(c->d_wave, c->wave_cap, hdr + total)) return rc;
+    if (int rc = ensure(c->d_wcount, c->wcount_cap, total)) return rc;
+    // counting sort by stale level straight into the pinned list; slots = position within the level
+    int32_t *level_end = reinterpret_cast<int32_t *>(c->wave_pin.data());
+    Triple *dst = c->wave_pin.data() + hdr;
+    fill.assign(nlevels + 2, 0);
+    for (const Triple &tr : stale) fill[tr.pad + 1]++;
+    for (int l = 1; l <= nlevels + 1; l++) fill[l] += fill[l - 1];
+    for (int l = 1; l <= nlevels; l++) level_end[l - 1] = fill[l + 1];
+    for (int l = nlevels; l < 4 * hdr; l++) level_end[l] = (int32_t)total;
+    const int cap = wave_slot_cap(c->S);
+    slot.resize(nviews);
+    for (const Triple &tr : stale) {                     // children precede parents in `stale`, so slot[tr.a] is final
+        const int l = tr.pad;
+        const int at = fill[l]++;
+        const int pos = at - (l >= 2 ? level_end[l - 2] : 0);
+        const int a_slot = dl[tr.a] == l - 1 && l > 1 ? slot[tr.a] : 0xFF;
+        const int d_slot = pos < cap ? pos : 0xFF;
+        slot[tr.dst] = d_slot;
+        Triple x = tr;
+        x.pad = a_slot | d_slot << 8 | (dl[tr.b] == 0 ? 0x10000 : 0);
+        dst[at] = x;
+    }
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_wave, c->wave_pin.data(), (hdr + total) * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, total * sizeof(uint32_t), c->stream));
+    if (int rc = launch_wave(c, c->d_wave, nlevels, hdr, (int)total, c->d_wcount)) return rc;
+    if (prof) p1 = std::chrono::steady_clock::now();
+    c->reps.tree_valid = false;
+    if (c->shard_count > 1) { if (int rc = shard_sum(c, c->d_wcount, (int64_t)total)) return rc; }
+    MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    const uint32_t *wc = c->wcount_pin.data();
+    for (size_t i = 0; i < total; i++) c->vcount[dst[i].dst] = wc[i];
+    if (prof) {
+        const auto p2 = std::chrono::steady_clock::now();
+        t_host += std::chrono::duration<double>(p1 - p0).count(); t_dev += std::chrono::duration<double>(p2 - p1).count();
+        n_calls++; n_triples += (long)total; n_levels += nlevels;
+        if (n_calls % 256 == 0)
+            fprintf(stderr, "[mpgpu profile] update_views x%ld: host %.1f us, launch..sync %.1f us per call; %.0f stale views in %.0f levels\n",
+                    n_calls, 1e6 * t_host / n_calls, 1e6 * t_dev / n_calls, (double)n_triples / n_calls, (double)n_levels / n_calls);
+    }
+    return 0;
+}
+
+// subtree lengths from (all-reduced) mismatch counts, children before parents
 void compute_lengths(Ctx *c)
 {
     const int nviews = 4 * c->n - 6;
     c->vlen.assign(nviews, 0);
-    for (auto &lv : c->levels)
-        for (const Triple &tr : lv) c->vlen[tr.dst] = c->vlen[tr.a] + c->vlen[tr.b] + c->vcount[tr.dst];
+    for (const Triple &tr : c->sched) c->vlen[tr.dst] = c->vlen[tr.a] + c->vlen[tr.b] + c->vcount[tr.dst];
     c->lens_valid = true;
 }
 
@@ -386,6 +489,8 @@ int mpgpu_destroy(mpgpu_ctx *c)
     cudaStreamSynchronize(c->stream);
     free_alignment(c);
     if (c->d_triples) cudaFree(c->d_triples);
+    if (c->d_wave) cudaFree(c->d_wave);
+    if (c->d_wcount) cudaFree(c->d_wcount);
     if (c->d_scalar) cudaFree(c->d_scalar);
     if (c->d_offs) cudaFree(c->d_offs);
     if (c->d_ctl) cudaFree(c->d_ctl);

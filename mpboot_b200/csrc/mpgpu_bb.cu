@@ -527,7 +527,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             if (moved) {
                 prof.start();
                 c->tree_set = true; c->lens_valid = false;
-                if (int rc = compute_views(c)) return rc;
+                if (int rc = update_views(c)) return rc;
                 compute_lengths(c);
                 batch = 16;
                 prof.stop(4);
@@ -656,7 +656,7 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         t.hookup(q + 2, r);
         treelen = best;
         c->lens_valid = false;
-        if ((rc = compute_views(c))) break;
+        if ((rc = update_views(c))) break;
         compute_lengths(c);
     }
     if (d_edges) cudaFree(d_edges);

@@ -188,8 +188,16 @@ struct Ctx {
     std::vector<uint32_t> vlen;           // subtree length of each view
     bool tree_set = false, lens_valid = false;
     HostTree tree;
-    std::vector<std::vector<Triple>> levels;
+    std::vector<Triple> sched;            // every inner view once, children before parents; pad = dependency level (1-based)
+    int sched_levels = 0;
+    std::vector<int32_t> sc_level, sc_stack, sc_dl, sc_slot, sc_fill;   // scratch of build_schedule / update_views (no allocation per move)
+    std::vector<Triple> sc_stale;
     Triple *d_triples = nullptr; size_t triples_cap = 0;
+    // incremental update after a move (update_views): children of every view at its last compute
+    std::vector<int2> view_kids; bool kids_valid = false;
+    PinnedArray<Triple> wave_pin; PinnedArray<uint32_t> wcount_pin;
+    Triple *d_wave = nullptr; size_t wave_cap = 0;
+    uint32_t *d_wcount = nullptr; size_t wcount_cap = 0;
     uint32_t *d_scalar = nullptr;         // small scratch for scalar results
 
     // scan
@@ -234,6 +242,7 @@ static inline int ensure(T *&ptr, size_t &cap, size_t need)
 // ---- shared host helpers (mpgpu_api.cu) -----------------------------------------------------
 int shard_sum(Ctx *c, void *dev_i32, int64_t count);   // in-place int32 all-reduce over the shards (no-op for one shard)
 int compute_views(Ctx *c);
+int update_views(Ctx *c);        // after apply_spr_move on c->tree: recompute only the stale views, one launch
 void compute_lengths(Ctx *c);
 int need_tree(Ctx *c, bool lens);
 int run_scan(Ctx *c);
@@ -247,6 +256,9 @@ void free_reps(Ctx *c);
 // ---- kernel launchers (fitch_kernels.cu) -------------------------------------------------
 int launch_compress(Ctx *c);
 int launch_level(Ctx *c, const Triple *d_triples, int ntriples);
+int launch_wave(Ctx *c, const Triple *d_list, int nlevels, int hdr, int total, uint32_t *d_wcount);
+int wave_slot_cap(int S);
+size_t wave_smem_bytes(int S, int entries);      // dynamic shared memory of k_fitch_wave for a list of `entries` Triples
 int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out);
 int launch_scan(Ctx *c, int task0, int ntasks, int nslots);
 int launch_scan_rows(Ctx *c, int ntasks, int nslots);

@@ -221,3 +221,23 @@ def test_replicate_reweighting_search_matches_oracle():
         ret, bn, bs, nins = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, 6)
         assert ret == want and portlib.rng_draws() == draws
         assert np.array_equal(bn[3:], wring[0][3:]) and np.array_equal(bs[3:], wring[1][3:])
+
+
+@pytest.mark.parametrize("n,L,dt,seed", [(60, 5000, 1, 51), (40, 1200, 2, 52), (30, 700, 6, 53), (24, 600, 0, 54)])
+def test_incremental_view_update_equals_full_recompute(n, L, dt, seed):
+    """After every applied move the search recomputes only the stale directed views (k_fitch_wave, one
+    launch).  What it leaves in the context must be, word for word and length for length, what a fresh
+    mpgpu_set_tree of the final tree computes (k_fitch_level, every view)."""
+    c = make_case(n, L, dt, seed)
+    eng = _engine(c["codes"], c["weights"], dt)
+    portlib.seed_rng(seed)
+    ret, bn, bs, nins = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, 6)
+    refs = [(node, slot) for node in range(n + 1, 2 * n - 1) for slot in range(3)]
+    inc_len = [eng.view_length(node, slot) for node, slot in refs]
+    inc_planes = [eng.view_planes(node, slot) for node, slot in refs]
+    inc_score = eng.tree_score()
+    eng.set_tree(bn, bs)
+    assert eng.tree_score() == inc_score == ret
+    assert inc_len == [eng.view_length(node, slot) for node, slot in refs]
+    for (node, slot), p in zip(refs, inc_planes):
+        assert np.array_equal(p, eng.view_planes(node, slot)), (node, slot)
