@@ -111,6 +111,67 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]["bytes"])
+    except Exception:
+        return None
+
+
+def bench_search(eng, case, args):
+    """Whole plain SPR search (pllOptimizeSprParsimony) from the workload's random tree through the C-ABI with
+    host ring tables in and out -- the call MPBoot makes -- next to the reference's own search on one host core
+    (same start, same RNG stream; score, draw count and final tree must be identical)."""
+    import ctypes as C
+    from oracle import portlib, reflib
+    use_ref = reflib.available()
+    if use_ref:
+        L_ = reflib.lib()
+        seed_fn, draws_fn = L_.mpref_seed_rng, L_.mpref_rng_draws
+        fn = C.cast(L_.mpref_random_double, C.c_void_p).value
+    else:
+        seed_fn, draws_fn, fn = portlib.seed_rng, portlib.rng_draws, portlib.rng_fn_address()
+    best = None
+    for _ in range(3):
+        seed_fn(1234)
+        t0 = time.time()
+        r, bn, bs, nins = eng.optimize_spr(case["bn"], case["bs"], fn, 1, args.maxtrav)
+        dt = time.time() - t0
+        if best is None or dt < best:
+            best = dt
+    draws = int(draws_fn())
+    out = {"what": "mpgpu_optimize_spr from the random tree to convergence, host buffers (e2e), best of 3",
+           "wall_s": best, "insertions": int(nins), "insertions_per_s": nins / best, "final_score": int(r), "rng_draws": draws}
+    # N1: the refinement loop of optimizeBootTrees over resident codes, from the search's final tree
+    Bref = 20
+    boot = make_replicates(case, Bref, seed=9)
+    tbn = np.tile(bn, (Bref, 1)); tbs = np.tile(bs, (Bref, 1))
+    seed_fn(99)
+    t0 = time.time()
+    sc, _, _, rins = eng.refine_replicates(boot, tbn, tbs, fn, 1, args.maxtrav)
+    dt = time.time() - t0
+    out["refine"] = {"what": "mpgpu_refine_replicates: %d bootstrap replicates re-weighted over the resident codes and hill-climbed from the search's final tree" % Bref,
+                     "wall_s": dt, "replicates_per_s": Bref / dt, "insertions": int(rins), "insertions_per_s": rins / dt}
+    eng.set_tree(case["bn"], case["bs"])
+    if not args.no_cpu_baseline and args.workload in ("c2", "c3", "c5", "tiny"):
+        if use_ref:
+            ref = reflib.RefEngine(case["chars"], case["weights"], case["datatype"], n_informative=case["n_inf"]); kind = "reference"
+        else:
+            ref = portlib.OracleEngine(case["codes"], case["weights"], case["datatype"]); kind = "port"
+        ref.set_ring(case["bn"], case["bs"])
+        seed_fn(1234)
+        t0 = time.time()
+        r_ref = ref.optimize_spr(1, args.maxtrav, bb=False)
+        dt = time.time() - t0
+        bn_ref, bs_ref = ref.get_ring()
+        same = bool(r_ref == r and int(draws_fn()) == draws and np.array_equal(bn[3:], bn_ref[3:]) and np.array_equal(bs[3:], bs_ref[3:]))
+        out["cpu_baseline"] = {"wall_s": dt, "cores": 1, "kind": kind, "final_score": int(r_ref), "identical_result": same,
+                               "sample": "the whole search (pllOptimizeSprParsimony), single-threaded code"}
+        out["speedup_vs_one_core"] = dt / best
+    return out
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -224,7 +285,7 @@ def bench_bb(eng, case, order, vb, n_cand, args, flush):
                      "peak_source": "2 x %s bf16_tflops (no int8 figure is measured; nominal dense int8 is 4500)"
                                     % ("MEASURED_PEAKS.json" if peak_bf16 else "fallback"),
                      "kernel_ms": tc, "shape": "%d rows x %d patterns x %d replicates, K splits %d" % (rows, pat, B, splits),
-                     "algorithmic_ops_per_launch": ops, "traffic": None},
+                     "algorithmic_ops_per_launch": ops, "traffic": measured_traffic(args.workload, "k_reps_tc")},
     }
     # the whole -bb SPR search from the same random tree, cutoff off
     from mpboot_b200.engine import HostRng, Treels
@@ -474,13 +535,16 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB memset)",
                        "parallelism": "pattern-sharded x%d, NCCL all-reduce of int32 counts" % world if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_spr_scan", "peak_source": peak_src,
+                         "traffic": measured_traffic(args.workload, "k_spr_scan") if world == 1 else None,
+                         "kernel": "k_spr_scan", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker_s * 1e3},
             "e2e": {"value": (n_cand / e2e_s) * ops_per_ins, "unit": UNIT, "insertions_per_s": n_cand / e2e_s,
                     "h2d_bytes_per_step": None, "d2h_bytes_per_step": 4 * (n_cand + 2 * nvis), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
         }
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
+        if world == 1 and not args.no_search:
+            line["search"] = bench_search(eng, case, args)
         if world == 1 and not args.no_bb:
             bb, boot, seg = bench_bb(eng, case, order, vb, n_cand, args, flush)
             if not args.no_cpu_baseline:
@@ -507,6 +571,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bb", action="store_true", help="skip the -bb (replicate scoring) section")
+    ap.add_argument("--no-search", action="store_true", help="skip the whole-search (pllOptimizeSprParsimony) section")
     ap.add_argument("--replicates", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -156,6 +156,20 @@ int mpgpu_optimize_spr(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot,
                        int mintrav, int maxtrav, mpgpu_rng_fn rng, void *rng_user,
                        uint32_t *best, int64_t *n_insertions);
 
+/* ---- R12 / N1: the refinement loop of IQTree::optimizeBootTrees, default policy (iqtree.cpp:2795-2862) ----
+ * For sample = 0 .. B-1, in order: the alignment is re-weighted with boot_samples[sample]
+ * (Alignment::modifyPatternFreq, alignment.cpp:117 -- here: new frequencies over the codes that are
+ * already resident, no alignment re-creation, no PHYLIP/newick round trip), the replicate's tree
+ * (ring tables, trees_bn/trees_bs[sample][3*(2n-1)], modified in place) is hill-climbed with
+ * pllOptimizeSprParsimony (doNNISearch -> :3244, radius maxtrav = params->spr_maxtrav or
+ * opt_btree_spr), and scores[sample] receives its return value.  rng is the host's random_double();
+ * the draws of consecutive samples are consumed in order, exactly as the reference's sequential
+ * loop does, so the refined trees and scores are the reference's.  The caller maps the trees
+ * to treels indices (:2847-2858).  The original frequencies are restored before returning. */
+int mpgpu_refine_replicates(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples, int stride,
+                            int32_t *trees_bn, int32_t *trees_bs, int mintrav, int maxtrav,
+                            mpgpu_rng_fn rng, void *rng_user, uint32_t *scores, int64_t *n_insertions);
+
 /* ---- R7: _pllComputeRandomizedStepwiseAdditionParsimonyTree (sprparsimony.cpp:3224, 3107, 2977) ----
  * Builds a randomized-stepwise-addition tree over the loaded alignment and runs the SPR rounds
  * of _pllMakeParsimonyTreeFast on it (radius spr_dist).  *random_seed is tr->randomNumberSeed

@@ -93,7 +93,7 @@ static int build_planes(Ctx *c, bool realloc_views)
     int64_t glob = (words + quantum - 1) / quantum * quantum;
     if (glob == 0) glob = quantum;
     const int newWl = (int)(glob / c->shard_count);
-    if (newWl != c->Wl || glob != c->glob_words) realloc_views = true;
+    (void)realloc_views;
     c->glob_words = (int)glob; c->Wl = newWl; c->w0 = (int64_t)c->shard_rank * newWl;
     {
         const int SG = c->S < 4 ? c->S : 4, G = (c->S + SG - 1) / SG;
@@ -108,12 +108,14 @@ static int build_planes(Ctx *c, bool realloc_views)
     MPGPU_CUDA(cudaMemcpyAsync(c->d_inf_ptn, inf_ptn.data(), sizeof(int32_t) * inf_ptn.size(), cudaMemcpyHostToDevice, c->stream));
 
     const size_t nviews = (size_t)(4 * c->n - 6);
-    if (realloc_views || !c->d_views) {
+    const size_t need = nviews * c->view_stride;
+    if (!c->d_views || need > c->views_alloc) {              // re-weighting (replicates, ratchet) keeps the allocation
         if (c->d_views) cudaFree(c->d_views);
         if (c->d_vcount) cudaFree(c->d_vcount);
-        c->d_views = nullptr; c->d_vcount = nullptr;
-        MPGPU_CUDA(cudaMalloc((void **)&c->d_views, nviews * c->view_stride * sizeof(uint32_t)));
+        c->d_views = nullptr; c->d_vcount = nullptr; c->views_alloc = 0;
+        MPGPU_CUDA(cudaMalloc((void **)&c->d_views, need * sizeof(uint32_t)));
         MPGPU_CUDA(cudaMalloc((void **)&c->d_vcount, nviews * sizeof(uint32_t)));
+        c->views_alloc = need;
     }
     if (c->n_inf > 0) { if (int rc = launch_compress(c)) return rc; }
     else MPGPU_CUDA(cudaMemsetAsync(c->d_views, 0xff, (size_t)c->n * c->view_stride * sizeof(uint32_t), c->stream));

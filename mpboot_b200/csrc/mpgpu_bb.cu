@@ -691,6 +691,33 @@ int mpgpu_optimize_spr(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int
     return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, rng, rng_user, nullptr, best, n_insertions);
 }
 
+int mpgpu_refine_replicates(mpgpu_ctx *c, int B, const uint16_t *boot_samples, int stride,
+                            int32_t *trees_bn, int32_t *trees_bs, int mintrav, int maxtrav,
+                            mpgpu_rng_fn rng, void *rng_user, uint32_t *scores, int64_t *n_insertions)
+{
+    if (!c || !boot_samples || !trees_bn || !trees_bs || !rng || !scores) { set_error("null argument"); return 1; }
+    if (!c->d_views) { set_error("no alignment loaded"); return 1; }
+    if (B < 0 || stride < c->P) { set_error("boot_samples stride is smaller than the number of patterns"); return 1; }
+    const std::vector<int32_t> saved = c->weights;
+    const size_t ring = (size_t)3 * (2 * c->n - 1);
+    std::vector<int32_t> w(c->P);
+    int64_t total = 0;
+    int rc = 0;
+    for (int b = 0; b < B && !rc; b++) {
+        const uint16_t *row = boot_samples + (size_t)b * stride;
+        for (int i = 0; i < c->P; i++) w[i] = row[i];
+        c->tree_set = false;                               // the planes change: no view of the previous sample survives
+        if ((rc = mpgpu_set_weights(c, w.data()))) break;
+        int64_t ins = 0;
+        rc = optimize_impl(c, trees_bn + b * ring, trees_bs + b * ring, mintrav, maxtrav, rng, rng_user, nullptr, scores + b, &ins);
+        total += ins;
+    }
+    c->tree_set = false;
+    if (int rc2 = mpgpu_set_weights(c, saved.data())) { if (!rc) rc = rc2; }
+    if (n_insertions) *n_insertions = total;
+    return rc;
+}
+
 int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state, uint32_t *best, int64_t *n_insertions)
 {

@@ -183,6 +183,7 @@ struct Ctx {
     // views
     uint32_t *d_views = nullptr;          // [4n-6][S][Wl]
     size_t view_stride = 0;               // S*Wl
+    size_t views_alloc = 0;               // words allocated behind d_views
     uint32_t *d_vcount = nullptr;         // [4n-6] mismatch count of each view (this shard)
     std::vector<uint32_t> vcount;         // host copy (all-reduced when sharded)
     std::vector<uint32_t> vlen;           // subtree length of each view

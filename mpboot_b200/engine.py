@@ -60,6 +60,7 @@ def lib():
     L.mpgpu_scan_finish.argtypes = [vp, vp, vp, vp, vp, i32]
     L.mpgpu_optimize_spr.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.mpgpu_stepwise_addition.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.mpgpu_refine_replicates.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
     L.mpgpu_load_replicates.argtypes = [vp, i32, vp, i32, vp, i32]
     L.mpgpu_load_replicates2.argtypes = [vp, i32, vp, i32, vp, i32, vp]
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
@@ -301,6 +302,21 @@ class Engine:
                                            C.c_void_p(rng_fn_ptr), C.c_void_p(rng_user) if rng_user else None,
                                            C.byref(best), C.byref(nins)))
         return best.value, bn, bs, nins.value
+
+    def refine_replicates(self, boot, trees_bn, trees_bs, rng_fn_ptr, mintrav=1, maxtrav=6, rng_user=None):
+        """The default-policy loop of IQTree::optimizeBootTrees: replicate b = frequencies boot[b] over the
+        resident codes + its tree (ring tables, rows of trees_bn/trees_bs).  Returns (scores, trees_bn,
+        trees_bs, insertions scored)."""
+        boot = np.ascontiguousarray(boot, dtype=np.uint16)
+        B, stride = boot.shape
+        tbn = np.array(trees_bn, dtype=np.int32, copy=True).reshape(B, -1)
+        tbs = np.array(trees_bs, dtype=np.int32, copy=True).reshape(B, -1)
+        assert tbn.shape[1] == 3 * (2 * self.n - 1)
+        scores = np.zeros(B, dtype=np.uint32); nins = C.c_int64()
+        self._ck(self.L.mpgpu_refine_replicates(self.h, B, _p(boot), stride, _p(tbn), _p(tbs), mintrav, maxtrav,
+                                                C.c_void_p(rng_fn_ptr), C.c_void_p(rng_user) if rng_user else None,
+                                                _p(scores), C.byref(nins)))
+        return scores, tbn, tbs, nins.value
 
     # -- R7
     def stepwise_addition(self, seed, spr_dist, rng_fn_ptr, rng_user=None):

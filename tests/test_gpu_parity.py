@@ -241,3 +241,38 @@ def test_incremental_view_update_equals_full_recompute(n, L, dt, seed):
     assert inc_len == [eng.view_length(node, slot) for node, slot in refs]
     for (node, slot), p in zip(refs, inc_planes):
         assert np.array_equal(p, eng.view_planes(node, slot)), (node, slot)
+
+
+@pytest.mark.parametrize("n,L,dt,seed", [(36, 2500, 1, 81), (28, 900, 2, 82)])
+def test_refine_replicates_matches_sequential_reference_loop(n, L, dt, seed):
+    """N1 (IQTree::optimizeBootTrees default policy, iqtree.cpp:2795-2862): B replicates refined in one
+    call over the resident codes == the reference's sequential loop (re-weight, re-allocate, hill-climb),
+    one RNG stream running through all replicates."""
+    from tests.helpers import make_boot
+    c = make_case(n, L, dt, seed)
+    B = 5
+    boot = make_boot(c, B, seed)
+    boot[1, :7] = 0                                           # zero-frequency patterns drop out of the planes
+    o = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    o.set_ring(c["bn"], c["bs"]); o.allocate(False)
+    portlib.seed_rng(5)
+    o.optimize_spr(1, 6, bb=False)
+    start = o.get_ring()                                      # the replicates' trees: one good tree and the raw one
+    trees_bn = np.stack([start[0] if b % 2 == 0 else c["bn"] for b in range(B)]).astype(np.int32)
+    trees_bs = np.stack([start[1] if b % 2 == 0 else c["bs"] for b in range(B)]).astype(np.int32)
+    portlib.seed_rng(77)
+    want_scores, want_rings = [], []
+    for b in range(B):
+        o.set_weights(boot[b].astype(np.int32)); o.set_ring(trees_bn[b], trees_bs[b]); o.allocate(False)
+        want_scores.append(o.optimize_spr(1, 6, bb=False))
+        want_rings.append(o.get_ring())
+    draws = portlib.rng_draws()
+    eng = _engine(c["codes"], c["weights"], dt, c["bn"], c["bs"])
+    s0 = eng.tree_score()
+    portlib.seed_rng(77)
+    scores, tbn, tbs, nins = eng.refine_replicates(boot, trees_bn, trees_bs, portlib.rng_fn_address(), 1, 6)
+    assert list(scores) == want_scores and portlib.rng_draws() == draws and nins > 0
+    for b in range(B):
+        assert np.array_equal(tbn[b][3:], want_rings[b][0][3:]) and np.array_equal(tbs[b][3:], want_rings[b][1][3:]), b
+    eng.set_tree(c["bn"], c["bs"])                            # original frequencies are back
+    assert eng.tree_score() == s0
