@@ -171,6 +171,7 @@ static inline int2 kid_pair(const Triple &tr) { return tr.a < tr.b ? make_int2(t
 int compute_views(Ctx *c)
 {
     const int nviews = 4 * c->n - 6;
+    c->wave_pending = 0;
     build_schedule(c);
     const size_t total = c->sched.size();
     const int nl = c->sched_levels;
@@ -202,9 +203,12 @@ int compute_views(Ctx *c)
 // them is stale -- about half of the views, in a forest as deep as the tree.  They are
 // recomputed by ONE k_fitch_wave launch; the mismatch counts of the stale views come back
 // compact.  Needs complete counts on every shard (all-reduce callback) like compute_lengths.
-int update_views(Ctx *c)
+// defer = true: nothing is waited for; the counts are scattered by settle_views() after the caller's next
+// stream synchronize (the search loop plans and launches the next scan batch in the meantime).
+int update_views(Ctx *c, bool defer)
 {
     const int nviews = 4 * c->n - 6;
+    c->wave_pending = 0;
     if (!c->kids_valid || (int)c->view_kids.size() != nviews || (int)c->vcount.size() != nviews ||
         (c->shard_count > 1 && !c->allreduce) || getenv("MPGPU_NO_WAVE"))
         return compute_views(c);
@@ -268,9 +272,10 @@ int update_views(Ctx *c)
     c->reps.tree_valid = false;
     if (c->shard_count > 1) { if (int rc = shard_sum(c, c->d_wcount, (int64_t)total)) return rc; }
     MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->wave_pending = (int)total; c->wave_hdr = hdr;
+    if (defer) return 0;
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-    const uint32_t *wc = c->wcount_pin.data();
-    for (size_t i = 0; i < total; i++) c->vcount[dst[i].dst] = wc[i];
+    settle_views(c, false);
     if (prof) {
         const auto p2 = std::chrono::steady_clock::now();
         t_host += std::chrono::duration<double>(p1 - p0).count(); t_dev += std::chrono::duration<double>(p2 - p1).count();
@@ -280,6 +285,17 @@ int update_views(Ctx *c)
                     n_calls, 1e6 * t_host / n_calls, 1e6 * t_dev / n_calls, (double)n_triples / n_calls, (double)n_levels / n_calls);
     }
     return 0;
+}
+
+// after a stream synchronize: the counts of a deferred update_views land in vcount (and vlen)
+void settle_views(Ctx *c, bool lengths)
+{
+    if (!c->wave_pending) return;
+    const Triple *list = c->wave_pin.data() + c->wave_hdr;
+    const uint32_t *wc = c->wcount_pin.data();
+    for (int i = 0; i < c->wave_pending; i++) c->vcount[list[i].dst] = wc[i];
+    c->wave_pending = 0;
+    if (lengths) compute_lengths(c);
 }
 
 // subtree lengths from (all-reduced) mismatch counts, children before parents
@@ -358,6 +374,12 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
     }
     MPGPU_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counts, nout * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    settle_views(c, true);
+    if (!c->lens_valid) { set_error("view lengths not set"); return 1; }
+    const size_t ntasks = pl.tasks.size();
+    pl.task_const.resize(ntasks);
+    for (size_t k = 0; k < ntasks; k++)                 // len(S) + len(D1) + len(D2)
+        pl.task_const[k] = c->vlen[pl.task_vids[3 * k]] + c->vlen[pl.task_vids[3 * k + 1]] + c->vlen[pl.task_vids[3 * k + 2]];
     const int32_t *base = c->h_counts, *cnt = c->h_counts + pl.task_cap;
     const int32_t *ctask = pl.cand_task.data();
     const uint32_t *tconst = pl.task_const.data();
@@ -378,7 +400,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
     ScanPlan &pl = c->plan;
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
     ScanPlanner planner;
-    if (int rc = planner.begin(c->tree, c->vlen, order, first, count, mintrav, maxtrav, vstride_vec, pl)) return rc;
+    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl)) return rc;
     if (int rc = reserve_plan(c)) return rc;
     MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, ((size_t)pl.task_cap + pl.cand_ref.size() + 1) * sizeof(int32_t), c->stream));
     int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep): 1: 0.338 ms, 2: 0.316 ms, 4: 0.337 ms, 6: 0.390 ms e2e
@@ -727,7 +749,7 @@ int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, in
     if (!order || first < 1 || count < 0 || first + count > 2 * c->n - 1) { set_error("bad visit range"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
-    if (int rc = build_scan_plan(c->tree, c->vlen, order, first, count, mintrav, maxtrav, vstride_vec, c->plan)) return rc;
+    if (int rc = build_scan_plan(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, c->plan)) return rc;
     if (int rc = upload_plan(c)) return rc;
     if (n_cand) *n_cand = c->plan.n_cand;
     if (n_tasks) *n_tasks = (int)c->plan.tasks.size();

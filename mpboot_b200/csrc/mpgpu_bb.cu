@@ -526,9 +526,11 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             prof.stop(3);
             if (moved) {
                 prof.start();
+                // the stale views are recomputed behind the host's back: the next batch is planned and launched
+                // while k_fitch_wave runs, and its counts land with that batch's read-back (finish_scan)
                 c->tree_set = true; c->lens_valid = false;
-                if (int rc = update_views(c)) return rc;
-                compute_lengths(c);
+                if (int rc = update_views(c, true)) return rc;
+                if (!c->wave_pending) compute_lengths(c);
                 batch = 16;
                 prof.stop(4);
             } else {
@@ -536,6 +538,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             }
         }
     } while (randomMP < startMP);
+    if (c->wave_pending) { MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, true); }
     prof.report(prof_names, 5);
     g_rp.report(g_rp_names, 8);
     for (int k = 0; k < 8; k++) { g_rp.t[k] = 0; g_rp.n[k] = 0; }
@@ -634,6 +637,7 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         e = cudaMemcpyAsync(ins.data(), d_ins, (size_t)ne * 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "stepwise addition read-back"); break; }
+        settle_views(c, true);                                                    // counts of the previous step's view update
         // stepwiseAddition(tr, pr, q, f->back): pre-order, children only below a subtree of positive length
         best = 2147483647u;                                                       // tr->bestParsimony = INT_MAX :3141
         int insert_ref = 0;
@@ -656,8 +660,12 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         t.hookup(q + 2, r);
         treelen = best;
         c->lens_valid = false;
-        if ((rc = update_views(c))) break;
-        compute_lengths(c);
+        if ((rc = update_views(c, true))) break;                                  // settled after the next step's read-back
+        if (!c->wave_pending) compute_lengths(c);
+    }
+    if (!rc && c->wave_pending) {
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "stepwise addition");
+        else settle_views(c, true);
     }
     if (d_edges) cudaFree(d_edges);
     if (d_ins) cudaFree(d_ins);

@@ -89,7 +89,8 @@ struct ScanPlan {
     std::vector<ScanTask> tasks;
     std::vector<int32_t> visit_begin;     // count+1
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
-    std::vector<uint32_t> task_const;     // len(S)+len(D1)+len(D2) per task
+    std::vector<int32_t> task_vids;       // view ids of S, D1, D2 per task
+    std::vector<uint32_t> task_const;     // len(S)+len(D1)+len(D2) per task (filled by finish_scan from the view lengths)
     int n_cand = 0;                      // candidates / ops actually used (the vectors are sized to an upper bound)
     int n_ops = 0;
     int max_slot = 0;
@@ -197,6 +198,7 @@ struct Ctx {
     // incremental update after a move (update_views): children of every view at its last compute
     std::vector<int2> view_kids; bool kids_valid = false;
     PinnedArray<Triple> wave_pin; PinnedArray<uint32_t> wcount_pin;
+    int wave_pending = 0, wave_hdr = 0;   // deferred update_views: counts in flight (settle_views after the next synchronize)
     Triple *d_wave = nullptr; size_t wave_cap = 0;
     uint32_t *d_wcount = nullptr; size_t wcount_cap = 0;
     uint32_t *d_scalar = nullptr;         // small scratch for scalar results
@@ -243,7 +245,8 @@ static inline int ensure(T *&ptr, size_t &cap, size_t need)
 // ---- shared host helpers (mpgpu_api.cu) -----------------------------------------------------
 int shard_sum(Ctx *c, void *dev_i32, int64_t count);   // in-place int32 all-reduce over the shards (no-op for one shard)
 int compute_views(Ctx *c);
-int update_views(Ctx *c);        // after apply_spr_move on c->tree: recompute only the stale views, one launch
+int update_views(Ctx *c, bool defer = false);   // after apply_spr_move on c->tree: recompute only the stale views, one launch
+void settle_views(Ctx *c, bool lengths);        // after a stream synchronize: land the counts of a deferred update_views
 void compute_lengths(Ctx *c);
 int need_tree(Ctx *c, bool lens);
 int run_scan(Ctx *c);
@@ -287,7 +290,7 @@ class ScanPlanner {                      // incremental form of build_scan_plan 
 public:
     ScanPlanner();
     ~ScanPlanner();
-    int begin(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order, int first, int count,
+    int begin(const HostTree &t, const int32_t *order, int first, int count,
               int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan);
     void add(int v0, int v1);
     void finish();
@@ -297,7 +300,7 @@ private:
     ScanPlanner(const ScanPlanner &);
     ScanPlanner &operator=(const ScanPlanner &);
 };
-int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
+int build_scan_plan(const HostTree &t, const int32_t *order,
                     int first, int count, int mintrav, int maxtrav, uint32_t vstride_vec, ScanPlan &plan);
 void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);
 

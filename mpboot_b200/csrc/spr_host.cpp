@@ -119,21 +119,20 @@ struct Builder {
 struct ScanPlanner::Impl {
     Builder b;
     const HostTree &t;
-    const std::vector<uint32_t> &vlen;
     const int32_t *order;
     int first, mintrav, maxtrav;
-    Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const std::vector<uint32_t> &vl, const int32_t *ord,
-         int f, int mi, int ma) : b(tt, plan, vstride), t(tt), vlen(vl), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
+    Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const int32_t *ord,
+         int f, int mi, int ma) : b(tt, plan, vstride), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
 };
 
 ScanPlanner::ScanPlanner() : impl(nullptr) {}
 ScanPlanner::~ScanPlanner() { delete impl; }
 
-int ScanPlanner::begin(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order, int first, int count,
+int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int count,
                        int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan)
 {
     delete impl; impl = nullptr;
-    plan.tasks.clear(); plan.visit_begin.clear(); plan.task_const.clear();
+    plan.tasks.clear(); plan.visit_begin.clear(); plan.task_vids.clear();
     plan.n_cand = 0; plan.n_ops = 0; plan.max_slot = 0;
     plan.task_cap = 2 * count;
     const int n = t.n;
@@ -141,7 +140,7 @@ int ScanPlanner::begin(const HostTree &t, const std::vector<uint32_t> &vlen, con
     if (maxtrav > n - 3) maxtrav = n - 3;                       // :2275 (tr->ntips == mxtips during the search)
     if (maxtrav > kMaxTrav) { set_error("maxtrav exceeds the scan kernel's stack depth"); return 1; }   // slots < 0xFE
     if ((uint64_t)(4 * n - 6) * vstride >= 0x7fffffffULL) { set_error("view array too large for 32-bit scan offsets"); return 1; }
-    impl = new Impl(t, plan, vstride, vlen, order, first, mintrav, maxtrav);
+    impl = new Impl(t, plan, vstride, order, first, mintrav, maxtrav);
     Builder &b = impl->b;
     // upper bounds: one side of a visit reaches at most 4 * (2^maxtrav - 1) branches, never more than the tree has
     const size_t per_side = std::min<size_t>((size_t)4 << std::max(maxtrav, 0), (size_t)2 * n);
@@ -162,7 +161,6 @@ void ScanPlanner::add(int v0, int v1)
     Builder &b = impl->b;
     ScanPlan &plan = b.plan;
     const HostTree &t = impl->t;
-    const std::vector<uint32_t> &vlen = impl->vlen;
     const int mintrav = impl->mintrav, maxtrav = impl->maxtrav;
     for (int v = v0; v < v1; v++) {
         plan.visit_begin.push_back(b.ncand);
@@ -182,7 +180,7 @@ void ScanPlanner::add(int v0, int v1)
                 if (!b.tip[p2]) b.expand_top(p2, 0xFEu, mintrav, maxtrav);
                 task.op_end = b.nops;
                 plan.tasks.push_back(task);
-                plan.task_const.push_back(vlen[t.vid(q)] + vlen[t.vid(p1)] + vlen[t.vid(p2)]);
+                plan.task_vids.push_back(t.vid(q)); plan.task_vids.push_back(t.vid(p1)); plan.task_vids.push_back(t.vid(p2));
             }
         }
         if (!b.tip[q] && maxtrav > 0) {                         // :2333
@@ -200,7 +198,7 @@ void ScanPlanner::add(int v0, int v1)
                 if (!b.tip[q2]) b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
                 task.op_end = b.nops;
                 plan.tasks.push_back(task);
-                plan.task_const.push_back(vlen[t.vid(p)] + vlen[t.vid(q1)] + vlen[t.vid(q2)]);
+                plan.task_vids.push_back(t.vid(p)); plan.task_vids.push_back(t.vid(q1)); plan.task_vids.push_back(t.vid(q2));
             }
         }
     }
@@ -213,11 +211,11 @@ void ScanPlanner::finish()
     plan.visit_begin.push_back(plan.n_cand);
 }
 
-int build_scan_plan(const HostTree &t, const std::vector<uint32_t> &vlen, const int32_t *order,
+int build_scan_plan(const HostTree &t, const int32_t *order,
                     int first, int count, int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan)
 {
     ScanPlanner pl;
-    if (int rc = pl.begin(t, vlen, order, first, count, mintrav, maxtrav, vstride, plan)) return rc;
+    if (int rc = pl.begin(t, order, first, count, mintrav, maxtrav, vstride, plan)) return rc;
     pl.add(0, count);
     pl.finish();
     return 0;

@@ -89,6 +89,45 @@ def evolve_alignment(n, nsites, datatype, mu, seed, gap=0.01, amb=0.001):
     return chars
 
 
+def evolve_alignment_blocked(n, nsites, datatype, mu, seed, gap=0.01, amb=0.001, block=1 << 17):
+    """The same model as evolve_alignment for alignments too large for its n x nsites float temporaries
+    (C4: 1000 x 1 000 000): the topology (sequence of leaf splits) is drawn first, then the sites are
+    evolved down it block by block.  A different random stream than evolve_alignment -- only the bench's
+    large workloads use it."""
+    rng = np.random.default_rng(seed)
+    S = STATES[datatype]
+    alpha = np.frombuffer(ALPHABET[datatype], dtype=np.uint8)
+    splits, live = [], 1
+    while live < n:
+        splits.append(int(rng.integers(live)))
+        live += 1
+    order = rng.permutation(n)
+    codes = np.frombuffer(AMBIGUITY[datatype], dtype=np.uint8) if datatype in AMBIGUITY else None
+    chars = np.empty((n, nsites), dtype=np.uint8)
+    for s0 in range(0, nsites, block):
+        m = min(block, nsites - s0)
+        seqs = [rng.integers(0, S, size=m, dtype=np.uint8)]
+        for k in splits:
+            parent = seqs.pop(k)
+            for _ in range(2):
+                child = parent.copy()
+                hit = rng.random(m, dtype=np.float32) < mu
+                nh = int(hit.sum())
+                if nh:
+                    child[hit] = (child[hit] + rng.integers(1, S, size=nh, dtype=np.uint8)) % S
+                seqs.append(child)
+        blk = np.empty((n, m), dtype=np.uint8)
+        for i, k in enumerate(order):
+            blk[i] = alpha[seqs[int(k)]]
+        if gap > 0:
+            blk[rng.random((n, m), dtype=np.float32) < gap] = ord("-")
+        if amb > 0 and codes is not None:
+            msk = rng.random((n, m), dtype=np.float32) < amb
+            blk[msk] = codes[rng.integers(0, len(codes), size=int(msk.sum()))]
+        chars[:, s0:s0 + m] = blk
+    return chars
+
+
 def compress_patterns(chars):
     """Unique columns (in order of first appearance) and their frequencies:
     the Alignment::addPattern step of the host (alignment.cpp), restated with numpy."""
