@@ -31,6 +31,12 @@ int  mporacle_optimize_spr(mporacle *o, int mintrav, int maxtrav, int bb);
 unsigned mporacle_ras(mporacle *o, long seed, int spr_dist);
 unsigned long mporacle_sweep_count_insertions(mporacle *o, int mintrav, int maxtrav, int per_site, int reps);
 
+/* Sankoff (-cost) */
+int  mporacle_set_cost_matrix(mporacle *o, const unsigned *cost, const int *segment_upper, int nseg);
+int  mporacle_get_sankoff_vect(mporacle *o, int node, uint16_t *out);
+void mporacle_set_best(mporacle *o, unsigned best);
+int  mporacle_remainder_bounds(mporacle *o, unsigned *out);
+
 double mporacle_random_double(void *unused);
 void mporacle_seed_rng(uint64_t seed);
 uint64_t mporacle_rng_draws(void);

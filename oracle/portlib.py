@@ -62,6 +62,10 @@ def lib():
         L.mporacle_undetermined.argtypes = [i]
         L.mporacle_reps.argtypes = [vp, vp, i, i, vp, i, vp]
         L.mporacle_segments.argtypes = [vp, vp, i, i, vp]
+        L.mporacle_set_cost_matrix.argtypes = [vp, vp, vp, i]
+        L.mporacle_get_sankoff_vect.argtypes = [vp, i, vp]
+        L.mporacle_set_best.argtypes = [vp, C.c_uint]
+        L.mporacle_remainder_bounds.argtypes = [vp, vp]
         from .reflib import _boot_protos
         _boot_protos(L, "mporacle")
         _lib = L
@@ -136,6 +140,26 @@ class OracleEngine(BootMixin):
     def allocate(self, per_site=False):
         self.W = lib().mporacle_allocate(self.h, int(per_site))
         return self.W
+
+    # ---- Sankoff (-cost)
+    def set_cost_matrix(self, cost, segment_upper):
+        if cost is None:
+            return lib().mporacle_set_cost_matrix(self.h, None, None, 0)
+        c = np.ascontiguousarray(cost, dtype=np.uint32); seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
+        return lib().mporacle_set_cost_matrix(self.h, _p(c), _p(seg), len(seg))
+
+    def sankoff_vect(self, node):
+        out = np.zeros((self.W, self.S), dtype=np.uint16)
+        lib().mporacle_get_sankoff_vect(self.h, node, _p(out))
+        return out
+
+    def set_best(self, best):
+        lib().mporacle_set_best(self.h, int(best))
+
+    def remainder_bounds(self):
+        out = np.zeros(65536, dtype=np.uint32)
+        k = lib().mporacle_remainder_bounds(self.h, _p(out))
+        return out[:k].copy()
 
     def num_informative(self):
         return lib().mporacle_num_informative(self.h)

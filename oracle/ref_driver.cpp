@@ -26,13 +26,20 @@
 
 extern "C" void pllBaseSubstitute(pllInstance *tr, partitionList *partitions);   /* utils.c:2526 */
 
-/* Sankoff-only helper (parstree.cpp:606) referenced from the -cost branch of
- * _allocateParsimonyDataStructures; never reached because pllCostMatrix stays NULL. */
-int ParsTree::findMstScore(int) { fprintf(stderr, "mpref: Sankoff path not built\n"); abort(); return 0; }
+/* Sankoff-only helper referenced from compressSankoffDNA (sprparsimony.cpp:2809): the weight of a
+ * minimum spanning tree over the unambiguous states present in a pattern, under the cost matrix.
+ * ParsTree lives in parstree.cpp, which cannot be compiled without the whole program, so this is
+ * NOT the reference: it is re-typed from parstree.cpp:606-677 (Prim from the first present state,
+ * ties to the lowest state index) on the PLL codes of the pattern.  An MST's weight does not depend
+ * on the tie-breaking, so any correct MST gives the reference's number. */
+static struct mpref *g_mst_handle = NULL;
+static int mst_score_of_pattern(struct mpref *h, int ptn);
+ParsTree::ParsTree(Alignment *a) { aln = a; }
+int ParsTree::findMstScore(int ptn) { return mst_score_of_pattern(g_mst_handle, ptn); }
 
 /* ---- globals the engine expects from iqtree.cpp / tools.cpp ------------------------- */
 Params *globalParam = NULL;                 /* iqtree.cpp:601 */
-parsimonyNumber *pllCostMatrix = NULL;      /* iqtree.cpp (Sankoff; unused: Fitch only) */
+parsimonyNumber *pllCostMatrix = NULL;      /* iqtree.cpp:  Sankoff cost matrix (-cost), NULL = Fitch */
 int pllCostNstates = 0;
 parsimonyNumber *vectorCostMatrix = NULL;
 int pllRepsSegments = -1;
@@ -69,8 +76,11 @@ struct mpref {
     node *pool;
     std::vector<nodeptr> base;            /* base[i] = ring slot 0 of node i (1..2n-2) */
     std::vector<unsigned char> ybuf;
-    IQTree iq;
+    ParsTree iq;                          /* compressSankoffDNA dynamic_casts iqtree to ParsTree (:2809) */
     Alignment aln;
+    std::vector<parsimonyNumber> cost;    /* Sankoff: this handle's cost matrix and segments (globals point here) */
+    std::vector<int> seg_upper;
+    mpref() : iq((Alignment *)NULL) {}
     Params params;
     /* recorder for the saveCurrentTree up-call */
     std::vector<int> saved_mp;
@@ -187,7 +197,76 @@ MPREF_API mpref *mpref_create(int n, int P, int datatype, const unsigned char *c
     return h;
 }
 
-static void make_current(mpref *h) { globalParam = &h->params; iqtree = &h->iq; }
+static void make_current(mpref *h)
+{
+    globalParam = &h->params; iqtree = &h->iq; g_mst_handle = h;
+    if (!h->cost.empty()) {
+        pllCostMatrix = &h->cost[0]; pllCostNstates = h->states;
+        pllRepsSegments = (int)h->seg_upper.size(); pllSegmentUpper = &h->seg_upper[0];
+    } else {
+        pllCostMatrix = NULL; pllCostNstates = 0;
+    }
+}
+
+/* -cost: what ParsTree::initParsData / IQTree::doSegmenting leave in the globals (pllCostMatrix,
+ * pllCostNstates, pllRepsSegments, pllSegmentUpper) before the engine runs, then initializeCostMatrix
+ * (sprparsimony.cpp:159).  cost[i*S+j] = cost from state i to j.  nseg/segment_upper as doSegmenting. */
+MPREF_API int mpref_set_cost_matrix(mpref *h, const unsigned int *cost, const int *segment_upper, int nseg)
+{
+    if (h->allocated) { make_current(h); _pllFreeParsimonyDataStructures(h->tr, h->pr); h->allocated = false; }
+    if (vectorCostMatrix) { rax_free(vectorCostMatrix); vectorCostMatrix = NULL; }
+    if (!cost) { h->cost.clear(); h->seg_upper.clear(); make_current(h); return 0; }
+    h->cost.assign(cost, cost + (size_t)h->states * h->states);
+    h->seg_upper.assign(segment_upper, segment_upper + nseg);
+    make_current(h);
+    initializeCostMatrix();
+    first_call = true;
+    return (int)highest_cost;
+}
+
+/* Sankoff parsVect of one node as the engine holds it: u16 [parsimonyLength/16][S][16] (:2725-2733) */
+MPREF_API int mpref_get_sankoff_vect(mpref *h, int node, unsigned short *out)
+{
+    size_t L = h->pinfo->parsimonyLength, S = h->states;
+    const unsigned short *v = (const unsigned short *)&h->pinfo->parsVect[L * S * (size_t)node];
+    memcpy(out, v, L * S * sizeof(unsigned short));
+    return (int)L;
+}
+MPREF_API void mpref_set_best(mpref *h, unsigned int best) { h->tr->bestParsimony = best; }
+MPREF_API int mpref_remainder_bounds(mpref *h, unsigned int *out)
+{
+    (void)h;
+    if (!pllRemainderLowerBounds) return 0;
+    for (int i = 0; i < pllRepsSegments - 1; i++) out[i] = pllRemainderLowerBounds[i];
+    return pllRepsSegments - 1;
+}
+
+static int mst_score_of_pattern(mpref *h, int ptn)
+{
+    const int S = h->states;
+    const unsigned int *bv = getBitVector(h->datatype);
+    std::vector<char> present(S, 0);
+    for (int t = 1; t <= h->n; t++) {
+        unsigned int m = bv[h->tr->yVector[t][ptn]];
+        if (m && !(m & (m - 1))) present[__builtin_ctz(m)] = 1;      /* pat[j] < num_states: unambiguous only */
+    }
+    int cnt = 0;
+    for (int i = 0; i < S; i++) cnt += present[i];
+    if (cnt <= 1) return 0;
+    std::vector<unsigned int> label(S, UINT_MAX);
+    std::vector<char> added(S, 0);
+    for (int c = 0; c < S; c++) if (present[c]) { label[c] = 0; break; }
+    unsigned int score = 0;
+    for (int it = 0; it < cnt; it++) {
+        int add = -1; unsigned int best = UINT_MAX;
+        for (int c = 0; c < S; c++) if (present[c] && !added[c] && label[c] < best) { best = label[c]; add = c; }
+        if (add < 0) break;
+        added[add] = 1; score += label[add];
+        for (int c = 0; c < S; c++)
+            if (present[c] && !added[c] && label[c] > h->cost[(size_t)add * S + c]) label[c] = h->cost[(size_t)add * S + c];
+    }
+    return (int)score;
+}
 
 MPREF_API void mpref_boot_free(mpref *h);
 MPREF_API void mpref_destroy(mpref *h)

@@ -57,6 +57,10 @@ def lib():
         L.mpref_reps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.mpref_sweep_count_insertions.restype = C.c_ulong
         L.mpref_sweep_count_insertions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mpref_set_cost_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.mpref_get_sankoff_vect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mpref_set_best.argtypes = [C.c_void_p, C.c_uint]
+        L.mpref_remainder_bounds.argtypes = [C.c_void_p, C.c_void_p]
         _boot_protos(L, "mpref")
         _lib = L
     return _lib
@@ -215,6 +219,29 @@ class RefEngine(BootMixin):
 
     def num_informative(self):
         return lib().mpref_num_informative(self.h)
+
+    # ---- Sankoff (-cost): the engine switches on pllCostMatrix (sprparsimony.cpp:556, 967, 2830)
+    def set_cost_matrix(self, cost, segment_upper):
+        """cost [S][S] (None = back to Fitch), segment_upper as IQTree::doSegmenting; returns highest_cost."""
+        if cost is None:
+            return lib().mpref_set_cost_matrix(self.h, None, None, 0)
+        c = np.ascontiguousarray(cost, dtype=np.uint32); seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
+        assert c.shape == (self.S, self.S)
+        return lib().mpref_set_cost_matrix(self.h, _p(c), _p(seg), len(seg))
+
+    def sankoff_vect(self, node):
+        """u16 [parsimonyLength][S] cost vector of one node (de-blocked from [len/16][S][16])."""
+        raw = np.zeros(self.W * self.S, dtype=np.uint16)
+        L = lib().mpref_get_sankoff_vect(self.h, node, _p(raw))
+        return raw.reshape(L // 16, self.S, 16).transpose(0, 2, 1).reshape(L, self.S)
+
+    def set_best(self, best):
+        lib().mpref_set_best(self.h, int(best))
+
+    def remainder_bounds(self):
+        out = np.zeros(65536, dtype=np.uint32)
+        k = lib().mpref_remainder_bounds(self.h, _p(out))
+        return out[:k].copy()
 
     def parsvect(self, node):
         out = np.zeros((self.S, self.W), dtype=np.uint32)
