@@ -199,7 +199,42 @@ int mpgpu_load_replicates2(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples, 
 /* groups = 1 + wrap-prone segments, exceptions = patterns on the exact CUDA-core path,
  * tensor = 1 when the tcgen05 path is enabled.  Any pointer may be NULL. */
 int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
-/* Options: "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests);
+/* ---- R11: -cost, Sankoff weighted parsimony --------------------------------------------------------
+ * Replaces the Sankoff half of the engine: compressSankoffDNA (sprparsimony.cpp:2637-2826),
+ * newviewSankoffParsimonyIterativeFastSIMD (:477-551), evaluateSankoffParsimonyIterativeFastSIMD
+ * (:880-961), pllComputeSankoffPatternParsimony (:3346-3360), the remainder lower bounds built from
+ * ParsTree::findMstScore (parstree.cpp:606; sprparsimony.cpp:2801-2823).  The reference switches on the
+ * global pllCostMatrix (:556, :967, :2830; set in iqtree.cpp:605); here the switch is this call.
+ *
+ * cost = [nstates][nstates] u32 (ParsTree::cost_matrix after loadCostMatrixFile, parstree.cpp:31-90),
+ * segment_upper/nseg = pllSegmentUpper / pllRepsSegments (IQTree::doSegmenting, iqtree.cpp:3793): interior
+ * bounds multiples of 16, the last one = the number of informative patterns.  cost = NULL returns to Fitch.
+ * After this call every entry point above (tree score, view lengths = tr->parsimonyScore[], pattern
+ * parsimony, scan, SPR search, stepwise addition) computes weighted parsimony with the reference's
+ * integers, including the per-segment 16-bit wrap of the weighted sums (:944-948).
+ * Preconditions checked here (error otherwise, there is no fallback): the matrix is symmetric and
+ * (ntaxa+1)*(max cost+1) <= 65535 -- then no u16 of the reference wraps inside a vector and the score
+ * does not depend on the orientation the reference happens to hold.  Sharded contexts and the -bb
+ * replicate contraction are not available under -cost. */
+int mpgpu_set_cost_matrix(mpgpu_ctx *ctx, const uint32_t *cost, int nstates, const int32_t *segment_upper, int nseg,
+                          uint32_t *highest_cost);
+/* vector_length = the reference's per-node vector length in patterns (informative patterns padded to 16,
+ * :2664-2667); remainder_bounds = pllRemainderLowerBounds[nseg-1].  Pointers may be NULL. */
+int mpgpu_sankoff_layout(mpgpu_ctx *ctx, int *vector_length, int *n_bounds, uint32_t *remainder_bounds, int capacity);
+/* The cost vector of the subtree behind ring slot (node, slot) in the reference's layout u16
+ * [vector_length][nstates] (parsVect of that node when xPars sits on the slot). */
+int mpgpu_sankoff_view(mpgpu_ctx *ctx, int node, int slot, uint16_t *out);
+/* Early termination (:951-956).  mpgpu_scan_* always return the exact score of every insertion (what the
+ * reference computes with perSiteScores = 1).  In plain mode the reference leaves evaluateSankoff... as
+ * soon as a prefix of segment sums plus the remainder bound exceeds tr->bestParsimony and returns that
+ * estimate instead; est_max[j] = max over segments of (prefix + bound) for candidate j of the last scan, so
+ * "est_max[j] > bestParsimony" <=> the reference exits early for j (its return value is then > best and
+ * changes nothing).  mpgpu_optimize_spr / mpgpu_stepwise_addition replay exactly this; option
+ * "sankoff_exact" = 1 switches the replay off (the reference's perSiteScores mode). */
+int mpgpu_scan_bounds(mpgpu_ctx *ctx, uint32_t *est_max, int capacity);
+
+/* Options: "sankoff_exact" 0/1 (see mpgpu_scan_bounds);
+ * "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests);
  * "reps_timing" 0/1 (CUDA events around the largest tensor-kernel launch, read by mpgpu_reps_timing). */
 int mpgpu_set_option(mpgpu_ctx *ctx, const char *name, int value);
 /* Device time (ms, CUDA events on the context's stream) of the largest tensor-kernel launch since the

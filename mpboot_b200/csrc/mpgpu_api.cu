@@ -35,8 +35,16 @@ static int states_of(int datatype)
 static void find_informative(Ctx *c, const uint8_t *yvec)
 {
     int und = 0;
-    state_mask_table(c->datatype, nullptr, &und);
+    const uint32_t *mt = state_mask_table(c->datatype, nullptr, &und);
     c->informative.assign(c->P, 1);
+    c->present.assign(c->P, 0);
+    for (int t = 0; t < c->n; t++) {                       // unambiguous states per pattern (ParsTree::findMstScore)
+        const uint8_t *row = yvec + (size_t)t * c->P;
+        for (int i = 0; i < c->P; i++) {
+            const uint32_t m = mt[row[i]];
+            if (m && !(m & (m - 1))) c->present[i] |= m;
+        }
+    }
     if (c->sort_alignment) {
         std::vector<int32_t> first(c->P, -1);
         std::fill(c->informative.begin(), c->informative.end(), 0);
@@ -124,6 +132,7 @@ static int build_planes(Ctx *c, bool realloc_views)
     c->kids_valid = false;
     c->ptn_site_valid = false;
     c->reps.tree_valid = false;
+    if (c->sk.on) return sk_build(c);
     return 0;
 }
 
@@ -186,7 +195,8 @@ int compute_views(Ctx *c)
     }
     MPGPU_CUDA(cudaMemcpyAsync(c->d_triples, flat.data(), total * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaMemsetAsync(c->d_vcount, 0, nviews * sizeof(uint32_t), c->stream));
-    for (int l = 1; l <= nl; l++)
+    if (c->sk.on) { if (int rc = sk_compute_levels(c, start, nl)) return rc; }
+    else for (int l = 1; l <= nl; l++)
         if (int rc = launch_level(c, c->d_triples + start[l], start[l + 1] - start[l])) return rc;
     c->reps.tree_valid = false;
     if (c->shard_count > 1 && c->allreduce) { if (int rc = shard_sum(c, c->d_vcount, nviews)) return rc; }
@@ -239,6 +249,7 @@ int update_views(Ctx *c, bool defer)
     }
     const size_t total = stale.size();
     if (total == 0) return 0;
+    if (c->sk.on) { c->reps.tree_valid = false; return sk_update_stale(c, stale, nlevels); }
     const int hdr = (nlevels + 3) / 4;
     if (wave_smem_bytes(c->S, hdr + (int)total) > 200 * 1024) { c->kids_valid = false; return compute_views(c); }   // list does not fit in shared memory
     if (!c->wave_pin.reserve(2 * (hdr + total) + 64) || !c->wcount_pin.reserve(2 * total + 64)) { set_error("pinned allocation failed"); return 1; }
@@ -303,6 +314,11 @@ void compute_lengths(Ctx *c)
 {
     const int nviews = 4 * c->n - 6;
     c->vlen.assign(nviews, 0);
+    if (c->sk.on) {      // parsimonyScore[node] of the Sankoff kernel: unweighted u16 sum of per-pattern minima (:491, :547), tips 0
+        for (const Triple &tr : c->sched) c->vlen[tr.dst] = c->vcount[tr.dst] & 0xFFFFu;
+        c->lens_valid = true;
+        return;
+    }
     for (const Triple &tr : c->sched) c->vlen[tr.dst] = c->vlen[tr.a] + c->vlen[tr.b] + c->vcount[tr.dst];
     c->lens_valid = true;
 }
@@ -353,6 +369,7 @@ int upload_plan(Ctx *c)
 int run_scan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
+    if (c->sk.on) return sk_run_scan(c);
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
     MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, (nout + 1) * sizeof(int32_t), c->stream));
     if (int rc = launch_scan(c, 0, (int)pl.tasks.size(), pl.max_slot)) return rc;
@@ -363,6 +380,7 @@ int run_scan(Ctx *c)
 int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
 {
     ScanPlan &pl = c->plan;
+    if (c->sk.on) return sk_finish_scan(c, visit_begin, mp, cand_ref, cand_prune, capacity);
     if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
     if (nout * sizeof(int32_t) > c->h_counts_cap) {
@@ -398,6 +416,11 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
 int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int mintrav, int maxtrav)
 {
     ScanPlan &pl = c->plan;
+    if (c->sk.on) {          // one piece: the per-(candidate, segment) output is sized from the finished plan
+        if (int rc = build_scan_plan(c->tree, order, first, count, mintrav, maxtrav, (uint32_t)(c->sk.vstride / 4), pl)) return rc;
+        if (int rc = upload_plan(c)) return rc;
+        return sk_run_scan(c);
+    }
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
     ScanPlanner planner;
     if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl)) return rc;
@@ -512,6 +535,7 @@ int mpgpu_destroy(mpgpu_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_alignment(c);
+    sk_free(c);
     if (c->d_triples) cudaFree(c->d_triples);
     if (c->d_wave) cudaFree(c->d_wave);
     if (c->d_wcount) cudaFree(c->d_wcount);
@@ -596,6 +620,7 @@ int mpgpu_get_layout(mpgpu_ctx *c, int *states, int *ref_words, int *shard_words
 static int copy_view_ref_layout(mpgpu_ctx *c, int vid, uint32_t *out)
 {
     if (c->shard_count != 1) { set_error("plane read-back is single-shard only"); return 1; }
+    if (c->sk.on && vid >= c->n) { set_error("Fitch planes of inner views do not exist under -cost: use mpgpu_sankoff_view"); return 1; }
     std::vector<uint32_t> tmp(c->view_stride);
     MPGPU_CUDA(cudaMemcpyAsync(tmp.data(), c->d_views + (size_t)vid * c->view_stride, c->view_stride * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, c->stream));
@@ -680,6 +705,7 @@ int mpgpu_get_view_planes(mpgpu_ctx *c, int node, int slot, uint32_t *out)
 static int edge_mismatch(mpgpu_ctx *c, int node, int slot, uint32_t *count, bool reduce)
 {
     if (int rc = need_tree(c, false)) return rc;
+    if (c->sk.on) { set_error("edge mismatch counts are a Fitch quantity (a cost matrix is set)"); return 1; }
     if (int rc = check_ref(c, node, slot)) return rc;
     MPGPU_CUDA(cudaSetDevice(c->device));
     const int r = 3 * node + slot;
@@ -699,6 +725,7 @@ int mpgpu_edge_mismatch_partial(mpgpu_ctx *c, int node, int slot, uint32_t *coun
 int mpgpu_tree_score(mpgpu_ctx *c, uint32_t *score)
 {
     if (int rc = need_tree(c, c && c->reduces())) return rc;
+    if (c->sk.on) { MPGPU_CUDA(cudaSetDevice(c->device)); return sk_tree_score(c, 3, score); }
     uint32_t mis = 0;
     if (int rc = edge_mismatch(c, 1, 0, &mis, c->shard_count > 1 && c->allreduce)) return rc;
     if (c->reduces()) *score = mis + c->vlen[c->tree.vid(c->tree.back(3))];
@@ -711,6 +738,7 @@ int mpgpu_pattern_parsimony(mpgpu_ctx *c, uint16_t *ptn_pars, int32_t *sum)
     if (int rc = need_tree(c, false)) return rc;
     if (!ptn_pars) { set_error("null argument"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
+    if (c->sk.on) return sk_pattern_parsimony(c, ptn_pars, c->sort_alignment ? c->n_inf : c->P, sum);
     const int nbits = 16;
     if (int rc = compute_site_counters(c, nbits)) return rc;
     if (int rc = ensure_ptn_site(c)) return rc;
@@ -733,6 +761,76 @@ int mpgpu_pattern_parsimony(mpgpu_ctx *c, uint16_t *ptn_pars, int32_t *sum)
     return 0;
 }
 
+// ---- R11: -cost (Sankoff) ----------------------------------------------------------------------
+int mpgpu_set_cost_matrix(mpgpu_ctx *c, const uint32_t *cost, int nstates, const int32_t *segment_upper, int nseg, uint32_t *highest)
+{
+    if (!c) { set_error("null context"); return 1; }
+    if (!c->d_views) { set_error("no alignment loaded"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    Sankoff &k = c->sk;
+    if (!cost) {                                            // back to Fitch
+        k.on = false;
+        c->lens_valid = false; c->kids_valid = false;
+        if (c->tree_set) { if (int rc = compute_views(c)) return rc; if (c->reduces()) compute_lengths(c); }
+        return 0;
+    }
+    if (nstates != c->S) { set_error("cost matrix size does not match the alignment's state count"); return 1; }
+    if (!segment_upper || nseg < 1) { set_error("segment_upper is required (IQTree::doSegmenting, iqtree.cpp:3793)"); return 1; }
+    if (c->reps.loaded) { set_error("-bb replicate scoring is not available under -cost in this library"); return 1; }
+    uint32_t mx = 0;
+    for (int i = 0; i < nstates; i++)
+        for (int j = 0; j < nstates; j++) {
+            if (cost[i * nstates + j] != cost[j * nstates + i]) {
+                set_error("asymmetric cost matrix: the directed-view engine needs cost[i][j] == cost[j][i] (root invariance)");
+                return 1;
+            }
+            mx = std::max(mx, cost[i * nstates + j]);
+        }
+    if (mx >= 65535) { set_error("cost matrix entry too large"); return 1; }
+    k.cost.assign(cost, cost + nstates * nstates);
+    k.highest = mx + 1;                                     // initializeCostMatrix :159-163
+    k.seg_upper.assign(segment_upper, segment_upper + nseg);
+    k.nseg = nseg;
+    k.cost_dirty = true;
+    k.on = true;
+    if (int rc = sk_build(c)) { k.on = false; return rc; }
+    c->lens_valid = false; c->kids_valid = false;
+    if (c->tree_set) { if (int rc = compute_views(c)) return rc; compute_lengths(c); }
+    if (highest) *highest = k.highest;
+    return 0;
+}
+
+int mpgpu_sankoff_layout(mpgpu_ctx *c, int *vector_length, int *n_bounds, uint32_t *remainder_bounds, int capacity)
+{
+    if (!c || !c->sk.on) { set_error("no cost matrix set"); return 1; }
+    if (vector_length) *vector_length = c->sk.Lref;
+    const int nb = c->sk.nseg > 1 ? c->sk.nseg - 1 : 0;
+    if (n_bounds) *n_bounds = nb;
+    if (remainder_bounds) {
+        if (capacity < nb) { set_error("capacity too small"); return 1; }
+        for (int i = 0; i < nb; i++) remainder_bounds[i] = c->sk.lb[i];
+    }
+    return 0;
+}
+
+int mpgpu_sankoff_view(mpgpu_ctx *c, int node, int slot, uint16_t *out)
+{
+    if (int rc = need_tree(c, false)) return rc;
+    if (!c->sk.on) { set_error("no cost matrix set"); return 1; }
+    if (int rc = check_ref(c, node, slot)) return rc;
+    if (!out) { set_error("null argument"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    return sk_raw_view(c, 3 * node + slot, out);
+}
+
+int mpgpu_scan_bounds(mpgpu_ctx *c, uint32_t *est_max, int capacity)
+{
+    if (!c || !c->sk.on) { set_error("no cost matrix set"); return 1; }
+    if (!est_max || capacity < (int)c->sk.h_est.size()) { set_error("capacity too small"); return 1; }
+    memcpy(est_max, c->sk.h_est.data(), c->sk.h_est.size() * sizeof(uint32_t));
+    return 0;
+}
+
 int mpgpu_visit_order(mpgpu_ctx *c, int32_t *order)
 {
     if (int rc = need_tree(c, false)) return rc;
@@ -748,7 +846,7 @@ int mpgpu_scan_plan(mpgpu_ctx *c, const int32_t *order, int first, int count, in
     if (int rc = need_tree(c, true)) return rc;
     if (!order || first < 1 || count < 0 || first + count > 2 * c->n - 1) { set_error("bad visit range"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
-    const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
+    const uint32_t vstride_vec = c->sk.on ? (uint32_t)(c->sk.vstride / 4) : (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
     if (int rc = build_scan_plan(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, c->plan)) return rc;
     if (int rc = upload_plan(c)) return rc;
     if (n_cand) *n_cand = c->plan.n_cand;

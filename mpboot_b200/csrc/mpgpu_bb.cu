@@ -431,7 +431,11 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
 {
     if (!c->reduces()) { set_error("the SPR search on a sharded context needs mpgpu_set_allreduce"); return 1; }
     if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
+    if (bb && c->sk.on) { set_error("-bb replicate scoring is not available under -cost in this library"); return 1; }
     if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
+    // -cost, plain mode: evaluateSankoff... leaves early when a prefix of segment sums plus the remainder bound
+    // exceeds tr->bestParsimony (:951-956); its return value is then > best, i.e. the insertion changes nothing
+    const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1;
     const int n = c->n, nvisit = 2 * n - 2;
     uint32_t score = 0;
     if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
@@ -504,6 +508,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 for (int j = vbegin[v]; j < vbegin[v + 1]; j++) {
                     const uint32_t m = mp[j];
                     scored++;
+                    if (sk_early && c->sk.h_est[j] > bestParsimony) continue;
                     if (bb) save_call(call_of[(size_t)v + 1 + j], m, cprune[j], cref[j]);        // testInsertParsimony :2163-2166
                     if (m < bestParsimony) bestTreeScoreHits = 1;                 // :2168
                     else if (m == bestParsimony) bestTreeScoreHits++;
@@ -596,7 +601,9 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
     if (!c->reduces()) { set_error("stepwise addition on a sharded context needs mpgpu_set_allreduce"); return 1; }
     compute_lengths(c);
     uint32_t treelen = 0;
-    {
+    const bool sk = c->sk.on;
+    if (sk) { if (int rc = sk_tree_score(c, f, &treelen)) return rc; }
+    else {
         uint32_t mis = 0;
         MPGPU_CUDA(cudaMemsetAsync(c->d_scalar, 0, sizeof(uint32_t), c->stream));
         if (int rc = launch_edge_mismatch(c, t.vid(f), t.vid(t.back(f)), c->d_scalar)) return rc;
@@ -626,6 +633,11 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
             if (!t.is_tip(x)) { stack.push_back(t.back(t.next(t.next(x)))); stack.push_back(t.back(t.next(x))); }
         }
         const int ne = (int)edges.size();
+        if (sk) {                                        // junction(x, back(x), new tip) = the whole tree's score (no early exit: :951 `!stepwiseAddition_on`)
+            if ((rc = sk_junctions(c, edges.data(), ne, nullptr))) break;
+            ins.resize(ne);
+            for (int e2 = 0; e2 < ne; e2++) ins[e2] = (int32_t)(c->sk.h_tot[e2].x - treelen);
+        } else {
         if ((rc = ensure(d_edges, edges_cap, (size_t)ne))) break;
         if ((rc = ensure(d_ins, ins_cap, (size_t)ne))) break;
         ins.resize(ne);
@@ -637,6 +649,7 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         e = cudaMemcpyAsync(ins.data(), d_ins, (size_t)ne * 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "stepwise addition read-back"); break; }
+        }
         settle_views(c, true);                                                    // counts of the previous step's view update
         // stepwiseAddition(tr, pr, q, f->back): pre-order, children only below a subtree of positive length
         best = 2147483647u;                                                       // tr->bestParsimony = INT_MAX :3141
@@ -746,6 +759,7 @@ int mpgpu_set_option(mpgpu_ctx *c, const char *name, int value)
         c->reps.use_tensor = value != 0;
         return 0;
     }
+    if (!strcmp(name, "sankoff_exact")) { c->sk.exact = value != 0; return 0; }
     if (!strcmp(name, "reps_timing")) { c->reps.timing = value != 0; c->reps.timed_rows = 0; return 0; }
     set_error(std::string("unknown option: ") + name);
     return 1;
@@ -785,6 +799,7 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (!c || !boot || !segment_upper) { set_error("null argument"); return 1; }
     if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
     if (B < 1 || nseg < 1) { set_error("need at least one replicate and one segment"); return 1; }
+    if (c->sk.on) { set_error("-bb replicate scoring is not available under -cost in this library"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     free_reps(c);
     Reps &r = c->reps;

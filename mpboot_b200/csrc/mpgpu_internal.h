@@ -158,6 +158,31 @@ struct Reps {
     int reclassifications = 0;            // times a wrap check moved a segment out of the tensor path's bulk group
 };
 
+// ---- Sankoff (-cost) state (R11; sankoff.cu) ------------------------------------------------------
+struct Sankoff {
+    bool on = false;                      // a cost matrix is set: every score is weighted parsimony
+    bool exact = false;                   // option "sankoff_exact": perSiteScores mode, no lower-bound early exit (:951)
+    bool cost_dirty = true;
+    std::vector<uint32_t> cost;           // pllCostMatrix [S][S]
+    uint32_t highest = 0;                 // highest_cost = max + 1 (:160)
+    std::vector<int32_t> seg_upper; int nseg = 0;
+    std::vector<uint32_t> lb;             // pllRemainderLowerBounds [nseg-1]
+    int Lref = 0;                         // the reference's vector length (informative patterns padded to 16)
+    int Lp = 0, Lh = 0;                   // device patterns per state row (padded to 64) and 32-bit words (pattern pairs)
+    size_t vstride = 0;                   // 32-bit words per view: S * Lh
+    uint32_t *d_views = nullptr; size_t views_cap = 0;     // [4n-6][S][Lh] transformed cost vectors, u16x2
+    uint2 *d_w = nullptr;                 // [Lh] weights of the pair's two patterns
+    int32_t *d_seg = nullptr;             // [Lh] segment of the pair
+    uint32_t *d_lb = nullptr;             // [nseg]
+    uint32_t *d_mask = nullptr;           // [256] code -> state mask
+    uint32_t *d_segout = nullptr; size_t segout_cap = 0;   // [rows][nseg] exact weighted sums per segment (mod 2^32)
+    uint2 *d_tot = nullptr; size_t tot_cap = 0;            // [rows] (total, max_seg(prefix + lb))
+    uint2 *h_tot = nullptr; size_t h_tot_cap = 0;          // pinned copy
+    int4 *d_list = nullptr; size_t list_cap = 0;
+    uint32_t *d_tmp = nullptr; size_t tmp_cap = 0;
+    std::vector<uint32_t> h_est;          // per candidate of the last scan: max_seg(prefix + lb); > bestParsimony <=> the reference exits early
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -171,6 +196,7 @@ struct Ctx {
     int n = 0, P = 0, datatype = 0, S = 0, sort_alignment = 1;
     std::vector<int32_t> weights;
     std::vector<uint8_t> informative;
+    std::vector<uint32_t> present;        // [P] unambiguous states present among the tips (findMstScore, parstree.cpp:606)
     int n_inf = 0;
     int64_t n_sites = 0;
     int ref_words = 0;                    // reference parsimonyLength (padded to 8)
@@ -221,6 +247,8 @@ struct Ctx {
 
     // replicate scoring
     Reps reps;
+    // weighted parsimony
+    Sankoff sk;
     // aliases the scan kernel's ROWS mode reads (owned by reps)
     int32_t *d_row_of = nullptr, *d_row_tasks = nullptr;
     uint32_t *d_rows_site = nullptr;
@@ -256,6 +284,18 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
 int compute_site_counters(Ctx *c, int nbits);       // bit-sliced per-site counters of the current tree -> d_bitcnt
 int ensure_ptn_site(Ctx *c);                        // first expanded site of every reported pattern -> d_ptn_site
 void free_reps(Ctx *c);
+
+// ---- Sankoff (-cost) path (sankoff.cu) ------------------------------------------------------------
+void sk_free(Ctx *c);
+int sk_build(Ctx *c);
+int sk_compute_levels(Ctx *c, const std::vector<int32_t> &start, int nl);
+int sk_update_stale(Ctx *c, std::vector<Triple> &stale, int nlevels);
+int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn);
+int sk_tree_score(Ctx *c, int start_ref, uint32_t *score);
+int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum);
+int sk_raw_view(Ctx *c, int ref, uint16_t *out);
+int sk_run_scan(Ctx *c);
+int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity);
 
 // ---- kernel launchers (fitch_kernels.cu) -------------------------------------------------
 int launch_compress(Ctx *c);

@@ -1,0 +1,617 @@
+// R11 (-cost): Sankoff weighted parsimony on the device.
+//
+// Reference: compressSankoffDNA sprparsimony.cpp:2637-2826, newviewSankoffParsimonyIterativeFastSIMD
+// :477-551, evaluateSankoffParsimonyIterativeFastSIMD :880-961 (per-segment u16 sums, lower-bound
+// early exit :951-956), pllComputeSankoffPatternParsimony :3346-3360, ParsTree::findMstScore
+// parstree.cpp:606-677.
+//
+// Design (not the reference's): the reference keeps one u16 cost vector per node, [pattern][state],
+// and re-orients it lazily.  Here every DIRECTED view v of the tree keeps the min-plus transform
+//      v'[z] = min_x (v[x] + cost[z][x])
+// of its cost vector, state-major over pattern pairs (two u16 patterns per 32-bit word), because
+// everything the search needs is a sum of transforms:
+//      newview    dst  = a' + b'                       dst' = minplus(dst)
+//      any score       = sum_ptn w * min_z (A' + B' + C')[z]      (junction of three views)
+//      insertion  U_c  = U_y' + X'  (X = sibling),  mp = junction(U_c', view(c)', S')
+// With a symmetric cost matrix the minimum over all inner labelings does not depend on where the
+// tree is rooted, and with (n+1)*highest <= 65535 no u16 of the reference can wrap inside a
+// vector, so these integers are the reference's (mpgpu_set_cost_matrix checks both and fails
+// otherwise; the parity tests prove it against golden vectors from the reference itself).
+// The per-segment 16-bit wrap of the weighted sum (:944-948) and the early exit are reproduced
+// exactly: the kernels accumulate exact per-(candidate, segment) sums mod 2^32, k_sk_finish
+// masks each to 16 bits and returns the total and max_seg(prefix + remainder bound), from which
+// the host replays "est > bestParsimony" in order.
+//
+// The inner operation min(acc, v + c) on two u16 lanes is one Blackwell DPX instruction
+// (VIADDMNMX.U16x2, __viaddmin_u16x2); the cost matrix sits in constant memory and is folded
+// into the instruction as an immediate constant-bank operand by full unrolling.
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+
+#include "mpgpu_internal.h"
+
+namespace mpgpu {
+
+__constant__ uint32_t c_cost2[kMaxStates * kMaxStates];   // cost[z][x] in both halfwords, row stride = S
+static const Ctx *g_cost_owner[64];
+
+static int bind_cost(Ctx *c)
+{
+    if (c->device >= 0 && c->device < 64 && g_cost_owner[c->device] == c && !c->sk.cost_dirty) return 0;
+    uint32_t tmp[kMaxStates * kMaxStates];
+    memset(tmp, 0, sizeof tmp);
+    for (int i = 0; i < c->S * c->S; i++) tmp[i] = c->sk.cost[i] | c->sk.cost[i] << 16;
+    MPGPU_CUDA(cudaMemcpyToSymbolAsync(c_cost2, tmp, sizeof tmp, 0, cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->device >= 0 && c->device < 64) g_cost_owner[c->device] = c;
+    c->sk.cost_dirty = false;
+    return 0;
+}
+
+// ---- device helpers -------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void sk_minplus(const uint32_t (&v)[S], uint32_t (&o)[S])
+{
+#pragma unroll
+    for (int z = 0; z < S; z++) {
+        uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+        for (int x = 0; x < S; x++) acc = __viaddmin_u16x2(v[x], c_cost2[z * S + x], acc);
+        o[z] = acc;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void sk_load(const uint32_t *__restrict__ p, size_t Lh, uint32_t (&r)[S])
+{
+#pragma unroll
+    for (int s = 0; s < S; s++) r[s] = __ldg(p + s * Lh);
+}
+
+// per-pattern minimum over the states of a + b + c (packed u16x2)
+template <int S>
+__device__ __forceinline__ uint32_t sk_best3(const uint32_t (&a)[S], const uint32_t *__restrict__ pb,
+                                             const uint32_t *__restrict__ pc, size_t Lh)
+{
+    uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+    for (int z = 0; z < S; z++) best = __vminu2(best, a[z] + __ldg(pb + z * Lh) + __ldg(pc + z * Lh));
+    return best;
+}
+
+// weighted contribution of the lane's two patterns, summed per segment over the warp
+__device__ __forceinline__ void sk_accum(uint32_t best, uint2 w, int myseg, int seg_lo, int seg_hi,
+                                         uint32_t *__restrict__ out_row, bool lane0)
+{
+    const uint32_t v = (best & 0xFFFFu) * w.x + (best >> 16) * w.y;
+    for (int s = seg_lo; s <= seg_hi; s++) {
+        const uint32_t r = __reduce_add_sync(0xffffffffu, myseg == s ? v : 0u);
+        if (lane0 && r) atomicAdd(out_row + s, r);
+    }
+}
+
+// ---- tips: v[x] = 0 if the tip's code allows x else highest (:2739-2745); padded patterns all 0 ----
+template <int S>
+__global__ void __launch_bounds__(128) k_sk_tips(const uint8_t *__restrict__ codes, int P, int ntaxa,
+                                                 const int32_t *__restrict__ inf_ptn, int n_inf,
+                                                 const uint32_t *__restrict__ mask_table, uint32_t highest,
+                                                 uint32_t *__restrict__ views, size_t vstride, int Lh)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)ntaxa * Lh) return;
+    const int tip = (int)(gid / Lh), i = (int)(gid % Lh);
+    uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+    if (2 * i < n_inf) m0 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i]]];
+    if (2 * i + 1 < n_inf) m1 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i + 1]]];
+    uint32_t v[S], o[S];
+#pragma unroll
+    for (int x = 0; x < S; x++) v[x] = ((m0 >> x) & 1u ? 0u : highest) | ((m1 >> x) & 1u ? 0u : highest) << 16;
+    sk_minplus<S>(v, o);
+    uint32_t *dst = views + (size_t)tip * vstride + i;
+#pragma unroll
+    for (int z = 0; z < S; z++) dst[(size_t)z * Lh] = o[z];
+}
+
+// ---- newview (:477-551): one thread per (triple, pattern pair) -------------------------------
+// score[dst] += sum over the reference's L patterns of min_z (a' + b')[z]  (unweighted, :547)
+template <int S>
+__global__ void __launch_bounds__(128) k_sk_level(uint32_t *views, size_t vstride, int Lh, int Lref_pairs,
+                                                  const Triple *__restrict__ triples, int ntriples,
+                                                  uint32_t *__restrict__ vscore, uint32_t *__restrict__ compact)
+{
+    const int per = Lh / 32;                       // warps per triple
+    const int gw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (gw >= ntriples * per) return;
+    const int lane = threadIdx.x & 31;
+    const int ti = gw / per, i = (gw % per) * 32 + lane;
+    const Triple tr = triples[ti];
+    const uint32_t *pa = views + (size_t)tr.a * vstride + i, *pb = views + (size_t)tr.b * vstride + i;
+    uint32_t v[S], o[S];
+    uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int x = 0; x < S; x++) { v[x] = pa[(size_t)x * Lh] + pb[(size_t)x * Lh]; mn = __vminu2(mn, v[x]); }
+    sk_minplus<S>(v, o);
+    uint32_t *dst = views + (size_t)tr.dst * vstride + i;
+#pragma unroll
+    for (int z = 0; z < S; z++) dst[(size_t)z * Lh] = o[z];
+    const uint32_t contrib = i < Lref_pairs ? (mn & 0xFFFFu) + (mn >> 16) : 0u;
+    const uint32_t r = __reduce_add_sync(0xffffffffu, contrib);
+    if (lane == 0 && r) atomicAdd(compact ? compact + ti : vscore + tr.dst, r);
+}
+
+// raw cost vector of a directed view (tests): a' + b' for an inner view, the tip vector otherwise
+__global__ void k_sk_raw(const uint32_t *__restrict__ views, size_t vstride, int Lh, int S, int va, int vb,
+                         uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lh) return;
+    for (int x = 0; x < S; x++)
+        out[(size_t)x * Lh + i] = views[(size_t)va * vstride + (size_t)x * Lh + i] + views[(size_t)vb * vstride + (size_t)x * Lh + i];
+}
+__global__ void k_sk_raw_tip(const uint8_t *__restrict__ codes, int P, int tip, const int32_t *__restrict__ inf_ptn, int n_inf,
+                             const uint32_t *__restrict__ mask_table, uint32_t highest, int Lh, int S, uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lh) return;
+    uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+    if (2 * i < n_inf) m0 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i]]];
+    if (2 * i + 1 < n_inf) m1 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i + 1]]];
+    for (int x = 0; x < S; x++)
+        out[(size_t)x * Lh + i] = ((m0 >> x) & 1u ? 0u : highest) | ((m1 >> x) & 1u ? 0u : highest) << 16;
+}
+
+// ---- junctions: score of the tree seen from an inner node whose three neighbours are a, b, c ----
+// (evaluateSankoff... :880-961 on any edge of that node; stepwise insertion of a tip c into the
+// branch (a, b)).  One warp per (junction, 64-pattern chunk); ptn_out = per-pattern minimum of
+// junction 0 (pllComputeSankoffPatternParsimony).
+template <int S>
+__global__ void __launch_bounds__(128) k_sk_junction(const uint32_t *__restrict__ views, size_t vstride, int Lh,
+                                                     const int4 *__restrict__ list, int count,
+                                                     const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
+                                                     uint32_t *__restrict__ segout, uint32_t *__restrict__ ptn_out)
+{
+    const int nchunks = Lh / 32;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (int64_t)count * nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int)(gw / count), e = (int)(gw % count);
+    const int i = chunk * 32 + lane;
+    const int4 j = __ldg(list + e);
+    uint32_t a[S];
+    sk_load<S>(views + (size_t)j.x * vstride + i, (size_t)Lh, a);
+    const uint32_t best = sk_best3<S>(a, views + (size_t)j.y * vstride + i, views + (size_t)j.z * vstride + i, (size_t)Lh);
+    if (ptn_out && e == 0) ptn_out[i] = best;
+    const uint2 w = __ldg(wts + i);
+    const int myseg = __ldg(segof + i);
+    const int seg_lo = __shfl_sync(0xffffffffu, myseg, 0), seg_hi = __shfl_sync(0xffffffffu, myseg, 31);
+    sk_accum(best, w, myseg, seg_lo, seg_hi, segout + (size_t)e * nseg, lane == 0);
+}
+
+// ---- the SPR scan (testInsertParsimony batched; same program streams as k_spr_scan) ------------
+// One warp = (task, chunk of 32 pattern pairs).  The stack holds U' (transformed up-views) per
+// lane in shared memory: [slot][state][lane].
+template <int S>
+__device__ __forceinline__ void sk_child(const uint32_t (&U)[S], const uint32_t *__restrict__ px, const uint32_t *__restrict__ pc,
+                                         const uint32_t *__restrict__ ps, size_t Lh,
+                                         bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
+                                         uint2 w, int myseg, int seg_lo, int seg_hi, bool lane0)
+{
+    uint32_t U1[S], U1p[S];
+#pragma unroll
+    for (int x = 0; x < S; x++) U1[x] = U[x] + __ldg(px + x * Lh);
+    sk_minplus<S>(U1, U1p);
+    if (do_dst) {
+#pragma unroll
+        for (int z = 0; z < S; z++) dst[z * 32] = U1p[z];
+    }
+    if (do_out) {
+        const uint32_t best = sk_best3<S>(U1p, pc, ps, Lh);
+        sk_accum(best, w, myseg, seg_lo, seg_hi, out_row, lane0);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views4, int Lh,
+                                                 const ScanTask *__restrict__ tasks, int ntasks,
+                                                 const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
+                                                 int nslots, int cand_bias,
+                                                 const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
+                                                 uint32_t *__restrict__ segout)
+{
+    extern __shared__ uint32_t sk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    const unsigned nchunks = Lh / 32;
+    if (gw >= (unsigned)ntasks * nchunks) return;
+    const unsigned chunk = gw / (unsigned)ntasks, ti = gw - chunk * (unsigned)ntasks;
+    const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
+    const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
+    const size_t L = (size_t)Lh;
+    const int i = chunk * 32 + lane;
+    uint32_t *stack = sk_smem + (size_t)warp * nslots * S * 32 + lane;
+    const bool lane0 = lane == 0;
+    const uint2 w = __ldg(wts + i);
+    const int myseg = __ldg(segof + i);
+    const int seg_lo = __shfl_sync(0xffffffffu, myseg, 0), seg_hi = __shfl_sync(0xffffffffu, myseg, 31);
+    uint32_t *outc = segout + (size_t)(t1.z - cand_bias) * nseg;
+    const uint32_t *ps = reinterpret_cast<const uint32_t *>(views4 + (uint32_t)t0.x) + i;
+
+    for (int oi = t0.w; oi < t1.x; oi++) {
+        const int2 f = __ldg(offs + oi);
+        const int2 cw = __ldg(ctl + oi);
+        const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;
+        const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;
+        const uint32_t *pa = reinterpret_cast<const uint32_t *>(views4 + (uint32_t)f.x) + i;
+        const uint32_t *pb = reinterpret_cast<const uint32_t *>(views4 + (uint32_t)f.y) + i;
+        uint32_t U[S];
+        if (src < 0xfe) {
+            const uint32_t *sp = stack + (size_t)src * S * 32;
+#pragma unroll
+            for (int z = 0; z < S; z++) U[z] = sp[z * 32];
+        } else {
+            sk_load<S>(reinterpret_cast<const uint32_t *>(views4 + (uint32_t)(src == 0xff ? t0.z : t0.y)) + i, L, U);
+        }
+        if (o1 != 0xffff || dst1 != 0xff)
+            sk_child<S>(U, pb, pa, ps, L, o1 != 0xffff, outc + (size_t)o1 * nseg, dst1 != 0xff, stack + (size_t)dst1 * S * 32,
+                        w, myseg, seg_lo, seg_hi, lane0);
+        if (o2 != 0xffff || dst2 != 0xff)
+            sk_child<S>(U, pa, pb, ps, L, o2 != 0xffff, outc + (size_t)o2 * nseg, dst2 != 0xff, stack + (size_t)dst2 * S * 32,
+                        w, myseg, seg_lo, seg_hi, lane0);
+    }
+}
+
+// ---- per row: total = sum_seg (sum mod 2^16) (:944-948), est = max_{seg < nseg-1} (prefix + lb[seg]) (:951-956) ----
+__global__ void k_sk_finish(const uint32_t *__restrict__ segout, int nseg, const uint32_t *__restrict__ lb, int rows,
+                            uint2 *__restrict__ out)
+{
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t total = 0, est = 0;
+    for (int base = 0; base < nseg; base += 32) {
+        const int s = base + lane;
+        uint32_t v = s < nseg ? segout[(size_t)row * nseg + s] & 0xFFFFu : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+        if (s < nseg - 1) est = max(est, total + v + lb[s]);
+        total += __shfl_sync(0xffffffffu, v, 31);
+    }
+    est = __reduce_max_sync(0xffffffffu, est);
+    if (lane == 0) out[row] = make_uint2(total, est);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+#define SK_DISPATCH(CALL)                                                                      \
+    switch (c->S) {                                                                            \
+    case 2:  { constexpr int S_ = 2;  CALL; } break;                                           \
+    case 4:  { constexpr int S_ = 4;  CALL; } break;                                           \
+    case 20: { constexpr int S_ = 20; CALL; } break;                                           \
+    case 32: { constexpr int S_ = 32; CALL; } break;                                           \
+    default: set_error("unsupported state count"); return 1;                                   \
+    }
+
+void sk_free(Ctx *c)
+{
+    Sankoff &k = c->sk;
+    if (k.d_views) cudaFree(k.d_views);
+    if (k.d_w) cudaFree(k.d_w);
+    if (k.d_seg) cudaFree(k.d_seg);
+    if (k.d_lb) cudaFree(k.d_lb);
+    if (k.d_mask) cudaFree(k.d_mask);
+    if (k.d_segout) cudaFree(k.d_segout);
+    if (k.d_tot) cudaFree(k.d_tot);
+    if (k.d_list) cudaFree(k.d_list);
+    if (k.d_tmp) cudaFree(k.d_tmp);
+    if (k.h_tot) cudaFreeHost(k.h_tot);
+    k.d_views = nullptr; k.d_w = nullptr; k.d_seg = nullptr; k.d_lb = nullptr; k.d_mask = nullptr;
+    k.d_segout = nullptr; k.d_tot = nullptr; k.d_list = nullptr; k.d_tmp = nullptr; k.h_tot = nullptr;
+    k.views_cap = k.segout_cap = k.tot_cap = k.list_cap = k.tmp_cap = k.h_tot_cap = 0;
+    if (c->device >= 0 && c->device < 64 && g_cost_owner[c->device] == c) g_cost_owner[c->device] = nullptr;
+}
+
+// ParsTree::findMstScore (parstree.cpp:606-677): Prim over the unambiguous states present in a pattern
+static uint32_t mst_weight(const Sankoff &k, int S, uint32_t present)
+{
+    if (__builtin_popcount(present) <= 1) return 0;
+    uint32_t label[kMaxStates];
+    uint32_t todo = present, score = 0;
+    for (int s = 0; s < S; s++) label[s] = 0xFFFFFFFFu;
+    label[__builtin_ctz(present)] = 0;
+    while (todo) {
+        int add = -1; uint32_t best = 0xFFFFFFFFu;
+        for (int s = 0; s < S; s++) if ((todo >> s & 1u) && label[s] < best) { best = label[s]; add = s; }
+        if (add < 0) break;
+        todo &= ~(1u << add);
+        score += label[add];
+        for (int s = 0; s < S; s++)
+            if ((todo >> s & 1u) && label[s] > k.cost[add * S + s]) label[s] = k.cost[add * S + s];
+    }
+    return score;
+}
+
+// vectors, weights, segment ids, remainder bounds for the current alignment and weights
+int sk_build(Ctx *c)
+{
+    Sankoff &k = c->sk;
+    const int S = c->S, n = c->n, ninf = c->n_inf;
+    if (c->shard_count != 1) { set_error("-cost (Sankoff) runs on unsharded contexts only"); return 1; }
+    if ((int64_t)(n + 1) * k.highest > 65535) {
+        set_error("cost matrix too large for this many taxa: (ntaxa+1)*(max cost+1) must stay below 65536 (a u16 of the reference could wrap)");
+        return 1;
+    }
+    if (k.seg_upper.empty() || k.seg_upper.back() != ninf) { set_error("segment_upper must end at the number of informative patterns"); return 1; }
+    for (int s = 0; s + 1 < k.nseg; s++)
+        if (k.seg_upper[s] % 16 || k.seg_upper[s] <= (s ? k.seg_upper[s - 1] : 0) || k.seg_upper[s] >= ninf) {
+            set_error("segment_upper: interior bounds must be increasing multiples of 16 (iqtree.cpp:3804)"); return 1;
+        }
+    k.Lref = ninf % 16 ? ninf + 16 - ninf % 16 : ninf;
+    k.Lp = std::max(64, (ninf + 63) / 64 * 64);
+    k.Lh = k.Lp / 2;
+    k.vstride = (size_t)S * k.Lh;
+    const size_t nviews = (size_t)(4 * n - 6);
+    if ((nviews * k.vstride) / 4 > 0xFFFFFFFFull) { set_error("alignment too large for 32-bit view offsets"); return 1; }
+    if (int rc = ensure(k.d_views, k.views_cap, nviews * k.vstride)) return rc;
+    if (k.d_w) cudaFree(k.d_w);
+    if (k.d_seg) cudaFree(k.d_seg);
+    if (k.d_lb) cudaFree(k.d_lb);
+    k.d_w = nullptr; k.d_seg = nullptr; k.d_lb = nullptr;
+    MPGPU_CUDA(cudaMalloc((void **)&k.d_w, sizeof(uint2) * k.Lh));
+    MPGPU_CUDA(cudaMalloc((void **)&k.d_seg, sizeof(int32_t) * k.Lh));
+    MPGPU_CUDA(cudaMalloc((void **)&k.d_lb, sizeof(uint32_t) * std::max(1, k.nseg)));
+    if (!k.d_mask) MPGPU_CUDA(cudaMalloc((void **)&k.d_mask, sizeof(uint32_t) * 256));
+    // informativePtnWgt is u16 (:2755); entry j = the j-th informative pattern
+    std::vector<uint2> w(k.Lh, make_uint2(0, 0));
+    std::vector<int32_t> seg(k.Lh, k.nseg - 1);
+    std::vector<uint32_t> wflat(ninf > 0 ? ninf : 1, 0), present(ninf > 0 ? ninf : 1, 0);
+    {
+        int j = 0;
+        for (int i = 0; i < c->P; i++) {
+            if (!c->informative[i]) continue;
+            wflat[j] = (uint32_t)(uint16_t)c->weights[i];
+            present[j] = c->present[j];          // findMstScore(ptn) indexes the alignment directly: informative patterns come first
+            j++;
+        }
+        int s = 0;
+        for (j = 0; j < ninf; j++) {
+            while (s + 1 < k.nseg && j >= k.seg_upper[s]) s++;
+            if (j & 1) w[j / 2].y = wflat[j]; else { w[j / 2].x = wflat[j]; seg[j / 2] = s; }
+        }
+    }
+    // remainder lower bounds (:2801-2823): for seg < nseg-1, sum over ptn >= segment_upper[seg] of mst(ptn) * weight(ptn)
+    k.lb.assign(std::max(1, k.nseg), 0);
+    if (k.nseg > 1) {
+        std::unordered_map<uint32_t, uint32_t> memo;
+        std::vector<uint32_t> suffix(ninf + 1, 0);
+        for (int j = ninf - 1; j >= 0; j--) {
+            auto it = memo.find(present[j]);
+            uint32_t m;
+            if (it == memo.end()) { m = mst_weight(k, S, present[j]); memo[present[j]] = m; } else m = it->second;
+            suffix[j] = suffix[j + 1] + m * wflat[j];
+        }
+        for (int s = 0; s + 1 < k.nseg; s++) k.lb[s] = suffix[k.seg_upper[s]];
+    }
+    int nc = 0;
+    const uint32_t *mt = state_mask_table(c->datatype, &nc, nullptr);
+    uint32_t mask256[256];
+    for (int i = 0; i < 256; i++) mask256[i] = i < nc ? mt[i] : 0xFFFFFFFFu;
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_w, w.data(), sizeof(uint2) * k.Lh, cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_seg, seg.data(), sizeof(int32_t) * k.Lh, cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_lb, k.lb.data(), sizeof(uint32_t) * k.lb.size(), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_mask, mask256, sizeof mask256, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = bind_cost(c)) return rc;
+    const int64_t total = (int64_t)n * k.Lh;
+    const int blocks = (int)((total + 127) / 128);
+    SK_DISPATCH((k_sk_tips<S_><<<blocks, 128, 0, c->stream>>>(c->d_codes, c->P, n, c->d_inf_ptn, ninf, k.d_mask, k.highest,
+                                                              k.d_views, k.vstride, k.Lh)));
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int sk_launch_level(Ctx *c, const Triple *d_triples, int ntriples, uint32_t *d_compact)
+{
+    if (ntriples == 0) return 0;
+    Sankoff &k = c->sk;
+    if (int rc = bind_cost(c)) return rc;
+    const int64_t warps = (int64_t)ntriples * (k.Lh / 32);
+    const int blocks = (int)((warps + 3) / 4);
+    SK_DISPATCH((k_sk_level<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.Lref / 2, d_triples, ntriples,
+                                                               c->d_vcount, d_compact)));
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// all directed views (levels are in c->d_triples, level l at [start[l], start[l+1]))
+int sk_compute_levels(Ctx *c, const std::vector<int32_t> &start, int nl)
+{
+    for (int l = 1; l <= nl; l++)
+        if (int rc = sk_launch_level(c, c->d_triples + start[l], start[l + 1] - start[l], nullptr)) return rc;
+    return 0;
+}
+
+// stale views after a move: `stale` is in dependency order with pad = stale level (1-based)
+int sk_update_stale(Ctx *c, std::vector<Triple> &stale, int nlevels)
+{
+    const size_t total = stale.size();
+    std::vector<int32_t> start(nlevels + 2, 0);
+    for (const Triple &tr : stale) start[tr.pad + 1]++;
+    for (int l = 1; l <= nlevels + 1; l++) start[l] += start[l - 1];
+    if (!c->wave_pin.reserve(total + 64) || !c->wcount_pin.reserve(total + 64)) { set_error("pinned allocation failed"); return 1; }
+    if (int rc = ensure(c->d_wave, c->wave_cap, total)) return rc;
+    if (int rc = ensure(c->d_wcount, c->wcount_cap, total)) return rc;
+    Triple *dst = c->wave_pin.data();
+    {
+        std::vector<int32_t> fill(start.begin(), start.end());
+        for (const Triple &tr : stale) dst[fill[tr.pad]++] = tr;
+    }
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_wave, dst, total * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, total * sizeof(uint32_t), c->stream));
+    for (int l = 1; l <= nlevels; l++)
+        if (int rc = sk_launch_level(c, c->d_wave + start[l], start[l + 1] - start[l], c->d_wcount + start[l])) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < total; i++) c->vcount[dst[i].dst] = c->wcount_pin.data()[i];
+    return 0;
+}
+
+static int sk_ensure_out(Ctx *c, size_t rows)
+{
+    Sankoff &k = c->sk;
+    if (int rc = ensure(k.d_segout, k.segout_cap, rows * k.nseg + 1)) return rc;
+    if (int rc = ensure(k.d_tot, k.tot_cap, rows + 1)) return rc;
+    if ((rows + 1) * sizeof(uint2) > k.h_tot_cap) {
+        if (k.h_tot) cudaFreeHost(k.h_tot);
+        k.h_tot = nullptr; k.h_tot_cap = 0;
+        const size_t want = (rows + rows / 2 + 1024) * sizeof(uint2);
+        MPGPU_CUDA(cudaHostAlloc((void **)&k.h_tot, want, cudaHostAllocDefault));
+        k.h_tot_cap = want;
+    }
+    return 0;
+}
+
+static int sk_finish_rows(Ctx *c, int rows)
+{
+    Sankoff &k = c->sk;
+    const int blocks = (rows * 32 + 127) / 128;
+    k_sk_finish<<<blocks, 128, 0, c->stream>>>(k.d_segout, k.nseg, k.d_lb, rows, k.d_tot);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    MPGPU_CUDA(cudaMemcpyAsync(k.h_tot, k.d_tot, (size_t)rows * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// scores of `count` junctions (view ids a, b, c); results in c->sk.h_tot[j] = (total, est); ptn = per-pattern
+// minima of junction 0 (u16, Lp entries) when not null
+int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn)
+{
+    Sankoff &k = c->sk;
+    if (count <= 0) return 0;
+    if (int rc = bind_cost(c)) return rc;
+    if (int rc = sk_ensure_out(c, (size_t)count)) return rc;
+    if (int rc = ensure(k.d_list, k.list_cap, (size_t)count)) return rc;
+    if (ptn) { if (int rc = ensure(k.d_tmp, k.tmp_cap, (size_t)k.Lh)) return rc; }
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_list, list, (size_t)count * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)count * k.nseg * sizeof(uint32_t), c->stream));
+    const int64_t warps = (int64_t)count * (k.Lh / 32);
+    const int blocks = (int)((warps + 3) / 4);
+    SK_DISPATCH((k_sk_junction<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, count, k.d_w, k.d_seg, k.nseg,
+                                                                  k.d_segout, ptn ? k.d_tmp : nullptr)));
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    if (ptn) MPGPU_CUDA(cudaMemcpyAsync(ptn, k.d_tmp, (size_t)k.Lh * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return sk_finish_rows(c, count);      // synchronizes: `list` may be a host temporary
+}
+
+// the inner node next to the tip `start` (tr->start): its three neighbour views
+static int4 start_junction(const HostTree &t, int start = 3)
+{
+    const int r = t.back(start);
+    return make_int4(t.vid(start), t.vid(t.back(t.next(r))), t.vid(t.back(t.next(t.next(r)))), 0);
+}
+
+int sk_tree_score(Ctx *c, int start_ref, uint32_t *score)
+{
+    const int4 j = start_junction(c->tree, start_ref);
+    if (int rc = sk_junctions(c, &j, 1, nullptr)) return rc;
+    *score = c->sk.h_tot[0].x;
+    return 0;
+}
+
+// pllComputeSankoffPatternParsimony (:3346-3360): per-pattern minimum at the start edge, L entries
+int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum)
+{
+    Sankoff &k = c->sk;
+    std::vector<uint16_t> tmp((size_t)k.Lp);
+    const int4 j = start_junction(c->tree);
+    if (int rc = sk_junctions(c, &j, 1, tmp.data())) return rc;
+    int s = 0, jj = 0;
+    for (int i = 0; i < c->P && jj < k.Lp; i++) {
+        if (!c->informative[i]) continue;
+        s += (int)tmp[jj] * (int)(uint16_t)c->weights[i];
+        jj++;
+    }
+    for (int i = 0; i < count; i++) ptn_pars[i] = i < k.Lp ? tmp[i] : 0;
+    if (sum) *sum = s;
+    return 0;
+}
+
+int sk_raw_view(Ctx *c, int ref, uint16_t *out)
+{
+    Sankoff &k = c->sk;
+    const HostTree &t = c->tree;
+    if (int rc = ensure(k.d_tmp, k.tmp_cap, k.vstride)) return rc;
+    const int blocks = (k.Lh + 127) / 128;
+    if (t.is_tip(ref))
+        k_sk_raw_tip<<<blocks, 128, 0, c->stream>>>(c->d_codes, c->P, ref / 3 - 1, c->d_inf_ptn, c->n_inf, k.d_mask, k.highest, k.Lh, c->S, k.d_tmp);
+    else
+        k_sk_raw<<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, c->S, t.vid(t.back(t.next(ref))), t.vid(t.back(t.next(t.next(ref)))), k.d_tmp);
+    MPGPU_CUDA(cudaGetLastError());
+    std::vector<uint16_t> tmp((size_t)c->S * k.Lp);
+    MPGPU_CUDA(cudaMemcpyAsync(tmp.data(), k.d_tmp, k.vstride * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < k.Lref; i++)
+        for (int x = 0; x < c->S; x++) out[(size_t)i * c->S + x] = tmp[(size_t)x * k.Lp + i];
+    return 0;
+}
+
+// scan: the whole plan in one launch, per-(candidate, segment) sums, then totals and bounds
+int sk_run_scan(Ctx *c)
+{
+    Sankoff &k = c->sk;
+    ScanPlan &pl = c->plan;
+    const int ntasks = (int)pl.tasks.size();
+    const int rows = pl.n_cand;
+    if (int rc = bind_cost(c)) return rc;
+    if (int rc = sk_ensure_out(c, (size_t)rows + 1)) return rc;
+    if (rows == 0 || ntasks == 0) return 0;
+    MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)rows * k.nseg * sizeof(uint32_t), c->stream));
+    const int nslots = pl.max_slot > 0 ? pl.max_slot : 1;
+    const size_t per_warp = (size_t)nslots * c->S * 32 * sizeof(uint32_t);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
+    const long long warps = (long long)ntasks * (k.Lh / 32);
+    const long long blocks = (warps + wpb - 1) / wpb;
+    if (blocks > 0x7fffffffLL) { set_error("scan grid too large"); return 1; }
+#define SK_SCAN_LAUNCH                                                                                                         \
+    {                                                                                                                          \
+        static size_t configured = 0;                                                                                          \
+        if (smem > 48 * 1024 && smem > configured) {                                                                           \
+            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));   \
+            configured = 200 * 1024;                                                                                           \
+        }                                                                                                                      \
+        k_sk_scan<S_><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh,       \
+            c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
+            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout);                                                                  \
+    }
+    SK_DISPATCH(SK_SCAN_LAUNCH);
+#undef SK_SCAN_LAUNCH
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
+{
+    Sankoff &k = c->sk;
+    ScanPlan &pl = c->plan;
+    if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
+    k.h_est.resize(pl.n_cand);
+    if (pl.n_cand > 0) {
+        if (int rc = sk_finish_rows(c, pl.n_cand)) return rc;
+        for (int j = 0; j < pl.n_cand; j++) { mp[j] = k.h_tot[j].x; k.h_est[j] = k.h_tot[j].y; }
+    } else {
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
+    if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
+    if (cand_prune) memcpy(cand_prune, pl.cand_prune.data(), pl.n_cand * sizeof(int32_t));
+    return 0;
+}
+
+}  // namespace mpgpu

@@ -66,6 +66,10 @@ def lib():
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
     L.mpgpu_reps_timing.argtypes = [vp, vp, vp, vp, vp]
     L.mpgpu_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.mpgpu_set_cost_matrix.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.mpgpu_sankoff_layout.argtypes = [vp, vp, vp, vp, i32]
+    L.mpgpu_sankoff_view.argtypes = [vp, i32, i32, vp]
+    L.mpgpu_scan_bounds.argtypes = [vp, vp, i32]
     L.mpgpu_reps_current_tree.argtypes = [vp, vp]
     L.mpgpu_reps_candidates.argtypes = [vp, vp, i32, vp]
     L.mpgpu_reps_candidates_device.argtypes = [vp, vp, i32, vp, vp]
@@ -317,6 +321,37 @@ class Engine:
                                                 C.c_void_p(rng_fn_ptr), C.c_void_p(rng_user) if rng_user else None,
                                                 _p(scores), C.byref(nins)))
         return scores, tbn, tbs, nins.value
+
+    # -- R11 (-cost)
+    def set_cost_matrix(self, cost, segment_upper):
+        """pllCostMatrix + pllSegmentUpper: switches the context to Sankoff weighted parsimony (None: back to Fitch).
+        Returns highest_cost."""
+        if cost is None:
+            self._ck(self.L.mpgpu_set_cost_matrix(self.h, None, 0, None, 0, None))
+            return 0
+        cost = np.ascontiguousarray(cost, dtype=np.uint32)
+        seg = np.ascontiguousarray(segment_upper, dtype=np.int32)
+        hi = C.c_uint32()
+        self._ck(self.L.mpgpu_set_cost_matrix(self.h, _p(cost), cost.shape[0], _p(seg), len(seg), C.byref(hi)))
+        return hi.value
+
+    def sankoff_layout(self):
+        L, nb = C.c_int(), C.c_int()
+        self._ck(self.L.mpgpu_sankoff_layout(self.h, C.byref(L), C.byref(nb), None, 0))
+        lb = np.zeros(max(nb.value, 1), dtype=np.uint32)
+        self._ck(self.L.mpgpu_sankoff_layout(self.h, None, None, _p(lb), nb.value))
+        return L.value, lb[:nb.value]
+
+    def sankoff_view(self, node, slot=0):
+        L, _ = self.sankoff_layout()
+        out = np.zeros((L, self.S), dtype=np.uint16)
+        self._ck(self.L.mpgpu_sankoff_view(self.h, node, slot, _p(out)))
+        return out
+
+    def scan_bounds(self, n_cand):
+        out = np.zeros(max(n_cand, 1), dtype=np.uint32)
+        self._ck(self.L.mpgpu_scan_bounds(self.h, _p(out), max(n_cand, 1)))
+        return out[:n_cand]
 
     # -- R7
     def stepwise_addition(self, seed, spr_dist, rng_fn_ptr, rng_user=None):

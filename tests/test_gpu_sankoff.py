@@ -1,0 +1,194 @@
+"""GPU parity, -cost (Sankoff weighted parsimony): the CUDA path through the C-ABI against
+the golden vectors tools/make_golden_sankoff.py produced by running the reference itself (tip vectors, node
+vectors, node scores, remainder bounds, every insertion score of a sweep, the decisions of the same sweep in
+plain mode with the lower-bound early exit, whole searches in both modes, RAS trees) and against the C oracle
+on further seeded cases.  Bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import portlib
+from tests.helpers import make_case
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FILES = sorted(glob.glob(os.path.join(GOLD, "sankoff_*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in FILES]
+
+
+def _engine(g, tree=True):
+    from mpboot_b200.engine import Engine
+    eng = Engine()
+    eng.load_alignment(g["codes"], g["weights"], int(g["datatype"]))
+    if tree:
+        eng.set_tree(g["bn"], g["bs"])
+    assert eng.set_cost_matrix(g["cost"], g["seg"]) == int(g["highest"])
+    return eng
+
+
+def _replay_visit(mp, est, cref, cprune, best_in, early):
+    """testInsertParsimony's bookkeeping (:2168-2176) over one visit, with the reference's early exit (:951-956)"""
+    best, hits, ins, rem = int(best_in), 1, 0, 0
+    for j in range(len(mp)):
+        if early and int(est[j]) > best:
+            continue
+        m = int(mp[j])
+        if m < best:
+            hits = 1
+        elif m == best:
+            hits += 1
+        if m < best or (m == best and portlib.lib().mporacle_random_double(None) <= 1.0 / hits):
+            best, ins, rem = m, int(cref[j]), int(cprune[j])
+    return np.array([best, rem // 3, rem % 3 if rem else 0, ins // 3, ins % 3 if ins else 0, hits], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_golden_vectors_scores_bounds(path):
+    g = dict(np.load(path))
+    n, ninf = int(g["n"]), int(g["n_inf"])
+    eng = _engine(g)
+    L, lb = eng.sankoff_layout()
+    assert L == int(g["L"]) and np.array_equal(lb, g["lower_bounds"])
+    for t in range(1, n + 1):
+        assert np.array_equal(eng.sankoff_view(t), g["tips"][t - 1])
+    assert eng.tree_score() == int(g["score"])
+    order = eng.visit_order()
+    assert np.array_equal(order[1:], g["order"][1:])
+    for k in range(n + 1, 2 * n - 1):                    # the reference's vectors face tr->start after evaluate(start, full)
+        node, slot = int(order[k]) // 3, int(order[k]) % 3
+        assert np.array_equal(eng.sankoff_view(node, slot), g["node_vect"][node - n - 1]), node
+        assert eng.view_length(node, slot) == int(g["node_score"][node - n - 1])
+    pp, sm = eng.pattern_parsimony()
+    assert sm == int(g["ptn_sum"]) and np.array_equal(pp[:ninf], g["ptn_pars"][:ninf])
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_golden_insertion_scores_and_early_exit(path):
+    g = dict(np.load(path))
+    n, mt = int(g["n"]), int(g["maxtrav"])
+    eng = _engine(g)
+    vb, mp, cref, cprune = eng.scan_visits(g["order"], 1, 2 * n - 2, 1, mt)
+    est = eng.scan_bounds(len(mp))
+    assert np.array_equal(vb, g["visit_begin"])
+    assert np.array_equal(mp.astype(np.int32), g["visit_mp"])                  # exact score of every insertion
+    for early, key, draws in ((True, "plain_visit_out", int(g["plain_draws"])), (False, "visit_out", None)):
+        portlib.seed_rng(31337)
+        for i in range(1, 2 * n - 1):
+            a, b = vb[i - 1], vb[i]
+            out = _replay_visit(mp[a:b], est[a:b], cref[a:b], cprune[a:b], int(g["score"]), early and len(g["seg"]) > 1)
+            assert np.array_equal(out, g[key][i - 1]), (key, i)
+        if draws is not None:
+            assert portlib.rng_draws() == draws
+    for first in (1, n, 2 * n - 2):                                            # batching must not matter
+        vb1, mp1, _, _ = eng.scan_visits(g["order"], first, 1, 1, mt)
+        assert np.array_equal(mp1.astype(np.int32), g["visit_mp"][vb[first - 1]: vb[first]])
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_golden_searches_and_ras(path):
+    g = dict(np.load(path))
+    mt = int(g["maxtrav"])
+    eng = _engine(g, tree=False)
+    for tag, exact in (("plain", 0), ("bb", 1)):
+        eng.set_option("sankoff_exact", exact)
+        portlib.seed_rng(2024)
+        ret, bn, bs, nins = eng.optimize_spr(g["bn"], g["bs"], portlib.rng_fn_address(), 1, mt)
+        assert ret == int(g["opt_%s_ret" % tag])
+        assert portlib.rng_draws() == int(g["opt_%s_draws" % tag])
+        assert np.array_equal(bn[3:], g["opt_%s_bn" % tag][3:]) and np.array_equal(bs[3:], g["opt_%s_bs" % tag][3:])
+        eng.set_tree(bn, bs)
+        assert eng.tree_score() == ret
+    eng.set_option("sankoff_exact", 0)
+    portlib.seed_rng(77)
+    best, bn, bs, nins, _ = eng.stepwise_addition(int(g["ras_seed"]), mt, portlib.rng_fn_address())
+    assert best == int(g["ras_ret"])
+    assert portlib.rng_draws() == int(g["ras_draws"])
+    assert np.array_equal(bn[3:], g["ras_bn"][3:]) and np.array_equal(bs[3:], g["ras_bs"][3:])
+
+
+@pytest.mark.parametrize("n,L,dt,seed,hi", [(60, 4000, 1, 51, 6), (40, 1200, 2, 52, 5), (25, 600, 6, 53, 4), (18, 400, 0, 54, 7),
+                                             (90, 3000, 1, 55, 40)])
+def test_oracle_seeded_cases(n, L, dt, seed, hi):
+    from mpboot_b200.engine import Engine
+    c = make_case(n, L, dt, seed)
+    S = {0: 2, 1: 4, 2: 20, 6: 32}[dt]
+    rng = np.random.default_rng(seed)
+    cost = rng.integers(1, hi, size=(S, S)); cost = np.minimum(cost, cost.T); np.fill_diagonal(cost, 0)
+    ninf = c["n_inf"]
+    seg = np.array([s for s in range(80, ninf, 80)] + [ninf], dtype=np.int32)
+    ora = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    hi_o = ora.set_cost_matrix(cost.astype(np.uint32), seg)
+    ora.set_ring(c["bn"], c["bs"])
+    eng = Engine()
+    eng.load_alignment(c["codes"], c["weights"], dt)
+    assert eng.set_cost_matrix(cost, seg) == hi_o
+    eng.set_tree(c["bn"], c["bs"])
+    ora.allocate(per_site=False)
+    s0 = ora.evaluate_full(per_site=False)
+    assert eng.tree_score() == s0
+    assert np.array_equal(eng.sankoff_layout()[1], ora.remainder_bounds())
+    ora.allocate(per_site=True)
+    assert ora.evaluate_full(per_site=True) == s0
+    pp, sm = eng.pattern_parsimony()
+    opp, osm = ora.pattern_parsimony(ninf)
+    assert sm == osm and np.array_equal(pp[:ninf], opp[:ninf])
+    order = eng.visit_order()
+    vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, 5)
+    portlib.seed_rng(5)
+    for i in range(1, 2 * n - 1):
+        ora.record(False)
+        ora.rearrange(i, 1, 5, True, s0)
+        assert np.array_equal(ora.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32)), i
+    for exact in (0, 1):                                  # whole searches, both modes, then RAS
+        eng.set_option("sankoff_exact", exact)
+        portlib.seed_rng(99)
+        ora.set_ring(c["bn"], c["bs"]); ora.allocate(bool(exact))
+        want = ora.optimize_spr(1, 5, bb=bool(exact))
+        wd = portlib.rng_draws()
+        wbn, wbs = ora.get_ring()
+        portlib.seed_rng(99)
+        ret, bn, bs, _ = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, 5)
+        assert ret == want and portlib.rng_draws() == wd
+        assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+    eng.set_option("sankoff_exact", 0)
+    portlib.seed_rng(11)
+    want = ora.ras(777 + seed, 4); wd = portlib.rng_draws(); wbn, wbs = ora.get_ring()
+    portlib.seed_rng(11)
+    best, bn, bs, _, _ = eng.stepwise_addition(777 + seed, 4, portlib.rng_fn_address())
+    assert best == want and portlib.rng_draws() == wd
+    assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+
+
+def test_unit_costs_equal_fitch_and_switch_back():
+    from mpboot_b200.engine import Engine
+    c = make_case(30, 2000, 1, 61)
+    eng = Engine()
+    eng.load_alignment(c["codes"], c["weights"], 1)
+    eng.set_tree(c["bn"], c["bs"])
+    fitch = eng.tree_score()
+    order = eng.visit_order()
+    vb, mp_f, _, _ = eng.scan_visits(order, 1, 58, 1, 4)
+    eng.set_cost_matrix((1 - np.eye(4)).astype(np.uint32), np.array([c["n_inf"]], dtype=np.int32))
+    assert eng.tree_score() == fitch
+    vb2, mp_s, _, _ = eng.scan_visits(order, 1, 58, 1, 4)
+    assert np.array_equal(vb, vb2) and np.array_equal(mp_f, mp_s)
+    eng.set_cost_matrix(None, None)
+    assert eng.tree_score() == fitch
+
+
+def test_preconditions_fail_loudly():
+    from mpboot_b200.engine import Engine, MpGpuError
+    c = make_case(12, 300, 1, 62)
+    eng = Engine()
+    eng.load_alignment(c["codes"], c["weights"], 1)
+    seg = np.array([c["n_inf"]], dtype=np.int32)
+    asym = np.array([[0, 1, 2, 2], [2, 0, 2, 2], [2, 2, 0, 2], [2, 2, 2, 0]], dtype=np.uint32)
+    with pytest.raises(MpGpuError, match="asymmetric"):
+        eng.set_cost_matrix(asym, seg)
+    with pytest.raises(MpGpuError, match="too large"):
+        eng.set_cost_matrix((6000 * (1 - np.eye(4))).astype(np.uint32), seg)
+    with pytest.raises(MpGpuError, match="segment_upper"):
+        eng.set_cost_matrix((1 - np.eye(4)).astype(np.uint32), np.array([c["n_inf"] - 1], dtype=np.int32))
