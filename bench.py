@@ -231,6 +231,95 @@ def cpu_baseline(case, maxtrav, budget_s=20.0):
     return ins, dt, kind, "%d of %d node visits of the same sweep (%d insertions), plain mode" % (nvis, 2 * n - 2, ins)
 
 
+def bench_cost(case, order, args, flush, stream, local):
+    """the same sweep under -cost (Sankoff weighted parsimony, transitions 1 / transversions 2
+    for DNA, random symmetric costs 1..4 otherwise) on a context of its own.  Device-timed step = memset of the
+    per-(candidate, segment) sums + k_sk_scan (every insertion of the sweep); e2e = mpgpu_scan_visits with host
+    buffers (plan, H2D, k_sk_scan, k_sk_finish, D2H).  CPU baseline = the reference's own Sankoff kernels
+    (evaluateSankoff.../newviewSankoff...SIMD, Vec16us) on one host core, same visits, bounded sample."""
+    import torch
+    from mpboot_b200 import engine
+    from oracle import portlib, reflib
+    n, ninf, dt = case["n"], case["n_inf"], case["datatype"]
+    eng = engine.Engine(device=local, stream=stream)
+    eng.load_alignment(case["codes"], case["weights"], dt)
+    eng.set_tree(case["bn"], case["bs"])
+    S = eng.S
+    seg = do_segmenting(eng.pattern_parsimony()[0][:ninf], case["weights"], ninf)
+    if len(seg) == 0 or seg[-1] != ninf:
+        seg = np.append(seg[seg < ninf], ninf).astype(np.int32)
+    if S == 4:
+        cost = np.array([[0, 2, 1, 2], [2, 0, 2, 1], [1, 2, 0, 2], [2, 1, 2, 0]], dtype=np.uint32)
+    else:
+        r = np.random.default_rng(7).integers(1, 5, size=(S, S)); cost = np.minimum(r, r.T); np.fill_diagonal(cost, 0)
+        cost = cost.astype(np.uint32)
+    eng.set_cost_matrix(cost, seg)
+    score = eng.tree_score()
+    nvis = 2 * n - 2
+    n_cand, n_tasks = eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        flush.zero_(); eng.scan_launch()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record(); eng.scan_launch(); ev[k][1].record()
+    torch.cuda.synchronize()
+    ker_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3 / steps
+    vb, mp, _, _ = eng.scan_finish(n_cand, nvis)
+    t0 = time.time()
+    for _ in range(3):
+        vb2, mp2, _, _ = eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
+    e2e_s = (time.time() - t0) / 3
+    assert np.array_equal(mp, mp2)
+    L, lb = eng.sankoff_layout()
+    alg_bytes = 4.0 * S * L * n_cand                 # canonical: the Q and R cost vectors (u16 [L][S]) of every insertion
+    peak, peak_src = measured_peak()
+    pairs = (L + 63) // 64 * 32
+    out = {"what": "the same sweep under -cost (Sankoff), %d segments" % len(seg), "tree_score": int(score),
+           "insertions_per_step": int(n_cand), "ms_per_step": ker_s * 1e3, "insertions_per_s": n_cand / ker_s,
+           "minplus_u16x2_ops_per_s": n_cand / ker_s * pairs * S * S,
+           "roofline": {"bound": "hbm", "kernel": "k_sk_scan", "achieved": alg_bytes / ker_s / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg_bytes / ker_s / 1e9 / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                        "kernel_ms": ker_s * 1e3, "traffic": measured_traffic(args.workload, "k_sk_scan"),
+                        "note": "canonical accounting 4*S*L bytes per insertion; the kernel is bound by the DPX/ALU pipe "
+                                "(S*S VIADDMNMX.U16x2 per pattern pair per insertion), see profiles/"},
+           "e2e": {"insertions_per_s": n_cand / e2e_s, "ms_per_step": e2e_s * 1e3,
+                   "h2d_bytes_per_step": int(eng.scan_plan_bytes()), "d2h_bytes_per_step": 8 * int(n_cand)}}
+    if not args.no_search:
+        rng = engine.HostRng(12345)
+        t0 = time.time()
+        ret, bn, bs, nins = eng.optimize_spr(case["bn"], case["bs"], rng.fn, 1, args.maxtrav, rng_user=rng.user)
+        out["search"] = {"what": "mpgpu_optimize_spr under -cost from the random tree (early exit replayed)", "wall_s": time.time() - t0,
+                         "insertions": int(nins), "final_score": int(ret)}
+    if not args.no_cpu_baseline:
+        use_ref = reflib.available()
+        ref = (reflib.RefEngine(case["chars"], case["weights"], dt, n_informative=ninf) if use_ref
+               else portlib.OracleEngine(case["codes"], case["weights"], dt))
+        ref.set_cost_matrix(cost, seg)
+        ref.set_ring(case["bn"], case["bs"])
+        ref.allocate(per_site=True)
+        s0 = ref.evaluate_full(per_site=True)
+        assert s0 == score, "reference and device disagree on the -cost tree score"
+        ins, nv = 0, 0
+        t0 = time.time()
+        for i in range(1, nvis + 1):
+            ref.record(False)
+            ref.rearrange(i, 1, args.maxtrav, True, s0)
+            got = ref.saved()[1:]
+            assert np.array_equal(got, mp[vb[i - 1]: vb[i]].astype(np.int32)), "insertion scores differ from the reference"
+            ins += len(got); nv += 1
+            if time.time() - t0 > args.cpu_budget:
+                break
+        dt_s = time.time() - t0
+        out["cpu_baseline"] = {"insertions_per_s": ins / dt_s, "cores": 1, "kind": "reference" if use_ref else "port",
+                               "sample": "%d of %d node visits of the same sweep (%d insertions, exact mode, every score checked "
+                                         "against the device) in %.1f s" % (nv, nvis, ins, dt_s)}
+    eng.close()
+    return out
+
+
 def make_replicates(case, B, seed=5):
     """boot_samples_pars as MPBoot draws them: multinomial resampling of the sites, counted per pattern
     (alignment.cpp:1985-1990, iqtree.cpp:285-313)."""
@@ -555,6 +644,8 @@ def run_ours(args):
             if not args.no_cpu_baseline:
                 bb["cpu_baseline"] = cpu_baseline_bb(case, boot, seg, args.maxtrav, budget_s=args.cpu_budget)
             line["bb"] = bb
+        if world == 1 and not args.no_cost:
+            line["cost"] = bench_cost(case, order, args, flush, stream, local)
         if world == 1 and not args.no_cpu_baseline:
             ins, dt, kind, sample = cpu_baseline(case, args.maxtrav, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": ins / dt * ops_per_ins, "unit": UNIT, "cores": 1, "kind": kind,
@@ -576,6 +667,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bb", action="store_true", help="skip the -bb (replicate scoring) section")
+    ap.add_argument("--no-cost", action="store_true", help="skip the -cost (Sankoff) section")
     ap.add_argument("--no-search", action="store_true", help="skip the whole-search (pllOptimizeSprParsimony) section")
     ap.add_argument("--replicates", type=int, default=1000)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

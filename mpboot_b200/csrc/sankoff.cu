@@ -49,46 +49,124 @@ static int bind_cost(Ctx *c)
     return 0;
 }
 
+// ---- layout ---------------------------------------------------------------------------------
+// A view is [chunk][state][lane][V] 32-bit words: a chunk is 32*V pattern pairs, lane l of a warp owns
+// V consecutive pairs of it, and the S state words of a lane sit at a compile-time distance
+// (32*V words) from each other -- one address computation per view, immediate offsets per state.
+template <int S> struct SkLay { static const int V = S <= 4 ? 2 : 1; static const int CH = 32 * V; };
+static inline int sk_vpl(int S) { return S <= 4 ? 2 : 1; }
+
+template <int V> struct SkVec;
+template <> struct SkVec<1> { typedef uint32_t T; };
+template <> struct SkVec<2> { typedef uint2 T; };
+template <int V> __device__ __forceinline__ void sk_ldv(const uint32_t *p, uint32_t *r);
+template <> __device__ __forceinline__ void sk_ldv<1>(const uint32_t *p, uint32_t *r) { r[0] = __ldg(p); }
+template <> __device__ __forceinline__ void sk_ldv<2>(const uint32_t *p, uint32_t *r)
+{
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p)); r[0] = t.x; r[1] = t.y;
+}
+template <int V> __device__ __forceinline__ void sk_stv(uint32_t *p, const uint32_t *r);
+template <> __device__ __forceinline__ void sk_stv<1>(uint32_t *p, const uint32_t *r) { p[0] = r[0]; }
+template <> __device__ __forceinline__ void sk_stv<2>(uint32_t *p, const uint32_t *r) { *reinterpret_cast<uint2 *>(p) = make_uint2(r[0], r[1]); }
+
+// the cost matrix in registers (small S) or read from the constant bank at every use
+template <int S> struct SkCost {
+    uint32_t m[S <= 4 ? S * S : 1];
+    __device__ __forceinline__ void init()
+    {
+        if (S <= 4) {
+#pragma unroll
+            for (int i = 0; i < (S <= 4 ? S * S : 1); i++) m[i] = c_cost2[i];
+        }
+    }
+    __device__ __forceinline__ uint32_t at(int z, int x) const { return S <= 4 ? m[(z * S + x) % (S <= 4 ? S * S : 1)] : c_cost2[z * S + x]; }
+};
+
 // ---- device helpers -------------------------------------------------------------------------
-template <int S>
-__device__ __forceinline__ void sk_minplus(const uint32_t (&v)[S], uint32_t (&o)[S])
+// v, o: [S][V]
+template <int S, int V>
+__device__ __forceinline__ void sk_minplus(const SkCost<S> &cm, const uint32_t (&v)[S * V], uint32_t (&o)[S * V])
 {
 #pragma unroll
     for (int z = 0; z < S; z++) {
-        uint32_t acc = 0xFFFFFFFFu;
 #pragma unroll
-        for (int x = 0; x < S; x++) acc = __viaddmin_u16x2(v[x], c_cost2[z * S + x], acc);
-        o[z] = acc;
+        for (int k = 0; k < V; k++) {
+            uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+            for (int x = 0; x < S; x++) acc = __viaddmin_u16x2(v[x * V + k], cm.at(z, x), acc);
+            o[z * V + k] = acc;
+        }
     }
 }
 
-template <int S>
-__device__ __forceinline__ void sk_load(const uint32_t *__restrict__ p, size_t Lh, uint32_t (&r)[S])
+template <int S, int V>
+__device__ __forceinline__ void sk_load(const uint32_t *__restrict__ p, uint32_t (&r)[S * V])
 {
 #pragma unroll
-    for (int s = 0; s < S; s++) r[s] = __ldg(p + s * Lh);
+    for (int s = 0; s < S; s++) sk_ldv<V>(p + s * 32 * V, &r[s * V]);
 }
 
-// per-pattern minimum over the states of a + b + c (packed u16x2)
-template <int S>
-__device__ __forceinline__ uint32_t sk_best3(const uint32_t (&a)[S], const uint32_t *__restrict__ pb,
-                                             const uint32_t *__restrict__ pc, size_t Lh)
+// per-pattern minimum over the states of a + b + c (packed u16x2), V words
+template <int S, int V>
+__device__ __forceinline__ void sk_best3(const uint32_t (&a)[S * V], const uint32_t *__restrict__ pb,
+                                         const uint32_t *__restrict__ pc, uint32_t (&best)[V])
 {
-    uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-    for (int z = 0; z < S; z++) best = __vminu2(best, a[z] + __ldg(pb + z * Lh) + __ldg(pc + z * Lh));
-    return best;
-}
-
-// weighted contribution of the lane's two patterns, summed per segment over the warp
-__device__ __forceinline__ void sk_accum(uint32_t best, uint2 w, int myseg, int seg_lo, int seg_hi,
-                                         uint32_t *__restrict__ out_row, bool lane0)
-{
-    const uint32_t v = (best & 0xFFFFu) * w.x + (best >> 16) * w.y;
-    for (int s = seg_lo; s <= seg_hi; s++) {
-        const uint32_t r = __reduce_add_sync(0xffffffffu, myseg == s ? v : 0u);
-        if (lane0 && r) atomicAdd(out_row + s, r);
+    for (int k = 0; k < V; k++) best[k] = 0xFFFFFFFFu;
+#pragma unroll
+    for (int z = 0; z < S; z++) {
+        uint32_t b[V], c[V];
+        sk_ldv<V>(pb + z * 32 * V, b);
+        sk_ldv<V>(pc + z * 32 * V, c);
+#pragma unroll
+        for (int k = 0; k < V; k++) best[k] = __vminu2(best[k], a[z * V + k] + b[k] + c[k]);
     }
+}
+
+// Which segments a warp's lanes belong to: lanes are consecutive in pattern space, so a segment is a lane
+// range.  uniform: the whole chunk lies in one segment (one REDUX); otherwise a warp prefix sum gives
+// every segment's sum at its last lane (first = first lane of the lane's segment).
+struct SkSeg { int myseg, first; bool uniform, last, lane0; };
+__device__ __forceinline__ SkSeg sk_seg_setup(int myseg, int lane)
+{
+    SkSeg g;
+    g.myseg = myseg; g.lane0 = lane == 0;
+    const unsigned same = __match_any_sync(0xffffffffu, myseg);
+    g.first = __ffs(same) - 1;
+    g.last = (31 - __clz(same)) == lane;
+    g.uniform = same == 0xffffffffu;
+    return g;
+}
+
+// weighted contribution of the lane's 2*V patterns, summed per segment over the warp
+template <int V>
+__device__ __forceinline__ void sk_accum(const uint32_t (&best)[V], const uint2 (&w)[V], const SkSeg &g,
+                                         uint32_t *__restrict__ out_row)
+{
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < V; k++) v += (best[k] & 0xFFFFu) * w[k].x + (best[k] >> 16) * w[k].y;
+    if (g.uniform) {
+        const uint32_t r = __reduce_add_sync(0xffffffffu, v);
+        if (g.lane0 && r) atomicAdd(out_row + g.myseg, r);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+    const uint32_t before = __shfl_sync(0xffffffffu, v, (g.first + 31) & 31);
+    if (g.last) {
+        const uint32_t r = v - (g.first ? before : 0u);
+        if (r) atomicAdd(out_row + g.myseg, r);
+    }
+}
+
+// word index of pattern pair i, state s, in a view
+template <int S>
+__device__ __forceinline__ size_t sk_index(int i, int s)
+{
+    constexpr int V = SkLay<S>::V;
+    return ((size_t)(i / (32 * V)) * S + s) * 32 * V + i % (32 * V);
 }
 
 // ---- tips: v[x] = 0 if the tip's code allows x else highest (:2739-2745); padded patterns all 0 ----
@@ -104,50 +182,61 @@ __global__ void __launch_bounds__(128) k_sk_tips(const uint8_t *__restrict__ cod
     uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
     if (2 * i < n_inf) m0 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i]]];
     if (2 * i + 1 < n_inf) m1 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i + 1]]];
+    SkCost<S> cm; cm.init();
     uint32_t v[S], o[S];
 #pragma unroll
     for (int x = 0; x < S; x++) v[x] = ((m0 >> x) & 1u ? 0u : highest) | ((m1 >> x) & 1u ? 0u : highest) << 16;
-    sk_minplus<S>(v, o);
-    uint32_t *dst = views + (size_t)tip * vstride + i;
+    sk_minplus<S, 1>(cm, v, o);
+    uint32_t *dst = views + (size_t)tip * vstride;
 #pragma unroll
-    for (int z = 0; z < S; z++) dst[(size_t)z * Lh] = o[z];
+    for (int z = 0; z < S; z++) dst[sk_index<S>(i, z)] = o[z];
 }
 
-// ---- newview (:477-551): one thread per (triple, pattern pair) -------------------------------
+// ---- newview (:477-551): one warp per (triple, chunk) -------------------------------------------
 // score[dst] += sum over the reference's L patterns of min_z (a' + b')[z]  (unweighted, :547)
 template <int S>
 __global__ void __launch_bounds__(128) k_sk_level(uint32_t *views, size_t vstride, int Lh, int Lref_pairs,
                                                   const Triple *__restrict__ triples, int ntriples,
                                                   uint32_t *__restrict__ vscore, uint32_t *__restrict__ compact)
 {
-    const int per = Lh / 32;                       // warps per triple
+    constexpr int V = SkLay<S>::V;
+    const int per = Lh / (32 * V);                 // warps per triple
     const int gw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (gw >= ntriples * per) return;
     const int lane = threadIdx.x & 31;
-    const int ti = gw / per, i = (gw % per) * 32 + lane;
+    const int ti = gw / per, chunk = gw % per;
     const Triple tr = triples[ti];
-    const uint32_t *pa = views + (size_t)tr.a * vstride + i, *pb = views + (size_t)tr.b * vstride + i;
-    uint32_t v[S], o[S];
-    uint32_t mn = 0xFFFFFFFFu;
+    const size_t off = (size_t)chunk * S * 32 * V + lane * V;
+    SkCost<S> cm; cm.init();
+    uint32_t v[S * V], o[S * V], b[S * V], mn[V];
+    sk_load<S, V>(views + (size_t)tr.a * vstride + off, v);
+    sk_load<S, V>(views + (size_t)tr.b * vstride + off, b);
 #pragma unroll
-    for (int x = 0; x < S; x++) { v[x] = pa[(size_t)x * Lh] + pb[(size_t)x * Lh]; mn = __vminu2(mn, v[x]); }
-    sk_minplus<S>(v, o);
-    uint32_t *dst = views + (size_t)tr.dst * vstride + i;
+    for (int k = 0; k < V; k++) mn[k] = 0xFFFFFFFFu;
 #pragma unroll
-    for (int z = 0; z < S; z++) dst[(size_t)z * Lh] = o[z];
-    const uint32_t contrib = i < Lref_pairs ? (mn & 0xFFFFu) + (mn >> 16) : 0u;
+    for (int x = 0; x < S; x++)
+#pragma unroll
+        for (int k = 0; k < V; k++) { v[x * V + k] += b[x * V + k]; mn[k] = __vminu2(mn[k], v[x * V + k]); }
+    sk_minplus<S, V>(cm, v, o);
+    uint32_t *dst = views + (size_t)tr.dst * vstride + off;
+#pragma unroll
+    for (int z = 0; z < S; z++) sk_stv<V>(dst + z * 32 * V, &o[z * V]);
+    uint32_t contrib = 0;
+#pragma unroll
+    for (int k = 0; k < V; k++)
+        if (chunk * 32 * V + lane * V + k < Lref_pairs) contrib += (mn[k] & 0xFFFFu) + (mn[k] >> 16);
     const uint32_t r = __reduce_add_sync(0xffffffffu, contrib);
     if (lane == 0 && r) atomicAdd(compact ? compact + ti : vscore + tr.dst, r);
 }
 
-// raw cost vector of a directed view (tests): a' + b' for an inner view, the tip vector otherwise
-__global__ void k_sk_raw(const uint32_t *__restrict__ views, size_t vstride, int Lh, int S, int va, int vb,
-                         uint32_t *__restrict__ out)
+// raw cost vector of a directed view (tests): a' + b' for an inner view, the tip vector otherwise; out = [S][Lh]
+template <int S>
+__global__ void k_sk_raw(const uint32_t *__restrict__ views, size_t vstride, int Lh, int va, int vb, uint32_t *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Lh) return;
     for (int x = 0; x < S; x++)
-        out[(size_t)x * Lh + i] = views[(size_t)va * vstride + (size_t)x * Lh + i] + views[(size_t)vb * vstride + (size_t)x * Lh + i];
+        out[(size_t)x * Lh + i] = views[(size_t)va * vstride + sk_index<S>(i, x)] + views[(size_t)vb * vstride + sk_index<S>(i, x)];
 }
 __global__ void k_sk_raw_tip(const uint8_t *__restrict__ codes, int P, int tip, const int32_t *__restrict__ inf_ptn, int n_inf,
                              const uint32_t *__restrict__ mask_table, uint32_t highest, int Lh, int S, uint32_t *__restrict__ out)
@@ -163,51 +252,86 @@ __global__ void k_sk_raw_tip(const uint8_t *__restrict__ codes, int P, int tip, 
 
 // ---- junctions: score of the tree seen from an inner node whose three neighbours are a, b, c ----
 // (evaluateSankoff... :880-961 on any edge of that node; stepwise insertion of a tip c into the
-// branch (a, b)).  One warp per (junction, 64-pattern chunk); ptn_out = per-pattern minimum of
-// junction 0 (pllComputeSankoffPatternParsimony).
+// branch (a, b)).  One warp per (junction, chunk); ptn_out = per-pattern minimum of junction 0
+// (pllComputeSankoffPatternParsimony), plain pair order.
 template <int S>
 __global__ void __launch_bounds__(128) k_sk_junction(const uint32_t *__restrict__ views, size_t vstride, int Lh,
                                                      const int4 *__restrict__ list, int count,
                                                      const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
                                                      uint32_t *__restrict__ segout, uint32_t *__restrict__ ptn_out)
 {
-    const int nchunks = Lh / 32;
+    constexpr int V = SkLay<S>::V;
+    const int nchunks = Lh / (32 * V);
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= (int64_t)count * nchunks) return;
     const int lane = threadIdx.x & 31;
     const int chunk = (int)(gw / count), e = (int)(gw % count);
-    const int i = chunk * 32 + lane;
+    const size_t off = (size_t)chunk * S * 32 * V + lane * V;
+    const int i0 = chunk * 32 * V + lane * V;
     const int4 j = __ldg(list + e);
-    uint32_t a[S];
-    sk_load<S>(views + (size_t)j.x * vstride + i, (size_t)Lh, a);
-    const uint32_t best = sk_best3<S>(a, views + (size_t)j.y * vstride + i, views + (size_t)j.z * vstride + i, (size_t)Lh);
-    if (ptn_out && e == 0) ptn_out[i] = best;
-    const uint2 w = __ldg(wts + i);
-    const int myseg = __ldg(segof + i);
-    const int seg_lo = __shfl_sync(0xffffffffu, myseg, 0), seg_hi = __shfl_sync(0xffffffffu, myseg, 31);
-    sk_accum(best, w, myseg, seg_lo, seg_hi, segout + (size_t)e * nseg, lane == 0);
+    uint32_t a[S * V], best[V];
+    sk_load<S, V>(views + (size_t)j.x * vstride + off, a);
+    sk_best3<S, V>(a, views + (size_t)j.y * vstride + off, views + (size_t)j.z * vstride + off, best);
+    if (ptn_out && e == 0) {
+#pragma unroll
+        for (int k = 0; k < V; k++) ptn_out[i0 + k] = best[k];
+    }
+    uint2 w[V];
+#pragma unroll
+    for (int k = 0; k < V; k++) w[k] = __ldg(wts + i0 + k);
+    const SkSeg g = sk_seg_setup(__ldg(segof + i0), lane);
+    sk_accum<V>(best, w, g, segout + (size_t)e * nseg);
 }
 
 // ---- the SPR scan (testInsertParsimony batched; same program streams as k_spr_scan) ------------
-// One warp = (task, chunk of 32 pattern pairs).  The stack holds U' (transformed up-views) per
-// lane in shared memory: [slot][state][lane].
-template <int S>
-__device__ __forceinline__ void sk_child(const uint32_t (&U)[S], const uint32_t *__restrict__ px, const uint32_t *__restrict__ pc,
-                                         const uint32_t *__restrict__ ps, size_t Lh,
+// One warp = (task, chunk).  The stack holds U' (transformed up-views) per lane in shared memory:
+// [slot][state][lane][V].
+template <int S, int V>
+__device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U)[S * V], const uint32_t *__restrict__ px,
+                                         const uint32_t *__restrict__ pc, const uint32_t *__restrict__ ps,
                                          bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
-                                         uint2 w, int myseg, int seg_lo, int seg_hi, bool lane0)
+                                         const uint2 (&w)[V], const SkSeg &g)
 {
-    uint32_t U1[S], U1p[S];
+    uint32_t U1[S * V], U1p[S * V];
+    sk_load<S, V>(px, U1);
 #pragma unroll
-    for (int x = 0; x < S; x++) U1[x] = U[x] + __ldg(px + x * Lh);
-    sk_minplus<S>(U1, U1p);
+    for (int x = 0; x < S * V; x++) U1[x] += U[x];
+    sk_minplus<S, V>(cm, U1, U1p);
     if (do_dst) {
 #pragma unroll
-        for (int z = 0; z < S; z++) dst[z * 32] = U1p[z];
+        for (int z = 0; z < S; z++) sk_stv<V>(dst + z * 32 * V, &U1p[z * V]);
     }
     if (do_out) {
-        const uint32_t best = sk_best3<S>(U1p, pc, ps, Lh);
-        sk_accum(best, w, myseg, seg_lo, seg_hi, out_row, lane0);
+        uint32_t best[V];
+        sk_best3<S, V>(U1p, pc, ps, best);
+        sk_accum<V>(best, w, g, out_row);
+    }
+}
+
+// register form (small S): X = sibling view, C = the child's own view, Sv = pruned subtree, all already loaded
+template <int S, int V>
+__device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (&U)[S * V], const uint32_t (&X)[S * V],
+                                           const uint32_t (&C)[S * V], const uint32_t (&Sv)[S * V],
+                                           bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
+                                           const uint2 (&w)[V], const SkSeg &g)
+{
+    uint32_t U1[S * V], U1p[S * V];
+#pragma unroll
+    for (int x = 0; x < S * V; x++) U1[x] = U[x] + X[x];
+    sk_minplus<S, V>(cm, U1, U1p);
+    if (do_dst) {
+#pragma unroll
+        for (int z = 0; z < S; z++) sk_stv<V>(dst + z * 32 * V, &U1p[z * V]);
+    }
+    if (do_out) {
+        uint32_t best[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) best[k] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int z = 0; z < S; z++)
+#pragma unroll
+            for (int k = 0; k < V; k++) best[k] = __vminu2(best[k], U1p[z * V + k] + C[z * V + k] + Sv[z * V + k]);
+        sk_accum<V>(best, w, g, out_row);
     }
 }
 
@@ -219,45 +343,83 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
                                                  const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
                                                  uint32_t *__restrict__ segout)
 {
+    constexpr int V = SkLay<S>::V;
+    constexpr bool HOLD = S <= 4;         // child views and the pruned subtree's view live in registers; next op prefetched
     extern __shared__ uint32_t sk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned gw = blockIdx.x * (blockDim.x >> 5) + warp;
-    const unsigned nchunks = Lh / 32;
+    const unsigned nchunks = Lh / (32 * V);
     if (gw >= (unsigned)ntasks * nchunks) return;
     const unsigned chunk = gw / (unsigned)ntasks, ti = gw - chunk * (unsigned)ntasks;
     const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
     const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
-    const size_t L = (size_t)Lh;
-    const int i = chunk * 32 + lane;
-    uint32_t *stack = sk_smem + (size_t)warp * nslots * S * 32 + lane;
-    const bool lane0 = lane == 0;
-    const uint2 w = __ldg(wts + i);
-    const int myseg = __ldg(segof + i);
-    const int seg_lo = __shfl_sync(0xffffffffu, myseg, 0), seg_hi = __shfl_sync(0xffffffffu, myseg, 31);
+    const int i0 = chunk * 32 * V + lane * V;
+    const uint32_t *vbase = reinterpret_cast<const uint32_t *>(views4) + (size_t)chunk * S * 32 * V + lane * V;
+    uint32_t *stack = sk_smem + (size_t)warp * nslots * S * 32 * V + lane * V;
+    uint2 w[V];
+#pragma unroll
+    for (int k = 0; k < V; k++) w[k] = __ldg(wts + i0 + k);
+    const SkSeg g = sk_seg_setup(__ldg(segof + i0), lane);
     uint32_t *outc = segout + (size_t)(t1.z - cand_bias) * nseg;
-    const uint32_t *ps = reinterpret_cast<const uint32_t *>(views4 + (uint32_t)t0.x) + i;
+    const uint32_t *ps = vbase + (size_t)(uint32_t)t0.x * 4;
+    SkCost<S> cm; cm.init();
+    const int oe = t1.x;
+    if (t0.w >= oe) return;
 
-    for (int oi = t0.w; oi < t1.x; oi++) {
-        const int2 f = __ldg(offs + oi);
-        const int2 cw = __ldg(ctl + oi);
+    uint32_t Sv[HOLD ? S * V : 1], A[HOLD ? S * V : 1], B[HOLD ? S * V : 1];
+    int2 f = __ldg(offs + t0.w);
+    int2 cwn = __ldg(ctl + t0.w);
+    if (HOLD) {
+        sk_load<S, V>(ps, reinterpret_cast<uint32_t (&)[S * V]>(Sv));
+        sk_load<S, V>(vbase + (size_t)(uint32_t)f.x * 4, reinterpret_cast<uint32_t (&)[S * V]>(A));
+        sk_load<S, V>(vbase + (size_t)(uint32_t)f.y * 4, reinterpret_cast<uint32_t (&)[S * V]>(B));
+    }
+    for (int oi = t0.w; oi < oe; oi++) {
+        const int2 cw = cwn;
+        const int2 fc = f;
+        uint32_t An[HOLD ? S * V : 1], Bn[HOLD ? S * V : 1];
+        if (oi + 1 < oe) {
+            f = __ldg(offs + oi + 1);
+            cwn = __ldg(ctl + oi + 1);
+            if (HOLD) {
+                sk_load<S, V>(vbase + (size_t)(uint32_t)f.x * 4, reinterpret_cast<uint32_t (&)[S * V]>(An));
+                sk_load<S, V>(vbase + (size_t)(uint32_t)f.y * 4, reinterpret_cast<uint32_t (&)[S * V]>(Bn));
+            }
+        }
         const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;
         const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;
-        const uint32_t *pa = reinterpret_cast<const uint32_t *>(views4 + (uint32_t)f.x) + i;
-        const uint32_t *pb = reinterpret_cast<const uint32_t *>(views4 + (uint32_t)f.y) + i;
-        uint32_t U[S];
+        uint32_t U[S * V];
         if (src < 0xfe) {
-            const uint32_t *sp = stack + (size_t)src * S * 32;
+            const uint32_t *sp = stack + (size_t)src * S * 32 * V;
 #pragma unroll
-            for (int z = 0; z < S; z++) U[z] = sp[z * 32];
+            for (int z = 0; z < S; z++) {
+                if (V == 2) { const uint2 t = *reinterpret_cast<const uint2 *>(sp + z * 32 * V); U[z * V] = t.x; U[z * V + V - 1] = t.y; }
+                else U[z * V] = sp[z * 32 * V];
+            }
         } else {
-            sk_load<S>(reinterpret_cast<const uint32_t *>(views4 + (uint32_t)(src == 0xff ? t0.z : t0.y)) + i, L, U);
+            sk_load<S, V>(vbase + (size_t)(uint32_t)(src == 0xff ? t0.z : t0.y) * 4, U);
         }
-        if (o1 != 0xffff || dst1 != 0xff)
-            sk_child<S>(U, pb, pa, ps, L, o1 != 0xffff, outc + (size_t)o1 * nseg, dst1 != 0xff, stack + (size_t)dst1 * S * 32,
-                        w, myseg, seg_lo, seg_hi, lane0);
-        if (o2 != 0xffff || dst2 != 0xff)
-            sk_child<S>(U, pa, pb, ps, L, o2 != 0xffff, outc + (size_t)o2 * nseg, dst2 != 0xff, stack + (size_t)dst2 * S * 32,
-                        w, myseg, seg_lo, seg_hi, lane0);
+        if (HOLD) {
+            if (o1 != 0xffff || dst1 != 0xff)
+                sk_child_r<S, V>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(B), reinterpret_cast<uint32_t (&)[S * V]>(A),
+                                 reinterpret_cast<uint32_t (&)[S * V]>(Sv), o1 != 0xffff, outc + (size_t)o1 * nseg, dst1 != 0xff,
+                                 stack + (size_t)dst1 * S * 32 * V, w, g);
+            if (o2 != 0xffff || dst2 != 0xff)
+                sk_child_r<S, V>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(A), reinterpret_cast<uint32_t (&)[S * V]>(B),
+                                 reinterpret_cast<uint32_t (&)[S * V]>(Sv), o2 != 0xffff, outc + (size_t)o2 * nseg, dst2 != 0xff,
+                                 stack + (size_t)dst2 * S * 32 * V, w, g);
+#pragma unroll
+            for (int x = 0; x < (HOLD ? S * V : 1); x++) { A[x] = An[x]; B[x] = Bn[x]; }
+        } else {
+            const uint32_t *pa = vbase + (size_t)(uint32_t)fc.x * 4;
+            const uint32_t *pb = vbase + (size_t)(uint32_t)fc.y * 4;
+            if (o1 != 0xffff || dst1 != 0xff)
+                sk_child<S, V>(cm, U, pb, pa, ps, o1 != 0xffff, outc + (size_t)o1 * nseg, dst1 != 0xff, stack + (size_t)dst1 * S * 32 * V,
+                               w, g);
+            if (o2 != 0xffff || dst2 != 0xff)
+                sk_child<S, V>(cm, U, pa, pb, ps, o2 != 0xffff, outc + (size_t)o2 * nseg, dst2 != 0xff, stack + (size_t)dst2 * S * 32 * V,
+                               w, g);
+        }
     }
 }
 
@@ -346,7 +508,7 @@ int sk_build(Ctx *c)
             set_error("segment_upper: interior bounds must be increasing multiples of 16 (iqtree.cpp:3804)"); return 1;
         }
     k.Lref = ninf % 16 ? ninf + 16 - ninf % 16 : ninf;
-    k.Lp = std::max(64, (ninf + 63) / 64 * 64);
+    k.Lp = std::max(256, (ninf + 255) / 256 * 256);      // whole chunks for every lane width
     k.Lh = k.Lp / 2;
     k.vstride = (size_t)S * k.Lh;
     const size_t nviews = (size_t)(4 * n - 6);
@@ -362,7 +524,7 @@ int sk_build(Ctx *c)
     if (!k.d_mask) MPGPU_CUDA(cudaMalloc((void **)&k.d_mask, sizeof(uint32_t) * 256));
     // informativePtnWgt is u16 (:2755); entry j = the j-th informative pattern
     std::vector<uint2> w(k.Lh, make_uint2(0, 0));
-    std::vector<int32_t> seg(k.Lh, k.nseg - 1);
+    std::vector<int32_t> seg(k.Lh, k.nseg - 1);          // per pair; a lane's V pairs never straddle (bounds are multiples of 16)
     std::vector<uint32_t> wflat(ninf > 0 ? ninf : 1, 0), present(ninf > 0 ? ninf : 1, 0);
     {
         int j = 0;
@@ -415,7 +577,7 @@ static int sk_launch_level(Ctx *c, const Triple *d_triples, int ntriples, uint32
     if (ntriples == 0) return 0;
     Sankoff &k = c->sk;
     if (int rc = bind_cost(c)) return rc;
-    const int64_t warps = (int64_t)ntriples * (k.Lh / 32);
+    const int64_t warps = (int64_t)ntriples * (k.Lh / (32 * sk_vpl(c->S)));
     const int blocks = (int)((warps + 3) / 4);
     SK_DISPATCH((k_sk_level<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.Lref / 2, d_triples, ntriples,
                                                                c->d_vcount, d_compact)));
@@ -496,7 +658,7 @@ int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn)
     if (ptn) { if (int rc = ensure(k.d_tmp, k.tmp_cap, (size_t)k.Lh)) return rc; }
     MPGPU_CUDA(cudaMemcpyAsync(k.d_list, list, (size_t)count * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)count * k.nseg * sizeof(uint32_t), c->stream));
-    const int64_t warps = (int64_t)count * (k.Lh / 32);
+    const int64_t warps = (int64_t)count * (k.Lh / (32 * sk_vpl(c->S)));
     const int blocks = (int)((warps + 3) / 4);
     SK_DISPATCH((k_sk_junction<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, count, k.d_w, k.d_seg, k.nseg,
                                                                   k.d_segout, ptn ? k.d_tmp : nullptr)));
@@ -548,7 +710,8 @@ int sk_raw_view(Ctx *c, int ref, uint16_t *out)
     if (t.is_tip(ref))
         k_sk_raw_tip<<<blocks, 128, 0, c->stream>>>(c->d_codes, c->P, ref / 3 - 1, c->d_inf_ptn, c->n_inf, k.d_mask, k.highest, k.Lh, c->S, k.d_tmp);
     else
-        k_sk_raw<<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, c->S, t.vid(t.back(t.next(ref))), t.vid(t.back(t.next(t.next(ref)))), k.d_tmp);
+        SK_DISPATCH((k_sk_raw<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, t.vid(t.back(t.next(ref))),
+                                                                 t.vid(t.back(t.next(t.next(ref)))), k.d_tmp)));
     MPGPU_CUDA(cudaGetLastError());
     std::vector<uint16_t> tmp((size_t)c->S * k.Lp);
     MPGPU_CUDA(cudaMemcpyAsync(tmp.data(), k.d_tmp, k.vstride * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -570,12 +733,13 @@ int sk_run_scan(Ctx *c)
     if (rows == 0 || ntasks == 0) return 0;
     MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)rows * k.nseg * sizeof(uint32_t), c->stream));
     const int nslots = pl.max_slot > 0 ? pl.max_slot : 1;
-    const size_t per_warp = (size_t)nslots * c->S * 32 * sizeof(uint32_t);
+    const int V = sk_vpl(c->S);
+    const size_t per_warp = (size_t)nslots * c->S * 32 * V * sizeof(uint32_t);
     int wpb = 4;
     while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
-    const long long warps = (long long)ntasks * (k.Lh / 32);
+    const long long warps = (long long)ntasks * (k.Lh / (32 * V));
     const long long blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL) { set_error("scan grid too large"); return 1; }
 #define SK_SCAN_LAUNCH                                                                                                         \
