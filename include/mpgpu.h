@@ -270,7 +270,14 @@ typedef struct mpgpu_bb_hooks {
     int32_t (*push_tree_logl)(void *user, double cur_logl);
     int32_t (*materialize)(void *user, const int32_t *back_node, const int32_t *back_slot,
                            int32_t remove_ref, int32_t insert_ref, int32_t tree_index);
+    /* policy MPGPU_BB_MULHITS only (may be NULL otherwise): replicate `sample` scored rell >= boot_logl[sample]
+     * with tree `tree_index`; clear_first != 0 <=> rell > boot_logl[sample], i.e. boot_trees_parsimony[sample]
+     * .clear() comes first (iqtree.cpp:3517-3520), then insert-if-absent (:3531-3534). */
+    void (*mulhit)(void *user, int32_t sample, int32_t tree_index, int32_t clear_first);
 } mpgpu_bb_hooks;
+#define MPGPU_BB_DEFAULT 0     /* iqtree.cpp:3687-3731 */
+#define MPGPU_BB_MULHITS 1     /* params->multiple_hits without -topboot, iqtree.cpp:3498-3531: every tree that ties a
+                                * replicate's best score is kept; no tie-break draw, boot_counts / boot_trees untouched */
 typedef struct mpgpu_bb_state {
     int32_t B;
     double *boot_logl;        /* [B] in/out */
@@ -289,6 +296,7 @@ typedef struct mpgpu_bb_state {
     int32_t ratchet;                          /* 0 = normal iteration */
     const uint16_t *ratchet_pattern_pars;     /* in, when ratchet */
     int32_t ratchet_last_score;               /* out */
+    int32_t policy;                           /* MPGPU_BB_DEFAULT / MPGPU_BB_MULHITS */
 } mpgpu_bb_state;
 int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,
@@ -310,6 +318,9 @@ void mpgpu_treels_logl(const mpgpu_treels *t, double *out);
 int64_t mpgpu_treels_num_materialized(const mpgpu_treels *t);
 void mpgpu_treels_materialized(const mpgpu_treels *t, int64_t *out);
 void mpgpu_treels_hooks(mpgpu_treels *t, mpgpu_rng_fn rng, void *rng_user, mpgpu_bb_hooks *out);
+/* -mulhits: boot_trees_parsimony as collected through the mulhit hook: sizes[nsamples], then the members of
+ * every set in ascending order, concatenated into flat (up to capacity); returns the total count. */
+int64_t mpgpu_treels_mulhits(const mpgpu_treels *t, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -395,9 +395,21 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
     const double eps = st->ufboot_epsilon;
     int32_t tree_index = hk->push_tree_logl(hk->user, cur_logl);
     bool have = false;
+    const bool mulhits = st->policy == MPGPU_BB_MULHITS;
     auto one = [&](int b, int32_t res) {
         const double rell = -(double)res;
         const double bl = st->boot_logl[b];
+        if (mulhits) {                                   // iqtree.cpp:3498-3531
+            if (rell >= bl) {
+                if (!have) {
+                    have = true;
+                    tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
+                }
+                if (rell > bl) st->boot_logl[b] = rell;
+                hk->mulhit(hk->user, b, tree_index, rell > bl);
+            }
+            return;
+        }
         if (rell > bl + eps || (rell > bl - eps && hk->random_double(hk->user) <= 1.0 / (st->boot_counts[b] + 1))) {
             if (!have) {
                 have = true;
@@ -746,6 +758,8 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, 
     if (!hooks->random_double || !hooks->push_tree_logl || !hooks->materialize) { set_error("incomplete -bb hooks"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
     if (state->B != c->reps.Buser || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
+    if (state->policy != MPGPU_BB_DEFAULT && state->policy != MPGPU_BB_MULHITS) { set_error("unknown -bb policy"); return 1; }
+    if (state->policy == MPGPU_BB_MULHITS && !hooks->mulhit) { set_error("policy MPGPU_BB_MULHITS needs the mulhit hook"); return 1; }
     state->n_calls = 0; state->n_reps = 0;
     BBRun bb{hooks, state};
     return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, hooks->random_double, hooks->user, &bb, best, n_insertions);

@@ -8,6 +8,7 @@
 #include "mpgpu_internal.h"
 
 #include <cstring>
+#include <set>
 #include <unordered_map>
 
 struct mpgpu_treels {
@@ -15,6 +16,7 @@ struct mpgpu_treels {
     std::vector<double> logl;                              // treels_logl
     std::unordered_map<uint64_t, int32_t> index;           // treels
     std::vector<int64_t> mats;                             // 4 per materialised tree: remove_ref, insert_ref, tree_index, fingerprint
+    std::vector<std::set<int32_t>> mulhits;                // boot_trees_parsimony (-mulhits)
     mpgpu_rng_fn rng = nullptr; void *rng_user = nullptr;
 };
 
@@ -77,6 +79,15 @@ int32_t hook_materialize(void *user, const int32_t *bn, const int32_t *bs, int32
     return tree_index;
 }
 
+void hook_mulhit(void *user, int32_t sample, int32_t tree_index, int32_t clear_first)
+{
+    mpgpu_treels *h = (mpgpu_treels *)user;
+    if ((size_t)sample >= h->mulhits.size()) h->mulhits.resize((size_t)sample + 1);
+    std::set<int32_t> &s = h->mulhits[sample];
+    if (clear_first) s.clear();                            // iqtree.cpp:3517-3520
+    s.insert(tree_index);                                  // :3531-3534
+}
+
 }  // namespace
 
 extern "C" {
@@ -111,6 +122,18 @@ void mpgpu_treels_hooks(mpgpu_treels *h, mpgpu_rng_fn rng, void *rng_user, mpgpu
     out->random_double = hook_rng;
     out->push_tree_logl = hook_push;
     out->materialize = hook_materialize;
+    out->mulhit = hook_mulhit;
+}
+int64_t mpgpu_treels_mulhits(const mpgpu_treels *h, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity)
+{
+    int64_t tot = 0;
+    for (int32_t s = 0; s < nsamples; s++) {
+        const bool have = h && (size_t)s < h->mulhits.size();
+        if (sizes) sizes[s] = have ? (int32_t)h->mulhits[s].size() : 0;
+        if (!have) continue;
+        for (int32_t v : h->mulhits[s]) { if (flat && tot < capacity) flat[tot] = v; tot++; }
+    }
+    return tot;
 }
 
 }  // extern "C"

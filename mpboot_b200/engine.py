@@ -86,6 +86,8 @@ def lib():
     L.mpgpu_treels_num_materialized.argtypes = [vp]
     L.mpgpu_treels_materialized.argtypes = [vp, vp]
     L.mpgpu_treels_hooks.argtypes = [vp, vp, vp, vp]
+    L.mpgpu_treels_mulhits.restype = i64
+    L.mpgpu_treels_mulhits.argtypes = [vp, i32, vp, vp, i64]
     _lib = L
     return L
 
@@ -97,14 +99,15 @@ def _p(a):
 class BBHooks(C.Structure):
     """mpgpu_bb_hooks (include/mpgpu.h)"""
     _fields_ = [("user", C.c_void_p), ("random_double", C.c_void_p), ("push_tree_logl", C.c_void_p),
-                ("materialize", C.c_void_p)]
+                ("materialize", C.c_void_p), ("mulhit", C.c_void_p)]
 
 
 class BBState(C.Structure):
     """mpgpu_bb_state (include/mpgpu.h)"""
     _fields_ = [("B", C.c_int32), ("boot_logl", C.c_void_p), ("boot_counts", C.c_void_p), ("boot_trees", C.c_void_p),
                 ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64),
-                ("ratchet", C.c_int32), ("ratchet_pattern_pars", C.c_void_p), ("ratchet_last_score", C.c_int32)]
+                ("ratchet", C.c_int32), ("ratchet_pattern_pars", C.c_void_p), ("ratchet_last_score", C.c_int32),
+                ("policy", C.c_int32)]
 
 
 class HostRng:
@@ -142,6 +145,14 @@ class Treels:
         out = np.zeros(max(k, 1), dtype=np.float64)
         self.L.mpgpu_treels_logl(self.h, _p(out))
         return out[:k]
+
+    def mulhits(self, nsamples):
+        """boot_trees_parsimony (-mulhits): (sizes[nsamples], members ascending, concatenated)"""
+        sizes = np.zeros(nsamples, dtype=np.int32)
+        tot = self.L.mpgpu_treels_mulhits(self.h, nsamples, _p(sizes), None, 0)
+        flat = np.zeros(max(tot, 1), dtype=np.int32)
+        self.L.mpgpu_treels_mulhits(self.h, nsamples, _p(sizes), _p(flat), tot)
+        return sizes, flat[:tot]
 
     def materialized(self):
         k = self.L.mpgpu_treels_num_materialized(self.h)
@@ -409,14 +420,14 @@ class Engine:
         return ptr.value, pitch.value
 
     def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
-                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None):
+                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None, mulhits=False):
         """pllOptimizeSprParsimony + saveCurrentTree (default policy).  hooks: BBHooks (e.g.
         Treels.hooks(rng)); boot_* arrays are updated in place.  Returns (startMP, back_node,
         back_slot, insertions scored, saveCurrentTree calls, REPS vectors used)."""
         bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
         assert boot_logl.dtype == np.float64 and boot_counts.dtype == np.int32 and boot_trees.dtype == np.int32
         st = BBState(len(boot_logl), boot_logl.ctypes.data, boot_counts.ctypes.data, boot_trees.ctypes.data,
-                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0)
+                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0)
         if ratchet_pattern_pars is not None:            # ratchet iteration (iqtree.cpp:3283-3294)
             rp = np.zeros(max(self.P, len(ratchet_pattern_pars)), dtype=np.uint16)
             rp[: len(ratchet_pattern_pars)] = ratchet_pattern_pars

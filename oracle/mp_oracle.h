@@ -31,6 +31,9 @@ int  mporacle_optimize_spr(mporacle *o, int mintrav, int maxtrav, int bb);
 unsigned mporacle_ras(mporacle *o, long seed, int spr_dist);
 unsigned long mporacle_sweep_count_insertions(mporacle *o, int mintrav, int maxtrav, int per_site, int reps);
 
+/* -mulhits */
+void mporacle_boot_set_mulhits(mporacle *o, int on);
+int  mporacle_boot_mulhits(mporacle *o, int *sizes, int *flat, int cap);
 /* Sankoff (-cost) */
 int  mporacle_set_cost_matrix(mporacle *o, const unsigned *cost, const int *segment_upper, int nseg);
 int  mporacle_get_sankoff_vect(mporacle *o, int node, uint16_t *out);

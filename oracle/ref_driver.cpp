@@ -561,7 +561,10 @@ MPREF_API unsigned long mpref_sweep_count_insertions(mpref *h, int mintrav, int 
  * scores come from the reference's pllComputePatternParsimony; the skip bound is
  * pllComputeRellRemainBound (:3821-3858) over pllCalcMinParsScorePattern and ras_pars_score. */
 #include <map>
+#include <set>
 struct BootSim {
+    bool multiple_hits;                                       /* params->multiple_hits (-mulhits), :3498-3531 */
+    std::vector<std::set<int> > boot_trees_parsimony;
     int B, stride, nseg;
     std::vector<unsigned short *> boot_samples_pars;          /* aligned, P+16, zero padded (:220-233) */
     std::vector<int> segment_upper;
@@ -642,6 +645,7 @@ MPREF_API void mpref_boot_init(mpref *h, int B, const unsigned short *boot, int 
     b->pattern_pars = (unsigned short *)aligned32(sizeof(unsigned short) * (b->stride + 16));
     b->calls = b->reps_rows = b->skipped = b->bad_sum = 0;
     b->on_ratchet_hclimb1 = false; b->original_sample = NULL;
+    b->multiple_hits = false; b->boot_trees_parsimony.assign(B, std::set<int>());
     h->boot = b;
 }
 
@@ -656,6 +660,21 @@ MPREF_API void mpref_boot_set_ratchet(mpref *h, const unsigned short *original_s
     memcpy(b->pattern_pars, initial_ptn, sizeof(unsigned short) * h->P);
 }
 
+MPREF_API void mpref_boot_set_mulhits(mpref *h, int on) { h->boot->multiple_hits = on != 0; }
+/* boot_trees_parsimony: sizes[B] and the sets' members, ascending, concatenated; returns the total */
+MPREF_API int mpref_boot_mulhits(mpref *h, int *sizes, int *flat, int cap)
+{
+    BootSim *b = h->boot;
+    int tot = 0;
+    for (int s = 0; s < b->B; s++) {
+        sizes[s] = (int)b->boot_trees_parsimony[s].size();
+        for (std::set<int>::iterator it = b->boot_trees_parsimony[s].begin(); it != b->boot_trees_parsimony[s].end(); ++it) {
+            if (tot < cap) flat[tot] = *it;
+            tot++;
+        }
+    }
+    return tot;
+}
 MPREF_API void mpref_boot_set_cutoff(mpref *h, double c) { if (h->boot) h->boot->logl_cutoff = c; }
 MPREF_API void mpref_boot_set_state(mpref *h, const double *bl, const int *bc, const int *bt)
 {
@@ -722,6 +741,23 @@ static void boot_save_current_tree(mpref *h, double cur_logl)
         }
         rell = -(double)res;
         if (skipped) { b->skipped++; continue; }                                           /* :3484 */
+        if (b->multiple_hits) {                                                            /* :3498-3531 (no -topboot) */
+            if (rell >= b->boot_logl[sample]) {
+                if (!have_str) {
+                    have_str = true;
+                    unsigned long long fp = mpref_tree_fingerprint(h);
+                    std::map<unsigned long long, int>::iterator it = b->treels.find(fp);
+                    if (it != b->treels.end()) tree_index = it->second;
+                    else { tree_index = (int)b->treels_logl.size() - 1; b->treels[fp] = tree_index; }
+                    long long m[5] = { call, 0, 0, tree_index, (long long)fp };
+                    b->mat.insert(b->mat.end(), m, m + 5);
+                }
+                if (rell > b->boot_logl[sample]) { b->boot_trees_parsimony[sample].clear(); b->boot_logl[sample] = rell; }
+                if (b->boot_trees_parsimony[sample].find(tree_index) == b->boot_trees_parsimony[sample].end())
+                    b->boot_trees_parsimony[sample].insert(tree_index);
+            }
+            continue;                                                                      /* neither :3587 nor :3687 applies */
+        }
         if (rell > b->boot_logl[sample] + b->eps
             || (rell > b->boot_logl[sample] - b->eps && random_double() <= 1.0 / (b->boot_counts[sample] + 1))) {   /* :3689 */
             if (!have_str) {                                                               /* :3692-3708 */

@@ -77,6 +77,8 @@ def _boot_protos(L, pre):
     getattr(L, pre + "_boot_init").argtypes = [vp, i, vp, i, vp, i, C.c_double, C.c_double, vp]
     getattr(L, pre + "_boot_free").argtypes = [vp]
     getattr(L, pre + "_boot_set_cutoff").argtypes = [vp, C.c_double]
+    getattr(L, pre + "_boot_set_mulhits").argtypes = [vp, i]
+    getattr(L, pre + "_boot_mulhits").argtypes = [vp, vp, vp, i]
     getattr(L, pre + "_boot_set_ratchet").argtypes = [vp, vp, vp]
     getattr(L, pre + "_boot_set_state").argtypes = [vp, vp, vp, vp]
     getattr(L, pre + "_boot_get_state").argtypes = [vp, vp, vp, vp]
@@ -118,6 +120,18 @@ class BootMixin:
 
     def boot_set_cutoff(self, c):
         self._f("_boot_set_cutoff")(self.h, float(c))
+
+    def boot_set_mulhits(self, on=True):
+        """params->multiple_hits (-mulhits without -topboot, iqtree.cpp:3498-3531)"""
+        self._f("_boot_set_mulhits")(self.h, int(on))
+
+    def boot_mulhits(self):
+        """boot_trees_parsimony: (sizes[B], members of every set ascending, concatenated)"""
+        sizes = np.zeros(self._B, dtype=np.int32)
+        tot = self._f("_boot_mulhits")(self.h, _p(sizes), None, 0)
+        flat = np.zeros(max(tot, 1), dtype=np.int32)
+        self._f("_boot_mulhits")(self.h, _p(sizes), _p(flat), tot)
+        return sizes, flat[:tot]
 
     def boot_set_state(self, boot_logl, boot_counts, boot_trees):
         a = np.ascontiguousarray(boot_logl, dtype=np.float64)

@@ -46,7 +46,7 @@ def ratchet_setup(c, pp, seed):
     return w2, orig, init
 
 
-def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None):
+def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None, mulhits=False):
     if ratchet is not None:
         eng.set_weights(ratchet[0])
     else:
@@ -56,16 +56,19 @@ def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=No
     eng.boot_init(boot, seg, cutoff, 0.5, bound)
     if ratchet is not None:
         eng.boot_set_ratchet(ratchet[1], ratchet[2])
+    if mulhits:
+        eng.boot_set_mulhits(True)
     (reflib.lib().mpref_seed_rng if is_ref else portlib.seed_rng)(seed)
     eng.record(False)
     ret = eng.optimize_spr(1, mt, bb=True)
     draws = reflib.lib().mpref_rng_draws() if is_ref else portlib.rng_draws()
     return dict(ret=ret, draws=draws, ring=eng.get_ring(), state=eng.boot_state(), counters=eng.boot_counters(),
-                treels=eng.boot_treels(), mats=eng.boot_mats(), saved=eng.saved())
+                treels=eng.boot_treels(), mats=eng.boot_mats(), saved=eng.saved(), mulhits=eng.boot_mulhits())
 
 
 def same(a, b):
     assert a["ret"] == b["ret"] and a["draws"] == b["draws"]
+    assert all(np.array_equal(x, y) for x, y in zip(a["mulhits"], b["mulhits"]))
     assert all(np.array_equal(x, y) for x, y in zip(a["ring"], b["ring"]))
     assert all(np.array_equal(x, y) for x, y in zip(a["state"], b["state"]))
     assert a["counters"] == b["counters"] and a["counters"][4] == 0
@@ -110,6 +113,57 @@ def test_port_bb_ratchet_iteration_equals_reference(n, L, dt, seed, B, mu):
         assert x["counters"][1] < a["counters"][1]
 
 
+MULHITS_CASES = [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05), (30, 800, 1, 21, 64, 0.01), (20, 300, 6, 9, 30, 0.05)]
+MULHITS_GOLD = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "mulhits.npz")
+
+
+@needs_ref
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", MULHITS_CASES)
+def test_port_bb_mulhits_equals_reference(n, L, dt, seed, B, mu):
+    """-mulhits (params->multiple_hits, iqtree.cpp:3498-3531): every tree tying a replicate's best score is kept in
+    boot_trees_parsimony[sample]; no tie-break draws from saveCurrentTree."""
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    a = run_bb(o, c, boot, seg, 0.0, None, False, mulhits=True)
+    same(a, run_bb(r, c, boot, seg, 0.0, None, True, mulhits=True))
+    assert a["mulhits"][0].min() >= 1                                    # every replicate has at least one best tree
+    assert dt == 6 or a["mulhits"][0].max() > 1                          # ties are kept (the 32-state case has none)
+    d = run_bb(o, c, boot, seg, 0.0, None, False)
+    assert a["draws"] < d["draws"]                                       # the default policy's tie-break draws are gone
+    cutoff = -(a["ret"] + 4.0)
+    x = run_bb(o, c, boot, seg, cutoff, bound, False, mulhits=True)
+    same(x, run_bb(r, c, boot, seg, cutoff, ras, True, mulhits=True))
+    y = run_bb(o, c, boot, seg, cutoff, None, False, mulhits=True)      # the skip test is decision-neutral here too
+    assert all(np.array_equal(p, q) for p, q in zip(x["mulhits"], y["mulhits"])) and np.array_equal(x["state"][0], y["state"][0])
+
+
+def mulhits_golden_case(g, k):
+    n, L, dt, seed, B, mu = [x for x in MULHITS_CASES[k]]
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    assert np.array_equal(boot, g["c%d_boot" % k]) and np.array_equal(c["codes"], g["c%d_codes" % k])   # same seeded inputs
+    return c, o, seg, boot, bound
+
+
+def check_mulhits_golden(g, k, tag, r):
+    p = "c%d_%s_" % (k, tag)
+    assert r["ret"] == int(g[p + "ret"]) and r["draws"] == int(g[p + "draws"])
+    assert np.array_equal(r["ring"][0][3:], g[p + "bn"][3:]) and np.array_equal(r["ring"][1][3:], g[p + "bs"][3:])
+    assert np.array_equal(r["state"][0], g[p + "boot_logl"])
+    assert np.array_equal(r["mulhits"][0], g[p + "sizes"]) and np.array_equal(r["mulhits"][1], g[p + "flat"])
+    assert np.array_equal(r["treels"], g[p + "treels"])
+    assert np.array_equal(r["mats_tf"], g[p + "mats"])                 # tree_index, topology fingerprint per materialised tree
+
+
+@pytest.mark.parametrize("k", range(len(MULHITS_CASES)))
+def test_port_bb_mulhits_matches_golden(k):
+    g = dict(np.load(MULHITS_GOLD))
+    c, o, seg, boot, bound = mulhits_golden_case(g, k)
+    for tag in ("all", "cut"):
+        r = run_bb(o, c, boot, seg, float(g["c%d_%s_cutoff" % (k, tag)]), None, False, mulhits=True)
+        r["mats_tf"] = r["mats"][:, [3, 4]]
+        check_mulhits_golden(g, k, tag, r)
+
+
 def test_fingerprint_matches_python_helper():
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(16, 300, 1, 3, 8)
     res = run_bb(o, c, boot, seg, 0.0, None, False)
@@ -125,7 +179,7 @@ import os
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASE_FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith("sankoff_"))
+                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith(("sankoff_", "mulhits")))
 IDS = [os.path.basename(p)[:-4] for p in CASE_FILES]
 
 

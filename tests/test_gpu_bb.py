@@ -86,7 +86,7 @@ def test_reps_wrap_free_bulk_uses_no_exceptions():
     assert groups == 1 and exc == 0 and t == 1                # everything on the tensor path
 
 
-def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None):
+def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None, mulhits=False):
     from mpboot_b200.engine import Treels
     eng = _engine(c, boot, seg, tensor, ratchet)
     B = boot.shape[0]
@@ -96,9 +96,10 @@ def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None):
     portlib.seed_rng(seed)
     ret, bn, bs, nins, ncalls, nreps = eng.optimize_spr_bb(c["bn"], c["bs"], tl.hooks(portlib.rng_fn_address()),
                                                            bl, bc, bt, cutoff, 0.5, 1, mt,
-                                                           ratchet_pattern_pars=None if ratchet is None else ratchet[2])
+                                                           ratchet_pattern_pars=None if ratchet is None else ratchet[2],
+                                                           mulhits=mulhits)
     return dict(ret=ret, draws=portlib.rng_draws(), ring=(bn, bs), state=(bl, bc, bt), ncalls=ncalls, nreps=nreps,
-                treels=tl.logl(), mats=tl.materialized(), nins=nins)
+                treels=tl.logl(), mats=tl.materialized(), nins=nins, mulhits=tl.mulhits(B))
 
 
 @pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
@@ -135,3 +136,36 @@ def test_bb_search_matches_golden(path):
         r["counters"] = (r["ncalls"], len(r["treels"]), r["nreps"])
         r["mats"] = r["mats"][:, [2, 3]]
         check_against_golden(g, tag, r)
+
+
+# ---- -mulhits (params->multiple_hits, iqtree.cpp:3498-3531): policy MPGPU_BB_MULHITS ----
+from tests.test_bb_cpu import MULHITS_CASES, MULHITS_GOLD, check_mulhits_golden, mulhits_golden_case  # noqa: E402
+
+
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("k", range(len(MULHITS_CASES)))
+def test_bb_mulhits_matches_golden_and_oracle(k, tensor):
+    g = dict(np.load(MULHITS_GOLD))
+    c, o, seg, boot, bound = mulhits_golden_case(g, k)
+    for tag in ("all", "cut"):
+        cutoff = float(g["c%d_%s_cutoff" % (k, tag)])
+        r = _run_gpu_bb(c, boot, seg, cutoff, tensor, mulhits=True)
+        r["mats_tf"] = r["mats"][:, [2, 3]]
+        check_mulhits_golden(g, k, tag, r)                       # what the reference driver produced
+        w = run_bb(o, c, boot, seg, cutoff, None, False, mulhits=True)
+        assert r["ncalls"] == w["counters"][0] and r["nreps"] == w["counters"][2]
+        assert np.array_equal(r["mats"][:, :2], w["mats"][:, 1:3])   # pruned ref, insertion ref of every materialised tree
+        assert np.array_equal(r["state"][1], w["state"][1]) and np.array_equal(r["state"][2], w["state"][2])   # untouched
+
+
+def test_bb_mulhits_ratchet_iteration_matches_oracle():
+    from tests.test_bb_cpu import ratchet_setup
+    n, L, dt, seed, B, mu = MULHITS_CASES[2]
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    rt = ratchet_setup(c, pp, seed)
+    w = run_bb(o, c, boot, seg, 0.0, None, False, ratchet=rt, mulhits=True)
+    r = _run_gpu_bb(c, boot, seg, 0.0, 1, ratchet=rt, mulhits=True)
+    assert r["ret"] == w["ret"] and r["draws"] == w["draws"]
+    assert np.array_equal(r["state"][0], w["state"][0])
+    assert all(np.array_equal(x, y) for x, y in zip(r["mulhits"], w["mulhits"]))
+    assert np.array_equal(r["treels"], w["treels"])
