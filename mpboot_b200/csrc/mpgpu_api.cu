@@ -769,6 +769,7 @@ int mpgpu_set_cost_matrix(mpgpu_ctx *c, const uint32_t *cost, int nstates, const
     MPGPU_CUDA(cudaSetDevice(c->device));
     Sankoff &k = c->sk;
     if (!cost) {                                            // back to Fitch
+        if (c->reps.loaded && k.on) { set_error("replicates are loaded for -cost scoring: reload them after leaving -cost"); return 1; }
         k.on = false;
         c->lens_valid = false; c->kids_valid = false;
         if (c->tree_set) { if (int rc = compute_views(c)) return rc; if (c->reduces()) compute_lengths(c); }
@@ -776,7 +777,7 @@ int mpgpu_set_cost_matrix(mpgpu_ctx *c, const uint32_t *cost, int nstates, const
     }
     if (nstates != c->S) { set_error("cost matrix size does not match the alignment's state count"); return 1; }
     if (!segment_upper || nseg < 1) { set_error("segment_upper is required (IQTree::doSegmenting, iqtree.cpp:3793)"); return 1; }
-    if (c->reps.loaded) { set_error("-bb replicate scoring is not available under -cost in this library"); return 1; }
+    if (c->reps.loaded) { set_error("set the cost matrix before mpgpu_load_replicates (the replicate tables are built per scoring mode)"); return 1; }
     uint32_t mx = 0;
     for (int i = 0; i < nstates; i++)
         for (int j = 0; j < nstates; j++) {

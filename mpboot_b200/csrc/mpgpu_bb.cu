@@ -214,6 +214,94 @@ struct RepsOut {
     std::vector<int32_t> orig;                    // per call: score on original_sample (column Buser), when loaded
 };
 
+// Read-back of one chunk whose results sit in reps.d_res[ncalls][Bpad] (and hit flags in d_call_hit when thr):
+// the original-frequency column of every call, and only the rows of calls that can change a replicate.
+static int reps_read_back(Ctx *c, int ncalls, int done, const int32_t *thr, RepsOut &out, std::vector<int32_t> &hit_list)
+{
+    Reps &r = c->reps;
+    // ---- read back: the original-frequency score of every call (ratchet iterations) ----
+    if (r.has_orig) {
+        MPGPU_CUDA(cudaMemcpy2DAsync(out.orig.data() + done, 4, r.d_res + r.Buser, (size_t)r.Bpad * 4, 4, (size_t)ncalls,
+                                     cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    // ---- read back: only the rows of calls that can change a replicate ----
+    bool all_rows = true;
+    if (thr) {
+        int32_t *fl = (int32_t *)r.pinned((size_t)ncalls * 4);
+        if (!fl) { set_error("pinned host allocation failed"); return 2; }
+        MPGPU_CUDA(cudaMemcpyAsync(fl, r.d_call_hit, (size_t)ncalls * 4, cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        hit_list.clear();
+        for (int i = 0; i < ncalls; i++) if (fl[i]) hit_list.push_back(i);
+        if ((int)hit_list.size() * 2 < ncalls) {
+            all_rows = false;
+            const int nl = (int)hit_list.size();
+            if (nl) {
+                if (int rc = ensure(r.d_hit_list, r.hit_list_cap, (size_t)nl)) return rc;
+                if (int rc = ensure(r.d_res_hit, r.res_hit_cap, (size_t)nl * r.Bpad)) return rc;
+                MPGPU_CUDA(cudaMemcpyAsync(r.d_hit_list, hit_list.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
+                if (int rc = launch_gather_res_rows(c, r.d_res, r.d_hit_list, nl, r.d_res_hit)) return rc;
+                const size_t off = out.dense.size(), bytes = (size_t)nl * r.Bpad * 4;
+                void *hp = r.pinned(bytes);
+                if (!hp) { set_error("pinned host allocation failed"); return 2; }
+                MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res_hit, bytes, cudaMemcpyDeviceToHost, c->stream));
+                MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+                out.dense.resize(off + (size_t)nl * r.Bpad);
+                memcpy(out.dense.data() + off, hp, bytes);
+                for (int i = 0; i < nl; i++) out.dense_off[done + hit_list[i]] = (int64_t)(off + (size_t)i * r.Bpad);
+            }
+        }
+    }
+    if (all_rows) {
+        const size_t off = out.dense.size(), bytes = (size_t)ncalls * r.Bpad * 4;
+        void *hp = r.pinned(bytes);
+        if (!hp) { set_error("pinned host allocation failed"); return 2; }
+        MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res, bytes, cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        out.dense.resize(off + (size_t)ncalls * r.Bpad);
+        memcpy(out.dense.data() + off, hp, bytes);
+        for (int i = 0; i < ncalls; i++) out.dense_off[done + i] = (int64_t)(off + (size_t)i * r.Bpad);
+    }
+    return 0;
+}
+
+// -cost: the calls' vectors are per-pattern cost rows (sankoff.cu), one exact contraction per chunk
+static int sk_reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, RepsOut &out, bool device_only)
+{
+    Reps &r = c->reps;
+    const ScanPlan &pl = c->plan;
+    if (thr) {
+        if (!r.d_thr) MPGPU_CUDA(cudaMalloc((void **)&r.d_thr, (size_t)r.Bpad * 4));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.Buser * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    std::vector<int32_t> &row_of = r.h_row_of, &call_row = r.h_row_tasks;
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    const int cap = sk_reps_rows_capacity(c) - 1;
+    std::vector<int32_t> hit_list;
+    int done = 0;
+    while (done < m) {
+        row_of.assign(pl.n_cand > 0 ? pl.n_cand : 1, -1);
+        call_row.clear();
+        int nsel = 0, k = done;
+        for (; k < m; k++) {
+            const int j = cands[k];
+            if (j < 0) { call_row.push_back(0); continue; }
+            if (j >= pl.n_cand) { set_error("candidate index out of range"); return 1; }
+            if (row_of[j] < 0) { if (nsel + 1 > cap) break; row_of[j] = nsel++; }
+            call_row.push_back(1 + row_of[j]);
+        }
+        if (k == done) { set_error("REPS row buffers too small for a single candidate"); return 1; }
+        if (device_only && k < m) { set_error("REPS batch does not fit the row buffers in one piece (raise MPGPU_REPS_ROW_BYTES)"); return 1; }
+        const int ncalls = k - done;
+        if (int rc = sk_reps_chunk(c, row_of.data(), nsel, call_row.data(), ncalls, thr != nullptr)) return rc;
+        if (device_only) return 0;
+        if (int rc = reps_read_back(c, ncalls, done, thr, out, hit_list)) return rc;
+        done = k;
+    }
+    return 0;
+}
+
 // REPS vectors for the calls cands[0..m) of the last planned scan batch (-1 = the current tree),
 // in order.  thr (host, [B], nullable): only entries with res <= thr[b] are needed by the caller.
 // device_only: enqueue the work of a single chunk and return without reading anything back (d_res holds
@@ -228,6 +316,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     out.dense_off.assign(m, -1);
     out.orig.assign(r.has_orig ? m : 0, 0);
     if (m == 0) return 0;
+    if (c->sk.on) return sk_reps_run(c, cands, m, thr, out, device_only);
     if (int rc = refresh_tree_rows(c)) return rc;
     // rows the whole list would like to have; ensure_rows clamps to the memory budget
     {
@@ -311,50 +400,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
         if (int rc = launch_reps_combine(c, kTreeRows - 1, r.d_calls, ncalls, r.d_res, thr ? r.d_thr : nullptr, r.d_call_hit)) return rc;
         rp_stop(c, 6);
         if (device_only) return 0;
-        // ---- read back: the original-frequency score of every call (ratchet iterations) ----
-        if (r.has_orig) {
-            MPGPU_CUDA(cudaMemcpy2DAsync(out.orig.data() + done, 4, r.d_res + r.Buser, (size_t)r.Bpad * 4, 4, (size_t)ncalls,
-                                         cudaMemcpyDeviceToHost, c->stream));
-            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-        }
-        // ---- read back: only the rows of calls that can change a replicate ----
-        bool all_rows = true;
-        if (thr) {
-            int32_t *fl = (int32_t *)r.pinned((size_t)ncalls * 4);
-            if (!fl) { set_error("pinned host allocation failed"); return 2; }
-            MPGPU_CUDA(cudaMemcpyAsync(fl, r.d_call_hit, (size_t)ncalls * 4, cudaMemcpyDeviceToHost, c->stream));
-            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-            hit_list.clear();
-            for (int i = 0; i < ncalls; i++) if (fl[i]) hit_list.push_back(i);
-            if ((int)hit_list.size() * 2 < ncalls) {
-                all_rows = false;
-                const int nl = (int)hit_list.size();
-                if (nl) {
-                    if (int rc = ensure(r.d_hit_list, r.hit_list_cap, (size_t)nl)) return rc;
-                    if (int rc = ensure(r.d_res_hit, r.res_hit_cap, (size_t)nl * r.Bpad)) return rc;
-                    MPGPU_CUDA(cudaMemcpyAsync(r.d_hit_list, hit_list.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
-                    if (int rc = launch_gather_res_rows(c, r.d_res, r.d_hit_list, nl, r.d_res_hit)) return rc;
-                    const size_t off = out.dense.size(), bytes = (size_t)nl * r.Bpad * 4;
-                    void *hp = r.pinned(bytes);
-                    if (!hp) { set_error("pinned host allocation failed"); return 2; }
-                    MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res_hit, bytes, cudaMemcpyDeviceToHost, c->stream));
-                    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-                    out.dense.resize(off + (size_t)nl * r.Bpad);
-                    memcpy(out.dense.data() + off, hp, bytes);
-                    for (int i = 0; i < nl; i++) out.dense_off[done + hit_list[i]] = (int64_t)(off + (size_t)i * r.Bpad);
-                }
-            }
-        }
-        if (all_rows) {
-            const size_t off = out.dense.size(), bytes = (size_t)ncalls * r.Bpad * 4;
-            void *hp = r.pinned(bytes);
-            if (!hp) { set_error("pinned host allocation failed"); return 2; }
-            MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res, bytes, cudaMemcpyDeviceToHost, c->stream));
-            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-            out.dense.resize(off + (size_t)ncalls * r.Bpad);
-            memcpy(out.dense.data() + off, hp, bytes);
-            for (int i = 0; i < ncalls; i++) out.dense_off[done + i] = (int64_t)(off + (size_t)i * r.Bpad);
-        }
+        if (int rc = reps_read_back(c, ncalls, done, thr, out, hit_list)) return rc;
         rp_stop(c, 7);
         done = k;
     }
@@ -443,11 +489,11 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
 {
     if (!c->reduces()) { set_error("the SPR search on a sharded context needs mpgpu_set_allreduce"); return 1; }
     if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
-    if (bb && c->sk.on) { set_error("-bb replicate scoring is not available under -cost in this library"); return 1; }
+    if (bb && c->sk.on != c->reps.loaded_sankoff) { set_error("the replicates were loaded for the other scoring mode: call mpgpu_load_replicates after mpgpu_set_cost_matrix"); return 1; }
     if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
     // -cost, plain mode: evaluateSankoff... leaves early when a prefix of segment sums plus the remainder bound
     // exceeds tr->bestParsimony (:951-956); its return value is then > best, i.e. the insertion changes nothing
-    const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1;
+    const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1 && !bb;   // -bb runs with perSiteScores: no early exit
     const int n = c->n, nvisit = 2 * n - 2;
     uint32_t score = 0;
     if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
@@ -813,7 +859,7 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (!c || !boot || !segment_upper) { set_error("null argument"); return 1; }
     if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
     if (B < 1 || nseg < 1) { set_error("need at least one replicate and one segment"); return 1; }
-    if (c->sk.on) { set_error("-bb replicate scoring is not available under -cost in this library"); return 1; }
+    if (c->sk.on && !c->sort_alignment) { set_error("-cost with -bb needs sort_alignment (informative patterns first)"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     free_reps(c);
     Reps &r = c->reps;
@@ -855,9 +901,12 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (rc) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "uploading replicate weights");
     r.G = 1;
-    if (int rc2 = build_classification(c)) return rc2;
-    r.reclassifications = 0;
-    if (r.use_tensor) { if (int rc2 = make_w8_tensor_map(c)) return rc2; }
+    r.loaded_sankoff = c->sk.on;
+    if (!c->sk.on) {                      // -cost: per-pattern cost rows go through the exact kernel of sankoff.cu
+        if (int rc2 = build_classification(c)) return rc2;
+        r.reclassifications = 0;
+        if (r.use_tensor) { if (int rc2 = make_w8_tensor_map(c)) return rc2; }
+    }
     r.loaded = true;
     r.tree_valid = false;
     return 0;

@@ -101,6 +101,7 @@ struct ScanPlan {
 static const int kTreeRows = 17;          // rows 0..15: bit planes of the tree's per-site counters, row 16: their weighted sum
 struct Reps {
     bool loaded = false;
+    bool loaded_sankoff = false;          // loaded while a cost matrix was set: REPS runs on per-pattern cost rows (sankoff.cu)
     int B = 0, Bpad = 0;                  // weight columns (replicates, + 1 for original_sample), padded to the tensor tile (256)
     int Buser = 0;                        // replicates proper: columns [0, Buser); column Buser = original_sample when has_orig
     bool has_orig = false;
@@ -180,6 +181,11 @@ struct Sankoff {
     uint2 *h_tot = nullptr; size_t h_tot_cap = 0;          // pinned copy
     int4 *d_list = nullptr; size_t list_cap = 0;
     uint32_t *d_tmp = nullptr; size_t tmp_cap = 0;
+    // -bb under -cost: per-pattern cost rows (row 0 = the current tree), their REPS, row bookkeeping
+    uint32_t *d_rows = nullptr; size_t rows_cap = 0;       // [rows][Lh]
+    int32_t *d_X = nullptr; size_t X_cap = 0;              // [rows][Bpad]
+    int32_t *d_row_of = nullptr; size_t row_of_cap = 0;    // [n_cand]
+    int32_t *d_call_row = nullptr; size_t call_row_cap = 0;
     std::vector<uint32_t> h_est;          // per candidate of the last scan: max_seg(prefix + lb); > bestParsimony <=> the reference exits early
 };
 
@@ -295,6 +301,8 @@ int sk_tree_score(Ctx *c, int start_ref, uint32_t *score);
 int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum);
 int sk_raw_view(Ctx *c, int ref, uint16_t *out);
 int sk_run_scan(Ctx *c);
+int sk_reps_rows_capacity(Ctx *c);
+int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_call_row, int ncalls, bool use_thr);
 int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity);
 
 // ---- kernel launchers (fitch_kernels.cu) -------------------------------------------------

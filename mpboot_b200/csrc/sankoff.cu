@@ -286,7 +286,20 @@ __global__ void __launch_bounds__(128) k_sk_junction(const uint32_t *__restrict_
 // ---- the SPR scan (testInsertParsimony batched; same program streams as k_spr_scan) ------------
 // One warp = (task, chunk).  The stack holds U' (transformed up-views) per lane in shared memory:
 // [slot][state][lane][V].
-template <int S, int V>
+// ROWS (the -bb second pass): instead of accumulating, the per-pattern minima of the insertion -- its
+// _pattern_pars vector (pllComputeSankoffPatternParsimony :3346) -- go to out_row[0..V) (pattern-pair order).
+template <int V, bool ROWS>
+__device__ __forceinline__ void sk_emit(const uint32_t (&best)[V], const uint2 (&w)[V], const SkSeg &g, uint32_t *__restrict__ out_row)
+{
+    if (ROWS) {
+#pragma unroll
+        for (int k = 0; k < V; k++) out_row[k] = best[k];
+    } else {
+        sk_accum<V>(best, w, g, out_row);
+    }
+}
+
+template <int S, int V, bool ROWS>
 __device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U)[S * V], const uint32_t *__restrict__ px,
                                          const uint32_t *__restrict__ pc, const uint32_t *__restrict__ ps,
                                          bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
@@ -304,12 +317,12 @@ __device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U
     if (do_out) {
         uint32_t best[V];
         sk_best3<S, V>(U1p, pc, ps, best);
-        sk_accum<V>(best, w, g, out_row);
+        sk_emit<V, ROWS>(best, w, g, out_row);
     }
 }
 
 // register form (small S): X = sibling view, C = the child's own view, Sv = pruned subtree, all already loaded
-template <int S, int V>
+template <int S, int V, bool ROWS>
 __device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (&U)[S * V], const uint32_t (&X)[S * V],
                                            const uint32_t (&C)[S * V], const uint32_t (&Sv)[S * V],
                                            bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
@@ -331,17 +344,19 @@ __device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (
         for (int z = 0; z < S; z++)
 #pragma unroll
             for (int k = 0; k < V; k++) best[k] = __vminu2(best[k], U1p[z * V + k] + C[z * V + k] + Sv[z * V + k]);
-        sk_accum<V>(best, w, g, out_row);
+        sk_emit<V, ROWS>(best, w, g, out_row);
     }
 }
 
-template <int S>
+// ROWS: row_of[candidate] >= 0 selects the candidates whose vector is wanted; rows = [row][Lh]
+template <int S, bool ROWS>
 __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views4, int Lh,
                                                  const ScanTask *__restrict__ tasks, int ntasks,
                                                  const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
                                                  int nslots, int cand_bias,
                                                  const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
-                                                 uint32_t *__restrict__ segout)
+                                                 uint32_t *__restrict__ segout,
+                                                 const int32_t *__restrict__ row_of, uint32_t *__restrict__ rows)
 {
     constexpr int V = SkLay<S>::V;
     constexpr bool HOLD = S <= 4;         // child views and the pruned subtree's view live in registers; next op prefetched
@@ -361,6 +376,7 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
     for (int k = 0; k < V; k++) w[k] = __ldg(wts + i0 + k);
     const SkSeg g = sk_seg_setup(__ldg(segof + i0), lane);
     uint32_t *outc = segout + (size_t)(t1.z - cand_bias) * nseg;
+    const int32_t *rowc = ROWS ? row_of + (t1.z - cand_bias) : nullptr;
     const uint32_t *ps = vbase + (size_t)(uint32_t)t0.x * 4;
     SkCost<S> cm; cm.init();
     const int oe = t1.x;
@@ -387,7 +403,12 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
             }
         }
         const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;
-        const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;
+        uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;
+        uint32_t *out1 = outc + (size_t)o1 * nseg, *out2 = outc + (size_t)o2 * nseg;
+        if (ROWS) {
+            if (o1 != 0xffff) { const int r = __ldg(rowc + o1); if (r < 0) o1 = 0xffff; else out1 = rows + (size_t)r * Lh + i0; }
+            if (o2 != 0xffff) { const int r = __ldg(rowc + o2); if (r < 0) o2 = 0xffff; else out2 = rows + (size_t)r * Lh + i0; }
+        }
         uint32_t U[S * V];
         if (src < 0xfe) {
             const uint32_t *sp = stack + (size_t)src * S * 32 * V;
@@ -401,12 +422,12 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
         }
         if (HOLD) {
             if (o1 != 0xffff || dst1 != 0xff)
-                sk_child_r<S, V>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(B), reinterpret_cast<uint32_t (&)[S * V]>(A),
-                                 reinterpret_cast<uint32_t (&)[S * V]>(Sv), o1 != 0xffff, outc + (size_t)o1 * nseg, dst1 != 0xff,
+                sk_child_r<S, V, ROWS>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(B), reinterpret_cast<uint32_t (&)[S * V]>(A),
+                                 reinterpret_cast<uint32_t (&)[S * V]>(Sv), o1 != 0xffff, out1, dst1 != 0xff,
                                  stack + (size_t)dst1 * S * 32 * V, w, g);
             if (o2 != 0xffff || dst2 != 0xff)
-                sk_child_r<S, V>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(A), reinterpret_cast<uint32_t (&)[S * V]>(B),
-                                 reinterpret_cast<uint32_t (&)[S * V]>(Sv), o2 != 0xffff, outc + (size_t)o2 * nseg, dst2 != 0xff,
+                sk_child_r<S, V, ROWS>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(A), reinterpret_cast<uint32_t (&)[S * V]>(B),
+                                 reinterpret_cast<uint32_t (&)[S * V]>(Sv), o2 != 0xffff, out2, dst2 != 0xff,
                                  stack + (size_t)dst2 * S * 32 * V, w, g);
 #pragma unroll
             for (int x = 0; x < (HOLD ? S * V : 1); x++) { A[x] = An[x]; B[x] = Bn[x]; }
@@ -414,10 +435,10 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
             const uint32_t *pa = vbase + (size_t)(uint32_t)fc.x * 4;
             const uint32_t *pb = vbase + (size_t)(uint32_t)fc.y * 4;
             if (o1 != 0xffff || dst1 != 0xff)
-                sk_child<S, V>(cm, U, pb, pa, ps, o1 != 0xffff, outc + (size_t)o1 * nseg, dst1 != 0xff, stack + (size_t)dst1 * S * 32 * V,
+                sk_child<S, V, ROWS>(cm, U, pb, pa, ps, o1 != 0xffff, out1, dst1 != 0xff, stack + (size_t)dst1 * S * 32 * V,
                                w, g);
             if (o2 != 0xffff || dst2 != 0xff)
-                sk_child<S, V>(cm, U, pa, pb, ps, o2 != 0xffff, outc + (size_t)o2 * nseg, dst2 != 0xff, stack + (size_t)dst2 * S * 32 * V,
+                sk_child<S, V, ROWS>(cm, U, pa, pb, ps, o2 != 0xffff, out2, dst2 != 0xff, stack + (size_t)dst2 * S * 32 * V,
                                w, g);
         }
     }
@@ -443,6 +464,66 @@ __global__ void k_sk_finish(const uint32_t *__restrict__ segout, int nseg, const
     if (lane == 0) out[row] = make_uint2(total, est);
 }
 
+// ---- -bb under -cost: REPS of per-pattern cost rows (iqtree.cpp:3411-3449) ---------------------------
+// res[row][b] = sum_seg ((sum_{ptn in seg} row[ptn] * w_b[ptn]) mod 2^16): the u16 lane arithmetic of the reference
+// equals the exact sum mod 2^32 masked per segment.  Exact CUDA-core kernel: one thread per replicate, R rows per
+// block held in registers, the rows' patterns staged through shared memory, weights read pattern-major (coalesced).
+template <int R>
+__global__ void __launch_bounds__(128) k_sk_reps(const uint32_t *__restrict__ rows, int Lh, int nrows,
+                                                 const uint16_t *__restrict__ w16T, int Bpad, int upper,
+                                                 const int32_t *__restrict__ seg_upper, int nseg, int32_t *__restrict__ X)
+{
+    constexpr int TP = 128;                                 // pattern pairs per staged tile
+    __shared__ uint32_t a_s[R][TP];
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    const int r0 = blockIdx.y * R;
+    uint32_t acc[R], tot[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { acc[r] = 0; tot[r] = 0; }
+    int seg = 0;
+    int bound = seg_upper[0];
+    const int last = seg_upper[nseg - 1] < upper ? seg_upper[nseg - 1] : upper;
+    for (int p0 = 0; p0 < last; p0 += 2 * TP) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < R * TP; k += 128) {
+            const int r = k / TP, j = k % TP;
+            a_s[r][j] = (r0 + r < nrows && p0 / 2 + j < Lh) ? rows[(size_t)(r0 + r) * Lh + p0 / 2 + j] : 0u;
+        }
+        __syncthreads();
+        const int pe = min(last - p0, 2 * TP);
+        for (int q = 0; q < pe; q += 2) {
+            const int p = p0 + q;
+            while (p >= bound && seg < nseg - 1) {          // segment boundary (multiples of 16): mask and restart
+#pragma unroll
+                for (int r = 0; r < R; r++) { tot[r] += acc[r] & 0xFFFFu; acc[r] = 0; }
+                bound = seg_upper[++seg];
+            }
+            const uint32_t w0 = w16T[(size_t)p * Bpad + b];
+            const uint32_t w1 = p + 1 < last ? w16T[(size_t)(p + 1) * Bpad + b] : 0u;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t a = a_s[r][q >> 1];
+                acc[r] += (a & 0xFFFFu) * w0 + (a >> 16) * w1;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (r0 + r < nrows) X[(size_t)(r0 + r) * Bpad + b] = (int32_t)(tot[r] + (acc[r] & 0xFFFFu));
+}
+
+// res[call] = X[row of call]; hit[call] = some replicate reaches its threshold
+__global__ void k_sk_res_gather(const int32_t *__restrict__ X, const int32_t *__restrict__ call_row, int ncalls, int Bpad, int Buser,
+                                int32_t *__restrict__ res, const int32_t *__restrict__ thr, int32_t *__restrict__ call_hit)
+{
+    const int call = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (call >= ncalls || b >= Bpad) return;
+    const int32_t v = X[(size_t)call_row[call] * Bpad + b];
+    res[(size_t)call * Bpad + b] = v;
+    if (thr && b < Buser && v <= thr[b]) call_hit[call] = 1;
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 #define SK_DISPATCH(CALL)                                                                      \
     switch (c->S) {                                                                            \
@@ -465,6 +546,12 @@ void sk_free(Ctx *c)
     if (k.d_tot) cudaFree(k.d_tot);
     if (k.d_list) cudaFree(k.d_list);
     if (k.d_tmp) cudaFree(k.d_tmp);
+    if (k.d_rows) cudaFree(k.d_rows);
+    if (k.d_X) cudaFree(k.d_X);
+    if (k.d_row_of) cudaFree(k.d_row_of);
+    if (k.d_call_row) cudaFree(k.d_call_row);
+    k.d_rows = nullptr; k.d_X = nullptr; k.d_row_of = nullptr; k.d_call_row = nullptr;
+    k.rows_cap = k.X_cap = k.row_of_cap = k.call_row_cap = 0;
     if (k.h_tot) cudaFreeHost(k.h_tot);
     k.d_views = nullptr; k.d_w = nullptr; k.d_seg = nullptr; k.d_lb = nullptr; k.d_mask = nullptr;
     k.d_segout = nullptr; k.d_tot = nullptr; k.d_list = nullptr; k.d_tmp = nullptr; k.h_tot = nullptr;
@@ -746,12 +833,12 @@ int sk_run_scan(Ctx *c)
     {                                                                                                                          \
         static size_t configured = 0;                                                                                          \
         if (smem > 48 * 1024 && smem > configured) {                                                                           \
-            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));   \
+            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));   \
             configured = 200 * 1024;                                                                                           \
         }                                                                                                                      \
-        k_sk_scan<S_><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh,       \
+        k_sk_scan<S_, false><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
             c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
-            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout);                                                                  \
+            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, nullptr, nullptr);                                                \
     }
     SK_DISPATCH(SK_SCAN_LAUNCH);
 #undef SK_SCAN_LAUNCH
@@ -775,6 +862,96 @@ int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref
     if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
     if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
     if (cand_prune) memcpy(cand_prune, pl.cand_prune.data(), pl.n_cand * sizeof(int32_t));
+    return 0;
+}
+
+// ---- -bb under -cost ------------------------------------------------------------------------------
+// One chunk of saveCurrentTree calls: call_row[i] = 0 for the current tree, 1 + k for the k-th selected candidate
+// (row_of[candidate] = k, -1 = not selected; nsel of them).  Leaves res[call][Bpad] in reps.d_res and the hit flags in
+// reps.d_call_hit (when thr).
+int sk_reps_rows_capacity(Ctx *c)
+{
+    size_t budget = (size_t)2 << 30;
+    if (const char *e = getenv("MPGPU_REPS_ROW_BYTES")) { long long v = atoll(e); if (v > 0) budget = (size_t)v; }
+    const size_t per_row = (size_t)c->sk.Lh * 4 + (size_t)c->reps.Bpad * 4;
+    return (int)std::max<size_t>(64, std::min<size_t>(budget / per_row, (size_t)1 << 20));
+}
+
+int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_call_row, int ncalls, bool use_thr)
+{
+    Sankoff &k = c->sk;
+    Reps &r = c->reps;
+    ScanPlan &pl = c->plan;
+    const int nrows = 1 + nsel;
+    if (int rc = bind_cost(c)) return rc;
+    if (int rc = ensure(k.d_rows, k.rows_cap, (size_t)nrows * k.Lh)) return rc;
+    if (int rc = ensure(k.d_X, k.X_cap, (size_t)nrows * r.Bpad)) return rc;
+    if (int rc = ensure(k.d_row_of, k.row_of_cap, (size_t)std::max(pl.n_cand, 1))) return rc;
+    if (int rc = ensure(k.d_call_row, k.call_row_cap, (size_t)ncalls)) return rc;
+    if (int rc = ensure(r.d_res, r.res_cap, (size_t)ncalls * r.Bpad)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_call_row, h_call_row, (size_t)ncalls * 4, cudaMemcpyHostToDevice, c->stream));
+    // row 0: the current tree's vector (junction at the start edge, every pattern)
+    {
+        const HostTree &t = c->tree;
+        const int rr = t.back(3);
+        const int4 j = make_int4(t.vid(3), t.vid(t.back(t.next(rr))), t.vid(t.back(t.next(t.next(rr)))), 0);
+        if (int rc = sk_ensure_out(c, 1)) return rc;
+        if (int rc = ensure(k.d_list, k.list_cap, (size_t)1)) return rc;
+        MPGPU_CUDA(cudaMemcpyAsync(k.d_list, &j, sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)k.nseg * sizeof(uint32_t), c->stream));
+        const int64_t warps = (int64_t)(k.Lh / (32 * sk_vpl(c->S)));
+        const int blocks = (int)((warps + 3) / 4);
+        SK_DISPATCH((k_sk_junction<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, 1, k.d_w, k.d_seg, k.nseg,
+                                                                      k.d_segout, k.d_rows)));
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // `j` is a stack temporary
+    }
+    if (nsel > 0) {
+        MPGPU_CUDA(cudaMemcpyAsync(k.d_row_of, h_row_of, (size_t)pl.n_cand * 4, cudaMemcpyHostToDevice, c->stream));
+        const int ntasks = (int)pl.tasks.size();
+        const int nslots = pl.max_slot > 0 ? pl.max_slot : 1;
+        const int V = sk_vpl(c->S);
+        const size_t per_warp = (size_t)nslots * c->S * 32 * V * sizeof(uint32_t);
+        int wpb = 4;
+        while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+        const size_t smem = per_warp * wpb;
+        const long long warps = (long long)ntasks * (k.Lh / (32 * V));
+        const long long blocks = (warps + wpb - 1) / wpb;
+#define SK_ROWS_LAUNCH                                                                                                         \
+    {                                                                                                                          \
+        static size_t configured = 0;                                                                                          \
+        if (smem > 48 * 1024 && smem > configured) {                                                                           \
+            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024))); \
+            configured = 200 * 1024;                                                                                           \
+        }                                                                                                                      \
+        k_sk_scan<S_, true><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
+            c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
+            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, k.d_row_of, k.d_rows + k.Lh);                                     \
+    }
+        SK_DISPATCH(SK_ROWS_LAUNCH);
+#undef SK_ROWS_LAUNCH
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    {
+        constexpr int R = 8;
+        dim3 grid((unsigned)(r.Bpad / 128), (unsigned)((nrows + R - 1) / R));
+        k_sk_reps<R><<<grid, 128, 0, c->stream>>>(k.d_rows, k.Lh, nrows, r.d_w16T, r.Bpad, r.upper, r.d_seg_upper, (int)r.seg_upper.size(), k.d_X);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    if (use_thr) {
+        if (int rc = ensure(r.d_call_hit, r.call_hit_cap, (size_t)ncalls)) return rc;
+        MPGPU_CUDA(cudaMemsetAsync(r.d_call_hit, 0, (size_t)ncalls * 4, c->stream));
+    }
+    {
+        dim3 grid((unsigned)((r.Bpad + 255) / 256), (unsigned)ncalls);
+        k_sk_res_gather<<<grid, 256, 0, c->stream>>>(k.d_X, k.d_call_row, ncalls, r.Bpad, r.Buser, r.d_res, use_thr ? r.d_thr : nullptr, r.d_call_hit);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    r.rows_scored += nrows;
     return 0;
 }
 

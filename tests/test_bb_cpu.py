@@ -46,7 +46,8 @@ def ratchet_setup(c, pp, seed):
     return w2, orig, init
 
 
-def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None, mulhits=False):
+def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None, mulhits=False, cost=None):
+    eng.set_cost_matrix(cost, seg if cost is not None else None)      # -cost: pllCostMatrix + pllSegmentUpper (None = Fitch)
     if ratchet is not None:
         eng.set_weights(ratchet[0])
     else:
@@ -164,6 +165,66 @@ def test_port_bb_mulhits_matches_golden(k):
         check_mulhits_golden(g, k, tag, r)
 
 
+# ---- -cost together with -bb: saveCurrentTree on Sankoff pattern vectors (pllComputeSankoffPatternParsimony :3346) ----
+SANKOFF_BB_CASES = [(16, 400, 1, 7, 40, 0.05), (14, 300, 2, 5, 30, 0.05), (22, 700, 1, 21, 50, 0.02), (12, 260, 6, 9, 24, 0.05)]
+SANKOFF_BB_GOLD = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "skbb.npz")
+
+
+def sankoff_bb_cost(dt, seed):
+    S = {0: 2, 1: 4, 2: 20, 6: 32}[dt]
+    if S == 4:
+        return np.array([[0, 2, 1, 2], [2, 0, 2, 1], [1, 2, 0, 2], [2, 1, 2, 0]], dtype=np.uint32)
+    r = np.random.default_rng(300 + seed).integers(1, 5, size=(S, S))
+    r = np.minimum(r, r.T); np.fill_diagonal(r, 0)
+    return r.astype(np.uint32)
+
+
+@needs_ref
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", SANKOFF_BB_CASES)
+def test_port_sankoff_bb_equals_reference(n, L, dt, seed, B, mu):
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    cost = sankoff_bb_cost(dt, seed)
+    r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    a = run_bb(o, c, boot, seg, 0.0, None, False, cost=cost)
+    same(a, run_bb(r, c, boot, seg, 0.0, None, True, cost=cost))
+    cutoff = -(a["ret"] + 6.0)
+    x = run_bb(o, c, boot, seg, cutoff, None, False, cost=cost)
+    same(x, run_bb(r, c, boot, seg, cutoff, None, True, cost=cost))
+    assert x["counters"][1] < x["counters"][0]
+    m = run_bb(o, c, boot, seg, 0.0, None, False, cost=cost, mulhits=True)
+    same(m, run_bb(r, c, boot, seg, 0.0, None, True, cost=cost, mulhits=True))
+    for e in (o, r):
+        e.set_cost_matrix(None, None)
+
+
+def sankoff_bb_golden_case(g, k):
+    n, L, dt, seed, B, mu = SANKOFF_BB_CASES[k]
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    assert np.array_equal(boot, g["c%d_boot" % k]) and np.array_equal(c["codes"], g["c%d_codes" % k])
+    return c, o, seg, boot, g["c%d_cost" % k]
+
+
+def check_sankoff_bb_golden(g, k, tag, r):
+    p = "c%d_%s_" % (k, tag)
+    assert r["ret"] == int(g[p + "ret"]) and r["draws"] == int(g[p + "draws"])
+    assert np.array_equal(r["ring"][0][3:], g[p + "bn"][3:]) and np.array_equal(r["ring"][1][3:], g[p + "bs"][3:])
+    for x, key in zip(r["state"], ("boot_logl", "boot_counts", "boot_trees")):
+        assert np.array_equal(x, g[p + key]), key
+    assert np.array_equal(r["treels"], g[p + "treels"])
+    assert np.array_equal(r["mats_tf"], g[p + "mats"])
+
+
+@pytest.mark.parametrize("k", range(len(SANKOFF_BB_CASES)))
+def test_port_sankoff_bb_matches_golden(k):
+    g = dict(np.load(SANKOFF_BB_GOLD))
+    c, o, seg, boot, cost = sankoff_bb_golden_case(g, k)
+    for tag in ("all", "cut"):
+        r = run_bb(o, c, boot, seg, float(g["c%d_%s_cutoff" % (k, tag)]), None, False, cost=cost)
+        r["mats_tf"] = r["mats"][:, [3, 4]]
+        check_sankoff_bb_golden(g, k, tag, r)
+    o.set_cost_matrix(None, None)
+
+
 def test_fingerprint_matches_python_helper():
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(16, 300, 1, 3, 8)
     res = run_bb(o, c, boot, seg, 0.0, None, False)
@@ -179,7 +240,7 @@ import os
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASE_FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith(("sankoff_", "mulhits")))
+                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith(("sankoff_", "mulhits", "skbb")))
 IDS = [os.path.basename(p)[:-4] for p in CASE_FILES]
 
 

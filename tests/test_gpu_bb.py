@@ -16,13 +16,15 @@ CASES = [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05), (30, 800, 1, 21, 
          (40, 1500, 1, 11, 300, 0.05), (16, 300, 0, 3, 20, 0.05)]
 
 
-def _engine(c, boot, seg, tensor, ratchet=None):
+def _engine(c, boot, seg, tensor, ratchet=None, cost=None):
     from mpboot_b200.engine import Engine
     eng = Engine()
     eng.set_option("reps_tensor", tensor)
     eng.load_alignment(c["codes"], c["weights"], c["datatype"])
     if ratchet is not None:
         eng.set_weights(ratchet[0])                 # the search runs on the perturbed frequencies
+    if cost is not None:
+        eng.set_cost_matrix(cost, seg)              # -cost: before the replicates are loaded
     eng.set_tree(c["bn"], c["bs"])
     eng.load_replicates(boot, seg, original_sample=None if ratchet is None else ratchet[1])
     return eng
@@ -86,9 +88,9 @@ def test_reps_wrap_free_bulk_uses_no_exceptions():
     assert groups == 1 and exc == 0 and t == 1                # everything on the tensor path
 
 
-def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None, mulhits=False):
+def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None, mulhits=False, cost=None):
     from mpboot_b200.engine import Treels
-    eng = _engine(c, boot, seg, tensor, ratchet)
+    eng = _engine(c, boot, seg, tensor, ratchet, cost)
     B = boot.shape[0]
     bl = np.full(B, -float(np.iinfo(np.int64).max), dtype=np.float64)   # -LONG_MAX, iqtree.cpp:248
     bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
@@ -169,3 +171,57 @@ def test_bb_mulhits_ratchet_iteration_matches_oracle():
     assert np.array_equal(r["state"][0], w["state"][0])
     assert all(np.array_equal(x, y) for x, y in zip(r["mulhits"], w["mulhits"]))
     assert np.array_equal(r["treels"], w["treels"])
+
+
+# ---- -cost together with -bb: REPS on Sankoff pattern vectors (k_sk_scan<ROWS> + k_sk_reps) ----
+from tests.test_bb_cpu import (SANKOFF_BB_CASES, SANKOFF_BB_GOLD, check_sankoff_bb_golden, sankoff_bb_cost,  # noqa: E402
+                               sankoff_bb_golden_case)
+
+
+@pytest.mark.parametrize("k", range(len(SANKOFF_BB_CASES)))
+def test_sankoff_reps_vectors_match_oracle(k):
+    n, L, dt, seed, B, mu = SANKOFF_BB_CASES[k]
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    cost = sankoff_bb_cost(dt, seed)
+    ninf = c["n_inf"]
+    o.set_cost_matrix(cost, seg)
+    try:
+        eng = _engine(c, boot, seg, 1, cost=cost)
+        o.set_ring(c["bn"], c["bs"]); o.allocate(True)
+        s1 = o.evaluate_full(True)
+        spp, _ = o.pattern_parsimony(ninf)
+        assert np.array_equal(eng.reps_current_tree(), portlib.reps(spp, boot[:, :ninf], seg))
+        order = eng.visit_order()
+        for i in (1, n + 1, 2 * n - 2):
+            o.set_ring(c["bn"], c["bs"]); o.allocate(True); o.evaluate_full(True)
+            o.record(True)
+            o.rearrange(i, 1, 6, True, s1)
+            mps, ptn = o.saved(True)
+            vb, mp, cref, cprune = eng.scan_visits(order, i, 1, 1, 6)
+            assert np.array_equal(mps[1:], mp.astype(np.int32))
+            got = eng.reps_candidates(np.arange(-1, len(mp), dtype=np.int32))
+            for q in range(len(mps)):
+                assert np.array_equal(got[q], portlib.reps(ptn[q, :ninf], boot[:, :ninf], seg)), (i, q)
+    finally:
+        o.set_cost_matrix(None, None)
+
+
+@pytest.mark.parametrize("k", range(len(SANKOFF_BB_CASES)))
+def test_sankoff_bb_search_matches_golden_and_oracle(k):
+    g = dict(np.load(SANKOFF_BB_GOLD))
+    c, o, seg, boot, cost = sankoff_bb_golden_case(g, k)
+    try:
+        for tag in ("all", "cut"):
+            cutoff = float(g["c%d_%s_cutoff" % (k, tag)])
+            r = _run_gpu_bb(c, boot, seg, cutoff, 1, cost=cost)
+            r["mats_tf"] = r["mats"][:, [2, 3]]
+            check_sankoff_bb_golden(g, k, tag, r)                # what the reference driver produced
+            w = run_bb(o, c, boot, seg, cutoff, None, False, cost=cost)
+            assert r["ncalls"] == w["counters"][0] and r["nreps"] == w["counters"][2]
+            assert np.array_equal(r["mats"][:, :2], w["mats"][:, 1:3])
+        w = run_bb(o, c, boot, seg, 0.0, None, False, cost=cost, mulhits=True)
+        r = _run_gpu_bb(c, boot, seg, 0.0, 1, cost=cost, mulhits=True)
+        assert r["ret"] == w["ret"] and r["draws"] == w["draws"] and np.array_equal(r["state"][0], w["state"][0])
+        assert all(np.array_equal(x, y) for x, y in zip(r["mulhits"], w["mulhits"]))
+    finally:
+        o.set_cost_matrix(None, None)

@@ -13,7 +13,7 @@ from tests.helpers import make_case
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASE_FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
-                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith(("sankoff_", "mulhits")))
+                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith(("sankoff_", "mulhits", "skbb")))
 
 
 def load(path):
