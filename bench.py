@@ -174,6 +174,24 @@ def bench_search(eng, case, args):
         out["cpu_baseline"] = {"wall_s": dt, "cores": 1, "kind": kind, "final_score": int(r_ref), "identical_result": same,
                                "sample": "the whole search (pllOptimizeSprParsimony), single-threaded code"}
         out["speedup_vs_one_core"] = dt / best
+        # MPBoot's own starting point (config[0], `-s`): one randomized-stepwise-addition tree + its SPR rounds
+        # (_pllComputeRandomizedStepwiseAdditionParsimonyTree, sprparsimony.cpp:3224), same seeds on both sides
+        seed_fn(4321)
+        t0 = time.time()
+        rb, rbn, rbs, rins2, _ = eng.stepwise_addition(777, args.maxtrav, fn)
+        t_gpu = time.time() - t0
+        d_gpu = int(draws_fn())
+        seed_fn(4321)
+        t0 = time.time()
+        rb_ref = ref.ras(777, args.maxtrav)
+        t_ref = time.time() - t0
+        wbn, wbs = ref.get_ring()
+        out["ras"] = {"what": "one RAS tree + SPR rounds (mpgpu_stepwise_addition, host buffers) vs the reference on one core",
+                      "wall_s": t_gpu, "insertions": int(rins2), "final_score": int(rb), "reference_wall_s": t_ref,
+                      "identical_result": bool(rb == rb_ref and d_gpu == int(draws_fn()) and np.array_equal(rbn[3:], wbn[3:])
+                                               and np.array_equal(rbs[3:], wbs[3:])),
+                      "speedup_vs_one_core": t_ref / t_gpu}
+        eng.set_tree(case["bn"], case["bs"])
     return out
 
 
@@ -293,6 +311,49 @@ def bench_cost(case, order, args, flush, stream, local):
         ret, bn, bs, nins = eng.optimize_spr(case["bn"], case["bs"], rng.fn, 1, args.maxtrav, rng_user=rng.user)
         out["search"] = {"what": "mpgpu_optimize_spr under -cost from the random tree (early exit replayed)", "wall_s": time.time() - t0,
                          "insertions": int(nins), "final_score": int(ret)}
+    if not args.no_bb:
+        # -cost with -bb: every insertion's per-pattern cost vector (k_sk_scan<ROWS>) against B replicates (k_sk_reps, exact u16 weights)
+        os.environ.setdefault("MPGPU_REPS_ROW_BYTES", str(6 << 30))
+        boot = make_replicates(case, args.replicates)
+        eng.load_replicates(boot, seg)
+        eng.set_tree(case["bn"], case["bs"])
+        eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
+        calls = []
+        for v in range(nvis):
+            calls.append(-1); calls.extend(range(vb[v], vb[v + 1]))
+        calls = np.array(calls, dtype=np.int32)
+        eng.scan_launch(); eng.reps_candidates_device(calls)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        e0.record(); eng.scan_launch(); eng.reps_candidates_device(calls); e1.record()
+        torch.cuda.synchronize()
+        bb_s = e0.elapsed_time(e1) * 1e-3
+        macs = float(len(np.unique(calls))) * L * args.replicates
+        out["bb"] = {"what": "the same sweep under -cost -bb, cutoff off: every insertion's pattern vector x %d replicates "
+                             "(exact CUDA-core contraction, u16 lanes with per-segment wrap)" % args.replicates,
+                     "calls_per_step": int(len(calls)), "ms_per_step": bb_s * 1e3, "reps_vectors_per_s": len(calls) / bb_s,
+                     "mac_per_s": macs / bb_s}
+        if not args.no_cpu_baseline:
+            use_ref = reflib.available()
+            ref = (reflib.RefEngine(case["chars"], case["weights"], dt, n_informative=ninf) if use_ref
+                   else portlib.OracleEngine(case["codes"], case["weights"], dt))
+            ref.set_cost_matrix(cost, seg)
+            ref.set_ring(case["bn"], case["bs"])
+            ref.allocate(per_site=True)
+            s0 = ref.evaluate_full(per_site=True)
+            ref.boot_init(boot, seg, 0.0, 0.5, None)
+            nv, t0 = 0, time.time()
+            for i in range(1, nvis + 1):
+                ref.rearrange(i, 1, args.maxtrav, True, s0)
+                nv += 1
+                if time.time() - t0 > args.cpu_budget:
+                    break
+            dt_s = time.time() - t0
+            cnt = ref.boot_counters()
+            out["bb"]["cpu_baseline"] = {"reps_vectors_per_s": cnt[2] / dt_s, "cores": 1, "kind": "reference" if use_ref else "port",
+                                         "sample": "%d of %d node visits (%d REPS vectors x %d replicates) in %.1f s"
+                                                   % (nv, nvis, cnt[2], args.replicates, dt_s)}
     if not args.no_cpu_baseline:
         use_ref = reflib.available()
         ref = (reflib.RefEngine(case["chars"], case["weights"], dt, n_informative=ninf) if use_ref

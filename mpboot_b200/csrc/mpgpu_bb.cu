@@ -848,6 +848,14 @@ int mpgpu_reps_info(mpgpu_ctx *c, int *groups, int *exceptions, int *tensor)
     return 0;
 }
 
+int mpgpu_sankoff_reps_stats(mpgpu_ctx *c, int64_t *tensor_chunks, int64_t *exact_chunks)
+{
+    if (!c) { set_error("null context"); return 1; }
+    if (tensor_chunks) *tensor_chunks = c->sk.tensor_chunks;
+    if (exact_chunks) *exact_chunks = c->sk.exact_chunks;
+    return 0;
+}
+
 int mpgpu_load_replicates(mpgpu_ctx *c, int B, const uint16_t *boot, int stride, const int32_t *segment_upper, int nseg)
 {
     return mpgpu_load_replicates2(c, B, boot, stride, segment_upper, nseg, nullptr);
@@ -902,10 +910,27 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (e != cudaSuccess) return cuda_fail(e, "uploading replicate weights");
     r.G = 1;
     r.loaded_sankoff = c->sk.on;
-    if (!c->sk.on) {                      // -cost: per-pattern cost rows go through the exact kernel of sankoff.cu
+    if (!c->sk.on) {
         if (int rc2 = build_classification(c)) return rc2;
         r.reclassifications = 0;
         if (r.use_tensor) { if (int rc2 = make_w8_tensor_map(c)) return rc2; }
+    } else {
+        // -cost: the rows are per-pattern costs (sankoff.cu).  The u8 operand is only usable when no replicate weight
+        // exceeds 255; whether a chunk may take the tensor path is decided per chunk (costs <= 255, no segment can wrap).
+        r.n_heavy = 0;
+        for (int p = 0; p < r.upper; p++) r.n_heavy += r.heavy[p] ? 1 : 0;
+        r.n_exc = 0;
+        if (r.use_tensor && r.n_heavy == 0) {
+            uint8_t *d_is_exc = nullptr;
+            MPGPU_CUDA(cudaMalloc((void **)&d_is_exc, (size_t)r.Kpad));
+            MPGPU_CUDA(cudaMemsetAsync(d_is_exc, 0, (size_t)r.Kpad, c->stream));
+            int rc2 = launch_build_w8(c, d_is_exc);
+            cudaError_t e2 = cudaStreamSynchronize(c->stream);
+            cudaFree(d_is_exc);
+            if (rc2) return rc2;
+            if (e2 != cudaSuccess) return cuda_fail(e2, "building the tensor operand");
+            if (int rc3 = make_w8_tensor_map(c)) return rc3;
+        }
     }
     r.loaded = true;
     r.tree_valid = false;

@@ -186,6 +186,9 @@ struct Sankoff {
     int32_t *d_X = nullptr; size_t X_cap = 0;              // [rows][Bpad]
     int32_t *d_row_of = nullptr; size_t row_of_cap = 0;    // [n_cand]
     int32_t *d_call_row = nullptr; size_t call_row_cap = 0;
+    uint8_t *d_rows8 = nullptr; size_t rows8_cap = 0;      // [rows][Kpad] the same rows as u8 (tensor path)
+    uint32_t *d_colmax = nullptr; size_t colmax_cap = 0;   // [Lh] per-pattern maximum over the chunk's rows (u16x2) + [2] flags
+    int64_t tensor_chunks = 0, exact_chunks = 0;           // statistics: which contraction the chunks took
     std::vector<uint32_t> h_est;          // per candidate of the last scan: max_seg(prefix + lb); > bestParsimony <=> the reference exits early
 };
 
@@ -328,6 +331,7 @@ int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows
 int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows);
 int make_w8_tensor_map(Ctx *c);
 int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows);
+int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrows, int32_t *X, int x_pitch);
 int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row);
 int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr, int32_t *d_call_hit);
 int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, int nlist, int32_t *d_out);

@@ -339,6 +339,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 // 4 bits -> 4 bytes of 0/1 (bit j -> byte j)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
+// BYTES: the A operand is already u8, K-major, [row][a_pitch bytes] (per-pattern Sankoff costs, -cost with -bb):
+// thread r copies the 128 bytes of its row into the swizzled tile instead of expanding 128 bits.
+template <bool BYTES>
 __global__ void __launch_bounds__(THREADS, 1)
 k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_a, int a_pitch, int a_kb0,
           int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
@@ -379,6 +382,30 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
         // ---- A producers: thread r owns tile row r ----
         const int r = threadIdx.x;
         const bool live = (m0 + r) < nrows;
+        if (BYTES) {
+            const uint4 *src8 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(rows_a) + (size_t)(m0 + r) * a_pitch);
+            const uint32_t sw8 = (uint32_t)(r & 7);
+            uint4 cur[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) cur[q] = live ? __ldg(src8 + (size_t)kb_begin * 8 + q) : make_uint4(0, 0, 0, 0);
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                uint4 nxt[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    nxt[q] = (live && it + 1 < nkb) ? __ldg(src8 + (size_t)(kb_begin + it + 1) * 8 + q) : make_uint4(0, 0, 0, 0);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                uint8_t *arow = smem_gen + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+#pragma unroll
+                for (int q = 0; q < 8; q++) *reinterpret_cast<uint4 *>(arow + ((q ^ sw8) << 4)) = cur[q];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+#pragma unroll
+                for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+            }
+        } else {
         const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch) - a_kb0;   // row starts at K-block a_kb0
         const uint32_t sw = (uint32_t)(r & 7);
         // the 128 bits of K-block it+PF are requested while K-block it is expanded: the L2 latency of
@@ -413,6 +440,7 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(s));
             }
+        }
         }
     } else if (warp == 4) {
         // ---- B producer (TMA) ----
@@ -526,7 +554,7 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int
     if (kb_hi <= kb_lo) return 0;
     static bool configured = false;
     if (!configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         configured = true;
     }
     const int mt = (nrows + tc::M - 1) / tc::M, nt = r.Bpad / tc::N;
@@ -552,8 +580,49 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int
         if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
         MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
     }
-    tc::k_reps_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
-                                                                    x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
+    tc::k_reps_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
+                                                                           x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
+    if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// X[0..nrows)[b] += rows8 x w8 over all K-blocks: rows8 = u8 [nrows][pitch_bytes] (pitch = Kpad), X pitch x_pitch (zeroed by
+// the caller).  The -cost / -bb contraction (per-pattern Sankoff costs that fit in u8, wrap-free segments).
+int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrows, int32_t *X, int x_pitch)
+{
+    Reps &r = c->reps;
+    if (nrows == 0) return 0;
+    if (!r.tmap_valid) { set_error("replicate weights not loaded"); return 1; }
+    static bool configured = false;
+    if (!configured) {
+        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        configured = true;
+    }
+    const int mt = (nrows + tc::M - 1) / tc::M, nt = r.Bpad / tc::N;
+    const int nkb = r.Kpad / tc::KB;
+    int splits = 1;
+    {
+        const int ctas = mt * nt, sms = 148, epi = 24;
+        long best = -1;
+        for (int sp = 1; sp <= 32 && sp * 8 <= nkb; sp++) {
+            const long waves = ((long)ctas * sp + sms - 1) / sms;
+            const long cost = waves * ((nkb + sp - 1) / sp + epi);
+            if (best < 0 || cost < best) { best = cost; splits = sp; }
+        }
+    }
+    const int per = (nkb + splits - 1) / splits;
+    splits = (nkb + per - 1) / per;
+    dim3 grid(mt, nt, splits);
+    const bool timed = r.timing && nrows >= r.timed_rows;
+    if (timed) {
+        if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
+        MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
+    }
+    tc::k_reps_tc<true><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
+                                                                          reinterpret_cast<const uint32_t *>(rows8), pitch_bytes, 0,
+                                                                          0, nrows, 0, nkb, per, r.B, x_pitch, X);
     if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());

@@ -512,6 +512,57 @@ __global__ void __launch_bounds__(128) k_sk_reps(const uint32_t *__restrict__ ro
         if (r0 + r < nrows) X[(size_t)(r0 + r) * Bpad + b] = (int32_t)(tot[r] + (acc[r] & 0xFFFFu));
 }
 
+// ---- tensor path of the same contraction: the rows as u8 + the proof that nothing can wrap --------
+// rows (u16x2 words) -> rows8 [row][Kpad] u8; flags[0] = 1 when some cost does not fit in a byte
+__global__ void k_sk_pack(const uint32_t *__restrict__ rows, int Lh, int nrows, int Kpad, uint8_t *__restrict__ rows8,
+                          uint32_t *__restrict__ flags)
+{
+    const int per = Kpad / 8;                               // 8 patterns (4 words in, 8 bytes out) per thread
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)nrows * per) return;
+    const int row = (int)(gid / per), t = (int)(gid % per);
+    const uint4 v = *reinterpret_cast<const uint4 *>(rows + (size_t)row * Lh + 4 * t);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lo = 0, hi = 0, over = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t a = w[q] & 0xFFFFu, b = w[q] >> 16;
+        over |= (a | b) >> 8;
+        const uint32_t two = (a & 0xFFu) | (b & 0xFFu) << 8;
+        if (q < 2) lo |= two << (16 * q); else hi |= two << (16 * (q - 2));
+    }
+    *reinterpret_cast<uint2 *>(rows8 + (size_t)row * Kpad + 8 * t) = make_uint2(lo, hi);
+    if (over) flags[0] = 1;
+}
+
+// colmax[p] = max over the chunk's rows of the cost of pattern p
+__global__ void k_sk_colmax(const uint32_t *__restrict__ rows, int Lh, int nrows, uint32_t *__restrict__ colmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lh) return;
+    uint32_t m = 0;
+    for (int r = blockIdx.y; r < nrows; r += gridDim.y) m = __vmaxu2(m, rows[(size_t)r * Lh + i]);
+    atomicMax(colmax + 2 * i, m & 0xFFFFu);
+    atomicMax(colmax + 2 * i + 1, m >> 16);
+}
+
+// flags[1] = 1 when, for some segment and replicate, sum_{ptn in seg} colmax[ptn] * w_b[ptn] reaches 2^16: only then
+// can a 16-bit segment sum of some row wrap (:3424-3431); otherwise every masked sum equals the plain sum.
+__global__ void __launch_bounds__(256) k_sk_wrapcheck(const uint32_t *__restrict__ colmax, const uint16_t *__restrict__ w16T, int Bpad, int B,
+                                                      const int32_t *__restrict__ seg_upper, int upper, uint32_t *__restrict__ flags)
+{
+    const int seg = blockIdx.x;
+    const int lo = seg ? seg_upper[seg - 1] : 0;
+    const int hi = min(seg_upper[seg], upper);
+    bool bad = false;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        unsigned long long sum = 0;
+        for (int p = lo; p < hi; p++) sum += (unsigned long long)colmax[p] * w16T[(size_t)p * Bpad + b];
+        if (sum >= 65536ull) bad = true;
+    }
+    if (bad) flags[1] = 1;
+}
+
 // res[call] = X[row of call]; hit[call] = some replicate reaches its threshold
 __global__ void k_sk_res_gather(const int32_t *__restrict__ X, const int32_t *__restrict__ call_row, int ncalls, int Bpad, int Buser,
                                 int32_t *__restrict__ res, const int32_t *__restrict__ thr, int32_t *__restrict__ call_hit)
@@ -550,6 +601,9 @@ void sk_free(Ctx *c)
     if (k.d_X) cudaFree(k.d_X);
     if (k.d_row_of) cudaFree(k.d_row_of);
     if (k.d_call_row) cudaFree(k.d_call_row);
+    if (k.d_rows8) cudaFree(k.d_rows8);
+    if (k.d_colmax) cudaFree(k.d_colmax);
+    k.d_rows8 = nullptr; k.d_colmax = nullptr; k.rows8_cap = k.colmax_cap = 0;
     k.d_rows = nullptr; k.d_X = nullptr; k.d_row_of = nullptr; k.d_call_row = nullptr;
     k.rows_cap = k.X_cap = k.row_of_cap = k.call_row_cap = 0;
     if (k.h_tot) cudaFreeHost(k.h_tot);
@@ -934,12 +988,37 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }
-    {
+    // tensor path (tcgen05 kind::i8 on the rows as u8) when every cost fits in a byte, no replicate weight exceeds 255 and no
+    // 16-bit segment sum of this chunk can wrap -- proved from the chunk's own column maxima; the exact kernel otherwise
+    bool tensor = r.use_tensor && r.tmap_valid && r.n_heavy == 0;
+    if (tensor) {
+        if (int rc = ensure(k.d_rows8, k.rows8_cap, (size_t)nrows * r.Kpad)) return rc;
+        if (int rc = ensure(k.d_colmax, k.colmax_cap, (size_t)2 * k.Lh + 2)) return rc;
+        uint32_t *flags = k.d_colmax + 2 * k.Lh;
+        MPGPU_CUDA(cudaMemsetAsync(k.d_colmax, 0, ((size_t)2 * k.Lh + 2) * 4, c->stream));
+        const int64_t pt = (int64_t)nrows * (r.Kpad / 8);
+        k_sk_pack<<<(unsigned)((pt + 255) / 256), 256, 0, c->stream>>>(k.d_rows, k.Lh, nrows, r.Kpad, k.d_rows8, flags);
+        dim3 cg((unsigned)((k.Lh + 255) / 256), (unsigned)std::min(nrows, 32));
+        k_sk_colmax<<<cg, 256, 0, c->stream>>>(k.d_rows, k.Lh, nrows, k.d_colmax);
+        k_sk_wrapcheck<<<(unsigned)r.seg_upper.size(), 256, 0, c->stream>>>(k.d_colmax, r.d_w16T, r.Bpad, r.B, r.d_seg_upper, r.upper, flags);
+        c->launches += 3;
+        MPGPU_CUDA(cudaGetLastError());
+        uint32_t h_flags[2] = {1, 1};
+        MPGPU_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        tensor = !h_flags[0] && !h_flags[1];
+    }
+    if (tensor) {
+        MPGPU_CUDA(cudaMemsetAsync(k.d_X, 0, (size_t)nrows * r.Bpad * 4, c->stream));
+        if (int rc = launch_reps_tc_bytes(c, k.d_rows8, r.Kpad, nrows, k.d_X, r.Bpad)) return rc;
+        k.tensor_chunks++;
+    } else {
         constexpr int R = 8;
         dim3 grid((unsigned)(r.Bpad / 128), (unsigned)((nrows + R - 1) / R));
         k_sk_reps<R><<<grid, 128, 0, c->stream>>>(k.d_rows, k.Lh, nrows, r.d_w16T, r.Bpad, r.upper, r.d_seg_upper, (int)r.seg_upper.size(), k.d_X);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
+        k.exact_chunks++;
     }
     if (use_thr) {
         if (int rc = ensure(r.d_call_hit, r.call_hit_cap, (size_t)ncalls)) return rc;

@@ -70,6 +70,7 @@ def lib():
     L.mpgpu_sankoff_layout.argtypes = [vp, vp, vp, vp, i32]
     L.mpgpu_sankoff_view.argtypes = [vp, i32, i32, vp]
     L.mpgpu_scan_bounds.argtypes = [vp, vp, i32]
+    L.mpgpu_sankoff_reps_stats.argtypes = [vp, vp, vp]
     L.mpgpu_reps_current_tree.argtypes = [vp, vp]
     L.mpgpu_reps_candidates.argtypes = [vp, vp, i32, vp]
     L.mpgpu_reps_candidates_device.argtypes = [vp, vp, i32, vp, vp]
@@ -358,6 +359,12 @@ class Engine:
         out = np.zeros((L, self.S), dtype=np.uint16)
         self._ck(self.L.mpgpu_sankoff_view(self.h, node, slot, _p(out)))
         return out
+
+    def sankoff_reps_stats(self):
+        """(chunks contracted on the tensor cores, chunks through the exact CUDA-core kernel) under -cost -bb"""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.L.mpgpu_sankoff_reps_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def scan_bounds(self, n_cand):
         out = np.zeros(max(n_cand, 1), dtype=np.uint32)

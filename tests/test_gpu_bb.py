@@ -225,3 +225,44 @@ def test_sankoff_bb_search_matches_golden_and_oracle(k):
         assert all(np.array_equal(x, y) for x, y in zip(r["mulhits"], w["mulhits"]))
     finally:
         o.set_cost_matrix(None, None)
+
+
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("k", [0, 2])
+def test_sankoff_reps_tensor_path_equals_exact(k, tensor):
+    """Light replicate weights, costs below 256, short segments: every chunk qualifies for the tcgen05 path; the same
+    vectors through the exact kernel (reps_tensor = 0) and through the oracle's u16 lanes."""
+    n, L, dt, seed, B, mu = SANKOFF_BB_CASES[k]
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu, heavy=False)
+    cost = sankoff_bb_cost(dt, seed)
+    ninf = c["n_inf"]
+    o.set_cost_matrix(cost, seg)
+    try:
+        eng = _engine(c, boot, seg, tensor, cost=cost)
+        o.set_ring(c["bn"], c["bs"]); o.allocate(True)
+        s1 = o.evaluate_full(True)
+        order = eng.visit_order()
+        vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, 6)
+        calls = []
+        for v in range(2 * n - 2):
+            calls.append(-1); calls.extend(range(vb[v], vb[v + 1]))
+        got = eng.reps_candidates(np.array(calls, dtype=np.int32))
+        row = 0
+        for i in range(1, 2 * n - 1):
+            o.set_ring(c["bn"], c["bs"]); o.allocate(True); o.evaluate_full(True)
+            o.record(True)
+            o.rearrange(i, 1, 6, True, s1)
+            mps, ptn = o.saved(True)
+            for q in range(len(mps)):
+                assert np.array_equal(got[row], portlib.reps(ptn[q, :ninf], boot[:, :ninf], seg)), (i, q)
+                row += 1
+        assert row == len(calls)
+        t, e = eng.sankoff_reps_stats()
+        assert (t > 0 and e == 0) if tensor else (t == 0 and e > 0)
+        w = run_bb(o, c, boot, seg, 0.0, None, False, cost=cost)
+        r = _run_gpu_bb(c, boot, seg, 0.0, tensor, cost=cost)
+        assert r["ret"] == w["ret"] and r["draws"] == w["draws"]
+        assert all(np.array_equal(x, y) for x, y in zip(r["state"], w["state"]))
+        assert np.array_equal(r["treels"], w["treels"])
+    finally:
+        o.set_cost_matrix(None, None)
