@@ -315,6 +315,7 @@ def bench_cost(case, order, args, flush, stream, local):
         # -cost with -bb: every insertion's per-pattern cost vector (k_sk_scan<ROWS>) against B replicates (k_sk_reps, exact u16 weights)
         os.environ.setdefault("MPGPU_REPS_ROW_BYTES", str(6 << 30))
         boot = make_replicates(case, args.replicates)
+        eng.set_option("reps_timing", 1)
         eng.load_replicates(boot, seg)
         eng.set_tree(case["bn"], case["bs"])
         eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
@@ -330,10 +331,21 @@ def bench_cost(case, order, args, flush, stream, local):
         torch.cuda.synchronize()
         bb_s = e0.elapsed_time(e1) * 1e-3
         macs = float(len(np.unique(calls))) * L * args.replicates
-        out["bb"] = {"what": "the same sweep under -cost -bb, cutoff off: every insertion's pattern vector x %d replicates "
-                             "(exact CUDA-core contraction, u16 lanes with per-segment wrap)" % args.replicates,
+        tch, ech = eng.sankoff_reps_stats()
+        out["bb"] = {"what": "the same sweep under -cost -bb, cutoff off: every insertion's per-pattern cost vector x %d replicates "
+                             "(k_sk_scan<ROWS> + u8 pack + wrap proof + contraction)" % args.replicates,
                      "calls_per_step": int(len(calls)), "ms_per_step": bb_s * 1e3, "reps_vectors_per_s": len(calls) / bb_s,
-                     "mac_per_s": macs / bb_s}
+                     "mac_per_s": macs / bb_s, "chunks_on_tensor_cores": int(tch), "chunks_on_exact_kernel": int(ech)}
+        if tch:
+            tc_ms, rows, npat, splits = eng.reps_timing()
+            ops = 2.0 * rows * npat * args.replicates
+            peak_tc = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1650.0)) \
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 3300.0
+            out["bb"]["roofline"] = {"bound": "tensor", "kernel": "k_reps_tc<BYTES>", "achieved": ops / (tc_ms * 1e-3) / 1e12,
+                                     "peak": peak_tc, "unit": "TOP/s (int8, s32 accumulate)", "frac": ops / (tc_ms * 1e-3) / 1e12 / peak_tc,
+                                     "kernel_ms": tc_ms, "shape": "%d rows x %d patterns x %d replicates, K splits %d"
+                                                                  % (rows, npat, args.replicates, splits),
+                                     "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (no int8 figure is measured)"}
         if not args.no_cpu_baseline:
             use_ref = reflib.available()
             ref = (reflib.RefEngine(case["chars"], case["weights"], dt, n_informative=ninf) if use_ref

@@ -186,6 +186,7 @@ struct Sankoff {
     int32_t *d_X = nullptr; size_t X_cap = 0;              // [rows][Bpad]
     int32_t *d_row_of = nullptr; size_t row_of_cap = 0;    // [n_cand]
     int32_t *d_call_row = nullptr; size_t call_row_cap = 0;
+    uint32_t *d_stack = nullptr; size_t stack_cap = 0;     // S > 4: the scan kernel's per-warp stacks (resident warps only)
     uint8_t *d_rows8 = nullptr; size_t rows8_cap = 0;      // [rows][Kpad] the same rows as u8 (tensor path)
     uint32_t *d_colmax = nullptr; size_t colmax_cap = 0;   // [Lh] per-pattern maximum over the chunk's rows (u16x2) + [2] flags
     int64_t tensor_chunks = 0, exact_chunks = 0;           // statistics: which contraction the chunks took

@@ -305,19 +305,40 @@ __device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U
                                          bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
                                          const uint2 (&w)[V], const SkSeg &g)
 {
-    uint32_t U1[S * V], U1p[S * V];
+    // Large S (V = 1): the target state z is a rolled loop (2 per trip, two accumulators each) so that the body stays in the
+    // instruction cache (fully unrolled it is 2 x S*S instructions per child), the cost row of z comes from shared memory
+    // four entries per LDS.128, and U_c'[z] is consumed at once (stack store / minimum) instead of living in S more registers.
+    static_assert(V == 1, "pointer form is the large-S path");
+    (void)cm;
+    extern __shared__ uint32_t sk_smem[];                   // [0, S*S): cost[z][x] in both halfwords (k_sk_scan fills it)
+    uint32_t U1[S];
     sk_load<S, V>(px, U1);
 #pragma unroll
-    for (int x = 0; x < S * V; x++) U1[x] += U[x];
-    sk_minplus<S, V>(cm, U1, U1p);
-    if (do_dst) {
+    for (int x = 0; x < S; x++) U1[x] += U[x];
+    uint32_t best = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int z = 0; z < S; z += 2) {
+        const uint4 *c0 = reinterpret_cast<const uint4 *>(sk_smem + z * S), *c1 = reinterpret_cast<const uint4 *>(sk_smem + (z + 1) * S);
+        uint32_t a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
 #pragma unroll
-        for (int z = 0; z < S; z++) sk_stv<V>(dst + z * 32 * V, &U1p[z * V]);
+        for (int x = 0; x < S; x += 4) {
+            const uint4 p = c0[x >> 2], q = c1[x >> 2];
+            a0 = __viaddmin_u16x2(U1[x], p.x, a0);     a1 = __viaddmin_u16x2(U1[x + 1], p.y, a1);
+            a0 = __viaddmin_u16x2(U1[x + 2], p.z, a0); a1 = __viaddmin_u16x2(U1[x + 3], p.w, a1);
+            b0 = __viaddmin_u16x2(U1[x], q.x, b0);     b1 = __viaddmin_u16x2(U1[x + 1], q.y, b1);
+            b0 = __viaddmin_u16x2(U1[x + 2], q.z, b0); b1 = __viaddmin_u16x2(U1[x + 3], q.w, b1);
+        }
+        const uint32_t r0 = __vminu2(a0, a1), r1 = __vminu2(b0, b1);
+        if (do_dst) { dst[z * 32] = r0; dst[(z + 1) * 32] = r1; }
+        if (do_out) {
+            const uint32_t t0 = r0 + __ldg(pc + z * 32) + __ldg(ps + z * 32);
+            const uint32_t t1 = r1 + __ldg(pc + (z + 1) * 32) + __ldg(ps + (z + 1) * 32);
+            best = __vimin3_u16x2(best, t0, t1);
+        }
     }
     if (do_out) {
-        uint32_t best[V];
-        sk_best3<S, V>(U1p, pc, ps, best);
-        sk_emit<V, ROWS>(best, w, g, out_row);
+        uint32_t bv[V] = {best};
+        sk_emit<V, ROWS>(bv, w, g, out_row);
     }
 }
 
@@ -356,21 +377,30 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
                                                  int nslots, int cand_bias,
                                                  const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
                                                  uint32_t *__restrict__ segout,
-                                                 const int32_t *__restrict__ row_of, uint32_t *__restrict__ rows)
+                                                 const int32_t *__restrict__ row_of, uint32_t *__restrict__ rows,
+                                                 uint32_t *__restrict__ gstack)
 {
     constexpr int V = SkLay<S>::V;
     constexpr bool HOLD = S <= 4;         // child views and the pruned subtree's view live in registers; next op prefetched
+    // S > 4: a warp's stack (nslots * S * 128 B) would leave room for only a few warps per SM in shared memory, so the grid is
+    // persistent (resident CTAs only, each warp walks the work list) and the stacks live in an L2-resident global scratch.
     extern __shared__ uint32_t sk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    const unsigned wid = blockIdx.x * (blockDim.x >> 5) + warp, wstride = gridDim.x * (blockDim.x >> 5);
     const unsigned nchunks = Lh / (32 * V);
-    if (gw >= (unsigned)ntasks * nchunks) return;
+    const unsigned total = (unsigned)ntasks * nchunks;
+    uint32_t *stack = (gstack ? gstack + (size_t)wid * nslots * S * 32 * V : sk_smem + (size_t)warp * nslots * S * 32 * V) + lane * V;
+    SkCost<S> cm; cm.init();
+    if (!HOLD) {                            // large S: the cost matrix in shared memory (read by sk_child as LDS.128)
+        for (int i = threadIdx.x; i < S * S; i += blockDim.x) sk_smem[i] = c_cost2[i];
+        __syncthreads();
+    }
+    for (unsigned gw = wid; gw < total; gw += wstride) {
     const unsigned chunk = gw / (unsigned)ntasks, ti = gw - chunk * (unsigned)ntasks;
     const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
     const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
     const int i0 = chunk * 32 * V + lane * V;
     const uint32_t *vbase = reinterpret_cast<const uint32_t *>(views4) + (size_t)chunk * S * 32 * V + lane * V;
-    uint32_t *stack = sk_smem + (size_t)warp * nslots * S * 32 * V + lane * V;
     uint2 w[V];
 #pragma unroll
     for (int k = 0; k < V; k++) w[k] = __ldg(wts + i0 + k);
@@ -378,9 +408,8 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
     uint32_t *outc = segout + (size_t)(t1.z - cand_bias) * nseg;
     const int32_t *rowc = ROWS ? row_of + (t1.z - cand_bias) : nullptr;
     const uint32_t *ps = vbase + (size_t)(uint32_t)t0.x * 4;
-    SkCost<S> cm; cm.init();
     const int oe = t1.x;
-    if (t0.w >= oe) return;
+    if (t0.w >= oe) continue;
 
     uint32_t Sv[HOLD ? S * V : 1], A[HOLD ? S * V : 1], B[HOLD ? S * V : 1];
     int2 f = __ldg(offs + t0.w);
@@ -420,7 +449,7 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
         } else {
             sk_load<S, V>(vbase + (size_t)(uint32_t)(src == 0xff ? t0.z : t0.y) * 4, U);
         }
-        if (HOLD) {
+        if constexpr (HOLD) {
             if (o1 != 0xffff || dst1 != 0xff)
                 sk_child_r<S, V, ROWS>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(B), reinterpret_cast<uint32_t (&)[S * V]>(A),
                                  reinterpret_cast<uint32_t (&)[S * V]>(Sv), o1 != 0xffff, out1, dst1 != 0xff,
@@ -441,6 +470,8 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
                 sk_child<S, V, ROWS>(cm, U, pa, pb, ps, o2 != 0xffff, out2, dst2 != 0xff, stack + (size_t)dst2 * S * 32 * V,
                                w, g);
         }
+    }
+    if (gstack) __syncwarp();              // the next work item reuses the stack
     }
 }
 
@@ -601,6 +632,8 @@ void sk_free(Ctx *c)
     if (k.d_X) cudaFree(k.d_X);
     if (k.d_row_of) cudaFree(k.d_row_of);
     if (k.d_call_row) cudaFree(k.d_call_row);
+    if (k.d_stack) cudaFree(k.d_stack);
+    k.d_stack = nullptr; k.stack_cap = 0;
     if (k.d_rows8) cudaFree(k.d_rows8);
     if (k.d_colmax) cudaFree(k.d_colmax);
     k.d_rows8 = nullptr; k.d_colmax = nullptr; k.rows8_cap = k.colmax_cap = 0;
@@ -862,6 +895,33 @@ int sk_raw_view(Ctx *c, int ref, uint16_t *out)
     return 0;
 }
 
+// launch geometry of k_sk_scan.  S <= 4: one warp per (task, chunk), stacks in shared memory.  S > 4: persistent grid of
+// resident CTAs (4 warps each), stacks in the global scratch d_stack (resident warps x per_warp bytes: L2-resident).
+static int sk_scan_geometry(Ctx *c, int ntasks, size_t per_warp, bool rows, int *wpb, size_t *smem, long long *blocks)
+{
+    Sankoff &k = c->sk;
+    const int V = sk_vpl(c->S);
+    const long long warps = (long long)ntasks * (k.Lh / (32 * V));
+    if (c->S <= 4) {
+        int w = 4;
+        while (w > 1 && per_warp * w > 96 * 1024) w >>= 1;
+        *wpb = w; *smem = per_warp * w;
+        if (*smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
+        *blocks = (warps + w - 1) / w;
+        if (*blocks > 0x7fffffffLL) { set_error("scan grid too large"); return 1; }
+        return 0;
+    }
+    static int sms = 0;
+    if (!sms) { cudaDeviceProp prop; MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device)); sms = prop.multiProcessorCount; }
+    // register-limited residency: 85 / 127 registers per thread (S = 20 / 32), 101 / 138 for the ROWS variant
+    const int per_sm = c->S <= 20 ? (rows ? 4 : 5) : (rows ? 3 : 4);
+    long long b = (long long)sms * per_sm;
+    if (b * 4 > warps) b = (warps + 3) / 4;
+    *wpb = 4; *smem = (size_t)c->S * c->S * sizeof(uint32_t); *blocks = b > 0 ? b : 1;      // shared memory: the cost matrix only
+    if (int rc = ensure(k.d_stack, k.stack_cap, (size_t)(*blocks) * 4 * per_warp / sizeof(uint32_t))) return rc;
+    return 0;
+}
+
 // scan: the whole plan in one launch, per-(candidate, segment) sums, then totals and bounds
 int sk_run_scan(Ctx *c)
 {
@@ -877,12 +937,9 @@ int sk_run_scan(Ctx *c)
     const int V = sk_vpl(c->S);
     const size_t per_warp = (size_t)nslots * c->S * 32 * V * sizeof(uint32_t);
     int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-    const size_t smem = per_warp * wpb;
-    if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
-    const long long warps = (long long)ntasks * (k.Lh / (32 * V));
-    const long long blocks = (warps + wpb - 1) / wpb;
-    if (blocks > 0x7fffffffLL) { set_error("scan grid too large"); return 1; }
+    size_t smem = 0;
+    long long blocks = 0;
+    if (int rc = sk_scan_geometry(c, ntasks, per_warp, false, &wpb, &smem, &blocks)) return rc;
 #define SK_SCAN_LAUNCH                                                                                                         \
     {                                                                                                                          \
         static size_t configured = 0;                                                                                          \
@@ -892,7 +949,7 @@ int sk_run_scan(Ctx *c)
         }                                                                                                                      \
         k_sk_scan<S_, false><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
             c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
-            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, nullptr, nullptr);                                                \
+            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, nullptr, nullptr, c->S > 4 ? k.d_stack : nullptr);                \
     }
     SK_DISPATCH(SK_SCAN_LAUNCH);
 #undef SK_SCAN_LAUNCH
@@ -968,10 +1025,9 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
         const int V = sk_vpl(c->S);
         const size_t per_warp = (size_t)nslots * c->S * 32 * V * sizeof(uint32_t);
         int wpb = 4;
-        while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-        const size_t smem = per_warp * wpb;
-        const long long warps = (long long)ntasks * (k.Lh / (32 * V));
-        const long long blocks = (warps + wpb - 1) / wpb;
+        size_t smem = 0;
+        long long blocks = 0;
+        if (int rc = sk_scan_geometry(c, ntasks, per_warp, true, &wpb, &smem, &blocks)) return rc;
 #define SK_ROWS_LAUNCH                                                                                                         \
     {                                                                                                                          \
         static size_t configured = 0;                                                                                          \
@@ -981,7 +1037,7 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
         }                                                                                                                      \
         k_sk_scan<S_, true><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
             c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
-            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, k.d_row_of, k.d_rows + k.Lh);                                     \
+            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, k.d_row_of, k.d_rows + k.Lh, c->S > 4 ? k.d_stack : nullptr);     \
     }
         SK_DISPATCH(SK_ROWS_LAUNCH);
 #undef SK_ROWS_LAUNCH
