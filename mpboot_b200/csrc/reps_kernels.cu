@@ -339,11 +339,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 // 4 bits -> 4 bytes of 0/1 (bit j -> byte j)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-// BYTES: the A operand is already u8, K-major, [row][a_pitch bytes] (per-pattern Sankoff costs, -cost with -bb):
-// thread r copies the 128 bytes of its row into the swizzled tile instead of expanding 128 bits.
+// BYTES: the A operand is already u8, K-major, [row][Kpad] (per-pattern Sankoff costs, -cost with -bb): the TMA warp
+// loads its 128 x 128 tile through tmap_a next to the weights (one more cp.async.bulk.tensor per stage, rows beyond
+// nrows zero-filled) and warps 0-3 only run the epilogue.
 template <bool BYTES>
 __global__ void __launch_bounds__(THREADS, 1)
-k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restrict__ rows_a, int a_pitch, int a_kb0,
+k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ CUtensorMap tmap_a,
+          const uint32_t *__restrict__ rows_a, int a_pitch, int a_kb0,
           int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -364,7 +366,7 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
     if (nkb <= 0) return;                                                  // uniform over the CTA
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), BYTES ? 1 : 5); mbar_init(empty_bar(s), 1); }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -382,30 +384,7 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
         // ---- A producers: thread r owns tile row r ----
         const int r = threadIdx.x;
         const bool live = (m0 + r) < nrows;
-        if (BYTES) {
-            const uint4 *src8 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(rows_a) + (size_t)(m0 + r) * a_pitch);
-            const uint32_t sw8 = (uint32_t)(r & 7);
-            uint4 cur[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) cur[q] = live ? __ldg(src8 + (size_t)kb_begin * 8 + q) : make_uint4(0, 0, 0, 0);
-            for (int it = 0; it < nkb; it++) {
-                const int s = it % STAGES;
-                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                uint4 nxt[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    nxt[q] = (live && it + 1 < nkb) ? __ldg(src8 + (size_t)(kb_begin + it + 1) * 8 + q) : make_uint4(0, 0, 0, 0);
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                uint8_t *arow = smem_gen + (size_t)s * STAGE_BYTES + (size_t)r * 128;
-#pragma unroll
-                for (int q = 0; q < 8; q++) *reinterpret_cast<uint4 *>(arow + ((q ^ sw8) << 4)) = cur[q];
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(s));
-#pragma unroll
-                for (int q = 0; q < 8; q++) cur[q] = nxt[q];
-            }
-        } else {
+        if (!BYTES) {
         const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch) - a_kb0;   // row starts at K-block a_kb0
         const uint32_t sw = (uint32_t)(r & 7);
         // the 128 bits of K-block it+PF are requested while K-block it is expanded: the L2 latency of
@@ -449,7 +428,8 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const uint32_t *__restric
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), B_BYTES);
+                mbar_arrive_expect_tx(full_bar(s), BYTES ? STAGE_BYTES : B_BYTES);
+                if (BYTES) tma_load_2d(base + s * STAGE_BYTES, &tmap_a, (kb_begin + it) * KB, m0, full_bar(s));
                 tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmap_w8, (kb_begin + it) * KB, n0, full_bar(s));
             }
         }
@@ -518,9 +498,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_w8_tensor_map(Ctx *c)
+static int get_encode(EncodeTiledFn *out)
 {
-    Reps &r = c->reps;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -529,6 +508,15 @@ int make_w8_tensor_map(Ctx *c)
         if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return 1; }
         encode = (EncodeTiledFn)fn;
     }
+    *out = encode;
+    return 0;
+}
+
+int make_w8_tensor_map(Ctx *c)
+{
+    Reps &r = c->reps;
+    EncodeTiledFn encode = nullptr;
+    if (int rc = get_encode(&encode)) return rc;
     static_assert(sizeof(CUtensorMap) <= sizeof(r.tmap_w8), "tensor map storage too small");
     const cuuint64_t dims[2] = {(cuuint64_t)r.Kpad, (cuuint64_t)r.Bpad};
     const cuuint64_t strides[1] = {(cuuint64_t)r.Kpad};                   // bytes between replicate rows
@@ -580,7 +568,8 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int
         if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
         MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
     }
-    tc::k_reps_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
+    tc::k_reps_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
+                                                                           *reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
                                                                            x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
     if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
     c->launches++;
@@ -620,7 +609,21 @@ int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrow
         if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
         MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
     }
+    alignas(64) unsigned char tmap_a[128];
+    {
+        EncodeTiledFn encode = nullptr;
+        if (int rc = get_encode(&encode)) return rc;
+        const cuuint64_t dims[2] = {(cuuint64_t)pitch_bytes, (cuuint64_t)nrows};
+        const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+        const cuuint32_t box[2] = {(cuuint32_t)tc::KB, (cuuint32_t)tc::M};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult res = encode(reinterpret_cast<CUtensorMap *>(tmap_a), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)rows8, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (res != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed for the cost rows"); return 1; }
+    }
     tc::k_reps_tc<true><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
+                                                                          *reinterpret_cast<const CUtensorMap *>(tmap_a),
                                                                           reinterpret_cast<const uint32_t *>(rows8), pitch_bytes, 0,
                                                                           0, nrows, 0, nkb, per, r.B, x_pitch, X);
     if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
