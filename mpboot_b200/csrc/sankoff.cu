@@ -395,7 +395,9 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
         for (int i = threadIdx.x; i < S * S; i += blockDim.x) sk_smem[i] = c_cost2[i];
         __syncthreads();
     }
-    for (unsigned gw = wid; gw < total; gw += wstride) {
+    unsigned gw = wid;
+    if (gw >= total) return;
+    do {                                    // one trip for S <= 4 (the grid covers the work list), a strided walk otherwise
     const unsigned chunk = gw / (unsigned)ntasks, ti = gw - chunk * (unsigned)ntasks;
     const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
     const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
@@ -471,8 +473,8 @@ __global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views
                                w, g);
         }
     }
-    if (gstack) __syncwarp();              // the next work item reuses the stack
-    }
+    if (!HOLD) __syncwarp();               // the next work item reuses the stack
+    } while (!HOLD && (gw += wstride) < total);
 }
 
 // ---- per row: total = sum_seg (sum mod 2^16) (:944-948), est = max_{seg < nseg-1} (prefix + lb[seg]) (:951-956) ----
@@ -895,6 +897,16 @@ int sk_raw_view(Ctx *c, int ref, uint16_t *out)
     return 0;
 }
 
+// resident CTAs of 128 threads per SM for the instantiation the launch will use (register-limited for S > 4)
+static int sk_scan_occupancy(Ctx *c, bool rows, size_t smem, int *per_sm)
+{
+    int occ = 0;
+    if (rows) { SK_DISPATCH(MPGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sk_scan<S_, true>, 128, smem))); }
+    else { SK_DISPATCH(MPGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sk_scan<S_, false>, 128, smem))); }
+    *per_sm = occ > 0 ? occ : 1;
+    return 0;
+}
+
 // launch geometry of k_sk_scan.  S <= 4: one warp per (task, chunk), stacks in shared memory.  S > 4: persistent grid of
 // resident CTAs (4 warps each), stacks in the global scratch d_stack (resident warps x per_warp bytes: L2-resident).
 static int sk_scan_geometry(Ctx *c, int ntasks, size_t per_warp, bool rows, int *wpb, size_t *smem, long long *blocks)
@@ -913,8 +925,8 @@ static int sk_scan_geometry(Ctx *c, int ntasks, size_t per_warp, bool rows, int 
     }
     static int sms = 0;
     if (!sms) { cudaDeviceProp prop; MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device)); sms = prop.multiProcessorCount; }
-    // register-limited residency: 85 / 127 registers per thread (S = 20 / 32), 101 / 138 for the ROWS variant
-    const int per_sm = c->S <= 20 ? (rows ? 4 : 5) : (rows ? 3 : 4);
+    int per_sm = 1;
+    if (int rc = sk_scan_occupancy(c, rows, (size_t)c->S * c->S * sizeof(uint32_t), &per_sm)) return rc;
     long long b = (long long)sms * per_sm;
     if (b * 4 > warps) b = (warps + 3) / 4;
     *wpb = 4; *smem = (size_t)c->S * c->S * sizeof(uint32_t); *blocks = b > 0 ? b : 1;      // shared memory: the cost matrix only

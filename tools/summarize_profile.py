@@ -12,8 +12,9 @@ tag = sys.argv[1]
 go = os.path.join(ROOT, "gpurun_out")
 out = []
 
-lp = os.path.join(go, "launches_%s.csv" % tag)
-if os.path.exists(lp):
+def launch_list(lp, command):
+    if not os.path.exists(lp):
+        return
     rows = [r for r in csv.reader(l for l in open(lp) if not l.startswith("=="))]
     hdr = rows[0]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -23,9 +24,14 @@ if os.path.exists(lp):
             d[r[ki].split("(")[0][-70:]].append(float(r[vi].replace(",", "")))
     tot = sum(sum(v) for v in d.values())
     out.append("== ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised) ==")
-    out.append("command: python bench.py --steps 3 --warmup 3 --no-cpu-baseline")
+    out.append("command: " + command)
     for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         out.append("%-72s n=%3d avg=%9.2f us total=%9.3f ms share=%5.1f%%" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e6, 100 * sum(v) / tot))
+    out.append("")
+
+
+launch_list(os.path.join(go, "launches_%s.csv" % tag), "python bench.py --steps 3 --warmup 3 --no-cpu-baseline   (first 800 launches: timed sweeps + whole-search section)")
+launch_list(os.path.join(go, "launches2_%s.csv" % tag), "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-search   (first 400 launches: timed sweeps, -bb and -cost sections)")
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -70,8 +76,9 @@ def full_capture(rep, title):
 
 full_capture(os.path.join(go, "prof_scan_%s.ncu-rep" % tag), "kernel k_spr_scan")
 full_capture(os.path.join(go, "prof_reps_%s.ncu-rep" % tag), "kernel k_reps_tc (tcgen05 kind::i8 replicate contraction)")
+full_capture(os.path.join(go, "prof_sk_%s.ncu-rep" % tag), "kernel k_sk_scan (-cost: Sankoff insertion scoring, DPX min-plus)")
 
-for name in ("bench_%s.json" % tag, "bench_ref_%s.json" % tag):
+for name in ("bench_%s.json" % tag, "bench_ref_%s.json" % tag, "cost_c3_%s.json" % tag, "cost_c5_%s.json" % tag):
     bp = os.path.join(go, name)
     if os.path.exists(bp):
         out.append("")
