@@ -214,8 +214,9 @@ int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
  * integers, including the per-segment 16-bit wrap of the weighted sums (:944-948).
  * Preconditions checked here (error otherwise, there is no fallback): the matrix is symmetric and
  * (ntaxa+1)*(max cost+1) <= 65535 -- then no u16 of the reference wraps inside a vector and the score
- * does not depend on the orientation the reference happens to hold.  Sharded contexts and the -bb
- * replicate contraction are not available under -cost. */
+ * does not depend on the orientation the reference happens to hold.  Sharded contexts: install
+ * mpgpu_set_allreduce first (the shards hold ranges of pattern pairs; per-segment sums are reduced before the
+ * 16-bit masks).  -cost with -bb: see mpgpu_sankoff_reps_stats below (unsharded contexts only). */
 int mpgpu_set_cost_matrix(mpgpu_ctx *ctx, const uint32_t *cost, int nstates, const int32_t *segment_upper, int nseg,
                           uint32_t *highest_cost);
 /* vector_length = the reference's per-node vector length in patterns (informative patterns padded to 16,

@@ -169,7 +169,8 @@ struct Sankoff {
     std::vector<int32_t> seg_upper; int nseg = 0;
     std::vector<uint32_t> lb;             // pllRemainderLowerBounds [nseg-1]
     int Lref = 0;                         // the reference's vector length (informative patterns padded to 16)
-    int Lp = 0, Lh = 0;                   // device patterns per state row (padded to 64) and 32-bit words (pattern pairs)
+    int Lp = 0, Lh = 0;                   // this shard's patterns per state row (whole chunks) and 32-bit words (pattern pairs)
+    int Lp_glob = 0, pair0 = 0;           // patterns over all shards; first pattern pair of this shard
     size_t vstride = 0;                   // 32-bit words per view: S * Lh
     uint32_t *d_views = nullptr; size_t views_cap = 0;     // [4n-6][S][Lh] transformed cost vectors, u16x2
     uint2 *d_w = nullptr;                 // [Lh] weights of the pair's two patterns

@@ -174,14 +174,15 @@ template <int S>
 __global__ void __launch_bounds__(128) k_sk_tips(const uint8_t *__restrict__ codes, int P, int ntaxa,
                                                  const int32_t *__restrict__ inf_ptn, int n_inf,
                                                  const uint32_t *__restrict__ mask_table, uint32_t highest,
-                                                 uint32_t *__restrict__ views, size_t vstride, int Lh)
+                                                 uint32_t *__restrict__ views, size_t vstride, int Lh, int pair0)
 {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)ntaxa * Lh) return;
     const int tip = (int)(gid / Lh), i = (int)(gid % Lh);
+    const int64_t gp = 2 * ((int64_t)pair0 + i);           // first pattern of the pair, over all shards
     uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
-    if (2 * i < n_inf) m0 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i]]];
-    if (2 * i + 1 < n_inf) m1 = mask_table[codes[(size_t)tip * P + inf_ptn[2 * i + 1]]];
+    if (gp < n_inf) m0 = mask_table[codes[(size_t)tip * P + inf_ptn[gp]]];
+    if (gp + 1 < n_inf) m1 = mask_table[codes[(size_t)tip * P + inf_ptn[gp + 1]]];
     SkCost<S> cm; cm.init();
     uint32_t v[S], o[S];
 #pragma unroll
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(128) k_sk_level(uint32_t *views, size_t vstrid
     uint32_t contrib = 0;
 #pragma unroll
     for (int k = 0; k < V; k++)
-        if (chunk * 32 * V + lane * V + k < Lref_pairs) contrib += (mn[k] & 0xFFFFu) + (mn[k] >> 16);
+        if (chunk * 32 * V + lane * V + k < Lref_pairs) contrib += (mn[k] & 0xFFFFu) + (mn[k] >> 16);   // Lref_pairs: local
     const uint32_t r = __reduce_add_sync(0xffffffffu, contrib);
     if (lane == 0 && r) atomicAdd(compact ? compact + ti : vscore + tr.dst, r);
 }
@@ -673,7 +674,8 @@ int sk_build(Ctx *c)
 {
     Sankoff &k = c->sk;
     const int S = c->S, n = c->n, ninf = c->n_inf;
-    if (c->shard_count != 1) { set_error("-cost (Sankoff) runs on unsharded contexts only"); return 1; }
+    const int G = c->shard_count;
+    if (G > 1 && !c->allreduce) { set_error("-cost on a sharded context needs mpgpu_set_allreduce (install it before mpgpu_set_cost_matrix)"); return 1; }
     if ((int64_t)(n + 1) * k.highest > 65535) {
         set_error("cost matrix too large for this many taxa: (ntaxa+1)*(max cost+1) must stay below 65536 (a u16 of the reference could wrap)");
         return 1;
@@ -684,8 +686,12 @@ int sk_build(Ctx *c)
             set_error("segment_upper: interior bounds must be increasing multiples of 16 (iqtree.cpp:3804)"); return 1;
         }
     k.Lref = ninf % 16 ? ninf + 16 - ninf % 16 : ninf;
-    k.Lp = std::max(256, (ninf + 255) / 256 * 256);      // whole chunks for every lane width
+    // pattern sharding: shard r holds the pattern pairs [r * Lh, (r + 1) * Lh) of every view (whole chunks for every lane width)
+    const int quantum = 256 * G;
+    k.Lp_glob = std::max(quantum, (ninf + quantum - 1) / quantum * quantum);
+    k.Lp = k.Lp_glob / G;
     k.Lh = k.Lp / 2;
+    k.pair0 = c->shard_rank * k.Lh;
     k.vstride = (size_t)S * k.Lh;
     const size_t nviews = (size_t)(4 * n - 6);
     if ((nviews * k.vstride) / 4 > 0xFFFFFFFFull) { set_error("alignment too large for 32-bit view offsets"); return 1; }
@@ -713,7 +719,9 @@ int sk_build(Ctx *c)
         int s = 0;
         for (j = 0; j < ninf; j++) {
             while (s + 1 < k.nseg && j >= k.seg_upper[s]) s++;
-            if (j & 1) w[j / 2].y = wflat[j]; else { w[j / 2].x = wflat[j]; seg[j / 2] = s; }
+            const int lp = j / 2 - k.pair0;                  // local pair
+            if (lp < 0 || lp >= k.Lh) continue;
+            if (j & 1) w[lp].y = wflat[j]; else { w[lp].x = wflat[j]; seg[lp] = s; }
         }
     }
     // remainder lower bounds (:2801-2823): for seg < nseg-1, sum over ptn >= segment_upper[seg] of mst(ptn) * weight(ptn)
@@ -741,7 +749,7 @@ int sk_build(Ctx *c)
     const int64_t total = (int64_t)n * k.Lh;
     const int blocks = (int)((total + 127) / 128);
     SK_DISPATCH((k_sk_tips<S_><<<blocks, 128, 0, c->stream>>>(c->d_codes, c->P, n, c->d_inf_ptn, ninf, k.d_mask, k.highest,
-                                                              k.d_views, k.vstride, k.Lh)));
+                                                              k.d_views, k.vstride, k.Lh, k.pair0)));
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -755,7 +763,8 @@ static int sk_launch_level(Ctx *c, const Triple *d_triples, int ntriples, uint32
     if (int rc = bind_cost(c)) return rc;
     const int64_t warps = (int64_t)ntriples * (k.Lh / (32 * sk_vpl(c->S)));
     const int blocks = (int)((warps + 3) / 4);
-    SK_DISPATCH((k_sk_level<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.Lref / 2, d_triples, ntriples,
+    const int lref_local = std::max(0, std::min(k.Lh, k.Lref / 2 - k.pair0));
+    SK_DISPATCH((k_sk_level<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, lref_local, d_triples, ntriples,
                                                                c->d_vcount, d_compact)));
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
@@ -789,6 +798,7 @@ int sk_update_stale(Ctx *c, std::vector<Triple> &stale, int nlevels)
     MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, total * sizeof(uint32_t), c->stream));
     for (int l = 1; l <= nlevels; l++)
         if (int rc = sk_launch_level(c, c->d_wave + start[l], start[l + 1] - start[l], c->d_wcount + start[l])) return rc;
+    if (int rc = shard_sum(c, c->d_wcount, (int64_t)total)) return rc;
     MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < total; i++) c->vcount[dst[i].dst] = c->wcount_pin.data()[i];
@@ -831,16 +841,24 @@ int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn)
     if (int rc = bind_cost(c)) return rc;
     if (int rc = sk_ensure_out(c, (size_t)count)) return rc;
     if (int rc = ensure(k.d_list, k.list_cap, (size_t)count)) return rc;
-    if (ptn) { if (int rc = ensure(k.d_tmp, k.tmp_cap, (size_t)k.Lh)) return rc; }
+    const size_t Lh_glob = (size_t)k.Lp_glob / 2;
+    if (ptn) {                                              // every shard fills its slice of a zeroed full-length vector
+        if (int rc = ensure(k.d_tmp, k.tmp_cap, Lh_glob)) return rc;
+        if (c->shard_count > 1) MPGPU_CUDA(cudaMemsetAsync(k.d_tmp, 0, Lh_glob * sizeof(uint32_t), c->stream));
+    }
     MPGPU_CUDA(cudaMemcpyAsync(k.d_list, list, (size_t)count * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
     MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)count * k.nseg * sizeof(uint32_t), c->stream));
     const int64_t warps = (int64_t)count * (k.Lh / (32 * sk_vpl(c->S)));
     const int blocks = (int)((warps + 3) / 4);
     SK_DISPATCH((k_sk_junction<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, count, k.d_w, k.d_seg, k.nseg,
-                                                                  k.d_segout, ptn ? k.d_tmp : nullptr)));
+                                                                  k.d_segout, ptn ? k.d_tmp + k.pair0 : nullptr)));
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
-    if (ptn) MPGPU_CUDA(cudaMemcpyAsync(ptn, k.d_tmp, (size_t)k.Lh * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = shard_sum(c, k.d_segout, (int64_t)count * k.nseg)) return rc;      // exact sums mod 2^32 add up across shards
+    if (ptn) {
+        if (int rc = shard_sum(c, k.d_tmp, (int64_t)Lh_glob)) return rc;             // one shard is non-zero per word
+        MPGPU_CUDA(cudaMemcpyAsync(ptn, k.d_tmp, Lh_glob * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
     return sk_finish_rows(c, count);      // synchronizes: `list` may be a host temporary
 }
 
@@ -863,16 +881,16 @@ int sk_tree_score(Ctx *c, int start_ref, uint32_t *score)
 int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum)
 {
     Sankoff &k = c->sk;
-    std::vector<uint16_t> tmp((size_t)k.Lp);
+    std::vector<uint16_t> tmp((size_t)k.Lp_glob);
     const int4 j = start_junction(c->tree);
     if (int rc = sk_junctions(c, &j, 1, tmp.data())) return rc;
     int s = 0, jj = 0;
-    for (int i = 0; i < c->P && jj < k.Lp; i++) {
+    for (int i = 0; i < c->P && jj < k.Lp_glob; i++) {
         if (!c->informative[i]) continue;
         s += (int)tmp[jj] * (int)(uint16_t)c->weights[i];
         jj++;
     }
-    for (int i = 0; i < count; i++) ptn_pars[i] = i < k.Lp ? tmp[i] : 0;
+    for (int i = 0; i < count; i++) ptn_pars[i] = i < k.Lp_glob ? tmp[i] : 0;
     if (sum) *sum = s;
     return 0;
 }
@@ -880,6 +898,7 @@ int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum)
 int sk_raw_view(Ctx *c, int ref, uint16_t *out)
 {
     Sankoff &k = c->sk;
+    if (c->shard_count != 1) { set_error("vector read-back is single-shard only"); return 1; }
     const HostTree &t = c->tree;
     if (int rc = ensure(k.d_tmp, k.tmp_cap, k.vstride)) return rc;
     const int blocks = (k.Lh + 127) / 128;
@@ -967,6 +986,7 @@ int sk_run_scan(Ctx *c)
 #undef SK_SCAN_LAUNCH
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
+    if (int rc = shard_sum(c, k.d_segout, (int64_t)rows * k.nseg)) return rc;
     return 0;
 }
 
@@ -1006,6 +1026,7 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
     Reps &r = c->reps;
     ScanPlan &pl = c->plan;
     const int nrows = 1 + nsel;
+    if (c->shard_count != 1) { set_error("-cost with -bb runs on unsharded contexts only (a segment's 16-bit sum is not additive over shards)"); return 1; }
     if (int rc = bind_cost(c)) return rc;
     if (int rc = ensure(k.d_rows, k.rows_cap, (size_t)nrows * k.Lh)) return rc;
     if (int rc = ensure(k.d_X, k.X_cap, (size_t)nrows * r.Bpad)) return rc;

@@ -79,6 +79,43 @@ def main():
         u = bb_run(one, c, boot, seg, 5); v = bb_run(sh, c, boot, seg, 5)
         for k in range(len(u)):
             assert np.array_equal(np.asarray(u[k]), np.asarray(v[k])), "bb result %d differs" % k
+        # -cost (Sankoff): fresh contexts (the cost matrix goes in before any replicates); scores, node scores, pattern vector,
+        # every insertion score with its early-exit bound, whole searches in both modes, RAS
+        S = one.S
+        rng = np.random.default_rng(seed)
+        cost = rng.integers(1, 5, size=(S, S)); cost = np.minimum(cost, cost.T); np.fill_diagonal(cost, 0)
+        cseg = np.array([x for x in range(160, ninf, 160)] + [ninf], dtype=np.int32)
+        one2 = engine.Engine(device=local, stream=st.cuda_stream)
+        sh2 = sharded.sharded_engine(local, stream=st.cuda_stream)
+        for e in (one2, sh2):
+            e.load_alignment(c["codes"], c["weights"], dt)
+            e.set_cost_matrix(cost, cseg)
+            e.set_tree(c["bn"], c["bs"])
+        cs1, cs2 = one2.tree_score(), sh2.tree_score()
+        assert cs1 == cs2, (cs1, cs2)
+        assert np.array_equal(one2.sankoff_layout()[1], sh2.sankoff_layout()[1])
+        for node in (n + 1, 2 * n - 2):
+            for slot in range(3):
+                assert one2.view_length(node, slot) == sh2.view_length(node, slot)
+        p1c, q1c = one2.pattern_parsimony(); p2c, q2c = sh2.pattern_parsimony()
+        assert q1c == q2c and np.array_equal(p1c[:ninf], p2c[:ninf])
+        ac = one2.scan_visits(order, 1, 2 * n - 2, 1, 6); bc_ = sh2.scan_visits(order, 1, 2 * n - 2, 1, 6)
+        assert all(np.array_equal(x, y) for x, y in zip(ac, bc_))
+        assert np.array_equal(one2.scan_bounds(len(ac[1])), sh2.scan_bounds(len(ac[1])))
+        for exact in (0, 1):
+            one2.set_option("sankoff_exact", exact); sh2.set_option("sankoff_exact", exact)
+            r1 = engine.HostRng(91); r2 = engine.HostRng(91)
+            x = one2.optimize_spr(c["bn"], c["bs"], r1.fn, 1, 6, rng_user=r1.user)
+            y = sh2.optimize_spr(c["bn"], c["bs"], r2.fn, 1, 6, rng_user=r2.user)
+            assert x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2]) and x[3] == y[3]
+            assert r1.state.value == r2.state.value
+        one2.set_option("sankoff_exact", 0); sh2.set_option("sankoff_exact", 0)
+        r1 = engine.HostRng(92); r2 = engine.HostRng(92)
+        x = one2.stepwise_addition(4242, 5, r1.fn, rng_user=r1.user); y = sh2.stepwise_addition(4242, 5, r2.fn, rng_user=r2.user)
+        assert x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2]) and r1.state.value == r2.state.value
+        one2.close(); sh2.close()
+        if rank == 0:
+            print("   -cost: sharded x%d == unsharded (score %d, %d insertions, searches in both modes, RAS score %d)" % (world, cs1, len(ac[1]), x[0]), flush=True)
         if rank == 0:
             print("case n=%d L=%d dt=%d identity=%s: sharded x%d == unsharded (score %d, %d insertions, %d all-reduces, %d int32)"
                   % (n, L, dt, not compress, world, s1, len(a[1]), sh.allreduce_stats["calls"], sh.allreduce_stats["elements"]), flush=True)
