@@ -39,6 +39,8 @@ static const Ctx *g_cost_owner[64];
 static int bind_cost(Ctx *c)
 {
     if (c->device >= 0 && c->device < 64 && g_cost_owner[c->device] == c && !c->sk.cost_dirty) return 0;
+    if (c->device >= 0 && c->device < 64 && g_cost_owner[c->device] && g_cost_owner[c->device] != c)
+        cudaStreamSynchronize(g_cost_owner[c->device]->stream);     // another context's kernels may still read the constant bank
     uint32_t tmp[kMaxStates * kMaxStates];
     memset(tmp, 0, sizeof tmp);
     for (int i = 0; i < c->S * c->S; i++) tmp[i] = c->sk.cost[i] | c->sk.cost[i] << 16;

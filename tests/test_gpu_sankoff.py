@@ -192,3 +192,71 @@ def test_preconditions_fail_loudly():
         eng.set_cost_matrix((6000 * (1 - np.eye(4))).astype(np.uint32), seg)
     with pytest.raises(MpGpuError, match="segment_upper"):
         eng.set_cost_matrix((1 - np.eye(4)).astype(np.uint32), np.array([c["n_inf"] - 1], dtype=np.int32))
+
+
+@pytest.mark.parametrize("n,L,dt,seed", [(4, 60, 1, 71), (5, 40, 1, 72), (7, 90, 0, 73), (9, 30, 2, 74)])
+def test_small_and_ragged_inputs(n, L, dt, seed):
+    """Minimum taxon counts, fewer informative patterns than one 16-lane vector, a single segment."""
+    from mpboot_b200.engine import Engine
+    c = make_case(n, L, dt, seed, mu=0.3)
+    if c["n_inf"] == 0:
+        pytest.skip("no informative pattern in this draw")
+    S = {0: 2, 1: 4, 2: 20, 6: 32}[dt]
+    rng = np.random.default_rng(seed)
+    cost = rng.integers(1, 7, size=(S, S)); cost = np.minimum(cost, cost.T); np.fill_diagonal(cost, 0)
+    seg = np.array([c["n_inf"]], dtype=np.int32)
+    ora = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    ora.set_cost_matrix(cost.astype(np.uint32), seg)
+    ora.set_ring(c["bn"], c["bs"])
+    eng = Engine()
+    eng.load_alignment(c["codes"], c["weights"], dt)
+    eng.set_cost_matrix(cost, seg)
+    eng.set_tree(c["bn"], c["bs"])
+    ora.allocate(per_site=True)
+    s0 = ora.evaluate_full(per_site=True)
+    assert eng.tree_score() == s0
+    order = eng.visit_order()
+    mt = 3
+    vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, mt)
+    for i in range(1, 2 * n - 1):
+        ora.record(False)
+        ora.rearrange(i, 1, mt, True, s0)
+        assert np.array_equal(ora.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32)), i
+    portlib.seed_rng(3)
+    ora.set_ring(c["bn"], c["bs"]); ora.allocate(False)
+    want = ora.optimize_spr(1, mt, bb=False); wd = portlib.rng_draws(); wbn, wbs = ora.get_ring()
+    portlib.seed_rng(3)
+    ret, bn, bs, _ = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, mt)
+    assert ret == want and portlib.rng_draws() == wd and np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+
+
+def test_reweighting_under_cost():
+    """Ratchet / bootstrap re-weighting (mpgpu_set_weights) with a cost matrix set: zero weights, weights above 255, the
+    16-bit truncation of informativePtnWgt (:2755) and segment sums that wrap."""
+    from mpboot_b200.engine import Engine
+    n, dt = 26, 1
+    c = make_case(n, 900, dt, 81)
+    ninf = c["n_inf"]
+    cost = np.array([[0, 3, 1, 3], [3, 0, 3, 1], [1, 3, 0, 3], [3, 1, 3, 0]], dtype=np.uint32)
+    seg = np.array([s for s in range(64, ninf, 64)] + [ninf], dtype=np.int32)
+    rng = np.random.default_rng(5)
+    w2 = c["weights"].copy()
+    w2[:ninf] = rng.integers(0, 4, size=ninf)
+    w2[3] = 300; w2[10] = 9000; w2[11] = 70000        # a segment sum that wraps; a weight that loses its high bits as u16
+    ora = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    ora.set_cost_matrix(cost, seg)
+    eng = Engine()
+    eng.load_alignment(c["codes"], c["weights"], dt)
+    eng.set_cost_matrix(cost, seg)
+    eng.set_tree(c["bn"], c["bs"])
+    for w in (w2, c["weights"]):
+        ora.set_weights(w); ora.set_ring(c["bn"], c["bs"]); ora.allocate(per_site=True)
+        s0 = ora.evaluate_full(per_site=True)
+        eng.set_weights(w)
+        assert eng.tree_score() == s0
+        order = eng.visit_order()
+        vb, mp, _, _ = eng.scan_visits(order, 1, 2 * n - 2, 1, 4)
+        for i in (1, 7, n + 3, 2 * n - 2):
+            ora.record(False)
+            ora.rearrange(i, 1, 4, True, s0)
+            assert np.array_equal(ora.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32)), i
