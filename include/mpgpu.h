@@ -282,8 +282,16 @@ typedef struct mpgpu_bb_hooks {
      * with tree `tree_index`; clear_first != 0 <=> rell > boot_logl[sample], i.e. boot_trees_parsimony[sample]
      * .clear() comes first (iqtree.cpp:3517-3520), then insert-if-absent (:3531-3534). */
     void (*mulhit)(void *user, int32_t sample, int32_t tree_index, int32_t clear_first);
+    /* policy MPGPU_BB_MULHITS_TOP only (may be NULL otherwise): a newly seen tree enters boot_trees_parsimony_top[sample]
+     * (kept in decreasing rell order: insert before the first entry with a smaller rell, iqtree.cpp:3563-3568);
+     * pop_worst != 0 <=> the list is full and its last entry is dropped first (:3571).  Returns the rell of the list's
+     * last entry after the update (the new boot_threshold when the list was full, :3578). */
+    int32_t (*tophit)(void *user, int32_t sample, int32_t tree_index, int32_t rell, int32_t pop_worst);
 } mpgpu_bb_hooks;
 #define MPGPU_BB_DEFAULT 0     /* iqtree.cpp:3687-3731 */
+#define MPGPU_BB_MULHITS_TOP 2 /* -mulhits -topboot N (store_top_boot_trees, iqtree.cpp:3536-3583): per replicate the N best newly
+                                * seen trees; state->top_n = N, state->top_count / state->boot_threshold [B] in/out; boot_logl,
+                                * boot_counts, boot_trees untouched, no tie-break draw */
 #define MPGPU_BB_MULHITS 1     /* params->multiple_hits without -topboot, iqtree.cpp:3498-3531: every tree that ties a
                                 * replicate's best score is kept; no tie-break draw, boot_counts / boot_trees untouched */
 typedef struct mpgpu_bb_state {
@@ -304,7 +312,10 @@ typedef struct mpgpu_bb_state {
     int32_t ratchet;                          /* 0 = normal iteration */
     const uint16_t *ratchet_pattern_pars;     /* in, when ratchet */
     int32_t ratchet_last_score;               /* out */
-    int32_t policy;                           /* MPGPU_BB_DEFAULT / MPGPU_BB_MULHITS */
+    int32_t policy;                           /* MPGPU_BB_DEFAULT / MPGPU_BB_MULHITS / MPGPU_BB_MULHITS_TOP */
+    int32_t top_n;                            /* MPGPU_BB_MULHITS_TOP: params->store_top_boot_trees */
+    int32_t *top_count;                       /* [B] in/out: boot_trees_parsimony_top[sample].size() */
+    int32_t *boot_threshold;                  /* [B] in/out: IQTree::boot_threshold (vector<int>, starts at -INT_MAX, iqtree.cpp:267) */
 } mpgpu_bb_state;
 int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,
@@ -329,6 +340,9 @@ void mpgpu_treels_hooks(mpgpu_treels *t, mpgpu_rng_fn rng, void *rng_user, mpgpu
 /* -mulhits: boot_trees_parsimony as collected through the mulhit hook: sizes[nsamples], then the members of
  * every set in ascending order, concatenated into flat (up to capacity); returns the total count. */
 int64_t mpgpu_treels_mulhits(const mpgpu_treels *t, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity);
+/* -mulhits -topboot: boot_trees_parsimony_top as collected through the tophit hook: sizes[nsamples], then (tree_index, rell)
+ * pairs in list order, concatenated into flat (2 ints per pair, up to capacity pairs); returns the pair count. */
+int64_t mpgpu_treels_toplists(const mpgpu_treels *t, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -440,11 +440,33 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
     const mpgpu_bb_hooks *hk = bb->hooks;
     const double eps = st->ufboot_epsilon;
     int32_t tree_index = hk->push_tree_logl(hk->user, cur_logl);
+    const int32_t tree_index_pushed = tree_index;         // treels_logl.size() - 1 of this call
     bool have = false;
     const bool mulhits = st->policy == MPGPU_BB_MULHITS;
     auto one = [&](int b, int32_t res) {
         const double rell = -(double)res;
         const double bl = st->boot_logl[b];
+        if (st->policy == MPGPU_BB_MULHITS_TOP) {        // iqtree.cpp:3536-3583
+            const int32_t N = st->top_n;
+            if (st->top_count[b] < N || rell > (double)st->boot_threshold[b]) {
+                const int32_t pushed = tree_index_pushed;
+                if (!have) {
+                    have = true;
+                    tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
+                }
+                if (tree_index == pushed) {              // a newly added tree (:3556)
+                    const int32_t r = (int32_t)rell;
+                    if (st->top_count[b] < N) {
+                        hk->tophit(hk->user, b, tree_index, r, 0);
+                        st->top_count[b]++;
+                        if (!(st->boot_threshold[b] < r)) st->boot_threshold[b] = r;          // :3569
+                    } else {
+                        st->boot_threshold[b] = hk->tophit(hk->user, b, tree_index, r, 1);    // :3571-3578
+                    }
+                }
+            }
+            return;
+        }
         if (mulhits) {                                   // iqtree.cpp:3498-3531
             if (rell >= bl) {
                 if (!have) {
@@ -804,7 +826,10 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, 
     if (!hooks->random_double || !hooks->push_tree_logl || !hooks->materialize) { set_error("incomplete -bb hooks"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
     if (state->B != c->reps.Buser || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
-    if (state->policy != MPGPU_BB_DEFAULT && state->policy != MPGPU_BB_MULHITS) { set_error("unknown -bb policy"); return 1; }
+    if (state->policy != MPGPU_BB_DEFAULT && state->policy != MPGPU_BB_MULHITS && state->policy != MPGPU_BB_MULHITS_TOP) { set_error("unknown -bb policy"); return 1; }
+    if (state->policy == MPGPU_BB_MULHITS_TOP && (!hooks->tophit || state->top_n < 1 || !state->top_count || !state->boot_threshold)) {
+        set_error("policy MPGPU_BB_MULHITS_TOP needs the tophit hook, top_n >= 1, top_count and boot_threshold"); return 1;
+    }
     if (state->policy == MPGPU_BB_MULHITS && !hooks->mulhit) { set_error("policy MPGPU_BB_MULHITS needs the mulhit hook"); return 1; }
     state->n_calls = 0; state->n_reps = 0;
     BBRun bb{hooks, state};

@@ -17,6 +17,7 @@ struct mpgpu_treels {
     std::unordered_map<uint64_t, int32_t> index;           // treels
     std::vector<int64_t> mats;                             // 4 per materialised tree: remove_ref, insert_ref, tree_index, fingerprint
     std::vector<std::set<int32_t>> mulhits;                // boot_trees_parsimony (-mulhits)
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> top;   // boot_trees_parsimony_top (-mulhits -topboot)
     mpgpu_rng_fn rng = nullptr; void *rng_user = nullptr;
 };
 
@@ -88,6 +89,18 @@ void hook_mulhit(void *user, int32_t sample, int32_t tree_index, int32_t clear_f
     s.insert(tree_index);                                  // :3531-3534
 }
 
+int32_t hook_tophit(void *user, int32_t sample, int32_t tree_index, int32_t rell, int32_t pop_worst)
+{
+    mpgpu_treels *h = (mpgpu_treels *)user;
+    if ((size_t)sample >= h->top.size()) h->top.resize((size_t)sample + 1);
+    std::vector<std::pair<int32_t, int32_t>> &t = h->top[sample];
+    if (pop_worst && !t.empty()) t.pop_back();             // iqtree.cpp:3571
+    size_t pos = 0;
+    while (pos < t.size() && !(t[pos].second < rell)) pos++;   // :3563-3566
+    t.insert(t.begin() + pos, std::make_pair(tree_index, rell));
+    return t.back().second;
+}
+
 }  // namespace
 
 extern "C" {
@@ -123,6 +136,18 @@ void mpgpu_treels_hooks(mpgpu_treels *h, mpgpu_rng_fn rng, void *rng_user, mpgpu
     out->push_tree_logl = hook_push;
     out->materialize = hook_materialize;
     out->mulhit = hook_mulhit;
+    out->tophit = hook_tophit;
+}
+int64_t mpgpu_treels_toplists(const mpgpu_treels *h, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity)
+{
+    int64_t tot = 0;
+    for (int32_t s = 0; s < nsamples; s++) {
+        const bool have = h && (size_t)s < h->top.size();
+        if (sizes) sizes[s] = have ? (int32_t)h->top[s].size() : 0;
+        if (!have) continue;
+        for (const auto &pr : h->top[s]) { if (flat && tot < capacity) { flat[2 * tot] = pr.first; flat[2 * tot + 1] = pr.second; } tot++; }
+    }
+    return tot;
 }
 int64_t mpgpu_treels_mulhits(const mpgpu_treels *h, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity)
 {

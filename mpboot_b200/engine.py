@@ -89,6 +89,8 @@ def lib():
     L.mpgpu_treels_hooks.argtypes = [vp, vp, vp, vp]
     L.mpgpu_treels_mulhits.restype = i64
     L.mpgpu_treels_mulhits.argtypes = [vp, i32, vp, vp, i64]
+    L.mpgpu_treels_toplists.restype = i64
+    L.mpgpu_treels_toplists.argtypes = [vp, i32, vp, vp, i64]
     _lib = L
     return L
 
@@ -100,7 +102,7 @@ def _p(a):
 class BBHooks(C.Structure):
     """mpgpu_bb_hooks (include/mpgpu.h)"""
     _fields_ = [("user", C.c_void_p), ("random_double", C.c_void_p), ("push_tree_logl", C.c_void_p),
-                ("materialize", C.c_void_p), ("mulhit", C.c_void_p)]
+                ("materialize", C.c_void_p), ("mulhit", C.c_void_p), ("tophit", C.c_void_p)]
 
 
 class BBState(C.Structure):
@@ -108,7 +110,7 @@ class BBState(C.Structure):
     _fields_ = [("B", C.c_int32), ("boot_logl", C.c_void_p), ("boot_counts", C.c_void_p), ("boot_trees", C.c_void_p),
                 ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64),
                 ("ratchet", C.c_int32), ("ratchet_pattern_pars", C.c_void_p), ("ratchet_last_score", C.c_int32),
-                ("policy", C.c_int32)]
+                ("policy", C.c_int32), ("top_n", C.c_int32), ("top_count", C.c_void_p), ("boot_threshold", C.c_void_p)]
 
 
 class HostRng:
@@ -153,6 +155,14 @@ class Treels:
         tot = self.L.mpgpu_treels_mulhits(self.h, nsamples, _p(sizes), None, 0)
         flat = np.zeros(max(tot, 1), dtype=np.int32)
         self.L.mpgpu_treels_mulhits(self.h, nsamples, _p(sizes), _p(flat), tot)
+        return sizes, flat[:tot]
+
+    def toplists(self, nsamples):
+        """boot_trees_parsimony_top (-mulhits -topboot): (sizes[nsamples], (tree_index, rell) pairs in list order)"""
+        sizes = np.zeros(nsamples, dtype=np.int32)
+        tot = self.L.mpgpu_treels_toplists(self.h, nsamples, _p(sizes), None, 0)
+        flat = np.zeros((max(tot, 1), 2), dtype=np.int32)
+        self.L.mpgpu_treels_toplists(self.h, nsamples, _p(sizes), _p(flat), tot)
         return sizes, flat[:tot]
 
     def materialized(self):
@@ -427,14 +437,19 @@ class Engine:
         return ptr.value, pitch.value
 
     def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
-                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None, mulhits=False):
+                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None, mulhits=False, topboot=0):
         """pllOptimizeSprParsimony + saveCurrentTree (default policy).  hooks: BBHooks (e.g.
         Treels.hooks(rng)); boot_* arrays are updated in place.  Returns (startMP, back_node,
         back_slot, insertions scored, saveCurrentTree calls, REPS vectors used)."""
         bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
         assert boot_logl.dtype == np.float64 and boot_counts.dtype == np.int32 and boot_trees.dtype == np.int32
         st = BBState(len(boot_logl), boot_logl.ctypes.data, boot_counts.ctypes.data, boot_trees.ctypes.data,
-                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0)
+                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0, 0, None, None)
+        if topboot:                                     # -mulhits -topboot N
+            self._top_count = np.zeros(len(boot_logl), dtype=np.int32)
+            self._boot_threshold = np.full(len(boot_logl), -(2 ** 31 - 1), dtype=np.int32)
+            st.policy = 2; st.top_n = int(topboot)
+            st.top_count = self._top_count.ctypes.data; st.boot_threshold = self._boot_threshold.ctypes.data
         if ratchet_pattern_pars is not None:            # ratchet iteration (iqtree.cpp:3283-3294)
             rp = np.zeros(max(self.P, len(ratchet_pattern_pars)), dtype=np.uint16)
             rp[: len(ratchet_pattern_pars)] = ratchet_pattern_pars

@@ -34,6 +34,8 @@ unsigned long mporacle_sweep_count_insertions(mporacle *o, int mintrav, int maxt
 /* -mulhits */
 void mporacle_boot_set_mulhits(mporacle *o, int on);
 int  mporacle_boot_mulhits(mporacle *o, int *sizes, int *flat, int cap);
+void mporacle_boot_set_topboot(mporacle *o, int n);
+int  mporacle_boot_toplists(mporacle *o, int *sizes, int *thresholds, int *flat, int cap);
 /* Sankoff (-cost) */
 int  mporacle_set_cost_matrix(mporacle *o, const unsigned *cost, const int *segment_upper, int nseg);
 int  mporacle_get_sankoff_vect(mporacle *o, int node, uint16_t *out);

@@ -565,6 +565,9 @@ MPREF_API unsigned long mpref_sweep_count_insertions(mpref *h, int mintrav, int 
 struct BootSim {
     bool multiple_hits;                                       /* params->multiple_hits (-mulhits), :3498-3531 */
     std::vector<std::set<int> > boot_trees_parsimony;
+    int store_top_boot_trees;                                 /* params->store_top_boot_trees (-mulhits -topboot N), :3536-3583 */
+    std::vector<std::vector<std::pair<int, int> > > boot_trees_parsimony_top;   /* (tree_index, rell), decreasing */
+    std::vector<int> boot_threshold;
     int B, stride, nseg;
     std::vector<unsigned short *> boot_samples_pars;          /* aligned, P+16, zero padded (:220-233) */
     std::vector<int> segment_upper;
@@ -646,6 +649,8 @@ MPREF_API void mpref_boot_init(mpref *h, int B, const unsigned short *boot, int 
     b->calls = b->reps_rows = b->skipped = b->bad_sum = 0;
     b->on_ratchet_hclimb1 = false; b->original_sample = NULL;
     b->multiple_hits = false; b->boot_trees_parsimony.assign(B, std::set<int>());
+    b->store_top_boot_trees = 0; b->boot_trees_parsimony_top.assign(B, std::vector<std::pair<int, int> >());
+    b->boot_threshold.assign(B, -INT_MAX);                    /* iqtree.cpp:267 */
     h->boot = b;
 }
 
@@ -661,6 +666,22 @@ MPREF_API void mpref_boot_set_ratchet(mpref *h, const unsigned short *original_s
 }
 
 MPREF_API void mpref_boot_set_mulhits(mpref *h, int on) { h->boot->multiple_hits = on != 0; }
+MPREF_API void mpref_boot_set_topboot(mpref *h, int n) { h->boot->multiple_hits = n > 0 || h->boot->multiple_hits; h->boot->store_top_boot_trees = n; }
+/* boot_trees_parsimony_top: sizes[B], thresholds[B], then (tree_index, rell) pairs in list order, concatenated; returns the pair count */
+MPREF_API int mpref_boot_toplists(mpref *h, int *sizes, int *thresholds, int *flat, int cap)
+{
+    BootSim *b = h->boot;
+    int tot = 0;
+    for (int s = 0; s < b->B; s++) {
+        sizes[s] = (int)b->boot_trees_parsimony_top[s].size();
+        thresholds[s] = b->boot_threshold[s];
+        for (size_t k = 0; k < b->boot_trees_parsimony_top[s].size(); k++) {
+            if (tot < cap) { flat[2 * tot] = b->boot_trees_parsimony_top[s][k].first; flat[2 * tot + 1] = b->boot_trees_parsimony_top[s][k].second; }
+            tot++;
+        }
+    }
+    return tot;
+}
 /* boot_trees_parsimony: sizes[B] and the sets' members, ascending, concatenated; returns the total */
 MPREF_API int mpref_boot_mulhits(mpref *h, int *sizes, int *flat, int cap)
 {
@@ -741,6 +762,37 @@ static void boot_save_current_tree(mpref *h, double cur_logl)
         }
         rell = -(double)res;
         if (skipped) { b->skipped++; continue; }                                           /* :3484 */
+        if (b->multiple_hits && b->store_top_boot_trees) {                                 /* :3536-3583 */
+            std::vector<std::pair<int, int> > &top = b->boot_trees_parsimony_top[sample];
+            const int N = b->store_top_boot_trees;
+            if ((int)top.size() < N || rell > b->boot_threshold[sample]) {
+                if (!have_str) {
+                    have_str = true;
+                    unsigned long long fp = mpref_tree_fingerprint(h);
+                    std::map<unsigned long long, int>::iterator it = b->treels.find(fp);
+                    if (it != b->treels.end()) tree_index = it->second;
+                    else { tree_index = (int)b->treels_logl.size() - 1; b->treels[fp] = tree_index; }
+                    long long m[5] = { call, 0, 0, tree_index, (long long)fp };
+                    b->mat.insert(b->mat.end(), m, m + 5);
+                }
+                if (tree_index == (int)b->treels_logl.size() - 1) {                        /* newly added :3556 */
+                    int count = (int)top.size();
+                    if (count < N) {
+                        std::vector<std::pair<int, int> >::iterator it;
+                        for (it = top.begin(); it < top.end(); it++) if (it->second < rell) break;
+                        top.insert(it, std::make_pair(tree_index, (int)rell));
+                        b->boot_threshold[sample] = (b->boot_threshold[sample] < rell) ? b->boot_threshold[sample] : (int)rell;
+                    } else if (count == N && rell > b->boot_threshold[sample]) {
+                        top.pop_back();
+                        std::vector<std::pair<int, int> >::iterator it;
+                        for (it = top.begin(); it < top.end(); it++) if (it->second < rell) break;
+                        top.insert(it, std::make_pair(tree_index, (int)rell));
+                        b->boot_threshold[sample] = top[N - 1].second;
+                    }
+                }
+            }
+            continue;
+        }
         if (b->multiple_hits) {                                                            /* :3498-3531 (no -topboot) */
             if (rell >= b->boot_logl[sample]) {
                 if (!have_str) {

@@ -79,6 +79,8 @@ def _boot_protos(L, pre):
     getattr(L, pre + "_boot_set_cutoff").argtypes = [vp, C.c_double]
     getattr(L, pre + "_boot_set_mulhits").argtypes = [vp, i]
     getattr(L, pre + "_boot_mulhits").argtypes = [vp, vp, vp, i]
+    getattr(L, pre + "_boot_set_topboot").argtypes = [vp, i]
+    getattr(L, pre + "_boot_toplists").argtypes = [vp, vp, vp, vp, i]
     getattr(L, pre + "_boot_set_ratchet").argtypes = [vp, vp, vp]
     getattr(L, pre + "_boot_set_state").argtypes = [vp, vp, vp, vp]
     getattr(L, pre + "_boot_get_state").argtypes = [vp, vp, vp, vp]
@@ -124,6 +126,18 @@ class BootMixin:
     def boot_set_mulhits(self, on=True):
         """params->multiple_hits (-mulhits without -topboot, iqtree.cpp:3498-3531)"""
         self._f("_boot_set_mulhits")(self.h, int(on))
+
+    def boot_set_topboot(self, n):
+        """params->store_top_boot_trees with -mulhits (iqtree.cpp:3536-3583)"""
+        self._f("_boot_set_topboot")(self.h, int(n))
+
+    def boot_toplists(self):
+        """boot_trees_parsimony_top: (sizes[B], boot_threshold[B], (tree_index, rell) pairs in list order, concatenated)"""
+        sizes = np.zeros(self._B, dtype=np.int32); thr = np.zeros(self._B, dtype=np.int32)
+        tot = self._f("_boot_toplists")(self.h, _p(sizes), _p(thr), None, 0)
+        flat = np.zeros((max(tot, 1), 2), dtype=np.int32)
+        self._f("_boot_toplists")(self.h, _p(sizes), _p(thr), _p(flat), tot)
+        return sizes, thr, flat[:tot]
 
     def boot_mulhits(self):
         """boot_trees_parsimony: (sizes[B], members of every set ascending, concatenated)"""

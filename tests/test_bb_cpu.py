@@ -46,7 +46,7 @@ def ratchet_setup(c, pp, seed):
     return w2, orig, init
 
 
-def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None, mulhits=False, cost=None):
+def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=None, mulhits=False, cost=None, topboot=0):
     eng.set_cost_matrix(cost, seg if cost is not None else None)      # -cost: pllCostMatrix + pllSegmentUpper (None = Fitch)
     if ratchet is not None:
         eng.set_weights(ratchet[0])
@@ -59,17 +59,21 @@ def run_bb(eng, c, boot, seg, cutoff, bound, is_ref, seed=2024, mt=6, ratchet=No
         eng.boot_set_ratchet(ratchet[1], ratchet[2])
     if mulhits:
         eng.boot_set_mulhits(True)
+    if topboot:
+        eng.boot_set_topboot(topboot)
     (reflib.lib().mpref_seed_rng if is_ref else portlib.seed_rng)(seed)
     eng.record(False)
     ret = eng.optimize_spr(1, mt, bb=True)
     draws = reflib.lib().mpref_rng_draws() if is_ref else portlib.rng_draws()
     return dict(ret=ret, draws=draws, ring=eng.get_ring(), state=eng.boot_state(), counters=eng.boot_counters(),
-                treels=eng.boot_treels(), mats=eng.boot_mats(), saved=eng.saved(), mulhits=eng.boot_mulhits())
+                treels=eng.boot_treels(), mats=eng.boot_mats(), saved=eng.saved(), mulhits=eng.boot_mulhits(),
+                toplists=eng.boot_toplists())
 
 
 def same(a, b):
     assert a["ret"] == b["ret"] and a["draws"] == b["draws"]
     assert all(np.array_equal(x, y) for x, y in zip(a["mulhits"], b["mulhits"]))
+    assert all(np.array_equal(x, y) for x, y in zip(a["toplists"], b["toplists"]))
     assert all(np.array_equal(x, y) for x, y in zip(a["ring"], b["ring"]))
     assert all(np.array_equal(x, y) for x, y in zip(a["state"], b["state"]))
     assert a["counters"] == b["counters"] and a["counters"][4] == 0
@@ -138,11 +142,29 @@ def test_port_bb_mulhits_equals_reference(n, L, dt, seed, B, mu):
     assert all(np.array_equal(p, q) for p, q in zip(x["mulhits"], y["mulhits"])) and np.array_equal(x["state"][0], y["state"][0])
 
 
+@needs_ref
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", MULHITS_CASES[:3])
+@pytest.mark.parametrize("N", [1, 3, 10])
+def test_port_bb_topboot_equals_reference(n, L, dt, seed, B, mu, N):
+    """-mulhits -topboot N (store_top_boot_trees, iqtree.cpp:3536-3583): per replicate the N best newly seen trees"""
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    a = run_bb(o, c, boot, seg, 0.0, None, False, topboot=N)
+    same(a, run_bb(r, c, boot, seg, 0.0, None, True, topboot=N))
+    assert a["toplists"][0].max() == N
+    cutoff = -(a["ret"] + 4.0)
+    x = run_bb(o, c, boot, seg, cutoff, bound, False, topboot=N)
+    same(x, run_bb(r, c, boot, seg, cutoff, ras, True, topboot=N))
+
+
 def mulhits_golden_case(g, k):
     n, L, dt, seed, B, mu = [x for x in MULHITS_CASES[k]]
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
     assert np.array_equal(boot, g["c%d_boot" % k]) and np.array_equal(c["codes"], g["c%d_codes" % k])   # same seeded inputs
     return c, o, seg, boot, bound
+
+
+TOPBOOT_NS = (1, 4)
 
 
 def check_mulhits_golden(g, k, tag, r):
@@ -153,6 +175,9 @@ def check_mulhits_golden(g, k, tag, r):
     assert np.array_equal(r["mulhits"][0], g[p + "sizes"]) and np.array_equal(r["mulhits"][1], g[p + "flat"])
     assert np.array_equal(r["treels"], g[p + "treels"])
     assert np.array_equal(r["mats_tf"], g[p + "mats"])                 # tree_index, topology fingerprint per materialised tree
+    if p + "top_sizes" in g:
+        assert np.array_equal(r["toplists"][0], g[p + "top_sizes"]) and np.array_equal(r["toplists"][1], g[p + "top_thr"])
+        assert np.array_equal(r["toplists"][2], g[p + "top_flat"])
 
 
 @pytest.mark.parametrize("k", range(len(MULHITS_CASES)))
@@ -161,6 +186,11 @@ def test_port_bb_mulhits_matches_golden(k):
     c, o, seg, boot, bound = mulhits_golden_case(g, k)
     for tag in ("all", "cut"):
         r = run_bb(o, c, boot, seg, float(g["c%d_%s_cutoff" % (k, tag)]), None, False, mulhits=True)
+        r["mats_tf"] = r["mats"][:, [3, 4]]
+        check_mulhits_golden(g, k, tag, r)
+    for N in TOPBOOT_NS:                                               # -mulhits -topboot N
+        tag = "top%d" % N
+        r = run_bb(o, c, boot, seg, float(g["c%d_%s_cutoff" % (k, tag)]), None, False, topboot=N)
         r["mats_tf"] = r["mats"][:, [3, 4]]
         check_mulhits_golden(g, k, tag, r)
 

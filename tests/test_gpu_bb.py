@@ -88,7 +88,7 @@ def test_reps_wrap_free_bulk_uses_no_exceptions():
     assert groups == 1 and exc == 0 and t == 1                # everything on the tensor path
 
 
-def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None, mulhits=False, cost=None):
+def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None, mulhits=False, cost=None, topboot=0):
     from mpboot_b200.engine import Treels
     eng = _engine(c, boot, seg, tensor, ratchet, cost)
     B = boot.shape[0]
@@ -99,9 +99,11 @@ def _run_gpu_bb(c, boot, seg, cutoff, tensor, seed=2024, mt=6, ratchet=None, mul
     ret, bn, bs, nins, ncalls, nreps = eng.optimize_spr_bb(c["bn"], c["bs"], tl.hooks(portlib.rng_fn_address()),
                                                            bl, bc, bt, cutoff, 0.5, 1, mt,
                                                            ratchet_pattern_pars=None if ratchet is None else ratchet[2],
-                                                           mulhits=mulhits)
+                                                           mulhits=mulhits, topboot=topboot)
+    top = tl.toplists(B)
+    thr = eng._boot_threshold.copy() if topboot else np.full(B, -(2 ** 31 - 1), dtype=np.int32)
     return dict(ret=ret, draws=portlib.rng_draws(), ring=(bn, bs), state=(bl, bc, bt), ncalls=ncalls, nreps=nreps,
-                treels=tl.logl(), mats=tl.materialized(), nins=nins, mulhits=tl.mulhits(B))
+                treels=tl.logl(), mats=tl.materialized(), nins=nins, mulhits=tl.mulhits(B), toplists=(top[0], thr, top[1]))
 
 
 @pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
@@ -266,3 +268,20 @@ def test_sankoff_reps_tensor_path_equals_exact(k, tensor):
         assert np.array_equal(r["treels"], w["treels"])
     finally:
         o.set_cost_matrix(None, None)
+
+
+@pytest.mark.parametrize("k", range(len(MULHITS_CASES)))
+def test_bb_topboot_matches_golden_and_oracle(k):
+    """-mulhits -topboot N (policy MPGPU_BB_MULHITS_TOP, iqtree.cpp:3536-3583)"""
+    from tests.test_bb_cpu import TOPBOOT_NS
+    g = dict(np.load(MULHITS_GOLD))
+    c, o, seg, boot, bound = mulhits_golden_case(g, k)
+    for N in TOPBOOT_NS:
+        r = _run_gpu_bb(c, boot, seg, 0.0, 1, topboot=N)
+        r["mats_tf"] = r["mats"][:, [2, 3]]
+        check_mulhits_golden(g, k, "top%d" % N, r)
+    w = run_bb(o, c, boot, seg, -(int(g["c%d_all_ret" % k]) + 4.0), None, False, topboot=3)
+    r = _run_gpu_bb(c, boot, seg, -(int(g["c%d_all_ret" % k]) + 4.0), 0, topboot=3)
+    assert r["ret"] == w["ret"] and r["draws"] == w["draws"] and np.array_equal(r["treels"], w["treels"])
+    assert all(np.array_equal(x, y) for x, y in zip(r["toplists"], w["toplists"]))
+    assert np.array_equal(r["mats"][:, :2], w["mats"][:, 1:3])

@@ -31,4 +31,19 @@ if __name__ == "__main__":
             g[p + "treels"] = x["treels"]; g[p + "mats"] = x["mats"][:, [3, 4]]
             print(k, tag, "ret", x["ret"], "draws", x["draws"], "calls", x["counters"][0], "trees", len(x["treels"]),
                   "set sizes", x["mulhits"][0].min(), x["mulhits"][0].max(), "materialised", len(x["mats"]))
+    from tests.test_bb_cpu import TOPBOOT_NS
+    for k, (n, L, dt, seed, B, mu) in enumerate(MULHITS_CASES):          # -mulhits -topboot N
+        c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+        r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+        for N in TOPBOOT_NS:
+            x = run_bb(r, c, boot, seg, 0.0, None, True, topboot=N)
+            p = "c%d_top%d_" % (k, N)
+            g[p + "cutoff"] = 0.0; g[p + "ret"] = x["ret"]; g[p + "draws"] = x["draws"]
+            g[p + "bn"], g[p + "bs"] = x["ring"]
+            g[p + "boot_logl"] = x["state"][0]
+            g[p + "sizes"], g[p + "flat"] = x["mulhits"]
+            g[p + "treels"] = x["treels"]; g[p + "mats"] = x["mats"][:, [3, 4]]
+            g[p + "top_sizes"], g[p + "top_thr"], g[p + "top_flat"] = x["toplists"]
+            print(k, "topboot", N, "ret", x["ret"], "draws", x["draws"], "materialised", len(x["mats"]), "list sizes",
+                  x["toplists"][0].min(), x["toplists"][0].max())
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mulhits.npz"), **g)
