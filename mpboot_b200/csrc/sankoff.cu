@@ -374,7 +374,7 @@ __device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (
 
 // ROWS: row_of[candidate] >= 0 selects the candidates whose vector is wanted; rows = [row][Lh]
 template <int S, bool ROWS>
-__global__ void __launch_bounds__(128) k_sk_scan(const uint4 *__restrict__ views4, int Lh,
+__global__ void __launch_bounds__(128, S <= 4 ? 5 : 1) k_sk_scan(const uint4 *__restrict__ views4, int Lh,
                                                  const ScanTask *__restrict__ tasks, int ntasks,
                                                  const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
                                                  int nslots, int cand_bias,
