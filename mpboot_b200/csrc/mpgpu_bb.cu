@@ -536,11 +536,21 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     }
     Prof prof;
     static const char *const prof_names[] = {"plan+launch", "scan wait", "reps", "replay", "views", "moves"};
+    double move_gap = 8.0;
+    auto after_move_batch = [](double gap) {
+        static const int fixed = getenv("MPGPU_SEARCH_BATCH") ? atoi(getenv("MPGPU_SEARCH_BATCH")) : 0;   // tuning knob
+        if (fixed > 0) return fixed;
+        const int b = (int)(2.0 * gap) + 1;
+        return b < 2 ? 2 : (b > 16 ? 16 : b);
+    };
     do {
         startMP = randomMP;
         visit_order(c->tree, order);                              // nodeRectifierPars :3297
         int i = 1;
-        int batch = 16;
+        // Speculation depth: visits planned and scored per batch.  Everything after the first accepted move of a batch is
+        // thrown away, so right after a move the batch follows the recent distance between moves (x2, within [2, 16]);
+        // while no move happens it doubles.  Only the amount of wasted work depends on it, never a result.
+        int batch = after_move_batch(move_gap);
         while (i <= nvisit) {
             int count = std::min(batch, nvisit - i + 1);
             prof.start();
@@ -616,7 +626,8 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 c->tree_set = true; c->lens_valid = false;
                 if (int rc = update_views(c, true)) return rc;
                 if (!c->wave_pending) compute_lengths(c);
-                batch = 16;
+                move_gap = 0.75 * move_gap + 0.25 * (double)v;          // v = visits consumed by this batch (the last one moved)
+                batch = after_move_batch(move_gap);
                 prof.stop(4);
             } else {
                 batch = std::min(batch * 2, nvisit);
