@@ -277,3 +277,42 @@ def test_refine_replicates_matches_sequential_reference_loop(n, L, dt, seed):
         assert np.array_equal(tbn[b][3:], want_rings[b][0][3:]) and np.array_equal(tbs[b][3:], want_rings[b][1][3:]), b
     eng.set_tree(c["bn"], c["bs"])                            # original frequencies are back
     assert eng.tree_score() == s0
+
+
+def _c2_parts():
+    """BASELINE's C2 shape (200 taxa x 100 000 sites, every site its own pattern, the bench's alignment) and its two column
+    halves; the cut sits where the number of informative sites before it is a multiple of 16."""
+    import bench
+    from mpboot_b200 import hostprep, synth
+    n, sites, dt, mu, seed, tseed = bench.WORKLOADS["c2"]
+    chars = synth.evolve_alignment(n, sites, dt, mu, seed)
+    full = hostprep.prepare(chars, dt, compress=False)
+    inf = hostprep.informative_mask(__import__("mpboot_b200.encoding", fromlist=["encode"]).encode(chars, dt), dt)
+    csum = np.cumsum(inf)
+    cut = int(np.nonzero((csum % 16 == 0) & (np.arange(sites) >= sites // 2))[0][0]) + 1
+    a = hostprep.prepare(chars[:, :cut], dt, compress=False)
+    b = hostprep.prepare(chars[:, cut:], dt, compress=False)
+    bn, bs = synth.random_tree_rings(n, np.random.default_rng(tseed))
+    return n, dt, full, a, b, bn, bs
+
+
+def test_full_size_c2_additivity_over_sites():
+    """Full BASELINE size (C2: 200 x 100 000).  Parsimony is a sum over sites, so every number the path produces on the
+    whole alignment must equal the sum of the numbers on its two column halves: tree score, every view length, every
+    insertion score of a whole sweep (14 476 of them) and the per-pattern vector's total."""
+    n, dt, full, a, b, bn, bs = _c2_parts()
+    engs = [_engine(p["codes"], p["weights"], dt, bn, bs) for p in (full, a, b)]
+    assert engs[0].n_inf == engs[1].n_inf + engs[2].n_inf
+    s = [e.tree_score() for e in engs]
+    assert s[0] == s[1] + s[2]
+    for node, slot in ((n + 1, 0), (n + 77, 2), (2 * n - 2, 1)):
+        assert engs[0].view_length(node, slot) == engs[1].view_length(node, slot) + engs[2].view_length(node, slot)
+    order = engs[0].visit_order()
+    res = [e.scan_visits(order, 1, 2 * n - 2, 1, 6) for e in engs]
+    assert len(res[0][1]) == 14476
+    for k in (0, 2, 3):
+        assert np.array_equal(res[0][k], res[1][k]) and np.array_equal(res[0][k], res[2][k])      # same candidates
+    assert np.array_equal(res[0][1].astype(np.int64), res[1][1].astype(np.int64) + res[2][1].astype(np.int64))
+    pp = [e.pattern_parsimony() for e in engs]
+    assert pp[0][1] == pp[1][1] + pp[2][1] == s[0]
+    assert np.array_equal(pp[0][0][: engs[0].n_inf], np.concatenate([pp[1][0][: engs[1].n_inf], pp[2][0][: engs[2].n_inf]]))

@@ -260,3 +260,36 @@ def test_reweighting_under_cost():
             ora.record(False)
             ora.rearrange(i, 1, 4, True, s0)
             assert np.array_equal(ora.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32)), i
+
+
+def test_full_size_c2_additivity_over_sites_under_cost():
+    """Full BASELINE size (C2: 200 x 100 000) under -cost: with segment bounds that respect the cut, the weighted score
+    (per-segment 16-bit sums included), every insertion score of a whole sweep and the node scores (mod 2^16) on the whole
+    alignment equal the sums over its two column halves; the early-exit bounds stay consistent with the totals."""
+    from tests.test_gpu_parity import _c2_parts
+    from mpboot_b200.engine import Engine
+    n, dt, full, a, b, bn, bs = _c2_parts()
+    cost = np.array([[0, 2, 1, 2], [2, 0, 2, 1], [1, 2, 0, 2], [2, 1, 2, 0]], dtype=np.uint32)
+    na, nb = a["n_inf"], b["n_inf"]
+    assert na % 16 == 0
+    seg_a = np.array(list(range(96, na, 96)) + [na], dtype=np.int32)
+    seg_b = np.array(list(range(96, nb, 96)) + [nb], dtype=np.int32)
+    seg_f = np.concatenate([seg_a, na + seg_b]).astype(np.int32)
+    engs = []
+    for p, seg in ((full, seg_f), (a, seg_a), (b, seg_b)):
+        e = Engine()
+        e.load_alignment(p["codes"], p["weights"], dt)
+        e.set_cost_matrix(cost, seg)
+        e.set_tree(bn, bs)
+        engs.append(e)
+    s = [e.tree_score() for e in engs]
+    assert s[0] == s[1] + s[2]
+    for node, slot in ((n + 1, 0), (n + 77, 2), (2 * n - 2, 1)):
+        assert engs[0].view_length(node, slot) == (engs[1].view_length(node, slot) + engs[2].view_length(node, slot)) & 0xFFFF
+    order = engs[0].visit_order()
+    res = [e.scan_visits(order, 1, 2 * n - 2, 1, 6) for e in engs]
+    assert len(res[0][1]) == 14476
+    assert np.array_equal(res[0][1].astype(np.int64), res[1][1].astype(np.int64) + res[2][1].astype(np.int64))
+    est = engs[0].scan_bounds(14476)
+    lb = engs[0].sankoff_layout()[1]
+    assert (est.astype(np.int64) >= int(lb[0])).all()          # est_max >= first prefix + its remainder bound >= the bound alone
