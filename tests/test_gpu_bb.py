@@ -285,3 +285,45 @@ def test_bb_topboot_matches_golden_and_oracle(k):
     assert r["ret"] == w["ret"] and r["draws"] == w["draws"] and np.array_equal(r["treels"], w["treels"])
     assert all(np.array_equal(x, y) for x, y in zip(r["toplists"], w["toplists"]))
     assert np.array_equal(r["mats"][:, :2], w["mats"][:, 1:3])
+
+
+def test_full_size_c2_reps_linearity_and_dot_product():
+    """Full BASELINE size (C2: 200 x 100 000 patterns, B = 999 replicates in three blocks A, B, A + B): with MPBoot's own
+    segmentation no 16-bit segment sum wraps, so REPS is linear in the replicate frequencies -- res(A + B) = res(A) + res(B)
+    for the current tree and for every insertion of 40 node visits -- and, for the current tree, equals the plain integer dot
+    product of the per-pattern scores with the frequencies (numpy int64), all through the tensor-core path."""
+    import bench
+    from tests.test_gpu_parity import _c2_parts
+    from mpboot_b200.engine import Engine
+    n, dt, full, a, b, bn, bs = _c2_parts()
+    ninf = full["n_inf"]
+    eng = Engine()
+    eng.load_alignment(full["codes"], full["weights"], dt)
+    eng.set_tree(bn, bs)
+    pp, sm = eng.pattern_parsimony()
+    seg = bench.do_segmenting(pp[:ninf], full["weights"], ninf)
+    rng = np.random.default_rng(12)
+    K = 333
+    wa = rng.multinomial(ninf, np.full(ninf, 1.0 / ninf), size=K).astype(np.uint16)
+    wb = rng.multinomial(ninf, np.full(ninf, 1.0 / ninf), size=K).astype(np.uint16)
+    boot = np.concatenate([wa, wb, wa + wb]).astype(np.uint16)
+    eng.load_replicates(boot, seg)
+    groups, exc, tensor = eng.reps_info()
+    assert tensor == 1 and groups == 1 and exc == 0
+    cur = eng.reps_current_tree().astype(np.int64)
+    want = boot.astype(np.int64) @ pp[:ninf].astype(np.int64)
+    assert np.array_equal(cur, want)
+    order = eng.visit_order()
+    vb, mp, cref, cprune = eng.scan_visits(order, 150, 40, 1, 6)
+    got = eng.reps_candidates(np.arange(-1, len(mp), dtype=np.int32)).astype(np.int64)
+    assert len(mp) > 1000
+    assert np.array_equal(got[:, 2 * K: 3 * K], got[:, :K] + got[:, K: 2 * K])
+    # a candidate's replicate score under the all-ones replicate would be its parsimony score: A + B has column sums 2 * ninf / ninf
+    ones = np.ones((1, ninf), dtype=np.uint16)
+    eng2 = Engine()
+    eng2.load_alignment(full["codes"], full["weights"], dt)
+    eng2.set_tree(bn, bs)
+    eng2.load_replicates(ones, seg)
+    eng2.scan_visits(order, 150, 40, 1, 6)
+    r1 = eng2.reps_candidates(np.arange(-1, len(mp), dtype=np.int32))[:, 0]
+    assert r1[0] == sm and np.array_equal(r1[1:].astype(np.int64), mp.astype(np.int64))
