@@ -56,7 +56,11 @@ def full_capture(rep, title):
         if w in hdr:
             i = hdr.index(w)
             out.append("%-70s %s | %s" % (w, rows[1][i], " | ".join(r[i] for r in rows[2:])))
-    tens = [h for h in hdr if ("tensor" in h or "tmem" in h.lower()) and ".avg." in h]
+    # tensor / TMEM activity; of ncu's constant hardware peaks only the two that back the int8 roofline denominator
+    tens = [h for h in hdr if ("tensor" in h or "tmem" in h.lower()) and ".avg." in h
+            and ("peak_sustained" not in h.split(".avg.")[1] or h.endswith("pct_of_peak_sustained_active") or h.endswith("pct_of_peak_sustained_elapsed")
+                 or h in ("sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.peak_sustained",
+                          "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.peak_sustained"))]
     for h in tens:
         if h not in WANT:
             i = hdr.index(h)
