@@ -714,16 +714,30 @@ __global__ void k_site_counters(const uint32_t *__restrict__ views, size_t view_
     uint32_t cnt[16];
 #pragma unroll
     for (int b = 0; b < 16; b++) cnt[b] = 0;
-    for (int i = 0; i < npairs; i++) {
-        uint32_t a[S], bb[S];
-        load_states<S>(views + (size_t)pairs[2 * i] * view_stride + off, gs, a);
-        load_states<S>(views + (size_t)pairs[2 * i + 1] * view_stride + off, gs, bb);
-        uint32_t carry = ~any_and<S>(a, bb);
+    // The pair loop is a chain of dependent loads when taken one pair at a time (one thread per site word, ~2n pairs):
+    // U pairs are loaded first (independent requests in flight), then folded into the counters.
+    constexpr int U = S <= 4 ? 8 : 2;
+    for (int i0 = 0; i0 < npairs; i0 += U) {
+        uint32_t mis[U];
 #pragma unroll
-        for (int b = 0; b < 16; b++) {
-            const uint32_t t = cnt[b] & carry;
-            cnt[b] ^= carry;
-            carry = t;
+        for (int u = 0; u < U; u++) {
+            mis[u] = 0;
+            if (i0 + u < npairs) {
+                uint32_t a[S], bb[S];
+                load_states<S>(views + (size_t)__ldg(pairs + 2 * (i0 + u)) * view_stride + off, gs, a);
+                load_states<S>(views + (size_t)__ldg(pairs + 2 * (i0 + u) + 1) * view_stride + off, gs, bb);
+                mis[u] = ~any_and<S>(a, bb);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint32_t carry = mis[u];
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const uint32_t t = cnt[b] & carry;
+                cnt[b] ^= carry;
+                carry = t;
+            }
         }
     }
 #pragma unroll
@@ -732,7 +746,7 @@ __global__ void k_site_counters(const uint32_t *__restrict__ views, size_t view_
 
 int launch_site_counters(Ctx *c, int npairs, int nbits)
 {
-    int threads = 128, blocks = (c->Wl + threads - 1) / threads;
+    int threads = 32, blocks = (c->Wl + threads - 1) / threads;      // few threads in total (one per site word): spread them over the SMs
     switch (c->S) {
     case 2:  k_site_counters<2><<<blocks, threads, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, c->d_pairs, npairs, nbits, c->d_bitcnt); break;
     case 4:  k_site_counters<4><<<blocks, threads, 0, c->stream>>>(c->d_views, c->view_stride, c->Wl, c->d_pairs, npairs, nbits, c->d_bitcnt); break;

@@ -181,15 +181,28 @@ static int refresh_tree_rows(Ctx *c)
     const int upper0 = c->sort_alignment ? c->n_inf : c->P;
     if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper0 > 0 ? upper0 : 1))) return rc;
     if (int rc = launch_gather_patterns(c, nbits, upper0)) return rc;
-    MPGPU_CUDA(cudaMemsetAsync(r.d_segmax, 0, (size_t)nseg * 4, c->stream));
-    if (int rc = launch_seg_check(c, r.d_segmax)) return rc;
-    if (int rc = shard_sum(c, r.d_segmax, nseg)) return rc;
     std::vector<int32_t> segmax(nseg);
-    MPGPU_CUDA(cudaMemcpyAsync(segmax.data(), r.d_segmax, (size_t)nseg * 4, cudaMemcpyDeviceToHost, c->stream));
-    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-    bool grew = false;
-    for (int g = 0; g < nseg; g++) if (segmax[g] >= 65536 && !r.seg_flagged[g]) { r.seg_flagged[g] = 1; grew = true; }
-    if (grew) { if (int rc = build_classification(c)) return rc; }
+    bool exact_check = true;
+    if (c->shard_count == 1 && (int)r.seg_wmax.size() == nseg) {
+        // cheap sufficient test first: (max score in the segment + 1) * (largest weight sum of the segment over the replicates)
+        MPGPU_CUDA(cudaMemsetAsync(r.d_segmax, 0, (size_t)nseg * 4, c->stream));
+        if (int rc = launch_seg_cmax(c, r.d_segmax)) return rc;
+        MPGPU_CUDA(cudaMemcpyAsync(segmax.data(), r.d_segmax, (size_t)nseg * 4, cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        exact_check = false;
+        for (int g = 0; g < nseg; g++)
+            if (!r.seg_flagged[g] && (int64_t)(segmax[g] + 1) * r.seg_wmax[g] >= 65536) { exact_check = true; break; }
+    }
+    if (exact_check) {
+        MPGPU_CUDA(cudaMemsetAsync(r.d_segmax, 0, (size_t)nseg * 4, c->stream));
+        if (int rc = launch_seg_check(c, r.d_segmax)) return rc;
+        if (int rc = shard_sum(c, r.d_segmax, nseg)) return rc;
+        MPGPU_CUDA(cudaMemcpyAsync(segmax.data(), r.d_segmax, (size_t)nseg * 4, cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        bool grew = false;
+        for (int g = 0; g < nseg; g++) if (segmax[g] >= 65536 && !r.seg_flagged[g]) { r.seg_flagged[g] = 1; grew = true; }
+        if (grew) { if (int rc = build_classification(c)) return rc; }
+    }
     rp_stop(c, 1);
     if (int rc = ensure_rows(c, kTreeRows + 64)) return rc;
     if (c->ptn_identity) {
@@ -949,6 +962,17 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (!c->sk.on) {
         if (int rc2 = build_classification(c)) return rc2;
         r.reclassifications = 0;
+        if (c->shard_count == 1 && r.upper > 0) {           // seg_wmax: the wrap check against an all-zero score vector = max_b sum w
+            const int upper1 = c->sort_alignment ? c->n_inf : c->P;
+            if (int rc2 = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper1 > 0 ? upper1 : 1))) return rc2;
+            MPGPU_CUDA(cudaMemsetAsync(c->d_ptn, 0, (size_t)(upper1 > 0 ? upper1 : 1) * sizeof(uint16_t), c->stream));
+            MPGPU_CUDA(cudaMemsetAsync(r.d_segmax, 0, (size_t)nseg_ * 4, c->stream));
+            r.p_lo = 0; r.p_hi = r.upper;
+            if (int rc2 = launch_seg_check(c, r.d_segmax)) return rc2;
+            r.seg_wmax.assign(nseg_, 0);
+            MPGPU_CUDA(cudaMemcpyAsync(r.seg_wmax.data(), r.d_segmax, (size_t)nseg_ * 4, cudaMemcpyDeviceToHost, c->stream));
+            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        } else r.seg_wmax.clear();
         if (r.use_tensor) { if (int rc2 = make_w8_tensor_map(c)) return rc2; }
     } else {
         // -cost: the rows are per-pattern costs (sankoff.cu).  The u8 operand is only usable when no replicate weight

@@ -120,6 +120,7 @@ struct Reps {
     int32_t *d_seg_upper = nullptr;       // [nseg]
     std::vector<uint8_t> heavy;           // [upper] some replicate weight > 255
     std::vector<uint8_t> seg_flagged;     // [nseg] segment is in a group of its own (can wrap)
+    std::vector<int32_t> seg_wmax;        // [nseg] max over replicates of the segment's weight sum (the wrap check at score 0)
     int32_t *d_exc_ptn = nullptr, *d_exc_group = nullptr; size_t exc_cap = 0, exc_group_cap = 0;
     alignas(64) unsigned char tmap_w8[128];
     bool tmap_valid = false;
@@ -328,6 +329,7 @@ const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined);
 int launch_transpose_boot(Ctx *c, const uint16_t *d_boot16, int stride, uint8_t *d_heavy);
 int launch_build_w8(Ctx *c, const uint8_t *d_is_exc);
 int launch_seg_check(Ctx *c, int32_t *d_segmax);
+int launch_seg_cmax(Ctx *c, int32_t *d_cmax);
 int launch_edge_rows(Ctx *c, const int4 *d_edges, int nedges, uint32_t *d_rows);
 int launch_gather_rows(Ctx *c, const uint32_t *d_src, uint32_t *d_dst, int nrows);
 int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows);

@@ -111,6 +111,31 @@ __global__ void __launch_bounds__(256) k_seg_check(const uint16_t *__restrict__ 
     if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(&segmax[seg], v);
 }
 
+// cmax[seg] = max over the segment's patterns of the tree's per-pattern score: (cmax + 1) * max_b sum_{ptn in seg} w_b[ptn]
+// bounds the sum k_seg_check computes, without touching the weights
+__global__ void __launch_bounds__(128) k_seg_cmax(const uint16_t *__restrict__ ptn_pars, const int32_t *__restrict__ seg_upper, int upper,
+                                                  int32_t *__restrict__ cmax)
+{
+    const int seg = blockIdx.x;
+    const int lo = seg ? seg_upper[seg - 1] : 0;
+    const int hi = min(seg_upper[seg], upper);
+    int m = 0;
+    for (int p = lo + threadIdx.x; p < hi; p += blockDim.x) m = max(m, (int)__ldg(ptn_pars + p));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&cmax[seg], m);
+}
+
+int launch_seg_cmax(Ctx *c, int32_t *d_cmax)
+{
+    Reps &r = c->reps;
+    const int nseg = (int)r.seg_upper.size();
+    if (r.upper == 0) return 0;
+    k_seg_cmax<<<nseg, 128, 0, c->stream>>>(c->d_ptn, r.d_seg_upper, r.upper, d_cmax);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_seg_check(Ctx *c, int32_t *d_segmax)
 {
     Reps &r = c->reps;
