@@ -450,21 +450,26 @@ int compute_site_counters(Ctx *c, int nbits)
 {
     const HostTree &t = c->tree;
     const int n = c->n;
-    std::vector<int32_t> order;
+    std::vector<int32_t> &order = c->sc_order;
     visit_order(t, order);
-    std::vector<int32_t> pairs;
+    // staging in a page-locked buffer of the context: the upload is asynchronous and nothing has to be waited for here
+    // (two halves used alternately: the previous upload may still be in flight when the next tree arrives)
+    const size_t need = (size_t)2 * (n - 1);
+    if (!c->pairs_pin.reserve(2 * need + 16)) { set_error("pinned allocation failed"); return 1; }
+    int32_t *pairs = c->pairs_pin.data() + (c->pairs_flip ? need : 0);
+    c->pairs_flip ^= 1;
+    size_t k = 0;
     for (int i = n + 1; i <= 2 * n - 2; i++) {
         const int r = order[i];
-        pairs.push_back(t.vid(t.back(t.next(r))));
-        pairs.push_back(t.vid(t.back(t.next(t.next(r)))));
+        pairs[k++] = t.vid(t.back(t.next(r)));
+        pairs[k++] = t.vid(t.back(t.next(t.next(r))));
     }
-    pairs.push_back(t.vid(3)); pairs.push_back(t.vid(t.back(3)));
-    const int npairs = (int)pairs.size() / 2;
-    if (int rc = ensure(c->d_pairs, c->pairs_cap, pairs.size())) return rc;
+    pairs[k++] = t.vid(3); pairs[k++] = t.vid(t.back(3));
+    const int npairs = (int)k / 2;
+    if (int rc = ensure(c->d_pairs, c->pairs_cap, k)) return rc;
     if (int rc = ensure(c->d_bitcnt, c->bitcnt_cap, (size_t)16 * c->Wl)) return rc;
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_pairs, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_pairs, pairs, k * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     if (int rc = launch_site_counters(c, npairs, nbits)) return rc;
-    MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // `pairs` goes out of scope
     return 0;
 }
 

@@ -424,7 +424,16 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
 struct BBRun {
     const mpgpu_bb_hooks *hooks;
     mpgpu_bb_state *st;
+    // host screen: replicate b can only be touched by a call with res <= screen[b] = floor(-boot_logl[b] + eps)
+    // (rell > boot_logl - eps, rell >= boot_logl and rell == boot_logl all imply it); kept current as boot_logl moves
+    std::vector<int32_t> screen;
 };
+
+static inline int32_t bb_screen_of(double boot_logl, double eps)
+{
+    const double lim = std::floor(-boot_logl + eps);
+    return lim >= 2147483647.0 ? 2147483647 : (lim <= -2147483648.0 ? (int32_t)-2147483647 - 1 : (int32_t)lim);
+}
 
 static inline bool bb_passes_logl(const mpgpu_bb_state *st, double cur_logl)
 {
@@ -504,7 +513,17 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
     };
     if (ro.dense_off[call] >= 0) {                      // else: no replicate of this call reaches its threshold
         const int32_t *row = ro.dense.data() + ro.dense_off[call];
-        for (int b = 0; b < st->B; b++) one(b, row[b]);
+        if (st->policy == MPGPU_BB_MULHITS_TOP) {
+            for (int b = 0; b < st->B; b++) one(b, row[b]);
+        } else {
+            const int32_t *scr = bb->screen.data();
+            for (int b = 0; b < st->B; b++) {
+                if (row[b] > scr[b]) continue;          // integer screen: nothing of :3498-3531 / :3687-3731 can fire
+                const double before = st->boot_logl[b];
+                one(b, row[b]);
+                if (st->boot_logl[b] != before) bb->screen[b] = bb_screen_of(st->boot_logl[b], eps);
+            }
+        }
     }
     st->n_reps++;
 }
@@ -587,10 +606,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                         if (st->ratchet ? all : bb_passes(st, mp[j])) { call_of[(size_t)v + 1 + j] = (int32_t)pass_cands.size(); pass_cands.push_back(j); }
                 }
                 thr.resize(st->B);
-                for (int b = 0; b < st->B; b++) {
-                    const double lim = std::floor(-st->boot_logl[b] + st->ufboot_epsilon);
-                    thr[b] = lim >= 2147483647.0 ? 2147483647 : (lim <= -2147483648.0 ? (int32_t)-2147483647 - 1 : (int32_t)lim);
-                }
+                for (int b = 0; b < st->B; b++) thr[b] = bb_screen_of(st->boot_logl[b], st->ufboot_epsilon);
                 if (int rc = reps_run(c, pass_cands.data(), (int)pass_cands.size(), thr.data(), ro)) return rc;
             }
             prof.stop(2); prof.start();
@@ -856,7 +872,9 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, 
     }
     if (state->policy == MPGPU_BB_MULHITS && !hooks->mulhit) { set_error("policy MPGPU_BB_MULHITS needs the mulhit hook"); return 1; }
     state->n_calls = 0; state->n_reps = 0;
-    BBRun bb{hooks, state};
+    BBRun bb{hooks, state, {}};
+    bb.screen.resize((size_t)state->B);
+    for (int b = 0; b < state->B; b++) bb.screen[b] = bb_screen_of(state->boot_logl[b], state->ufboot_epsilon);
     return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, hooks->random_double, hooks->user, &bb, best, n_insertions);
 }
 

@@ -252,6 +252,8 @@ struct Ctx {
     // pattern scores
     uint32_t *d_bitcnt = nullptr; size_t bitcnt_cap = 0;   // bit-sliced per-site counters
     int32_t *d_pairs = nullptr; size_t pairs_cap = 0;
+    PinnedArray<int32_t> pairs_pin; int pairs_flip = 0;    // staging of the (child view, child view) pairs of compute_site_counters
+    std::vector<int32_t> sc_order;
     uint16_t *d_ptn = nullptr; size_t ptn_cap = 0;
     int64_t *d_ptn_site = nullptr; size_t ptn_site_cap = 0;
     bool ptn_site_valid = false;
