@@ -321,6 +321,17 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,
                           uint32_t *best, int64_t *n_insertions);
 
+/* ---- host-only entry points: no device, no CUDA call ----
+ * The tree-walking half of the path on ring tables, for hosts that keep their own search loop and for tests of the host
+ * logic: nodeRectifierPars' visit order (sprparsimony.cpp:2046-2101), the candidates rearrangeParsimony /
+ * addTraverseParsimony test for visits order[first .. first+count) in the reference's order (:2208-2376) -- the same
+ * enumeration mpgpu_scan_* score -- and restoreTreeRearrangeParsimony's move (:2379). */
+int mpgpu_host_visit_order(int ntaxa, const int32_t *back_node, const int32_t *back_slot, int32_t *order);
+int mpgpu_host_enumerate(int ntaxa, const int32_t *back_node, const int32_t *back_slot, const int32_t *order, int first, int count,
+                         int mintrav, int maxtrav, int32_t *visit_begin, int32_t *cand_ref, int32_t *cand_prune, int capacity,
+                         int *n_cand);
+int mpgpu_host_apply_spr(int ntaxa, int32_t *back_node, int32_t *back_slot, int32_t remove_ref, int32_t insert_ref);
+
 /* ---- host-side helper: a minimal treels / treels_logl container (iqtree.h) ----
  * For hosts that do not bring their own (tests, bench.py): collects treels_logl, keys
  * materialised trees by a canonical topology hash like the treels map (iqtree.cpp:3299-3312,

@@ -86,6 +86,8 @@ struct ScanPlan {
     PinnedArray<ScanOffs> offs;
     PinnedArray<ScanCtl> ctl;
     PinnedArray<ScanTask> tasks_pin;      // upload copy of `tasks`
+    std::vector<ScanOffs> offs_host;      // host-only plans (mpgpu_host_enumerate: no device, no page-locked memory)
+    std::vector<ScanCtl> ctl_host;
     std::vector<ScanTask> tasks;
     std::vector<int32_t> visit_begin;     // count+1
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
@@ -349,7 +351,7 @@ public:
     ScanPlanner();
     ~ScanPlanner();
     int begin(const HostTree &t, const int32_t *order, int first, int count,
-              int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan);
+              int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan, bool host_only = false);
     void add(int v0, int v1);
     void finish();
 private:

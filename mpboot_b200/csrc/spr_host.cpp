@@ -9,6 +9,7 @@
 #include "mpgpu_internal.h"
 
 #include <algorithm>
+#include <cstring>
 
 namespace mpgpu {
 
@@ -129,7 +130,7 @@ ScanPlanner::ScanPlanner() : impl(nullptr) {}
 ScanPlanner::~ScanPlanner() { delete impl; }
 
 int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int count,
-                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan)
+                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan, bool host_only)
 {
     delete impl; impl = nullptr;
     plan.tasks.clear(); plan.visit_begin.clear(); plan.task_vids.clear();
@@ -145,11 +146,14 @@ int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int c
     // upper bounds: one side of a visit reaches at most 4 * (2^maxtrav - 1) branches, never more than the tree has
     const size_t per_side = std::min<size_t>((size_t)4 << std::max(maxtrav, 0), (size_t)2 * n);
     const size_t cap = (size_t)count * 2 * per_side + 16;
-    if (!plan.offs.reserve(cap + cap / 4) || !plan.ctl.reserve(cap + cap / 4) || !plan.tasks_pin.reserve((size_t)plan.task_cap + 16)) {
+    if (host_only) {
+        plan.offs_host.resize(cap + cap / 4); plan.ctl_host.resize(cap + cap / 4);
+    } else if (!plan.offs.reserve(cap + cap / 4) || !plan.ctl.reserve(cap + cap / 4) || !plan.tasks_pin.reserve((size_t)plan.task_cap + 16)) {
         set_error("page-locked host allocation for the scan plan failed"); return 1;
     }
     if (plan.cand_ref.size() < cap) { plan.cand_ref.resize(cap); plan.cand_prune.resize(cap); plan.cand_task.resize(cap); }
-    b.offs = plan.offs.data(); b.ctl = plan.ctl.data();
+    b.offs = host_only ? plan.offs_host.data() : plan.offs.data();
+    b.ctl = host_only ? plan.ctl_host.data() : plan.ctl.data();
     b.cand_ref = plan.cand_ref.data(); b.cand_prune = plan.cand_prune.data(); b.cand_task = plan.cand_task.data();
     plan.tasks.reserve((size_t)plan.task_cap);
     return 0;
@@ -232,3 +236,61 @@ void apply_spr_move(HostTree &t, int p, int q)
 }
 
 }  // namespace mpgpu
+
+// ---- host-only entry points (no device, no CUDA call): the tree-walking half of the path for hosts that keep their own
+// search loop and for the CPU tests of the host logic ---------------------------------------------------------------
+using namespace mpgpu;
+
+static int host_tree_from(int ntaxa, const int32_t *back_node, const int32_t *back_slot, HostTree &t)
+{
+    if (ntaxa < 4 || !back_node || !back_slot) { set_error("bad tree argument"); return 1; }
+    const int len = 3 * (2 * ntaxa - 1);
+    t.n = ntaxa; t.bn.assign(back_node, back_node + len); t.bs.assign(back_slot, back_slot + len);
+    return 0;
+}
+
+extern "C" {
+
+int mpgpu_host_visit_order(int ntaxa, const int32_t *back_node, const int32_t *back_slot, int32_t *order)
+{
+    HostTree t;
+    if (int rc = host_tree_from(ntaxa, back_node, back_slot, t)) return rc;
+    if (!order) { set_error("null argument"); return 1; }
+    std::vector<int32_t> o;
+    visit_order(t, o);
+    memcpy(order, o.data(), o.size() * sizeof(int32_t));
+    return 0;
+}
+
+int mpgpu_host_enumerate(int ntaxa, const int32_t *back_node, const int32_t *back_slot, const int32_t *order, int first, int count,
+                         int mintrav, int maxtrav, int32_t *visit_begin, int32_t *cand_ref, int32_t *cand_prune, int capacity, int *n_cand)
+{
+    HostTree t;
+    if (int rc = host_tree_from(ntaxa, back_node, back_slot, t)) return rc;
+    if (!order || !visit_begin || first < 1 || count < 0 || first + count > 2 * ntaxa - 1) { set_error("bad visit range"); return 1; }
+    ScanPlan plan;
+    ScanPlanner pl;
+    if (int rc = pl.begin(t, order, first, count, mintrav, maxtrav, 1u, plan, true)) return rc;
+    pl.add(0, count);
+    pl.finish();
+    if (n_cand) *n_cand = plan.n_cand;
+    if (plan.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
+    memcpy(visit_begin, plan.visit_begin.data(), plan.visit_begin.size() * sizeof(int32_t));
+    if (cand_ref) memcpy(cand_ref, plan.cand_ref.data(), (size_t)plan.n_cand * sizeof(int32_t));
+    if (cand_prune) memcpy(cand_prune, plan.cand_prune.data(), (size_t)plan.n_cand * sizeof(int32_t));
+    return 0;
+}
+
+int mpgpu_host_apply_spr(int ntaxa, int32_t *back_node, int32_t *back_slot, int32_t remove_ref, int32_t insert_ref)
+{
+    HostTree t;
+    if (int rc = host_tree_from(ntaxa, back_node, back_slot, t)) return rc;
+    const int len = 3 * (2 * ntaxa - 1);
+    if (remove_ref < 3 * (ntaxa + 1) || remove_ref >= len || insert_ref < 3 || insert_ref >= len) { set_error("bad move"); return 1; }
+    apply_spr_move(t, remove_ref, insert_ref);
+    memcpy(back_node, t.bn.data(), (size_t)len * sizeof(int32_t));
+    memcpy(back_slot, t.bs.data(), (size_t)len * sizeof(int32_t));
+    return 0;
+}
+
+}  // extern "C"

@@ -31,6 +31,7 @@ int  mporacle_optimize_spr(mporacle *o, int mintrav, int maxtrav, int bb);
 unsigned mporacle_ras(mporacle *o, long seed, int spr_dist);
 unsigned long mporacle_sweep_count_insertions(mporacle *o, int mintrav, int maxtrav, int per_site, int reps);
 
+void mporacle_saved_refs(mporacle *o, int *out);      /* (pruned ref, insertion ref) of every recorded saveCurrentTree call */
 /* -mulhits */
 void mporacle_boot_set_mulhits(mporacle *o, int on);
 int  mporacle_boot_mulhits(mporacle *o, int *sizes, int *flat, int cap);

@@ -199,6 +199,14 @@ class OracleEngine(BootMixin):
             lib().mporacle_saved_ptn(self.h, _p(pt))
         return mp, pt
 
+    def saved_refs(self):
+        """(pruned ref, insertion ref) per recorded call (0, 0 = the current tree), ref = 3 * node + slot"""
+        k = lib().mporacle_saved_count(self.h)
+        out = np.zeros((max(k, 1), 2), dtype=np.int32)
+        if k:
+            lib().mporacle_saved_refs(self.h, _p(out))
+        return out[:k]
+
     def rearrange(self, i, mintrav, maxtrav, per_site, best_in):
         out = np.zeros(6, dtype=np.uint32)
         rc = lib().mporacle_rearrange(self.h, i, mintrav, maxtrav, int(per_site), int(best_in), _p(out))

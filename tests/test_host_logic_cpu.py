@@ -1,0 +1,119 @@
+"""CPU suite, host logic: the tree-walking half of the library (visit order, candidate enumeration, applying a move) runs
+without a device through the mpgpu_host_* entry points and must reproduce the reference's order exactly -- checked against
+the golden vectors (produced by the reference itself) and, call by call, against the C oracle's record of which (pruned
+ref, insertion ref) pair every saveCurrentTree / testInsertParsimony call saw."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from mpboot_b200 import engine
+from oracle import portlib
+from tests.helpers import make_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASE_FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "*.npz"))
+                    if not f.endswith("tables.npz") and not os.path.basename(f).startswith(("sankoff_", "mulhits", "skbb")))
+IDS = [os.path.basename(p)[:-4] for p in CASE_FILES]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def host_visit_order(n, bn, bs):
+    L = engine.lib()
+    L.mpgpu_host_visit_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    bn = np.ascontiguousarray(bn, dtype=np.int32); bs = np.ascontiguousarray(bs, dtype=np.int32)
+    out = np.zeros(2 * n - 1, dtype=np.int32)
+    assert L.mpgpu_host_visit_order(n, _p(bn), _p(bs), _p(out)) == 0, L.mpgpu_last_error()
+    return out
+
+
+def host_enumerate(n, bn, bs, order, first, count, mintrav, maxtrav):
+    L = engine.lib()
+    L.mpgpu_host_enumerate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    bn = np.ascontiguousarray(bn, dtype=np.int32); bs = np.ascontiguousarray(bs, dtype=np.int32)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    cap = count * (8 << min(maxtrav, 10)) + 16
+    vb = np.zeros(count + 1, dtype=np.int32); cr = np.zeros(cap, dtype=np.int32); cp = np.zeros(cap, dtype=np.int32)
+    nc = C.c_int()
+    assert L.mpgpu_host_enumerate(n, _p(bn), _p(bs), _p(order), first, count, mintrav, maxtrav, _p(vb), _p(cr), _p(cp), cap,
+                                  C.byref(nc)) == 0, L.mpgpu_last_error()
+    return vb, cr[: nc.value], cp[: nc.value]
+
+
+def host_apply_spr(n, bn, bs, remove_ref, insert_ref):
+    L = engine.lib()
+    L.mpgpu_host_apply_spr.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
+    assert L.mpgpu_host_apply_spr(n, _p(bn), _p(bs), int(remove_ref), int(insert_ref)) == 0, L.mpgpu_last_error()
+    return bn, bs
+
+
+@pytest.mark.parametrize("path", CASE_FILES, ids=IDS)
+def test_visit_order_and_candidate_counts_match_golden(path):
+    g = dict(np.load(path))
+    n, mt = int(g["n"]), int(g["maxtrav"])
+    order = host_visit_order(n, g["bn"], g["bs"])
+    assert np.array_equal(order[1:], g["order"][1:])                          # nodeRectifierPars
+    vb, cref, cprune = host_enumerate(n, g["bn"], g["bs"], order, 1, 2 * n - 2, 1, mt)
+    assert np.array_equal(vb, g["visit_begin"]) and len(cref) == len(g["visit_mp"])
+
+
+@pytest.mark.parametrize("n,L,dt,seed,mt", [(12, 200, 1, 1, 6), (33, 300, 1, 2, 6), (64, 200, 2, 3, 4), (20, 100, 0, 4, 3),
+                                              (100, 150, 1, 5, 6), (7, 120, 1, 6, 6), (4, 80, 1, 7, 6), (48, 100, 6, 8, 12)])
+def test_enumeration_matches_oracle_call_by_call(n, L, dt, seed, mt):
+    """Every candidate of every node visit: same pruned ref and insertion ref, in the same order, as the oracle's
+    rearrangeParsimony / addTraverseParsimony restatement saw them; also in pieces (batching must not matter)."""
+    c = make_case(n, L, dt, seed, mu=0.2)
+    o = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    o.set_ring(c["bn"], c["bs"]); o.allocate(True)
+    s0 = o.evaluate_full(True)
+    order = host_visit_order(n, c["bn"], c["bs"])
+    rn, rs = o.get_nodep()
+    assert np.array_equal((3 * rn + rs)[1:], order[1:])
+    vb, cref, cprune = host_enumerate(n, c["bn"], c["bs"], order, 1, 2 * n - 2, 1, mt)
+    for i in range(1, 2 * n - 1):
+        o.record(False)
+        o.rearrange(i, 1, mt, True, s0)
+        refs = o.saved_refs()
+        assert tuple(refs[0]) == (0, 0)                                        # the current tree first (:2286)
+        assert np.array_equal(refs[1:, 0], cprune[vb[i - 1]: vb[i]]), i
+        assert np.array_equal(refs[1:, 1], cref[vb[i - 1]: vb[i]]), i
+    for first, count in ((1, 1), (2, 3), (n, n - 2), (2 * n - 2, 1)):
+        if first + count > 2 * n - 1 or count < 1:
+            continue
+        vb1, cr1, cp1 = host_enumerate(n, c["bn"], c["bs"], order, first, count, 1, mt)
+        a, b = vb[first - 1], vb[first - 1 + count]
+        assert np.array_equal(vb1, vb[first - 1: first + count] - a)
+        assert np.array_equal(cr1, cref[a:b]) and np.array_equal(cp1, cprune[a:b])
+
+
+@pytest.mark.parametrize("n,seed", [(10, 11), (40, 12), (90, 13)])
+def test_apply_move_matches_oracle(n, seed):
+    """restoreTreeRearrangeParsimony (:2379): after applying the oracle's chosen move the ring tables agree, over a chain of moves."""
+    c = make_case(n, 300, 1, seed, mu=0.15)
+    o = portlib.OracleEngine(c["codes"], c["weights"], 1)
+    o.set_ring(c["bn"], c["bs"]); o.allocate(False)
+    s0 = o.evaluate_full(False)
+    bn, bs = np.array(c["bn"], dtype=np.int32), np.array(c["bs"], dtype=np.int32)
+    portlib.seed_rng(3)
+    moved = 0
+    for i in range(1, 2 * n - 1):
+        rc, out = o.rearrange(i, 1, 5, False, s0)
+        rem, ins = 3 * int(out[1]) + int(out[2]), 3 * int(out[3]) + int(out[4])
+        if not out[1] or not out[3]:
+            continue
+        o.apply_move(False)
+        bn, bs = host_apply_spr(n, bn, bs, rem, ins)
+        wbn, wbs = o.get_ring()
+        assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:]), i
+        s0 = o.evaluate_full(False)
+        moved += 1
+        if moved >= 12:
+            break
+    assert moved >= 3
