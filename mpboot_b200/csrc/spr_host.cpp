@@ -41,8 +41,13 @@ namespace {
 struct Builder {
     const int n;
     ScanPlan &plan;
-    std::vector<int32_t> c1, c2, voff_;     // per ref: back(next(ref)), back(next(next(ref))), view offset
-    std::vector<uint8_t> tip;
+    // per ref, one record (one cache line touch per visited node): back(next(ref)), back(next(next(ref))), view offset, is-tip
+    struct Ref { int32_t c1, c2, voff, tip; };
+    std::vector<Ref> ref_;
+    // views of the same data for the callers that index by field
+    struct Field1 { const std::vector<Ref> &r; int32_t operator[](int i) const { return r[i].c1; } } c1{ref_};
+    struct Field2 { const std::vector<Ref> &r; int32_t operator[](int i) const { return r[i].c2; } } c2{ref_};
+    struct FieldT { const std::vector<Ref> &r; bool operator[](int i) const { return r[i].tip != 0; } } tip{ref_};
     int prune_ref = 0, task_index = 0, cand_base = 0;
     // raw cursors into the plan's arrays (sized up front)
     ScanOffs *offs = nullptr; ScanCtl *ctl = nullptr;
@@ -52,50 +57,58 @@ struct Builder {
     Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride) : n(t.n), plan(pp)
     {
         const int nref = 3 * (2 * n - 1);
-        c1.assign(nref, 0); c2.assign(nref, 0); voff_.assign(nref, 0); tip.assign(nref, 1);
+        ref_.assign(nref, Ref{0, 0, 0, 1});
         for (int node = 1; node <= 2 * n - 2; node++) {
             const int ns = node <= n ? 1 : 3;
             for (int sl = 0; sl < ns; sl++) {
                 const int r = 3 * node + sl;
-                voff_[r] = (int32_t)((uint32_t)t.vid(r) * vstride);
+                ref_[r].voff = (int32_t)((uint32_t)t.vid(r) * vstride);
                 if (node > n) {
-                    tip[r] = 0;
+                    ref_[r].tip = 0;
                     const int a = 3 * node + (sl + 1) % 3, b = 3 * node + (sl + 2) % 3;
-                    c1[r] = t.back(a); c2[r] = t.back(b);
+                    ref_[r].c1 = t.back(a); ref_[r].c2 = t.back(b);
                 }
             }
         }
     }
-    int32_t voff(int ref) const { return voff_[ref]; }
+    int32_t voff(int ref) const { return ref_[ref].voff; }
 
-    int new_op(uint32_t src, int a, int b)
+    // One expand op for the node whose children (seen from it) are a and b; src = where its up-view comes from.
+    // The op's control words are built in registers while the children are walked and stored once.
+    void expand(int a, int b, uint32_t src, int mintrav, int maxtrav, int depth)
     {
-        offs[nops].c1 = voff_[a]; offs[nops].c2 = voff_[b];
-        ctl[nops].outs = 0xFFFFFFFFu; ctl[nops].meta = src | 0xFF00u | 0xFF0000u;
-        return nops++;
+        const int me = nops++;
+        offs[me].c1 = ref_[a].voff; offs[me].c2 = ref_[b].voff;
+        uint32_t outs = 0xFFFFFFFFu, meta = src | 0xFF00u | 0xFF0000u;
+        child(a, 0, mintrav, maxtrav, depth, outs, meta);
+        child(b, 1, mintrav, maxtrav, depth, outs, meta);
+        ctl[me].outs = outs; ctl[me].meta = meta;
     }
 
-    // addTraverseParsimony(tr, pr, p, q, mintrav, maxtrav, doAll = FALSE) for q = x.
-    // parent_op/which identify the expand op that scores x; depth is x's distance (1-based).
-    void traverse(int x, int mintrav, int maxtrav, int parent_op, int which, int depth)
+    // addTraverseParsimony(tr, pr, p, q, mintrav, maxtrav, doAll = FALSE) for q = x, the `which`-th child of the op being
+    // built (outs / meta); depth is x's distance from the removed node (1-based).
+    void child(int x, int which, int mintrav, int maxtrav, int depth, uint32_t &outs, uint32_t &meta)
     {
         if (--mintrav <= 0) {                                   // testInsertParsimony(p, x)
             const int idx = ncand++;
-            cand_ref[idx] = x; cand_prune[idx] = prune_ref; cand_task[idx] = task_index;
+            cand_ref[idx] = x;                                  // cand_prune / cand_task: constant per task, filled by end_task()
             const uint32_t rel = (uint32_t)(idx - cand_base);
-            uint32_t &w = ctl[parent_op].outs;
-            w = which == 0 ? ((w & 0xFFFF0000u) | rel) : ((w & 0x0000FFFFu) | (rel << 16));
+            outs = which == 0 ? ((outs & 0xFFFF0000u) | rel) : ((outs & 0x0000FFFFu) | (rel << 16));
         }
-        if (!tip[x] && (--maxtrav > 0)) {
+        const Ref &rx = ref_[x];
+        if (!rx.tip && (--maxtrav > 0)) {
             const int slot = 2 * (depth - 1) + which;           // U_x goes here
-            uint32_t &w = ctl[parent_op].meta;
-            w = which == 0 ? ((w & ~0xFF00u) | ((uint32_t)slot << 8)) : ((w & ~0xFF0000u) | ((uint32_t)slot << 16));
+            meta = which == 0 ? ((meta & ~0xFF00u) | ((uint32_t)slot << 8)) : ((meta & ~0xFF0000u) | ((uint32_t)slot << 16));
             if (slot + 1 > max_slot) max_slot = slot + 1;
-            const int a = c1[x], b = c2[x];
-            const int me = new_op((uint32_t)slot, a, b);
-            traverse(a, mintrav, maxtrav, me, 0, depth + 1);
-            traverse(b, mintrav, maxtrav, me, 1, depth + 1);
+            expand(rx.c1, rx.c2, (uint32_t)slot, mintrav, maxtrav, depth + 1);
         }
+    }
+
+    // candidates [cand_base, ncand) belong to the task that just ended
+    void end_task()
+    {
+        std::fill(cand_prune + cand_base, cand_prune + ncand, prune_ref);
+        std::fill(cand_task + cand_base, cand_task + ncand, task_index);
     }
 
     // the two addTraverseParsimony calls made for one inner neighbour `nb` of the removed node:
@@ -103,10 +116,7 @@ struct Builder {
     // is the D1 neighbour, src code 0xFF) or D1 (src code 0xFE).
     void expand_top(int nb, uint32_t src_code, int mintrav, int maxtrav)
     {
-        const int a = c1[nb], b = c2[nb];
-        const int me = new_op(src_code, a, b);
-        traverse(a, mintrav, maxtrav, me, 0, 1);
-        traverse(b, mintrav, maxtrav, me, 1, 1);
+        expand(ref_[nb].c1, ref_[nb].c2, src_code, mintrav, maxtrav, 1);
     }
 };
 
@@ -182,6 +192,7 @@ void ScanPlanner::add(int v0, int v1)
                 b.prune_ref = p; b.task_index = (int)plan.tasks.size();
                 if (!b.tip[p1]) b.expand_top(p1, 0xFFu, mintrav, maxtrav);
                 if (!b.tip[p2]) b.expand_top(p2, 0xFEu, mintrav, maxtrav);
+                b.end_task();
                 task.op_end = b.nops;
                 plan.tasks.push_back(task);
                 plan.task_vids.push_back(t.vid(q)); plan.task_vids.push_back(t.vid(p1)); plan.task_vids.push_back(t.vid(p2));
@@ -200,6 +211,7 @@ void ScanPlanner::add(int v0, int v1)
                 b.prune_ref = q; b.task_index = (int)plan.tasks.size();
                 if (!b.tip[q1]) b.expand_top(q1, 0xFFu, mintrav2, maxtrav);
                 if (!b.tip[q2]) b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
+                b.end_task();
                 task.op_end = b.nops;
                 plan.tasks.push_back(task);
                 plan.task_vids.push_back(t.vid(p)); plan.task_vids.push_back(t.vid(q1)); plan.task_vids.push_back(t.vid(q2));
@@ -268,7 +280,7 @@ int mpgpu_host_enumerate(int ntaxa, const int32_t *back_node, const int32_t *bac
     HostTree t;
     if (int rc = host_tree_from(ntaxa, back_node, back_slot, t)) return rc;
     if (!order || !visit_begin || first < 1 || count < 0 || first + count > 2 * ntaxa - 1) { set_error("bad visit range"); return 1; }
-    ScanPlan plan;
+    static thread_local ScanPlan plan;                     // its arrays are sized to an upper bound: keep them across calls
     ScanPlanner pl;
     if (int rc = pl.begin(t, order, first, count, mintrav, maxtrav, 1u, plan, true)) return rc;
     pl.add(0, count);
