@@ -128,38 +128,44 @@ def bench_search(eng, case, args):
     """Whole plain SPR search (pllOptimizeSprParsimony) from the workload's random tree through the C-ABI with
     host ring tables in and out -- the call MPBoot makes -- next to the reference's own search on one host core
     (same start, same RNG stream; score, draw count and final tree must be identical)."""
-    import ctypes as C
-    from oracle import portlib, reflib
-    use_ref = reflib.available()
-    if use_ref:
-        L_ = reflib.lib()
-        seed_fn, draws_fn = L_.mpref_seed_rng, L_.mpref_rng_draws
-        fn = C.cast(L_.mpref_random_double, C.c_void_p).value
-    else:
-        seed_fn, draws_fn, fn = portlib.seed_rng, portlib.rng_draws, portlib.rng_fn_address()
+    from mpboot_b200 import engine
+    # Our arm draws from the library's own splitmix64 (mpgpu_splitmix64_double); the reference side below is seeded with
+    # the same value on its own copy of the same generator, so both see the same stream.  Nothing under oracle/ runs
+    # inside our timed calls.
+    GOLD, INV = 0x9E3779B97F4A7C15, pow(0x9E3779B97F4A7C15, -1, 1 << 64)
+
+    def draws_of(rng, seed):
+        return ((rng.state.value - seed) * INV) % (1 << 64)
+
     best = None
     for _ in range(3):
-        seed_fn(1234)
+        rng = engine.HostRng(1234)
         t0 = time.time()
-        r, bn, bs, nins = eng.optimize_spr(case["bn"], case["bs"], fn, 1, args.maxtrav)
+        r, bn, bs, nins = eng.optimize_spr(case["bn"], case["bs"], rng.fn, 1, args.maxtrav, rng_user=rng.user)
         dt = time.time() - t0
         if best is None or dt < best:
             best = dt
-    draws = int(draws_fn())
+    draws = int(draws_of(rng, 1234))
     out = {"what": "mpgpu_optimize_spr from the random tree to convergence, host buffers (e2e), best of 3",
            "wall_s": best, "insertions": int(nins), "insertions_per_s": nins / best, "final_score": int(r), "rng_draws": draws}
     # N1: the refinement loop of optimizeBootTrees over resident codes, from the search's final tree
     Bref = 20
     boot = make_replicates(case, Bref, seed=9)
     tbn = np.tile(bn, (Bref, 1)); tbs = np.tile(bs, (Bref, 1))
-    seed_fn(99)
+    rng = engine.HostRng(99)
     t0 = time.time()
-    sc, _, _, rins = eng.refine_replicates(boot, tbn, tbs, fn, 1, args.maxtrav)
+    sc, _, _, rins = eng.refine_replicates(boot, tbn, tbs, rng.fn, 1, args.maxtrav, rng_user=rng.user)
     dt = time.time() - t0
     out["refine"] = {"what": "mpgpu_refine_replicates: %d bootstrap replicates re-weighted over the resident codes and hill-climbed from the search's final tree" % Bref,
                      "wall_s": dt, "replicates_per_s": Bref / dt, "insertions": int(rins), "insertions_per_s": rins / dt}
     eng.set_tree(case["bn"], case["bs"])
     if not args.no_cpu_baseline and args.workload in ("c2", "c3", "c5", "tiny"):
+        from oracle import portlib, reflib
+        use_ref = reflib.available()
+        if use_ref:
+            seed_fn, draws_fn = reflib.lib().mpref_seed_rng, reflib.lib().mpref_rng_draws
+        else:
+            seed_fn, draws_fn = portlib.seed_rng, portlib.rng_draws
         if use_ref:
             ref = reflib.RefEngine(case["chars"], case["weights"], case["datatype"], n_informative=case["n_inf"]); kind = "reference"
         else:
@@ -176,11 +182,11 @@ def bench_search(eng, case, args):
         out["speedup_vs_one_core"] = dt / best
         # MPBoot's own starting point (config[0], `-s`): one randomized-stepwise-addition tree + its SPR rounds
         # (_pllComputeRandomizedStepwiseAdditionParsimonyTree, sprparsimony.cpp:3224), same seeds on both sides
-        seed_fn(4321)
+        rng = engine.HostRng(4321)
         t0 = time.time()
-        rb, rbn, rbs, rins2, _ = eng.stepwise_addition(777, args.maxtrav, fn)
+        rb, rbn, rbs, rins2, _ = eng.stepwise_addition(777, args.maxtrav, rng.fn, rng_user=rng.user)
         t_gpu = time.time() - t0
-        d_gpu = int(draws_fn())
+        d_gpu = int(draws_of(rng, 4321))
         seed_fn(4321)
         t0 = time.time()
         rb_ref = ref.ras(777, args.maxtrav)
