@@ -317,7 +317,7 @@ template <int S, int NW>
 static int launch_wave_t(Ctx *c, const Triple *d_list, int nlevels, int hdr, int total, uint32_t *d_wcount)
 {
     const size_t smem = wave_smem_bytes(S, hdr + total);
-    static size_t opted = 0;
+    static size_t opted_dev[64] = {0}; size_t &opted = opted_dev[c->device & 63];   /* the attribute is per device */
     if (smem > opted) {
         MPGPU_CUDA(cudaFuncSetAttribute(k_fitch_wave<S, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         opted = smem;
@@ -652,7 +652,7 @@ static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
     while (wpb > 1 && per_warp * wpb > budget) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (smem > 48 * 1024 && smem > configured) {
         MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         configured = 200 * 1024;

@@ -565,7 +565,7 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int
     if (!r.tmap_valid) { set_error("replicate weights not loaded"); return 1; }
     const int kb_lo = r.kb_lo, kb_hi = r.kb_hi;
     if (kb_hi <= kb_lo) return 0;
-    static bool configured = false;
+    static bool configured_dev[64] = {false}; bool &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (!configured) {
         MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         configured = true;
@@ -609,7 +609,7 @@ int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrow
     Reps &r = c->reps;
     if (nrows == 0) return 0;
     if (!r.tmap_valid) { set_error("replicate weights not loaded"); return 1; }
-    static bool configured = false;
+    static bool configured_dev[64] = {false}; bool &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (!configured) {
         MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         configured = true;

@@ -975,7 +975,7 @@ int sk_run_scan(Ctx *c)
     if (int rc = sk_scan_geometry(c, ntasks, per_warp, false, &wpb, &smem, &blocks)) return rc;
 #define SK_SCAN_LAUNCH                                                                                                         \
     {                                                                                                                          \
-        static size_t configured = 0;                                                                                          \
+        static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */                                                                                          \
         if (smem > 48 * 1024 && smem > configured) {                                                                           \
             MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));   \
             configured = 200 * 1024;                                                                                           \
@@ -1065,7 +1065,7 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
         if (int rc = sk_scan_geometry(c, ntasks, per_warp, true, &wpb, &smem, &blocks)) return rc;
 #define SK_ROWS_LAUNCH                                                                                                         \
     {                                                                                                                          \
-        static size_t configured = 0;                                                                                          \
+        static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */                                                                                          \
         if (smem > 48 * 1024 && smem > configured) {                                                                           \
             MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024))); \
             configured = 200 * 1024;                                                                                           \
