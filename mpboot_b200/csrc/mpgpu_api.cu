@@ -586,6 +586,8 @@ int mpgpu_load_alignment(mpgpu_ctx *c, int ntaxa, int npatterns, int datatype,
     MPGPU_CUDA(cudaSetDevice(c->device));
     free_alignment(c);
     free_reps(c);
+    c->sk.on = false;                       // a new alignment starts in Fitch mode (resetGlobalParamOnNewAln, sprparsimony.cpp:143): the
+                                            // cost matrix's segment bounds belong to the old pattern set
     c->n = ntaxa; c->P = npatterns; c->datatype = datatype; c->S = S; c->sort_alignment = sort_alignment;
     c->weights.assign(aliaswgt, aliaswgt + npatterns);
     for (int i = 0; i < npatterns; i++) if (aliaswgt[i] < 0) { set_error("negative pattern weight"); return 1; }
