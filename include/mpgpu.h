@@ -234,7 +234,7 @@ int mpgpu_sankoff_view(mpgpu_ctx *ctx, int node, int slot, uint16_t *out);
  * "sankoff_exact" = 1 switches the replay off (the reference's perSiteScores mode). */
 int mpgpu_scan_bounds(mpgpu_ctx *ctx, uint32_t *est_max, int capacity);
 /* -cost together with -bb: set the cost matrix first, then mpgpu_load_replicates; mpgpu_reps_* and
- * mpgpu_optimize_spr_bb (both policies) then score the Sankoff pattern vectors (pllComputeSankoffPatternParsimony :3346)
+ * mpgpu_optimize_spr_bb (every policy) then score the Sankoff pattern vectors (pllComputeSankoffPatternParsimony :3346)
  * of the current tree / of every insertion with the u16 semantics of iqtree.cpp:3424-3449.  Per chunk of calls the
  * contraction runs on the int8 tensor cores when every cost and replicate weight fits in a byte and no 16-bit segment
  * sum of the chunk can wrap (proved from the chunk's column maxima), and on an exact CUDA-core kernel otherwise;
