@@ -525,7 +525,7 @@ def run_reference(args):
     ins = sum(r[0] for r in res)
     elapsed = max(r[1] for r in res)
     kind, sample = res[0][2], res[0][3]
-    sites = case["sites"]
+    sites = int(np.asarray(case["weights"][: case["n_inf"]], dtype=np.int64).sum())   # the engine works on the informative sites, expanded by weight (compressDNA)
     ins_per_s = ins / elapsed
     value = ins_per_s * 2.0 * sites
     line = {
