@@ -156,6 +156,12 @@ int mpgpu_optimize_spr(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot,
                        int mintrav, int maxtrav, mpgpu_rng_fn rng, void *rng_user,
                        uint32_t *best, int64_t *n_insertions);
 
+/* About the last mpgpu_optimize_spr / _bb / stepwise search on this context: the score of the tree it started
+ * from -- what the reference computes at sprparsimony.cpp:3277 and asserts equal to IQ-TREE's own kernel
+ * (-iqtree->curScore, :3279), so the host can keep that cross-check --, the moves applied (:3312) and the
+ * scan batches launched.  Any pointer may be NULL. */
+int mpgpu_search_info(mpgpu_ctx *ctx, uint32_t *start_score, int64_t *moves, int64_t *batches);
+
 /* ---- R12 / N1: the refinement loop of IQTree::optimizeBootTrees, default policy (iqtree.cpp:2795-2862) ----
  * For sample = 0 .. B-1, in order: the alignment is re-weighted with boot_samples[sample]
  * (Alignment::modifyPatternFreq, alignment.cpp:117 -- here: new frequencies over the codes that are

@@ -653,19 +653,39 @@ int mpgpu_set_tree(mpgpu_ctx *c, const int32_t *back_node, const int32_t *back_s
     if (!c->d_views) { set_error("no alignment loaded"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     const int n = c->n, len = 3 * (2 * n - 1);
-    HostTree &t = c->tree;
+    // validate into a temporary and commit only on success: every slot of a complete unrooted binary tree is hooked
+    // symmetrically, and the table is ONE tree (a symmetric table can still be cyclic or disconnected, which would send
+    // the schedule builder's traversal round in circles): a walk from tip 1 must reach all 2n-2 nodes, each once.
+    HostTree t;
     t.n = n; t.bn.assign(back_node, back_node + len); t.bs.assign(back_slot, back_slot + len);
-    // validate: every slot of a complete unrooted binary tree is hooked symmetrically
-    for (int node = 1; node <= 2 * n - 2; node++) {
+    const char *bad = nullptr;
+    for (int node = 1; node <= 2 * n - 2 && !bad; node++) {
         const int ns = node <= n ? 1 : 3;
         for (int s = 0; s < ns; s++) {
             const int r = 3 * node + s;
             const int bnode = t.bn[r], bslot = t.bs[r];
-            if (bnode < 1 || bnode > 2 * n - 2 || bslot < 0 || bslot > (bnode <= n ? 0 : 2)) { set_error("ring table: dangling or out-of-range back pointer"); return 1; }
+            if (bnode < 1 || bnode > 2 * n - 2 || bslot < 0 || bslot > (bnode <= n ? 0 : 2)) { bad = "ring table: dangling or out-of-range back pointer"; break; }
             const int b = 3 * bnode + bslot;
-            if (t.bn[b] != node || t.bs[b] != s) { set_error("ring table: back pointers are not symmetric"); return 1; }
+            if (t.bn[b] != node || t.bs[b] != s) { bad = "ring table: back pointers are not symmetric"; break; }
         }
     }
+    if (!bad) {
+        std::vector<uint8_t> seen((size_t)2 * n - 1, 0);
+        std::vector<int> stack;
+        int reached = 1;
+        seen[1] = 1;
+        stack.push_back(t.back(3));
+        while (!stack.empty() && !bad) {
+            const int x = stack.back(); stack.pop_back();       // ref by which the walk enters node x/3
+            const int node = x / 3;
+            if (seen[node]) { bad = "ring table: not a tree (a node is reachable along two paths)"; break; }
+            seen[node] = 1; reached++;
+            if (node > n) { stack.push_back(t.back(t.next(x))); stack.push_back(t.back(t.next(t.next(x)))); }
+        }
+        if (!bad && reached != 2 * n - 2) bad = "ring table: not connected (tip 1 does not reach every node)";
+    }
+    if (bad) { c->tree_set = false; c->lens_valid = false; c->kids_valid = false; set_error(bad); return 1; }
+    c->tree.n = n; c->tree.bn.swap(t.bn); c->tree.bs.swap(t.bs);
     c->tree_set = true; c->lens_valid = false;
     if (int rc = compute_views(c)) return rc;
     if (c->reduces()) compute_lengths(c);

@@ -539,7 +539,8 @@ using namespace mpgpu;
 // order, and throws the rest of a batch away as soon as a move is applied (the only event that
 // changes any score).
 static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
-                         mpgpu_rng_fn rng, void *rng_user, BBRun *bb, uint32_t *best, int64_t *n_insertions)
+                         mpgpu_rng_fn rng, void *rng_user, BBRun *bb, uint32_t *best, int64_t *n_insertions,
+                         bool stepwise_on = false)
 {
     if (!c->reduces()) { set_error("the SPR search on a sharded context needs mpgpu_set_allreduce"); return 1; }
     if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
@@ -547,11 +548,14 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
     // -cost, plain mode: evaluateSankoff... leaves early when a prefix of segment sums plus the remainder bound
     // exceeds tr->bestParsimony (:951-956); its return value is then > best, i.e. the insertion changes nothing
-    const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1 && !bb;   // -bb runs with perSiteScores: no early exit
+    // (-bb runs with perSiteScores: no early exit; neither do the SPR rounds of the stepwise-addition tree, where the
+    // reference keeps doing_stepwise_addition set for the whole of _pllMakeParsimonyTreeFast, :3226-3233 / :951)
+    const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1 && !bb && !stepwise_on;
     const int n = c->n, nvisit = 2 * n - 2;
     uint32_t score = 0;
     if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
     uint32_t bestParsimony = score;
+    c->search_start_score = score; c->search_moves = 0; c->search_batches = 0;
     uint32_t randomMP = bestParsimony, startMP = 0;
     uint32_t cur_score = score;                                     // score of the tree in c->tree
     unsigned int bestIterationScoreHits = 1;
@@ -587,6 +591,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             int count = std::min(batch, nvisit - i + 1);
             prof.start();
             if (int rc = scan_batch_pipelined(c, order.data(), i, count, mintrav, maxtrav)) return rc;
+            c->search_batches++;
             prof.stop(0); prof.start();
             const int nc = c->plan.n_cand;
             vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
@@ -606,6 +611,13 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                         if (st->ratchet ? all : bb_passes(st, mp[j])) { call_of[(size_t)v + 1 + j] = (int32_t)pass_cands.size(); pass_cands.push_back(j); }
                 }
                 thr.resize(st->B);
+                if (st->policy == MPGPU_BB_MULHITS_TOP) {
+                    // :3540 acts on top_count < N || rell > boot_threshold and never looks at boot_logl; lists only fill up and
+                    // thresholds only rise within a batch, so the values at batch start give a safe superset
+                    for (int b = 0; b < st->B; b++)
+                        thr[b] = st->top_count[b] < st->top_n ? 2147483647
+                               : (st->boot_threshold[b] <= -2147483647 ? 2147483647 : -st->boot_threshold[b] - 1);
+                } else
                 for (int b = 0; b < st->B; b++) thr[b] = bb_screen_of(st->boot_logl[b], st->ufboot_epsilon);
                 if (int rc = reps_run(c, pass_cands.data(), (int)pass_cands.size(), thr.data(), ro)) return rc;
             }
@@ -644,6 +656,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                     randomMP = bestParsimony;
                     cur_score = bestParsimony;
                     moved = true;
+                    c->search_moves++;
                 }
             }
             i += v;
@@ -820,8 +833,17 @@ int mpgpu_stepwise_addition(mpgpu_ctx *c, int64_t *random_seed, int spr_dist, mp
     memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
     memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
     int64_t more = 0;
-    if (int rc = optimize_impl(c, back_node, back_slot, 1, spr_dist, rng, rng_user, nullptr, best, &more)) return rc;
+    if (int rc = optimize_impl(c, back_node, back_slot, 1, spr_dist, rng, rng_user, nullptr, best, &more, true)) return rc;
     if (n_insertions) *n_insertions = scored + more;
+    return 0;
+}
+
+int mpgpu_search_info(mpgpu_ctx *c, uint32_t *start_score, int64_t *moves, int64_t *batches)
+{
+    if (!c) { set_error("null argument"); return 1; }
+    if (start_score) *start_score = c->search_start_score;
+    if (moves) *moves = c->search_moves;
+    if (batches) *batches = c->search_batches;
     return 0;
 }
 

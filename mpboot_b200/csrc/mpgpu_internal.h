@@ -205,6 +205,8 @@ struct Ctx {
     mpgpu_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     bool reduces() const { return shard_count == 1 || allreduce != nullptr; }   // results are complete on this shard
     int64_t launches = 0;
+    // the last SPR search on this context (mpgpu_search_info)
+    uint32_t search_start_score = 0; int64_t search_moves = 0, search_batches = 0;
 
     // alignment
     int n = 0, P = 0, datatype = 0, S = 0, sort_alignment = 1;
