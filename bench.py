@@ -518,6 +518,11 @@ def run_reference(args):
     ncores = max(1, len(os.sched_getaffinity(0)))
     nproc = min(ncores, 64)
     budget = 6.0
+    # dlopen the reference library in THIS process before the fork, so that the driver's loaded-library record of the
+    # reference arm shows oracle/_ref/libmpref.so (the workers inherit the mapping)
+    from oracle import reflib
+    if reflib.available():
+        reflib.lib()
     with mp.get_context("fork").Pool(nproc) as pool:
         t0 = time.time()
         res = pool.starmap(_ref_worker, [(case, args.maxtrav, budget, args.steps, args.warmup)] * nproc)
@@ -537,6 +542,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": kind, "sample": sample + " per step, x%d processes" % nproc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
+        "worker_kinds": sorted(set(r[2] for r in res)),
     }
     print(json.dumps(line), flush=True)
 

@@ -499,32 +499,42 @@ template <int S> struct StateVec {
     }
 };
 
-// Scores one child: Uc = fitch(U, X) (X = sibling view), optional store of Uc, optional count.
-// ROWS: instead of counting, the mismatch bits of the insertion (the candidate's per-site
-// delta row under -bb) go to rowp[0] when rowp is not null.
-template <int S, bool ROWS>
-__device__ __forceinline__ void scan_child(const uint32_t (&U)[S], const uint32_t (&X)[S], const uint32_t (&C)[S],
-                                           const uint32_t (&Sv)[S], bool do_out, int32_t *__restrict__ outp,
+// Scores one child on the VW words this lane owns: Uc = fitch(U, X) (X = sibling view), optional store of Uc, optional
+// count.  ROWS: instead of counting, the mismatch bits of the insertion (the candidate's per-site delta row under -bb,
+// DESIGN.md section 5) go to rowp[32*j] when rowp is not null.  One REDUX and one RED per child whatever VW is.
+template <int S, bool ROWS, int VW>
+__device__ __forceinline__ void scan_child(const uint32_t (&U)[VW][S], const uint32_t (&X)[VW][S], const uint32_t (&C)[VW][S],
+                                           const uint32_t (&Sv)[VW][S], bool do_out, int32_t *__restrict__ outp,
                                            uint32_t *__restrict__ rowp,
                                            bool do_dst, uint32_t dst_addr, bool lane0)
 {
-    const uint32_t n = any_and<S>(U, X);
-    uint32_t Uc[S];
+    uint32_t Uc[VW][S];
 #pragma unroll
-    for (int k = 0; k < S; k++) Uc[k] = fitch1(U[k], X[k], n);
+    for (int j = 0; j < VW; j++) {
+        const uint32_t n = any_and<S>(U[j], X[j]);
+#pragma unroll
+        for (int k = 0; k < S; k++) Uc[j][k] = fitch1(U[j][k], X[j][k], n);
+    }
     if (do_dst) {
-        StateVec<S> sv; sv.pack(Uc);
-        sv.store_shared(dst_addr);
+#pragma unroll
+        for (int j = 0; j < VW; j++) {
+            StateVec<S> sv; sv.pack(Uc[j]);
+            sv.store_shared(dst_addr + j * (Lay<S>::G * 32 * (int)sizeof(typename VecOf<S>::T)));
+        }
     }
     if (do_out) {
-        const uint32_t m = any_and<S>(Uc, C);
-        uint32_t z = 0;
+        int pc = 0;
 #pragma unroll
-        for (int k = 0; k < S; k++) z |= fitch1(Uc[k], C[k], m) & Sv[k];
-        if (ROWS) {
-            if (rowp) *rowp = ~z;
-        } else {
-            const int cnt = __reduce_add_sync(0xffffffffu, __popc(~z));
+        for (int j = 0; j < VW; j++) {
+            const uint32_t m = any_and<S>(Uc[j], C[j]);
+            uint32_t z = 0;
+#pragma unroll
+            for (int k = 0; k < S; k++) z |= fitch1(Uc[j][k], C[j][k], m) & Sv[j][k];
+            if (ROWS) { if (rowp) rowp[32 * j] = ~z; }
+            else pc += __popc(~z);
+        }
+        if (!ROWS) {
+            const int cnt = __reduce_add_sync(0xffffffffu, pc);
             if (lane0) atomicAdd(outp, cnt);
         }
     }
@@ -534,6 +544,27 @@ __device__ __forceinline__ void scan_child(const uint32_t (&U)[S], const uint32_
 // kernel parameters at every use (it did, ~8 instructions per shared or global address)
 __device__ __forceinline__ void pin(uint32_t &x) { asm volatile("" : "+r"(x)); }
 __device__ __forceinline__ void pin(const void *&x) { asm volatile("" : "+l"(x)); }
+
+// VW site words of a view operand, one StateVec per word; word j of this lane sits 32 vectors after word j-1
+template <int S, int VW> struct WideVec {
+    typedef typename VecOf<S>::T V;
+    StateVec<S> w[VW];
+    __device__ __forceinline__ void load(const V *__restrict__ p, uint32_t gstride)
+    {
+#pragma unroll
+        for (int j = 0; j < VW; j++) w[j].load(p + 32 * j, gstride);
+    }
+    __device__ __forceinline__ void load_shared(uint32_t addr)
+    {
+#pragma unroll
+        for (int j = 0; j < VW; j++) w[j].load_shared(addr + j * (Lay<S>::G * 32 * (int)sizeof(V)));
+    }
+    __device__ __forceinline__ void unpack(uint32_t (&r)[VW][S]) const
+    {
+#pragma unroll
+        for (int j = 0; j < VW; j++) w[j].unpack(r[j]);
+    }
+};
 
 // The program arrives as two streams so that the loads of op i+1's child views can be issued
 // while op i computes without rotating whole op records through registers:
@@ -545,7 +576,10 @@ __device__ __forceinline__ void pin(const void *&x) { asm volatile("" : "+l"(x))
 // ROWS = the -bb second pass: for the candidates with row_of[candidate] >= 0 the per-site
 // mismatch row is written to rows[row_of][Wl] instead of counting (tasks = only those that
 // have such a candidate; task_ids maps the dense task index to the plan's task).
-template <int S, bool PF, bool ROWS>
+// VW = 32-word chunks per warp (1, 2 or 4; Wl is a multiple of 128 words): a lane owns word l of each of them, so the
+// control-word decode, the offs / ctl loads, the branches and the address arithmetic of an op are paid once for VW
+// chunks and a scored child costs one REDUX + one RED (r02: 66 -> ~38 warp instructions per insertion and chunk).
+template <int S, bool PF, bool ROWS, int VW>
 __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int Wl,
                            const ScanTask *__restrict__ tasks, int ntasks,
                            const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
@@ -558,37 +592,40 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned gw = blockIdx.x * (blockDim.x >> 5) + warp;
-    const unsigned nchunks = Wl / kChunkWords;
-    if (gw >= (unsigned)ntasks * nchunks) return;
-    const unsigned chunk = gw / (unsigned)ntasks;
-    unsigned ti = gw - chunk * (unsigned)ntasks;
+    const unsigned ngroups = Wl / (kChunkWords * VW);
+    if (gw >= (unsigned)ntasks * ngroups) return;
+    const unsigned cgroup = gw / (unsigned)ntasks;
+    unsigned ti = gw - cgroup * (unsigned)ntasks;
     if (ROWS) ti = (unsigned)__ldg(task_ids + ti);
     const int4 t0 = __ldg(reinterpret_cast<const int4 *>(tasks + ti));       // s_vid, d1, d2, op_begin
     const int4 t1 = __ldg(reinterpret_cast<const int4 *>(tasks + ti) + 1);   // op_end, base_out, cand_base
     const uint32_t gsv = (uint32_t)Wl;                                       // group stride in vectors
-    const void *vb_ = views + (size_t)chunk * kChunkWords + lane;
+    const void *vb_ = views + (size_t)cgroup * (kChunkWords * VW) + lane;
     pin(vb_);
     const V *vbase = static_cast<const V *>(vb_);
-    constexpr uint32_t kSlotBytes = Lay<S>::G * 32 * sizeof(V);              // [group][lane] vectors
+    constexpr uint32_t kSlotBytes = VW * Lay<S>::G * 32 * sizeof(V);         // [word j][group][lane] vectors
     uint32_t sstack = (uint32_t)__cvta_generic_to_shared(smem4) +
                       (uint32_t)warp * (uint32_t)nslots * kSlotBytes + lane * (uint32_t)sizeof(V);
     pin(sstack);
     const bool lane0 = lane == 0;
     int32_t *outc = out + t1.z;                                              // candidates of this task
     const int32_t *rowc = ROWS ? row_of + (t1.z - row_bias) : nullptr;   // cand_base counts from the base slots
-    uint32_t *rowbase = ROWS ? rows + (size_t)chunk * kChunkWords + lane : nullptr;
+    uint32_t *rowbase = ROWS ? rows + (size_t)cgroup * (kChunkWords * VW) + lane : nullptr;
 
-    uint32_t Sv[S];
+    uint32_t Sv[VW][S];
     {
-        StateVec<S> a, b, c;
+        WideVec<S, VW> a, b, c;
         a.load(vbase + (uint32_t)t0.x, gsv);
         b.load(vbase + (uint32_t)t0.y, gsv);
         c.load(vbase + (uint32_t)t0.z, gsv);
         a.unpack(Sv);
-        uint32_t d1[S], d2[S];
-        b.unpack(d1); c.unpack(d2);
         if (!ROWS) {
-            const int cnt = __reduce_add_sync(0xffffffffu, __popc(~any_and<S>(d1, d2)));
+            uint32_t d1[VW][S], d2[VW][S];
+            b.unpack(d1); c.unpack(d2);
+            int pc = 0;
+#pragma unroll
+            for (int j = 0; j < VW; j++) pc += __popc(~any_and<S>(d1[j], d2[j]));
+            const int cnt = __reduce_add_sync(0xffffffffu, pc);
             if (lane0) atomicAdd(&out[t1.y], cnt);
         }
     }
@@ -600,7 +637,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     int2 f0 = __ldg(offs + oi);
     int2 f1 = f0;
     if (oi + 1 < oe) f1 = __ldg(offs + oi + 1);
-    StateVec<S> A0, B0, A1, B1;
+    WideVec<S, VW> A0, B0, A1, B1;
     A0.load(vbase + (uint32_t)f0.x, gsv);
     B0.load(vbase + (uint32_t)f0.y, gsv);
 
@@ -615,10 +652,10 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
         const int2 cw = __ldg(ctl + oi);                                                               \
         const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;       \
         const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;                                  \
-        StateVec<S> Uv;                                                                                \
+        WideVec<S, VW> Uv;                                                                             \
         if (src < 0xfe) Uv.load_shared(sstack + src * kSlotBytes);                                     \
         else Uv.load(vbase + (uint32_t)(src == 0xff ? t0.z : t0.y), gsv);                              \
-        uint32_t U[S], A[S], B[S];                                                                     \
+        uint32_t U[VW][S], A[VW][S], B[VW][S];                                                         \
         Uv.unpack(U); AC.unpack(A); BC.unpack(B);                                                      \
         uint32_t *rp1 = nullptr, *rp2 = nullptr;                                                       \
         if (ROWS) {                                                                                    \
@@ -626,9 +663,9 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
             if (o2 != 0xffff) { const int r = __ldg(rowc + o2); if (r >= 0) rp2 = rowbase + (size_t)r * Wl; } \
         }                                                                                              \
         if (o1 != 0xffff || dst1 != 0xff)                                                              \
-            scan_child<S, ROWS>(U, B, A, Sv, o1 != 0xffff, outc + o1, rp1, dst1 != 0xff, sstack + dst1 * kSlotBytes, lane0); \
+            scan_child<S, ROWS, VW>(U, B, A, Sv, o1 != 0xffff, outc + o1, rp1, dst1 != 0xff, sstack + dst1 * kSlotBytes, lane0); \
         if (o2 != 0xffff || dst2 != 0xff)                                                              \
-            scan_child<S, ROWS>(U, A, B, Sv, o2 != 0xffff, outc + o2, rp2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0); \
+            scan_child<S, ROWS, VW>(U, A, B, Sv, o2 != 0xffff, outc + o2, rp2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0); \
     }
 
     for (;;) {
@@ -640,12 +677,12 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
 #undef MPGPU_SCAN_STEP
 }
 
-template <int S, bool ROWS>
-static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
+template <int S, bool ROWS, int VW, bool PF4 = false>
+static int launch_scan_v(Ctx *c, int task0, int ntasks, int nslots)
 {
     typedef typename VecOf<S>::T V;
-    constexpr bool PF = S <= 4;
-    const size_t per_warp = (size_t)(nslots > 0 ? nslots : 1) * Lay<S>::G * 32 * sizeof(V);
+    constexpr bool PF = S <= 4 && (VW <= 2 || PF4);
+    const size_t per_warp = (size_t)(nslots > 0 ? nslots : 1) * Lay<S>::G * 32 * sizeof(V) * VW;
     int wpb = 4;           // small CTAs: ragged task lengths retire early, measured best on B200 (profiles/)
     if (const char *e = getenv("MPGPU_SCAN_WPB")) { int v = atoi(e); if (v >= 1 && v <= 32) wpb = v; }   // tuning knob
     const size_t budget = 96 * 1024;
@@ -654,19 +691,47 @@ static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
     if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
     static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (smem > 48 * 1024 && smem > configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF, ROWS, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         configured = 200 * 1024;
     }
-    const long long warps = (long long)ntasks * (c->Wl / kChunkWords);
+    const long long warps = (long long)ntasks * (c->Wl / (kChunkWords * VW));
     const long long blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
-    k_spr_scan<S, PF, ROWS><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
+    k_spr_scan<S, PF, ROWS, VW><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
         reinterpret_cast<const V *>(c->d_views), c->Wl, c->d_tasks + (ROWS ? 0 : task0), ntasks, reinterpret_cast<const int2 *>(c->d_offs),
         reinterpret_cast<const int2 *>(c->d_ctl), nslots > 0 ? nslots : 1, c->d_counts,
         ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, c->plan.task_cap, ROWS ? c->d_rows_site : nullptr);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Chunks per warp: as wide as the grid allows while it still fills the device a few times over (a small batch of a small
+// alignment keeps one chunk per warp: there the launch is latency-bound and more warps finish sooner).
+template <int S, bool ROWS>
+static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
+{
+    int vw = 1;
+    if (S <= 4) {
+        static const int forced = getenv("MPGPU_SCAN_VW") ? atoi(getenv("MPGPU_SCAN_VW")) : 0;     // tuning knob
+        static int sms_dev[64] = {0};
+        int &sms = sms_dev[c->device & 63];
+        if (!sms) { cudaDeviceProp prop; MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device)); sms = prop.multiProcessorCount; }
+        const long long warps1 = (long long)ntasks * (c->Wl / kChunkWords);
+        const long long fill = (long long)sms * 32;                     // ~2 waves of 16 resident warps per SM
+        if (warps1 / 4 >= fill) vw = 4;
+        else if (warps1 / 2 >= fill) vw = 2;
+        if (forced == 1 || forced == 2 || forced == 4) vw = forced;
+    }
+    switch (vw) {
+    case 4: {
+        static const bool pf4 = getenv("MPGPU_SCAN_PF4") && atoi(getenv("MPGPU_SCAN_PF4")) != 0;    // tuning knob
+        if (pf4) return launch_scan_v<S, ROWS, (S <= 4 ? 4 : 1), true>(c, task0, ntasks, nslots);
+        return launch_scan_v<S, ROWS, (S <= 4 ? 4 : 1)>(c, task0, ntasks, nslots);
+    }
+    case 2:  return launch_scan_v<S, ROWS, (S <= 4 ? 2 : 1)>(c, task0, ntasks, nslots);
+    default: return launch_scan_v<S, ROWS, 1>(c, task0, ntasks, nslots);
+    }
 }
 
 // tasks [task0, task0 + ntasks) of the uploaded plan
