@@ -201,6 +201,98 @@ def bench_search(eng, case, args):
     return out
 
 
+def measured_profile(workload, kernel):
+    """ncu --set full numbers of `kernel` on `workload` (profiles/traffic.json): DRAM bytes and executed warp instructions
+    per launch -- counts taken under the profiler, never timings."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]
+    except Exception:
+        return {}
+
+
+def roofline_of(workload, world, alg_bytes, ker_s, peak, peak_src, n_cand, words):
+    """k_spr_scan is bounded by the ALU pipe (LOP3 / ISETP / SHF / IADD3 issue at one warp instruction per 2 cycles per SM
+    sub-partition, B300_MICROARCH.md "Pipe rates"): its working set is L2-resident and every view is read once per prune
+    task, so the canonical-bytes HBM figure exceeds 1 and says nothing about utilisation.  Reported: the instruction
+    roofline (ALU-pipe warp instructions per launch from the committed ncu capture / measured kernel time, against
+    SMs x 4 x 0.5 x SM clock) AND the canonical-bytes fraction the contract defines (8*S*W bytes per insertion)."""
+    hbm = {"achieved": alg_bytes / ker_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ker_s / 1e9 / peak,
+           "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes}
+    prof = measured_profile(workload, "k_spr_scan") if world == 1 else {}
+    out = {"kernel": "k_spr_scan", "kernel_ms": ker_s * 1e3, "traffic": prof.get("bytes"), "canonical_hbm": hbm}
+    alu = prof.get("alu_inst")
+    if alu:
+        try:
+            mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+        except Exception:
+            mhz = 1965.0
+        sms = 148
+        peak_alu = sms * 4 * 0.5 * mhz * 1e6 / 1e9                 # G warp-instructions/s the ALU pipes can issue
+        ach = alu / ker_s / 1e9
+        chunks = n_cand * (words // 32)
+        out.update({"bound": "alu", "achieved": ach, "peak": peak_alu, "unit": "G warp-inst/s (ALU pipe)", "frac": ach / peak_alu,
+                    "peak_source": "148 SMs x 4 sub-partitions x 0.5 inst/clk x %.0f MHz (sm_max_mhz)" % mhz,
+                    "alu_warp_inst_per_launch": alu, "warp_inst_per_launch": prof.get("inst"),
+                    "warp_inst_per_insertion_chunk": (prof.get("inst") / chunks) if prof.get("inst") else None,
+                    "profile_source": prof.get("source")})
+    else:
+        out.update({"bound": "hbm", "achieved": hbm["achieved"], "peak": peak, "unit": "GB/s", "frac": hbm["frac"], "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes})
+    return out
+
+
+BB1000_CASE = "c1_100x5000"
+
+
+def start_bb1000_stock(args):
+    """Section bb1000 (third metric of BASELINE.json: -bb 1000 wall time through the unchanged host): the unmodified
+    reference program on one host core, started now so that it runs while the GPU sections do."""
+    import subprocess as sp
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import mpboot_dropin_check as dropin
+    except Exception as e:
+        return {"unavailable": "tools/mpboot_dropin_check.py: %r" % (e,)}
+    stock, gpu = os.path.join(dropin.BIN, "mpboot-avx"), os.path.join(dropin.BIN, "mpboot-avx-gpu")
+    if not (os.path.exists(stock) and os.path.exists(gpu)):
+        return {"unavailable": "integration/_bin binaries are not built (integration/build.sh needs /root/reference)"}
+    out = os.path.join(ROOT, "gpurun_out", "bb1000")
+    os.makedirs(out, exist_ok=True)
+    aln = dropin.make_alignment(BB1000_CASE, out)
+    pre = os.path.join(out, BB1000_CASE + ".bb.stock")
+    t0 = time.time()
+    proc = sp.Popen([stock, "-s", aln, "-seed", "1", "-bb", "1000", "-pre", pre], stdout=sp.PIPE, stderr=sp.STDOUT, text=True)
+    return {"dropin": dropin, "proc": proc, "t0": t0, "aln": aln, "out": out, "stock_prefix": pre, "gpu": gpu}
+
+
+def finish_bb1000(job, args):
+    import re
+    if "unavailable" in job:
+        return job
+    dropin = job["dropin"]
+    pre = os.path.join(job["out"], BB1000_CASE + ".bb.gpu")
+    g = dropin.run_binary(job["gpu"], job["aln"], pre, ["-bb", "1000"], 1800)
+    so, _ = job["proc"].communicate(timeout=3600)
+    stock_wall = time.time() - job["t0"]
+    m = re.search(r"Wall-clock time used for tree search: ([0-9.]+) sec", so)
+    stock_search = float(m.group(1)) if m else None
+    same = {}
+    for ext in (".treefile", ".contree", ".splits.nex"):
+        try:
+            same[ext] = open(job["stock_prefix"] + ext, "rb").read() == open(pre + ext, "rb").read()
+        except OSError:
+            same[ext] = False
+    n, L = dropin.CASES[BB1000_CASE][0], dropin.CASES[BB1000_CASE][1]
+    return {"what": "mpboot -s <aln> -seed 1 -bb 1000 through the unchanged MPBoot host: integration/_bin/mpboot-avx-gpu (the reference "
+                    "program + integration/mpboot_gpu.patch + libmpgpu) against integration/_bin/mpboot-avx (the unmodified reference, "
+                    "AVX build, one core) on the same box; times are the program's own 'Wall-clock time used for tree search'",
+            "workload": "synthetic DNA %d taxa x %d sites (C1's largest fixture)" % (n, L),
+            "stock_search_wall_s": stock_search, "gpu_search_wall_s": g["search_wall_s"],
+            "speedup": (stock_search / g["search_wall_s"]) if (stock_search and g["search_wall_s"]) else None,
+            "gpu_process_wall_s": g["process_wall_s"], "stock_process_wall_s_upper_bound": stock_wall,
+            "identical_outputs": same, "best_score": g["best_score"], "gpu_stats": g["stats"], "gpu_rc": g["rc"]}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -590,10 +682,115 @@ def workload_name(name, nshards, case):
         name, {0: "BIN", 1: "DNA", 2: "AA", 6: "MORPH32"}[dt], n, case["sites"], case["sites"] // nshards)
 
 
+def measure_sweep(args, workload, scaling, steps, world, rank, local, stream, flush, want_clocks):
+    """One workload's SPR sweep on `world` GPUs: device-timed step (kernel + in-library exchange step), the kernel alone,
+    the end-to-end call with host buffers, and -- at world > 1 -- a check of every reduced insertion score against an
+    unsharded context that rank 0 builds over the whole alignment."""
+    import torch
+    import torch.distributed as dist
+    from mpboot_b200 import engine, sharded
+
+    case = build_case(workload, world, scaling)
+    n = case["n"]
+    eng = engine.Engine(device=local, stream=stream, shard_rank=rank, shard_count=world)
+    if world > 1:
+        sharded.connect_peers(eng)               # the exchange step lives in the library: one-shot all-reduce over NVLink peer memory
+    eng.load_alignment(case["codes"], case["weights"], case["datatype"])
+    eng.set_tree(case["bn"], case["bs"])
+    order = eng.visit_order()
+    nvis = 2 * n - 2
+    n_cand, n_tasks = eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
+    S, W = eng.S, eng.shard_words
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, exchange):
+        """nsteps launches bracketed by CUDA events on the library's stream; exchange = False times the scan kernel alone
+        (option "exchange" 0: the shard's partial counts stay partial)."""
+        if world > 1:
+            eng.set_option("exchange", 1 if exchange else 0)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        barrier()
+        t0 = time.time()
+        for k in range(nsteps):
+            flush.zero_()                        # L2 flush between timed iterations (outside the events)
+            ev[k][0].record()
+            eng.scan_launch()
+            ev[k][1].record()
+        barrier()
+        wall = time.time() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+            eng.set_option("exchange", 1)
+        return ms, wall
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        eng.scan_launch()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local) if want_clocks else None
+    if sampler:
+        sampler.start()
+    dev_ms, t_wall = timed(steps, True)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - launches0
+    ker_ms = timed(steps, False)[0] if world > 1 else dev_ms
+    eng.scan_plan(order, 1, nvis, 1, args.maxtrav)                     # the timed loop without exchange left partial counts behind
+    eng.scan_launch()
+    vb, mp, cref, cprune = eng.scan_finish(n_cand, nvis)
+
+    # e2e: the reference-facing call with host buffers (plan on host, H2D, kernel, exchange, D2H, finish)
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):                           # untimed warm-up of the end-to-end path (page-locked buffers)
+        eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        vb2, mp2, _, _ = eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
+    barrier()
+    e2e_s = (time.time() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+    assert np.array_equal(mp, mp2), "device-resident and end-to-end paths disagree"
+
+    check = None
+    if world > 1:
+        # every reduced score against an unsharded context over the whole alignment (rank 0), and the same vector on every rank
+        h = torch.tensor([int(np.asarray(mp, dtype=np.int64).sum() % (1 << 62)), int(len(mp))], device="cuda", dtype=torch.int64)
+        hs = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        same_on_all = all(bool((x == hs[0]).all()) for x in hs)
+        if rank == 0:
+            one = engine.Engine(device=local, stream=stream)
+            one.load_alignment(case["codes"], case["weights"], case["datatype"])
+            one.set_tree(case["bn"], case["bs"])
+            _, mp1, _, _ = one.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
+            s1 = one.tree_score()
+            one.close()
+            check = {"insertion_scores_equal_unsharded": bool(np.array_equal(mp1, mp)), "tree_score_equal_unsharded": bool(s1 == eng.tree_score()),
+                     "identical_on_all_ranks": same_on_all, "insertions_compared": int(len(mp)),
+                     "exchange_steps": int(eng.peer_stats()[0]), "exchange_timeouts": int(eng.peer_stats()[2])}
+            assert check["insertion_scores_equal_unsharded"] and check["tree_score_equal_unsharded"] and same_on_all, check
+        else:
+            eng.tree_score()                     # the collective half of rank 0's call
+    res = {"case": case, "eng": eng, "order": order, "n_cand": n_cand, "n_tasks": n_tasks, "S": S, "W": W, "nvis": nvis,
+           "sites_total": eng.n_sites, "dev_ms": dev_ms, "ker_ms": ker_ms, "e2e_s": e2e_s, "launches": launches, "clocks": clocks,
+           "wall_s": t_wall, "vb": vb, "mp": mp, "check": check, "barrier": barrier}
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mpboot_b200 import engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -607,8 +804,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    case = build_case(args.workload, world, args.scaling)
-    n = case["n"]
+    # the drop-in's -bb 1000 run (section bb1000) starts the stock binary now, on a host core, so that its minutes
+    # overlap the GPU sections below
+    bb1000_job = start_bb1000_stock(args) if (rank == 0 and world == 1 and not args.no_bb1000) else None
+
     # a real (non-default) stream shared by torch and the library, so that torch.cuda.Event
     # brackets exactly the library's launches (the legacy default stream's handle is NULL,
     # which mpgpu_create takes as "make a private stream")
@@ -616,101 +815,38 @@ def run_ours(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    eng = engine.Engine(device=local, stream=stream, shard_rank=rank, shard_count=world)
-    eng.load_alignment(case["codes"], case["weights"], case["datatype"])
-    eng.set_tree(case["bn"], case["bs"])
-    if world > 1:
-        vc = torch.from_numpy(eng.view_counts_partial().astype(np.int32)).cuda()
-        dist.all_reduce(vc)
-        eng.set_view_counts(vc.cpu().numpy().astype(np.uint32))
-    order = eng.visit_order()
-    nvis = 2 * n - 2
-    n_cand, n_tasks = eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
-    S, W = eng.S, eng.shard_words
-    sites_total = eng.n_sites
-
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
-    def step_device():
-        ptr = eng.scan_launch()
-        if world > 1:
-            t = torch.as_tensor(DevCounts(ptr, n_cand + 2 * nvis), device="cuda")
-            dist.all_reduce(t)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step_device()
-    barrier()
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.time()
-    for k in range(args.steps):
-        flush.zero_()                            # L2 flush between timed iterations (outside the events)
-        ev[k][0].record()
-        kev[k][0].record()
-        ptr = eng.scan_launch()
-        kev[k][1].record()
-        if world > 1:
-            t = torch.as_tensor(DevCounts(ptr, n_cand + 2 * nvis), device="cuda")
-            dist.all_reduce(t)
-        ev[k][1].record()
-    barrier()
-    t_wall = time.time() - t_wall0
-    clocks = sampler.stop()
-    launches = eng.launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    ker_ms = sum(a.elapsed_time(b) for a, b in kev)
-    if world > 1:
-        tt = torch.tensor([dev_ms, ker_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, ker_ms = float(tt[0]), float(tt[1])
-
-    # correctness of what was timed: finish the last step and compare with a fresh end-to-end call
-    vb, mp, cref, cprune = eng.scan_finish(n_cand, nvis) if world == 1 else (None, None, None, None)
-
-    # e2e: the reference-facing call with host buffers (plan on host, H2D, kernel, D2H, finish)
-    e2e_steps = max(3, min(args.steps, 10))
-    if world == 1:                               # untimed warm-up of the end-to-end path (page-locked buffers, helper thread)
-        for _ in range(2):
-            eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
-    barrier()
-    t0 = time.time()
-    for _ in range(e2e_steps):
-        if world == 1:
-            vb2, mp2, _, _ = eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16)
-        else:
-            eng.scan_plan(order, 1, nvis, 1, args.maxtrav)
-            ptr = eng.scan_launch()
-            t = torch.as_tensor(DevCounts(ptr, n_cand + 2 * nvis), device="cuda")
-            dist.all_reduce(t)
-            vb2, mp2, _, _ = eng.scan_finish(n_cand, nvis)
-    barrier()
-    e2e_s = (time.time() - t0) / e2e_steps
-    if world > 1:
-        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt[0])
-    if world == 1:
-        assert np.array_equal(mp, mp2), "device-resident and end-to-end paths disagree"
+    r = measure_sweep(args, args.workload, args.scaling, args.steps, world, rank, local, stream, flush, True)
+    eng, case, order, n_cand, n_tasks, S, W, nvis = r["eng"], r["case"], r["order"], r["n_cand"], r["n_tasks"], r["S"], r["W"], r["nvis"]
+    vb = r["vb"]
+    sites_total = r["sites_total"]
+    c4 = None
+    if not args.no_c4 and args.workload == "c2":
+        # north_star's scaling configuration: 1000 taxa x 1M sites, the SAME alignment sharded over the GPUs (strong)
+        r4 = measure_sweep(args, "c4", "strong", max(3, args.steps // 2), world, rank, local, stream, flush, False)
+        ops4 = 2.0 * r4["sites_total"]
+        ms4 = r4["dev_ms"] / max(3, args.steps // 2)
+        c4 = {"workload": workload_name("c4", world, r4["case"]), "scaling": "strong", "n_gpus": world,
+              "ms_per_step": ms4, "kernel_ms": r4["ker_ms"] / max(3, args.steps // 2), "insertions_per_step": r4["n_cand"],
+              "insertions_per_s": r4["n_cand"] / (ms4 * 1e-3), "value": r4["n_cand"] / (ms4 * 1e-3) * ops4, "unit": UNIT,
+              "e2e_ms_per_step": r4["e2e_s"] * 1e3, "words_per_plane_per_gpu": r4["W"],
+              "canonical_hbm_frac": 8.0 * r4["S"] * r4["W"] * r4["n_cand"] / (r4["ker_ms"] / max(3, args.steps // 2) * 1e-3) / 1e9 / measured_peak()[0],
+              "check": r4["check"],
+              "note": "speed-up over 1 GPU = this key's ms_per_step at n_gpus = 1 (same alignment) / ms_per_step here"}
+        r4["eng"].close()
+        del r4
 
     if rank == 0:
         ops_per_ins = 2.0 * sites_total
-        ms_per_step = dev_ms / args.steps
+        ms_per_step = r["dev_ms"] / args.steps
         ins_per_s = n_cand / (ms_per_step * 1e-3)
         value = ins_per_s * ops_per_ins
         peak, peak_src = measured_peak()
         alg_bytes = 8.0 * S * W * n_cand                       # canonical 8*S*W bytes per insertion (this shard)
-        ker_s = ker_ms * 1e-3 / args.steps
+        ker_s = r["ker_ms"] * 1e-3 / args.steps
         achieved = alg_bytes / ker_s / 1e9
+        e2e_s = r["e2e_s"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
@@ -719,15 +855,19 @@ def run_ours(args):
             "config": {"workload": workload_name(args.workload, world, case), "maxtrav": args.maxtrav,
                        "states": S, "words_per_plane_per_gpu": W, "prune_tasks": n_tasks, "bb": False,
                        "l2": "flushed between timed steps (256 MiB memset)",
-                       "parallelism": "pattern-sharded x%d, NCCL all-reduce of int32 counts" % world if world > 1 else "single GPU"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload, "k_spr_scan") if world == 1 else None,
-                         "kernel": "k_spr_scan", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ker_s * 1e3},
+                       "parallelism": ("pattern-sharded x%d, in-library one-shot all-reduce of the int32 counts over NVLink peer memory "
+                                       "(k_peer_allreduce, on the stream)" % world) if world > 1 else "single GPU"},
+            "roofline": roofline_of(args.workload, world, alg_bytes, ker_s, peak, peak_src, n_cand, W),
             "e2e": {"value": (n_cand / e2e_s) * ops_per_ins, "unit": UNIT, "insertions_per_s": n_cand / e2e_s,
                     "h2d_bytes_per_step": None, "d2h_bytes_per_step": 4 * (n_cand + 2 * nvis), "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
+            "gpu_launches": int(r["launches"]), "clocks": r["clocks"], "wall_s": r["wall_s"],
         }
+        if world > 1:
+            line["exchange"] = {"what": "device time of the exchange step per sweep = step - scan kernel alone (max over ranks each)",
+                                "ms_per_step": (r["dev_ms"] - r["ker_ms"]) / args.steps, "int32_per_step": n_cand + 2 * nvis,
+                                "check": r["check"]}
+        if c4:
+            line["c4_strong"] = c4
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
         if world == 1 and not args.no_search:
             line["search"] = bench_search(eng, case, args)
@@ -742,6 +882,8 @@ def run_ours(args):
             ins, dt, kind, sample = cpu_baseline(case, args.maxtrav, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": ins / dt * ops_per_ins, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": sample, "insertions_per_s": ins / dt}
+        if bb1000_job is not None:
+            line["bb1000"] = finish_bb1000(bb1000_job, args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -761,6 +903,8 @@ def main():
     ap.add_argument("--no-bb", action="store_true", help="skip the -bb (replicate scoring) section")
     ap.add_argument("--no-cost", action="store_true", help="skip the -cost (Sankoff) section")
     ap.add_argument("--no-search", action="store_true", help="skip the whole-search (pllOptimizeSprParsimony) section")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (1000 taxa x 1M sites, strong scaling) section")
+    ap.add_argument("--no-bb1000", action="store_true", help="skip the drop-in section (MPBoot -bb 1000: patched vs stock binary)")
     ap.add_argument("--replicates", type=int, default=1000)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the workload's sites per GPU (default), strong = the workload's sites in total, sharded")

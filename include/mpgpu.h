@@ -60,6 +60,22 @@ int mpgpu_destroy(mpgpu_ctx *ctx);
  * only offer the *_partial calls and the caller reduces. */
 typedef int (*mpgpu_allreduce_fn)(void *user, void *dev_buf, int64_t count, void *stream);
 int mpgpu_set_allreduce(mpgpu_ctx *ctx, mpgpu_allreduce_fn fn, void *user);
+/* The same exchange step inside the library, on the device, without NCCL and without the host: a one-shot all-reduce
+ * over NVLink peer memory (every shard stores its partial vector into every peer's exchange region, raises a flag, waits
+ * for the peers' flags and sums; one small kernel on the context's stream, peer_exchange.cu).  For the shards of one
+ * NVSwitch box (shard_count <= 8), one process per GPU:
+ *   mpgpu_peer_prepare  allocates this shard's region for vectors of up to `capacity` int32 (longer ones go in pieces)
+ *                       and returns its CUDA IPC handle (64 bytes) in handle_out;
+ *   the host gathers the handles of all shards in shard order (any transport: torch.distributed all_gather, MPI, a file);
+ *   mpgpu_peer_connect  maps the peers' regions.  From then on every call behaves as with an all-reduce callback
+ *                       installed (complete results on every shard), and the callback, if any, is no longer used.
+ * All shards must issue the same sequence of calls (they run the same replicated search anyway).  A shard whose peer
+ * does not show up within 2 s records an error (mpgpu_peer_stats) instead of hanging the device. */
+int mpgpu_peer_prepare(mpgpu_ctx *ctx, int64_t capacity, void *handle_out);
+int mpgpu_peer_connect(mpgpu_ctx *ctx, const void *handles);
+/* exchange steps issued / int32 elements reduced so far, and the device-side error flag (0 = none, 1 + q = shard q
+ * did not arrive).  Any pointer may be NULL. */
+int mpgpu_peer_stats(mpgpu_ctx *ctx, int64_t *calls, int64_t *elements, int *error);
 /* The stream all kernels are launched on (cudaStream_t). */
 void *mpgpu_stream(mpgpu_ctx *ctx);
 int mpgpu_synchronize(mpgpu_ctx *ctx);
@@ -249,7 +265,9 @@ int mpgpu_sankoff_reps_stats(mpgpu_ctx *ctx, int64_t *tensor_chunks, int64_t *ex
 
 /* Options: "sankoff_exact" 0/1 (see mpgpu_scan_bounds);
  * "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests);
- * "reps_timing" 0/1 (CUDA events around the largest tensor-kernel launch, read by mpgpu_reps_timing). */
+ * "reps_timing" 0/1 (CUDA events around the largest tensor-kernel launch, read by mpgpu_reps_timing);
+ * "exchange" 1/0 (sharded contexts: 0 skips the exchange step, so every result stays this shard's partial -- for timing the
+ * kernels without it). */
 int mpgpu_set_option(mpgpu_ctx *ctx, const char *name, int value);
 /* Device time (ms, CUDA events on the context's stream) of the largest tensor-kernel launch since the
  * last call, with its shape: rows x patterns (K, padded to 128) x replicates, and the K splits used. */

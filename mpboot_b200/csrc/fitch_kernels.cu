@@ -719,8 +719,9 @@ static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
         if (!sms) { cudaDeviceProp prop; MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device)); sms = prop.multiProcessorCount; }
         const long long warps1 = (long long)ntasks * (c->Wl / kChunkWords);
         const long long fill = (long long)sms * 32;                     // ~2 waves of 16 resident warps per SM
-        if (warps1 / 4 >= fill) vw = 4;
-        else if (warps1 / 2 >= fill) vw = 2;
+        static const int auto_max = getenv("MPGPU_SCAN_VW_MAX") ? atoi(getenv("MPGPU_SCAN_VW_MAX")) : 1;   // measured on B200 (profiles/r02*): see DESIGN.md
+        if (auto_max >= 4 && warps1 / 4 >= fill) vw = 4;
+        else if (auto_max >= 2 && warps1 / 2 >= fill) vw = 2;
         if (forced == 1 || forced == 2 || forced == 4) vw = forced;
     }
     switch (vw) {

@@ -75,7 +75,8 @@ static void free_alignment(Ctx *c)
 
 int shard_sum(Ctx *c, void *dev_i32, int64_t count)
 {
-    if (c->shard_count == 1 || count <= 0) return 0;
+    if (c->shard_count == 1 || count <= 0 || c->exchange_off) return 0;
+    if (c->peer.ready) return peer_allreduce(c, dev_i32, count);       // one kernel on the stream, NVLink peer memory
     if (!c->allreduce) { set_error("sharded context: this call needs mpgpu_set_allreduce (or use the *_partial calls)"); return 1; }
     if (c->allreduce(c->allreduce_user, dev_i32, count, (void *)c->stream)) { set_error("the all-reduce callback failed"); return 1; }
     return 0;
@@ -101,19 +102,25 @@ static int build_planes(Ctx *c, bool realloc_views)
     int64_t glob = (words + quantum - 1) / quantum * quantum;
     if (glob == 0) glob = quantum;
     const int newWl = (int)(glob / c->shard_count);
-    (void)realloc_views;
     c->glob_words = (int)glob; c->Wl = newWl; c->w0 = (int64_t)c->shard_rank * newWl;
     {
         const int SG = c->S < 4 ? c->S : 4, G = (c->S + SG - 1) / SG;
         c->view_stride = (size_t)G * SG * c->Wl;      // state-interleaved groups, see fitch_kernels.cu
     }
 
-    if (c->d_site_start) { cudaFree(c->d_site_start); c->d_site_start = nullptr; }
-    if (c->d_inf_ptn) { cudaFree(c->d_inf_ptn); c->d_inf_ptn = nullptr; }
-    MPGPU_CUDA(cudaMalloc((void **)&c->d_site_start, sizeof(int64_t) * (c->n_inf + 1)));
-    MPGPU_CUDA(cudaMalloc((void **)&c->d_inf_ptn, sizeof(int32_t) * inf_ptn.size()));
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_site_start, site_start.data(), sizeof(int64_t) * (c->n_inf + 1), cudaMemcpyHostToDevice, c->stream));
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_inf_ptn, inf_ptn.data(), sizeof(int32_t) * inf_ptn.size(), cudaMemcpyHostToDevice, c->stream));
+    // the staging buffer is page-locked and owned by the context: wait for the previous upload from it (normally long
+    // finished), then nothing below has to be waited for -- re-weighting (ratchet, replicates) is a copy and a launch
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    if (!c->site_pin.reserve((size_t)c->n_inf + 1)) { set_error("pinned allocation failed"); return 1; }
+    memcpy(c->site_pin.data(), site_start.data(), sizeof(int64_t) * (c->n_inf + 1));
+    if (realloc_views || !c->d_site_start || !c->d_inf_ptn) {
+        if (c->d_site_start) { cudaFree(c->d_site_start); c->d_site_start = nullptr; }
+        if (c->d_inf_ptn) { cudaFree(c->d_inf_ptn); c->d_inf_ptn = nullptr; }
+        MPGPU_CUDA(cudaMalloc((void **)&c->d_site_start, sizeof(int64_t) * (c->n_inf + 1)));
+        MPGPU_CUDA(cudaMalloc((void **)&c->d_inf_ptn, sizeof(int32_t) * inf_ptn.size()));
+        MPGPU_CUDA(cudaMemcpy(c->d_inf_ptn, inf_ptn.data(), sizeof(int32_t) * inf_ptn.size(), cudaMemcpyHostToDevice));   // informative patterns depend on the codes only
+    }
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_site_start, c->site_pin.data(), sizeof(int64_t) * (c->n_inf + 1), cudaMemcpyHostToDevice, c->stream));
 
     const size_t nviews = (size_t)(4 * c->n - 6);
     const size_t need = nviews * c->view_stride;
@@ -122,12 +129,11 @@ static int build_planes(Ctx *c, bool realloc_views)
         if (c->d_vcount) cudaFree(c->d_vcount);
         c->d_views = nullptr; c->d_vcount = nullptr; c->views_alloc = 0;
         MPGPU_CUDA(cudaMalloc((void **)&c->d_views, need * sizeof(uint32_t)));
-        MPGPU_CUDA(cudaMalloc((void **)&c->d_vcount, nviews * sizeof(uint32_t)));
+        MPGPU_CUDA(cudaMalloc((void **)&c->d_vcount, (nviews + 4) * sizeof(uint32_t)));     // + slack: the peer exchange moves whole int4
         c->views_alloc = need;
     }
     if (c->n_inf > 0) { if (int rc = launch_compress(c)) return rc; }
     else MPGPU_CUDA(cudaMemsetAsync(c->d_views, 0xff, (size_t)c->n * c->view_stride * sizeof(uint32_t), c->stream));
-    MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // host staging vectors go out of scope
     c->lens_valid = false;
     c->kids_valid = false;
     c->ptn_site_valid = false;
@@ -177,10 +183,12 @@ static void build_schedule(Ctx *c)
 static inline int2 kid_pair(const Triple &tr) { return tr.a < tr.b ? make_int2(tr.a, tr.b) : make_int2(tr.b, tr.a); }
 
 // all directed views of c->tree: level schedule + one launch per level (throughput path)
-int compute_views(Ctx *c)
+int compute_views(Ctx *c, bool want_start_edge)
 {
     const int nviews = 4 * c->n - 6;
     c->wave_pending = 0;
+    c->views_stale = false;
+    c->start_edge_valid = false;
     build_schedule(c);
     const size_t total = c->sched.size();
     const int nl = c->sched_levels;
@@ -199,10 +207,20 @@ int compute_views(Ctx *c)
     else for (int l = 1; l <= nl; l++)
         if (int rc = launch_level(c, c->d_triples + start[l], start[l + 1] - start[l])) return rc;
     c->reps.tree_valid = false;
-    if (c->shard_count > 1 && c->allreduce) { if (int rc = shard_sum(c, c->d_vcount, nviews)) return rc; }
-    c->vcount.assign(nviews, 0);
-    MPGPU_CUDA(cudaMemcpyAsync(c->vcount.data(), c->d_vcount, nviews * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (c->shard_count > 1 && c->reduces()) { if (int rc = shard_sum(c, c->d_vcount, nviews)) return rc; }
+    // the mismatch count across the edge at tip 1 (evaluateParsimony at tr->start, :3277) rides along with the counts
+    const bool edge = want_start_edge && !c->sk.on && c->reduces();
+    if (edge) {
+        MPGPU_CUDA(cudaMemsetAsync(c->d_scalar, 0, sizeof(uint32_t), c->stream));
+        if (int rc = launch_edge_mismatch(c, c->tree.vid(3), c->tree.vid(c->tree.back(3)), c->d_scalar)) return rc;
+        if (int rc = shard_sum(c, c->d_scalar, 1)) return rc;
+    }
+    if (!c->vcount_pin.reserve((size_t)nviews + 1)) { set_error("pinned allocation failed"); return 1; }
+    MPGPU_CUDA(cudaMemcpyAsync(c->vcount_pin.data(), c->d_vcount, nviews * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (edge) MPGPU_CUDA(cudaMemcpyAsync(c->vcount_pin.data() + nviews, c->d_scalar, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->vcount.assign(c->vcount_pin.data(), c->vcount_pin.data() + nviews);
+    if (edge) { c->start_edge_mis = c->vcount_pin.data()[nviews]; c->start_edge_valid = true; }
     c->view_kids.assign(nviews, make_int2(-1, -1));
     for (const Triple &tr : c->sched) c->view_kids[tr.dst] = kid_pair(tr);
     c->kids_valid = true;
@@ -220,7 +238,7 @@ int update_views(Ctx *c, bool defer)
     const int nviews = 4 * c->n - 6;
     c->wave_pending = 0;
     if (!c->kids_valid || (int)c->view_kids.size() != nviews || (int)c->vcount.size() != nviews ||
-        (c->shard_count > 1 && !c->allreduce) || getenv("MPGPU_NO_WAVE"))
+        (c->shard_count > 1 && !c->reduces()) || getenv("MPGPU_NO_WAVE"))
         return compute_views(c);
     static const bool prof = getenv("MPGPU_PROFILE") != nullptr;
     static double t_host = 0, t_dev = 0; static long n_calls = 0, n_triples = 0, n_levels = 0;
@@ -328,6 +346,11 @@ int need_tree(Ctx *c, bool lens)
     if (!c) { set_error("null context"); return 1; }
     if (!c->d_views) { set_error("no alignment loaded"); return 1; }
     if (!c->tree_set) { set_error("no tree set"); return 1; }
+    if (c->views_stale) {                   // the planes were re-weighted under this tree (mpgpu_set_weights / mpgpu_set_cost_matrix)
+        if (cudaSetDevice(c->device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+        if (int rc = compute_views(c)) return rc;
+        if (c->reduces()) compute_lengths(c);
+    }
     if (lens && !c->lens_valid) { set_error("view lengths not set (sharded context: call mpgpu_set_view_counts)"); return 1; }
     return 0;
 }
@@ -373,7 +396,7 @@ int run_scan(Ctx *c)
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
     MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, (nout + 1) * sizeof(int32_t), c->stream));
     if (int rc = launch_scan(c, 0, (int)pl.tasks.size(), pl.max_slot)) return rc;
-    if (c->shard_count > 1 && c->allreduce) return shard_sum(c, c->d_counts, (int64_t)nout);
+    if (c->shard_count > 1 && c->reduces()) return shard_sum(c, c->d_counts, (int64_t)nout);
     return 0;
 }
 
@@ -440,7 +463,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         if (v0 >= count) break;
     }
     planner.finish();
-    if (c->shard_count > 1 && c->allreduce) return shard_sum(c, c->d_counts, (int64_t)pl.task_cap + pl.n_cand);
+    if (c->shard_count > 1 && c->reduces()) return shard_sum(c, c->d_counts, (int64_t)pl.task_cap + pl.n_cand);
     return 0;
 }
 
@@ -555,6 +578,7 @@ int mpgpu_destroy(mpgpu_ctx *c)
     if (c->d_ptn) cudaFree(c->d_ptn);
     if (c->d_ptn_site) cudaFree(c->d_ptn_site);
     free_reps(c);
+    peer_free(c);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -606,10 +630,7 @@ int mpgpu_set_weights(mpgpu_ctx *c, const int32_t *aliaswgt)
     for (int i = 0; i < c->P; i++) if (aliaswgt[i] < 0) { set_error("negative pattern weight"); return 1; }
     c->weights.assign(aliaswgt, aliaswgt + c->P);
     if (int rc = build_planes(c, false)) return rc;
-    if (c->tree_set) {                      // views depend on the planes
-        if (int rc = compute_views(c)) return rc;
-        if (c->reduces()) compute_lengths(c);
-    }
+    if (c->tree_set) { c->views_stale = true; c->lens_valid = false; c->kids_valid = false; }   // views depend on the planes: recomputed on first use
     return 0;
 }
 
@@ -649,6 +670,16 @@ int mpgpu_get_tip_planes(mpgpu_ctx *c, int tip, uint32_t *out)
 
 int mpgpu_set_tree(mpgpu_ctx *c, const int32_t *back_node, const int32_t *back_slot)
 {
+    return mpgpu::set_tree_impl(c, back_node, back_slot, false);
+}
+
+}  // extern "C"
+
+namespace mpgpu {
+// mpgpu_set_tree; want_start_edge = also bring back the mismatch count across the edge at tip 1 with the view counts, so
+// that the score of the tree (evaluateParsimony at tr->start) costs no second round trip (start_edge_mis / start_edge_valid)
+int set_tree_impl(Ctx *c, const int32_t *back_node, const int32_t *back_slot, bool want_start_edge)
+{
     if (!c || !back_node || !back_slot) { set_error("null argument"); return 1; }
     if (!c->d_views) { set_error("no alignment loaded"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
@@ -687,10 +718,13 @@ int mpgpu_set_tree(mpgpu_ctx *c, const int32_t *back_node, const int32_t *back_s
     if (bad) { c->tree_set = false; c->lens_valid = false; c->kids_valid = false; set_error(bad); return 1; }
     c->tree.n = n; c->tree.bn.swap(t.bn); c->tree.bs.swap(t.bs);
     c->tree_set = true; c->lens_valid = false;
-    if (int rc = compute_views(c)) return rc;
+    if (int rc = compute_views(c, want_start_edge)) return rc;
     if (c->reduces()) compute_lengths(c);
     return 0;
 }
+}  // namespace mpgpu
+
+extern "C" {
 
 int mpgpu_get_view_counts_partial(mpgpu_ctx *c, uint32_t *counts)
 {
@@ -754,7 +788,7 @@ int mpgpu_tree_score(mpgpu_ctx *c, uint32_t *score)
     if (int rc = need_tree(c, c && c->reduces())) return rc;
     if (c->sk.on) { MPGPU_CUDA(cudaSetDevice(c->device)); return sk_tree_score(c, 3, score); }
     uint32_t mis = 0;
-    if (int rc = edge_mismatch(c, 1, 0, &mis, c->shard_count > 1 && c->allreduce)) return rc;
+    if (int rc = edge_mismatch(c, 1, 0, &mis, c->shard_count > 1 && c->reduces())) return rc;
     if (c->reduces()) *score = mis + c->vlen[c->tree.vid(c->tree.back(3))];
     else *score = mis;
     return 0;
@@ -772,7 +806,7 @@ int mpgpu_pattern_parsimony(mpgpu_ctx *c, uint16_t *ptn_pars, int32_t *sum)
     const int upper = c->sort_alignment ? c->n_inf : c->P;                // :3380-3381
     if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)upper + 2)) return rc;
     if (int rc = launch_gather_patterns(c, nbits, upper)) return rc;
-    if (c->shard_count > 1 && c->allreduce) {
+    if (c->shard_count > 1 && c->reduces()) {
         // every pattern is non-zero on exactly one shard: summing u16 pairs as int32 cannot carry
         MPGPU_CUDA(cudaMemsetAsync(c->d_ptn + upper, 0, 2 * sizeof(uint16_t), c->stream));
         if (int rc = shard_sum(c, c->d_ptn, (upper + 1) / 2)) return rc;

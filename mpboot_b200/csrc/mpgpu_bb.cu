@@ -545,7 +545,15 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     if (!c->reduces()) { set_error("the SPR search on a sharded context needs mpgpu_set_allreduce"); return 1; }
     if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
     if (bb && c->sk.on != c->reps.loaded_sankoff) { set_error("the replicates were loaded for the other scoring mode: call mpgpu_load_replicates after mpgpu_set_cost_matrix"); return 1; }
-    if (int rc = mpgpu_set_tree(c, back_node, back_slot)) return rc;
+    // MPGPU_PROFILE=1: host-side section times per search; MPGPU_PROFILE=2: accumulated over the process, printed at exit
+    static const bool cumulative = getenv("MPGPU_PROFILE") && atoi(getenv("MPGPU_PROFILE")) >= 2;
+    static Prof g_sp;
+    Prof local_prof;
+    Prof &prof = cumulative ? g_sp : local_prof;
+    static const char *const prof_names[] = {"plan+launch", "scan wait", "reps", "replay", "views", "set_tree"};
+    prof.start();
+    if (int rc = set_tree_impl(c, back_node, back_slot, true)) return rc;
+    prof.stop(5);
     // -cost, plain mode: evaluateSankoff... leaves early when a prefix of segment sums plus the remainder bound
     // exceeds tr->bestParsimony (:951-956); its return value is then > best, i.e. the insertion changes nothing
     // (-bb runs with perSiteScores: no early exit; neither do the SPR rounds of the stepwise-addition tree, where the
@@ -553,7 +561,8 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1 && !bb && !stepwise_on;
     const int n = c->n, nvisit = 2 * n - 2;
     uint32_t score = 0;
-    if (int rc = mpgpu_tree_score(c, &score)) return rc;          // :3277
+    if (c->start_edge_valid) score = c->start_edge_mis + c->vlen[c->tree.vid(c->tree.back(3))];   // :3277, read back with the view counts
+    else if (int rc = mpgpu_tree_score(c, &score)) return rc;
     uint32_t bestParsimony = score;
     c->search_start_score = score; c->search_moves = 0; c->search_batches = 0;
     uint32_t randomMP = bestParsimony, startMP = 0;
@@ -570,22 +579,32 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
         if (!bb->st->ratchet_pattern_pars) { set_error("ratchet iteration: ratchet_pattern_pars is null"); return 1; }
         ratchet_stale = segmented_u16_dot(bb->st->ratchet_pattern_pars, c->reps.original_sample.data(), c->reps.seg_upper, c->reps.upper);
     }
-    Prof prof;
-    static const char *const prof_names[] = {"plan+launch", "scan wait", "reps", "replay", "views", "moves"};
-    double move_gap = 8.0;
-    auto after_move_batch = [](double gap) {
+    // Speculation depth: visits planned and scored per batch.  Everything after the first accepted move of a batch is
+    // thrown away, so right after a move the batch follows the recent distance between moves (x2); while no move happens
+    // it grows fourfold.  The distance is remembered across searches (refinement and ratchet searches start near an
+    // optimum: whole passes in one batch).  The ceiling keeps the thrown-away kernel time of one batch near 25 us
+    // (~9 G scored chunk-insertions/s, ~36 insertions per visit).  Only wasted work depends on any of this, never a result.
+    double &move_gap = c->move_gap;
+    const int spec_cap = [&]() {
+        const double units_per_visit = 36.0 * (double)(c->Wl / kChunkWords) * (c->S <= 4 ? 1.0 : c->S / 4.0);
+        double v = 25e-6 * 9e9 / units_per_visit;
+        if (bb) {                               // under -bb the batch's candidates also go through the replicate contraction
+            const double vb = 25e-6 * 2.5e15 / (2.0 * 36.0 * (double)std::max(1, c->reps.upper) * (double)std::max(1, c->reps.B));
+            if (vb < v) v = vb;
+        }
+        return v > (double)nvisit ? nvisit : (v < 16.0 ? 16 : (int)v);
+    }();
+    int since_move = 0;
+    auto after_move_batch = [spec_cap](double gap) {
         static const int fixed = getenv("MPGPU_SEARCH_BATCH") ? atoi(getenv("MPGPU_SEARCH_BATCH")) : 0;   // tuning knob
         if (fixed > 0) return fixed;
         const int b = (int)(2.0 * gap) + 1;
-        return b < 2 ? 2 : (b > 16 ? 16 : b);
+        return b < 2 ? 2 : (b > spec_cap ? spec_cap : b);
     };
     do {
         startMP = randomMP;
         visit_order(c->tree, order);                              // nodeRectifierPars :3297
         int i = 1;
-        // Speculation depth: visits planned and scored per batch.  Everything after the first accepted move of a batch is
-        // thrown away, so right after a move the batch follows the recent distance between moves (x2, within [2, 16]);
-        // while no move happens it doubles.  Only the amount of wasted work depends on it, never a result.
         int batch = after_move_batch(move_gap);
         while (i <= nvisit) {
             int count = std::min(batch, nvisit - i + 1);
@@ -668,18 +687,26 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 c->tree_set = true; c->lens_valid = false;
                 if (int rc = update_views(c, true)) return rc;
                 if (!c->wave_pending) compute_lengths(c);
-                move_gap = 0.75 * move_gap + 0.25 * (double)v;          // v = visits consumed by this batch (the last one moved)
+                move_gap = 0.75 * move_gap + 0.25 * (double)(since_move + v);   // visits since the previous move
+                since_move = 0;
                 batch = after_move_batch(move_gap);
                 prof.stop(4);
             } else {
-                batch = std::min(batch * 2, nvisit);
+                since_move += v;
+                batch = std::min(batch * 4, nvisit);
             }
         }
     } while (randomMP < startMP);
+    if ((double)since_move > move_gap) move_gap = 0.75 * move_gap + 0.25 * (double)since_move;   // a quiet search: speculate deeper next time
     if (c->wave_pending) { MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, true); }
-    prof.report(prof_names, 5);
-    g_rp.report(g_rp_names, 8);
-    for (int k = 0; k < 8; k++) { g_rp.t[k] = 0; g_rp.n[k] = 0; }
+    if (cumulative) {
+        static bool registered = false;
+        if (!registered) { registered = true; atexit([]() { g_sp.report(prof_names, 6); g_rp.report(g_rp_names, 8); }); }
+    } else {
+        prof.report(prof_names, 6);
+        g_rp.report(g_rp_names, 8);
+        for (int k = 0; k < 8; k++) { g_rp.t[k] = 0; g_rp.n[k] = 0; }
+    }
     memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
     memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
     *best = startMP;
@@ -909,6 +936,7 @@ int mpgpu_set_option(mpgpu_ctx *c, const char *name, int value)
         return 0;
     }
     if (!strcmp(name, "sankoff_exact")) { c->sk.exact = value != 0; return 0; }
+    if (!strcmp(name, "exchange")) { c->exchange_off = value == 0; return 0; }
     if (!strcmp(name, "reps_timing")) { c->reps.timing = value != 0; c->reps.timed_rows = 0; return 0; }
     set_error(std::string("unknown option: ") + name);
     return 1;
@@ -980,7 +1008,7 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     MPGPU_CUDA(cudaMalloc((void **)&r.d_w8, (size_t)r.Bpad * r.Kpad));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_w16T, (size_t)std::max(r.upper, 1) * r.Bpad * sizeof(uint16_t)));
     MPGPU_CUDA(cudaMalloc((void **)&r.d_seg_upper, (size_t)nseg_ * 4));
-    MPGPU_CUDA(cudaMalloc((void **)&r.d_segmax, (size_t)nseg_ * 4));
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_segmax, ((size_t)nseg_ + 4) * 4));      // + slack: the peer exchange moves whole int4
     MPGPU_CUDA(cudaMalloc((void **)&d_boot16, (size_t)r.B * stride * sizeof(uint16_t)));
     MPGPU_CUDA(cudaMalloc((void **)&d_heavy, r.heavy.size()));
     MPGPU_CUDA(cudaMemcpyAsync(r.d_seg_upper, segment_upper, (size_t)nseg_ * 4, cudaMemcpyHostToDevice, c->stream));

@@ -197,13 +197,31 @@ struct Sankoff {
     std::vector<uint32_t> h_est;          // per candidate of the last scan: max_seg(prefix + lb); > bestParsimony <=> the reference exits early
 };
 
+// ---- exchange step of sharded contexts over NVLink peer memory (peer_exchange.cu) -------------------
+static const int kMaxPeers = 8;           // shards of one NVSwitch box
+static const int kPeerBlocks = 32;        // CTAs of the one-shot all-reduce (one flag per block, rank and parity)
+struct PeerExchange {
+    bool ready = false;
+    void *region = nullptr; size_t bytes = 0;      // this rank's slots[2][R][cap] int32 + flags[2][R][kPeerBlocks] u32
+    size_t cap = 0;                                // ints per slot
+    void *mapped[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // IPC mappings of the peers' regions
+    int32_t *slots[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t *flags[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t epoch = 0;
+    int *d_err = nullptr;                          // set by a block whose peer never arrived (bounded spin)
+    int32_t *d_tmp = nullptr; size_t tmp_cap = 0;  // aligned scratch for vectors that are not whole int4
+    int64_t calls = 0, elements = 0;
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int shard_rank = 0, shard_count = 1;
     mpgpu_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
-    bool reduces() const { return shard_count == 1 || allreduce != nullptr; }   // results are complete on this shard
+    PeerExchange peer;
+    bool exchange_off = false;            // option "exchange" 0: shard_sum is skipped (timing the kernels alone; results stay partial)
+    bool reduces() const { return shard_count == 1 || allreduce != nullptr || peer.ready; }   // results are complete on this shard
     int64_t launches = 0;
     // the last SPR search on this context (mpgpu_search_info)
     uint32_t search_start_score = 0; int64_t search_moves = 0, search_batches = 0;
@@ -222,6 +240,7 @@ struct Ctx {
     uint8_t *d_codes = nullptr;           // [n][P]
     int64_t *d_site_start = nullptr;      // [n_inf+1] first expanded site of informative pattern k
     int32_t *d_inf_ptn = nullptr;         // [n_inf] pattern index of informative pattern k
+    PinnedArray<int64_t> site_pin;        // upload staging of d_site_start (re-weighting: no allocation, no wait)
 
     // views
     uint32_t *d_views = nullptr;          // [4n-6][S][Wl]
@@ -231,6 +250,10 @@ struct Ctx {
     std::vector<uint32_t> vcount;         // host copy (all-reduced when sharded)
     std::vector<uint32_t> vlen;           // subtree length of each view
     bool tree_set = false, lens_valid = false;
+    bool views_stale = false;             // the planes changed under a resident tree: views are recomputed on first use (need_tree)
+    uint32_t start_edge_mis = 0; bool start_edge_valid = false;   // mismatch count across the edge at tip 1, read back with the view counts
+    PinnedArray<uint32_t> vcount_pin;     // read-back staging of compute_views
+    double move_gap = 8.0;                // SPR search: recent distance (node visits) between applied moves, kept across searches
     HostTree tree;
     std::vector<Triple> sched;            // every inner view once, children before parents; pad = dependency level (1-based)
     int sched_levels = 0;
@@ -289,8 +312,11 @@ static inline int ensure(T *&ptr, size_t &cap, size_t need)
 }
 
 // ---- shared host helpers (mpgpu_api.cu) -----------------------------------------------------
+void peer_free(Ctx *c);
+int peer_allreduce(Ctx *c, void *dev_i32, int64_t count);
 int shard_sum(Ctx *c, void *dev_i32, int64_t count);   // in-place int32 all-reduce over the shards (no-op for one shard)
-int compute_views(Ctx *c);
+int compute_views(Ctx *c, bool want_start_edge = false);
+int set_tree_impl(Ctx *c, const int32_t *back_node, const int32_t *back_slot, bool want_start_edge);
 int update_views(Ctx *c, bool defer = false);   // after apply_spr_move on c->tree: recompute only the stale views, one launch
 void settle_views(Ctx *c, bool lengths);        // after a stream synchronize: land the counts of a deferred update_views
 void compute_lengths(Ctx *c);

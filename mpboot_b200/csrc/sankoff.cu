@@ -677,7 +677,7 @@ int sk_build(Ctx *c)
     Sankoff &k = c->sk;
     const int S = c->S, n = c->n, ninf = c->n_inf;
     const int G = c->shard_count;
-    if (G > 1 && !c->allreduce) { set_error("-cost on a sharded context needs mpgpu_set_allreduce (install it before mpgpu_set_cost_matrix)"); return 1; }
+    if (G > 1 && !c->reduces()) { set_error("-cost on a sharded context needs mpgpu_set_allreduce (install it before mpgpu_set_cost_matrix)"); return 1; }
     if ((int64_t)(n + 1) * k.highest > 65535) {
         set_error("cost matrix too large for this many taxa: (ntaxa+1)*(max cost+1) must stay below 65536 (a u16 of the reference could wrap)");
         return 1;

@@ -97,7 +97,10 @@ struct Builder {
         }
         const Ref &rx = ref_[x];
         if (!rx.tip && (--maxtrav > 0)) {
-            const int slot = 2 * (depth - 1) + which;           // U_x goes here
+            // U_x goes here.  The first child is expanded by the very next op, which reads its up-view before it writes
+            // anything, so first children only need two slots, alternating with the depth (never the slot the op itself
+            // reads); a second child waits for the first child's whole subtree and gets the slot of its depth.
+            const int slot = which == 0 ? (depth & 1) : 1 + depth;
             meta = which == 0 ? ((meta & ~0xFF00u) | ((uint32_t)slot << 8)) : ((meta & ~0xFF0000u) | ((uint32_t)slot << 16));
             if (slot + 1 > max_slot) max_slot = slot + 1;
             expand(rx.c1, rx.c2, (uint32_t)slot, mintrav, maxtrav, depth + 1);

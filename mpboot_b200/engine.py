@@ -34,6 +34,10 @@ def lib():
     L.mpgpu_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32]
     L.mpgpu_destroy.argtypes = [vp]
     L.mpgpu_set_allreduce.argtypes = [vp, vp, vp]
+    L.mpgpu_peer_prepare.argtypes = [vp, i64, vp]
+    L.mpgpu_peer_connect.argtypes = [vp, vp]
+    L.mpgpu_peer_stats.argtypes = [vp, vp, vp, vp]
+    L.mpgpu_search_info.argtypes = [vp, vp, vp, vp]
     L.mpgpu_stream.restype = vp
     L.mpgpu_stream.argtypes = [vp]
     L.mpgpu_synchronize.argtypes = [vp]
@@ -193,6 +197,30 @@ class Engine:
         """callback: a ctypes function object of type mpgpu_allreduce_fn (see mpboot_b200.sharded)."""
         self._allreduce_cb = callback                    # keep it alive
         self._ck(self.L.mpgpu_set_allreduce(self.h, C.cast(callback, C.c_void_p), None))
+
+    def peer_prepare(self, capacity=1 << 16):
+        """mpgpu_peer_prepare: this shard's exchange region for vectors of up to `capacity` int32; returns its CUDA IPC
+        handle (64 bytes) for the other shards."""
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self.L.mpgpu_peer_prepare(self.h, int(capacity), _p(h)))
+        return h
+
+    def peer_connect(self, handles):
+        """mpgpu_peer_connect: handles = uint8 [shard_count][64], the IPC handles of all shards in shard order."""
+        h = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert h.shape == (self.shard_count, 64)
+        self._ck(self.L.mpgpu_peer_connect(self.h, _p(h)))
+
+    def peer_stats(self):
+        calls, elems, err = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        self._ck(self.L.mpgpu_peer_stats(self.h, C.byref(calls), C.byref(elems), C.byref(err)))
+        return calls.value, elems.value, err.value
+
+    def search_info(self):
+        """(score of the start tree, moves applied, scan batches) of the last SPR search on this context."""
+        s, m, b = C.c_uint32(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.mpgpu_search_info(self.h, C.byref(s), C.byref(m), C.byref(b)))
+        return s.value, m.value, b.value
 
     def _ck(self, rc):
         if rc:

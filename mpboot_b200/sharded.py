@@ -58,14 +58,35 @@ def make_allreduce(group=None, device="cuda"):
     return ALLREDUCE_FN(_cb), stats
 
 
-def sharded_engine(device, stream=None, group=None):
-    """An Engine holding this rank's word slice, with the NCCL all-reduce installed: every call
-    then returns complete results on every rank."""
+def connect_peers(eng, group=None, capacity=1 << 16):
+    """The exchange step inside the library (mpgpu_peer_prepare / mpgpu_peer_connect): every rank exports the CUDA IPC
+    handle of its exchange region, the handles travel once over torch.distributed, and from then on the library sums its
+    count vectors itself with a one-shot all-reduce kernel over NVLink peer memory -- no NCCL launch, no host callback."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.from_numpy(eng.peer_prepare(capacity).copy())
+    if dist.get_backend(group) == "nccl":
+        mine = mine.cuda()
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    eng.peer_connect(np.stack([h.cpu().numpy() for h in allh]))
+    dist.barrier(group=group)                   # every rank has mapped every region before anyone pushes into one
+
+
+def sharded_engine(device, stream=None, group=None, exchange="nccl"):
+    """An Engine holding this rank's word slice with its exchange step installed: every call then returns complete
+    results on every rank.  exchange = "nccl": the all-reduce callback over torch.distributed; "peer": the library's own
+    one-shot all-reduce over NVLink peer memory (one NVSwitch box, one process per GPU)."""
     import torch.distributed as dist
     from . import engine
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     eng = engine.Engine(device=device, stream=stream, shard_rank=rank, shard_count=world)
-    cb, stats = make_allreduce(group)
-    eng.set_allreduce(cb)
-    eng.allreduce_stats = stats
+    if exchange == "peer":
+        connect_peers(eng, group)
+        eng.allreduce_stats = None
+    else:
+        cb, stats = make_allreduce(group)
+        eng.set_allreduce(cb)
+        eng.allreduce_stats = stats
     return eng

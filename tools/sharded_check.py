@@ -35,8 +35,10 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     st = torch.cuda.Stream(); torch.cuda.set_stream(st)
     ok = True
+    exchanges = os.environ.get("SHARDED_EXCHANGE", "peer,nccl").split(",")
     # (n, sites, datatype, seed, compress patterns?)  -- with and without site == pattern identity
-    for (n, L, dt, seed, compress) in [(40, 9000, 1, 11, False), (24, 6000, 2, 5, True), (64, 20000, 1, 41, True), (20, 5000, 6, 9, False)]:
+    for exchange, (n, L, dt, seed, compress) in [(x, cs) for x in exchanges for cs in
+                                                 [(40, 9000, 1, 11, False), (24, 6000, 2, 5, True), (64, 20000, 1, 41, True), (20, 5000, 6, 9, False)]]:
         c = make_case(n, L, dt, seed)
         if not compress:
             from mpboot_b200 import hostprep, synth
@@ -44,7 +46,7 @@ def main():
             prep = hostprep.prepare(chars, dt, compress=False)
             c.update(chars=prep["chars"], codes=prep["codes"], weights=prep["weights"], n_inf=prep["n_inf"])
         one = engine.Engine(device=local, stream=st.cuda_stream)
-        sh = sharded.sharded_engine(local, stream=st.cuda_stream)
+        sh = sharded.sharded_engine(local, stream=st.cuda_stream, exchange=exchange)
         for e in (one, sh):
             e.load_alignment(c["codes"], c["weights"], dt)
             e.set_tree(c["bn"], c["bs"])
@@ -86,7 +88,7 @@ def main():
         cost = rng.integers(1, 5, size=(S, S)); cost = np.minimum(cost, cost.T); np.fill_diagonal(cost, 0)
         cseg = np.array([x for x in range(160, ninf, 160)] + [ninf], dtype=np.int32)
         one2 = engine.Engine(device=local, stream=st.cuda_stream)
-        sh2 = sharded.sharded_engine(local, stream=st.cuda_stream)
+        sh2 = sharded.sharded_engine(local, stream=st.cuda_stream, exchange=exchange)
         for e in (one2, sh2):
             e.load_alignment(c["codes"], c["weights"], dt)
             e.set_cost_matrix(cost, cseg)
@@ -117,8 +119,12 @@ def main():
         if rank == 0:
             print("   -cost: sharded x%d == unsharded (score %d, %d insertions, searches in both modes, RAS score %d)" % (world, cs1, len(ac[1]), x[0]), flush=True)
         if rank == 0:
-            print("case n=%d L=%d dt=%d identity=%s: sharded x%d == unsharded (score %d, %d insertions, %d all-reduces, %d int32)"
-                  % (n, L, dt, not compress, world, s1, len(a[1]), sh.allreduce_stats["calls"], sh.allreduce_stats["elements"]), flush=True)
+            calls, elems = (sh.allreduce_stats["calls"], sh.allreduce_stats["elements"]) if sh.allreduce_stats else sh.peer_stats()[:2]
+            print("[%s] case n=%d L=%d dt=%d identity=%s: sharded x%d == unsharded (score %d, %d insertions, %d exchange steps, %d int32)"
+                  % (exchange, n, L, dt, not compress, world, s1, len(a[1]), calls, elems), flush=True)
+        if exchange == "peer":
+            assert sh.peer_stats()[2] == 0, "peer exchange timed out waiting for a shard"
+        one.close(); sh.close()
     dist.barrier()
     if rank == 0:
         print("SHARDED_CHECK_OK world=%d" % world, flush=True)
