@@ -345,6 +345,24 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,
                           uint32_t *best, int64_t *n_insertions);
 
+/* ---- N2: support summarisation, the split table of a weighted collection of trees -----------------------------------
+ * Replaces the arithmetic of MTreeSet::convertSplits (mtreeset.cpp:362-440) as IQTree::summarizeBootstrap drives it
+ * (iqtree.cpp:3872-3989: SW_COUNT, no threshold): every tree's bipartitions in the order MTree::convertSplits pushes them
+ * (mtree.cpp:917-939, post-order by edge), normalised like Split::shouldInvert (split.cpp:100-107), merged over the
+ * trees with their weights summed, distinct splits in first-seen order.
+ * A tree is the reverse-Polish token stream of that traversal from its root leaf's neighbour: token t >= 0 = leaf with
+ * taxon id t (pushes {t}, emits it), token -k (k >= 2) = inner node joining the k topmost subtrees (emits their union);
+ * the last token emits the edge to the root leaf.  tokens of tree i: [token_begin[i], token_begin[i+1]); tree_weight[i] as
+ * MTreeSet::tree_weights (trees of weight 0 are scanned too -- leave them out, or put a tree whose supports are wanted
+ * last with weight 0 and read its splits' rows through emit_unique).
+ * Out: *n_unique distinct splits; split_bits [n_unique][(ntaxa+31)/32] (taxon i = bit i%32 of word i/32, as class Split),
+ * split_weight [n_unique] = summed tree weights, both in first-seen order; emit_unique [number of tokens] = row of every
+ * emitted split.  Any of the three may be NULL; capacity = rows available in split_bits / split_weight.
+ * Needs a context only for its device and stream (no alignment). */
+int mpgpu_split_table(mpgpu_ctx *ctx, int ntaxa, int ntrees, const int32_t *tokens, const int64_t *token_begin,
+                      const int32_t *tree_weight, int32_t *n_unique, uint32_t *split_bits, int32_t *split_weight,
+                      int32_t *emit_unique, int capacity);
+
 /* ---- host-only entry points: no device, no CUDA call ----
  * The tree-walking half of the path on ring tables, for hosts that keep their own search loop and for tests of the host
  * logic: nodeRectifierPars' visit order (sprparsimony.cpp:2046-2101), the candidates rearrangeParsimony /

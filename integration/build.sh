@@ -35,7 +35,7 @@ if [ "$WHAT" = all ] || [ "$WHAT" = stock ]; then
     echo "built $HERE/_bin/mpboot-avx"
 fi
 if [ "$WHAT" = all ] || [ "$WHAT" = gpu ]; then
-    make -C "$REPO/mpboot_b200/csrc" > /dev/null
+    make -j"$JOBS" -C "$REPO/mpboot_b200/csrc" > /dev/null
     copy_src "$WORK/src-gpu"
     (cd "$WORK/src-gpu" && patch -p1 --binary < "$HERE/mpboot_gpu.patch")
     configure_and_make "$WORK/src-gpu" "$WORK/build-gpu" -DMPGPU_DIR="$REPO"

@@ -76,7 +76,10 @@ static void free_alignment(Ctx *c)
 int shard_sum(Ctx *c, void *dev_i32, int64_t count)
 {
     if (c->shard_count == 1 || count <= 0 || c->exchange_off) return 0;
-    if (c->peer.ready) return peer_allreduce(c, dev_i32, count);       // one kernel on the stream, NVLink peer memory
+    // small vectors (every count vector of the search): one kernel on the stream over NVLink peer memory, latency-bound;
+    // large ones (-bb: rows x replicates of s32) are bandwidth-bound and go to the host's collective (NCCL ring / NVLS)
+    // when one is installed next to the peer exchange -- the one-shot kernel moves shard_count x the vector
+    if (c->peer.ready && (!c->allreduce || (size_t)count <= 4 * c->peer.cap)) return peer_allreduce(c, dev_i32, count);
     if (!c->allreduce) { set_error("sharded context: this call needs mpgpu_set_allreduce (or use the *_partial calls)"); return 1; }
     if (c->allreduce(c->allreduce_user, dev_i32, count, (void *)c->stream)) { set_error("the all-reduce callback failed"); return 1; }
     return 0;

@@ -38,6 +38,7 @@ def lib():
     L.mpgpu_peer_connect.argtypes = [vp, vp]
     L.mpgpu_peer_stats.argtypes = [vp, vp, vp, vp]
     L.mpgpu_search_info.argtypes = [vp, vp, vp, vp]
+    L.mpgpu_split_table.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32]
     L.mpgpu_stream.restype = vp
     L.mpgpu_stream.argtypes = [vp]
     L.mpgpu_synchronize.argtypes = [vp]
@@ -215,6 +216,23 @@ class Engine:
         calls, elems, err = C.c_int64(0), C.c_int64(0), C.c_int(0)
         self._ck(self.L.mpgpu_peer_stats(self.h, C.byref(calls), C.byref(elems), C.byref(err)))
         return calls.value, elems.value, err.value
+
+    def split_table(self, ntaxa, tokens, token_begin, tree_weight):
+        """mpgpu_split_table: (split_bits [U][W] uint32, split_weight [U], emit_unique [tokens]) in first-seen order."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        token_begin = np.ascontiguousarray(token_begin, dtype=np.int64)
+        tree_weight = np.ascontiguousarray(tree_weight, dtype=np.int32)
+        ntrees = len(tree_weight)
+        assert len(token_begin) == ntrees + 1
+        nemit = int(token_begin[-1] - token_begin[0])
+        W = (ntaxa + 31) // 32
+        nu = C.c_int32(0)
+        bits = np.zeros((nemit, W), dtype=np.uint32)
+        wgt = np.zeros(nemit, dtype=np.int32)
+        eu = np.zeros(nemit, dtype=np.int32)
+        self._ck(self.L.mpgpu_split_table(self.h, int(ntaxa), ntrees, _p(tokens), _p(token_begin), _p(tree_weight), C.byref(nu),
+                                          _p(bits), _p(wgt), _p(eu), nemit))
+        return bits[: nu.value].copy(), wgt[: nu.value].copy(), eu
 
     def search_info(self):
         """(score of the start tree, moves applied, scan batches) of the last SPR search on this context."""
