@@ -719,7 +719,7 @@ static int launch_scan_t(Ctx *c, int task0, int ntasks, int nslots)
         if (!sms) { cudaDeviceProp prop; MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device)); sms = prop.multiProcessorCount; }
         const long long warps1 = (long long)ntasks * (c->Wl / kChunkWords);
         const long long fill = (long long)sms * 32;                     // ~2 waves of 16 resident warps per SM
-        static const int auto_max = getenv("MPGPU_SCAN_VW_MAX") ? atoi(getenv("MPGPU_SCAN_VW_MAX")) : 1;   // measured on B200 (profiles/r02*): see DESIGN.md
+        static const int auto_max = getenv("MPGPU_SCAN_VW_MAX") ? atoi(getenv("MPGPU_SCAN_VW_MAX")) : 4;   // measured on B200 (profiles/r02b): C2 sweep 0.1605 / 0.1603 / 0.1476 ms at 1 / 2 / 4 chunks per warp
         if (auto_max >= 4 && warps1 / 4 >= fill) vw = 4;
         else if (auto_max >= 2 && warps1 / 2 >= fill) vw = 2;
         if (forced == 1 || forced == 2 || forced == 4) vw = forced;
