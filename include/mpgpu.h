@@ -12,6 +12,9 @@
  *     no CUDA device is usable every compute call fails.
  *   - the caller owns all host buffers; the context owns all device memory.  Calls are
  *     synchronous on return unless stated otherwise.
+ *   - threading: like the reference's engine (file-scope globals, sprparsimony.cpp:127-141) a context is not re-entrant,
+ *     and contexts on the SAME device must be driven from one host thread (under -cost they share one constant bank for
+ *     the cost matrix, re-bound on alternating use).  One process (or thread) per GPU is the intended layout.
  *   - trees travel as PLL "ring tables": nodes 1..n are tips, n+1..2n-2 inner nodes; an inner
  *     node has ring slots 0,1,2 (slot s+1 = ->next of slot s, pllrepo/src/pll.h:687-702), a
  *     tip only slot 0.  back_node[3*i+s] / back_slot[3*i+s] = node number and slot hooked to

@@ -43,21 +43,30 @@ __host__ __device__ inline uint32_t code_mask(int datatype, uint32_t code)
     }
 }
 
-static uint32_t g_mask_table[256];
+// one immutable table per data type, built once (callers keep the pointer; contexts on several host threads share them)
 const uint32_t *state_mask_table(int datatype, int *ncodes, int *undetermined)
 {
-    int nc = 0, und = 0;
+    struct Tables {
+        uint32_t t[4][256];                      // indexed by a code byte; codes the data type does not define map to the empty set
+        Tables()
+        {
+            const int dts[4] = {MPGPU_BINARY_DATA, MPGPU_DNA_DATA, MPGPU_AA_DATA, MPGPU_GENERIC_32};
+            const int ncs[4] = {4, 16, 23, 33};
+            for (int k = 0; k < 4; k++) for (int i = 0; i < 256; i++) t[k][i] = i < ncs[k] ? code_mask(dts[k], (uint32_t)i) : 0u;
+        }
+    };
+    static const Tables tables;                  // thread-safe initialisation (C++11 magic static)
+    int nc = 0, und = 0, k = 0;
     switch (datatype) {
-    case MPGPU_BINARY_DATA: nc = 4;  und = 3;  break;
-    case MPGPU_DNA_DATA:    nc = 16; und = 15; break;
-    case MPGPU_AA_DATA:     nc = 23; und = 22; break;
-    case MPGPU_GENERIC_32:  nc = 33; und = 32; break;
+    case MPGPU_BINARY_DATA: nc = 4;  und = 3;  k = 0; break;
+    case MPGPU_DNA_DATA:    nc = 16; und = 15; k = 1; break;
+    case MPGPU_AA_DATA:     nc = 23; und = 22; k = 2; break;
+    case MPGPU_GENERIC_32:  nc = 33; und = 32; k = 3; break;
     default: return nullptr;
     }
-    for (int i = 0; i < nc; i++) g_mask_table[i] = code_mask(datatype, (uint32_t)i);
     if (ncodes) *ncodes = nc;
     if (undetermined) *undetermined = und;
-    return g_mask_table;
+    return tables.t[k];
 }
 
 // ------------------------------------------------------------------------------------------

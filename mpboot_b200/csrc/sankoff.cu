@@ -944,7 +944,8 @@ static int sk_scan_geometry(Ctx *c, int ntasks, size_t per_warp, bool rows, int 
         if (*blocks > 0x7fffffffLL) { set_error("scan grid too large"); return 1; }
         return 0;
     }
-    static int sms = 0;
+    static int sms_dev[64] = {0};                /* per device */
+    int &sms = sms_dev[c->device & 63];
     if (!sms) { cudaDeviceProp prop; MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device)); sms = prop.multiProcessorCount; }
     int per_sm = 1;
     if (int rc = sk_scan_occupancy(c, rows, (size_t)c->S * c->S * sizeof(uint32_t), &per_sm)) return rc;
