@@ -25,7 +25,9 @@ GPU_BIN = os.path.join(dropin.BIN, "mpboot-avx-gpu")
 
 RUNS = [("c1_12x300", "plain"), ("c1_12x300", "bb"), ("c1_17x1998", "plain"), ("c1_17x1998", "bb"),
         ("aa_20x600", "plain"), ("aa_20x600", "bb"), ("morph_16x400", "plain"),
-        ("c1_100x5000", "plain"), ("c1_100x5000", "bb")]
+        ("c1_100x5000", "plain"), ("c1_100x5000", "bb"),
+        ("mulhits_17x1998", "bb"), ("topboot_17x1998", "bb"), ("mulhits_aa_20x600", "bb"),
+        ("cost_17x1998", "plain"), ("cost_17x1998", "bb")]
 
 
 def _need_binary():

@@ -30,7 +30,14 @@ CASES = {
     "aa_20x600": (20, 600, synth.PLL_AA_DATA, 0.08, 13, ["-st", "AA"]),
     "morph_16x400": (16, 400, synth.PLL_GENERIC_32, 0.05, 14, ["-st", "MORPH"]),
     "c2_200x100000": (200, 100000, synth.PLL_DNA_DATA, 0.05, 2, []),
+    # the other replicate-bookkeeping policies of IQTree::saveCurrentTree (iqtree.cpp:3498-3583), same alignment as c1_17x1998
+    "mulhits_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-mulhits"]),
+    "topboot_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-mulhits", "-topboot", "3"]),
+    "mulhits_aa_20x600": (20, 600, synth.PLL_AA_DATA, 0.08, 13, ["-st", "AA", "-mulhits"]),
+    # -cost (Sankoff weighted parsimony, ParsTree): transitions 1 / transversions 2; "@tstv" = a cost file written next to the alignment
+    "cost_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv"]),
 }
+COST_FILES = {"@tstv": "4\n0 2 1 2\n2 0 2 1\n1 2 0 2\n2 1 2 0\n"}
 MODES = {"plain": [], "bb": ["-bb", "1000"]}
 OUTPUTS = {"plain": [".treefile"], "bb": [".treefile", ".contree", ".splits.nex"]}
 
@@ -53,6 +60,13 @@ def make_alignment(name, outdir):
 
 
 def run_binary(binary, aln, prefix, extra, timeout):
+    extra = list(extra)
+    for i, a in enumerate(extra):
+        if a in COST_FILES:
+            path = os.path.join(os.path.dirname(aln), a[1:] + ".cost")
+            with open(path, "w") as f:
+                f.write(COST_FILES[a])
+            extra[i] = path
     cmd = [binary, "-s", aln, "-seed", "1", "-pre", prefix] + extra
     env = dict(os.environ, MPBOOT_GPU_STATS="1")
     t0 = time.time()
