@@ -512,10 +512,10 @@ template <int S> struct StateVec {
 // count.  ROWS: instead of counting, the mismatch bits of the insertion (the candidate's per-site delta row under -bb,
 // DESIGN.md section 5) go to rowp[32*j] when rowp is not null.  One REDUX and one RED per child whatever VW is.
 template <int S, bool ROWS, int VW>
-__device__ __forceinline__ void scan_child(const uint32_t (&U)[VW][S], const uint32_t (&X)[VW][S], const uint32_t (&C)[VW][S],
+__device__ __forceinline__ void scan_child(uint32_t (&U)[VW][S], const uint32_t (&X)[VW][S], const uint32_t (&C)[VW][S],
                                            const uint32_t (&Sv)[VW][S], bool do_out, int32_t *__restrict__ outp,
                                            uint32_t *__restrict__ rowp,
-                                           bool do_dst, uint32_t dst_addr, bool lane0)
+                                           bool do_dst, uint32_t dst_addr, bool lane0, bool in_place)
 {
     uint32_t Uc[VW][S];
 #pragma unroll
@@ -546,6 +546,12 @@ __device__ __forceinline__ void scan_child(const uint32_t (&U)[VW][S], const uin
             const int cnt = __reduce_add_sync(0xffffffffu, pc);
             if (lane0) atomicAdd(outp, cnt);
         }
+    }
+    if (in_place) {                 // the first child's up-view stays in registers: the very next op expands that child
+#pragma unroll
+        for (int j = 0; j < VW; j++)
+#pragma unroll
+            for (int k = 0; k < S; k++) U[j][k] = Uc[j][k];
     }
 }
 
@@ -613,8 +619,10 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     pin(vb_);
     const V *vbase = static_cast<const V *>(vb_);
     constexpr uint32_t kSlotBytes = VW * Lay<S>::G * 32 * sizeof(V);         // [word j][group][lane] vectors
+    // stack slots 0 and 1 (first children) never reach shared memory: such an up-view is consumed by the very next op and
+    // stays in registers; the stack holds slots 2 .. nslots + 1 (second children, one per depth), addressed as slot * bytes
     uint32_t sstack = (uint32_t)__cvta_generic_to_shared(smem4) +
-                      (uint32_t)warp * (uint32_t)nslots * kSlotBytes + lane * (uint32_t)sizeof(V);
+                      (uint32_t)warp * (uint32_t)nslots * kSlotBytes + lane * (uint32_t)sizeof(V) - 2u * kSlotBytes;
     pin(sstack);
     const bool lane0 = lane == 0;
     int32_t *outc = out + t1.z;                                              // candidates of this task
@@ -661,21 +669,32 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
         const int2 cw = __ldg(ctl + oi);                                                               \
         const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;       \
         const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;                                  \
-        WideVec<S, VW> Uv;                                                                             \
-        if (src < 0xfe) Uv.load_shared(sstack + src * kSlotBytes);                                     \
-        else Uv.load(vbase + (uint32_t)(src == 0xff ? t0.z : t0.y), gsv);                              \
-        uint32_t U[VW][S], A[VW][S], B[VW][S];                                                         \
-        Uv.unpack(U); AC.unpack(A); BC.unpack(B);                                                      \
+        /* src 0 / 1: the up-view the previous op left in U (its first child, expanded right away) */  \
+        if (src >= 2) {                                                                                \
+            WideVec<S, VW> Uv;                                                                         \
+            if (src < 0xfe) Uv.load_shared(sstack + src * kSlotBytes);                                 \
+            else Uv.load(vbase + (uint32_t)(src == 0xff ? t0.z : t0.y), gsv);                          \
+            Uv.unpack(U);                                                                              \
+        }                                                                                              \
+        uint32_t A[VW][S], B[VW][S];                                                                   \
+        AC.unpack(A); BC.unpack(B);                                                                    \
         uint32_t *rp1 = nullptr, *rp2 = nullptr;                                                       \
         if (ROWS) {                                                                                    \
             if (o1 != 0xffff) { const int r = __ldg(rowc + o1); if (r >= 0) rp1 = rowbase + (size_t)r * Wl; } \
             if (o2 != 0xffff) { const int r = __ldg(rowc + o2); if (r >= 0) rp2 = rowbase + (size_t)r * Wl; } \
         }                                                                                              \
-        if (o1 != 0xffff || dst1 != 0xff)                                                              \
-            scan_child<S, ROWS, VW>(U, B, A, Sv, o1 != 0xffff, outc + o1, rp1, dst1 != 0xff, sstack + dst1 * kSlotBytes, lane0); \
+        /* second child first: its up-view goes to the stack; then the first child's replaces U */     \
         if (o2 != 0xffff || dst2 != 0xff)                                                              \
-            scan_child<S, ROWS, VW>(U, A, B, Sv, o2 != 0xffff, outc + o2, rp2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0); \
+            scan_child<S, ROWS, VW>(U, A, B, Sv, o2 != 0xffff, outc + o2, rp2, dst2 != 0xff, sstack + dst2 * kSlotBytes, lane0, false); \
+        if (o1 != 0xffff || dst1 != 0xff)                                                              \
+            scan_child<S, ROWS, VW>(U, B, A, Sv, o1 != 0xffff, outc + o1, rp1, false, 0u, lane0, dst1 != 0xff); \
     }
+
+    uint32_t U[VW][S];
+#pragma unroll
+    for (int j = 0; j < VW; j++)
+#pragma unroll
+        for (int k = 0; k < S; k++) U[j][k] = 0;
 
     for (;;) {
         MPGPU_SCAN_STEP(A0, B0, A1, B1, f0, f1, f0)
@@ -691,7 +710,8 @@ static int launch_scan_v(Ctx *c, int task0, int ntasks, int nslots)
 {
     typedef typename VecOf<S>::T V;
     constexpr bool PF = S <= 4 && (VW <= 2 || PF4);
-    const size_t per_warp = (size_t)(nslots > 0 ? nslots : 1) * Lay<S>::G * 32 * sizeof(V) * VW;
+    nslots = nslots > 2 ? nslots - 2 : 1;       // the planner's slots 0 / 1 live in registers (see k_spr_scan)
+    const size_t per_warp = (size_t)nslots * Lay<S>::G * 32 * sizeof(V) * VW;
     int wpb = 4;           // small CTAs: ragged task lengths retire early, measured best on B200 (profiles/)
     if (const char *e = getenv("MPGPU_SCAN_WPB")) { int v = atoi(e); if (v >= 1 && v <= 32) wpb = v; }   // tuning knob
     const size_t budget = 96 * 1024;
@@ -708,7 +728,7 @@ static int launch_scan_v(Ctx *c, int task0, int ntasks, int nslots)
     if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
     k_spr_scan<S, PF, ROWS, VW><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
         reinterpret_cast<const V *>(c->d_views), c->Wl, c->d_tasks + (ROWS ? 0 : task0), ntasks, reinterpret_cast<const int2 *>(c->d_offs),
-        reinterpret_cast<const int2 *>(c->d_ctl), nslots > 0 ? nslots : 1, c->d_counts,
+        reinterpret_cast<const int2 *>(c->d_ctl), nslots, c->d_counts,
         ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, c->plan.task_cap, ROWS ? c->d_rows_site : nullptr);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());

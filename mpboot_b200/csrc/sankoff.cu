@@ -682,9 +682,13 @@ int sk_build(Ctx *c)
         set_error("cost matrix too large for this many taxa: (ntaxa+1)*(max cost+1) must stay below 65536 (a u16 of the reference could wrap)");
         return 1;
     }
-    if (k.seg_upper.empty() || k.seg_upper.back() != ninf) { set_error("segment_upper must end at the number of informative patterns"); return 1; }
+    // The last bound is IQ-TREE's count of informative patterns (ras_pars_score != 0, iqtree.cpp:3814), which can be smaller
+    // than PLL's (two distinct codes, :2488-2495: e.g. a pattern of A and R): the patterns between the two cost nothing on
+    // any tree, lie in no segment and are never summed by the reference (:944-948 stops at pllSegmentUpper) -- weight 0 here.
+    if (k.seg_upper.empty() || k.seg_upper.back() > ninf || k.seg_upper.back() < 1) { set_error("segment_upper must end at the number of informative patterns"); return 1; }
+    const int last_bound = k.seg_upper.back();
     for (int s = 0; s + 1 < k.nseg; s++)
-        if (k.seg_upper[s] % 16 || k.seg_upper[s] <= (s ? k.seg_upper[s - 1] : 0) || k.seg_upper[s] >= ninf) {
+        if (k.seg_upper[s] % 16 || k.seg_upper[s] <= (s ? k.seg_upper[s - 1] : 0) || k.seg_upper[s] >= last_bound) {
             set_error("segment_upper: interior bounds must be increasing multiples of 16 (iqtree.cpp:3804)"); return 1;
         }
     k.Lref = ninf % 16 ? ninf + 16 - ninf % 16 : ninf;
@@ -714,7 +718,7 @@ int sk_build(Ctx *c)
         int j = 0;
         for (int i = 0; i < c->P; i++) {
             if (!c->informative[i]) continue;
-            wflat[j] = (uint32_t)(uint16_t)c->weights[i];
+            wflat[j] = j < last_bound ? (uint32_t)(uint16_t)c->weights[i] : 0u;
             present[j] = c->present[j];          // findMstScore(ptn) indexes the alignment directly: informative patterns come first
             j++;
         }

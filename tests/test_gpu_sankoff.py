@@ -14,6 +14,13 @@ from tests.helpers import make_case
 
 pytestmark = pytest.mark.gpu
 
+
+def _reference(chars, weights, dt, n_inf, codes):
+    from oracle import portlib, reflib
+    if reflib.available():
+        return reflib.RefEngine(chars, weights, dt, n_informative=n_inf)
+    return portlib.OracleEngine(codes, weights, dt)
+
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(glob.glob(os.path.join(GOLD, "sankoff_*.npz")))
 IDS = [os.path.basename(p)[:-4] for p in FILES]
@@ -191,7 +198,48 @@ def test_preconditions_fail_loudly():
     with pytest.raises(MpGpuError, match="too large"):
         eng.set_cost_matrix((6000 * (1 - np.eye(4))).astype(np.uint32), seg)
     with pytest.raises(MpGpuError, match="segment_upper"):
-        eng.set_cost_matrix((1 - np.eye(4)).astype(np.uint32), np.array([c["n_inf"] - 1], dtype=np.int32))
+        eng.set_cost_matrix((1 - np.eye(4)).astype(np.uint32), np.array([c["n_inf"] + 1], dtype=np.int32))
+    with pytest.raises(MpGpuError, match="segment_upper"):
+        eng.set_cost_matrix((1 - np.eye(4)).astype(np.uint32), np.array([24, c["n_inf"]], dtype=np.int32))      # interior bound not a multiple of 16
+
+
+def test_last_segment_bound_below_pll_informative_count():
+    """IQ-TREE's informative count (ras_pars_score != 0, the last segment bound, iqtree.cpp:3814) can be smaller than PLL's
+    (two distinct codes, sprparsimony.cpp:2488-2495): the patterns in between (e.g. A next to R) cost nothing on any tree and
+    the reference never sums them (:944-948 stops at pllSegmentUpper).  Scores must equal the reference's with those bounds."""
+    from mpboot_b200.engine import Engine
+    from mpboot_b200 import hostprep, synth
+    n = 14
+    chars = synth.evolve_alignment(n, 500, 1, 0.05, 65, gap=0.0, amb=0.0)
+    extra = np.full((n, 3), ord("A"), dtype=np.uint8)
+    extra[3, 0] = ord("R"); extra[5, 1] = ord("M"); extra[7, 2] = ord("N"); extra[8, 2] = ord("R")     # zero-cost, two codes each
+    prep = hostprep.prepare(np.concatenate([chars, extra], axis=1), 1)
+    bn, bs = synth.random_tree_rings(n, np.random.default_rng(3))
+    cost = np.array([[0, 2, 1, 2], [2, 0, 2, 1], [1, 2, 0, 2], [2, 1, 2, 0]], dtype=np.uint32)
+    eng = Engine()
+    eng.load_alignment(prep["codes"], prep["weights"], 1)
+    eng.set_tree(bn, bs)
+    pp, _ = eng.pattern_parsimony()
+    positive = int(np.count_nonzero(pp[: prep["n_inf"]]))
+    order = np.argsort(-(pp[: prep["n_inf"]].astype(np.int64) * prep["weights"][: prep["n_inf"]]), kind="stable")   # score x freq, like optimizeAlignment
+    idx = np.concatenate([order, np.arange(prep["n_inf"], prep["codes"].shape[1])])
+    codes = np.ascontiguousarray(prep["codes"][:, idx]); chars2 = np.ascontiguousarray(prep["chars"][:, idx]); w = np.ascontiguousarray(prep["weights"][idx])
+    assert positive < prep["n_inf"]
+    seg = np.array([16, 32, positive], dtype=np.int32)
+    ora = _reference(chars2, w, 1, prep["n_inf"], codes)
+    hi = ora.set_cost_matrix(cost, seg)
+    ora.set_ring(bn, bs); ora.allocate(per_site=True)
+    want = ora.evaluate_full(per_site=True)
+    eng2 = Engine()
+    eng2.load_alignment(codes, w, 1)
+    assert eng2.set_cost_matrix(cost, seg) == hi
+    eng2.set_tree(bn, bs)
+    assert eng2.tree_score() == want
+    order_v = eng2.visit_order()
+    for i in (1, n, 2 * n - 2):
+        vb, mp, _, _ = eng2.scan_visits(order_v, i, 1, 1, 6)
+        ora.record(False); ora.rearrange(i, 1, 6, True, want)
+        assert np.array_equal(ora.saved()[1:], mp.astype(np.int32))
 
 
 @pytest.mark.parametrize("n,L,dt,seed", [(4, 60, 1, 71), (5, 40, 1, 72), (7, 90, 0, 73), (9, 30, 2, 74)])
