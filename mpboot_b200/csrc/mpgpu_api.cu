@@ -189,7 +189,9 @@ static inline int2 kid_pair(const Triple &tr) { return tr.a < tr.b ? make_int2(t
 int compute_views(Ctx *c, bool want_start_edge)
 {
     const int nviews = 4 * c->n - 6;
-    c->wave_pending = 0;
+    c->wave_pending = 0; c->wave_lists.clear(); c->wave_used = 0; c->wc_used = 0; c->wave_fetched = false;
+    c->wcount_zeroed = false;                 // lists may have been in flight: their counters are not known to be zero
+    c->vstale.assign(nviews, 0); c->n_stale = 0;
     c->views_stale = false;
     c->start_edge_valid = false;
     build_schedule(c);
@@ -239,16 +241,17 @@ int compute_views(Ctx *c, bool want_start_edge)
 int update_views(Ctx *c, bool defer)
 {
     const int nviews = 4 * c->n - 6;
-    c->wave_pending = 0;
     if (!c->kids_valid || (int)c->view_kids.size() != nviews || (int)c->vcount.size() != nviews ||
         (c->shard_count > 1 && !c->reduces()) || getenv("MPGPU_NO_WAVE"))
         return compute_views(c);
     static const bool prof = getenv("MPGPU_PROFILE") != nullptr;
     static double t_host = 0, t_dev = 0; static long n_calls = 0, n_triples = 0, n_levels = 0;
     std::chrono::steady_clock::time_point p0, p1;
+    if (c->n_stale) { if (int rc = ensure_all_views(c)) return rc; }      // the eager scheme starts from current views
     if (prof) p0 = std::chrono::steady_clock::now();
     build_schedule(c);
-    std::vector<int32_t> &dl = c->sc_dl, &slot = c->sc_slot, &fill = c->sc_fill;
+    c->dl_dirty = true;
+    std::vector<int32_t> &dl = c->sc_dl;
     std::vector<Triple> &stale = c->sc_stale;
     dl.assign(nviews, 0);                               // stale level (0 = clean)
     stale.clear();
@@ -268,17 +271,66 @@ int update_views(Ctx *c, bool defer)
         stale.push_back(tr);
         c->view_kids[tr.dst] = k;
     }
+    if (prof) p1 = std::chrono::steady_clock::now();
+    if (int rc = submit_stale(c, stale, nlevels, defer, false)) return rc;
+    if (prof && !defer) {
+        const auto p2 = std::chrono::steady_clock::now();
+        t_host += std::chrono::duration<double>(p1 - p0).count(); t_dev += std::chrono::duration<double>(p2 - p1).count();
+        n_calls++; n_triples += (long)stale.size(); n_levels += nlevels;
+        if (n_calls % 256 == 0)
+            fprintf(stderr, "[mpgpu profile] update_views x%ld: host %.1f us, launch..sync %.1f us per call; %.0f stale views in %.0f levels\n",
+                    n_calls, 1e6 * t_host / n_calls, 1e6 * t_dev / n_calls, (double)n_triples / n_calls, (double)n_levels / n_calls);
+    }
+    return 0;
+}
+
+// The stale list (children before parents, pad = stale level) goes to the device as one k_fitch_wave launch (Fitch) or one
+// launch per level (Sankoff); the mismatch counts of the recomputed views come back compact.  Several lists can be in
+// flight (one per plan piece of a scan batch): they share the pinned / device staging arrays at increasing offsets and
+// are landed together by settle_views() after the caller's next stream synchronize.  incremental: the lengths of the
+// listed views are updated from their children's (every other view's length is current: the lazy scheme of the SPR
+// search); otherwise settle_views recomputes all lengths from the schedule.
+int submit_stale(Ctx *c, std::vector<Triple> &stale, int nlevels, bool defer, bool incremental)
+{
+    const int nviews = 4 * c->n - 6;
     const size_t total = stale.size();
     if (total == 0) return 0;
-    if (c->sk.on) { c->reps.tree_valid = false; return sk_update_stale(c, stale, nlevels); }
+    if (!incremental) c->reps.tree_valid = false;      // (the lazy scheme dropped the tree rows when the move was marked)
+    if (c->sk.on) {
+        if (c->wave_pending) { if (int rc = fetch_wave_counts(c)) return rc; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, false); }
+        if (int rc = sk_update_stale(c, stale, nlevels)) return rc;
+        if (incremental) for (const Triple &tr : stale) c->vlen[tr.dst] = c->vcount[tr.dst] & 0xFFFFu;
+        return 0;
+    }
     const int hdr = (nlevels + 3) / 4;
-    if (wave_smem_bytes(c->S, hdr + (int)total) > 200 * 1024) { c->kids_valid = false; return compute_views(c); }   // list does not fit in shared memory
-    if (!c->wave_pin.reserve(2 * (hdr + total) + 64) || !c->wcount_pin.reserve(2 * total + 64)) { set_error("pinned allocation failed"); return 1; }
-    if (int rc = ensure(c->d_wave, c->wave_cap, hdr + total)) return rc;
-    if (int rc = ensure(c->d_wcount, c->wcount_cap, total)) return rc;
+    if (wave_smem_bytes(c->S, hdr + (int)total) > 200 * 1024) {            // list does not fit in shared memory: everything, level by level
+        if (c->wave_pending) { if (int rc = fetch_wave_counts(c)) return rc; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, false); }
+        c->kids_valid = false;
+        if (int rc = compute_views(c)) return rc;
+        if (c->reduces()) compute_lengths(c);
+        return 0;
+    }
+    // staging for every list that can be in flight before the next settle: each view is listed at most once per settle
+    // in the lazy scheme, the eager one has a single list
+    const size_t cap_tr = (size_t)2 * nviews + 1024, cap_wc = (size_t)nviews + 1024;
+    if (c->wave_pin.size() < cap_tr || c->wcount_pin.size() < cap_wc || c->wave_cap < cap_tr || c->wcount_cap < cap_wc ||
+        c->wave_used + hdr + total > cap_tr || c->wc_used + total > cap_wc) {
+        if (c->wave_pending) { if (int rc = fetch_wave_counts(c)) return rc; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, false); }
+        if (!c->wave_pin.reserve(cap_tr) || !c->wcount_pin.reserve(cap_wc)) { set_error("pinned allocation failed"); return 1; }
+        if (int rc = ensure(c->d_wave, c->wave_cap, cap_tr)) return rc;
+        if (int rc = ensure(c->d_wcount, c->wcount_cap, cap_wc)) return rc;
+        MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, c->wcount_cap * sizeof(uint32_t), c->stream));
+        c->wcount_zeroed = true;
+    }
+    if (!c->wcount_zeroed) {
+        MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, c->wcount_cap * sizeof(uint32_t), c->stream));
+        c->wcount_zeroed = true;
+    }
+    std::vector<int32_t> &dl = c->sc_dl, &slot = c->sc_slot, &fill = c->sc_fill;     // dl[view] = stale level of the views of THIS list
     // counting sort by stale level straight into the pinned list; slots = position within the level
-    int32_t *level_end = reinterpret_cast<int32_t *>(c->wave_pin.data());
-    Triple *dst = c->wave_pin.data() + hdr;
+    const size_t off = c->wave_used, wc_off = c->wc_used;
+    int32_t *level_end = reinterpret_cast<int32_t *>(c->wave_pin.data() + off);
+    Triple *dst = c->wave_pin.data() + off + hdr;
     fill.assign(nlevels + 2, 0);
     for (const Triple &tr : stale) fill[tr.pad + 1]++;
     for (int l = 1; l <= nlevels + 1; l++) fill[l] += fill[l - 1];
@@ -297,37 +349,156 @@ int update_views(Ctx *c, bool defer)
         x.pad = a_slot | d_slot << 8 | (dl[tr.b] == 0 ? 0x10000 : 0);
         dst[at] = x;
     }
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_wave, c->wave_pin.data(), (hdr + total) * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
-    MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, total * sizeof(uint32_t), c->stream));
-    if (int rc = launch_wave(c, c->d_wave, nlevels, hdr, (int)total, c->d_wcount)) return rc;
-    if (prof) p1 = std::chrono::steady_clock::now();
-    c->reps.tree_valid = false;
-    if (c->shard_count > 1) { if (int rc = shard_sum(c, c->d_wcount, (int64_t)total)) return rc; }
-    MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    c->wave_pending = (int)total; c->wave_hdr = hdr;
+    MPGPU_CUDA(cudaMemcpyAsync(c->d_wave + off, c->wave_pin.data() + off, (hdr + total) * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_wave(c, c->d_wave + off, nlevels, hdr, (int)total, c->d_wcount + wc_off)) return rc;
+    if (c->shard_count > 1) { if (int rc = shard_sum(c, c->d_wcount + wc_off, (int64_t)total)) return rc; }
+    PendingWave pw; pw.list_off = (int)(off + hdr); pw.total = (int)total; pw.wc_off = (int)wc_off; pw.incremental = incremental;
+    c->wave_lists.push_back(pw);
+    c->wave_used += hdr + total; c->wc_used += total;
+    c->wave_pending += (int)total;
     if (defer) return 0;
+    if (int rc = fetch_wave_counts(c)) return rc;
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     settle_views(c, false);
-    if (prof) {
-        const auto p2 = std::chrono::steady_clock::now();
-        t_host += std::chrono::duration<double>(p1 - p0).count(); t_dev += std::chrono::duration<double>(p2 - p1).count();
-        n_calls++; n_triples += (long)total; n_levels += nlevels;
-        if (n_calls % 256 == 0)
-            fprintf(stderr, "[mpgpu profile] update_views x%ld: host %.1f us, launch..sync %.1f us per call; %.0f stale views in %.0f levels\n",
-                    n_calls, 1e6 * t_host / n_calls, 1e6 * t_dev / n_calls, (double)n_triples / n_calls, (double)n_levels / n_calls);
-    }
     return 0;
 }
 
-// after a stream synchronize: the counts of a deferred update_views land in vcount (and vlen)
+// the counts of every list in flight -> the pinned copy, and the device counters back to zero (stream-ordered; the caller
+// synchronizes, then settle_views lands them)
+int fetch_wave_counts(Ctx *c)
+{
+    if (!c->wave_pending || c->wave_fetched) return 0;
+    MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, (size_t)c->wc_used * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(c->d_wcount, 0, (size_t)c->wc_used * sizeof(uint32_t), c->stream));
+    c->wave_fetched = true;
+    return 0;
+}
+
+// after a stream synchronize that followed fetch_wave_counts: the counts of the lists in flight land in vcount (and vlen)
 void settle_views(Ctx *c, bool lengths)
 {
     if (!c->wave_pending) return;
-    const Triple *list = c->wave_pin.data() + c->wave_hdr;
-    const uint32_t *wc = c->wcount_pin.data();
-    for (int i = 0; i < c->wave_pending; i++) c->vcount[list[i].dst] = wc[i];
-    c->wave_pending = 0;
-    if (lengths) compute_lengths(c);
+    const uint32_t *wcp = c->wcount_pin.data();
+    bool full = false;
+    for (const PendingWave &pw : c->wave_lists) {
+        const Triple *list = c->wave_pin.data() + pw.list_off;
+        const uint32_t *wc = wcp + pw.wc_off;
+        if (pw.incremental) {
+            if (c->sk.on) for (int i = 0; i < pw.total; i++) { c->vcount[list[i].dst] = wc[i]; c->vlen[list[i].dst] = wc[i] & 0xFFFFu; }
+            else for (int i = 0; i < pw.total; i++) {             // sorted by level: children first
+                const Triple &tr = list[i];
+                c->vcount[tr.dst] = wc[i];
+                c->vlen[tr.dst] = c->vlen[tr.a] + c->vlen[tr.b] + wc[i];
+            }
+        } else {
+            for (int i = 0; i < pw.total; i++) c->vcount[list[i].dst] = wc[i];
+            full = true;
+        }
+    }
+    c->wave_lists.clear();
+    c->wave_pending = 0; c->wave_used = 0; c->wc_used = 0; c->wave_fetched = false;
+    if (lengths && full) compute_lengths(c);
+}
+
+// ---- lazy views (the SPR search) -----------------------------------------------------------------------------------
+// After a move about half of the directed views are out of date (every view whose subtree contains a changed edge), but
+// the next scan batch reads only the views around the next few pruning points.  The search therefore only MARKS views
+// after a move and recomputes, right before a batch is launched, the stale ones among the views its plan reads plus
+// what those depend on -- typically the path from the last moves to the pruning point, a few levels deep, instead of
+// ~2n views in a forest as deep as the tree.  Views nobody reads stay stale until ensure_all_views (need_tree).
+static inline int2 kid_pair_of(const HostTree &t, int r)
+{
+    const int a = t.vid(t.back(t.next(r))), b = t.vid(t.back(t.next(t.next(r))));
+    return a < b ? make_int2(a, b) : make_int2(b, a);
+}
+
+// the adjacency of these nodes changed: their views whose children differ from the last computation are stale, and so
+// is every view that contains a stale one (walk towards the views that read it)
+void mark_stale_nodes(Ctx *c, const int *nodes, int k)
+{
+    const HostTree &t = c->tree;
+    const int n = t.n, nviews = 4 * n - 6;
+    if ((int)c->vstale.size() != nviews) { c->vstale.assign(nviews, 0); c->n_stale = 0; }
+    std::vector<int32_t> &stack = c->sc_stack;
+    stack.clear();
+    for (int i = 0; i < k; i++) {
+        const int node = nodes[i];
+        if (node <= n) continue;
+        for (int s = 0; s < 3; s++) {
+            const int r = 3 * node + s, v = t.vid(r);
+            if (c->vstale[v]) continue;
+            const int2 now = kid_pair_of(t, r), was = c->view_kids[v];
+            if (now.x != was.x || now.y != was.y) { c->vstale[v] = 1; c->n_stale++; stack.push_back(r); }
+        }
+    }
+    while (!stack.empty()) {
+        const int r = stack.back(); stack.pop_back();
+        const int x = t.back(r);                             // view(r) is a child of the views behind the other two slots of x's node
+        if (t.is_tip(x)) continue;
+        for (int r2 = t.next(x); r2 != x; r2 = t.next(r2)) {
+            const int v = t.vid(r2);
+            if (!c->vstale[v]) { c->vstale[v] = 1; c->n_stale++; stack.push_back(r2); }
+        }
+    }
+    c->reps.tree_valid = false;
+}
+
+// Recompute the stale ones among the views behind the ring slots refs[0..count) and, first, the stale views they are
+// built from.  defer: the counts land with settle_views after the caller's next fetch_wave_counts + synchronize.
+int ensure_views(Ctx *c, const int32_t *refs, int count, bool defer)
+{
+    if (c->n_stale == 0 || count == 0) return 0;
+    const HostTree &t = c->tree;
+    const int nviews = 4 * t.n - 6;
+    std::vector<int32_t> &dl = c->sc_dl, &stack = c->sc_stack;
+    std::vector<Triple> &stale = c->sc_stale;
+    if ((int)dl.size() != nviews || c->dl_dirty) { dl.assign(nviews, 0); c->dl_dirty = false; }
+    stale.clear();
+    stack.clear();
+    int nlevels = 0;
+    for (int i = 0; i < count; i++) {
+        if (!c->vstale[t.vid(refs[i])]) continue;
+        stack.push_back(refs[i]);
+        while (!stack.empty()) {
+            const int r = stack.back();
+            const int v = t.vid(r);
+            if (!c->vstale[v]) { stack.pop_back(); continue; }
+            const int a = t.back(t.next(r)), b = t.back(t.next(t.next(r)));
+            const int va = t.vid(a), vb = t.vid(b);
+            const bool sa = c->vstale[va] != 0, sb = c->vstale[vb] != 0;
+            if (sa || sb) { if (sa) stack.push_back(a); if (sb) stack.push_back(b); continue; }
+            Triple tr; tr.dst = v; tr.a = va; tr.b = vb;
+            const int l = std::max(dl[va], dl[vb]) + 1;
+            // b = the clean operand when there is one (prefetched); a = the fresh one of the previous level (cached)
+            const bool fa = dl[va] != 0, fb = dl[vb] != 0;
+            if (!fa && fb) std::swap(tr.a, tr.b);
+            else if (fa && fb && dl[tr.a] != l - 1) std::swap(tr.a, tr.b);
+            tr.pad = l;
+            dl[v] = l;
+            if (l > nlevels) nlevels = l;
+            stale.push_back(tr);
+            c->view_kids[v] = va < vb ? make_int2(va, vb) : make_int2(vb, va);
+            c->vstale[v] = 0; c->n_stale--;
+            stack.pop_back();
+        }
+    }
+    if (stale.empty()) return 0;
+    c->dl_dirty = true;                       // an error return below leaves dl dirty
+    const int rc = submit_stale(c, stale, nlevels, defer, true);
+    for (const Triple &tr : stale) dl[tr.dst] = 0;
+    c->dl_dirty = false;
+    return rc;
+}
+
+int ensure_all_views(Ctx *c)
+{
+    if (c->n_stale == 0) return 0;
+    const int n = c->n;
+    std::vector<int32_t> refs;
+    refs.reserve((size_t)c->n_stale);
+    for (int node = n + 1; node <= 2 * n - 2; node++)
+        for (int s = 0; s < 3; s++) if (c->vstale[c->tree.vid(3 * node + s)]) refs.push_back(3 * node + s);
+    return ensure_views(c, refs.data(), (int)refs.size(), false);
 }
 
 // subtree lengths from (all-reduced) mismatch counts, children before parents
@@ -353,6 +524,10 @@ int need_tree(Ctx *c, bool lens)
         if (cudaSetDevice(c->device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
         if (int rc = compute_views(c)) return rc;
         if (c->reduces()) compute_lengths(c);
+    }
+    if (c->n_stale) {                       // an SPR search left views it did not need out of date
+        if (cudaSetDevice(c->device) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+        if (int rc = ensure_all_views(c)) return rc;
     }
     if (lens && !c->lens_valid) { set_error("view lengths not set (sharded context: call mpgpu_set_view_counts)"); return 1; }
     return 0;
@@ -381,7 +556,9 @@ static int reserve_plan(Ctx *c)
     if (int rc = ensure(c->d_offs, c->offs_cap, pl.offs.size() + 1)) return rc;
     if (int rc = ensure(c->d_ctl, c->ctl_cap, pl.ctl.size() + 1)) return rc;
     if (int rc = ensure(c->d_tasks, c->tasks_cap, (size_t)pl.task_cap + 1)) return rc;
+    const int32_t *before = c->d_counts;
     if (int rc = ensure(c->d_counts, c->counts_cap, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
+    if (c->d_counts != before) c->counts_dirty = c->counts_cap;         // a fresh allocation is not zero
     return 0;
 }
 
@@ -391,15 +568,85 @@ int upload_plan(Ctx *c)
     return upload_plan_range(c, 0, 0);
 }
 
+// d_counts[0, n) = 0 before a scan.  k_publish leaves the range it read zeroed, so in the search loop this is usually
+// nothing; any other reader leaves the counters dirty and the next scan pays one memset.
+int zero_counts(Ctx *c, size_t n)
+{
+    if (c->counts_dirty) {
+        const size_t m = std::min(c->counts_dirty, c->counts_cap);
+        MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, m * sizeof(int32_t), c->stream));
+    }
+    c->counts_dirty = n;                    // the scan about to be launched writes [0, n)
+    return 0;
+}
+
 // counts layout: [0, task_cap) joined-edge counts per task slot, then one count per candidate
 int run_scan(Ctx *c)
 {
     ScanPlan &pl = c->plan;
     if (c->sk.on) return sk_run_scan(c);
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
-    MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, (nout + 1) * sizeof(int32_t), c->stream));
+    if (int rc = zero_counts(c, nout + 1)) return rc;
     if (int rc = launch_scan(c, 0, (int)pl.tasks.size(), pl.max_slot)) return rc;
     if (c->shard_count > 1 && c->reduces()) return shard_sum(c, c->d_counts, (int64_t)nout);
+    return 0;
+}
+
+// The read-back of a small batch without a copy engine and without a stream synchronize: one block copies the scan
+// counts and the counts of the view updates in flight to mapped page-locked memory, puts the device counters back to
+// zero (the next batch needs no memset) and writes the flag word last; the host spins on the flag.
+__global__ void __launch_bounds__(512) k_publish(int32_t *__restrict__ counts, int nout, uint32_t *__restrict__ wcount, int nwc,
+                                                 int32_t *__restrict__ host_counts, uint32_t *__restrict__ host_wc,
+                                                 volatile uint32_t *host_flag, uint32_t epoch)
+{
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) { host_counts[i] = __ldcg(counts + i); counts[i] = 0; }
+    for (int i = threadIdx.x; i < nwc; i += blockDim.x) { host_wc[i] = __ldcg(wcount + i); wcount[i] = 0; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *host_flag = epoch;
+}
+
+static int ensure_h_counts(Ctx *c, size_t nout)
+{
+    if (nout * sizeof(int32_t) > c->h_counts_cap) {
+        if (c->h_counts) cudaFreeHost(c->h_counts);
+        c->h_counts = nullptr; c->h_counts_cap = 0;
+        const size_t want = (nout + nout / 2 + 1024) * sizeof(int32_t);
+        MPGPU_CUDA(cudaHostAlloc((void **)&c->h_counts, want, cudaHostAllocMapped));        // pinned: the read-back is on the e2e path
+        c->h_counts_cap = want;
+    }
+    if (!c->h_flag) {
+        MPGPU_CUDA(cudaHostAlloc((void **)&c->h_flag, 64, cudaHostAllocMapped));
+        *c->h_flag = 0;
+    }
+    return 0;
+}
+
+static const int kPublishMax = 16384;     // counters one k_publish block moves; larger read-backs take the copy engine
+
+int launch_publish(Ctx *c, int nout)
+{
+    if (int rc = ensure_h_counts(c, (size_t)nout)) return rc;
+    c->flag_epoch++;
+    if (c->flag_epoch == 0) c->flag_epoch = 1;
+    k_publish<<<1, 512, 0, c->stream>>>(c->d_counts, nout, c->d_wcount, (int)c->wc_used, c->h_counts, c->wcount_pin.data(),
+                                        c->h_flag, c->flag_epoch);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    if (c->wave_pending) c->wave_fetched = true;
+    c->counts_dirty = 0;
+    // spin on the flag; the stream is queried now and then so that a failed launch cannot hang the host
+    volatile uint32_t *flag = c->h_flag;
+    for (uint32_t spins = 1; *flag != c->flag_epoch; spins++) {
+        if ((spins & 0xFFFF) == 0) {
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "scan batch");
+            if (e == cudaSuccess && *flag != c->flag_epoch) { set_error("k_publish finished without raising its flag"); return 1; }
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
     return 0;
 }
 
@@ -409,15 +656,16 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
     if (c->sk.on) return sk_finish_scan(c, visit_begin, mp, cand_ref, cand_prune, capacity);
     if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
-    if (nout * sizeof(int32_t) > c->h_counts_cap) {
-        if (c->h_counts) cudaFreeHost(c->h_counts);
-        c->h_counts = nullptr; c->h_counts_cap = 0;
-        const size_t want = (nout + nout / 2 + 1024) * sizeof(int32_t);
-        MPGPU_CUDA(cudaHostAlloc((void **)&c->h_counts, want, cudaHostAllocDefault));        // pinned: the read-back is on the e2e path
-        c->h_counts_cap = want;
+    static const bool no_publish = getenv("MPGPU_NO_PUBLISH") != nullptr;
+    if (!no_publish && c->shard_count == 1 && nout + c->wc_used <= (size_t)kPublishMax && (c->wc_used == 0 || c->wcount_pin.data())) {
+        if (int rc = launch_publish(c, (int)nout)) return rc;
+    } else {
+        if (int rc = ensure_h_counts(c, nout)) return rc;
+        MPGPU_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counts, nout * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (int rc = fetch_wave_counts(c)) return rc;
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        c->counts_dirty = nout + 1;
     }
-    MPGPU_CUDA(cudaMemcpyAsync(c->h_counts, c->d_counts, nout * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     settle_views(c, true);
     if (!c->lens_valid) { set_error("view lengths not set"); return 1; }
     const size_t ntasks = pl.tasks.size();
@@ -442,16 +690,21 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
 int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int mintrav, int maxtrav)
 {
     ScanPlan &pl = c->plan;
+    const uint8_t *vstale = c->n_stale ? c->vstale.data() : nullptr;      // lazy views: the planner notes the stale views it reads
     if (c->sk.on) {          // one piece: the per-(candidate, segment) output is sized from the finished plan
-        if (int rc = build_scan_plan(c->tree, order, first, count, mintrav, maxtrav, (uint32_t)(c->sk.vstride / 4), pl)) return rc;
+        ScanPlanner planner;
+        if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, (uint32_t)(c->sk.vstride / 4), pl, false, vstale)) return rc;
+        planner.add(0, count);
+        planner.finish();
+        if (int rc = ensure_views(c, pl.need_refs.data(), (int)pl.need_refs.size(), false)) return rc;
         if (int rc = upload_plan(c)) return rc;
         return sk_run_scan(c);
     }
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
     ScanPlanner planner;
-    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl)) return rc;
+    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl, false, vstale)) return rc;
     if (int rc = reserve_plan(c)) return rc;
-    MPGPU_CUDA(cudaMemsetAsync(c->d_counts, 0, ((size_t)pl.task_cap + pl.cand_ref.size() + 1) * sizeof(int32_t), c->stream));
+    if (int rc = zero_counts(c, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep): 1: 0.338 ms, 2: 0.316 ms, 4: 0.337 ms, 6: 0.390 ms e2e
     if (const char *e = getenv("MPGPU_SCAN_PIECES")) { int v = atoi(e); if (v >= 1) pieces = v; }
     int v0 = 0;
@@ -460,6 +713,10 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         const int v1 = k == pieces - 1 ? count : std::min(count, v0 + std::max(1, (int)((long long)count * (k + 1) / (pieces * (pieces + 1) / 2))));
         const int ops0 = pl.n_ops, task0 = (int)pl.tasks.size();
         planner.add(v0, v1);
+        if (!pl.need_refs.empty()) {
+            if (int rc = ensure_views(c, pl.need_refs.data(), (int)pl.need_refs.size(), true)) return rc;
+            pl.need_refs.clear();
+        }
         if (int rc = upload_plan_range(c, ops0, task0)) return rc;
         if (int rc = launch_scan(c, task0, (int)pl.tasks.size() - task0, pl.max_slot)) return rc;
         v0 = v1;
@@ -492,6 +749,13 @@ int compute_site_counters(Ctx *c, int nbits)
     }
     pairs[k++] = t.vid(3); pairs[k++] = t.vid(t.back(3));
     const int npairs = (int)k / 2;
+    if (c->n_stale) {                          // inside an SPR search (lazy views): the views facing tr->start must be current
+        std::vector<int32_t> &refs = c->sc_refs;
+        refs.clear();
+        for (int i = n + 1; i <= 2 * n - 2; i++) { const int r = order[i]; refs.push_back(t.back(t.next(r))); refs.push_back(t.back(t.next(t.next(r)))); }
+        refs.push_back(t.back(3));
+        if (int rc = ensure_views(c, refs.data(), (int)refs.size(), true)) return rc;
+    }
     if (int rc = ensure(c->d_pairs, c->pairs_cap, k)) return rc;
     if (int rc = ensure(c->d_bitcnt, c->bitcnt_cap, (size_t)16 * c->Wl)) return rc;
     MPGPU_CUDA(cudaMemcpyAsync(c->d_pairs, pairs, k * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -576,6 +840,7 @@ int mpgpu_destroy(mpgpu_ctx *c)
     if (c->d_tasks) cudaFree(c->d_tasks);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->d_bitcnt) cudaFree(c->d_bitcnt);
     if (c->d_pairs) cudaFree(c->d_pairs);
     if (c->d_ptn) cudaFree(c->d_ptn);

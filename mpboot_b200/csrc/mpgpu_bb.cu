@@ -595,6 +595,8 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
         return v > (double)nvisit ? nvisit : (v < 16.0 ? 16 : (int)v);
     }();
     int since_move = 0;
+    static const bool eager_views = getenv("MPGPU_EAGER_VIEWS") != nullptr;
+    const bool lazy = !eager_views && c->kids_valid && c->lens_valid;
     auto after_move_batch = [spec_cap](double gap) {
         static const int fixed = getenv("MPGPU_SEARCH_BATCH") ? atoi(getenv("MPGPU_SEARCH_BATCH")) : 0;   // tuning knob
         if (fixed > 0) return fixed;
@@ -671,7 +673,10 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 if ((bestParsimony < randomMP ||
                      (bestParsimony == randomMP && rng(rng_user) <= 1.0 / bestIterationScoreHits)) &&
                     removeNode && insertNode) {
+                    const int pa = c->tree.back(c->tree.next(removeNode)), pb = c->tree.back(c->tree.next(c->tree.next(removeNode)));
+                    const int touched[5] = {removeNode / 3, pa / 3, pb / 3, insertNode / 3, c->tree.back(insertNode) / 3};
                     apply_spr_move(c->tree, removeNode, insertNode);              // :3312
+                    if (lazy) mark_stale_nodes(c, touched, 5);
                     randomMP = bestParsimony;
                     cur_score = bestParsimony;
                     moved = true;
@@ -682,11 +687,15 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             prof.stop(3);
             if (moved) {
                 prof.start();
-                // the stale views are recomputed behind the host's back: the next batch is planned and launched
-                // while k_fitch_wave runs, and its counts land with that batch's read-back (finish_scan)
-                c->tree_set = true; c->lens_valid = false;
-                if (int rc = update_views(c, true)) return rc;
-                if (!c->wave_pending) compute_lengths(c);
+                // lazy views: the move only marked the views it invalidated; the next batch recomputes the ones it reads.
+                // Eager scheme (MPGPU_EAGER_VIEWS): every stale view now, behind the host's back -- the next batch is
+                // planned and launched while k_fitch_wave runs, its counts land with that batch's read-back (finish_scan)
+                c->tree_set = true;
+                if (!lazy) {
+                    c->lens_valid = false;
+                    if (int rc = update_views(c, true)) return rc;
+                    if (!c->wave_pending) compute_lengths(c);
+                }
                 move_gap = 0.75 * move_gap + 0.25 * (double)(since_move + v);   // visits since the previous move
                 since_move = 0;
                 batch = after_move_batch(move_gap);
@@ -698,7 +707,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
         }
     } while (randomMP < startMP);
     if ((double)since_move > move_gap) move_gap = 0.75 * move_gap + 0.25 * (double)since_move;   // a quiet search: speculate deeper next time
-    if (c->wave_pending) { MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, true); }
+    if (c->wave_pending) { if (int rc = fetch_wave_counts(c)) return rc; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, true); }
     if (cumulative) {
         static bool registered = false;
         if (!registered) { registered = true; atexit([]() { g_sp.report(prof_names, 6); g_rp.report(g_rp_names, 8); }); }
@@ -807,6 +816,7 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         if ((rc = launch_tip_insert(c, d_edges, ne, d_ins))) break;
         if ((rc = shard_sum(c, d_ins, ne))) break;
         e = cudaMemcpyAsync(ins.data(), d_ins, (size_t)ne * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && fetch_wave_counts(c)) { rc = 1; break; }
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "stepwise addition read-back"); break; }
         }
@@ -837,7 +847,8 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         if (!c->wave_pending) compute_lengths(c);
     }
     if (!rc && c->wave_pending) {
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "stepwise addition");
+        if (fetch_wave_counts(c)) rc = 1;
+        else if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "stepwise addition");
         else settle_views(c, true);
     }
     if (d_edges) cudaFree(d_edges);

@@ -61,7 +61,7 @@ struct ScanTask {
     int32_t pad;
 };
 
-// Page-locked host array: the plan streams are uploaded piece by piece while the host keeps
+// Page-locked (and device-mapped: k_publish writes wave counts straight into one) host array: the plan streams are uploaded piece by piece while the host keeps
 // appending, so the copies must be truly asynchronous (pageable memory is staged synchronously).
 template <typename T> struct PinnedArray {
     T *p = nullptr; size_t cap = 0;
@@ -73,7 +73,7 @@ template <typename T> struct PinnedArray {
         if (n <= cap) return true;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        if (cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+        if (cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
         cap = n;
         return true;
     }
@@ -92,6 +92,7 @@ struct ScanPlan {
     std::vector<int32_t> visit_begin;     // count+1
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
     std::vector<int32_t> task_vids;       // view ids of S, D1, D2 per task
+    std::vector<int32_t> need_refs;       // ring slots whose (stale) views the plan reads, duplicates possible (lazy views)
     std::vector<uint32_t> task_const;     // len(S)+len(D1)+len(D2) per task (filled by finish_scan from the view lengths)
     int n_cand = 0;                      // candidates / ops actually used (the vectors are sized to an upper bound)
     int n_ops = 0;
@@ -213,6 +214,8 @@ struct PeerExchange {
     int64_t calls = 0, elements = 0;
 };
 
+struct PendingWave { int list_off, total, wc_off; bool incremental; };
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -263,7 +266,16 @@ struct Ctx {
     // incremental update after a move (update_views): children of every view at its last compute
     std::vector<int2> view_kids; bool kids_valid = false;
     PinnedArray<Triple> wave_pin; PinnedArray<uint32_t> wcount_pin;
-    int wave_pending = 0, wave_hdr = 0;   // deferred update_views: counts in flight (settle_views after the next synchronize)
+    int wave_pending = 0;                 // views whose recomputation is in flight (settle_views after the next synchronize)
+    std::vector<PendingWave> wave_lists;  // the lists in flight, in launch order
+    size_t wave_used = 0, wc_used = 0;    // staging consumed by them (Triples of wave_pin / d_wave, counters of wcount_pin / d_wcount)
+    bool wave_fetched = false;            // their counts are on the way to wcount_pin (fetch_wave_counts / k_publish)
+    bool wcount_zeroed = false;           // d_wcount is all zero outside the lists in flight
+    // lazy views of the SPR search: after a move only the views the next scan batch reads are recomputed (ensure_views)
+    std::vector<uint8_t> vstale;          // [4n-6] the view's content is out of date
+    int n_stale = 0;
+    std::vector<int32_t> sc_refs;         // scratch: ring slots handed to ensure_views
+    bool dl_dirty = false;                // sc_dl holds levels of an abandoned list
     Triple *d_wave = nullptr; size_t wave_cap = 0;
     uint32_t *d_wcount = nullptr; size_t wcount_cap = 0;
     uint32_t *d_scalar = nullptr;         // small scratch for scalar results
@@ -275,6 +287,9 @@ struct Ctx {
     ScanTask *d_tasks = nullptr; size_t tasks_cap = 0;
     int32_t *d_counts = nullptr; size_t counts_cap = 0;
     int32_t *h_counts = nullptr; size_t h_counts_cap = 0;   // pinned read-back buffer (bytes)
+    size_t counts_dirty = 0;              // leading ints of d_counts that may be non-zero (zero_counts clears them before a scan)
+    uint32_t *h_flag = nullptr;           // mapped page-locked word k_publish writes last: the host spins on it instead of a stream synchronize
+    uint32_t flag_epoch = 0;
 
     // pattern scores
     uint32_t *d_bitcnt = nullptr; size_t bitcnt_cap = 0;   // bit-sliced per-site counters
@@ -297,7 +312,9 @@ struct Ctx {
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
-#define MPGPU_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return ::mpgpu::cuda_fail(e__, #expr); } while (0)
+#define MPGPU_STR2(x) #x
+#define MPGPU_STR(x) MPGPU_STR2(x)
+#define MPGPU_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return ::mpgpu::cuda_fail(e__, #expr " (" __FILE__ ":" MPGPU_STR(__LINE__) ")"); } while (0)
 
 template <typename T>
 static inline int ensure(T *&ptr, size_t &cap, size_t need)
@@ -318,7 +335,14 @@ int shard_sum(Ctx *c, void *dev_i32, int64_t count);   // in-place int32 all-red
 int compute_views(Ctx *c, bool want_start_edge = false);
 int set_tree_impl(Ctx *c, const int32_t *back_node, const int32_t *back_slot, bool want_start_edge);
 int update_views(Ctx *c, bool defer = false);   // after apply_spr_move on c->tree: recompute only the stale views, one launch
-void settle_views(Ctx *c, bool lengths);        // after a stream synchronize: land the counts of a deferred update_views
+int submit_stale(Ctx *c, std::vector<Triple> &stale, int nlevels, bool defer, bool incremental);
+int fetch_wave_counts(Ctx *c);                  // before the stream synchronize that precedes settle_views
+void settle_views(Ctx *c, bool lengths);        // after that synchronize: land the counts of the deferred view updates
+void mark_stale_nodes(Ctx *c, const int *nodes, int k);   // lazy scheme: the adjacency of these nodes changed
+int ensure_views(Ctx *c, const int32_t *refs, int count, bool defer);   // recompute the stale ones among the views behind these ring slots (and what they depend on)
+int ensure_all_views(Ctx *c);
+int zero_counts(Ctx *c, size_t n);              // d_counts[0, n) = 0 before a scan
+int launch_publish(Ctx *c, int nout);           // counts (and the wave counts in flight) -> mapped host memory, device counters back to zero, flag
 void compute_lengths(Ctx *c);
 int need_tree(Ctx *c, bool lens);
 int run_scan(Ctx *c);
@@ -379,7 +403,8 @@ public:
     ScanPlanner();
     ~ScanPlanner();
     int begin(const HostTree &t, const int32_t *order, int first, int count,
-              int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan, bool host_only = false);
+              int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan, bool host_only = false,
+              const uint8_t *vstale = nullptr);
     void add(int v0, int v1);
     void finish();
 private:

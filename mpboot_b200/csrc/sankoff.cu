@@ -808,6 +808,7 @@ int sk_update_stale(Ctx *c, std::vector<Triple> &stale, int nlevels)
     MPGPU_CUDA(cudaMemcpyAsync(c->wcount_pin.data(), c->d_wcount, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < total; i++) c->vcount[dst[i].dst] = c->wcount_pin.data()[i];
+    c->wcount_zeroed = false;                // the Fitch wave expects zeroed counters
     return 0;
 }
 
@@ -1045,6 +1046,10 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
     {
         const HostTree &t = c->tree;
         const int rr = t.back(3);
+        if (c->n_stale) {                      // inside an SPR search (lazy views)
+            const int32_t need[2] = {t.back(t.next(rr)), t.back(t.next(t.next(rr)))};
+            if (int rc = ensure_views(c, need, 2, false)) return rc;
+        }
         const int4 j = make_int4(t.vid(3), t.vid(t.back(t.next(rr))), t.vid(t.back(t.next(t.next(rr)))), 0);
         if (int rc = sk_ensure_out(c, 1)) return rc;
         if (int rc = ensure(k.d_list, k.list_cap, (size_t)1)) return rc;

@@ -42,19 +42,20 @@ struct Builder {
     const int n;
     ScanPlan &plan;
     // per ref, one record (one cache line touch per visited node): back(next(ref)), back(next(next(ref))), view offset, is-tip
-    struct Ref { int32_t c1, c2, voff, tip; };
+    struct Ref { int32_t c1, c2, voff, tip; };      // tip: bit 0 = the node is a tip, bit 1 = its view is stale (lazy views of the search)
     std::vector<Ref> ref_;
     // views of the same data for the callers that index by field
     struct Field1 { const std::vector<Ref> &r; int32_t operator[](int i) const { return r[i].c1; } } c1{ref_};
     struct Field2 { const std::vector<Ref> &r; int32_t operator[](int i) const { return r[i].c2; } } c2{ref_};
-    struct FieldT { const std::vector<Ref> &r; bool operator[](int i) const { return r[i].tip != 0; } } tip{ref_};
+    struct FieldT { const std::vector<Ref> &r; bool operator[](int i) const { return (r[i].tip & 1) != 0; } } tip{ref_};
+    bool lazy = false;                   // some views are stale: every view the plan reads is checked (need)
     int prune_ref = 0, task_index = 0, cand_base = 0;
     // raw cursors into the plan's arrays (sized up front)
     ScanOffs *offs = nullptr; ScanCtl *ctl = nullptr;
     int32_t *cand_ref = nullptr, *cand_prune = nullptr, *cand_task = nullptr;
     int nops = 0, ncand = 0, max_slot = 0;
 
-    Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride) : n(t.n), plan(pp)
+    Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride, const uint8_t *vstale) : n(t.n), plan(pp), lazy(vstale != nullptr)
     {
         const int nref = 3 * (2 * n - 1);
         ref_.assign(nref, Ref{0, 0, 0, 1});
@@ -64,7 +65,7 @@ struct Builder {
                 const int r = 3 * node + sl;
                 ref_[r].voff = (int32_t)((uint32_t)t.vid(r) * vstride);
                 if (node > n) {
-                    ref_[r].tip = 0;
+                    ref_[r].tip = vstale && vstale[t.vid(r)] ? 2 : 0;
                     const int a = 3 * node + (sl + 1) % 3, b = 3 * node + (sl + 2) % 3;
                     ref_[r].c1 = t.back(a); ref_[r].c2 = t.back(b);
                 }
@@ -72,6 +73,8 @@ struct Builder {
         }
     }
     int32_t voff(int ref) const { return ref_[ref].voff; }
+    // the plan reads the view behind `ref`: noted when it is stale (once per plan)
+    void need(int ref) { if (ref_[ref].tip & 2) { ref_[ref].tip &= ~2; plan.need_refs.push_back(ref); } }
 
     // One expand op for the node whose children (seen from it) are a and b; src = where its up-view comes from.
     // The op's control words are built in registers while the children are walked and stored once.
@@ -79,6 +82,7 @@ struct Builder {
     {
         const int me = nops++;
         offs[me].c1 = ref_[a].voff; offs[me].c2 = ref_[b].voff;
+        if (lazy) { need(a); need(b); }
         uint32_t outs = 0xFFFFFFFFu, meta = src | 0xFF00u | 0xFF0000u;
         child(a, 0, mintrav, maxtrav, depth, outs, meta);
         child(b, 1, mintrav, maxtrav, depth, outs, meta);
@@ -96,7 +100,7 @@ struct Builder {
             outs = which == 0 ? ((outs & 0xFFFF0000u) | rel) : ((outs & 0x0000FFFFu) | (rel << 16));
         }
         const Ref &rx = ref_[x];
-        if (!rx.tip && (--maxtrav > 0)) {
+        if (!(rx.tip & 1) && (--maxtrav > 0)) {
             // U_x goes here.  The first child is expanded by the very next op, which reads its up-view before it writes
             // anything, so first children only need two slots, alternating with the depth (never the slot the op itself
             // reads); a second child waits for the first child's whole subtree and gets the slot of its depth.
@@ -136,17 +140,17 @@ struct ScanPlanner::Impl {
     const int32_t *order;
     int first, mintrav, maxtrav;
     Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const int32_t *ord,
-         int f, int mi, int ma) : b(tt, plan, vstride), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
+         int f, int mi, int ma, const uint8_t *vstale) : b(tt, plan, vstride, vstale), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
 };
 
 ScanPlanner::ScanPlanner() : impl(nullptr) {}
 ScanPlanner::~ScanPlanner() { delete impl; }
 
 int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int count,
-                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan, bool host_only)
+                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan, bool host_only, const uint8_t *vstale)
 {
     delete impl; impl = nullptr;
-    plan.tasks.clear(); plan.visit_begin.clear(); plan.task_vids.clear();
+    plan.tasks.clear(); plan.visit_begin.clear(); plan.task_vids.clear(); plan.need_refs.clear();
     plan.n_cand = 0; plan.n_ops = 0; plan.max_slot = 0;
     plan.task_cap = 2 * count;
     const int n = t.n;
@@ -154,7 +158,7 @@ int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int c
     if (maxtrav > n - 3) maxtrav = n - 3;                       // :2275 (tr->ntips == mxtips during the search)
     if (maxtrav > kMaxTrav) { set_error("maxtrav exceeds the scan kernel's stack depth"); return 1; }   // slots < 0xFE
     if ((uint64_t)(4 * n - 6) * vstride >= 0x7fffffffULL) { set_error("view array too large for 32-bit scan offsets"); return 1; }
-    impl = new Impl(t, plan, vstride, order, first, mintrav, maxtrav);
+    impl = new Impl(t, plan, vstride, order, first, mintrav, maxtrav, vstale);
     Builder &b = impl->b;
     // upper bounds: one side of a visit reaches at most 4 * (2^maxtrav - 1) branches, never more than the tree has
     const size_t per_side = std::min<size_t>((size_t)4 << std::max(maxtrav, 0), (size_t)2 * n);
@@ -193,6 +197,7 @@ void ScanPlanner::add(int v0, int v1)
                 task.op_begin = b.nops; task.base_out = (int)plan.tasks.size(); task.cand_base = plan.task_cap + b.ncand; task.pad = 0;
                 b.cand_base = b.ncand;
                 b.prune_ref = p; b.task_index = (int)plan.tasks.size();
+                if (b.lazy) { b.need(q); b.need(p1); b.need(p2); b.need(p); }     // p itself: the -bb edge row of the task reads both sides of (p, q)
                 if (!b.tip[p1]) b.expand_top(p1, 0xFFu, mintrav, maxtrav);
                 if (!b.tip[p2]) b.expand_top(p2, 0xFEu, mintrav, maxtrav);
                 b.end_task();
@@ -212,6 +217,7 @@ void ScanPlanner::add(int v0, int v1)
                 task.op_begin = b.nops; task.base_out = (int)plan.tasks.size(); task.cand_base = plan.task_cap + b.ncand; task.pad = 0;
                 b.cand_base = b.ncand;
                 b.prune_ref = q; b.task_index = (int)plan.tasks.size();
+                if (b.lazy) { b.need(p); b.need(q1); b.need(q2); b.need(q); }
                 if (!b.tip[q1]) b.expand_top(q1, 0xFFu, mintrav2, maxtrav);
                 if (!b.tip[q2]) b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
                 b.end_task();
