@@ -248,14 +248,35 @@ int launch_level(Ctx *c, const Triple *d_triples, int ntriples)
 // Triple.pad = a_slot | dst_slot << 8 | b_clean << 16 (slots 0xFF: not cached).  list = hdr
 // Triples reinterpreted as int32 level ends, then the triples; wcount[k] += popc(t_N) of triple k.
 // ------------------------------------------------------------------------------------------
+// host-mapped plan ranges -> their device arrays, spread over the grid (see StageArgs)
+__device__ __forceinline__ void stage_copy(const StageArgs &st, int first, int stride)
+{
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        for (int i = first; i < st.n[k]; i += stride) st.dst[k][i] = st.src[k][i];
+}
+__global__ void __launch_bounds__(256) k_stage(const StageArgs st) { stage_copy(st, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+
+int launch_stage(Ctx *c)
+{
+    if (!c->stage_pending) return 0;
+    c->stage_pending = false;
+    k_stage<<<8, 256, 0, c->stream>>>(c->stage_req);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int S> struct WaveCfg { static const int CAP = S <= 4 ? 32 : (S <= 20 ? 16 : 12); };
 
 template <int S, int NW>
 __global__ void __launch_bounds__(32 * NW) k_fitch_wave(uint32_t *views, size_t view_stride, int Wl,
                                                         const Triple *__restrict__ list, int nlevels, int hdr, int total,
-                                                        uint32_t *__restrict__ wcount)
+                                                        uint32_t *__restrict__ wcount, const StageArgs st)
 {
     extern __shared__ uint4 wave_smem[];
+    // the next scan's plan rides along (latency path of the search): one extra CTA copies it while the others update views
+    if (blockIdx.x * 32 >= Wl) { stage_copy(st, threadIdx.x, blockDim.x); return; }
     const int CAP = WaveCfg<S>::CAP;
     int4 *sl = reinterpret_cast<int4 *>(wave_smem);
     uint32_t *cache = reinterpret_cast<uint32_t *>(sl + hdr + total);
@@ -331,7 +352,10 @@ static int launch_wave_t(Ctx *c, const Triple *d_list, int nlevels, int hdr, int
         MPGPU_CUDA(cudaFuncSetAttribute(k_fitch_wave<S, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         opted = smem;
     }
-    k_fitch_wave<S, NW><<<c->Wl / 32, 32 * NW, smem, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_list, nlevels, hdr, total, d_wcount);
+    StageArgs st = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {0, 0, 0}};
+    if (c->stage_pending) { st = c->stage_req; c->stage_pending = false; }
+    const bool staging = st.n[0] + st.n[1] + st.n[2] > 0;
+    k_fitch_wave<S, NW><<<c->Wl / 32 + (staging ? 1 : 0), 32 * NW, smem, c->stream>>>(c->d_views, c->view_stride, c->Wl, d_list, nlevels, hdr, total, d_wcount, st);
     return 0;
 }
 
@@ -595,7 +619,7 @@ template <int S, int VW> struct WideVec {
 // control-word decode, the offs / ctl loads, the branches and the address arithmetic of an op are paid once for VW
 // chunks and a scored child costs one REDUX + one RED (r02: 66 -> ~38 warp instructions per insertion and chunk).
 template <int S, bool PF, bool ROWS, int VW>
-__global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int Wl,
+__device__ __forceinline__ void scan_body(const typename VecOf<S>::T *__restrict__ views, int Wl,
                            const ScanTask *__restrict__ tasks, int ntasks,
                            const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
                            int nslots, int32_t *__restrict__ out,
@@ -636,7 +660,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
         b.load(vbase + (uint32_t)t0.y, gsv);
         c.load(vbase + (uint32_t)t0.z, gsv);
         a.unpack(Sv);
-        if (!ROWS) {
+        if (!ROWS && t1.y >= 0) {                   // (a sub-task with base_out < 0 leaves the joined-edge count to its first sibling)
             uint32_t d1[VW][S], d2[VW][S];
             b.unpack(d1); c.unpack(d2);
             int pc = 0;
@@ -658,7 +682,7 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
     A0.load(vbase + (uint32_t)f0.x, gsv);
     B0.load(vbase + (uint32_t)f0.y, gsv);
 
-#define MPGPU_SCAN_STEP(AC, BC, AN, BN, FCUR, FNEXT, FLOAD)                                            \
+#define MPGPU_SCAN_STEP(AC, BC, AN, BN, FCUR, FNEXT, FLOAD, CWCUR, CWNEXT)                             \
     {                                                                                                  \
         if (PF) {                                                                                      \
             if (oi + 1 < oe) { AN.load(vbase + (uint32_t)FNEXT.x, gsv); BN.load(vbase + (uint32_t)FNEXT.y, gsv); } \
@@ -666,7 +690,8 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
             AC.load(vbase + (uint32_t)FCUR.x, gsv); BC.load(vbase + (uint32_t)FCUR.y, gsv);            \
         }                                                                                              \
         if (oi + 2 < oe) FLOAD = __ldg(offs + oi + 2);                                                 \
-        const int2 cw = __ldg(ctl + oi);                                                               \
+        const int2 cw = CWCUR;                                                                         \
+        if (oi + 1 < oe) CWNEXT = __ldg(ctl + oi + 1);      /* the control word of the next op, one op ahead */ \
         const uint32_t src = cw.y & 0xff, dst1 = (cw.y >> 8) & 0xff, dst2 = (cw.y >> 16) & 0xff;       \
         const uint32_t o1 = cw.x & 0xffff, o2 = (uint32_t)cw.x >> 16;                                  \
         /* src 0 / 1: the up-view the previous op left in U (its first child, expanded right away) */  \
@@ -696,18 +721,52 @@ __global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int W
 #pragma unroll
         for (int k = 0; k < S; k++) U[j][k] = 0;
 
+    int2 cw0 = __ldg(ctl + oi), cw1 = cw0;
     for (;;) {
-        MPGPU_SCAN_STEP(A0, B0, A1, B1, f0, f1, f0)
+        MPGPU_SCAN_STEP(A0, B0, A1, B1, f0, f1, f0, cw0, cw1)
         if (++oi >= oe) break;
-        MPGPU_SCAN_STEP(A1, B1, A0, B0, f1, f0, f1)
+        MPGPU_SCAN_STEP(A1, B1, A0, B0, f1, f0, f1, cw1, cw0)
         if (++oi >= oe) break;
     }
 #undef MPGPU_SCAN_STEP
 }
 
-template <int S, bool ROWS, int VW, bool PF4 = false>
+// pub.flag != nullptr (latency path of the search): the block that finishes last copies the counts -- and the counts of the
+// view updates in flight -- to mapped page-locked memory, puts the device counters back to zero and raises the flag the
+// host spins on: no copy engine, no second launch, no stream synchronize in the step.
+template <int S, bool PF, bool ROWS, int VW, bool PUB>
+__global__ void k_spr_scan(const typename VecOf<S>::T *__restrict__ views, int Wl,
+                           const ScanTask *__restrict__ tasks, int ntasks,
+                           const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
+                           int nslots, int32_t *__restrict__ out,
+                           const int32_t *__restrict__ task_ids, const int32_t *__restrict__ row_of, int row_bias,
+                           uint32_t *__restrict__ rows, const PubArgs pub)
+{
+    scan_body<S, PF, ROWS, VW>(views, Wl, tasks, ntasks, offs, ctl, nslots, out, task_ids, row_of, row_bias, rows);
+    if (!PUB) return;              // (a template parameter: the tail costs the wide variants 14 registers, i.e. a resident CTA)
+    __shared__ int s_last;
+    __syncthreads();                                 // every RED of this block is issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(pub.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < pub.nout; i += blockDim.x) { pub.host_counts[i] = __ldcg(out + i); out[i] = 0; }
+    for (int i = threadIdx.x; i < pub.nwc; i += blockDim.x) { pub.host_wc[i] = __ldcg(pub.wcount + i); pub.wcount[i] = 0; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {          // (every thread fenced its own writes at system scope before the barrier)
+        *pub.done = 0;
+        *reinterpret_cast<volatile uint32_t *>(pub.flag) = pub.epoch;
+    }
+}
+
+template <int S, bool ROWS, int VW, bool PF4 = false, bool PUB = false>
 static int launch_scan_v(Ctx *c, int task0, int ntasks, int nslots)
 {
+    if (!PUB && !ROWS && VW == 1 && !PF4 && c->pub_request) return launch_scan_v<S, ROWS, VW, PF4, !ROWS && VW == 1>(c, task0, ntasks, nslots);
     typedef typename VecOf<S>::T V;
     constexpr bool PF = S <= 4 && (VW <= 2 || PF4);
     nslots = nslots > 2 ? nslots - 2 : 1;       // the planner's slots 0 / 1 live in registers (see k_spr_scan)
@@ -720,16 +779,25 @@ static int launch_scan_v(Ctx *c, int task0, int ntasks, int nslots)
     if (smem > 200 * 1024) { set_error("scan stack does not fit in shared memory"); return 1; }
     static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (smem > 48 * 1024 && smem > configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF, ROWS, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        MPGPU_CUDA(cudaFuncSetAttribute(k_spr_scan<S, PF, ROWS, VW, PUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         configured = 200 * 1024;
     }
     const long long warps = (long long)ntasks * (c->Wl / (kChunkWords * VW));
     const long long blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL || warps > 0xffffffffLL) { set_error("scan grid too large"); return 1; }
-    k_spr_scan<S, PF, ROWS, VW><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
+    PubArgs pub = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0u};
+    if (PUB && c->pub_request) {
+        c->pub_request = false;
+        c->flag_epoch++;
+        if (c->flag_epoch == 0) c->flag_epoch = 1;
+        pub.host_counts = c->h_counts; pub.host_wc = c->wcount_pin.data(); pub.wcount = c->d_wcount; pub.flag = c->h_flag; pub.done = c->d_done;
+        pub.nout = c->pub_nout; pub.nwc = (int)c->wc_used; pub.epoch = c->flag_epoch;
+        c->pub_inflight = true;
+    }
+    k_spr_scan<S, PF, ROWS, VW, PUB><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(
         reinterpret_cast<const V *>(c->d_views), c->Wl, c->d_tasks + (ROWS ? 0 : task0), ntasks, reinterpret_cast<const int2 *>(c->d_offs),
         reinterpret_cast<const int2 *>(c->d_ctl), nslots, c->d_counts,
-        ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, c->plan.task_cap, ROWS ? c->d_rows_site : nullptr);
+        ROWS ? c->d_row_tasks : nullptr, ROWS ? c->d_row_of : nullptr, c->plan.task_cap, ROWS ? c->d_rows_site : nullptr, pub);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;

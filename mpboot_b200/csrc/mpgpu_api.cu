@@ -349,8 +349,12 @@ int submit_stale(Ctx *c, std::vector<Triple> &stale, int nlevels, bool defer, bo
         x.pad = a_slot | d_slot << 8 | (dl[tr.b] == 0 ? 0x10000 : 0);
         dst[at] = x;
     }
-    MPGPU_CUDA(cudaMemcpyAsync(c->d_wave + off, c->wave_pin.data() + off, (hdr + total) * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
-    if (int rc = launch_wave(c, c->d_wave + off, nlevels, hdr, (int)total, c->d_wcount + wc_off)) return rc;
+    // a short list is read by the kernel straight from the mapped staging array (every CTA reads it once: ~1 KB each over
+    // PCIe costs less than a copy-engine hop); a long one (the eager scheme: ~2n views) goes through device memory
+    const bool zero_copy = hdr + total <= 96;
+    if (!zero_copy)
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_wave + off, c->wave_pin.data() + off, (hdr + total) * sizeof(Triple), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_wave(c, zero_copy ? c->wave_pin.data() + off : c->d_wave + off, nlevels, hdr, (int)total, c->d_wcount + wc_off)) return rc;
     if (c->shard_count > 1) { if (int rc = shard_sum(c, c->d_wcount + wc_off, (int64_t)total)) return rc; }
     PendingWave pw; pw.list_off = (int)(off + hdr); pw.total = (int)total; pw.wc_off = (int)wc_off; pw.incremental = incremental;
     c->wave_lists.push_back(pw);
@@ -542,9 +546,11 @@ static int upload_plan_range(Ctx *c, int ops0, int task0)
         MPGPU_CUDA(cudaMemcpyAsync(c->d_offs + ops0, pl.offs.data() + ops0, (size_t)nops * sizeof(ScanOffs), cudaMemcpyHostToDevice, c->stream));
         MPGPU_CUDA(cudaMemcpyAsync(c->d_ctl + ops0, pl.ctl.data() + ops0, (size_t)nops * sizeof(ScanCtl), cudaMemcpyHostToDevice, c->stream));
     }
-    if (nt > 0) {
+    const int nsub = (int)pl.sub_tasks.size();           // a split plan (single piece): the sub-tasks sit behind the tasks
+    if (nt + nsub > 0) {
         memcpy(pl.tasks_pin.data() + task0, pl.tasks.data() + task0, (size_t)nt * sizeof(ScanTask));
-        MPGPU_CUDA(cudaMemcpyAsync(c->d_tasks + task0, pl.tasks_pin.data() + task0, (size_t)nt * sizeof(ScanTask), cudaMemcpyHostToDevice, c->stream));
+        if (nsub) memcpy(pl.tasks_pin.data() + task0 + nt, pl.sub_tasks.data(), (size_t)nsub * sizeof(ScanTask));
+        MPGPU_CUDA(cudaMemcpyAsync(c->d_tasks + task0, pl.tasks_pin.data() + task0, (size_t)(nt + nsub) * sizeof(ScanTask), cudaMemcpyHostToDevice, c->stream));
     }
     return 0;
 }
@@ -555,7 +561,7 @@ static int reserve_plan(Ctx *c)
     ScanPlan &pl = c->plan;
     if (int rc = ensure(c->d_offs, c->offs_cap, pl.offs.size() + 1)) return rc;
     if (int rc = ensure(c->d_ctl, c->ctl_cap, pl.ctl.size() + 1)) return rc;
-    if (int rc = ensure(c->d_tasks, c->tasks_cap, (size_t)pl.task_cap + 1)) return rc;
+    if (int rc = ensure(c->d_tasks, c->tasks_cap, std::max(pl.item_cap, (size_t)pl.task_cap) + 1)) return rc;
     const int32_t *before = c->d_counts;
     if (int rc = ensure(c->d_counts, c->counts_cap, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     if (c->d_counts != before) c->counts_dirty = c->counts_cap;         // a fresh allocation is not zero
@@ -567,6 +573,23 @@ int upload_plan(Ctx *c)
     if (int rc = reserve_plan(c)) return rc;
     return upload_plan_range(c, 0, 0);
 }
+
+// MPGPU_PROFILE=3: device-side timeline of the single-piece batches of the search (CUDA events between the stream ops)
+// next to the host's: where a move's ~70 us go.  Printed at exit.
+struct BatchProf {
+    bool on = getenv("MPGPU_PROFILE") && atoi(getenv("MPGPU_PROFILE")) >= 3;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool armed = false;
+    std::chrono::steady_clock::time_point h0, h1, h2;
+    double dev[3] = {0, 0, 0}, host[3] = {0, 0, 0}; long n = 0;
+    void rec(int k, cudaStream_t s) { if (!ev[0]) for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[k], s); }
+    ~BatchProf() {
+        if (on && n) fprintf(stderr, "[mpgpu profile] %ld single-piece batches: device uploads+wave %.1f us, scan %.1f us, publish %.1f us | host plan+enqueue %.1f us, "
+                             "enqueue..flag %.1f us, flag..done(settle+mp) %.1f us\n", n, 1e3 * dev[0] / n, 1e3 * dev[1] / n, 1e3 * dev[2] / n,
+                             1e6 * host[0] / n, 1e6 * host[1] / n, 1e6 * host[2] / n);
+    }
+};
+static BatchProf g_bp;
 
 // d_counts[0, n) = 0 before a scan.  k_publish leaves the range it read zeroed, so in the search loop this is usually
 // nothing; any other reader leaves the counters dirty and the next scan pays one memset.
@@ -624,18 +647,12 @@ static int ensure_h_counts(Ctx *c, size_t nout)
 
 static const int kPublishMax = 16384;     // counters one k_publish block moves; larger read-backs take the copy engine
 
-int launch_publish(Ctx *c, int nout)
+// spin on the flag word; the stream is queried now and then so that a failed launch cannot hang the host
+static int wait_flag(Ctx *c)
 {
-    if (int rc = ensure_h_counts(c, (size_t)nout)) return rc;
-    c->flag_epoch++;
-    if (c->flag_epoch == 0) c->flag_epoch = 1;
-    k_publish<<<1, 512, 0, c->stream>>>(c->d_counts, nout, c->d_wcount, (int)c->wc_used, c->h_counts, c->wcount_pin.data(),
-                                        c->h_flag, c->flag_epoch);
-    c->launches++;
-    MPGPU_CUDA(cudaGetLastError());
+    if (g_bp.armed) g_bp.h1 = std::chrono::steady_clock::now();
     if (c->wave_pending) c->wave_fetched = true;
     c->counts_dirty = 0;
-    // spin on the flag; the stream is queried now and then so that a failed launch cannot hang the host
     volatile uint32_t *flag = c->h_flag;
     for (uint32_t spins = 1; *flag != c->flag_epoch; spins++) {
         if ((spins & 0xFFFF) == 0) {
@@ -647,7 +664,21 @@ int launch_publish(Ctx *c, int nout)
         __builtin_ia32_pause();
 #endif
     }
+    if (g_bp.armed) g_bp.h2 = std::chrono::steady_clock::now();
     return 0;
+}
+
+int launch_publish(Ctx *c, int nout)
+{
+    if (int rc = ensure_h_counts(c, (size_t)nout)) return rc;
+    c->flag_epoch++;
+    if (c->flag_epoch == 0) c->flag_epoch = 1;
+    k_publish<<<1, 512, 0, c->stream>>>(c->d_counts, nout, c->d_wcount, (int)c->wc_used, c->h_counts, c->wcount_pin.data(),
+                                        c->h_flag, c->flag_epoch);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    if (g_bp.armed) g_bp.rec(3, c->stream);
+    return wait_flag(c);
 }
 
 int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity)
@@ -657,7 +688,11 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
     if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
     static const bool no_publish = getenv("MPGPU_NO_PUBLISH") != nullptr;
-    if (!no_publish && c->shard_count == 1 && nout + c->wc_used <= (size_t)kPublishMax && (c->wc_used == 0 || c->wcount_pin.data())) {
+    if (c->pub_inflight) {                 // the scan's last block publishes (latency path)
+        c->pub_inflight = false;
+        if (g_bp.armed) g_bp.rec(3, c->stream);
+        if (int rc = wait_flag(c)) return rc;
+    } else if (!no_publish && c->shard_count == 1 && nout + c->wc_used <= (size_t)kPublishMax && (c->wc_used == 0 || c->wcount_pin.data())) {
         if (int rc = launch_publish(c, (int)nout)) return rc;
     } else {
         if (int rc = ensure_h_counts(c, nout)) return rc;
@@ -682,6 +717,16 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
     if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
     if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
     if (cand_prune) memcpy(cand_prune, pl.cand_prune.data(), pl.n_cand * sizeof(int32_t));
+    if (g_bp.armed && g_bp.ev[3] && cudaEventSynchronize(g_bp.ev[3]) == cudaSuccess) {
+        const auto h3 = std::chrono::steady_clock::now();
+        float ms;
+        for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&ms, g_bp.ev[k], g_bp.ev[k + 1]) == cudaSuccess) g_bp.dev[k] += ms;
+        g_bp.host[0] += std::chrono::duration<double>(g_bp.h1 - g_bp.h0).count();
+        g_bp.host[1] += std::chrono::duration<double>(g_bp.h2 - g_bp.h1).count();
+        g_bp.host[2] += std::chrono::duration<double>(h3 - g_bp.h2).count();
+        g_bp.n++;
+    }
+    g_bp.armed = false;
     return 0;
 }
 
@@ -701,28 +746,62 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         return sk_run_scan(c);
     }
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
-    ScanPlanner planner;
-    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl, false, vstale)) return rc;
-    if (int rc = reserve_plan(c)) return rc;
-    if (int rc = zero_counts(c, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep): 1: 0.338 ms, 2: 0.316 ms, 4: 0.337 ms, 6: 0.390 ms e2e
     if (const char *e = getenv("MPGPU_SCAN_PIECES")) { int v = atoi(e); if (v >= 1) pieces = v; }
+    // a small batch is latency-bound (one warp per task and chunk walks ~100 ops): cut its tasks into sub-tasks
+    static const int split_depth = getenv("MPGPU_SPLIT_DEPTH") ? atoi(getenv("MPGPU_SPLIT_DEPTH")) : 3;
+    static const int split_max = getenv("MPGPU_SPLIT_MAXCOUNT") ? atoi(getenv("MPGPU_SPLIT_MAXCOUNT")) : 16;
+    const int sd = pieces == 1 && count <= split_max && split_depth > 0 ? split_depth : 0;
+    g_bp.armed = g_bp.on && pieces == 1;
+    if (g_bp.armed) { g_bp.h0 = std::chrono::steady_clock::now(); g_bp.rec(0, c->stream); }
+    ScanPlanner planner;
+    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl, false, vstale, sd)) return rc;
+    if (int rc = reserve_plan(c)) return rc;
+    if (int rc = zero_counts(c, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     int v0 = 0;
     for (int k = 0; k < pieces; k++) {
         // early pieces are smaller: the device should get going as soon as possible
         const int v1 = k == pieces - 1 ? count : std::min(count, v0 + std::max(1, (int)((long long)count * (k + 1) / (pieces * (pieces + 1) / 2))));
         const int ops0 = pl.n_ops, task0 = (int)pl.tasks.size();
         planner.add(v0, v1);
+        if (sd) planner.split();
+        // latency path (one piece, one shard, a small plan): the plan rides to the device with the wave launch (or a k_stage
+        // launch) and the scan's last block publishes the counts -- no copy engine and no stream synchronize in the step
+        static const bool no_lean = getenv("MPGPU_NO_LEAN") != nullptr || getenv("MPGPU_NO_PUBLISH") != nullptr;
+        const size_t plan_bytes = (size_t)pl.n_ops * 16 + (pl.tasks.size() + pl.sub_tasks.size()) * sizeof(ScanTask);
+        const bool lean = !no_lean && pieces == 1 && c->shard_count == 1 && plan_bytes <= 96 * 1024;
+        if (lean) {
+            const size_t nt = pl.tasks.size(), nsub = pl.sub_tasks.size();
+            memcpy(pl.tasks_pin.data(), pl.tasks.data(), nt * sizeof(ScanTask));
+            if (nsub) memcpy(pl.tasks_pin.data() + nt, pl.sub_tasks.data(), nsub * sizeof(ScanTask));
+            StageArgs &st = c->stage_req;
+            st.src[0] = reinterpret_cast<const uint4 *>(pl.tasks_pin.data()); st.dst[0] = reinterpret_cast<uint4 *>(c->d_tasks); st.n[0] = (int)(nt + nsub) * 2;
+            st.src[1] = reinterpret_cast<const uint4 *>(pl.offs.data()); st.dst[1] = reinterpret_cast<uint4 *>(c->d_offs); st.n[1] = (pl.n_ops + 1) / 2;
+            st.src[2] = reinterpret_cast<const uint4 *>(pl.ctl.data()); st.dst[2] = reinterpret_cast<uint4 *>(c->d_ctl); st.n[2] = (pl.n_ops + 1) / 2;
+            c->stage_pending = true;
+        }
         if (!pl.need_refs.empty()) {
             if (int rc = ensure_views(c, pl.need_refs.data(), (int)pl.need_refs.size(), true)) return rc;
             pl.need_refs.clear();
         }
-        if (int rc = upload_plan_range(c, ops0, task0)) return rc;
-        if (int rc = launch_scan(c, task0, (int)pl.tasks.size() - task0, pl.max_slot)) return rc;
+        if (lean) {
+            if (int rc = launch_stage(c)) return rc;            // no wave was launched: the plan goes alone
+            const size_t nout = (size_t)pl.task_cap + pl.n_cand;
+            if (nout + c->wc_used <= (size_t)kPublishMax) {
+                if (int rc = ensure_h_counts(c, nout)) return rc;
+                if (!c->d_done) { MPGPU_CUDA(cudaMalloc((void **)&c->d_done, 64)); MPGPU_CUDA(cudaMemsetAsync(c->d_done, 0, 64, c->stream)); }
+                c->pub_request = true; c->pub_nout = (int)nout;
+            }
+        } else if (int rc = upload_plan_range(c, ops0, task0)) return rc;
+        if (g_bp.armed) g_bp.rec(1, c->stream);
+        if (!pl.sub_tasks.empty()) { if (int rc = launch_scan(c, (int)pl.tasks.size(), (int)pl.sub_tasks.size(), pl.max_slot)) return rc; }
+        else if (int rc = launch_scan(c, task0, (int)pl.tasks.size() - task0, pl.max_slot)) return rc;
+        c->pub_request = false;                 // (nothing was launched: finish_scan publishes on its own)
         v0 = v1;
         if (v0 >= count) break;
     }
     planner.finish();
+    if (g_bp.armed) g_bp.rec(2, c->stream);
     if (c->shard_count > 1 && c->reduces()) return shard_sum(c, c->d_counts, (int64_t)pl.task_cap + pl.n_cand);
     return 0;
 }
@@ -841,6 +920,7 @@ int mpgpu_destroy(mpgpu_ctx *c)
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->d_done) cudaFree(c->d_done);
     if (c->d_bitcnt) cudaFree(c->d_bitcnt);
     if (c->d_pairs) cudaFree(c->d_pairs);
     if (c->d_ptn) cudaFree(c->d_ptn);

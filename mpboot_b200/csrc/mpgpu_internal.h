@@ -56,7 +56,8 @@ struct ScanTask {
     int32_t s_vid;      // pruned subtree (view offset in vector units)
     int32_t d1, d2;     // the two views that become neighbours when the node is removed (offsets)
     int32_t op_begin, op_end;
-    int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge) = the task's index
+    int32_t base_out;   // output slot of popc(~any(D1&D2)) (length of the joined edge) = the task's index; -1: a sub-task
+                        // that leaves the count to the task's first sub-task
     int32_t cand_base;  // output slot of the task's first candidate = task_cap + its candidate index
     int32_t pad;
 };
@@ -92,6 +93,10 @@ struct ScanPlan {
     std::vector<int32_t> visit_begin;     // count+1
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
     std::vector<int32_t> task_vids;       // view ids of S, D1, D2 per task
+    std::vector<ScanTask> sub_tasks;      // latency path: the tasks cut into independent sub-tasks (ScanPlanner::split); device copy behind the tasks
+    std::vector<int32_t> task_tops;       // [2 * task] the task's top-level ops (-1: that side is a tip), recorded for split plans
+    std::vector<int32_t> kid_op;          // scratch of split plans: op tree
+    size_t item_cap = 0;                  // ScanTask slots of the device array (tasks + sub-tasks)
     std::vector<int32_t> need_refs;       // ring slots whose (stale) views the plan reads, duplicates possible (lazy views)
     std::vector<uint32_t> task_const;     // len(S)+len(D1)+len(D2) per task (filled by finish_scan from the view lengths)
     int n_cand = 0;                      // candidates / ops actually used (the vectors are sized to an upper bound)
@@ -214,6 +219,13 @@ struct PeerExchange {
     int64_t calls = 0, elements = 0;
 };
 
+// Latency path of the search (single-piece batches on one shard): no copy engine in the step.
+// StageArgs: up to three host-mapped ranges (in 16-byte units) the next wave launch -- or a k_stage launch when no view is
+// stale -- copies to their device arrays before the scan starts: the plan's tasks, offs and ctl streams.
+struct StageArgs { const uint4 *src[3]; uint4 *dst[3]; int n[3]; };
+// PubArgs: the scan kernel's last block publishes the counts (flag == nullptr: nothing to do), see k_spr_scan
+struct PubArgs { int32_t *host_counts; uint32_t *host_wc; uint32_t *wcount; uint32_t *flag; uint32_t *done; int nout, nwc; uint32_t epoch; };
+
 struct PendingWave { int list_off, total, wc_off; bool incremental; };
 
 struct Ctx {
@@ -287,6 +299,10 @@ struct Ctx {
     ScanTask *d_tasks = nullptr; size_t tasks_cap = 0;
     int32_t *d_counts = nullptr; size_t counts_cap = 0;
     int32_t *h_counts = nullptr; size_t h_counts_cap = 0;   // pinned read-back buffer (bytes)
+    StageArgs stage_req = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {0, 0, 0}}; bool stage_pending = false;
+    bool pub_request = false, pub_inflight = false;       // the next launch_scan publishes / a fused publish is in flight (finish_scan spins)
+    int pub_nout = 0;
+    uint32_t *d_done = nullptr;           // block ticket of the fused publish
     size_t counts_dirty = 0;              // leading ints of d_counts that may be non-zero (zero_counts clears them before a scan)
     uint32_t *h_flag = nullptr;           // mapped page-locked word k_publish writes last: the host spins on it instead of a stream synchronize
     uint32_t flag_epoch = 0;
@@ -371,6 +387,7 @@ int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref
 int launch_compress(Ctx *c);
 int launch_level(Ctx *c, const Triple *d_triples, int ntriples);
 int launch_wave(Ctx *c, const Triple *d_list, int nlevels, int hdr, int total, uint32_t *d_wcount);
+int launch_stage(Ctx *c);                        // the pending StageArgs alone (no wave to ride on)
 int wave_slot_cap(int S);
 size_t wave_smem_bytes(int S, int entries);      // dynamic shared memory of k_fitch_wave for a list of `entries` Triples
 int launch_edge_mismatch(Ctx *c, int vidA, int vidB, uint32_t *d_out);
@@ -404,9 +421,10 @@ public:
     ~ScanPlanner();
     int begin(const HostTree &t, const int32_t *order, int first, int count,
               int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan, bool host_only = false,
-              const uint8_t *vstale = nullptr);
+              const uint8_t *vstale = nullptr, int split_depth = 0);
     void add(int v0, int v1);
     void finish();
+    void split();
 private:
     struct Impl;
     Impl *impl;

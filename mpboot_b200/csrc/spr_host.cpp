@@ -54,6 +54,8 @@ struct Builder {
     ScanOffs *offs = nullptr; ScanCtl *ctl = nullptr;
     int32_t *cand_ref = nullptr, *cand_prune = nullptr, *cand_task = nullptr;
     int nops = 0, ncand = 0, max_slot = 0;
+    // op tree (recorded when the plan may be split into sub-tasks): the ops that expand an op's first / second child
+    int32_t *kid_op = nullptr;           // [2 * op], -1 = that child is not expanded
 
     Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride, const uint8_t *vstale) : n(t.n), plan(pp), lazy(vstale != nullptr)
     {
@@ -78,20 +80,22 @@ struct Builder {
 
     // One expand op for the node whose children (seen from it) are a and b; src = where its up-view comes from.
     // The op's control words are built in registers while the children are walked and stored once.
-    void expand(int a, int b, uint32_t src, int mintrav, int maxtrav, int depth)
+    int expand(int a, int b, uint32_t src, int mintrav, int maxtrav, int depth)
     {
         const int me = nops++;
         offs[me].c1 = ref_[a].voff; offs[me].c2 = ref_[b].voff;
         if (lazy) { need(a); need(b); }
         uint32_t outs = 0xFFFFFFFFu, meta = src | 0xFF00u | 0xFF0000u;
-        child(a, 0, mintrav, maxtrav, depth, outs, meta);
-        child(b, 1, mintrav, maxtrav, depth, outs, meta);
+        const int k1 = child(a, 0, mintrav, maxtrav, depth, outs, meta);
+        const int k2 = child(b, 1, mintrav, maxtrav, depth, outs, meta);
         ctl[me].outs = outs; ctl[me].meta = meta;
+        if (kid_op) { kid_op[2 * me] = k1; kid_op[2 * me + 1] = k2; }
+        return me;
     }
 
     // addTraverseParsimony(tr, pr, p, q, mintrav, maxtrav, doAll = FALSE) for q = x, the `which`-th child of the op being
     // built (outs / meta); depth is x's distance from the removed node (1-based).
-    void child(int x, int which, int mintrav, int maxtrav, int depth, uint32_t &outs, uint32_t &meta)
+    int child(int x, int which, int mintrav, int maxtrav, int depth, uint32_t &outs, uint32_t &meta)
     {
         if (--mintrav <= 0) {                                   // testInsertParsimony(p, x)
             const int idx = ncand++;
@@ -107,8 +111,9 @@ struct Builder {
             const int slot = which == 0 ? (depth & 1) : 1 + depth;
             meta = which == 0 ? ((meta & ~0xFF00u) | ((uint32_t)slot << 8)) : ((meta & ~0xFF0000u) | ((uint32_t)slot << 16));
             if (slot + 1 > max_slot) max_slot = slot + 1;
-            expand(rx.c1, rx.c2, (uint32_t)slot, mintrav, maxtrav, depth + 1);
+            return expand(rx.c1, rx.c2, (uint32_t)slot, mintrav, maxtrav, depth + 1);
         }
+        return -1;
     }
 
     // candidates [cand_base, ncand) belong to the task that just ended
@@ -121,9 +126,58 @@ struct Builder {
     // the two addTraverseParsimony calls made for one inner neighbour `nb` of the removed node:
     // candidates are the branches to nb's children; the far side of nb is the task's D2 (when nb
     // is the D1 neighbour, src code 0xFF) or D1 (src code 0xFE).
-    void expand_top(int nb, uint32_t src_code, int mintrav, int maxtrav)
+    int expand_top(int nb, uint32_t src_code, int mintrav, int maxtrav)
     {
-        expand(ref_[nb].c1, ref_[nb].c2, src_code, mintrav, maxtrav, 1);
+        return expand(ref_[nb].c1, ref_[nb].c2, src_code, mintrav, maxtrav, 1);
+    }
+
+    // ---- sub-tasks (latency path) ----------------------------------------------------------------------------------
+    // A small batch is latency-bound: one warp walks a task's ~100 ops one after the other while most of the device
+    // idles.  split() re-emits a task as independent sub-tasks, one per op at depth `sdepth` of the op tree (and per
+    // childless op above it): the ops on the path from the task's top-level op down to that op are replayed without their
+    // scores (an op above the split depth is scored by the first sub-task that passes through it) and with only the
+    // up-view of the followed child, then the op's whole subtree follows verbatim.  The stack slots of the original
+    // program stay valid because a sub-task is a prefix-closed slice of it.
+    struct PathStep { int op, which; };
+    std::vector<PathStep> path;
+    std::vector<uint8_t> scored;         // [op] an internal op above the split depth whose scores were already given to a sub-task
+
+    int subtree_end(int op) const        // ops are emitted in DFS order: [op, subtree_end) is the op's subtree
+    {
+        int last = op;
+        for (;;) {
+            const int k2 = kid_op[2 * last + 1], k1 = kid_op[2 * last];
+            if (k2 >= 0) last = k2; else if (k1 >= 0) last = k1; else break;
+        }
+        return last + 1;
+    }
+    void emit_sub(const ScanTask &lt, int head, bool &first)
+    {
+        ScanTask st = lt;
+        st.base_out = first ? lt.base_out : -1;
+        first = false;
+        st.op_begin = nops;
+        for (const PathStep &ps : path) {
+            const int me = nops++;
+            offs[me] = offs[ps.op];
+            uint32_t outs = 0xFFFFFFFFu, meta = ctl[ps.op].meta;
+            if (!scored[ps.op]) { outs = ctl[ps.op].outs; scored[ps.op] = 1; }
+            meta = ps.which == 0 ? (meta | 0xFF0000u) : (meta | 0xFF00u);       // only the followed child's up-view
+            ctl[me].outs = outs; ctl[me].meta = meta;
+        }
+        const int e = subtree_end(head);
+        memcpy(offs + nops, offs + head, (size_t)(e - head) * sizeof(ScanOffs));
+        memcpy(ctl + nops, ctl + head, (size_t)(e - head) * sizeof(ScanCtl));
+        nops += e - head;
+        st.op_end = nops;
+        plan.sub_tasks.push_back(st);
+    }
+    void split_op(const ScanTask &lt, int op, int depth, int sdepth, bool &first)
+    {
+        const int k1 = kid_op[2 * op], k2 = kid_op[2 * op + 1];
+        if (depth >= sdepth || (k1 < 0 && k2 < 0)) { emit_sub(lt, op, first); return; }
+        if (k1 >= 0) { path.push_back(PathStep{op, 0}); split_op(lt, k1, depth + 1, sdepth, first); path.pop_back(); }
+        if (k2 >= 0) { path.push_back(PathStep{op, 1}); split_op(lt, k2, depth + 1, sdepth, first); path.pop_back(); }
     }
 };
 
@@ -139,6 +193,7 @@ struct ScanPlanner::Impl {
     const HostTree &t;
     const int32_t *order;
     int first, mintrav, maxtrav;
+    int split_depth = 0;
     Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const int32_t *ord,
          int f, int mi, int ma, const uint8_t *vstale) : b(tt, plan, vstride, vstale), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
 };
@@ -147,10 +202,12 @@ ScanPlanner::ScanPlanner() : impl(nullptr) {}
 ScanPlanner::~ScanPlanner() { delete impl; }
 
 int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int count,
-                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan, bool host_only, const uint8_t *vstale)
+                       int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan, bool host_only, const uint8_t *vstale,
+                       int split_depth)
 {
     delete impl; impl = nullptr;
     plan.tasks.clear(); plan.visit_begin.clear(); plan.task_vids.clear(); plan.need_refs.clear();
+    plan.sub_tasks.clear(); plan.task_tops.clear();
     plan.n_cand = 0; plan.n_ops = 0; plan.max_slot = 0;
     plan.task_cap = 2 * count;
     const int n = t.n;
@@ -162,13 +219,18 @@ int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int c
     Builder &b = impl->b;
     // upper bounds: one side of a visit reaches at most 4 * (2^maxtrav - 1) branches, never more than the tree has
     const size_t per_side = std::min<size_t>((size_t)4 << std::max(maxtrav, 0), (size_t)2 * n);
-    const size_t cap = (size_t)count * 2 * per_side + 16;
+    const size_t cap1 = (size_t)count * 2 * per_side + 16;
+    // split plans: every op once more (the sub-tasks' copies) plus the replayed paths (up to 2^(d-1) heads per side, d - 1 ops each)
+    impl->split_depth = host_only ? 0 : split_depth;
+    const size_t cap = impl->split_depth > 0 ? 2 * cap1 + (size_t)count * 4 * ((size_t)split_depth << split_depth) : cap1;
+    plan.item_cap = impl->split_depth > 0 ? (size_t)plan.task_cap * (1 + ((size_t)2 << split_depth)) : (size_t)plan.task_cap;
+    if (impl->split_depth > 0) { if (plan.kid_op.size() < 2 * cap1) plan.kid_op.resize(2 * cap1); b.kid_op = plan.kid_op.data(); }
     if (host_only) {
         plan.offs_host.resize(cap + cap / 4); plan.ctl_host.resize(cap + cap / 4);
-    } else if (!plan.offs.reserve(cap + cap / 4) || !plan.ctl.reserve(cap + cap / 4) || !plan.tasks_pin.reserve((size_t)plan.task_cap + 16)) {
+    } else if (!plan.offs.reserve(cap + cap / 4) || !plan.ctl.reserve(cap + cap / 4) || !plan.tasks_pin.reserve(plan.item_cap + 16)) {
         set_error("page-locked host allocation for the scan plan failed"); return 1;
     }
-    if (plan.cand_ref.size() < cap) { plan.cand_ref.resize(cap); plan.cand_prune.resize(cap); plan.cand_task.resize(cap); }
+    if (plan.cand_ref.size() < cap1) { plan.cand_ref.resize(cap1); plan.cand_prune.resize(cap1); plan.cand_task.resize(cap1); }
     b.offs = host_only ? plan.offs_host.data() : plan.offs.data();
     b.ctl = host_only ? plan.ctl_host.data() : plan.ctl.data();
     b.cand_ref = plan.cand_ref.data(); b.cand_prune = plan.cand_prune.data(); b.cand_task = plan.cand_task.data();
@@ -198,8 +260,10 @@ void ScanPlanner::add(int v0, int v1)
                 b.cand_base = b.ncand;
                 b.prune_ref = p; b.task_index = (int)plan.tasks.size();
                 if (b.lazy) { b.need(q); b.need(p1); b.need(p2); b.need(p); }     // p itself: the -bb edge row of the task reads both sides of (p, q)
-                if (!b.tip[p1]) b.expand_top(p1, 0xFFu, mintrav, maxtrav);
-                if (!b.tip[p2]) b.expand_top(p2, 0xFEu, mintrav, maxtrav);
+                int top1 = -1, top2 = -1;
+                if (!b.tip[p1]) top1 = b.expand_top(p1, 0xFFu, mintrav, maxtrav);
+                if (!b.tip[p2]) top2 = b.expand_top(p2, 0xFEu, mintrav, maxtrav);
+                if (b.kid_op) { plan.task_tops.push_back(top1); plan.task_tops.push_back(top2); }
                 b.end_task();
                 task.op_end = b.nops;
                 plan.tasks.push_back(task);
@@ -218,8 +282,10 @@ void ScanPlanner::add(int v0, int v1)
                 b.cand_base = b.ncand;
                 b.prune_ref = q; b.task_index = (int)plan.tasks.size();
                 if (b.lazy) { b.need(p); b.need(q1); b.need(q2); b.need(q); }
-                if (!b.tip[q1]) b.expand_top(q1, 0xFFu, mintrav2, maxtrav);
-                if (!b.tip[q2]) b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
+                int top1 = -1, top2 = -1;
+                if (!b.tip[q1]) top1 = b.expand_top(q1, 0xFFu, mintrav2, maxtrav);
+                if (!b.tip[q2]) top2 = b.expand_top(q2, 0xFEu, mintrav2, maxtrav);
+                if (b.kid_op) { plan.task_tops.push_back(top1); plan.task_tops.push_back(top2); }
                 b.end_task();
                 task.op_end = b.nops;
                 plan.tasks.push_back(task);
@@ -234,6 +300,27 @@ void ScanPlanner::finish()
 {
     ScanPlan &plan = impl->b.plan;
     plan.visit_begin.push_back(plan.n_cand);
+}
+
+// after the last add() of a plan begun with split_depth > 0: plan.sub_tasks = the tasks cut into sub-tasks at that depth of
+// their op trees (ops appended behind the plan's own; n_ops grows, the tasks and their op ranges stay as they are)
+void ScanPlanner::split()
+{
+    Builder &b = impl->b;
+    ScanPlan &plan = b.plan;
+    plan.sub_tasks.clear();
+    if (!b.kid_op || impl->split_depth <= 0) return;
+    b.scored.assign((size_t)b.nops, 0);
+    const int nlogical_ops = b.nops;
+    (void)nlogical_ops;
+    for (size_t k = 0; k < plan.tasks.size(); k++) {
+        bool first = true;
+        for (int side = 0; side < 2; side++) {
+            const int top = plan.task_tops[2 * k + side];
+            if (top >= 0) { b.path.clear(); b.split_op(plan.tasks[k], top, 1, impl->split_depth, first); }
+        }
+    }
+    plan.n_ops = b.nops;
 }
 
 int build_scan_plan(const HostTree &t, const int32_t *order,
