@@ -275,6 +275,10 @@ int mpgpu_set_option(mpgpu_ctx *ctx, const char *name, int value);
 /* Device time (ms, CUDA events on the context's stream) of the largest tensor-kernel launch since the
  * last call, with its shape: rows x patterns (K, padded to 128) x replicates, and the K splits used. */
 int mpgpu_reps_timing(mpgpu_ctx *ctx, float *tc_ms, int *rows, int *patterns, int *splits);
+/* Measurement aid (no reference counterpart): the issue rate of tcgen05.mma kind::i8 on this device, in int8 TOP/s -- one
+ * CTA per SM issuing M = 128, N = 256, K = 32 MMAs back to back from resident shared-memory tiles, `iters` x 64 per CTA.
+ * It is the measured denominator bench.py reports k_reps_tc's roofline against (MEASURED_PEAKS.json has no int8 figure). */
+int mpgpu_int8_peak(mpgpu_ctx *ctx, int iters, double *tops);
 /* res[b] = -rell[b] of the CURRENT tree for b < B (what the loop at :3424-3449 leaves in `res`
  * when no replicate is skipped).  Single shard. */
 int mpgpu_reps_current_tree(mpgpu_ctx *ctx, int32_t *res);

@@ -967,6 +967,13 @@ int mpgpu_reps_timing(mpgpu_ctx *c, float *tc_ms, int *rows, int *patterns, int 
     return 0;
 }
 
+int mpgpu_int8_peak(mpgpu_ctx *c, int iters, double *tops)
+{
+    if (!c || !tops || iters < 1) { set_error("bad argument"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    return measure_int8_peak(c, iters, tops);
+}
+
 int mpgpu_reps_info(mpgpu_ctx *c, int *groups, int *exceptions, int *tensor)
 {
     if (!c || !c->reps.loaded) { set_error("no replicates loaded"); return 1; }

@@ -409,6 +409,7 @@ int launch_reps_exc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, in
 int make_w8_tensor_map(Ctx *c);
 int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int x_row0, int nrows);
 int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrows, int32_t *X, int x_pitch);
+int measure_int8_peak(Ctx *c, int iters, double *tops);
 int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row);
 int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr, int32_t *d_call_hit);
 int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, int nlist, int32_t *d_out);

@@ -516,7 +516,71 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(N) : "memory");
 }
 
+// ---- the denominator of k_reps_tc's roofline, measured: tcgen05.mma kind::i8 issued back to back ----------------------
+// One CTA per SM, one warp: a 128 x 128 A tile and a 256 x 128 B tile sit in shared memory (SWIZZLE_128B, the layout the
+// contraction uses), and the elected lane issues M = 128, N = 256, K = 32 MMAs into one TMEM accumulator with nothing else
+// in the way -- no loads, no producers, no epilogue; a commit every 64 MMAs keeps the queue bounded.  ops = 2 M N K per MMA.
+__global__ void __launch_bounds__(32, 1) k_i8_peak(int iters)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar = base + STAGE_BYTES, tmem_slot = bar + 8;
+    const int lane = threadIdx.x;
+    for (int i = lane; i < STAGE_BYTES / 4; i += 32) reinterpret_cast<uint32_t *>(gen)[i] = 0x01000101u * (uint32_t)((i * 2654435761u) >> 31);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (lane == 0) {
+        const uint32_t idesc = umma_idesc();
+        const uint64_t ad = umma_desc(base), bd = umma_desc(base + A_BYTES);
+        uint32_t phase = 0;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+#pragma unroll
+                for (int k = 0; k < KB / 32; k++) umma_i8(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | j | k) != 0);
+            umma_commit(bar);
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(N) : "memory");
+}
+
 }  // namespace tc
+
+// measured issue rate of tcgen05.mma kind::i8 on this device, in int8 TOP/s (2 ops per multiply-accumulate)
+int measure_int8_peak(Ctx *c, int iters, double *tops)
+{
+    cudaDeviceProp prop;
+    MPGPU_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    const int smem = tc::STAGE_BYTES + 1024 + 64;
+    MPGPU_CUDA(cudaFuncSetAttribute(tc::k_i8_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t e0, e1;
+    MPGPU_CUDA(cudaEventCreate(&e0)); MPGPU_CUDA(cudaEventCreate(&e1));
+    tc::k_i8_peak<<<prop.multiProcessorCount, 32, smem, c->stream>>>(iters / 8 + 1);          // warm-up
+    MPGPU_CUDA(cudaEventRecord(e0, c->stream));
+    tc::k_i8_peak<<<prop.multiProcessorCount, 32, smem, c->stream>>>(iters);
+    MPGPU_CUDA(cudaEventRecord(e1, c->stream));
+    MPGPU_CUDA(cudaGetLastError());
+    MPGPU_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MPGPU_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->launches += 2;
+    const double ops = 2.0 * tc::M * tc::N * 32.0 * 64.0 * (double)iters * prop.multiProcessorCount;
+    *tops = ops / (ms * 1e-3) / 1e12;
+    return 0;
+}
 
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,

@@ -70,6 +70,7 @@ def lib():
     L.mpgpu_load_replicates2.argtypes = [vp, i32, vp, i32, vp, i32, vp]
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
     L.mpgpu_reps_timing.argtypes = [vp, vp, vp, vp, vp]
+    L.mpgpu_int8_peak.argtypes = [vp, C.c_int, vp]
     L.mpgpu_set_option.argtypes = [vp, C.c_char_p, i32]
     L.mpgpu_set_cost_matrix.argtypes = [vp, vp, i32, vp, i32, vp]
     L.mpgpu_sankoff_layout.argtypes = [vp, vp, vp, vp, i32]
@@ -462,6 +463,12 @@ class Engine:
         ms, rows, pat, sp = C.c_float(), C.c_int(), C.c_int(), C.c_int()
         self._ck(self.L.mpgpu_reps_timing(self.h, C.byref(ms), C.byref(rows), C.byref(pat), C.byref(sp)))
         return ms.value, rows.value, pat.value, sp.value
+
+    def int8_peak(self, iters=4096):
+        """measured tcgen05.mma kind::i8 issue rate of this device, int8 TOP/s"""
+        t = C.c_double()
+        self._ck(self.L.mpgpu_int8_peak(self.h, int(iters), C.byref(t)))
+        return t.value
 
     def reps_current_tree(self):
         out = np.zeros(self.B, dtype=np.int32)
