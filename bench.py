@@ -506,6 +506,56 @@ def make_replicates(case, B, seed=5):
     return rng.multinomial(int(w.sum()), w / w.sum(), size=B).astype(np.uint16)
 
 
+def bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream):
+    """-bb at N > 1 (every rank calls this): the pattern-sharded contexts score the same sweep's candidates against all B
+    replicates -- each shard contracts its slice of the patterns, the row x replicate partial sums are summed by the
+    in-library exchange step (k_peer_allreduce over NVLink) -- device-timed as the max over ranks; rank 0 then checks
+    REPS vectors against an unsharded context over the whole alignment."""
+    import torch
+    import torch.distributed as dist
+    from mpboot_b200 import engine
+    n, B, ninf = case["n"], args.replicates, case["n_inf"]
+    boot = make_replicates(case, B)
+    seg = do_segmenting(eng.pattern_parsimony()[0][:ninf], case["weights"], ninf)
+    eng.load_replicates(boot, seg)
+    calls = []
+    for v in range(2 * n - 2):
+        calls.append(-1); calls.extend(range(vb[v], vb[v + 1]))
+    calls = np.array(calls, dtype=np.int32)
+    eng.scan_plan(order, 1, 2 * n - 2, 1, args.maxtrav)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.scan_launch(); eng.reps_candidates_device(calls)
+    dist.barrier(); torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record(); eng.scan_launch(); eng.reps_candidates_device(calls); ev[k][1].record()
+    dist.barrier(); torch.cuda.synchronize()
+    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    step_ms = float(tt[0])
+    sample = calls[: min(len(calls), 400)]
+    got = eng.reps_candidates(sample)                         # collective: every rank ends up with the complete vectors
+    out = None
+    if rank == 0:
+        one = engine.Engine(device=local, stream=stream)
+        one.load_alignment(case["codes"], case["weights"], case["datatype"])
+        one.set_tree(case["bn"], case["bs"])
+        one.load_replicates(boot, do_segmenting(one.pattern_parsimony()[0][:ninf], case["weights"], ninf))
+        one.scan_plan(order, 1, 2 * n - 2, 1, args.maxtrav)
+        one.scan_launch()
+        want = one.reps_candidates(sample)
+        one.close()
+        out = {"what": "the C2 sweep under -bb on %d pattern shards, cutoff off: scan + delta rows + contraction of each shard's patterns + "
+                       "in-library exchange of the row x replicate sums + combine" % world,
+               "replicates": B, "calls_per_step": int(len(calls)), "ms_per_step": step_ms,
+               "reps_vectors_per_s": len(calls) / (step_ms * 1e-3), "insertions_per_s": n_cand / (step_ms * 1e-3),
+               "check": {"reps_vectors_equal_unsharded": bool(np.array_equal(got, want)), "vectors_compared": int(len(sample))}}
+        assert out["check"]["reps_vectors_equal_unsharded"], "sharded REPS vectors differ from the unsharded context"
+    return out
+
+
 def bench_bb(eng, case, order, vb, n_cand, args, flush):
     """The same sweep under -bb with the cutoff off: every scored insertion and, once per node visit, the
     current tree go through REPS against B = 1000 replicates (iqtree.cpp:3411-3449) -- the worst case for the
@@ -568,15 +618,20 @@ def bench_bb(eng, case, order, vb, n_cand, args, flush):
                      "kernel_ms": tc, "shape": "%d rows x %d patterns x %d replicates, K splits %d" % (rows, pat, B, splits),
                      "algorithmic_ops_per_launch": ops, "traffic": measured_traffic(args.workload, "k_reps_tc")},
     }
-    # the whole -bb SPR search from the same random tree, cutoff off
+    # the whole -bb SPR search from the same random tree, cutoff off (best of 2: the first call on a context also pays for the
+    # growth of the row / staging buffers and the first launches of the ROWS kernels, which MPBoot amortises over its ~1000 searches)
     from mpboot_b200.engine import HostRng, Treels
-    rs = HostRng(11)
-    bl = np.full(B, -float(np.iinfo(np.int64).max)); bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
-    tl = Treels(n)
-    t0 = time.time()
-    ret, bn2, bs2, nins, ncalls, nreps = eng.optimize_spr_bb(case["bn"], case["bs"], tl.hooks(rs.fn, rs.user), bl, bc, bt, 0.0, 0.5, 1, args.maxtrav)
-    dt = time.time() - t0
-    out["search"] = {"what": "mpgpu_optimize_spr_bb from the random tree, cutoff off, host buffers (e2e)", "wall_s": dt,
+    walls = []
+    for _ in range(2):
+        rs = HostRng(11)
+        bl = np.full(B, -float(np.iinfo(np.int64).max)); bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
+        tl = Treels(n)
+        t0 = time.time()
+        ret, bn2, bs2, nins, ncalls, nreps = eng.optimize_spr_bb(case["bn"], case["bs"], tl.hooks(rs.fn, rs.user), bl, bc, bt, 0.0, 0.5, 1, args.maxtrav)
+        walls.append(time.time() - t0)
+    dt = min(walls)
+    out["search"] = {"what": "mpgpu_optimize_spr_bb from the random tree, cutoff off, host buffers (e2e), best of 2", "wall_s": dt,
+                     "first_call_wall_s": walls[0],
                      "insertions": int(nins), "savecurrenttree_calls": int(ncalls), "reps_vectors": int(nreps),
                      "insertions_per_s": nins / dt, "reps_vectors_per_s": nreps / dt, "final_score": int(ret),
                      "replicates_won": int((bt >= 0).sum()), "trees_materialised": int(len(tl.materialized()))}
@@ -853,6 +908,10 @@ def run_ours(args):
         r4["eng"].close()
         del r4
 
+    bb_sharded = None
+    if world > 1 and not args.no_bb:
+        bb_sharded = bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream)
+
     if rank == 0:
         ops_per_ins = 2.0 * sites_total
         ms_per_step = r["dev_ms"] / args.steps
@@ -884,6 +943,8 @@ def run_ours(args):
                                 "check": r["check"]}
         if c4:
             line["c4_strong"] = c4
+        if bb_sharded:
+            line["bb"] = bb_sharded
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
         if world == 1 and not args.no_search:
             line["search"] = bench_search(eng, case, args)
