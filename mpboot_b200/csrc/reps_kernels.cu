@@ -15,6 +15,8 @@
 // weight above 255, or a segment whose 16-bit wrap cannot be ruled out -- are "exceptions" and
 // go through an exact CUDA-core kernel into their own column group, where the mod-2^16 is
 // applied after the combine.
+#include <type_traits>
+
 #include "mpgpu_internal.h"
 
 #include <cuda.h>
@@ -300,7 +302,7 @@ namespace tc {
 constexpr int M = 128, N = 256, KB = 128, STAGES = 4;
 constexpr int A_BYTES = M * KB, B_BYTES = N * KB, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int THREADS = 192;
+constexpr int threads_for(int npw) { return (npw + 2) * 32; }     // NPW producer warps + the TMA warp + the MMA warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -367,12 +369,17 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x0020
 // BYTES: the A operand is already u8, K-major, [row][Kpad] (per-pattern Sankoff costs, -cost with -bb): the TMA warp
 // loads its 128 x 128 tile through tmap_a next to the weights (one more cp.async.bulk.tensor per stage, rows beyond
 // nrows zero-filled) and warps 0-3 only run the epilogue.
-template <bool BYTES>
-__global__ void __launch_bounds__(THREADS, 1)
+// NPW = A-producer warps (4: a thread expands the 128 bits of its row per K-block; 8: two threads share a row, 64 bits each --
+// r02: four producers kept the tensor pipe at ~70 %).  Tiles are rasterised N-fastest (tile = m_tile * ntn + n_tile): the CTAs
+// resident together share their A rows through L2 instead of re-reading them from DRAM once per replicate tile.
+template <bool BYTES, int NPW>
+__global__ void __launch_bounds__(threads_for(NPW), 1)
 k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t *__restrict__ rows_a, int a_pitch, int a_kb0,
-          int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X)
+          int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X,
+          int mtn, int ntn, int n_fastest)
 {
+    constexpr int TMA_WARP = NPW, MMA_WARP = NPW + 1;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -383,7 +390,8 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));            // generic pointer to the aligned base
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * M, n0 = blockIdx.y * N;
+    const int tile = blockIdx.x;
+    const int m0 = (n_fastest ? tile / ntn : tile % mtn) * M, n0 = (n_fastest ? tile % ntn : tile / mtn) * N;
     const int kb_begin = kb_lo + blockIdx.z * kb_per_split;
     int kb_end = kb_begin + kb_per_split;
     if (kb_end > kb_hi) kb_end = kb_hi;
@@ -391,11 +399,11 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
     if (nkb <= 0) return;                                                  // uniform over the CTA
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), BYTES ? 1 : 5); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), BYTES ? 1 : NPW + 1); mbar_init(empty_bar(s), 1); }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(N) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -405,21 +413,24 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp < 4) {
-        // ---- A producers: thread r owns tile row r ----
-        const int r = threadIdx.x;
+    if (warp < NPW) {
+        // ---- A producers: thread t owns tile row t % 128; with 8 producer warps the two threads of a row expand 64 bits each ----
+        constexpr int SHARE = NPW / 4;                       // threads per row
+        constexpr int CH = 8 / SHARE;                        // 16-byte chunks (16 bits each) per thread and K-block
+        const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
         const bool live = (m0 + r) < nrows;
         if (!BYTES) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch) - a_kb0;   // row starts at K-block a_kb0
+        typedef typename std::conditional<SHARE == 1, uint4, uint2>::type BitsT;
+        const BitsT *src = reinterpret_cast<const BitsT *>(reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch) - a_kb0) + half;   // row starts at K-block a_kb0
         const uint32_t sw = (uint32_t)(r & 7);
-        // the 128 bits of K-block it+PF are requested while K-block it is expanded: the L2 latency of
+        // the bits of K-block it+PF are requested while K-block it is expanded: the L2 latency of
         // the row loads is off the critical path of the MMA pipeline
         constexpr int PF = 4;
-        uint4 pre[PF];
+        BitsT pre[PF];
 #pragma unroll
         for (int d = 0; d < PF; d++) {
-            pre[d] = make_uint4(0, 0, 0, 0);
-            if (live && d < nkb) pre[d] = __ldg(src + (kb_begin + d));
+            pre[d] = BitsT();
+            if (live && d < nkb) pre[d] = __ldg(src + (size_t)(kb_begin + d) * SHARE);
         }
         for (int it0 = 0; it0 < nkb; it0 += PF) {
 #pragma unroll
@@ -428,14 +439,15 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
                 if (it >= nkb) break;
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                const uint4 bits = pre[d];
-                if (live && it + PF < nkb) pre[d] = __ldg(src + (kb_begin + it + PF));
+                const BitsT bits = pre[d];
+                if (live && it + PF < nkb) pre[d] = __ldg(src + (size_t)(kb_begin + it + PF) * SHARE);
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 uint8_t *arow = smem_gen + (size_t)s * STAGE_BYTES + (size_t)r * 128;
-                const uint32_t wv[4] = {bits.x, bits.y, bits.z, bits.w};
+                const uint32_t *wv = reinterpret_cast<const uint32_t *>(&bits);
 #pragma unroll
-                for (int cidx = 0; cidx < 8; cidx++) {
-                    const uint32_t h = (wv[cidx >> 1] >> ((cidx & 1) * 16)) & 0xFFFFu;
+                for (int cc = 0; cc < CH; cc++) {
+                    const int cidx = half * CH + cc;
+                    const uint32_t h = (wv[cc >> 1] >> ((cc & 1) * 16)) & 0xFFFFu;
                     uint4 v;
                     v.x = spread4(h & 0xF); v.y = spread4((h >> 4) & 0xF); v.z = spread4((h >> 8) & 0xF); v.w = spread4(h >> 12);
                     *reinterpret_cast<uint4 *>(arow + ((cidx ^ sw) << 4)) = v;
@@ -446,7 +458,7 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
             }
         }
         }
-    } else if (warp == 4) {
+    } else if (warp == TMA_WARP) {
         // ---- B producer (TMA) ----
         if (lane == 0) {
             for (int it = 0; it < nkb; it++) {
@@ -512,8 +524,181 @@ k_reps_tc(const __grid_constant__ CUtensorMap tmap_w8, const __grid_constant__ C
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5)
+    if (warp == MMA_WARP)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(N) : "memory");
+}
+
+// ---- A operand in tensor memory (r02) -------------------------------------------------------------------------------
+// With both operands in shared memory the MMA reads 12 KB per instruction (A 4 KB + B 8 KB every 128 cycles = 96 B/clk)
+// while the producers write the A tile (32 B/clk) and TMA writes the B tile (64 B/clk): 192 B/clk against the SM's
+// 128 B/clk of shared-memory bandwidth -- the tensor pipe cannot exceed ~2/3 (measured 66-70 %).  The {0,1} A tile does
+// not have to exist in shared memory at all: tcgen05.mma takes A from TENSOR memory (lane = tile row, 32-bit column =
+// 4 consecutive K bytes), and the producers can put it there straight from registers with tcgen05.st.  Producer thread r
+// (row r, TMEM lane r) expands its 128 bits of a K-block into 32 words and stores them to the stage's 32 columns; the
+// MMA issuer passes [tmem_a + 8 k] for the k-th K = 32 slice.  Shared memory then carries the weights only
+// (64 B/clk read + 64 B/clk written), the stages are 32 KB and six of them fit.
+// TMEM: columns [0, 256) accumulator, [256, 256 + 32 * TA_STAGES) A stages (512 allocated; one CTA per SM).
+constexpr int TA_STAGES = 6;
+constexpr int TA_SMEM_BYTES = TA_STAGES * B_BYTES + 1024 + 256;
+constexpr int TA_ACOL = 256;
+
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}" :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+k_reps_tc_ta(const __grid_constant__ CUtensorMap tmap_w8,
+             const uint32_t *__restrict__ rows_a, int a_pitch, int a_kb0,
+             int x_row0, int nrows, int kb_lo, int kb_hi, int kb_per_split, int B, int x_pitch, int32_t *__restrict__ X,
+             int mtn, int ntn, int n_fastest)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + TA_STAGES * B_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (TA_STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * TA_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * TA_STAGES + 1);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int m0 = (n_fastest ? tile / ntn : tile % mtn) * M, n0 = (n_fastest ? tile % ntn : tile / mtn) * N;
+    const int kb_begin = kb_lo + blockIdx.z * kb_per_split;
+    int kb_end = kb_begin + kb_per_split;
+    if (kb_end > kb_hi) kb_end = kb_hi;
+    const int nkb = kb_end - kb_begin;
+    if (nkb <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TA_STAGES; s++) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < 4) {
+        // ---- A producers: thread r owns tile row r = TMEM lane r ----
+        const int r = threadIdx.x;
+        const bool live = (m0 + r) < nrows;
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows_a + (size_t)(m0 + r) * a_pitch) - a_kb0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)TA_ACOL;
+        constexpr int PF = 4;
+        uint4 pre[PF];
+#pragma unroll
+        for (int d = 0; d < PF; d++) {
+            pre[d] = make_uint4(0, 0, 0, 0);
+            if (live && d < nkb) pre[d] = __ldg(src + (kb_begin + d));
+        }
+        for (int it0 = 0; it0 < nkb; it0 += PF) {
+#pragma unroll
+            for (int d = 0; d < PF; d++) {
+                const int it = it0 + d;
+                if (it >= nkb) break;
+                const int s = it % TA_STAGES;
+                const uint32_t ph = (uint32_t)(it / TA_STAGES) & 1u;
+                const uint4 bits = pre[d];
+                if (live && it + PF < nkb) pre[d] = __ldg(src + (kb_begin + it + PF));
+                const uint32_t wv[4] = {bits.x, bits.y, bits.z, bits.w};
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = spread4((wv[j >> 3] >> ((j & 7) * 4)) & 0xFu);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                    "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                    "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                    :: "r"(lane_addr + (uint32_t)(s * 32)),
+                       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                       "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                       "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                       "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                    : "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % TA_STAGES;
+                const uint32_t ph = (uint32_t)(it / TA_STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), B_BYTES);
+                tma_load_2d(base + s * B_BYTES, &tmap_w8, (kb_begin + it) * KB, n0, full_bar(s));
+            }
+        }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc();
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % TA_STAGES;
+                const uint32_t ph = (uint32_t)(it / TA_STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t bd = umma_desc(base + s * B_BYTES);
+                const uint32_t at = tmem_base + (uint32_t)(TA_ACOL + s * 32);
+#pragma unroll
+                for (int k = 0; k < KB / 32; k++)
+                    umma_i8_ts(tmem_base, at + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+
+    if (warp < 4) {
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t *tile_s = reinterpret_cast<uint32_t *>(smem_gen) + warp * (32 * 33);
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int cb = 0; cb < N / 32; cb++) {
+            uint32_t v[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr + (uint32_t)(cb * 32)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j++) tile_s[lane * 33 + j] = v[j];
+            __syncwarp();
+            const int col = n0 + cb * 32 + lane;
+            for (int i = 0; i < 32; i++) {
+                const int mrow = m0 + warp * 32 + i;
+                const int val = (int)tile_s[i * 33 + lane];
+                if (mrow < nrows && col < B && val != 0)
+                    atomicAdd(&X[(size_t)(x_row0 + mrow) * x_pitch + col], val);
+            }
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
 }
 
 // ---- the denominator of k_reps_tc's roofline, measured: tcgen05.mma kind::i8 issued back to back ----------------------
@@ -631,9 +816,12 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int
     if (kb_hi <= kb_lo) return 0;
     static bool configured_dev[64] = {false}; bool &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (!configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         configured = true;
     }
+    static const int producers = getenv("MPGPU_REPS_PRODUCERS") ? atoi(getenv("MPGPU_REPS_PRODUCERS")) : 4;   // (8 measured slower: 1.10 vs 1.02 ms)     // tuning knobs
+    static const int n_fastest = getenv("MPGPU_REPS_RASTER") ? atoi(getenv("MPGPU_REPS_RASTER")) : 1;
     const int mt = (nrows + tc::M - 1) / tc::M, nt = r.Bpad / tc::N;
     const int nkb = kb_hi - kb_lo;
     // Split K so that the grid comes out in full waves of 148 CTAs (one per SM): cost model
@@ -651,15 +839,26 @@ int launch_reps_tc(Ctx *c, const uint32_t *a_base, int a_pitch, int a_word0, int
     if (const char *e = getenv("MPGPU_REPS_SPLITS")) { int v = atoi(e); if (v >= 1) splits = v; }
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
-    dim3 grid(mt, nt, splits);
+    dim3 grid(mt * nt, 1, splits);
     const bool timed = r.timing && nrows >= r.timed_rows;      // keep the events of the largest launch
     if (timed) {
         if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
         MPGPU_CUDA(cudaEventRecord(r.ev0, c->stream));
     }
-    tc::k_reps_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
+    static const int tmem_a = getenv("MPGPU_REPS_TMEM_A") ? atoi(getenv("MPGPU_REPS_TMEM_A")) : 1;
+    if (tmem_a) {
+        static bool ta_configured_dev[64] = {false}; bool &tac = ta_configured_dev[c->device & 63];
+        if (!tac) { MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TA_SMEM_BYTES)); tac = true; }
+        tc::k_reps_tc_ta<<<grid, 192, tc::TA_SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
+                                                                     x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X, mt, nt, n_fastest);
+    } else if (producers == 4)
+        tc::k_reps_tc<false, 4><<<grid, tc::threads_for(4), tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
                                                                            *reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
-                                                                           x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X);
+                                                                           x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X, mt, nt, n_fastest);
+    else
+        tc::k_reps_tc<false, 8><<<grid, tc::threads_for(8), tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
+                                                                           *reinterpret_cast<const CUtensorMap *>(r.tmap_w8), a_base, a_pitch, a_word0 / 4,
+                                                                           x_row0, nrows, kb_lo, kb_hi, per, r.B, r.G * r.Bpad, r.d_X, mt, nt, n_fastest);
     if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
@@ -675,7 +874,7 @@ int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrow
     if (!r.tmap_valid) { set_error("replicate weights not loaded"); return 1; }
     static bool configured_dev[64] = {false}; bool &configured = configured_dev[c->device & 63];   /* the attribute is per device */
     if (!configured) {
-        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        MPGPU_CUDA(cudaFuncSetAttribute(tc::k_reps_tc<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         configured = true;
     }
     const int mt = (nrows + tc::M - 1) / tc::M, nt = r.Bpad / tc::N;
@@ -692,7 +891,8 @@ int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrow
     }
     const int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
-    dim3 grid(mt, nt, splits);
+    dim3 grid(mt * nt, 1, splits);
+    static const int n_fastest = getenv("MPGPU_REPS_RASTER") ? atoi(getenv("MPGPU_REPS_RASTER")) : 1;
     const bool timed = r.timing && nrows >= r.timed_rows;
     if (timed) {
         if (!r.ev0) { MPGPU_CUDA(cudaEventCreate(&r.ev0)); MPGPU_CUDA(cudaEventCreate(&r.ev1)); }
@@ -711,10 +911,10 @@ int launch_reps_tc_bytes(Ctx *c, const uint8_t *rows8, int pitch_bytes, int nrow
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (res != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed for the cost rows"); return 1; }
     }
-    tc::k_reps_tc<true><<<grid, tc::THREADS, tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
+    tc::k_reps_tc<true, 4><<<grid, tc::threads_for(4), tc::SMEM_BYTES, c->stream>>>(*reinterpret_cast<const CUtensorMap *>(r.tmap_w8),
                                                                           *reinterpret_cast<const CUtensorMap *>(tmap_a),
                                                                           reinterpret_cast<const uint32_t *>(rows8), pitch_bytes, 0,
-                                                                          0, nrows, 0, nkb, per, r.B, x_pitch, X);
+                                                                          0, nrows, 0, nkb, per, r.B, x_pitch, X, mt, nt, n_fastest);
     if (timed) { MPGPU_CUDA(cudaEventRecord(r.ev1, c->stream)); r.timed_rows = nrows; r.timed_kblocks = nkb; r.timed_splits = splits; }
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick GPU probe (1 GPU): first -bb search on a context, lazy vs eager views
+# quick GPU probe (1 GPU): k_reps_tc with the A operand in tensor memory
 cd "$(dirname "$0")/.."
-echo "== default"; MPGPU_PROFILE=1 python tools/bb_search_probe.py c2 1 2>&1 | grep -v " 0.000 ms" | tail -16
-echo "== eager"; MPGPU_EAGER_VIEWS=1 MPGPU_PROFILE=1 python tools/bb_search_probe.py c2 1 2>&1 | grep -v " 0.000 ms" | tail -16
+timeout 600 python -m pytest tests/test_gpu_bb.py -m gpu -q -x 2>&1 | tail -12
+for ta in 1 0; do echo "== tmem_a $ta"; MPGPU_REPS_TMEM_A=$ta BB_PROBE_SEARCH=0 timeout 300 python tools/bb_probe.py c2 1000 2>&1 | grep "bb step\|differ\|equal\|check\|Error\|error" | tail -3; done
