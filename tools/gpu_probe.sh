@@ -1,5 +1,3 @@
 #!/bin/bash
-# quick GPU probe (1 GPU): stream-K contraction
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests/test_gpu_bb.py -m gpu -q -x 2>&1 | tail -12
-for sk in 1 0; do echo "== stream_k $sk"; MPGPU_REPS_STREAMK=$sk BB_PROBE_SEARCH=0 timeout 300 python tools/bb_probe.py c2 1000 2>&1 | grep "bb step\|differ\|equal\|check\|Error\|error" | tail -3; done
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_plan --csv python bench.py --steps 3 --warmup 3 --no-bb --no-cost --no-search --no-cpu-baseline --no-bb1000 --no-c4 2>/dev/null | grep k_plan | head -4 | awk -F'","' '{print $5, $(NF-1), $NF}' | cut -c1-200
