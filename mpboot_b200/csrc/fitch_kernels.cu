@@ -261,7 +261,11 @@ int launch_stage(Ctx *c)
 {
     if (!c->stage_pending) return 0;
     c->stage_pending = false;
-    k_stage<<<8, 256, 0, c->stream>>>(c->stage_req);
+    const int n16 = c->stage_req.n[0] + c->stage_req.n[1] + c->stage_req.n[2];
+    int blocks = (n16 + 255) / 256;                 // one 16-byte unit per thread where the plan is large: a single round trip to host memory
+    if (blocks < 8) blocks = 8;
+    if (blocks > 64) blocks = 64;
+    k_stage<<<blocks, 256, 0, c->stream>>>(c->stage_req);
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     return 0;

@@ -746,7 +746,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         return sk_run_scan(c);
     }
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
-    int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep): 1: 0.338 ms, 2: 0.316 ms, 4: 0.337 ms, 6: 0.390 ms e2e
+    int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep, staged pieces, r02): 2: 0.248 ms, 3: 0.249, 4: 0.264, 6: 0.304, 8: 0.344 e2e (copy-engine pieces: 2: 0.267)
     if (const char *e = getenv("MPGPU_SCAN_PIECES")) { int v = atoi(e); if (v >= 1) pieces = v; }
     // a small batch is latency-bound (one warp per task and chunk walks ~100 ops): cut its tasks into sub-tasks
     static const int split_depth = getenv("MPGPU_SPLIT_DEPTH") ? atoi(getenv("MPGPU_SPLIT_DEPTH")) : 3;
@@ -768,26 +768,33 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         // latency path (one piece, one shard, a small plan): the plan rides to the device with the wave launch (or a k_stage
         // launch) and the scan's last block publishes the counts -- no copy engine and no stream synchronize in the step
         static const bool no_lean = getenv("MPGPU_NO_LEAN") != nullptr || getenv("MPGPU_NO_PUBLISH") != nullptr;
-        const size_t plan_bytes = (size_t)pl.n_ops * 16 + (pl.tasks.size() + pl.sub_tasks.size()) * sizeof(ScanTask);
-        const bool lean = !no_lean && pieces == 1 && c->shard_count == 1 && plan_bytes <= 96 * 1024;
-        if (lean) {
-            const size_t nt = pl.tasks.size(), nsub = pl.sub_tasks.size();
-            memcpy(pl.tasks_pin.data(), pl.tasks.data(), nt * sizeof(ScanTask));
+        const int nops_piece = pl.n_ops - ops0;
+        const size_t nt = pl.tasks.size(), nsub = pl.sub_tasks.size();
+        const size_t plan_bytes = (size_t)nops_piece * 16 + (nt - task0 + nsub) * sizeof(ScanTask);
+        // staged pieces: the streams of this piece go from mapped host memory to their device arrays through a kernel (riding on
+        // the wave launch when there is one) instead of three copy-engine hops; any number of pieces, one shard or many
+        const bool staged = !no_lean && plan_bytes <= 512 * 1024;
+        const bool lean = staged && pieces == 1 && c->shard_count == 1 && plan_bytes <= 96 * 1024;
+        if (staged) {
+            memcpy(pl.tasks_pin.data() + task0, pl.tasks.data() + task0, (nt - task0) * sizeof(ScanTask));
             if (nsub) memcpy(pl.tasks_pin.data() + nt, pl.sub_tasks.data(), nsub * sizeof(ScanTask));
+            const int o0 = ops0 & ~1;                     // 16-byte units: an odd first op re-copies its (identical) predecessor
+            const int n16 = (pl.n_ops - o0 + 1) / 2;
             StageArgs &st = c->stage_req;
-            st.src[0] = reinterpret_cast<const uint4 *>(pl.tasks_pin.data()); st.dst[0] = reinterpret_cast<uint4 *>(c->d_tasks); st.n[0] = (int)(nt + nsub) * 2;
-            st.src[1] = reinterpret_cast<const uint4 *>(pl.offs.data()); st.dst[1] = reinterpret_cast<uint4 *>(c->d_offs); st.n[1] = (pl.n_ops + 1) / 2;
-            st.src[2] = reinterpret_cast<const uint4 *>(pl.ctl.data()); st.dst[2] = reinterpret_cast<uint4 *>(c->d_ctl); st.n[2] = (pl.n_ops + 1) / 2;
+            st.src[0] = reinterpret_cast<const uint4 *>(pl.tasks_pin.data() + task0); st.dst[0] = reinterpret_cast<uint4 *>(c->d_tasks + task0); st.n[0] = (int)(nt - task0 + nsub) * 2;
+            st.src[1] = reinterpret_cast<const uint4 *>(pl.offs.data() + o0); st.dst[1] = reinterpret_cast<uint4 *>(c->d_offs + o0); st.n[1] = n16;
+            st.src[2] = reinterpret_cast<const uint4 *>(pl.ctl.data() + o0); st.dst[2] = reinterpret_cast<uint4 *>(c->d_ctl + o0); st.n[2] = n16;
             c->stage_pending = true;
+            if (plan_bytes > 64 * 1024) { if (int rc = launch_stage(c)) return rc; }     // too much for the wave launch's single extra CTA
         }
         if (!pl.need_refs.empty()) {
             if (int rc = ensure_views(c, pl.need_refs.data(), (int)pl.need_refs.size(), true)) return rc;
             pl.need_refs.clear();
         }
-        if (lean) {
+        if (staged) {
             if (int rc = launch_stage(c)) return rc;            // no wave was launched: the plan goes alone
             const size_t nout = (size_t)pl.task_cap + pl.n_cand;
-            if (nout + c->wc_used <= (size_t)kPublishMax) {
+            if (lean && nout + c->wc_used <= (size_t)kPublishMax) {
                 if (int rc = ensure_h_counts(c, nout)) return rc;
                 if (!c->d_done) { MPGPU_CUDA(cudaMalloc((void **)&c->d_done, 64)); MPGPU_CUDA(cudaMemsetAsync(c->d_done, 0, 64, c->stream)); }
                 c->pub_request = true; c->pub_nout = (int)nout;
