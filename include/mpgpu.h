@@ -237,9 +237,11 @@ int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
  * After this call every entry point above (tree score, view lengths = tr->parsimonyScore[], pattern
  * parsimony, scan, SPR search, stepwise addition) computes weighted parsimony with the reference's
  * integers, including the per-segment 16-bit wrap of the weighted sums (:944-948).
- * Preconditions checked here (error otherwise, there is no fallback): the matrix is symmetric and
- * (ntaxa+1)*(max cost+1) <= 65535 -- then no u16 of the reference wraps inside a vector and the score
- * does not depend on the orientation the reference happens to hold.  Sharded contexts: install
+ * Precondition checked here (error otherwise, there is no fallback): (ntaxa+1)*(max cost+1) <= 65535 -- then no u16 of
+ * the reference wraps inside a vector.  The matrix may be asymmetric (the reference only repairs the triangle inequality,
+ * parstree.cpp:31-90): scores then depend on where the tree is rooted, and every entry point takes the reference's own rooting
+ * (an insertion at the node above the insertion point, :2160; a stepwise insertion at the new tip, :2994-2998; the tree at
+ * tr->start's neighbour) -- one more min-plus per scored insertion than for a symmetric matrix.  Sharded contexts: install
  * mpgpu_set_allreduce first (the shards hold ranges of pattern pairs; per-segment sums are reduced before the
  * 16-bit masks).  -cost with -bb: see mpgpu_sankoff_reps_stats below (unsharded contexts only). */
 int mpgpu_set_cost_matrix(mpgpu_ctx *ctx, const uint32_t *cost, int nstates, const int32_t *segment_upper, int nseg,

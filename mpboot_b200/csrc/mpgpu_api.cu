@@ -1195,14 +1195,15 @@ int mpgpu_set_cost_matrix(mpgpu_ctx *c, const uint32_t *cost, int nstates, const
     if (!segment_upper || nseg < 1) { set_error("segment_upper is required (IQTree::doSegmenting, iqtree.cpp:3793)"); return 1; }
     if (c->reps.loaded) { set_error("set the cost matrix before mpgpu_load_replicates (the replicate tables are built per scoring mode)"); return 1; }
     uint32_t mx = 0;
+    bool asym = false;
     for (int i = 0; i < nstates; i++)
         for (int j = 0; j < nstates; j++) {
-            if (cost[i * nstates + j] != cost[j * nstates + i]) {
-                set_error("asymmetric cost matrix: the directed-view engine needs cost[i][j] == cost[j][i] (root invariance)");
-                return 1;
-            }
+            // an asymmetric matrix is legal in the reference (ParsTree::initCostMatrix only repairs the triangle inequality,
+            // parstree.cpp:31-90): scores then depend on where the tree is rooted, and the kernels take the reference's rooted forms
+            if (cost[i * nstates + j] != cost[j * nstates + i]) asym = true;
             mx = std::max(mx, cost[i * nstates + j]);
         }
+    k.asym = asym;
     if (mx >= 65535) { set_error("cost matrix entry too large"); return 1; }
     k.cost.assign(cost, cost + nstates * nstates);
     k.highest = mx + 1;                                     // initializeCostMatrix :159-163

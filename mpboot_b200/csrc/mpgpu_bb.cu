@@ -540,7 +540,7 @@ using namespace mpgpu;
 // changes any score).
 static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                          mpgpu_rng_fn rng, void *rng_user, BBRun *bb, uint32_t *best, int64_t *n_insertions,
-                         bool stepwise_on = false)
+                         bool stepwise_on = false, const uint32_t *start_score = nullptr)
 {
     if (!c->reduces()) { set_error("the SPR search on a sharded context needs mpgpu_set_allreduce"); return 1; }
     if (mintrav != 1) { set_error("mintrav must be 1 (assert at sprparsimony.cpp:2278)"); return 1; }
@@ -561,7 +561,10 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     const bool sk_early = c->sk.on && !c->sk.exact && c->sk.nseg > 1 && !bb && !stepwise_on;
     const int n = c->n, nvisit = 2 * n - 2;
     uint32_t score = 0;
-    if (c->start_edge_valid) score = c->start_edge_mis + c->vlen[c->tree.vid(c->tree.back(3))];   // :3277, read back with the view counts
+    // the SPR rounds of a stepwise-addition tree start from the last insertion's score (randomMP = tr->bestParsimony, :3171: no
+    // evaluation at tr->start) -- the same number unless the cost matrix is asymmetric, where it is rooted at the last tip
+    if (start_score) score = *start_score;
+    else if (c->start_edge_valid) score = c->start_edge_mis + c->vlen[c->tree.vid(c->tree.back(3))];   // :3277, read back with the view counts
     else if (int rc = mpgpu_tree_score(c, &score)) return rc;
     uint32_t bestParsimony = score;
     c->search_start_score = score; c->search_moves = 0; c->search_batches = 0;
@@ -803,7 +806,7 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
         }
         const int ne = (int)edges.size();
         if (sk) {                                        // junction(x, back(x), new tip) = the whole tree's score (no early exit: :951 `!stepwiseAddition_on`)
-            if ((rc = sk_junctions(c, edges.data(), ne, nullptr))) break;
+            if ((rc = sk_junctions(c, edges.data(), ne, nullptr, true))) break;    // (an asymmetric matrix: rooted at the new tip, :2994-2998)
             ins.resize(ne);
             for (int e2 = 0; e2 < ne; e2++) ins[e2] = (int32_t)(c->sk.h_tot[e2].x - treelen);
         } else {
@@ -871,7 +874,7 @@ int mpgpu_stepwise_addition(mpgpu_ctx *c, int64_t *random_seed, int spr_dist, mp
     memcpy(back_node, c->tree.bn.data(), c->tree.bn.size() * sizeof(int32_t));
     memcpy(back_slot, c->tree.bs.data(), c->tree.bs.size() * sizeof(int32_t));
     int64_t more = 0;
-    if (int rc = optimize_impl(c, back_node, back_slot, 1, spr_dist, rng, rng_user, nullptr, best, &more, true)) return rc;
+    if (int rc = optimize_impl(c, back_node, back_slot, 1, spr_dist, rng, rng_user, nullptr, best, &more, true, &b0)) return rc;
     if (n_insertions) *n_insertions = scored + more;
     return 0;
 }

@@ -173,6 +173,7 @@ struct Sankoff {
     bool on = false;                      // a cost matrix is set: every score is weighted parsimony
     bool exact = false;                   // option "sankoff_exact": perSiteScores mode, no lower-bound early exit (:951)
     bool cost_dirty = true;
+    bool asym = false;                    // cost[i][j] != cost[j][i] somewhere: insertion and stepwise scores take the reference's rooted form
     std::vector<uint32_t> cost;           // pllCostMatrix [S][S]
     uint32_t highest = 0;                 // highest_cost = max + 1 (:160)
     std::vector<int32_t> seg_upper; int nseg = 0;
@@ -374,7 +375,7 @@ void sk_free(Ctx *c);
 int sk_build(Ctx *c);
 int sk_compute_levels(Ctx *c, const std::vector<int32_t> &start, int nl);
 int sk_update_stale(Ctx *c, std::vector<Triple> &stale, int nlevels);
-int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn);
+int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn, bool tip_rooted = false);
 int sk_tree_score(Ctx *c, int start_ref, uint32_t *score);
 int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum);
 int sk_raw_view(Ctx *c, int ref, uint16_t *out);

@@ -286,6 +286,55 @@ __global__ void __launch_bounds__(128) k_sk_junction(const uint32_t *__restrict_
     sk_accum<V>(best, w, g, segout + (size_t)e * nseg);
 }
 
+// ---- stepwise insertion of a tip under an ASYMMETRIC matrix: the reference evaluates at the new tip (stepwiseAddition :2994-2998
+// sets ti[1] = the new inner node, ti[2] = the tip), i.e. min_x (tip[x] + minplus(A' + B')[x]) with the tip's untransformed
+// vector (0 where the code allows x, highest elsewhere, :2739-2745) -- the junction form holds for symmetric matrices only.
+// list[e] = (view a, view b, tip's view id = tip - 1).
+template <int S>
+__global__ void __launch_bounds__(128) k_sk_tip_junction(const uint32_t *__restrict__ views, size_t vstride, int Lh,
+                                                         const int4 *__restrict__ list, int count,
+                                                         const uint8_t *__restrict__ codes, int P, const int32_t *__restrict__ inf_ptn, int n_inf,
+                                                         const uint32_t *__restrict__ mask_table, uint32_t highest, int pair0,
+                                                         const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
+                                                         uint32_t *__restrict__ segout)
+{
+    constexpr int V = SkLay<S>::V;
+    const int nchunks = Lh / (32 * V);
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (int64_t)count * nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int)(gw / count), e = (int)(gw % count);
+    const size_t off = (size_t)chunk * S * 32 * V + lane * V;
+    const int i0 = chunk * 32 * V + lane * V;
+    const int4 j = __ldg(list + e);
+    SkCost<S> cm; cm.init();
+    uint32_t a[S * V], b[S * V], t[S * V], best[V];
+    sk_load<S, V>(views + (size_t)j.x * vstride + off, a);
+    sk_load<S, V>(views + (size_t)j.y * vstride + off, b);
+#pragma unroll
+    for (int x = 0; x < S * V; x++) a[x] += b[x];
+    sk_minplus<S, V>(cm, a, t);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+        const int64_t gp = 2 * ((int64_t)pair0 + i0 + k);
+        uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+        if (gp < n_inf) m0 = mask_table[codes[(size_t)j.z * P + inf_ptn[gp]]];
+        if (gp + 1 < n_inf) m1 = mask_table[codes[(size_t)j.z * P + inf_ptn[gp + 1]]];
+        uint32_t bk = 0xFFFFFFFFu;
+#pragma unroll
+        for (int x = 0; x < S; x++) {
+            const uint32_t tip = ((m0 >> x) & 1u ? 0u : highest) | ((m1 >> x) & 1u ? 0u : highest) << 16;
+            bk = __vminu2(bk, tip + t[x * V + k]);
+        }
+        best[k] = bk;
+    }
+    uint2 w[V];
+#pragma unroll
+    for (int k = 0; k < V; k++) w[k] = __ldg(wts + i0 + k);
+    const SkSeg g = sk_seg_setup(__ldg(segof + i0), lane);
+    sk_accum<V>(best, w, g, segout + (size_t)e * nseg);
+}
+
 // ---- the SPR scan (testInsertParsimony batched; same program streams as k_spr_scan) ------------
 // One warp = (task, chunk).  The stack holds U' (transformed up-views) per lane in shared memory:
 // [slot][state][lane][V].
@@ -302,11 +351,15 @@ __device__ __forceinline__ void sk_emit(const uint32_t (&best)[V], const uint2 (
     }
 }
 
-template <int S, int V, bool ROWS>
+// ASYM (an asymmetric cost matrix): the score of the insertion is the reference's ROOTED evaluation at r, the node above the
+// insertion point -- min_x (U_c[x] + minplus(S' + view(c)')[x]) with U_c = U_y' + X' untransformed (evaluateSankoff...
+// :905-918 with left = r, right = the re-inserted node, after insertParsimony's newview :1951) -- instead of the junction
+// min_z (U_c' + view(c)' + S')[z], which equals it only when cost[i][j] == cost[j][i].  pu = where U lives (stack slot or view).
+template <int S, int V, bool ROWS, bool ASYM>
 __device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U)[S * V], const uint32_t *__restrict__ px,
                                          const uint32_t *__restrict__ pc, const uint32_t *__restrict__ ps,
                                          bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
-                                         const uint2 (&w)[V], const SkSeg &g)
+                                         const uint2 (&w)[V], const SkSeg &g, const uint32_t *pu)
 {
     // Large S (V = 1): the target state z is a rolled loop (2 per trip, two accumulators each) so that the body stays in the
     // instruction cache (fully unrolled it is 2 x S*S instructions per child), the cost row of z comes from shared memory
@@ -319,6 +372,47 @@ __device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U
 #pragma unroll
     for (int x = 0; x < S; x++) U1[x] += U[x];
     uint32_t best = 0xFFFFFFFFu;
+    if constexpr (ASYM) {
+        if (do_dst) {
+#pragma unroll 1
+            for (int z = 0; z < S; z += 2) {
+                const uint4 *c0 = reinterpret_cast<const uint4 *>(sk_smem + z * S), *c1 = reinterpret_cast<const uint4 *>(sk_smem + (z + 1) * S);
+                uint32_t a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int x = 0; x < S; x += 4) {
+                    const uint4 p = c0[x >> 2], q = c1[x >> 2];
+                    a0 = __viaddmin_u16x2(U1[x], p.x, a0);     a1 = __viaddmin_u16x2(U1[x + 1], p.y, a1);
+                    a0 = __viaddmin_u16x2(U1[x + 2], p.z, a0); a1 = __viaddmin_u16x2(U1[x + 3], p.w, a1);
+                    b0 = __viaddmin_u16x2(U1[x], q.x, b0);     b1 = __viaddmin_u16x2(U1[x + 1], q.y, b1);
+                    b0 = __viaddmin_u16x2(U1[x + 2], q.z, b0); b1 = __viaddmin_u16x2(U1[x + 3], q.w, b1);
+                }
+                dst[z * 32] = __vminu2(a0, a1); dst[(z + 1) * 32] = __vminu2(b0, b1);
+            }
+        }
+        if (do_out) {
+            uint32_t Wv[S];                                // the re-inserted node's vector: S' + view(c)'
+#pragma unroll
+            for (int x = 0; x < S; x++) Wv[x] = __ldg(pc + x * 32) + __ldg(ps + x * 32);
+#pragma unroll 1
+            for (int z = 0; z < S; z += 2) {
+                const uint4 *c0 = reinterpret_cast<const uint4 *>(sk_smem + z * S), *c1 = reinterpret_cast<const uint4 *>(sk_smem + (z + 1) * S);
+                uint32_t a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int x = 0; x < S; x += 4) {
+                    const uint4 p = c0[x >> 2], q = c1[x >> 2];
+                    a0 = __viaddmin_u16x2(Wv[x], p.x, a0);     a1 = __viaddmin_u16x2(Wv[x + 1], p.y, a1);
+                    a0 = __viaddmin_u16x2(Wv[x + 2], p.z, a0); a1 = __viaddmin_u16x2(Wv[x + 3], p.w, a1);
+                    b0 = __viaddmin_u16x2(Wv[x], q.x, b0);     b1 = __viaddmin_u16x2(Wv[x + 1], q.y, b1);
+                    b0 = __viaddmin_u16x2(Wv[x + 2], q.z, b0); b1 = __viaddmin_u16x2(Wv[x + 3], q.w, b1);
+                }
+                // U_c[z] (untransformed) re-read from where its two terms live: a dynamic index into U1 would go to local memory
+                const uint32_t u0 = pu[z * 32] + __ldg(px + z * 32), u1 = pu[(z + 1) * 32] + __ldg(px + (z + 1) * 32);
+                best = __vimin3_u16x2(best, u0 + __vminu2(a0, a1), u1 + __vminu2(b0, b1));
+            }
+            uint32_t bv[V] = {best};
+            sk_emit<V, ROWS>(bv, w, g, out_row);
+        }
+    } else {
 #pragma unroll 1
     for (int z = 0; z < S; z += 2) {
         const uint4 *c0 = reinterpret_cast<const uint4 *>(sk_smem + z * S), *c1 = reinterpret_cast<const uint4 *>(sk_smem + (z + 1) * S);
@@ -343,10 +437,11 @@ __device__ __forceinline__ void sk_child(const SkCost<S> &cm, const uint32_t (&U
         uint32_t bv[V] = {best};
         sk_emit<V, ROWS>(bv, w, g, out_row);
     }
+    }
 }
 
 // register form (small S): X = sibling view, C = the child's own view, Sv = pruned subtree, all already loaded
-template <int S, int V, bool ROWS>
+template <int S, int V, bool ROWS, bool ASYM>
 __device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (&U)[S * V], const uint32_t (&X)[S * V],
                                            const uint32_t (&C)[S * V], const uint32_t (&Sv)[S * V],
                                            bool do_out, uint32_t *__restrict__ out_row, bool do_dst, uint32_t *__restrict__ dst,
@@ -355,6 +450,26 @@ __device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (
     uint32_t U1[S * V], U1p[S * V];
 #pragma unroll
     for (int x = 0; x < S * V; x++) U1[x] = U[x] + X[x];
+    if constexpr (ASYM) {                    // see sk_child
+        if (do_dst) {
+            sk_minplus<S, V>(cm, U1, U1p);
+#pragma unroll
+            for (int z = 0; z < S; z++) sk_stv<V>(dst + z * 32 * V, &U1p[z * V]);
+        }
+        if (do_out) {
+            uint32_t Wv[S * V], Wp[S * V], best[V];
+#pragma unroll
+            for (int x = 0; x < S * V; x++) Wv[x] = C[x] + Sv[x];
+            sk_minplus<S, V>(cm, Wv, Wp);
+#pragma unroll
+            for (int k = 0; k < V; k++) best[k] = 0xFFFFFFFFu;
+#pragma unroll
+            for (int z = 0; z < S; z++)
+#pragma unroll
+                for (int k = 0; k < V; k++) best[k] = __vminu2(best[k], U1[z * V + k] + Wp[z * V + k]);
+            sk_emit<V, ROWS>(best, w, g, out_row);
+        }
+    } else {
     sk_minplus<S, V>(cm, U1, U1p);
     if (do_dst) {
 #pragma unroll
@@ -370,10 +485,11 @@ __device__ __forceinline__ void sk_child_r(const SkCost<S> &cm, const uint32_t (
             for (int k = 0; k < V; k++) best[k] = __vminu2(best[k], U1p[z * V + k] + C[z * V + k] + Sv[z * V + k]);
         sk_emit<V, ROWS>(best, w, g, out_row);
     }
+    }
 }
 
 // ROWS: row_of[candidate] >= 0 selects the candidates whose vector is wanted; rows = [row][Lh]
-template <int S, bool ROWS>
+template <int S, bool ROWS, bool ASYM>
 __global__ void __launch_bounds__(128, S <= 4 ? 5 : 1) k_sk_scan(const uint4 *__restrict__ views4, int Lh,
                                                  const ScanTask *__restrict__ tasks, int ntasks,
                                                  const int2 *__restrict__ offs, const int2 *__restrict__ ctl,
@@ -444,6 +560,7 @@ __global__ void __launch_bounds__(128, S <= 4 ? 5 : 1) k_sk_scan(const uint4 *__
             if (o2 != 0xffff) { const int r = __ldg(rowc + o2); if (r < 0) o2 = 0xffff; else out2 = rows + (size_t)r * Lh + i0; }
         }
         uint32_t U[S * V];
+        const uint32_t *pu = src < 0xfe ? stack + (size_t)src * S * 32 * V : vbase + (size_t)(uint32_t)(src == 0xff ? t0.z : t0.y) * 4;
         if (src < 0xfe) {
             const uint32_t *sp = stack + (size_t)src * S * 32 * V;
 #pragma unroll
@@ -456,11 +573,11 @@ __global__ void __launch_bounds__(128, S <= 4 ? 5 : 1) k_sk_scan(const uint4 *__
         }
         if constexpr (HOLD) {
             if (o1 != 0xffff || dst1 != 0xff)
-                sk_child_r<S, V, ROWS>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(B), reinterpret_cast<uint32_t (&)[S * V]>(A),
+                sk_child_r<S, V, ROWS, ASYM>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(B), reinterpret_cast<uint32_t (&)[S * V]>(A),
                                  reinterpret_cast<uint32_t (&)[S * V]>(Sv), o1 != 0xffff, out1, dst1 != 0xff,
                                  stack + (size_t)dst1 * S * 32 * V, w, g);
             if (o2 != 0xffff || dst2 != 0xff)
-                sk_child_r<S, V, ROWS>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(A), reinterpret_cast<uint32_t (&)[S * V]>(B),
+                sk_child_r<S, V, ROWS, ASYM>(cm, U, reinterpret_cast<uint32_t (&)[S * V]>(A), reinterpret_cast<uint32_t (&)[S * V]>(B),
                                  reinterpret_cast<uint32_t (&)[S * V]>(Sv), o2 != 0xffff, out2, dst2 != 0xff,
                                  stack + (size_t)dst2 * S * 32 * V, w, g);
 #pragma unroll
@@ -469,11 +586,11 @@ __global__ void __launch_bounds__(128, S <= 4 ? 5 : 1) k_sk_scan(const uint4 *__
             const uint32_t *pa = vbase + (size_t)(uint32_t)fc.x * 4;
             const uint32_t *pb = vbase + (size_t)(uint32_t)fc.y * 4;
             if (o1 != 0xffff || dst1 != 0xff)
-                sk_child<S, V, ROWS>(cm, U, pb, pa, ps, o1 != 0xffff, out1, dst1 != 0xff, stack + (size_t)dst1 * S * 32 * V,
-                               w, g);
+                sk_child<S, V, ROWS, ASYM>(cm, U, pb, pa, ps, o1 != 0xffff, out1, dst1 != 0xff, stack + (size_t)dst1 * S * 32 * V,
+                               w, g, pu);
             if (o2 != 0xffff || dst2 != 0xff)
-                sk_child<S, V, ROWS>(cm, U, pa, pb, ps, o2 != 0xffff, out2, dst2 != 0xff, stack + (size_t)dst2 * S * 32 * V,
-                               w, g);
+                sk_child<S, V, ROWS, ASYM>(cm, U, pa, pb, ps, o2 != 0xffff, out2, dst2 != 0xff, stack + (size_t)dst2 * S * 32 * V,
+                               w, g, pu);
         }
     }
     if (!HOLD) __syncwarp();               // the next work item reuses the stack
@@ -612,14 +729,18 @@ __global__ void k_sk_res_gather(const int32_t *__restrict__ X, const int32_t *__
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-#define SK_DISPATCH(CALL)                                                                      \
+#define SK_DISPATCH(...)                                                                       \
     switch (c->S) {                                                                            \
-    case 2:  { constexpr int S_ = 2;  CALL; } break;                                           \
-    case 4:  { constexpr int S_ = 4;  CALL; } break;                                           \
-    case 20: { constexpr int S_ = 20; CALL; } break;                                           \
-    case 32: { constexpr int S_ = 32; CALL; } break;                                           \
+    case 2:  { constexpr int S_ = 2;  __VA_ARGS__; } break;                                    \
+    case 4:  { constexpr int S_ = 4;  __VA_ARGS__; } break;                                    \
+    case 20: { constexpr int S_ = 20; __VA_ARGS__; } break;                                    \
+    case 32: { constexpr int S_ = 32; __VA_ARGS__; } break;                                    \
     default: set_error("unsupported state count"); return 1;                                   \
     }
+
+// the same with AS_ = the cost matrix is asymmetric (the rooted form of the insertion score, see sk_child)
+#define SK_DISPATCH_A(...)                                                                     \
+    if (c->sk.asym) { constexpr bool AS_ = true; SK_DISPATCH(__VA_ARGS__) } else { constexpr bool AS_ = false; SK_DISPATCH(__VA_ARGS__) }
 
 void sk_free(Ctx *c)
 {
@@ -841,7 +962,7 @@ static int sk_finish_rows(Ctx *c, int rows)
 
 // scores of `count` junctions (view ids a, b, c); results in c->sk.h_tot[j] = (total, est); ptn = per-pattern
 // minima of junction 0 (u16, Lp entries) when not null
-int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn)
+int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn, bool tip_rooted)
 {
     Sankoff &k = c->sk;
     if (count <= 0) return 0;
@@ -857,6 +978,10 @@ int sk_junctions(Ctx *c, const int4 *list, int count, uint16_t *ptn)
     MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)count * k.nseg * sizeof(uint32_t), c->stream));
     const int64_t warps = (int64_t)count * (k.Lh / (32 * sk_vpl(c->S)));
     const int blocks = (int)((warps + 3) / 4);
+    if (tip_rooted && k.asym && !ptn) {       // stepwise insertion under an asymmetric matrix: list[e].z is a tip, the score is rooted there
+        SK_DISPATCH((k_sk_tip_junction<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, count, c->d_codes, c->P, c->d_inf_ptn,
+                                                                          c->n_inf, k.d_mask, k.highest, k.pair0, k.d_w, k.d_seg, k.nseg, k.d_segout)));
+    } else
     SK_DISPATCH((k_sk_junction<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, count, k.d_w, k.d_seg, k.nseg,
                                                                   k.d_segout, ptn ? k.d_tmp + k.pair0 : nullptr)));
     c->launches++;
@@ -927,8 +1052,8 @@ int sk_raw_view(Ctx *c, int ref, uint16_t *out)
 static int sk_scan_occupancy(Ctx *c, bool rows, size_t smem, int *per_sm)
 {
     int occ = 0;
-    if (rows) { SK_DISPATCH(MPGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sk_scan<S_, true>, 128, smem))); }
-    else { SK_DISPATCH(MPGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sk_scan<S_, false>, 128, smem))); }
+    if (rows) { SK_DISPATCH_A(MPGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sk_scan<S_, true, AS_>, 128, smem))); }
+    else { SK_DISPATCH_A(MPGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sk_scan<S_, false, AS_>, 128, smem))); }
     *per_sm = occ > 0 ? occ : 1;
     return 0;
 }
@@ -983,14 +1108,14 @@ int sk_run_scan(Ctx *c)
     {                                                                                                                          \
         static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */                                                                                          \
         if (smem > 48 * 1024 && smem > configured) {                                                                           \
-            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));   \
+            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, false, AS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));   \
             configured = 200 * 1024;                                                                                           \
         }                                                                                                                      \
-        k_sk_scan<S_, false><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
+        k_sk_scan<S_, false, AS_><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
             c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
             pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, nullptr, nullptr, c->S > 4 ? k.d_stack : nullptr);                \
     }
-    SK_DISPATCH(SK_SCAN_LAUNCH);
+    SK_DISPATCH_A(SK_SCAN_LAUNCH);
 #undef SK_SCAN_LAUNCH
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
@@ -1077,14 +1202,14 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
     {                                                                                                                          \
         static size_t configured_dev[64] = {0}; size_t &configured = configured_dev[c->device & 63];   /* the attribute is per device */                                                                                          \
         if (smem > 48 * 1024 && smem > configured) {                                                                           \
-            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024))); \
+            MPGPU_CUDA(cudaFuncSetAttribute(k_sk_scan<S_, true, AS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024))); \
             configured = 200 * 1024;                                                                                           \
         }                                                                                                                      \
-        k_sk_scan<S_, true><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
+        k_sk_scan<S_, true, AS_><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
             c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
             pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, k.d_row_of, k.d_rows + k.Lh, c->S > 4 ? k.d_stack : nullptr);     \
     }
-        SK_DISPATCH(SK_ROWS_LAUNCH);
+        SK_DISPATCH_A(SK_ROWS_LAUNCH);
 #undef SK_ROWS_LAUNCH
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());

@@ -169,6 +169,63 @@ def test_oracle_seeded_cases(n, L, dt, seed, hi):
     assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
 
 
+@pytest.mark.parametrize("n,L,dt,seed,hi", [(40, 2500, 1, 151, 6), (24, 900, 2, 152, 5), (20, 500, 6, 153, 4), (18, 400, 0, 154, 7),
+                                             (70, 2000, 1, 155, 30)])
+def test_asymmetric_cost_matrix(n, L, dt, seed, hi):
+    """cost[i][j] != cost[j][i] is legal in the reference (parstree.cpp:31-90 only repairs the triangle inequality): scores then
+    depend on the root, so the device takes the reference's rooted forms -- an insertion is evaluated at r, the node above the
+    insertion point (testInsertParsimony :2160 on p->next->next), a stepwise insertion at the new tip (:2994-2998), the tree at
+    tr->start's neighbour.  Everything the symmetric cases check, against the oracle (pinned to the live reference on asymmetric
+    matrices by tests/test_oracle_cpu.py)."""
+    from mpboot_b200.engine import Engine
+    c = make_case(n, L, dt, seed)
+    S = {0: 2, 1: 4, 2: 20, 6: 32}[dt]
+    rng = np.random.default_rng(seed)
+    cost = rng.integers(1, hi, size=(S, S)); np.fill_diagonal(cost, 0)
+    if np.array_equal(cost, cost.T):
+        cost[0, 1] += 1
+    assert not np.array_equal(cost, cost.T)
+    ninf = c["n_inf"]
+    seg = np.array([s for s in range(80, ninf, 80)] + [ninf], dtype=np.int32)
+    ora = portlib.OracleEngine(c["codes"], c["weights"], dt)
+    hi_o = ora.set_cost_matrix(cost.astype(np.uint32), seg)
+    ora.set_ring(c["bn"], c["bs"])
+    eng = Engine()
+    eng.load_alignment(c["codes"], c["weights"], dt)
+    assert eng.set_cost_matrix(cost, seg) == hi_o
+    eng.set_tree(c["bn"], c["bs"])
+    ora.allocate(per_site=True)
+    s0 = ora.evaluate_full(per_site=True)
+    assert eng.tree_score() == s0
+    pp, sm = eng.pattern_parsimony()
+    opp, osm = ora.pattern_parsimony(ninf)
+    assert sm == osm and np.array_equal(pp[:ninf], opp[:ninf])
+    order = eng.visit_order()
+    vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, 5)
+    for i in range(1, 2 * n - 1):
+        ora.record(False)
+        ora.rearrange(i, 1, 5, True, s0)
+        assert np.array_equal(ora.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32)), i
+    for exact in (0, 1):                                  # whole searches, both modes, then RAS
+        eng.set_option("sankoff_exact", exact)
+        portlib.seed_rng(99)
+        ora.set_ring(c["bn"], c["bs"]); ora.allocate(bool(exact))
+        want = ora.optimize_spr(1, 5, bb=bool(exact))
+        wd = portlib.rng_draws()
+        wbn, wbs = ora.get_ring()
+        portlib.seed_rng(99)
+        ret, bn, bs, _ = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, 5)
+        assert ret == want and portlib.rng_draws() == wd
+        assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+    eng.set_option("sankoff_exact", 0)
+    portlib.seed_rng(11)
+    want = ora.ras(777 + seed, 4); wd = portlib.rng_draws(); wbn, wbs = ora.get_ring()
+    portlib.seed_rng(11)
+    best, bn, bs, _, _ = eng.stepwise_addition(777 + seed, 4, portlib.rng_fn_address())
+    assert best == want and portlib.rng_draws() == wd
+    assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+
+
 def test_unit_costs_equal_fitch_and_switch_back():
     from mpboot_b200.engine import Engine
     c = make_case(30, 2000, 1, 61)
@@ -192,9 +249,6 @@ def test_preconditions_fail_loudly():
     eng = Engine()
     eng.load_alignment(c["codes"], c["weights"], 1)
     seg = np.array([c["n_inf"]], dtype=np.int32)
-    asym = np.array([[0, 1, 2, 2], [2, 0, 2, 2], [2, 2, 0, 2], [2, 2, 2, 0]], dtype=np.uint32)
-    with pytest.raises(MpGpuError, match="asymmetric"):
-        eng.set_cost_matrix(asym, seg)
     with pytest.raises(MpGpuError, match="too large"):
         eng.set_cost_matrix((6000 * (1 - np.eye(4))).astype(np.uint32), seg)
     with pytest.raises(MpGpuError, match="segment_upper"):

@@ -122,3 +122,31 @@ def test_port_matches_reference_live(n, L, dt, seed):
     assert np.array_equal(ref.saved(), o.saved())
     r1 = ref.get_ring(); r2 = o.get_ring()
     assert np.array_equal(r1[0][3:], r2[0][3:]) and np.array_equal(r1[1][3:], r2[1][3:])
+
+
+@pytest.mark.skipif(not reflib.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("n,L,dt,seed,hi", [(20, 600, 1, 51, 6), (14, 300, 2, 52, 5), (12, 200, 6, 53, 4), (16, 300, 0, 54, 7)])
+def test_port_matches_reference_on_asymmetric_cost_matrices(n, L, dt, seed, hi):
+    """An asymmetric cost matrix makes Sankoff scores root-dependent; the port must follow the reference's own orientation
+    (evaluateSankoff... :905-918, left = p->back) -- tree score and every insertion score of a sweep, against the reference live.
+    This is what lets the GPU suite use the port as the oracle for asymmetric matrices."""
+    c = make_case(n, L, dt, seed)
+    S = {0: 2, 1: 4, 2: 20, 6: 32}[dt]
+    rng = np.random.default_rng(seed)
+    cost = rng.integers(1, hi, size=(S, S)); np.fill_diagonal(cost, 0)
+    if np.array_equal(cost, cost.T):
+        cost[0, 1] += 1
+    assert not np.array_equal(cost, cost.T)
+    ninf = c["n_inf"]
+    seg = np.array([s for s in range(80, ninf, 80)] + [ninf], dtype=np.int32)
+    got = []
+    for o in (portlib.OracleEngine(c["codes"], c["weights"], dt), reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=ninf)):
+        o.set_cost_matrix(cost.astype(np.uint32), seg)
+        o.set_ring(c["bn"], c["bs"]); o.allocate(per_site=True)
+        s0 = o.evaluate_full(per_site=True)
+        mps = []
+        for i in range(1, 2 * n - 1):
+            o.record(False); o.rearrange(i, 1, 5, True, s0)
+            mps.append(o.saved()[1:].copy())
+        got.append((s0, np.concatenate(mps)))
+    assert got[0][0] == got[1][0] and np.array_equal(got[0][1], got[1][1])
