@@ -36,8 +36,11 @@ CASES = {
     "mulhits_aa_20x600": (20, 600, synth.PLL_AA_DATA, 0.08, 13, ["-st", "AA", "-mulhits"]),
     # -cost (Sankoff weighted parsimony, ParsTree): transitions 1 / transversions 2; "@tstv" = a cost file written next to the alignment
     "cost_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv"]),
+    # an asymmetric matrix (obeys the triangle inequality, so ParsTree::initCostMatrix leaves it alone): scores depend on the root
+    "costasym_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@asym"]),
 }
-COST_FILES = {"@tstv": "4\n0 2 1 2\n2 0 2 1\n1 2 0 2\n2 1 2 0\n"}
+COST_FILES = {"@tstv": "4\n0 2 1 2\n2 0 2 1\n1 2 0 2\n2 1 2 0\n",
+              "@asym": "4\n0 3 1 2\n2 0 3 1\n2 2 0 3\n3 2 2 0\n"}
 MODES = {"plain": [], "bb": ["-bb", "1000"]}
 OUTPUTS = {"plain": [".treefile"], "bb": [".treefile", ".contree", ".splits.nex"]}
 
