@@ -506,15 +506,29 @@ def make_replicates(case, B, seed=5):
     return rng.multinomial(int(w.sum()), w / w.sum(), size=B).astype(np.uint16)
 
 
-def bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream):
-    """-bb at N > 1 (every rank calls this): the pattern-sharded contexts score the same sweep's candidates against all B
-    replicates -- each shard contracts its slice of the patterns, the row x replicate partial sums are summed by the
-    in-library exchange step (k_peer_allreduce over NVLink) -- device-timed as the max over ranks; rank 0 then checks
-    REPS vectors against an unsharded context over the whole alignment."""
+def bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream, mode):
+    """-bb at N > 1 (every rank calls this), the same sweep with the cutoff off, device-timed as the max over ranks, then a check
+    of REPS vectors against an unsharded context on rank 0.
+    mode "replicates" (north_star: replicates are sharded): every GPU holds the WHOLE C2 alignment and scores every candidate, but
+      contracts only its B / N replicates (mpgpu_set_replicate_shards) -- strong scaling of the 1-GPU bb step, nothing exchanged
+      on the device path (the searches exchange the rows of calls that can change a replicate);
+    mode "patterns": the pattern-sharded context of the main line -- each shard contracts its slice of the patterns and the
+      row x replicate partial sums (rows x 1024 s32) go through the exchange step."""
     import torch
     import torch.distributed as dist
-    from mpboot_b200 import engine
-    n, B, ninf = case["n"], args.replicates, case["n_inf"]
+    from mpboot_b200 import engine, sharded
+    B = args.replicates
+    if mode == "replicates":
+        case = build_case(args.workload, 1, "weak")                  # the single-GPU configuration, on every GPU
+        eng = engine.Engine(device=local, stream=stream)
+        eng.set_replicate_shards(rank, world)
+        sharded.connect_peers(eng)
+        eng.load_alignment(case["codes"], case["weights"], case["datatype"])
+        eng.set_tree(case["bn"], case["bs"])
+        order = eng.visit_order()
+        vb, mp, _, _ = eng.scan_visits(order, 1, 2 * case["n"] - 2, 1, args.maxtrav)
+        n_cand = len(mp)
+    n, ninf = case["n"], case["n_inf"]
     boot = make_replicates(case, B)
     seg = do_segmenting(eng.pattern_parsimony()[0][:ninf], case["weights"], ninf)
     eng.load_replicates(boot, seg)
@@ -547,12 +561,16 @@ def bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, loc
         one.scan_launch()
         want = one.reps_candidates(sample)
         one.close()
-        out = {"what": "the C2 sweep under -bb on %d pattern shards, cutoff off: scan + delta rows + contraction of each shard's patterns + "
-                       "in-library exchange of the row x replicate sums + combine" % world,
-               "replicates": B, "calls_per_step": int(len(calls)), "ms_per_step": step_ms,
+        what = ("the C2 sweep (200 x 100000, the 1-GPU configuration: strong scaling) under -bb with the %d replicates sharded over %d GPUs, cutoff off: "
+                "every GPU scans all candidates and contracts its B / N replicates" % (B, world)) if mode == "replicates" else \
+               ("the sweep of the main line under -bb on %d pattern shards, cutoff off: scan + delta rows + contraction of each shard's patterns + "
+                "in-library exchange of the row x replicate sums + combine" % world)
+        out = {"what": what, "replicates": B, "calls_per_step": int(len(calls)), "ms_per_step": step_ms,
                "reps_vectors_per_s": len(calls) / (step_ms * 1e-3), "insertions_per_s": n_cand / (step_ms * 1e-3),
                "check": {"reps_vectors_equal_unsharded": bool(np.array_equal(got, want)), "vectors_compared": int(len(sample))}}
         assert out["check"]["reps_vectors_equal_unsharded"], "sharded REPS vectors differ from the unsharded context"
+    if mode == "replicates":
+        eng.close()
     return out
 
 
@@ -908,9 +926,10 @@ def run_ours(args):
         r4["eng"].close()
         del r4
 
-    bb_sharded = None
+    bb_sharded = bb_patterns = None
     if world > 1 and not args.no_bb:
-        bb_sharded = bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream)
+        bb_sharded = bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream, "replicates")
+        bb_patterns = bench_bb_sharded(eng, case, order, vb, n_cand, args, flush, world, rank, local, stream, "patterns")
 
     if rank == 0:
         ops_per_ins = 2.0 * sites_total
@@ -945,6 +964,8 @@ def run_ours(args):
             line["c4_strong"] = c4
         if bb_sharded:
             line["bb"] = bb_sharded
+        if bb_patterns:
+            line["bb_pattern_shards"] = bb_patterns
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
         if world == 1 and not args.no_search:
             line["search"] = bench_search(eng, case, args)

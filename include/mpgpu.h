@@ -205,6 +205,15 @@ int mpgpu_refine_replicates(mpgpu_ctx *ctx, int B, const uint16_t *boot_samples,
 int mpgpu_stepwise_addition(mpgpu_ctx *ctx, int64_t *random_seed, int spr_dist, mpgpu_rng_fn rng, void *rng_user,
                             int32_t *back_node, int32_t *back_slot, uint32_t *best, int64_t *n_insertions);
 
+/* Replicate shards (multi-GPU -bb): every context holds the WHOLE alignment (shard_count = 1 at mpgpu_create) and scores all
+ * candidates itself, but keeps only its share [B*rank/count, B*(rank+1)/count) of the replicates, so the replicate contraction --
+ * the dominant cost under -bb -- divides by the number of GPUs.  Call before mpgpu_peer_prepare / mpgpu_set_allreduce and before
+ * mpgpu_load_replicates (which is still given the full B x stride table on every rank).  mpgpu_reps_* and the -bb searches keep
+ * their single-GPU meaning on every rank: the per-call hit flags are summed over the group and only the rows of calls that can
+ * change some replicate are assembled to full width through the exchange step, so every rank replays the same bookkeeping
+ * (iqtree.cpp:3405-3449 sees B replicates).  Also the way to run -cost -bb on several GPUs (pattern shards refuse it). */
+int mpgpu_set_replicate_shards(mpgpu_ctx *ctx, int rank, int count);
+
 /* ---- R8: replicate scoring, the REPS block of IQTree::saveCurrentTree (iqtree.cpp:3356-3449) ----
  * boot_samples: [B][stride] u16, boot_samples_pars exactly as IQTree::setParams fills it
  * (iqtree.cpp:220-233, 285-313; stride >= number of reported patterns); segment_upper/nseg
@@ -241,7 +250,8 @@ int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
  * the reference wraps inside a vector.  The matrix may be asymmetric (the reference only repairs the triangle inequality,
  * parstree.cpp:31-90): scores then depend on where the tree is rooted, and every entry point takes the reference's own rooting
  * (an insertion at the node above the insertion point, :2160; a stepwise insertion at the new tip, :2994-2998; the tree at
- * tr->start's neighbour) -- one more min-plus per scored insertion than for a symmetric matrix.  Sharded contexts: install
+ * tr->start's neighbour) -- one more min-plus per scored insertion than for a symmetric matrix; not together with -bb
+ * (mpgpu_load_replicates refuses: the reference's current-tree vector is then rooted at every visited edge in turn).  Sharded contexts: install
  * mpgpu_set_allreduce first (the shards hold ranges of pattern pairs; per-segment sums are reduced before the
  * 16-bit masks).  -cost with -bb: see mpgpu_sankoff_reps_stats below (unsharded contexts only). */
 int mpgpu_set_cost_matrix(mpgpu_ctx *ctx, const uint32_t *cost, int nstates, const int32_t *segment_upper, int nseg,

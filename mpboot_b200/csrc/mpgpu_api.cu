@@ -75,7 +75,13 @@ static void free_alignment(Ctx *c)
 
 int shard_sum(Ctx *c, void *dev_i32, int64_t count)
 {
-    if (c->shard_count == 1 || count <= 0 || c->exchange_off) return 0;
+    if (c->shard_count == 1) return 0;         // (replicate shards hold complete planes: nothing of the Fitch / Sankoff path is exchanged)
+    return group_sum(c, dev_i32, count);
+}
+
+int group_sum(Ctx *c, void *dev_i32, int64_t count)
+{
+    if (c->xcount() == 1 || count <= 0 || c->exchange_off) return 0;
     // small vectors (every count vector of the search): one kernel on the stream over NVLink peer memory, latency-bound;
     // large ones (-bb: rows x replicates of s32) are bandwidth-bound and go to the host's collective (NCCL ring / NVLS)
     // when one is installed next to the peer exchange -- the one-shot kernel moves shard_count x the vector

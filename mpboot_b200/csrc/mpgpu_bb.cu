@@ -39,7 +39,7 @@ void free_reps(Ctx *c)
 {
     Reps &r = c->reps;
     void *ptrs[] = {r.d_w8, r.d_w16T, r.d_seg_upper, r.d_segmax, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
-                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_call_hit, r.d_hit_list, r.d_res_hit};
+                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_call_hit, r.d_hit_list, r.d_res_hit, r.d_full};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (r.ev0) { cudaEventDestroy(r.ev0); cudaEventDestroy(r.ev1); }
     if (r.h_pin) cudaFreeHost(r.h_pin);
@@ -229,9 +229,23 @@ struct RepsOut {
 
 // Read-back of one chunk whose results sit in reps.d_res[ncalls][Bpad] (and hit flags in d_call_hit when thr):
 // the original-frequency column of every call, and only the rows of calls that can change a replicate.
+// replicate shards: rows [nrows][Bpad] of this rank's replicates (src, or the rows src[list[i]]) -> full-width rows
+// [nrows][Btot_pad] in d_full, every rank's columns in place, summed over the group (the other ranks' columns are zero here)
+static int assemble_full_rows(Ctx *c, const int32_t *src, int nrows, int Btot_pad)
+{
+    Reps &r = c->reps;
+    if (int rc = ensure(r.d_full, r.full_cap, (size_t)nrows * Btot_pad + 4)) return rc;
+    MPGPU_CUDA(cudaMemsetAsync(r.d_full, 0, (size_t)nrows * Btot_pad * 4, c->stream));
+    MPGPU_CUDA(cudaMemcpy2DAsync(r.d_full + r.rep_lo, (size_t)Btot_pad * 4, src, (size_t)r.Bpad * 4, (size_t)r.Buser * 4, (size_t)nrows,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+    return group_sum(c, r.d_full, (int64_t)nrows * Btot_pad);
+}
+
 static int reps_read_back(Ctx *c, int ncalls, int done, const int32_t *thr, RepsOut &out, std::vector<int32_t> &hit_list)
 {
     Reps &r = c->reps;
+    const bool reps_sharded = c->rep_count > 1;
+    const int W = out.Bpad;                                // row width on the host: Bpad, or the padded total over the replicate shards
     // ---- read back: the original-frequency score of every call (ratchet iterations) ----
     if (r.has_orig) {
         MPGPU_CUDA(cudaMemcpy2DAsync(out.orig.data() + done, 4, r.d_res + r.Buser, (size_t)r.Bpad * 4, 4, (size_t)ncalls,
@@ -243,6 +257,7 @@ static int reps_read_back(Ctx *c, int ncalls, int done, const int32_t *thr, Reps
     if (thr) {
         int32_t *fl = (int32_t *)r.pinned((size_t)ncalls * 4);
         if (!fl) { set_error("pinned host allocation failed"); return 2; }
+        if (reps_sharded) { if (int rc = group_sum(c, r.d_call_hit, ncalls)) return rc; }     // a call is read back when ANY shard's replicates can be hit
         MPGPU_CUDA(cudaMemcpyAsync(fl, r.d_call_hit, (size_t)ncalls * 4, cudaMemcpyDeviceToHost, c->stream));
         MPGPU_CUDA(cudaStreamSynchronize(c->stream));
         hit_list.clear();
@@ -255,26 +270,30 @@ static int reps_read_back(Ctx *c, int ncalls, int done, const int32_t *thr, Reps
                 if (int rc = ensure(r.d_res_hit, r.res_hit_cap, (size_t)nl * r.Bpad)) return rc;
                 MPGPU_CUDA(cudaMemcpyAsync(r.d_hit_list, hit_list.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
                 if (int rc = launch_gather_res_rows(c, r.d_res, r.d_hit_list, nl, r.d_res_hit)) return rc;
-                const size_t off = out.dense.size(), bytes = (size_t)nl * r.Bpad * 4;
+                const int32_t *rows = r.d_res_hit;
+                if (reps_sharded) { if (int rc = assemble_full_rows(c, r.d_res_hit, nl, W)) return rc; rows = r.d_full; }
+                const size_t off = out.dense.size(), bytes = (size_t)nl * W * 4;
                 void *hp = r.pinned(bytes);
                 if (!hp) { set_error("pinned host allocation failed"); return 2; }
-                MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res_hit, bytes, cudaMemcpyDeviceToHost, c->stream));
+                MPGPU_CUDA(cudaMemcpyAsync(hp, rows, bytes, cudaMemcpyDeviceToHost, c->stream));
                 MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-                out.dense.resize(off + (size_t)nl * r.Bpad);
+                out.dense.resize(off + (size_t)nl * W);
                 memcpy(out.dense.data() + off, hp, bytes);
-                for (int i = 0; i < nl; i++) out.dense_off[done + hit_list[i]] = (int64_t)(off + (size_t)i * r.Bpad);
+                for (int i = 0; i < nl; i++) out.dense_off[done + hit_list[i]] = (int64_t)(off + (size_t)i * W);
             }
         }
     }
     if (all_rows) {
-        const size_t off = out.dense.size(), bytes = (size_t)ncalls * r.Bpad * 4;
+        const int32_t *rows = r.d_res;
+        if (reps_sharded) { if (int rc = assemble_full_rows(c, r.d_res, ncalls, W)) return rc; rows = r.d_full; }
+        const size_t off = out.dense.size(), bytes = (size_t)ncalls * W * 4;
         void *hp = r.pinned(bytes);
         if (!hp) { set_error("pinned host allocation failed"); return 2; }
-        MPGPU_CUDA(cudaMemcpyAsync(hp, r.d_res, bytes, cudaMemcpyDeviceToHost, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(hp, rows, bytes, cudaMemcpyDeviceToHost, c->stream));
         MPGPU_CUDA(cudaStreamSynchronize(c->stream));
-        out.dense.resize(off + (size_t)ncalls * r.Bpad);
+        out.dense.resize(off + (size_t)ncalls * W);
         memcpy(out.dense.data() + off, hp, bytes);
-        for (int i = 0; i < ncalls; i++) out.dense_off[done + i] = (int64_t)(off + (size_t)i * r.Bpad);
+        for (int i = 0; i < ncalls; i++) out.dense_off[done + i] = (int64_t)(off + (size_t)i * W);
     }
     return 0;
 }
@@ -286,7 +305,7 @@ static int sk_reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, 
     const ScanPlan &pl = c->plan;
     if (thr) {
         if (!r.d_thr) MPGPU_CUDA(cudaMalloc((void **)&r.d_thr, (size_t)r.Bpad * 4));
-        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.Buser * 4, cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr + r.rep_lo, (size_t)r.Buser * 4, cudaMemcpyHostToDevice, c->stream));   // (replicate shards: this rank's thresholds)
     }
     std::vector<int32_t> &row_of = r.h_row_of, &call_row = r.h_row_tasks;
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -324,7 +343,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     Reps &r = c->reps;
     const ScanPlan &pl = c->plan;
     const HostTree &t = c->tree;
-    out.Bpad = r.Bpad;
+    out.Bpad = c->rep_count > 1 ? (r.B_total + 255) / 256 * 256 : r.Bpad;
     out.dense.clear();
     out.dense_off.assign(m, -1);
     out.orig.assign(r.has_orig ? m : 0, 0);
@@ -341,7 +360,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     const int max_rows = r.row_cap - kTreeRows;
     if (thr) {
         if (!r.d_thr) MPGPU_CUDA(cudaMalloc((void **)&r.d_thr, (size_t)r.Bpad * 4));
-        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr, (size_t)r.Buser * 4, cudaMemcpyHostToDevice, c->stream));
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_thr, thr + r.rep_lo, (size_t)r.Buser * 4, cudaMemcpyHostToDevice, c->stream));   // (replicate shards: this rank's thresholds)
     }
     // staging vectors live in the context: asynchronous uploads may still read them after we return
     std::vector<int32_t> &row_of = r.h_row_of, &row_tasks = r.h_row_tasks;
@@ -928,7 +947,7 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, 
     if (!c || !back_node || !back_slot || !hooks || !state || !best) { set_error("null argument"); return 1; }
     if (!hooks->random_double || !hooks->push_tree_logl || !hooks->materialize) { set_error("incomplete -bb hooks"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
-    if (state->B != c->reps.Buser || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
+    if (state->B != (c->rep_count > 1 ? c->reps.B_total : c->reps.Buser) || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
     if (state->policy != MPGPU_BB_DEFAULT && state->policy != MPGPU_BB_MULHITS && state->policy != MPGPU_BB_MULHITS_TOP) { set_error("unknown -bb policy"); return 1; }
     if (state->policy == MPGPU_BB_MULHITS_TOP && (!hooks->tophit || state->top_n < 1 || !state->top_count || !state->boot_threshold)) {
         set_error("policy MPGPU_BB_MULHITS_TOP needs the tophit hook, top_n >= 1, top_count and boot_threshold"); return 1;
@@ -1006,9 +1025,22 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
     if (B < 1 || nseg < 1) { set_error("need at least one replicate and one segment"); return 1; }
     if (c->sk.on && !c->sort_alignment) { set_error("-cost with -bb needs sort_alignment (informative patterns first)"); return 1; }
+    // Under an asymmetric matrix the reference's "current tree" call of every node visit is rooted at that visit's edge
+    // (rearrangeParsimony evaluates at p before it saves, :2286-2289), so its score and pattern vector change from visit to visit
+    // while the tree does not: the replicate path keeps ONE current-tree row per tree and cannot reproduce that.
+    if (c->sk.on && c->sk.asym) { set_error("-cost with an asymmetric matrix together with -bb is not supported (the current tree's vector depends on the visited edge)"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     free_reps(c);
     Reps &r = c->reps;
+    const int B_all = B;
+    int rep_lo = 0;
+    if (c->rep_count > 1) {                  // replicate shards: this context keeps replicates [lo, hi) (rows of `boot`)
+        rep_lo = (int)((int64_t)B * c->rep_rank / c->rep_count);
+        const int rep_hi = (int)((int64_t)B * (c->rep_rank + 1) / c->rep_count);
+        if (rep_hi <= rep_lo) { set_error("fewer replicates than replicate shards"); return 1; }
+        boot += (size_t)rep_lo * stride;
+        B = rep_hi - rep_lo;
+    }
     const int upper0 = c->sort_alignment ? c->n_inf : c->P;
     if (stride < upper0) { set_error("boot_samples stride is smaller than the number of reported patterns"); return 1; }
     for (int s = 0; s < nseg; s++) {
@@ -1081,8 +1113,20 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
             if (int rc3 = make_w8_tensor_map(c)) return rc3;
         }
     }
+    r.rep_lo = rep_lo; r.B_total = B_all;
     r.loaded = true;
     r.tree_valid = false;
+    return 0;
+}
+
+int mpgpu_set_replicate_shards(mpgpu_ctx *c, int rank, int count)
+{
+    if (!c) { set_error("null context"); return 1; }
+    if (count < 1 || rank < 0 || rank >= count) { set_error("bad shard arguments"); return 1; }
+    if (c->shard_count != 1) { set_error("replicate shards are for contexts that hold the whole alignment (shard_count = 1 at mpgpu_create)"); return 1; }
+    if (c->reps.loaded) { set_error("mpgpu_set_replicate_shards must precede mpgpu_load_replicates"); return 1; }
+    if (c->peer.ready || c->peer.region) { set_error("mpgpu_set_replicate_shards must precede mpgpu_peer_prepare"); return 1; }
+    c->rep_rank = rank; c->rep_count = count;
     return 0;
 }
 
@@ -1097,7 +1141,7 @@ int mpgpu_reps_current_tree(mpgpu_ctx *c, int32_t *res)
     const int32_t cand = -1;
     RepsOut ro;
     if (int rc = reps_run(c, &cand, 1, nullptr, ro)) return rc;
-    memcpy(res, ro.dense.data() + ro.dense_off[0], (size_t)c->reps.Buser * 4);
+    memcpy(res, ro.dense.data() + ro.dense_off[0], (size_t)(c->rep_count > 1 ? c->reps.B_total : c->reps.Buser) * 4);
     return 0;
 }
 
@@ -1124,7 +1168,8 @@ int mpgpu_reps_candidates(mpgpu_ctx *c, const int32_t *cand_idx, int m, int32_t 
     MPGPU_CUDA(cudaSetDevice(c->device));
     RepsOut ro;
     if (int rc = reps_run(c, cand_idx, m, nullptr, ro)) return rc;
-    for (int i = 0; i < m; i++) memcpy(res + (size_t)i * c->reps.Buser, ro.dense.data() + ro.dense_off[i], (size_t)c->reps.Buser * 4);
+    const size_t Bu = (size_t)(c->rep_count > 1 ? c->reps.B_total : c->reps.Buser);
+    for (int i = 0; i < m; i++) memcpy(res + (size_t)i * Bu, ro.dense.data() + ro.dense_off[i], Bu * 4);
     return 0;
 }
 

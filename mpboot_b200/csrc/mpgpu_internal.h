@@ -110,6 +110,8 @@ static const int kTreeRows = 17;          // rows 0..15: bit planes of the tree'
 struct Reps {
     bool loaded = false;
     bool loaded_sankoff = false;          // loaded while a cost matrix was set: REPS runs on per-pattern cost rows (sankoff.cu)
+    int rep_lo = 0, B_total = 0;          // replicate shards: first replicate held here, replicates over all shards (= Buser otherwise)
+    int32_t *d_full = nullptr; size_t full_cap = 0;   // replicate shards: full-width rows [calls][Btot_pad] assembled by the exchange
     int B = 0, Bpad = 0;                  // weight columns (replicates, + 1 for original_sample), padded to the tensor tile (256)
     int Buser = 0;                        // replicates proper: columns [0, Buser); column Buser = original_sample when has_orig
     bool has_orig = false;
@@ -233,7 +235,13 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int shard_rank = 0, shard_count = 1;
+    int shard_rank = 0, shard_count = 1;  // PATTERN shards: this context holds a word slice of every plane
+    // REPLICATE shards (mpgpu_set_replicate_shards; pattern-unsharded contexts only): every context holds the whole alignment and
+    // scores all candidates, but only columns [rep_lo, rep_lo + Buser) of the replicate-weight matrix: the -bb contraction, the
+    // dominant cost, divides by the number of GPUs, and only the rows of calls that can change a replicate are exchanged
+    int rep_rank = 0, rep_count = 1;
+    int xrank() const { return shard_count > 1 ? shard_rank : rep_rank; }     // rank / size of the exchange group
+    int xcount() const { return shard_count > 1 ? shard_count : rep_count; }
     mpgpu_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     PeerExchange peer;
     bool exchange_off = false;            // option "exchange" 0: shard_sum is skipped (timing the kernels alone; results stay partial)
@@ -348,7 +356,8 @@ static inline int ensure(T *&ptr, size_t &cap, size_t need)
 // ---- shared host helpers (mpgpu_api.cu) -----------------------------------------------------
 void peer_free(Ctx *c);
 int peer_allreduce(Ctx *c, void *dev_i32, int64_t count);
-int shard_sum(Ctx *c, void *dev_i32, int64_t count);   // in-place int32 all-reduce over the shards (no-op for one shard)
+int shard_sum(Ctx *c, void *dev_i32, int64_t count);
+int group_sum(Ctx *c, void *dev_i32, int64_t count);   // the same exchange over whatever group the context belongs to (pattern or replicate shards)   // in-place int32 all-reduce over the shards (no-op for one shard)
 int compute_views(Ctx *c, bool want_start_edge = false);
 int set_tree_impl(Ctx *c, const int32_t *back_node, const int32_t *back_slot, bool want_start_edge);
 int update_views(Ctx *c, bool defer = false);   // after apply_spr_move on c->tree: recompute only the stale views, one launch

@@ -107,7 +107,7 @@ int peer_allreduce(Ctx *c, void *dev_i32, int64_t count)
     int32_t *buf = static_cast<int32_t *>(dev_i32);
     PeerArgs a;
     for (int q = 0; q < kMaxPeers; q++) { a.slots[q] = px.slots[q]; a.flags[q] = px.flags[q]; }
-    a.rank = c->shard_rank; a.nranks = c->shard_count; a.cap = (unsigned long long)px.cap;
+    a.rank = c->xrank(); a.nranks = c->xcount(); a.cap = (unsigned long long)px.cap;
     int64_t done = 0;
     while (done < count) {
         const int64_t piece = std::min<int64_t>(count - done, (int64_t)px.cap);
@@ -148,14 +148,14 @@ extern "C" {
 int mpgpu_peer_prepare(mpgpu_ctx *c, int64_t capacity, void *handle_out)
 {
     if (!c || !handle_out) { set_error("null argument"); return 1; }
-    if (c->shard_count < 2) { set_error("peer exchange is for sharded contexts (shard_count >= 2)"); return 1; }
-    if (c->shard_count > kMaxPeers) { set_error("peer exchange supports up to 8 shards (one NVSwitch box)"); return 1; }
+    if (c->xcount() < 2) { set_error("peer exchange is for sharded contexts (pattern shards at mpgpu_create, or mpgpu_set_replicate_shards)"); return 1; }
+    if (c->xcount() > kMaxPeers) { set_error("peer exchange supports up to 8 shards (one NVSwitch box)"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     peer_free(c);
     PeerExchange &px = c->peer;
     if (capacity < 1024) capacity = 1024;
     px.cap = (size_t)((capacity + 3) & ~(int64_t)3);
-    const size_t R = (size_t)c->shard_count;
+    const size_t R = (size_t)c->xcount();
     const size_t slot_bytes = 2 * R * px.cap * sizeof(int32_t);
     const size_t flag_bytes = 2 * R * kPeerBlocks * sizeof(uint32_t);
     px.bytes = slot_bytes + flag_bytes;
@@ -177,11 +177,11 @@ int mpgpu_peer_connect(mpgpu_ctx *c, const void *handles)
     PeerExchange &px = c->peer;
     if (!px.region) { set_error("mpgpu_peer_prepare first"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
-    const size_t R = (size_t)c->shard_count;
+    const size_t R = (size_t)c->xcount();
     const size_t slot_bytes = 2 * R * px.cap * sizeof(int32_t);
-    for (int q = 0; q < c->shard_count; q++) {
+    for (int q = 0; q < c->xcount(); q++) {
         void *base = nullptr;
-        if (q == c->shard_rank) base = px.region;
+        if (q == c->xrank()) base = px.region;
         else {
             cudaIpcMemHandle_t h;
             memcpy(&h, static_cast<const char *>(handles) + (size_t)q * sizeof(h), sizeof(h));

@@ -71,6 +71,7 @@ def lib():
     L.mpgpu_reps_info.argtypes = [vp, vp, vp, vp]
     L.mpgpu_reps_timing.argtypes = [vp, vp, vp, vp, vp]
     L.mpgpu_int8_peak.argtypes = [vp, C.c_int, vp]
+    L.mpgpu_set_replicate_shards.argtypes = [vp, C.c_int, C.c_int]
     L.mpgpu_set_option.argtypes = [vp, C.c_char_p, i32]
     L.mpgpu_set_cost_matrix.argtypes = [vp, vp, i32, vp, i32, vp]
     L.mpgpu_sankoff_layout.argtypes = [vp, vp, vp, vp, i32]
@@ -463,6 +464,11 @@ class Engine:
         ms, rows, pat, sp = C.c_float(), C.c_int(), C.c_int(), C.c_int()
         self._ck(self.L.mpgpu_reps_timing(self.h, C.byref(ms), C.byref(rows), C.byref(pat), C.byref(sp)))
         return ms.value, rows.value, pat.value, sp.value
+
+    def set_replicate_shards(self, rank, count):
+        """multi-GPU -bb: this context keeps replicates [B*rank/count, B*(rank+1)/count) of what load_replicates is given"""
+        self._ck(self.L.mpgpu_set_replicate_shards(self.h, int(rank), int(count)))
+        self.rep_rank, self.rep_count = int(rank), int(count)
 
     def int8_peak(self, iters=4096):
         """measured tcgen05.mma kind::i8 issue rate of this device, int8 TOP/s"""

@@ -229,18 +229,25 @@ def test_sankoff_bb_search_matches_golden_and_oracle(k):
         o.set_cost_matrix(None, None)
 
 
-@pytest.mark.parametrize("asym", [False, True], ids=["symmetric", "asymmetric"])
+def test_asymmetric_cost_with_replicates_is_refused():
+    """Under an asymmetric matrix the reference's current-tree vector is rooted at the visited edge (:2286-2289) and changes from
+    visit to visit; the replicate path keeps one current-tree row per tree, so the combination fails loudly instead of drifting."""
+    from mpboot_b200.engine import MpGpuError
+    n, L, dt, seed, B, mu = SANKOFF_BB_CASES[0]
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu, heavy=False)
+    cost = sankoff_bb_cost(dt, seed).copy(); cost[0, 1] += 1
+    with pytest.raises(MpGpuError, match="asymmetric"):
+        _engine(c, boot, seg, 1, cost=cost)
+
+
 @pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
 @pytest.mark.parametrize("k", [0, 2])
-def test_sankoff_reps_tensor_path_equals_exact(k, tensor, asym):
+def test_sankoff_reps_tensor_path_equals_exact(k, tensor):
     """Light replicate weights, costs below 256, short segments: every chunk qualifies for the tcgen05 path; the same
-    vectors through the exact kernel (reps_tensor = 0) and through the oracle's u16 lanes.  asymmetric: the rooted form of
-    the insertion's per-pattern vector (k_sk_scan<ROWS, ASYM>)."""
+    vectors through the exact kernel (reps_tensor = 0) and through the oracle's u16 lanes."""
     n, L, dt, seed, B, mu = SANKOFF_BB_CASES[k]
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu, heavy=False)
     cost = sankoff_bb_cost(dt, seed)
-    if asym:
-        cost = cost.copy(); cost[0, 1] += 1; cost[2 % cost.shape[0], 0] += 2
     ninf = c["n_inf"]
     o.set_cost_matrix(cost, seg)
     try:

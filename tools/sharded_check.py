@@ -125,6 +125,60 @@ def main():
         if exchange == "peer":
             assert sh.peer_stats()[2] == 0, "peer exchange timed out waiting for a shard"
         one.close(); sh.close()
+    # ---- replicate shards (mpgpu_set_replicate_shards): whole alignment on every GPU, B / world replicates each ----
+    for (n, L, dt, seed, B) in [(30, 4000, 1, 21, 50), (22, 1500, 2, 22, 37), (26, 3000, 1, 23, 64)]:
+        c = make_case(n, L, dt, seed)
+        ninf = c["n_inf"]
+        one = engine.Engine(device=local, stream=st.cuda_stream)
+        rs = engine.Engine(device=local, stream=st.cuda_stream)
+        rs.set_replicate_shards(rank, world)
+        sharded.connect_peers(rs)
+        for e in (one, rs):
+            e.load_alignment(c["codes"], c["weights"], dt)
+            e.set_tree(c["bn"], c["bs"])
+        p1, _ = one.pattern_parsimony()
+        hv = [(1, 3, 40000), (2, 5, 300), (B - 1, 6, 65535)] + [(3, k, 900) for k in range(0, 40)]
+        boot = make_boot(c, B, seed, heavy=hv)
+        seg = bench.do_segmenting(p1[:ninf], c["weights"], ninf)
+        for e in (one, rs):
+            e.load_replicates(boot, seg)
+        assert np.array_equal(one.reps_current_tree(), rs.reps_current_tree())
+        order = one.visit_order()
+        a = one.scan_visits(order, 1, 2 * n - 2, 1, 6); b = rs.scan_visits(order, 1, 2 * n - 2, 1, 6)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        idx = np.arange(-1, min(len(a[1]), 500), dtype=np.int32)
+        assert np.array_equal(one.reps_candidates(idx), rs.reps_candidates(idx))
+        u = bb_run(one, c, boot, seg, 5); v = bb_run(rs, c, boot, seg, 5)
+        for k in range(len(u)):
+            assert np.array_equal(np.asarray(u[k]), np.asarray(v[k])), "replicate shards: bb result %d differs" % k
+        # -cost -bb: refused on pattern shards, runs on replicate shards
+        S = one.S
+        rng = np.random.default_rng(seed)
+        cost = rng.integers(1, 5, size=(S, S)); cost = np.minimum(cost, cost.T); np.fill_diagonal(cost, 0)
+        cseg = np.array([x for x in range(160, ninf, 160)] + [ninf], dtype=np.int32)
+        one2 = engine.Engine(device=local, stream=st.cuda_stream)
+        rs2 = engine.Engine(device=local, stream=st.cuda_stream)
+        rs2.set_replicate_shards(rank, world)
+        sharded.connect_peers(rs2)
+        boot2 = make_boot(c, B, seed + 1)
+        for e in (one2, rs2):
+            e.load_alignment(c["codes"], c["weights"], dt)
+            e.set_cost_matrix(cost, cseg)
+            e.set_tree(c["bn"], c["bs"])
+            e.load_replicates(boot2, cseg)
+        ac = one2.scan_visits(order, 1, 2 * n - 2, 1, 6); bc_ = rs2.scan_visits(order, 1, 2 * n - 2, 1, 6)
+        assert all(np.array_equal(x, y) for x, y in zip(ac, bc_))
+        idx = np.arange(-1, min(len(ac[1]), 300), dtype=np.int32)
+        assert np.array_equal(one2.reps_candidates(idx), rs2.reps_candidates(idx))
+        u2 = bb_run(one2, c, boot2, cseg, 6); v2 = bb_run(rs2, c, boot2, cseg, 6)
+        for k in range(len(u2)):
+            assert np.array_equal(np.asarray(u2[k]), np.asarray(v2[k])), "replicate shards: -cost -bb result %d differs" % k
+        assert rs.peer_stats()[2] == 0 and rs2.peer_stats()[2] == 0
+        if rank == 0:
+            print("[replicate shards] case n=%d L=%d dt=%d B=%d: x%d == unsharded (REPS vectors, whole -bb search: %d calls, %d vectors; -cost -bb search: %d vectors; %d exchange steps)"
+                  % (n, L, dt, B, world, u[4], u[5], u2[5], rs.peer_stats()[0]), flush=True)
+        for e in (one, rs, one2, rs2):
+            e.close()
     dist.barrier()
     if rank == 0:
         print("SHARDED_CHECK_OK world=%d" % world, flush=True)
