@@ -211,7 +211,8 @@ class Engine:
     def peer_connect(self, handles):
         """mpgpu_peer_connect: handles = uint8 [shard_count][64], the IPC handles of all shards in shard order."""
         h = np.ascontiguousarray(handles, dtype=np.uint8)
-        assert h.shape == (self.shard_count, 64)
+        group = self.shard_count if self.shard_count > 1 else getattr(self, "rep_count", 1)      # pattern or replicate shards
+        assert h.shape == (group, 64)
         self._ck(self.L.mpgpu_peer_connect(self.h, _p(h)))
 
     def peer_stats(self):
