@@ -250,8 +250,8 @@ int mpgpu_reps_info(mpgpu_ctx *ctx, int *groups, int *exceptions, int *tensor);
  * the reference wraps inside a vector.  The matrix may be asymmetric (the reference only repairs the triangle inequality,
  * parstree.cpp:31-90): scores then depend on where the tree is rooted, and every entry point takes the reference's own rooting
  * (an insertion at the node above the insertion point, :2160; a stepwise insertion at the new tip, :2994-2998; the tree at
- * tr->start's neighbour) -- one more min-plus per scored insertion than for a symmetric matrix; not together with -bb
- * (mpgpu_load_replicates refuses: the reference's current-tree vector is then rooted at every visited edge in turn).  Sharded contexts: install
+ * tr->start's neighbour; under -bb the current tree's vector at the edge of every node visit in turn, :2286-2289) -- one more
+ * min-plus per scored insertion than for a symmetric matrix.  Sharded contexts: install
  * mpgpu_set_allreduce first (the shards hold ranges of pattern pairs; per-segment sums are reduced before the
  * 16-bit masks).  -cost with -bb: see mpgpu_sankoff_reps_stats below (unsharded contexts only). */
 int mpgpu_set_cost_matrix(mpgpu_ctx *ctx, const uint32_t *cost, int nstates, const int32_t *segment_upper, int nseg,
@@ -295,7 +295,9 @@ int mpgpu_int8_peak(mpgpu_ctx *ctx, int iters, double *tops);
  * when no replicate is skipped).  Single shard. */
 int mpgpu_reps_current_tree(mpgpu_ctx *ctx, int32_t *res);
 /* The same for candidates of the last mpgpu_scan_visits / mpgpu_scan_plan batch: cand_idx[i]
- * indexes mp[] of that batch (-1 = the current tree); res is [m][B].  This is the REPS vector
+ * indexes mp[] of that batch (-1 = the current tree as evaluated at tr->start; -(2 + v) = the current tree as the batch's v-th
+ * node visit evaluates it, at its own edge, sprparsimony.cpp:2286 -- the same vector unless the cost matrix is asymmetric);
+ * res is [m][B].  This is the REPS vector
  * saveCurrentTree would compute inside testInsertParsimony (:2163-2166) for that insertion.
  * Single shard. */
 int mpgpu_reps_candidates(mpgpu_ctx *ctx, const int32_t *cand_idx, int m, int32_t *res);

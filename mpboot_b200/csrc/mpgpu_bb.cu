@@ -310,23 +310,37 @@ static int sk_reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, 
     std::vector<int32_t> &row_of = r.h_row_of, &call_row = r.h_row_tasks;
     MPGPU_CUDA(cudaStreamSynchronize(c->stream));
     const int cap = sk_reps_rows_capacity(c) - 1;
-    std::vector<int32_t> hit_list;
+    std::vector<int32_t> hit_list, visits, vrow;
+    const bool asym = c->sk.asym;
     int done = 0;
     while (done < m) {
         row_of.assign(pl.n_cand > 0 ? pl.n_cand : 1, -1);
-        call_row.clear();
+        call_row.clear(); visits.clear();
+        vrow.assign(pl.visit_ref.size() + 1, -1);
         int nsel = 0, k = done;
+        // call_row: 0 = the current tree at tr->start; -(1 + i) = the i-th visit row of the chunk; 1 + j = the j-th selected candidate
+        // (visit rows sit in front of the candidates' rows: the final row numbers are known once the chunk is carved)
         for (; k < m; k++) {
             const int j = cands[k];
-            if (j < 0) { call_row.push_back(0); continue; }
+            if (j < 0) {
+                // -(2 + v): the current tree as the v-th planned visit evaluates it (rooted at that visit's edge, :2286); the same
+                // vector as -1 unless the cost matrix is asymmetric
+                const int v = -j - 2;
+                if (!asym || j == -1) { call_row.push_back(0); continue; }
+                if (v >= (int)pl.visit_ref.size()) { set_error("visit index out of range"); return 1; }
+                if (vrow[v] < 0) { if (nsel + (int)visits.size() + 1 > cap) break; vrow[v] = (int)visits.size(); visits.push_back(v); }
+                call_row.push_back(-(1 + vrow[v]));
+                continue;
+            }
             if (j >= pl.n_cand) { set_error("candidate index out of range"); return 1; }
-            if (row_of[j] < 0) { if (nsel + 1 > cap) break; row_of[j] = nsel++; }
+            if (row_of[j] < 0) { if (nsel + (int)visits.size() + 1 > cap) break; row_of[j] = nsel++; }
             call_row.push_back(1 + row_of[j]);
         }
         if (k == done) { set_error("REPS row buffers too small for a single candidate"); return 1; }
         if (device_only && k < m) { set_error("REPS batch does not fit the row buffers in one piece (raise MPGPU_REPS_ROW_BYTES)"); return 1; }
-        const int ncalls = k - done;
-        if (int rc = sk_reps_chunk(c, row_of.data(), nsel, call_row.data(), ncalls, thr != nullptr)) return rc;
+        const int ncalls = k - done, nvis = (int)visits.size();
+        for (int &cr : call_row) cr = cr < 0 ? -cr : (cr > 0 ? cr + nvis : 0);      // visit row i -> 1 + i, candidate j -> 1 + nvis + j
+        if (int rc = sk_reps_chunk(c, row_of.data(), nsel, call_row.data(), ncalls, thr != nullptr, visits.data(), nvis)) return rc;
         if (device_only) return 0;
         if (int rc = reps_read_back(c, ncalls, done, thr, out, hit_list)) return rc;
         done = k;
@@ -591,7 +605,8 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
     uint32_t cur_score = score;                                     // score of the tree in c->tree
     unsigned int bestIterationScoreHits = 1;
     int64_t scored = 0;
-    std::vector<int32_t> order, vbegin, cref, cprune, pass_cands, call_of;
+    std::vector<int32_t> order, vbegin, cref, cprune, pass_cands, call_of, vis_idx;
+    std::vector<uint32_t> vis_score;
     std::vector<uint32_t> mp;
     std::vector<int32_t> thr;
     RepsOut ro;
@@ -640,6 +655,15 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
             vbegin.resize(count + 1); mp.resize(nc + 1); cref.resize(nc + 1); cprune.resize(nc + 1);
             if (int rc = finish_scan(c, vbegin.data(), mp.data(), cref.data(), cprune.data(), nc + 1)) return rc;
             prof.stop(1); prof.start();
+            // -cost with an asymmetric matrix: rearrangeParsimony evaluates the current tree at the visited edge before it saves it
+            // (:2286-2289), so the score (and the vector, see sk_reps_run) of a visit's current-tree call is rooted there
+            const bool visit_rooted = bb && c->sk.on && c->sk.asym;
+            if (visit_rooted) {
+                vis_idx.resize(count); vis_score.resize(count);
+                for (int v = 0; v < count; v++) vis_idx[v] = v;
+                if (int rc = sk_visit_edges(c, vis_idx.data(), count, nullptr)) return rc;
+                for (int v = 0; v < count; v++) vis_score[v] = c->sk.h_tot[v].x;
+            }
             if (bb) {
                 // every saveCurrentTree call of the batch, in order; call_of[] = index into the REPS results
                 mpgpu_bb_state *st = bb->st;
@@ -649,7 +673,10 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                 // every call of the batch is scored as long as the chain is alive (and none once it broke)
                 const bool all = st->ratchet && bb_passes_logl(st, -(double)ratchet_stale);
                 for (int v = 0; v < count; v++) {
-                    if (st->ratchet ? all : bb_passes(st, cur_score)) { call_of[(size_t)v + vbegin[v]] = (int32_t)pass_cands.size(); pass_cands.push_back(-1); }
+                    if (st->ratchet ? all : bb_passes(st, visit_rooted ? vis_score[v] : cur_score)) {
+                        call_of[(size_t)v + vbegin[v]] = (int32_t)pass_cands.size();
+                        pass_cands.push_back(visit_rooted ? -(2 + v) : -1);
+                    }
                     for (int j = vbegin[v]; j < vbegin[v + 1]; j++)
                         if (st->ratchet ? all : bb_passes(st, mp[j])) { call_of[(size_t)v + 1 + j] = (int32_t)pass_cands.size(); pass_cands.push_back(j); }
                 }
@@ -678,7 +705,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                     bb_save(bb, c, cur_logl, ro, k, remove_ref, insert_ref);
                     ratchet_stale = ro.orig[k];                                   // _pattern_pars now holds this tree's vector
                 };
-                if (bb) save_call(call_of[(size_t)v + vbegin[v]], cur_score, 0, 0);           // rearrangeParsimony :2286-2289
+                if (bb) save_call(call_of[(size_t)v + vbegin[v]], visit_rooted ? vis_score[v] : cur_score, 0, 0);   // rearrangeParsimony :2286-2289
                 for (int j = vbegin[v]; j < vbegin[v + 1]; j++) {
                     const uint32_t m = mp[j];
                     scored++;
@@ -1025,10 +1052,6 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     if (!c->d_codes) { set_error("no alignment loaded"); return 1; }
     if (B < 1 || nseg < 1) { set_error("need at least one replicate and one segment"); return 1; }
     if (c->sk.on && !c->sort_alignment) { set_error("-cost with -bb needs sort_alignment (informative patterns first)"); return 1; }
-    // Under an asymmetric matrix the reference's "current tree" call of every node visit is rooted at that visit's edge
-    // (rearrangeParsimony evaluates at p before it saves, :2286-2289), so its score and pattern vector change from visit to visit
-    // while the tree does not: the replicate path keeps ONE current-tree row per tree and cannot reproduce that.
-    if (c->sk.on && c->sk.asym) { set_error("-cost with an asymmetric matrix together with -bb is not supported (the current tree's vector depends on the visited edge)"); return 1; }
     MPGPU_CUDA(cudaSetDevice(c->device));
     free_reps(c);
     Reps &r = c->reps;

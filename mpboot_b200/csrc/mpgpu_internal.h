@@ -91,6 +91,7 @@ struct ScanPlan {
     std::vector<ScanCtl> ctl_host;
     std::vector<ScanTask> tasks;
     std::vector<int32_t> visit_begin;     // count+1
+    std::vector<int32_t> visit_ref;       // the ring slot each planned visit prunes at (tr->nodep[i])
     std::vector<int32_t> cand_ref, cand_prune, cand_task;
     std::vector<int32_t> task_vids;       // view ids of S, D1, D2 per task
     std::vector<ScanTask> sub_tasks;      // latency path: the tasks cut into independent sub-tasks (ScanPlanner::split); device copy behind the tasks
@@ -390,7 +391,9 @@ int sk_pattern_parsimony(Ctx *c, uint16_t *ptn_pars, int count, int32_t *sum);
 int sk_raw_view(Ctx *c, int ref, uint16_t *out);
 int sk_run_scan(Ctx *c);
 int sk_reps_rows_capacity(Ctx *c);
-int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_call_row, int ncalls, bool use_thr);
+int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_call_row, int ncalls, bool use_thr,
+                  const int32_t *h_visits = nullptr, int nvis = 0);
+int sk_visit_edges(Ctx *c, const int32_t *visits, int nv, uint32_t *d_rows_out);   // the current tree evaluated at the edges of planned visits -> h_tot (and rows)
 int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, int32_t *cand_prune, int capacity);
 
 // ---- kernel launchers (fitch_kernels.cu) -------------------------------------------------

@@ -335,6 +335,58 @@ __global__ void __launch_bounds__(128) k_sk_tip_junction(const uint32_t *__restr
     sk_accum<V>(best, w, g, segout + (size_t)e * nseg);
 }
 
+// ---- the current tree as rearrangeParsimony sees it at a node visit: evaluateParsimony(p) rooted at q = p->back (:2286),
+// min_x (q[x] + view(p)'[x]) with q's untransformed vector -- A' + B' of its two other neighbours, or its tip vector.  Only an
+// asymmetric matrix makes this differ from the junction at tr->start.  list[e] = (view p, a, b, 0) or (view p, tip - 1, 0, 1);
+// rows (nullable): the per-pattern minima of entry e go to rows[e][Lh] (pattern-pair order).
+template <int S>
+__global__ void __launch_bounds__(128) k_sk_edge_rows(const uint32_t *__restrict__ views, size_t vstride, int Lh,
+                                                      const int4 *__restrict__ list, int count,
+                                                      const uint8_t *__restrict__ codes, int P, const int32_t *__restrict__ inf_ptn, int n_inf,
+                                                      const uint32_t *__restrict__ mask_table, uint32_t highest, int pair0,
+                                                      const uint2 *__restrict__ wts, const int32_t *__restrict__ segof, int nseg,
+                                                      uint32_t *__restrict__ segout, uint32_t *__restrict__ rows)
+{
+    constexpr int V = SkLay<S>::V;
+    const int nchunks = Lh / (32 * V);
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (int64_t)count * nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int)(gw / count), e = (int)(gw % count);
+    const size_t off = (size_t)chunk * S * 32 * V + lane * V;
+    const int i0 = chunk * 32 * V + lane * V;
+    const int4 j = __ldg(list + e);
+    uint32_t pv[S * V], best[V];
+    sk_load<S, V>(views + (size_t)j.x * vstride + off, pv);
+    if (!j.w) {
+        sk_best3<S, V>(pv, views + (size_t)j.y * vstride + off, views + (size_t)j.z * vstride + off, best);
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+            const int64_t gp = 2 * ((int64_t)pair0 + i0 + k);
+            uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+            if (gp < n_inf) m0 = mask_table[codes[(size_t)j.y * P + inf_ptn[gp]]];
+            if (gp + 1 < n_inf) m1 = mask_table[codes[(size_t)j.y * P + inf_ptn[gp + 1]]];
+            uint32_t bk = 0xFFFFFFFFu;
+#pragma unroll
+            for (int x = 0; x < S; x++) {
+                const uint32_t tip = ((m0 >> x) & 1u ? 0u : highest) | ((m1 >> x) & 1u ? 0u : highest) << 16;
+                bk = __vminu2(bk, tip + pv[x * V + k]);
+            }
+            best[k] = bk;
+        }
+    }
+    if (rows) {
+#pragma unroll
+        for (int k = 0; k < V; k++) rows[(size_t)e * Lh + i0 + k] = best[k];
+    }
+    uint2 w[V];
+#pragma unroll
+    for (int k = 0; k < V; k++) w[k] = __ldg(wts + i0 + k);
+    const SkSeg g = sk_seg_setup(__ldg(segof + i0), lane);
+    sk_accum<V>(best, w, g, segout + (size_t)e * nseg);
+}
+
 // ---- the SPR scan (testInsertParsimony batched; same program streams as k_spr_scan) ------------
 // One warp = (task, chunk).  The stack holds U' (transformed up-views) per lane in shared memory:
 // [slot][state][lane][V].
@@ -1145,6 +1197,43 @@ int sk_finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref
 // One chunk of saveCurrentTree calls: call_row[i] = 0 for the current tree, 1 + k for the k-th selected candidate
 // (row_of[candidate] = k, -1 = not selected; nsel of them).  Leaves res[call][Bpad] in reps.d_res and the hit flags in
 // reps.d_call_hit (when thr).
+// The current tree evaluated at the edges of the planned visits visits[0..nv) (indices into plan.visit_ref): totals and early-exit
+// bounds land in h_tot[0..nv) (synchronizes), the per-pattern vectors in d_rows_out[e][Lh] when it is not null.
+int sk_visit_edges(Ctx *c, const int32_t *visits, int nv, uint32_t *d_rows_out)
+{
+    Sankoff &k = c->sk;
+    const HostTree &t = c->tree;
+    const ScanPlan &pl = c->plan;
+    if (nv <= 0) return 0;
+    if (c->shard_count != 1) { set_error("visit-rooted scores run on unsharded contexts only"); return 1; }
+    std::vector<int4> list((size_t)nv);
+    std::vector<int32_t> need;
+    for (int i = 0; i < nv; i++) {
+        if (visits[i] < 0 || visits[i] >= (int)pl.visit_ref.size()) { set_error("visit index out of range"); return 1; }
+        const int p = pl.visit_ref[visits[i]], q = t.back(p);
+        need.push_back(p);
+        if (t.is_tip(q)) list[i] = make_int4(t.vid(p), q / 3 - 1, 0, 1);
+        else {
+            const int a = t.back(t.next(q)), b = t.back(t.next(t.next(q)));
+            need.push_back(a); need.push_back(b);
+            list[i] = make_int4(t.vid(p), t.vid(a), t.vid(b), 0);
+        }
+    }
+    if (c->n_stale) { if (int rc = ensure_views(c, need.data(), (int)need.size(), false)) return rc; }
+    if (int rc = bind_cost(c)) return rc;
+    if (int rc = sk_ensure_out(c, (size_t)nv)) return rc;
+    if (int rc = ensure(k.d_list, k.list_cap, (size_t)nv)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(k.d_list, list.data(), (size_t)nv * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaMemsetAsync(k.d_segout, 0, (size_t)nv * k.nseg * sizeof(uint32_t), c->stream));
+    const int64_t warps = (int64_t)nv * (k.Lh / (32 * sk_vpl(c->S)));
+    const int blocks = (int)((warps + 3) / 4);
+    SK_DISPATCH((k_sk_edge_rows<S_><<<blocks, 128, 0, c->stream>>>(k.d_views, k.vstride, k.Lh, k.d_list, nv, c->d_codes, c->P, c->d_inf_ptn, c->n_inf,
+                                                                   k.d_mask, k.highest, k.pair0, k.d_w, k.d_seg, k.nseg, k.d_segout, d_rows_out)));
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return sk_finish_rows(c, nv);       // synchronizes: `list` is a host temporary
+}
+
 int sk_reps_rows_capacity(Ctx *c)
 {
     size_t budget = (size_t)2 << 30;
@@ -1153,12 +1242,15 @@ int sk_reps_rows_capacity(Ctx *c)
     return (int)std::max<size_t>(64, std::min<size_t>(budget / per_row, (size_t)1 << 20));
 }
 
-int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_call_row, int ncalls, bool use_thr)
+int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_call_row, int ncalls, bool use_thr,
+                  const int32_t *h_visits, int nvis)
 {
     Sankoff &k = c->sk;
     Reps &r = c->reps;
     ScanPlan &pl = c->plan;
-    const int nrows = 1 + nsel;
+    // rows: [0] the current tree rooted at tr->start, [1, 1 + nvis) the current tree at the edges of node visits (an asymmetric
+    // matrix only), then the selected candidates
+    const int nrows = 1 + nvis + nsel;
     if (c->shard_count != 1) { set_error("-cost with -bb runs on unsharded contexts only (a segment's 16-bit sum is not additive over shards)"); return 1; }
     if (int rc = bind_cost(c)) return rc;
     if (int rc = ensure(k.d_rows, k.rows_cap, (size_t)nrows * k.Lh)) return rc;
@@ -1188,6 +1280,7 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
         MPGPU_CUDA(cudaGetLastError());
         MPGPU_CUDA(cudaStreamSynchronize(c->stream));       // `j` is a stack temporary
     }
+    if (nvis > 0) { if (int rc = sk_visit_edges(c, h_visits, nvis, k.d_rows + k.Lh)) return rc; }
     if (nsel > 0) {
         MPGPU_CUDA(cudaMemcpyAsync(k.d_row_of, h_row_of, (size_t)pl.n_cand * 4, cudaMemcpyHostToDevice, c->stream));
         const int ntasks = (int)pl.tasks.size();
@@ -1207,7 +1300,7 @@ int sk_reps_chunk(Ctx *c, const int32_t *h_row_of, int nsel, const int32_t *h_ca
         }                                                                                                                      \
         k_sk_scan<S_, true, AS_><<<(unsigned)blocks, wpb * 32, smem, c->stream>>>(reinterpret_cast<const uint4 *>(k.d_views), k.Lh, \
             c->d_tasks, ntasks, reinterpret_cast<const int2 *>(c->d_offs), reinterpret_cast<const int2 *>(c->d_ctl), nslots,   \
-            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, k.d_row_of, k.d_rows + k.Lh, c->S > 4 ? k.d_stack : nullptr);     \
+            pl.task_cap, k.d_w, k.d_seg, k.nseg, k.d_segout, k.d_row_of, k.d_rows + (size_t)(1 + nvis) * k.Lh, c->S > 4 ? k.d_stack : nullptr);     \
     }
         SK_DISPATCH_A(SK_ROWS_LAUNCH);
 #undef SK_ROWS_LAUNCH

@@ -206,7 +206,7 @@ int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int c
                        int split_depth)
 {
     delete impl; impl = nullptr;
-    plan.tasks.clear(); plan.visit_begin.clear(); plan.task_vids.clear(); plan.need_refs.clear();
+    plan.tasks.clear(); plan.visit_begin.clear(); plan.visit_ref.clear(); plan.task_vids.clear(); plan.need_refs.clear();
     plan.sub_tasks.clear(); plan.task_tops.clear();
     plan.n_cand = 0; plan.n_ops = 0; plan.max_slot = 0;
     plan.task_cap = 2 * count;
@@ -247,6 +247,7 @@ void ScanPlanner::add(int v0, int v1)
     const int mintrav = impl->mintrav, maxtrav = impl->maxtrav;
     for (int v = v0; v < v1; v++) {
         plan.visit_begin.push_back(b.ncand);
+        plan.visit_ref.push_back(impl->order[impl->first + v]);
         if (maxtrav < mintrav) continue;                        // :2280
         const int p = impl->order[impl->first + v];
         const int q = t.back(p);

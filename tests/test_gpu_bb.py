@@ -229,25 +229,19 @@ def test_sankoff_bb_search_matches_golden_and_oracle(k):
         o.set_cost_matrix(None, None)
 
 
-def test_asymmetric_cost_with_replicates_is_refused():
-    """Under an asymmetric matrix the reference's current-tree vector is rooted at the visited edge (:2286-2289) and changes from
-    visit to visit; the replicate path keeps one current-tree row per tree, so the combination fails loudly instead of drifting."""
-    from mpboot_b200.engine import MpGpuError
-    n, L, dt, seed, B, mu = SANKOFF_BB_CASES[0]
-    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu, heavy=False)
-    cost = sankoff_bb_cost(dt, seed).copy(); cost[0, 1] += 1
-    with pytest.raises(MpGpuError, match="asymmetric"):
-        _engine(c, boot, seg, 1, cost=cost)
-
-
+@pytest.mark.parametrize("asym", [False, True], ids=["symmetric", "asymmetric"])
 @pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
 @pytest.mark.parametrize("k", [0, 2])
-def test_sankoff_reps_tensor_path_equals_exact(k, tensor):
+def test_sankoff_reps_tensor_path_equals_exact(k, tensor, asym):
     """Light replicate weights, costs below 256, short segments: every chunk qualifies for the tcgen05 path; the same
-    vectors through the exact kernel (reps_tensor = 0) and through the oracle's u16 lanes."""
+    vectors through the exact kernel (reps_tensor = 0) and through the oracle's u16 lanes.  asymmetric: the insertion's vector
+    in its rooted form (k_sk_scan<ROWS, ASYM>) and the current tree's vector rooted at every visited edge in turn (the call
+    -(2 + v), rearrangeParsimony :2286-2289), then a whole -bb search."""
     n, L, dt, seed, B, mu = SANKOFF_BB_CASES[k]
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu, heavy=False)
     cost = sankoff_bb_cost(dt, seed)
+    if asym:
+        cost = cost.copy(); cost[0, 1] += 1; cost[2 % cost.shape[0], 0] += 2
     ninf = c["n_inf"]
     o.set_cost_matrix(cost, seg)
     try:
@@ -258,7 +252,7 @@ def test_sankoff_reps_tensor_path_equals_exact(k, tensor):
         vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, 6)
         calls = []
         for v in range(2 * n - 2):
-            calls.append(-1); calls.extend(range(vb[v], vb[v + 1]))
+            calls.append(-(2 + v) if asym else -1); calls.extend(range(vb[v], vb[v + 1]))
         got = eng.reps_candidates(np.array(calls, dtype=np.int32))
         row = 0
         for i in range(1, 2 * n - 1):

@@ -1,3 +1,4 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests/test_gpu_bb.py -m gpu -q -x -k "tensor_path_equals_exact and asymmetric" 2>&1 | tail -40
+timeout 900 python -m pytest tests/test_gpu_bb.py tests/test_gpu_sankoff.py -m gpu -q -x 2>&1 | tail -12
+timeout 600 python -m pytest tests/test_gpu_dropin.py -m gpu -q -x -k "cost" 2>&1 | tail -5
