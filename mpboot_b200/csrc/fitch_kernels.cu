@@ -294,17 +294,16 @@ __global__ void __launch_bounds__(32 * NW) k_fitch_wave(uint32_t *views, size_t 
     const size_t gs = (size_t)Wl * Lay<S>::SG;
     const size_t off = (size_t)w * Lay<S>::SG;
 
-    // this warp's next triple: index nt, in level nl
-    int nt = -1, nl = 0;
-    {
-        int s0 = 0;
-        for (nl = 0; nl < nlevels; nl++) { const int e = level_end[nl]; if (s0 + warp < e) { nt = s0 + warp; break; } s0 = e; }
-    }
+    // this warp's next triple: index nt, in level nl.  The triples are dealt to the warps round robin over the WHOLE list, not per
+    // level: a lazy list of the search is a path with a view or two per level, and a warp that owns triples 8 levels apart has the
+    // clean operand of its next one in flight long before that level is reached (dealt per level, warps 0 and 1 did every level
+    // and waited a full L2 round trip in each).
+    int nt = warp < total ? warp : -1, nl = 0;
+    if (nt >= 0) while (nt >= level_end[nl]) nl++;
     uint32_t bp[S];
     if (nt >= 0) { const int4 d = tri[nt]; if (d.w & 0x10000) load_states_rw<S>(views + (size_t)d.z * view_stride + off, gs, bp); }
 
     for (int l = 0; l < nlevels; l++) {
-        const int t1 = level_end[l];
         while (nt >= 0 && nl == l) {
             const int cur = nt;
             const int4 d = tri[cur];
@@ -312,12 +311,8 @@ __global__ void __launch_bounds__(32 * NW) k_fitch_wave(uint32_t *views, size_t 
 #pragma unroll
             for (int k = 0; k < S; k++) b[k] = bp[k];
             // next triple of this warp and its clean operand
-            if (cur + NW < t1) nt = cur + NW;
-            else {
-                nt = -1;
-                int s0 = t1;
-                for (nl = l + 1; nl < nlevels; nl++) { const int e = level_end[nl]; if (s0 + warp < e) { nt = s0 + warp; break; } s0 = e; }
-            }
+            nt = cur + NW < total ? cur + NW : -1;
+            if (nt >= 0) while (nt >= level_end[nl]) nl++;
             if (nt >= 0) { const int4 dn = tri[nt]; if (dn.w & 0x10000) load_states_rw<S>(views + (size_t)dn.z * view_stride + off, gs, bp); }
             if (!(d.w & 0x10000)) load_states_rw<S>(views + (size_t)d.z * view_stride + off, gs, b);
             const int a_slot = d.w & 0xFF, d_slot = (d.w >> 8) & 0xFF;
@@ -366,14 +361,28 @@ static int launch_wave_t(Ctx *c, const Triple *d_list, int nlevels, int hdr, int
 int launch_wave(Ctx *c, const Triple *d_list, int nlevels, int hdr, int total, uint32_t *d_wcount)
 {
     if (nlevels == 0) return 0;
-    const int NW = 16;
+    // 16 warps per CTA: with the triples dealt round robin over the whole list a warp's next clean operand is in flight ~8 levels
+    // ahead on the lazy lists of the search (a view or two per level); 4 warps measured the same before that change
+    static const int forced = getenv("MPGPU_WAVE_WARPS") ? atoi(getenv("MPGPU_WAVE_WARPS")) : 0;      // tuning knob
+    const bool narrow = forced == 4;
     int rc = 0;
-    switch (c->S) {
-    case 2:  rc = launch_wave_t<2, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
-    case 4:  rc = launch_wave_t<4, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
-    case 20: rc = launch_wave_t<20, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
-    case 32: rc = launch_wave_t<32, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
-    default: set_error("unsupported state count"); return 1;
+    if (narrow) {
+        switch (c->S) {
+        case 2:  rc = launch_wave_t<2, 4>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        case 4:  rc = launch_wave_t<4, 4>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        case 20: rc = launch_wave_t<20, 4>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        case 32: rc = launch_wave_t<32, 4>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        default: set_error("unsupported state count"); return 1;
+        }
+    } else {
+        const int NW = 16;
+        switch (c->S) {
+        case 2:  rc = launch_wave_t<2, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        case 4:  rc = launch_wave_t<4, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        case 20: rc = launch_wave_t<20, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        case 32: rc = launch_wave_t<32, NW>(c, d_list, nlevels, hdr, total, d_wcount); break;
+        default: set_error("unsupported state count"); return 1;
+        }
     }
     if (rc) return rc;
     c->launches++;

@@ -494,6 +494,7 @@ int ensure_views(Ctx *c, const int32_t *refs, int count, bool defer)
     }
     if (stale.empty()) return 0;
     c->dl_dirty = true;                       // an error return below leaves dl dirty
+    c->lazy_lists++; c->lazy_views += (int64_t)stale.size(); c->lazy_levels += nlevels;
     const int rc = submit_stale(c, stale, nlevels, defer, true);
     for (const Triple &tr : stale) dl[tr.dst] = 0;
     c->dl_dirty = false;

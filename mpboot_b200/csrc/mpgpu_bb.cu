@@ -762,6 +762,9 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
         if (!registered) { registered = true; atexit([]() { g_sp.report(prof_names, 6); g_rp.report(g_rp_names, 8); }); }
     } else {
         prof.report(prof_names, 6);
+        if (prof.on && c->lazy_lists)
+            fprintf(stderr, "[mpgpu profile] lazy views: %lld lists, %.1f views in %.1f levels each (context totals)\n", (long long)c->lazy_lists,
+                    (double)c->lazy_views / c->lazy_lists, (double)c->lazy_levels / c->lazy_lists);
         g_rp.report(g_rp_names, 8);
         for (int k = 0; k < 8; k++) { g_rp.t[k] = 0; g_rp.n[k] = 0; }
     }

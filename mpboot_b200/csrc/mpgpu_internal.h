@@ -296,6 +296,7 @@ struct Ctx {
     // lazy views of the SPR search: after a move only the views the next scan batch reads are recomputed (ensure_views)
     std::vector<uint8_t> vstale;          // [4n-6] the view's content is out of date
     int n_stale = 0;
+    int64_t lazy_lists = 0, lazy_views = 0, lazy_levels = 0;   // statistics of the lazy lists (MPGPU_PROFILE)
     std::vector<int32_t> sc_refs;         // scratch: ring slots handed to ensure_views
     bool dl_dirty = false;                // sc_dl holds levels of an abandoned list
     Triple *d_wave = nullptr; size_t wave_cap = 0;
