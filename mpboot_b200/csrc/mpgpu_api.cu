@@ -743,9 +743,16 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
 {
     ScanPlan &pl = c->plan;
     const uint8_t *vstale = c->n_stale ? c->vstale.data() : nullptr;      // lazy views: the planner notes the stale views it reads
+    // the planner's slot table lives in the context: the SPR search patches the five nodes a move touches instead of paying O(n)
+    // per batch (set_tree and the stepwise phase drop it)
+    const uint32_t tab_stride = c->sk.on ? (uint32_t)(c->sk.vstride / 4) : (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
+    if (!c->ref_valid || c->ref_vstride != tab_stride || c->ref_table.size() != (size_t)3 * (2 * c->n - 1)) {
+        scan_ref_build(c->tree, tab_stride, c->ref_table);
+        c->ref_vstride = tab_stride; c->ref_valid = true;
+    }
     if (c->sk.on) {          // one piece: the per-(candidate, segment) output is sized from the finished plan
         ScanPlanner planner;
-        if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, (uint32_t)(c->sk.vstride / 4), pl, false, vstale)) return rc;
+        if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, (uint32_t)(c->sk.vstride / 4), pl, false, vstale, 0, c->ref_table.data())) return rc;
         planner.add(0, count);
         planner.finish();
         if (int rc = ensure_views(c, pl.need_refs.data(), (int)pl.need_refs.size(), false)) return rc;
@@ -762,7 +769,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
     g_bp.armed = g_bp.on && pieces == 1;
     if (g_bp.armed) { g_bp.h0 = std::chrono::steady_clock::now(); g_bp.rec(0, c->stream); }
     ScanPlanner planner;
-    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl, false, vstale, sd)) return rc;
+    if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl, false, vstale, sd, c->ref_table.data())) return rc;
     if (int rc = reserve_plan(c)) return rc;
     if (int rc = zero_counts(c, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     int v0 = 0;
@@ -1079,7 +1086,7 @@ int set_tree_impl(Ctx *c, const int32_t *back_node, const int32_t *back_slot, bo
     }
     if (bad) { c->tree_set = false; c->lens_valid = false; c->kids_valid = false; set_error(bad); return 1; }
     c->tree.n = n; c->tree.bn.swap(t.bn); c->tree.bs.swap(t.bs);
-    c->tree_set = true; c->lens_valid = false;
+    c->tree_set = true; c->lens_valid = false; c->ref_valid = false;
     if (int rc = compute_views(c, want_start_edge)) return rc;
     if (c->reduces()) compute_lengths(c);
     return 0;

@@ -726,6 +726,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                     const int touched[5] = {removeNode / 3, pa / 3, pb / 3, insertNode / 3, c->tree.back(insertNode) / 3};
                     apply_spr_move(c->tree, removeNode, insertNode);              // :3312
                     if (lazy) mark_stale_nodes(c, touched, 5);
+                    if (c->ref_valid) for (int k5 = 0; k5 < 5; k5++) scan_ref_fill(c->tree, c->ref_vstride, c->ref_table.data(), touched[k5]);
                     randomMP = bestParsimony;
                     cur_score = bestParsimony;
                     moved = true;
@@ -800,6 +801,7 @@ static int stepwise_phase(mpgpu_ctx *c, int64_t *seed, mpgpu_rng_fn rng, void *r
     const int n = c->n;
     HostTree &t = c->tree;
     t.n = n;
+    c->ref_valid = false;
     t.bn.assign(3 * (2 * n - 1), 0); t.bs.assign(3 * (2 * n - 1), 0);
     std::vector<int> perm(n + 2);
     for (int i = 1; i <= n; i++) perm[i] = i;                                   // makePermutationFast :2221

@@ -62,6 +62,10 @@ struct ScanTask {
     int32_t pad;
 };
 
+// One record per ring slot for the enumeration of a scan plan: the two slots behind an inner slot, the view offset (vector units)
+// and tip = view id << 2 | noted-by-the-current-plan << 1 | is-tip
+struct ScanRef { int32_t c1, c2, voff, tip; };
+
 // Page-locked (and device-mapped: k_publish writes wave counts straight into one) host array: the plan streams are uploaded piece by piece while the host keeps
 // appending, so the copies must be truly asynchronous (pageable memory is staged synchronously).
 template <typename T> struct PinnedArray {
@@ -305,6 +309,7 @@ struct Ctx {
 
     // scan
     ScanPlan plan;
+    std::vector<ScanRef> ref_table; uint32_t ref_vstride = 0; bool ref_valid = false;   // the planner's slot table, kept across the batches of a search
     ScanOffs *d_offs = nullptr; size_t offs_cap = 0;
     ScanCtl *d_ctl = nullptr; size_t ctl_cap = 0;
     ScanTask *d_tasks = nullptr; size_t tasks_cap = 0;
@@ -436,7 +441,7 @@ public:
     ~ScanPlanner();
     int begin(const HostTree &t, const int32_t *order, int first, int count,
               int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan, bool host_only = false,
-              const uint8_t *vstale = nullptr, int split_depth = 0);
+              const uint8_t *vstale = nullptr, int split_depth = 0, ScanRef *table = nullptr);
     void add(int v0, int v1);
     void finish();
     void split();
@@ -449,6 +454,8 @@ private:
 int build_scan_plan(const HostTree &t, const int32_t *order,
                     int first, int count, int mintrav, int maxtrav, uint32_t vstride_vec, ScanPlan &plan);
 void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);
+void scan_ref_build(const HostTree &t, uint32_t vstride, std::vector<ScanRef> &tab);
+void scan_ref_fill(const HostTree &t, uint32_t vstride, ScanRef *tab, int node);
 
 }  // namespace mpgpu
 

@@ -33,6 +33,32 @@ void visit_order(const HostTree &t, std::vector<int32_t> &order)
     }
 }
 
+// the records of all ring slots of `node` (see ScanRef)
+void scan_ref_fill(const HostTree &t, uint32_t vstride, ScanRef *tab, int node)
+{
+    const int n = t.n;
+    const int ns = node <= n ? 1 : 3;
+    for (int sl = 0; sl < ns; sl++) {
+        const int r = 3 * node + sl;
+        const int v = t.vid(r);
+        ScanRef &e = tab[r];
+        e.voff = (int32_t)((uint32_t)v * vstride);
+        e.tip = v << 2 | (node <= n ? 1 : 0);
+        e.c1 = 0; e.c2 = 0;
+        if (node > n) {
+            const int a = 3 * node + (sl + 1) % 3, b = 3 * node + (sl + 2) % 3;
+            e.c1 = t.back(a); e.c2 = t.back(b);
+        }
+    }
+}
+
+void scan_ref_build(const HostTree &t, uint32_t vstride, std::vector<ScanRef> &tab)
+{
+    const int n = t.n;
+    tab.assign((size_t)3 * (2 * n - 1), ScanRef{0, 0, 0, 1});
+    for (int node = 1; node <= 2 * n - 2; node++) scan_ref_fill(t, vstride, tab.data(), node);
+}
+
 namespace {
 
 // Flat per-ref tables of the tree for the enumeration (built once per plan): the two refs
@@ -41,14 +67,20 @@ namespace {
 struct Builder {
     const int n;
     ScanPlan &plan;
-    // per ref, one record (one cache line touch per visited node): back(next(ref)), back(next(next(ref))), view offset, is-tip
-    struct Ref { int32_t c1, c2, voff, tip; };      // tip: bit 0 = the node is a tip, bit 1 = its view is stale (lazy views of the search)
-    std::vector<Ref> ref_;
+    // per ref, one record (one cache line touch per visited node): back(next(ref)), back(next(next(ref))), view offset and
+    // tip = view id << 2 | noted << 1 | is-tip (ScanRef, mpgpu_internal.h).  The table is the caller's (the SPR search keeps
+    // one per context and patches the five nodes a move touches: building it is O(n), most of the host cost of a small batch)
+    // or, without one, built here.
+    typedef ScanRef Ref;
+    std::vector<Ref> own_;
+    Ref *ref_ = nullptr;
     // views of the same data for the callers that index by field
-    struct Field1 { const std::vector<Ref> &r; int32_t operator[](int i) const { return r[i].c1; } } c1{ref_};
-    struct Field2 { const std::vector<Ref> &r; int32_t operator[](int i) const { return r[i].c2; } } c2{ref_};
-    struct FieldT { const std::vector<Ref> &r; bool operator[](int i) const { return (r[i].tip & 1) != 0; } } tip{ref_};
-    bool lazy = false;                   // some views are stale: every view the plan reads is checked (need)
+    struct Field1 { Ref *const *r; int32_t operator[](int i) const { return (*r)[i].c1; } } c1{&ref_};
+    struct Field2 { Ref *const *r; int32_t operator[](int i) const { return (*r)[i].c2; } } c2{&ref_};
+    struct FieldT { Ref *const *r; bool operator[](int i) const { return ((*r)[i].tip & 1) != 0; } } tip{&ref_};
+    const uint8_t *vstale = nullptr;     // some views are stale: every view the plan reads is checked (need)
+    bool lazy = false;
+    std::vector<int32_t> noted;          // refs whose "noted" bit this plan set (cleared again by the destructor)
     int prune_ref = 0, task_index = 0, cand_base = 0;
     // raw cursors into the plan's arrays (sized up front)
     ScanOffs *offs = nullptr; ScanCtl *ctl = nullptr;
@@ -57,26 +89,20 @@ struct Builder {
     // op tree (recorded when the plan may be split into sub-tasks): the ops that expand an op's first / second child
     int32_t *kid_op = nullptr;           // [2 * op], -1 = that child is not expanded
 
-    Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride, const uint8_t *vstale) : n(t.n), plan(pp), lazy(vstale != nullptr)
+    Builder(const HostTree &t, ScanPlan &pp, uint32_t vstride, const uint8_t *vs, ScanRef *table)
+        : n(t.n), plan(pp), vstale(vs), lazy(vs != nullptr)
     {
-        const int nref = 3 * (2 * n - 1);
-        ref_.assign(nref, Ref{0, 0, 0, 1});
-        for (int node = 1; node <= 2 * n - 2; node++) {
-            const int ns = node <= n ? 1 : 3;
-            for (int sl = 0; sl < ns; sl++) {
-                const int r = 3 * node + sl;
-                ref_[r].voff = (int32_t)((uint32_t)t.vid(r) * vstride);
-                if (node > n) {
-                    ref_[r].tip = vstale && vstale[t.vid(r)] ? 2 : 0;
-                    const int a = 3 * node + (sl + 1) % 3, b = 3 * node + (sl + 2) % 3;
-                    ref_[r].c1 = t.back(a); ref_[r].c2 = t.back(b);
-                }
-            }
-        }
+        if (table) ref_ = table;
+        else { scan_ref_build(t, vstride, own_); ref_ = own_.data(); }
     }
+    ~Builder() { for (int32_t r : noted) ref_[r].tip &= ~2; }
     int32_t voff(int ref) const { return ref_[ref].voff; }
     // the plan reads the view behind `ref`: noted when it is stale (once per plan)
-    void need(int ref) { if (ref_[ref].tip & 2) { ref_[ref].tip &= ~2; plan.need_refs.push_back(ref); } }
+    void need(int ref)
+    {
+        int32_t &f = ref_[ref].tip;
+        if (!(f & 2) && vstale[f >> 2]) { f |= 2; noted.push_back(ref); plan.need_refs.push_back(ref); }
+    }
 
     // One expand op for the node whose children (seen from it) are a and b; src = where its up-view comes from.
     // The op's control words are built in registers while the children are walked and stored once.
@@ -195,7 +221,7 @@ struct ScanPlanner::Impl {
     int first, mintrav, maxtrav;
     int split_depth = 0;
     Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const int32_t *ord,
-         int f, int mi, int ma, const uint8_t *vstale) : b(tt, plan, vstride, vstale), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
+         int f, int mi, int ma, const uint8_t *vstale, ScanRef *table) : b(tt, plan, vstride, vstale, table), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
 };
 
 ScanPlanner::ScanPlanner() : impl(nullptr) {}
@@ -203,7 +229,7 @@ ScanPlanner::~ScanPlanner() { delete impl; }
 
 int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int count,
                        int mintrav, int maxtrav_in, uint32_t vstride, ScanPlan &plan, bool host_only, const uint8_t *vstale,
-                       int split_depth)
+                       int split_depth, ScanRef *table)
 {
     delete impl; impl = nullptr;
     plan.tasks.clear(); plan.visit_begin.clear(); plan.visit_ref.clear(); plan.task_vids.clear(); plan.need_refs.clear();
@@ -215,7 +241,7 @@ int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int c
     if (maxtrav > n - 3) maxtrav = n - 3;                       // :2275 (tr->ntips == mxtips during the search)
     if (maxtrav > kMaxTrav) { set_error("maxtrav exceeds the scan kernel's stack depth"); return 1; }   // slots < 0xFE
     if ((uint64_t)(4 * n - 6) * vstride >= 0x7fffffffULL) { set_error("view array too large for 32-bit scan offsets"); return 1; }
-    impl = new Impl(t, plan, vstride, order, first, mintrav, maxtrav, vstale);
+    impl = new Impl(t, plan, vstride, order, first, mintrav, maxtrav, vstale, table);
     Builder &b = impl->b;
     // upper bounds: one side of a visit reaches at most 4 * (2^maxtrav - 1) branches, never more than the tree has
     const size_t per_side = std::min<size_t>((size_t)4 << std::max(maxtrav, 0), (size_t)2 * n);
