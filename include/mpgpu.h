@@ -281,6 +281,9 @@ int mpgpu_sankoff_reps_stats(mpgpu_ctx *ctx, int64_t *tensor_chunks, int64_t *ex
 /* Options: "sankoff_exact" 0/1 (see mpgpu_scan_bounds);
  * "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests);
  * "reps_timing" 0/1 (CUDA events around the largest tensor-kernel launch, read by mpgpu_reps_timing);
+ * "sankoff_u32" 0/1 (-short_off, tools.cpp:2365: the reference's 32-bit Sankoff vectors -- pattern weights are not cut to 16 bits and
+ * the per-segment weighted sums and node scores do not wrap at 2^16; set before mpgpu_set_cost_matrix; the u16 bound on
+ * (ntaxa+1)*(max cost+1) still applies, within it the vectors themselves are the same numbers);
  * "exchange" 1/0 (sharded contexts: 0 skips the exchange step, so every result stays this shard's partial -- for timing the
  * kernels without it). */
 int mpgpu_set_option(mpgpu_ctx *ctx, const char *name, int value);

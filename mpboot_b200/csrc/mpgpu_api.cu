@@ -305,7 +305,7 @@ int submit_stale(Ctx *c, std::vector<Triple> &stale, int nlevels, bool defer, bo
     if (c->sk.on) {
         if (c->wave_pending) { if (int rc = fetch_wave_counts(c)) return rc; MPGPU_CUDA(cudaStreamSynchronize(c->stream)); settle_views(c, false); }
         if (int rc = sk_update_stale(c, stale, nlevels)) return rc;
-        if (incremental) for (const Triple &tr : stale) c->vlen[tr.dst] = c->vcount[tr.dst] & 0xFFFFu;
+        if (incremental) for (const Triple &tr : stale) c->vlen[tr.dst] = c->vcount[tr.dst] & c->sk.sum_mask();
         return 0;
     }
     const int hdr = (nlevels + 3) / 4;
@@ -394,7 +394,7 @@ void settle_views(Ctx *c, bool lengths)
         const Triple *list = c->wave_pin.data() + pw.list_off;
         const uint32_t *wc = wcp + pw.wc_off;
         if (pw.incremental) {
-            if (c->sk.on) for (int i = 0; i < pw.total; i++) { c->vcount[list[i].dst] = wc[i]; c->vlen[list[i].dst] = wc[i] & 0xFFFFu; }
+            if (c->sk.on) for (int i = 0; i < pw.total; i++) { c->vcount[list[i].dst] = wc[i]; c->vlen[list[i].dst] = wc[i] & c->sk.sum_mask(); }
             else for (int i = 0; i < pw.total; i++) {             // sorted by level: children first
                 const Triple &tr = list[i];
                 c->vcount[tr.dst] = wc[i];
@@ -518,7 +518,7 @@ void compute_lengths(Ctx *c)
     const int nviews = 4 * c->n - 6;
     c->vlen.assign(nviews, 0);
     if (c->sk.on) {      // parsimonyScore[node] of the Sankoff kernel: unweighted u16 sum of per-pattern minima (:491, :547), tips 0
-        for (const Triple &tr : c->sched) c->vlen[tr.dst] = c->vcount[tr.dst] & 0xFFFFu;
+        for (const Triple &tr : c->sched) c->vlen[tr.dst] = c->vcount[tr.dst] & c->sk.sum_mask();
         c->lens_valid = true;
         return;
     }

@@ -1001,6 +1001,11 @@ int mpgpu_set_option(mpgpu_ctx *c, const char *name, int value)
         return 0;
     }
     if (!strcmp(name, "sankoff_exact")) { c->sk.exact = value != 0; return 0; }
+    if (!strcmp(name, "sankoff_u32")) {
+        if (c->sk.on) { set_error("sankoff_u32 must be set before mpgpu_set_cost_matrix"); return 1; }
+        c->sk.wide = value != 0;
+        return 0;
+    }
     if (!strcmp(name, "exchange")) { c->exchange_off = value == 0; return 0; }
     if (!strcmp(name, "reps_timing")) { c->reps.timing = value != 0; c->reps.timed_rows = 0; return 0; }
     set_error(std::string("unknown option: ") + name);

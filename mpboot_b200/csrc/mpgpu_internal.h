@@ -180,6 +180,8 @@ struct Sankoff {
     bool on = false;                      // a cost matrix is set: every score is weighted parsimony
     bool exact = false;                   // option "sankoff_exact": perSiteScores mode, no lower-bound early exit (:951)
     bool cost_dirty = true;
+    bool wide = false;                    // option "sankoff_u32" (-short_off): weights and segment sums are 32-bit, no 16-bit wrap
+    uint32_t sum_mask() const { return wide ? 0xFFFFFFFFu : 0xFFFFu; }
     bool asym = false;                    // cost[i][j] != cost[j][i] somewhere: insertion and stepwise scores take the reference's rooted form
     std::vector<uint32_t> cost;           // pllCostMatrix [S][S]
     uint32_t highest = 0;                 // highest_cost = max + 1 (:160)

@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(128, S <= 4 ? 5 : 1) k_sk_scan(const uint4 *__
 
 // ---- per row: total = sum_seg (sum mod 2^16) (:944-948), est = max_{seg < nseg-1} (prefix + lb[seg]) (:951-956) ----
 __global__ void k_sk_finish(const uint32_t *__restrict__ segout, int nseg, const uint32_t *__restrict__ lb, int rows,
-                            uint2 *__restrict__ out)
+                            uint2 *__restrict__ out, uint32_t mask)
 {
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= rows) return;
@@ -659,7 +659,7 @@ __global__ void k_sk_finish(const uint32_t *__restrict__ segout, int nseg, const
     uint32_t total = 0, est = 0;
     for (int base = 0; base < nseg; base += 32) {
         const int s = base + lane;
-        uint32_t v = s < nseg ? segout[(size_t)row * nseg + s] & 0xFFFFu : 0u;
+        uint32_t v = s < nseg ? segout[(size_t)row * nseg + s] & mask : 0u;      // mask: 16 bits (Vec16us lanes, :944-948) or none (-short_off)
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
         if (s < nseg - 1) est = max(est, total + v + lb[s]);
@@ -891,7 +891,7 @@ int sk_build(Ctx *c)
         int j = 0;
         for (int i = 0; i < c->P; i++) {
             if (!c->informative[i]) continue;
-            wflat[j] = j < last_bound ? (uint32_t)(uint16_t)c->weights[i] : 0u;
+            wflat[j] = j < last_bound ? (k.wide ? (uint32_t)c->weights[i] : (uint32_t)(uint16_t)c->weights[i]) : 0u;   // informativePtnWgt is Numeric (:2755)
             present[j] = c->present[j];          // findMstScore(ptn) indexes the alignment directly: informative patterns come first
             j++;
         }
@@ -1004,7 +1004,7 @@ static int sk_finish_rows(Ctx *c, int rows)
 {
     Sankoff &k = c->sk;
     const int blocks = (rows * 32 + 127) / 128;
-    k_sk_finish<<<blocks, 128, 0, c->stream>>>(k.d_segout, k.nseg, k.d_lb, rows, k.d_tot);
+    k_sk_finish<<<blocks, 128, 0, c->stream>>>(k.d_segout, k.nseg, k.d_lb, rows, k.d_tot, k.sum_mask());
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     MPGPU_CUDA(cudaMemcpyAsync(k.h_tot, k.d_tot, (size_t)rows * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));

@@ -224,6 +224,9 @@ MPREF_API int mpref_set_cost_matrix(mpref *h, const unsigned int *cost, const in
     return (int)highest_cost;
 }
 
+/* -short_off (tools.cpp:2365): 32-bit Sankoff vectors and sums (Vec8ui instead of Vec16us); call before mpref_set_cost_matrix */
+MPREF_API void mpref_set_sankoff_short(mpref *h, int on) { h->params.sankoff_short_int = on != 0; }
+
 /* Sankoff parsVect of one node as the engine holds it: u16 [parsimonyLength/16][S][16] (:2725-2733) */
 MPREF_API int mpref_get_sankoff_vect(mpref *h, int node, unsigned short *out)
 {

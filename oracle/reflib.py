@@ -257,6 +257,10 @@ class RefEngine(BootMixin):
         assert c.shape == (self.S, self.S)
         return lib().mpref_set_cost_matrix(self.h, _p(c), _p(seg), len(seg))
 
+    def set_sankoff_short(self, on):
+        """False = -short_off: 32-bit Sankoff vectors and segment sums.  Before set_cost_matrix."""
+        lib().mpref_set_sankoff_short(self.h, 1 if on else 0)
+
     def sankoff_vect(self, node):
         """u16 [parsimonyLength][S] cost vector of one node (de-blocked from [len/16][S][16])."""
         raw = np.zeros(self.W * self.S, dtype=np.uint16)

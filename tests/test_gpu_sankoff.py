@@ -226,6 +226,57 @@ def test_asymmetric_cost_matrix(n, L, dt, seed, hi):
     assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
 
 
+@pytest.mark.parametrize("n,L,dt,seed,scale", [(20, 600, 1, 251, 700), (14, 300, 2, 252, 900), (30, 1500, 1, 253, 70000)])
+def test_short_off_u32_sums(n, L, dt, seed, scale):
+    """-short_off (tools.cpp:2365; option "sankoff_u32"): the reference's 32-bit vectors -- pattern weights are not cut to 16 bits
+    and the per-segment weighted sums do not wrap at 2^16.  Pattern weights scaled up so that every segment sum exceeds 2^16 (and,
+    in the last case, single weights exceed it): tree score, pattern vector, every insertion score of a sweep, whole searches in
+    both modes and a RAS tree against the reference itself (oracle/_ref with sankoff_short_int = false)."""
+    import ctypes as C
+    from oracle import reflib
+    from mpboot_b200.engine import Engine
+    if not reflib.available():
+        pytest.skip("oracle/_ref not built")
+    c = make_case(n, L, dt, seed)
+    w = (c["weights"].astype(np.int64) * scale).astype(np.int32)
+    S = {0: 2, 1: 4, 2: 20, 6: 32}[dt]
+    rng = np.random.default_rng(seed)
+    cost = rng.integers(1, 5, size=(S, S)); cost = np.minimum(cost, cost.T); np.fill_diagonal(cost, 0)
+    ninf = c["n_inf"]
+    seg = np.array([s for s in range(80, ninf, 80)] + [ninf], dtype=np.int32)
+    L_ = reflib.lib()
+    fn = C.cast(L_.mpref_random_double, C.c_void_p).value
+    ref = reflib.RefEngine(c["chars"], w, dt, n_informative=ninf)
+    ref.set_sankoff_short(False)
+    hi = ref.set_cost_matrix(cost.astype(np.uint32), seg)
+    ref.set_ring(c["bn"], c["bs"]); ref.allocate(per_site=True)
+    s0 = ref.evaluate_full(per_site=True)
+    eng = Engine()
+    eng.load_alignment(c["codes"], w, dt)
+    eng.set_option("sankoff_u32", 1)
+    assert eng.set_cost_matrix(cost, seg) == hi
+    eng.set_tree(c["bn"], c["bs"])
+    assert eng.tree_score() == s0
+    assert s0 > 65535 * len(seg) // 2                      # the 16-bit wrap would have changed it
+    order = eng.visit_order()
+    vb, mp, cref, cprune = eng.scan_visits(order, 1, 2 * n - 2, 1, 5)
+    for i in range(1, 2 * n - 1):
+        ref.record(False)
+        ref.rearrange(i, 1, 5, True, s0)
+        assert np.array_equal(ref.saved()[1:], mp[vb[i - 1]: vb[i]].astype(np.int32)), i
+    for exact in (0, 1):
+        eng.set_option("sankoff_exact", exact)
+        L_.mpref_seed_rng(99)
+        ref.set_ring(c["bn"], c["bs"]); ref.allocate(bool(exact))
+        want = ref.optimize_spr(1, 5, bb=bool(exact))
+        wd = L_.mpref_rng_draws()
+        wbn, wbs = ref.get_ring()
+        L_.mpref_seed_rng(99)
+        ret, bn, bs, _ = eng.optimize_spr(c["bn"], c["bs"], fn, 1, 5)
+        assert ret == want and L_.mpref_rng_draws() == wd
+        assert np.array_equal(bn[3:], wbn[3:]) and np.array_equal(bs[3:], wbs[3:])
+
+
 def test_unit_costs_equal_fitch_and_switch_back():
     from mpboot_b200.engine import Engine
     c = make_case(30, 2000, 1, 61)

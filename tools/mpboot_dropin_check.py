@@ -38,6 +38,8 @@ CASES = {
     "cost_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv"]),
     # an asymmetric matrix (obeys the triangle inequality, so ParsTree::initCostMatrix leaves it alone): scores depend on the root
     "costasym_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@asym"]),
+    # -short_off: 32-bit Sankoff vectors and segment sums (tools.cpp:2365)
+    "costu32_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv", "-short_off"]),
 }
 COST_FILES = {"@tstv": "4\n0 2 1 2\n2 0 2 1\n1 2 0 2\n2 1 2 0\n",
               "@asym": "4\n0 3 1 2\n2 0 3 1\n2 2 0 3\n3 2 2 0\n"}
