@@ -195,14 +195,57 @@ static inline int2 kid_pair(const Triple &tr) { return tr.a < tr.b ? make_int2(t
 int compute_views(Ctx *c, bool want_start_edge)
 {
     const int nviews = 4 * c->n - 6;
+    if (c->wave_pending) c->wcount_zeroed = false;      // lists were in flight and are dropped here: their counters are not zero
     c->wave_pending = 0; c->wave_lists.clear(); c->wave_used = 0; c->wc_used = 0; c->wave_fetched = false;
-    c->wcount_zeroed = false;                 // lists may have been in flight: their counters are not known to be zero
     c->vstale.assign(nviews, 0); c->n_stale = 0;
     c->views_stale = false;
     c->start_edge_valid = false;
     build_schedule(c);
     const size_t total = c->sched.size();
     const int nl = c->sched_levels;
+    // One k_fitch_wave launch for the whole schedule when its list fits in shared memory (up to ~3000 taxa) instead of one launch
+    // per dependency level: every search, every refinement replicate and every computeParsimony of the drop-in starts here, and
+    // ~20-60 launches of 3.5 us each were most of it (C2: ~200 us -> ~50 us; 100 x 5000: 137 us per set_tree, 1251 of them in a
+    // -bb 1000 run).  MPGPU_LEVEL_VIEWS=1 keeps the per-level launches.
+    static const bool level_views = getenv("MPGPU_LEVEL_VIEWS") != nullptr;
+    if (!level_views && !c->sk.on && c->reduces() && total > 0 &&
+        wave_smem_bytes(c->S, (nl + 3) / 4 + (int)total) <= 200 * 1024) {
+        std::vector<int32_t> &dl = c->sc_dl;
+        std::vector<Triple> &all = c->sc_stale;
+        dl.assign(nviews, 0);
+        all.clear();
+        c->vcount.assign(nviews, 0);
+        c->view_kids.assign(nviews, make_int2(-1, -1));
+        for (const Triple &tr0 : c->sched) {              // children first; pad = level
+            Triple tr = tr0;
+            const int l = tr.pad;
+            const bool fa = dl[tr.a] != 0, fb = dl[tr.b] != 0;    // b = the operand that is not of this list (a tip) when there is one; a = the one of level l - 1
+            if (!fa && fb) std::swap(tr.a, tr.b);
+            else if (fa && fb && dl[tr.a] != l - 1) std::swap(tr.a, tr.b);
+            dl[tr.dst] = l;
+            all.push_back(tr);
+            c->view_kids[tr.dst] = kid_pair(tr0);
+        }
+        c->dl_dirty = true;
+        c->kids_valid = true;
+        if (int rc = submit_stale(c, all, nl, true, false)) return rc;
+        const bool edge_w = want_start_edge && c->reduces();
+        if (edge_w) {
+            MPGPU_CUDA(cudaMemsetAsync(c->d_scalar, 0, sizeof(uint32_t), c->stream));
+            if (int rc = launch_edge_mismatch(c, c->tree.vid(3), c->tree.vid(c->tree.back(3)), c->d_scalar)) return rc;
+            if (int rc = shard_sum(c, c->d_scalar, 1)) return rc;
+            if (!c->vcount_pin.reserve((size_t)nviews + 1)) { set_error("pinned allocation failed"); return 1; }
+            MPGPU_CUDA(cudaMemcpyAsync(c->vcount_pin.data() + nviews, c->d_scalar, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (c->wave_pending) {                              // (0 when submit_stale fell back: then everything is settled already)
+            if (int rc = fetch_wave_counts(c)) return rc;
+            MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+            settle_views(c, false);
+        } else MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        if (edge_w) { c->start_edge_mis = c->vcount_pin.data()[nviews]; c->start_edge_valid = true; }
+        c->reps.tree_valid = false;
+        return 0;
+    }
     if (int rc = ensure(c->d_triples, c->triples_cap, total)) return rc;
     std::vector<int32_t> start(nl + 2, 0);
     for (const Triple &tr : c->sched) start[tr.pad + 1]++;
