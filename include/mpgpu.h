@@ -335,6 +335,13 @@ typedef struct mpgpu_bb_hooks {
      * pop_worst != 0 <=> the list is full and its last entry is dropped first (:3571).  Returns the rell of the list's
      * last entry after the update (the new boot_threshold when the list was full, :3578). */
     int32_t (*tophit)(void *user, int32_t sample, int32_t tree_index, int32_t rell, int32_t pop_worst);
+    /* policy MPGPU_BB_DISTINCT_ITER only (may be NULL otherwise): replicate `sample` accepted tree `tree_index` with score rell in
+     * iteration cur_it; the host updates boot_trees_parsimony_top[sample] / boot_trees_parsimony_top_iter[sample] as
+     * iqtree.cpp:3624-3669 (nothing if the tree is in the list; else the entry of this iteration is replaced when rell is better;
+     * else appended while the list has fewer than top_n entries; else the worst entry is replaced) and returns the new
+     * boot_threshold[sample]: the smallest rell of the list (:3671-3677), or `threshold` unchanged when the tree was in the list
+     * (the `continue` at :3634). */
+    int32_t (*disthit)(void *user, int32_t sample, int32_t tree_index, int32_t rell, int32_t cur_it, int32_t top_n, int32_t threshold);
 } mpgpu_bb_hooks;
 #define MPGPU_BB_DEFAULT 0     /* iqtree.cpp:3687-3731 */
 #define MPGPU_BB_MULHITS_TOP 2 /* -mulhits -topboot N (store_top_boot_trees, iqtree.cpp:3536-3583): per replicate the N best newly
@@ -342,6 +349,14 @@ typedef struct mpgpu_bb_hooks {
                                 * boot_counts, boot_trees untouched, no tie-break draw */
 #define MPGPU_BB_MULHITS 1     /* params->multiple_hits without -topboot, iqtree.cpp:3498-3531: every tree that ties a
                                 * replicate's best score is kept; no tie-break draw, boot_counts / boot_trees untouched */
+#define MPGPU_BB_DISTINCT_ITER 3 /* -distinct_iter_top_boot K (iqtree.cpp:3587-3685): per replicate up to K trees from distinct
+                                 * iterations; a tree is accepted when rell > boot_threshold, or rell == boot_threshold and
+                                 * random_double() <= K / boot_counts (boot_counts counts the calls with rell >= boot_threshold,
+                                 * reset to 1 by a new best); state->top_n = K, state->cur_it = IQTree::curIt, boot_threshold,
+                                 * boot_logl, boot_counts, boot_trees in/out.  Under this policy the remain-bound skip of the REPS
+                                 * loop (:3433-3445) changes decisions (it compares with boot_logl, acceptance with boot_threshold):
+                                 * it is replayed exactly when the bounds were given with mpgpu_set_remain_bounds.  Fitch scoring,
+                                 * unsharded contexts. */
 typedef struct mpgpu_bb_state {
     int32_t B;
     double *boot_logl;        /* [B] in/out */
@@ -364,10 +379,22 @@ typedef struct mpgpu_bb_state {
     int32_t top_n;                            /* MPGPU_BB_MULHITS_TOP: params->store_top_boot_trees */
     int32_t *top_count;                       /* [B] in/out: boot_trees_parsimony_top[sample].size() */
     int32_t *boot_threshold;                  /* [B] in/out: IQTree::boot_threshold (vector<int>, starts at -INT_MAX, iqtree.cpp:267) */
+    int32_t cur_it;                           /* MPGPU_BB_DISTINCT_ITER: IQTree::curIt of this search */
 } mpgpu_bb_state;
 int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,
                           uint32_t *best, int64_t *n_insertions);
+
+/* boot_samples_pars_remain_bounds (iqtree.cpp:3821-3858, IQTree::pllComputeRellRemainBound): bounds[b][s], s < nseg - 1 = a lower
+ * bound of replicate b's score over the patterns from segment_upper[s] on; per_replicate must be nseg - 1.  After
+ * mpgpu_load_replicates (which drops earlier bounds); NULL clears them.  Only policy MPGPU_BB_DISTINCT_ITER reads them: under the
+ * other policies the skip they allow is decision-neutral and the device scores every replicate anyway. */
+int mpgpu_set_remain_bounds(mpgpu_ctx *ctx, const int32_t *bounds, int per_replicate);
+/* What the skip test of iqtree.cpp:3433-3445 compares with boot_logl, for candidate cand_idx of the last scan batch (-1 = the
+ * current tree) and the replicates samples[0..m): out[i] = max over the segments nseg/4 < s < nseg-1 of (sum of the 16-bit
+ * segment sums up to s + bounds[samples[i]][s]); INT32_MIN when no segment is in that range.  The reference skips the replicate
+ * <=> -(out[i]) < boot_logl - ufboot_epsilon. */
+int mpgpu_reps_prefix_max(mpgpu_ctx *ctx, int32_t cand_idx, const int32_t *samples, int m, int32_t *out);
 
 /* ---- N2: support summarisation, the split table of a weighted collection of trees -----------------------------------
  * Replaces the arithmetic of MTreeSet::convertSplits (mtreeset.cpp:362-440) as IQTree::summarizeBootstrap drives it
@@ -420,6 +447,9 @@ int64_t mpgpu_treels_mulhits(const mpgpu_treels *t, int32_t nsamples, int32_t *s
 /* -mulhits -topboot: boot_trees_parsimony_top as collected through the tophit hook: sizes[nsamples], then (tree_index, rell)
  * pairs in list order, concatenated into flat (2 ints per pair, up to capacity pairs); returns the pair count. */
 int64_t mpgpu_treels_toplists(const mpgpu_treels *t, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity);
+/* -distinct_iter_top_boot: the lists above are then filled by the disthit hook (list order = insertion order); this returns
+ * boot_trees_parsimony_top_iter, the iteration of every entry in the same order (up to capacity ints); returns the count. */
+int64_t mpgpu_treels_topiters(const mpgpu_treels *t, int32_t nsamples, int32_t *flat, int64_t capacity);
 
 #ifdef __cplusplus
 }

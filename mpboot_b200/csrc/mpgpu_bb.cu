@@ -39,7 +39,8 @@ void free_reps(Ctx *c)
 {
     Reps &r = c->reps;
     void *ptrs[] = {r.d_w8, r.d_w16T, r.d_seg_upper, r.d_segmax, r.d_exc_ptn, r.d_exc_group, r.d_rows_site, r.d_rows_ptn, r.d_X, r.d_row_of,
-                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_call_hit, r.d_hit_list, r.d_res_hit, r.d_full};
+                    r.d_row_tasks, r.d_edges, r.d_calls, r.d_res, r.d_thr, r.d_call_hit, r.d_hit_list, r.d_res_hit, r.d_full,
+                    r.d_keep, r.d_keep_list, r.d_tree_ptn, r.d_remain, r.d_blist, r.d_segsum, r.d_pmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (r.ev0) { cudaEventDestroy(r.ev0); cudaEventDestroy(r.ev1); }
     if (r.h_pin) cudaFreeHost(r.h_pin);
@@ -181,6 +182,10 @@ static int refresh_tree_rows(Ctx *c)
     const int upper0 = c->sort_alignment ? c->n_inf : c->P;
     if (int rc = ensure(c->d_ptn, c->ptn_cap, (size_t)(upper0 > 0 ? upper0 : 1))) return rc;
     if (int rc = launch_gather_patterns(c, nbits, upper0)) return rc;
+    if (r.keep_on && r.upper > 0) {                      // the exact skip test reads them after the batch (c->d_ptn is scratch for other calls)
+        if (int rc = ensure(r.d_tree_ptn, r.tree_ptn_cap, (size_t)r.upper)) return rc;
+        MPGPU_CUDA(cudaMemcpyAsync(r.d_tree_ptn, c->d_ptn, (size_t)r.upper * sizeof(uint16_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
     std::vector<int32_t> segmax(nseg);
     bool exact_check = true;
     if (c->shard_count == 1 && (int)r.seg_wmax.size() == nseg) {
@@ -225,7 +230,57 @@ struct RepsOut {
     std::vector<int32_t> dense;                   // concatenated rows [Bpad]
     std::vector<int64_t> dense_off;               // per call: offset into dense, -1 = no replicate can be affected
     std::vector<int32_t> orig;                    // per call: score on original_sample (column Buser), when loaded
+    std::vector<int32_t> keep_slot;               // per call (keep_on): slot of its two bit rows in reps.d_keep, -1 = not kept
 };
+
+// keep_on: the bit rows (edge row, delta row; pattern space) of the calls of this chunk that were read back move to the side buffer
+// before the next chunk overwrites the row buffers
+static int keep_chunk_rows(Ctx *c, int ncalls, int done, RepsOut &out)
+{
+    Reps &r = c->reps;
+    std::vector<int32_t> list;
+    for (int i = 0; i < ncalls; i++) if (out.dense_off[done + i] >= 0) list.push_back(i);
+    const int nl = (int)list.size();
+    if (!nl) return 0;
+    const size_t need = (size_t)(r.keep_used + nl) * 2 * r.Pw;
+    if (need > r.keep_cap || !r.d_keep) {                  // grow, keeping the slots of the batch's earlier chunks
+        uint32_t *nb = nullptr;
+        const size_t want = need + need / 2 + 1024;
+        MPGPU_CUDA(cudaMalloc((void **)&nb, want * sizeof(uint32_t)));
+        if (r.d_keep && r.keep_used) MPGPU_CUDA(cudaMemcpyAsync(nb, r.d_keep, (size_t)r.keep_used * 2 * r.Pw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+        if (r.d_keep) cudaFree(r.d_keep);
+        r.d_keep = nb; r.keep_cap = want;
+    }
+    if (int rc = ensure(r.d_keep_list, r.keep_list_cap, (size_t)nl)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(r.d_keep_list, list.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t *src = c->ptn_identity ? r.d_rows_site : r.d_rows_ptn;
+    const int pitch = c->ptn_identity ? c->Wl : r.Pw;
+    if (int rc = launch_keep_rows(c, src, pitch, r.d_calls, r.d_keep_list, nl, r.d_keep + (size_t)r.keep_used * 2 * r.Pw)) return rc;
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));         // `list` is pageable and goes out of scope
+    for (int i = 0; i < nl; i++) out.keep_slot[done + list[i]] = r.keep_used + i;
+    r.keep_used += nl;
+    return 0;
+}
+
+// out[i] = max over the segments nseg/4 < s < nseg-1 of (prefix of 16-bit segment sums + remain bound) for the kept call in `slot`
+// and replicate blist[i] (INT_MIN when no segment is in range): what the skip test of iqtree.cpp:3433-3445 compares with boot_logl
+static int prefix_max(Ctx *c, int slot, const int32_t *blist, int nl, int32_t *out)
+{
+    Reps &r = c->reps;
+    if (nl == 0) return 0;
+    if (slot < 0 || slot >= r.keep_used) { set_error("internal: the rows of this call were not kept"); return 2; }
+    const int nseg = (int)r.seg_upper.size();
+    if (int rc = ensure(r.d_blist, r.blist_cap, (size_t)nl)) return rc;
+    if (int rc = ensure(r.d_pmax, r.pmax_cap, (size_t)nl)) return rc;
+    if (int rc = ensure(r.d_segsum, r.segsum_cap, (size_t)nl * nseg)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(r.d_blist, blist, (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_prefix_max(c, r.d_tree_ptn, r.d_keep + (size_t)slot * 2 * r.Pw, r.d_remain, r.d_blist, nl, r.d_segsum, r.d_pmax)) return rc;
+    MPGPU_CUDA(cudaMemcpyAsync(out, r.d_pmax, (size_t)nl * 4, cudaMemcpyDeviceToHost, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    r.prefix_calls++; r.prefix_pairs += nl;
+    return 0;
+}
 
 // Read-back of one chunk whose results sit in reps.d_res[ncalls][Bpad] (and hit flags in d_call_hit when thr):
 // the original-frequency column of every call, and only the rows of calls that can change a replicate.
@@ -361,6 +416,8 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     out.dense.clear();
     out.dense_off.assign(m, -1);
     out.orig.assign(r.has_orig ? m : 0, 0);
+    out.keep_slot.assign(r.keep_on ? m : 0, -1);
+    r.keep_used = 0;
     if (m == 0) return 0;
     if (c->sk.on) return sk_reps_run(c, cands, m, thr, out, device_only);
     if (int rc = refresh_tree_rows(c)) return rc;
@@ -447,6 +504,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
         rp_stop(c, 6);
         if (device_only) return 0;
         if (int rc = reps_read_back(c, ncalls, done, thr, out, hit_list)) return rc;
+        if (r.keep_on) { if (int rc = keep_chunk_rows(c, ncalls, done, out)) return rc; }
         rp_stop(c, 7);
         done = k;
     }
@@ -460,6 +518,9 @@ struct BBRun {
     // host screen: replicate b can only be touched by a call with res <= screen[b] = floor(-boot_logl[b] + eps)
     // (rell > boot_logl - eps, rell >= boot_logl and rell == boot_logl all imply it); kept current as boot_logl moves
     std::vector<int32_t> screen;
+    // MPGPU_BB_DISTINCT_ITER: replicates of the call at hand that reach their threshold, and their skip maxima
+    std::vector<int32_t> dist_list, dist_max;
+    int rc = 0;                      // first error of a bb_save (the replay lambdas return nothing)
 };
 
 static inline int32_t bb_screen_of(double boot_logl, double eps)
@@ -544,6 +605,37 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
         }
         if (rell == st->boot_logl[b]) st->boot_counts[b]++;
     };
+    if (ro.dense_off[call] >= 0 && st->policy == MPGPU_BB_DISTINCT_ITER) {          // iqtree.cpp:3587-3685
+        const int32_t *row = ro.dense.data() + ro.dense_off[call];
+        Reps &r = c->reps;
+        std::vector<int32_t> &L = bb->dist_list, &M = bb->dist_max;
+        L.clear();
+        for (int b = 0; b < st->B; b++) if (-(double)row[b] >= (double)st->boot_threshold[b]) L.push_back(b);     // :3588 can fire
+        // the remain-bound skip (:3433-3445, `continue` at :3484) compares with boot_logl, acceptance with boot_threshold <= boot_logl:
+        // decided exactly from the segment prefixes of the call's own pattern vector
+        const bool skip_test = r.remain_loaded && r.seg_upper.size() > 1;
+        if (skip_test && !L.empty()) {
+            M.resize(L.size());
+            if (int rc = prefix_max(c, ro.keep_slot[call], L.data(), (int)L.size(), M.data())) { if (!bb->rc) bb->rc = rc; st->n_reps++; return; }
+        }
+        for (size_t i = 0; i < L.size(); i++) {
+            const int b = L[i];
+            if (skip_test && M[i] != (int32_t)0x80000000 && (double)(-(int64_t)M[i]) < st->boot_logl[b] - eps) continue;
+            const double rell = -(double)row[b];
+            const int32_t thr = st->boot_threshold[b];
+            st->boot_counts[b]++;                                                              // :3588-3590
+            if (rell > (double)thr || hk->random_double(hk->user) <= st->top_n * 1.0 / st->boot_counts[b]) {      // :3592-3594 (else: rell == thr)
+                if (rell > st->boot_logl[b]) st->boot_counts[b] = 1;                           // :3597
+                if (!have) {
+                    have = true;
+                    tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
+                }
+                st->boot_trees[b] = tree_index;                                                // :3621
+                st->boot_logl[b] = std::max(st->boot_logl[b], rell);
+                st->boot_threshold[b] = hk->disthit(hk->user, b, tree_index, (int32_t)rell, st->cur_it, st->top_n, thr);   // :3624-3678
+            }
+        }
+    } else
     if (ro.dense_off[call] >= 0) {                      // else: no replicate of this call reaches its threshold
         const int32_t *row = ro.dense.data() + ro.dense_off[call];
         if (st->policy == MPGPU_BB_MULHITS_TOP) {
@@ -687,6 +779,10 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                     for (int b = 0; b < st->B; b++)
                         thr[b] = st->top_count[b] < st->top_n ? 2147483647
                                : (st->boot_threshold[b] <= -2147483647 ? 2147483647 : -st->boot_threshold[b] - 1);
+                } else if (st->policy == MPGPU_BB_DISTINCT_ITER) {
+                    // :3588 acts on rell >= boot_threshold; a threshold is the minimum of a list whose entries are only ever replaced by
+                    // better ones or joined by entries that reached it: it only rises within a batch
+                    for (int b = 0; b < st->B; b++) thr[b] = st->boot_threshold[b] <= -2147483647 ? 2147483647 : -st->boot_threshold[b];
                 } else
                 for (int b = 0; b < st->B; b++) thr[b] = bb_screen_of(st->boot_logl[b], st->ufboot_epsilon);
                 if (int rc = reps_run(c, pass_cands.data(), (int)pass_cands.size(), thr.data(), ro)) return rc;
@@ -717,6 +813,7 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                         bestParsimony = m; insertNode = cref[j]; removeNode = cprune[j];
                     }
                 }
+                if (bb && bb->rc) return bb->rc;
                 if (bestParsimony == randomMP) bestIterationScoreHits++;          // :3306
                 if (bestParsimony < randomMP) bestIterationScoreHits = 1;
                 if ((bestParsimony < randomMP ||
@@ -980,13 +1077,21 @@ int mpgpu_optimize_spr_bb(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, 
     if (!hooks->random_double || !hooks->push_tree_logl || !hooks->materialize) { set_error("incomplete -bb hooks"); return 1; }
     if (!c->reps.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
     if (state->B != (c->rep_count > 1 ? c->reps.B_total : c->reps.Buser) || !state->boot_logl || !state->boot_counts || !state->boot_trees) { set_error("bad -bb state"); return 1; }
-    if (state->policy != MPGPU_BB_DEFAULT && state->policy != MPGPU_BB_MULHITS && state->policy != MPGPU_BB_MULHITS_TOP) { set_error("unknown -bb policy"); return 1; }
+    if (state->policy != MPGPU_BB_DEFAULT && state->policy != MPGPU_BB_MULHITS && state->policy != MPGPU_BB_MULHITS_TOP &&
+        state->policy != MPGPU_BB_DISTINCT_ITER) { set_error("unknown -bb policy"); return 1; }
+    const bool distinct = state->policy == MPGPU_BB_DISTINCT_ITER;
+    if (distinct) {
+        if (!hooks->disthit || state->top_n < 1 || !state->boot_threshold) { set_error("policy MPGPU_BB_DISTINCT_ITER needs the disthit hook, top_n >= 1 and boot_threshold"); return 1; }
+        if (c->sk.on) { set_error("policy MPGPU_BB_DISTINCT_ITER is not available under -cost"); return 1; }
+        if (c->shard_count > 1 || c->rep_count > 1) { set_error("policy MPGPU_BB_DISTINCT_ITER needs an unsharded context"); return 1; }
+    }
+    if (c->reps.keep_on != distinct) { c->reps.keep_on = distinct; c->reps.tree_valid = false; }
     if (state->policy == MPGPU_BB_MULHITS_TOP && (!hooks->tophit || state->top_n < 1 || !state->top_count || !state->boot_threshold)) {
         set_error("policy MPGPU_BB_MULHITS_TOP needs the tophit hook, top_n >= 1, top_count and boot_threshold"); return 1;
     }
     if (state->policy == MPGPU_BB_MULHITS && !hooks->mulhit) { set_error("policy MPGPU_BB_MULHITS needs the mulhit hook"); return 1; }
     state->n_calls = 0; state->n_reps = 0;
-    BBRun bb{hooks, state, {}};
+    BBRun bb{hooks, state, {}, {}, {}, 0};
     bb.screen.resize((size_t)state->B);
     for (int b = 0; b < state->B; b++) bb.screen[b] = bb_screen_of(state->boot_logl[b], state->ufboot_epsilon);
     return optimize_impl(c, back_node, back_slot, mintrav, maxtrav, hooks->random_double, hooks->user, &bb, best, n_insertions);
@@ -1150,6 +1255,44 @@ int mpgpu_load_replicates2(mpgpu_ctx *c, int B, const uint16_t *boot, int stride
     r.loaded = true;
     r.tree_valid = false;
     return 0;
+}
+
+int mpgpu_set_remain_bounds(mpgpu_ctx *c, const int32_t *bounds, int per_replicate)
+{
+    if (!c) { set_error("null context"); return 1; }
+    Reps &r = c->reps;
+    if (!r.loaded) { set_error("no replicates loaded (mpgpu_load_replicates)"); return 1; }
+    if (c->shard_count > 1 || c->rep_count > 1) { set_error("mpgpu_set_remain_bounds needs an unsharded context"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    if (!bounds) { r.remain_loaded = false; return 0; }
+    const int nseg = (int)r.seg_upper.size();
+    if (per_replicate != nseg - 1) { set_error("remain bounds: need nseg - 1 values per replicate (iqtree.cpp:3842)"); return 1; }
+    r.remain_loaded = false;
+    if (nseg < 2) return 0;                                   // a single segment is never tested (:3433)
+    if (r.d_remain) { cudaFree(r.d_remain); r.d_remain = nullptr; }
+    MPGPU_CUDA(cudaMalloc((void **)&r.d_remain, (size_t)r.Buser * (nseg - 1) * 4));
+    MPGPU_CUDA(cudaMemcpyAsync(r.d_remain, bounds, (size_t)r.Buser * (nseg - 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    MPGPU_CUDA(cudaStreamSynchronize(c->stream));
+    r.remain_loaded = true;
+    return 0;
+}
+
+int mpgpu_reps_prefix_max(mpgpu_ctx *c, int32_t cand_idx, const int32_t *samples, int m, int32_t *out)
+{
+    if (int rc = need_tree(c, true)) return rc;
+    if (!samples || !out || m < 0) { set_error("bad argument"); return 1; }
+    Reps &r = c->reps;
+    if (!r.loaded || !r.remain_loaded) { set_error("mpgpu_reps_prefix_max needs replicates and remain bounds (mpgpu_set_remain_bounds)"); return 1; }
+    if (c->sk.on || c->shard_count > 1 || c->rep_count > 1) { set_error("mpgpu_reps_prefix_max: Fitch scoring on an unsharded context only"); return 1; }
+    for (int i = 0; i < m; i++) if (samples[i] < 0 || samples[i] >= r.Buser) { set_error("replicate index out of range"); return 1; }
+    MPGPU_CUDA(cudaSetDevice(c->device));
+    const bool was = r.keep_on;
+    if (!was) { r.keep_on = true; r.tree_valid = false; }
+    RepsOut ro;
+    int rc = reps_run(c, &cand_idx, 1, nullptr, ro);
+    if (!rc) rc = prefix_max(c, ro.keep_slot[0], samples, m, out);
+    if (!was) { r.keep_on = false; }
+    return rc;
 }
 
 int mpgpu_set_replicate_shards(mpgpu_ctx *c, int rank, int count)

@@ -173,6 +173,18 @@ struct Reps {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int timed_rows = 0, timed_kblocks = 0, timed_splits = 0;
     int reclassifications = 0;            // times a wrap check moved a segment out of the tensor path's bulk group
+    // -distinct_iter_top_boot (MPGPU_BB_DISTINCT_ITER): what the exact remain-bound skip needs after a batch's chunks are gone
+    bool keep_on = false;                 // keep the two bit rows of every call that is read back, and the tree's per-pattern scores
+    uint32_t *d_keep = nullptr; size_t keep_cap = 0;          // [slots][2][Pw]: edge row, delta row (pattern space)
+    int keep_used = 0;                                         // slots in use by the current batch
+    int32_t *d_keep_list = nullptr; size_t keep_list_cap = 0;
+    uint16_t *d_tree_ptn = nullptr; size_t tree_ptn_cap = 0;   // [upper] per-pattern scores of the tree the kept rows belong to
+    int32_t *d_remain = nullptr;                               // [Buser][nseg-1] boot_samples_pars_remain_bounds (mpgpu_set_remain_bounds)
+    bool remain_loaded = false;
+    int32_t *d_blist = nullptr; size_t blist_cap = 0;
+    int32_t *d_segsum = nullptr; size_t segsum_cap = 0;
+    int32_t *d_pmax = nullptr; size_t pmax_cap = 0;
+    int64_t prefix_calls = 0, prefix_pairs = 0;                // statistics
 };
 
 // ---- Sankoff (-cost) state (R11; sankoff.cu) ------------------------------------------------------
@@ -434,6 +446,9 @@ int measure_int8_peak(Ctx *c, int iters, double *tops);
 int launch_reps_tree_row(Ctx *c, int plane_row0, int nbits, int t_row);
 int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int32_t *d_res, const int32_t *d_thr, int32_t *d_call_hit);
 int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, int nlist, int32_t *d_out);
+int launch_keep_rows(Ctx *c, const uint32_t *d_src, int pitch, const int2 *d_calls, const int32_t *d_list, int nl, uint32_t *d_dst);
+int launch_prefix_max(Ctx *c, const uint16_t *d_tree_ptn, const uint32_t *d_rows2, const int32_t *d_remain, const int32_t *d_blist, int nl,
+                      int32_t *d_segsum, int32_t *d_out);
 
 // ---- host SPR logic (spr_host.cpp) ---------------------------------------------------------
 void visit_order(const HostTree &t, std::vector<int32_t> &order);

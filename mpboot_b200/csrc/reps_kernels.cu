@@ -1005,4 +1005,110 @@ int launch_gather_res_rows(Ctx *c, const int32_t *d_res, const int32_t *d_list, 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// -distinct_iter_top_boot (iqtree.cpp:3587-3685).  Under that policy a replicate is accepted against boot_threshold
+// (the worst of its top list) while the remain-bound skip of the REPS loop (:3433-3445) compares against boot_logl
+// (its best), so the skip changes decisions and has to be decided exactly:
+//     skipped(call, b)  <=>  exists s, nseg/4 < s < nseg-1 :  -(prefix_s + remain[b][s]) < boot_logl[b] - eps,
+//     prefix_s = sum_{j <= s} ( sum_{ptn in segment j} c[ptn] * w_b[ptn]  mod 2^16 )
+//  <=>  -(max_s (prefix_s + remain[b][s])) < boot_logl[b] - eps.
+// The maximum does not depend on the bookkeeping state, so the device computes it for the (call, replicate) pairs the
+// replay asks for: c = c_T - mis + delta from the tree's per-pattern scores and the call's two kept bit rows.
+// ------------------------------------------------------------------------------------------
+// rows (edge row, delta row) of the calls list[0..nl) -> dst[i][2][Pw]; a call without rows (the current tree) keeps zeros
+__global__ void __launch_bounds__(256) k_keep_rows(const uint32_t *__restrict__ src, int pitch, const int2 *__restrict__ calls,
+                                                   const int32_t *__restrict__ list, int Pw, uint32_t *__restrict__ dst)
+{
+    const int i = blockIdx.y;
+    const int2 cd = calls[list[i]];
+    uint32_t *d = dst + (size_t)i * 2 * Pw;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < Pw; w += gridDim.x * blockDim.x) {
+        d[w] = cd.x >= 0 ? __ldg(src + (size_t)cd.x * pitch + w) : 0u;
+        d[Pw + w] = cd.y >= 0 ? __ldg(src + (size_t)cd.y * pitch + w) : 0u;
+    }
+}
+
+int launch_keep_rows(Ctx *c, const uint32_t *d_src, int pitch, const int2 *d_calls, const int32_t *d_list, int nl, uint32_t *d_dst)
+{
+    Reps &r = c->reps;
+    for (int done = 0; done < nl; done += 65535) {
+        const int chunk = nl - done < 65535 ? nl - done : 65535;
+        dim3 grid((r.Pw + 255) / 256 < 8 ? (r.Pw + 255) / 256 : 8, chunk);
+        k_keep_rows<<<grid, 256, 0, c->stream>>>(d_src, pitch, d_calls, d_list + done, r.Pw, d_dst + (size_t)done * 2 * r.Pw);
+        c->launches++;
+        MPGPU_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// segsum[e][s] = ( sum_{ptn in segment s} (c_T[ptn] - mis[ptn] + delta[ptn]) * w[blist[e]][ptn] ) mod 2^16.
+// lane = list entry (consecutive replicates of a dense list read w16T coalesced), the warps of the grid split the segments;
+// the candidate's score of a pattern is uniform over the warp.
+__global__ void __launch_bounds__(256) k_seg_sums(const uint16_t *__restrict__ ptn_pars, const uint32_t *__restrict__ rows2, int Pw,
+                                                  const uint16_t *__restrict__ w16T, int Bpad, const int32_t *__restrict__ seg_upper,
+                                                  int nseg, int upper, const int32_t *__restrict__ blist, int nl, int32_t *__restrict__ segsum)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 32 + lane;
+    const int b = e < nl ? blist[e] : -1;
+    const int nwarps = gridDim.y * (blockDim.x >> 5);
+    for (int s = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nseg; s += nwarps) {
+        const int lo = s ? __ldg(seg_upper + s - 1) : 0;
+        int hi = __ldg(seg_upper + s);
+        if (hi > upper) hi = upper;
+        uint32_t acc = 0;
+        for (int p = lo; p < hi; p++) {
+            const uint32_t mis = (__ldg(rows2 + (p >> 5)) >> (p & 31)) & 1u, dlt = (__ldg(rows2 + Pw + (p >> 5)) >> (p & 31)) & 1u;
+            const uint32_t cand = (uint32_t)__ldg(ptn_pars + p) - mis + dlt;
+            if (b >= 0) acc += cand * (uint32_t)__ldg(w16T + (size_t)p * Bpad + b);      // mod 2^32 keeps the low 16 bits exact
+        }
+        if (b >= 0) segsum[(size_t)e * nseg + s] = (int32_t)(acc & 0xFFFFu);
+    }
+}
+
+// out[e] = max over nseg/4 < s < nseg-1 of (sum_{j<=s} segsum[e][j] + remain[blist[e]][s]); INT_MIN when no segment is in range.
+// One warp per entry: 32 segments per step, warp scan with a carry.
+__global__ void __launch_bounds__(256) k_prefix_max(const int32_t *__restrict__ segsum, int nseg, const int32_t *__restrict__ remain,
+                                                    const int32_t *__restrict__ blist, int nl, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= nl) return;
+    const int b = blist[e];
+    int carry = 0, best = (int)0x80000000;
+    for (int s0 = 0; s0 < nseg - 1; s0 += 32) {
+        const int s = s0 + lane;
+        int v = s < nseg ? segsum[(size_t)e * nseg + s] : 0;
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+        const int prefix = carry + v;
+        if (s > nseg / 4 && s < nseg - 1) {
+            const int tot = prefix + __ldg(remain + (size_t)b * (nseg - 1) + s);
+            if (tot > best) best = tot;
+        }
+        carry = __shfl_sync(0xffffffffu, prefix, 31);
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    if (lane == 0) out[e] = best;
+}
+
+int launch_prefix_max(Ctx *c, const uint16_t *d_tree_ptn, const uint32_t *d_rows2, const int32_t *d_remain, const int32_t *d_blist, int nl,
+                      int32_t *d_segsum, int32_t *d_out)
+{
+    Reps &r = c->reps;
+    const int nseg = (int)r.seg_upper.size();
+    if (nl == 0) return 0;
+    const int gx = (nl + 31) / 32;
+    int gy = (nseg + 7) / 8;                                   // 8 warps per block, one segment per warp and round
+    const int want = (148 * 8 + gx - 1) / gx;                  // enough blocks for every SM when the list is short
+    if (gy > want) gy = want;
+    if (gy < 1) gy = 1;
+    k_seg_sums<<<dim3(gx, gy), 256, 0, c->stream>>>(d_tree_ptn, d_rows2, r.Pw, r.d_w16T, r.Bpad, r.d_seg_upper, nseg, r.upper, d_blist, nl, d_segsum);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    k_prefix_max<<<(nl + 7) / 8, 256, 0, c->stream>>>(d_segsum, nseg, d_remain, d_blist, nl, d_out);
+    c->launches++;
+    MPGPU_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace mpgpu

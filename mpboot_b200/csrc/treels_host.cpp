@@ -7,6 +7,7 @@
 // reference uses the sorted-taxa newick string; both identify the topology).
 #include "mpgpu_internal.h"
 
+#include <algorithm>
 #include <cstring>
 #include <set>
 #include <unordered_map>
@@ -17,7 +18,8 @@ struct mpgpu_treels {
     std::unordered_map<uint64_t, int32_t> index;           // treels
     std::vector<int64_t> mats;                             // 4 per materialised tree: remove_ref, insert_ref, tree_index, fingerprint
     std::vector<std::set<int32_t>> mulhits;                // boot_trees_parsimony (-mulhits)
-    std::vector<std::vector<std::pair<int32_t, int32_t>>> top;   // boot_trees_parsimony_top (-mulhits -topboot)
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> top;   // boot_trees_parsimony_top (-mulhits -topboot, -distinct_iter_top_boot)
+    std::vector<std::vector<int32_t>> top_iter;            // boot_trees_parsimony_top_iter (-distinct_iter_top_boot)
     mpgpu_rng_fn rng = nullptr; void *rng_user = nullptr;
 };
 
@@ -101,6 +103,34 @@ int32_t hook_tophit(void *user, int32_t sample, int32_t tree_index, int32_t rell
     return t.back().second;
 }
 
+// -distinct_iter_top_boot: iqtree.cpp:3624-3677
+int32_t hook_disthit(void *user, int32_t sample, int32_t tree_index, int32_t rell, int32_t cur_it, int32_t top_n, int32_t threshold)
+{
+    mpgpu_treels *h = (mpgpu_treels *)user;
+    if ((size_t)sample >= h->top.size()) h->top.resize((size_t)sample + 1);
+    if ((size_t)sample >= h->top_iter.size()) h->top_iter.resize((size_t)sample + 1);
+    std::vector<std::pair<int32_t, int32_t>> &top = h->top[sample];
+    std::vector<int32_t> &iter = h->top_iter[sample];
+    const int t = std::min((int)top_n, (int)iter.size());
+    int c;
+    for (c = 0; c < t; c++) if (top[c].first == tree_index) return threshold;          // the tree is in the list: nothing (:3627-3634)
+    for (c = 0; c < t; c++)                                                            // this iteration has an entry: keep the better (:3637-3645)
+        if (iter[c] == cur_it) {
+            if (rell > top[c].second) { top[c].second = rell; top[c].first = tree_index; }
+            break;
+        }
+    if (c == t && t < top_n) { iter.push_back(cur_it); top.push_back(std::make_pair(tree_index, rell)); }   // :3648-3651
+    else if (c == t && t == top_n) {                                                   // full: the worst entry goes (:3654-3668)
+        int worst = 0;
+        for (int d = 1; d < t; d++) if (top[d].second < top[worst].second) worst = d;
+        top[worst] = std::make_pair(tree_index, rell);
+        iter[worst] = cur_it;
+    }
+    int32_t thr = top[0].second;                                                       // :3671-3677
+    for (size_t d = 1; d < top.size(); d++) if (top[d].second < thr) thr = top[d].second;
+    return thr;
+}
+
 }  // namespace
 
 extern "C" {
@@ -137,6 +167,17 @@ void mpgpu_treels_hooks(mpgpu_treels *h, mpgpu_rng_fn rng, void *rng_user, mpgpu
     out->materialize = hook_materialize;
     out->mulhit = hook_mulhit;
     out->tophit = hook_tophit;
+    out->disthit = hook_disthit;
+}
+// boot_trees_parsimony_top_iter: the iteration of every entry mpgpu_treels_toplists reports, in the same order
+int64_t mpgpu_treels_topiters(const mpgpu_treels *h, int32_t nsamples, int32_t *flat, int64_t capacity)
+{
+    int64_t tot = 0;
+    for (int32_t s = 0; s < nsamples; s++) {
+        if (!h || (size_t)s >= h->top_iter.size()) continue;
+        for (int32_t v : h->top_iter[s]) { if (flat && tot < capacity) flat[tot] = v; tot++; }
+    }
+    return tot;
 }
 int64_t mpgpu_treels_toplists(const mpgpu_treels *h, int32_t nsamples, int32_t *sizes, int32_t *flat, int64_t capacity)
 {

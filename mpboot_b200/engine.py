@@ -98,6 +98,10 @@ def lib():
     L.mpgpu_treels_mulhits.argtypes = [vp, i32, vp, vp, i64]
     L.mpgpu_treels_toplists.restype = i64
     L.mpgpu_treels_toplists.argtypes = [vp, i32, vp, vp, i64]
+    L.mpgpu_treels_topiters.restype = i64
+    L.mpgpu_treels_topiters.argtypes = [vp, i32, vp, i64]
+    L.mpgpu_set_remain_bounds.argtypes = [vp, vp, C.c_int]
+    L.mpgpu_reps_prefix_max.argtypes = [vp, i32, vp, C.c_int, vp]
     _lib = L
     return L
 
@@ -109,7 +113,7 @@ def _p(a):
 class BBHooks(C.Structure):
     """mpgpu_bb_hooks (include/mpgpu.h)"""
     _fields_ = [("user", C.c_void_p), ("random_double", C.c_void_p), ("push_tree_logl", C.c_void_p),
-                ("materialize", C.c_void_p), ("mulhit", C.c_void_p), ("tophit", C.c_void_p)]
+                ("materialize", C.c_void_p), ("mulhit", C.c_void_p), ("tophit", C.c_void_p), ("disthit", C.c_void_p)]
 
 
 class BBState(C.Structure):
@@ -117,7 +121,8 @@ class BBState(C.Structure):
     _fields_ = [("B", C.c_int32), ("boot_logl", C.c_void_p), ("boot_counts", C.c_void_p), ("boot_trees", C.c_void_p),
                 ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64),
                 ("ratchet", C.c_int32), ("ratchet_pattern_pars", C.c_void_p), ("ratchet_last_score", C.c_int32),
-                ("policy", C.c_int32), ("top_n", C.c_int32), ("top_count", C.c_void_p), ("boot_threshold", C.c_void_p)]
+                ("policy", C.c_int32), ("top_n", C.c_int32), ("top_count", C.c_void_p), ("boot_threshold", C.c_void_p),
+                ("cur_it", C.c_int32)]
 
 
 class HostRng:
@@ -171,6 +176,13 @@ class Treels:
         flat = np.zeros((max(tot, 1), 2), dtype=np.int32)
         self.L.mpgpu_treels_toplists(self.h, nsamples, _p(sizes), _p(flat), tot)
         return sizes, flat[:tot]
+
+    def topiters(self, nsamples):
+        """boot_trees_parsimony_top_iter (-distinct_iter_top_boot), in the order of toplists' pairs"""
+        tot = self.L.mpgpu_treels_topiters(self.h, nsamples, None, 0)
+        flat = np.zeros(max(tot, 1), dtype=np.int32)
+        self.L.mpgpu_treels_topiters(self.h, nsamples, _p(flat), tot)
+        return flat[:tot]
 
     def materialized(self):
         k = self.L.mpgpu_treels_num_materialized(self.h)
@@ -496,15 +508,36 @@ class Engine:
         self._ck(self.L.mpgpu_reps_candidates_device(self.h, _p(idx), len(idx), C.byref(ptr), C.byref(pitch)))
         return ptr.value, pitch.value
 
+    def set_remain_bounds(self, bounds):
+        """boot_samples_pars_remain_bounds [B][nseg-1] (IQTree::pllComputeRellRemainBound) or None"""
+        if bounds is None:
+            self._ck(self.L.mpgpu_set_remain_bounds(self.h, None, 0))
+            return
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        assert b.ndim == 2 and b.shape[0] == self.B
+        self._ck(self.L.mpgpu_set_remain_bounds(self.h, _p(b), b.shape[1]))
+
+    def reps_prefix_max(self, cand_idx, samples):
+        """max over the tested segments of (prefix of 16-bit segment sums + remain bound) for one candidate of the last scan
+        batch (-1 = the current tree) and the listed replicates: the left side of the skip test of iqtree.cpp:3433-3445"""
+        sm = np.ascontiguousarray(samples, dtype=np.int32)
+        out = np.zeros(len(sm), dtype=np.int32)
+        self._ck(self.L.mpgpu_reps_prefix_max(self.h, int(cand_idx), _p(sm), len(sm), _p(out)))
+        return out
+
     def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
-                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None, mulhits=False, topboot=0):
+                        mintrav=1, maxtrav=6, ratchet_pattern_pars=None, mulhits=False, topboot=0, distinct=0, cur_it=1,
+                        boot_threshold=None):
         """pllOptimizeSprParsimony + saveCurrentTree (default policy).  hooks: BBHooks (e.g.
         Treels.hooks(rng)); boot_* arrays are updated in place.  Returns (startMP, back_node,
         back_slot, insertions scored, saveCurrentTree calls, REPS vectors used)."""
         bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
         assert boot_logl.dtype == np.float64 and boot_counts.dtype == np.int32 and boot_trees.dtype == np.int32
         st = BBState(len(boot_logl), boot_logl.ctypes.data, boot_counts.ctypes.data, boot_trees.ctypes.data,
-                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0, 0, None, None)
+                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0, 0, None, None, int(cur_it))
+        if distinct:                                    # -distinct_iter_top_boot K: boot_threshold [B] int32 is the caller's, in/out
+            assert boot_threshold is not None and boot_threshold.dtype == np.int32 and len(boot_threshold) == len(boot_logl)
+            st.policy = 3; st.top_n = int(distinct); st.boot_threshold = boot_threshold.ctypes.data
         if topboot:                                     # -mulhits -topboot N
             self._top_count = np.zeros(len(boot_logl), dtype=np.int32)
             self._boot_threshold = np.full(len(boot_logl), -(2 ** 31 - 1), dtype=np.int32)

@@ -37,6 +37,8 @@ void mporacle_boot_set_mulhits(mporacle *o, int on);
 int  mporacle_boot_mulhits(mporacle *o, int *sizes, int *flat, int cap);
 void mporacle_boot_set_topboot(mporacle *o, int n);
 int  mporacle_boot_toplists(mporacle *o, int *sizes, int *thresholds, int *flat, int cap);
+void mporacle_boot_set_distinct(mporacle *o, int k, int cur_it);   /* -distinct_iter_top_boot k, iqtree.cpp:3587-3685 */
+int  mporacle_boot_topiters(mporacle *o, int *flat, int cap);
 /* Sankoff (-cost) */
 int  mporacle_set_cost_matrix(mporacle *o, const unsigned *cost, const int *segment_upper, int nseg);
 int  mporacle_get_sankoff_vect(mporacle *o, int node, uint16_t *out);

@@ -571,6 +571,9 @@ struct BootSim {
     int store_top_boot_trees;                                 /* params->store_top_boot_trees (-mulhits -topboot N), :3536-3583 */
     std::vector<std::vector<std::pair<int, int> > > boot_trees_parsimony_top;   /* (tree_index, rell), decreasing */
     std::vector<int> boot_threshold;
+    int distinct_iter_top_boot;                               /* params->distinct_iter_top_boot (-distinct_iter_top_boot K), :3587-3685 */
+    int curIt;                                                /* IQTree::curIt of the search */
+    std::vector<std::vector<int> > boot_trees_parsimony_top_iter;
     int B, stride, nseg;
     std::vector<unsigned short *> boot_samples_pars;          /* aligned, P+16, zero padded (:220-233) */
     std::vector<int> segment_upper;
@@ -654,6 +657,7 @@ MPREF_API void mpref_boot_init(mpref *h, int B, const unsigned short *boot, int 
     b->multiple_hits = false; b->boot_trees_parsimony.assign(B, std::set<int>());
     b->store_top_boot_trees = 0; b->boot_trees_parsimony_top.assign(B, std::vector<std::pair<int, int> >());
     b->boot_threshold.assign(B, -INT_MAX);                    /* iqtree.cpp:267 */
+    b->distinct_iter_top_boot = 0; b->curIt = 1;
     h->boot = b;
 }
 
@@ -670,6 +674,25 @@ MPREF_API void mpref_boot_set_ratchet(mpref *h, const unsigned short *original_s
 
 MPREF_API void mpref_boot_set_mulhits(mpref *h, int on) { h->boot->multiple_hits = on != 0; }
 MPREF_API void mpref_boot_set_topboot(mpref *h, int n) { h->boot->multiple_hits = n > 0 || h->boot->multiple_hits; h->boot->store_top_boot_trees = n; }
+MPREF_API void mpref_boot_set_distinct(mpref *h, int k, int cur_it)
+{
+    BootSim *b = h->boot;
+    if (b->distinct_iter_top_boot != k) {                     /* iqtree.cpp:270-277 */
+        b->distinct_iter_top_boot = k;
+        b->boot_trees_parsimony_top.assign(b->B, std::vector<std::pair<int, int> >());
+        b->boot_trees_parsimony_top_iter.assign(b->B, std::vector<int>());
+        b->boot_threshold.assign(b->B, -INT_MAX);
+    }
+    b->curIt = cur_it;
+}
+MPREF_API int mpref_boot_topiters(mpref *h, int *flat, int cap)
+{
+    BootSim *b = h->boot;
+    int tot = 0;
+    for (size_t s = 0; s < b->boot_trees_parsimony_top_iter.size(); s++)
+        for (size_t k = 0; k < b->boot_trees_parsimony_top_iter[s].size(); k++) { if (tot < cap) flat[tot] = b->boot_trees_parsimony_top_iter[s][k]; tot++; }
+    return tot;
+}
 /* boot_trees_parsimony_top: sizes[B], thresholds[B], then (tree_index, rell) pairs in list order, concatenated; returns the pair count */
 MPREF_API int mpref_boot_toplists(mpref *h, int *sizes, int *thresholds, int *flat, int cap)
 {
@@ -812,6 +835,51 @@ static void boot_save_current_tree(mpref *h, double cur_logl)
                     b->boot_trees_parsimony[sample].insert(tree_index);
             }
             continue;                                                                      /* neither :3587 nor :3687 applies */
+        }
+        if (b->distinct_iter_top_boot >= 1) {                                              /* :3587-3685 (!multiple_hits) */
+            const int K = b->distinct_iter_top_boot;
+            std::vector<std::pair<int, int> > &top = b->boot_trees_parsimony_top[sample];
+            std::vector<int> &top_iter = b->boot_trees_parsimony_top_iter[sample];
+            if (rell >= b->boot_threshold[sample]) b->boot_counts[sample]++;
+            if (rell > b->boot_threshold[sample]
+                || (rell == b->boot_threshold[sample] && random_double() <= (K * 1.0 / (b->boot_counts[sample])))) {
+                if (rell > b->boot_logl[sample]) b->boot_counts[sample] = 1;
+                if (!have_str) {
+                    have_str = true;
+                    unsigned long long fp = mpref_tree_fingerprint(h);
+                    std::map<unsigned long long, int>::iterator it = b->treels.find(fp);
+                    if (it != b->treels.end()) tree_index = it->second;
+                    else { tree_index = (int)b->treels_logl.size() - 1; b->treels[fp] = tree_index; }
+                    long long m[5] = { call, 0, 0, tree_index, (long long)fp };
+                    b->mat.insert(b->mat.end(), m, m + 5);
+                }
+                b->boot_trees[sample] = tree_index;
+                b->boot_logl[sample] = std::max(b->boot_logl[sample], rell);
+                int t = std::min(K, (int)top_iter.size());
+                int c;
+                bool tree_exists = false;
+                for (c = 0; t > 0 && c < t; c++) if (top[c].first == tree_index) { tree_exists = true; break; }
+                if (tree_exists) continue;
+                for (c = 0; t > 0 && c < t; c++) {                                         /* the iteration's representative */
+                    if (top_iter[c] == b->curIt) {
+                        if (rell > top[c].second) { top[c].second = rell; top[c].first = tree_index; }
+                        break;
+                    }
+                }
+                if (c == t & t < K) {                                                      /* room left: add */
+                    top_iter.push_back(b->curIt);
+                    top.push_back(std::make_pair(tree_index, rell));
+                }
+                if (c == t & t == K) {                                                     /* full: replace the worst */
+                    int worst_id = 0;
+                    int worst_score = top[worst_id].second;
+                    for (int d = 1; d < t; d++) if (top[d].second < worst_score) { worst_score = top[d].second; worst_id = d; }
+                    top[worst_id].first = tree_index; top[worst_id].second = rell; top_iter[worst_id] = b->curIt;
+                }
+                b->boot_threshold[sample] = top[0].second;
+                for (size_t d = 1; d < top.size(); d++) if (top[d].second < b->boot_threshold[sample]) b->boot_threshold[sample] = top[d].second;
+            }
+            continue;
         }
         if (rell > b->boot_logl[sample] + b->eps
             || (rell > b->boot_logl[sample] - b->eps && random_double() <= 1.0 / (b->boot_counts[sample] + 1))) {   /* :3689 */

@@ -81,6 +81,8 @@ def _boot_protos(L, pre):
     getattr(L, pre + "_boot_mulhits").argtypes = [vp, vp, vp, i]
     getattr(L, pre + "_boot_set_topboot").argtypes = [vp, i]
     getattr(L, pre + "_boot_toplists").argtypes = [vp, vp, vp, vp, i]
+    getattr(L, pre + "_boot_set_distinct").argtypes = [vp, i, i]
+    getattr(L, pre + "_boot_topiters").argtypes = [vp, vp, i]
     getattr(L, pre + "_boot_set_ratchet").argtypes = [vp, vp, vp]
     getattr(L, pre + "_boot_set_state").argtypes = [vp, vp, vp, vp]
     getattr(L, pre + "_boot_get_state").argtypes = [vp, vp, vp, vp]
@@ -130,6 +132,18 @@ class BootMixin:
     def boot_set_topboot(self, n):
         """params->store_top_boot_trees with -mulhits (iqtree.cpp:3536-3583)"""
         self._f("_boot_set_topboot")(self.h, int(n))
+
+    def boot_set_distinct(self, k, cur_it):
+        """params->distinct_iter_top_boot = k (iqtree.cpp:3587-3685) for the search to come in iteration cur_it (IQTree::curIt);
+        the lists and thresholds persist across calls with the same k"""
+        self._f("_boot_set_distinct")(self.h, int(k), int(cur_it))
+
+    def boot_topiters(self):
+        """boot_trees_parsimony_top_iter, in the order of boot_toplists' pairs"""
+        tot = self._f("_boot_topiters")(self.h, None, 0)
+        flat = np.zeros(max(tot, 1), dtype=np.int32)
+        self._f("_boot_topiters")(self.h, _p(flat), tot)
+        return flat[:tot]
 
     def boot_toplists(self):
         """boot_trees_parsimony_top: (sizes[B], boot_threshold[B], (tree_index, rell) pairs in list order, concatenated)"""

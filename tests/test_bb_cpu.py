@@ -157,6 +157,60 @@ def test_port_bb_topboot_equals_reference(n, L, dt, seed, B, mu, N):
     same(x, run_bb(r, c, boot, seg, cutoff, ras, True, topboot=N))
 
 
+def run_bb_distinct(eng, c, boot, seg, bound, is_ref, K, iters=3, seed=2024, mt=6, cutoff=0.0):
+    """-distinct_iter_top_boot K over several iterations (IQTree::curIt = 1, 2, ...): one bookkeeping state, every iteration an SPR
+    search from another random tree, as doTreeSearch drives pllOptimizeSprParsimony once per iteration"""
+    from mpboot_b200 import synth
+    eng.set_cost_matrix(None, None)
+    eng.set_weights(c["weights"])
+    eng.set_ring(c["bn"], c["bs"])
+    eng.allocate(per_site=True)
+    eng.boot_init(boot, seg, cutoff, 0.5, bound)
+    (reflib.lib().mpref_seed_rng if is_ref else portlib.seed_rng)(seed)
+    rets = []
+    for it in range(1, iters + 1):
+        bn, bs = (c["bn"], c["bs"]) if it == 1 else synth.random_tree_rings(c["n"], np.random.default_rng(5000 + it))
+        eng.set_ring(bn, bs)
+        eng.allocate(per_site=True)
+        eng.boot_set_distinct(K, it)
+        eng.record(False)
+        rets.append(eng.optimize_spr(1, mt, bb=True))
+    draws = reflib.lib().mpref_rng_draws() if is_ref else portlib.rng_draws()
+    return dict(ret=rets, draws=draws, ring=eng.get_ring(), state=eng.boot_state(), counters=eng.boot_counters(),
+                treels=eng.boot_treels(), mats=eng.boot_mats(), toplists=eng.boot_toplists(), topiters=eng.boot_topiters())
+
+
+def same_distinct(a, b):
+    assert a["ret"] == b["ret"] and a["draws"] == b["draws"]
+    assert all(np.array_equal(x, y) for x, y in zip(a["toplists"], b["toplists"])) and np.array_equal(a["topiters"], b["topiters"])
+    assert all(np.array_equal(x, y) for x, y in zip(a["ring"], b["ring"]))
+    assert all(np.array_equal(x, y) for x, y in zip(a["state"], b["state"]))
+    assert a["counters"] == b["counters"] and a["counters"][4] == 0
+    assert np.array_equal(a["treels"], b["treels"])
+    assert np.array_equal(a["mats"][:, [0, 3, 4]], b["mats"][:, [0, 3, 4]])
+
+
+DISTINCT_CASES = [(12, 300, 1, 7, 50, 0.05), (24, 400, 2, 5, 40, 0.05), (30, 800, 1, 21, 64, 0.01)]
+
+
+@needs_ref
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", DISTINCT_CASES)
+@pytest.mark.parametrize("K", [1, 3])
+def test_port_bb_distinct_iter_equals_reference(n, L, dt, seed, B, mu, K):
+    """-distinct_iter_top_boot K (iqtree.cpp:3587-3685): per replicate up to K trees from distinct iterations, accepted against
+    boot_threshold; with the remain bounds the skip test (against boot_logl) changes decisions, so it is compared too."""
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    r = reflib.RefEngine(c["chars"], c["weights"], dt, n_informative=c["n_inf"])
+    a = run_bb_distinct(o, c, boot, seg, None, False, K)
+    same_distinct(a, run_bb_distinct(r, c, boot, seg, None, True, K))
+    assert a["toplists"][0].max() == min(K, 2) and a["topiters"].max() > 1     # lists of several entries, entries of later iterations
+    x = run_bb_distinct(o, c, boot, seg, bound, False, K)
+    same_distinct(x, run_bb_distinct(r, c, boot, seg, ras, True, K))
+    assert x["counters"][3] > 0                                          # replicates were skipped ...
+    if K == 3 and n == 24:                                               # ... and that is not decision-neutral under this policy
+        assert not all(np.array_equal(p, q) for p, q in zip(x["state"], a["state"]))
+
+
 def mulhits_golden_case(g, k):
     n, L, dt, seed, B, mu = [x for x in MULHITS_CASES[k]]
     c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)

@@ -292,6 +292,97 @@ def test_bb_topboot_matches_golden_and_oracle(k):
     assert np.array_equal(r["mats"][:, :2], w["mats"][:, 1:3])
 
 
+# ---- -distinct_iter_top_boot (policy MPGPU_BB_DISTINCT_ITER, iqtree.cpp:3587-3685) --------------------------------------------
+def _remain_bounds(boot, seg, bound, upper):
+    """boot_samples_pars_remain_bounds (IQTree::pllComputeRellRemainBound, iqtree.cpp:3841-3856) from the per-pattern lower bounds"""
+    w = boot[:, :upper].astype(np.int64) * bound[:upper].astype(np.int64)
+    return np.stack([w[:, seg[s]:].sum(axis=1) for s in range(len(seg) - 1)], axis=1).astype(np.int32)
+
+
+def _prefix_max_numpy(ptn, boot, seg, remain):
+    """max over nseg/4 < s < nseg-1 of (sum of the 16-bit segment sums up to s + remain[b][s]), the loop at iqtree.cpp:3424-3445"""
+    nseg = len(seg)
+    res = np.zeros(boot.shape[0], dtype=np.int64)
+    best = np.full(boot.shape[0], -(2 ** 31), dtype=np.int64)
+    lo = 0
+    for s in range(nseg):
+        hi = min(int(seg[s]), len(ptn))
+        res += (boot[:, lo:hi].astype(np.int64) * ptn[lo:hi].astype(np.int64)).sum(axis=1) & 0xFFFF
+        if nseg // 4 < s < nseg - 1:
+            best = np.maximum(best, res + remain[:, s])
+        lo = hi
+    return best
+
+
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES[:5])
+def test_reps_prefix_max_matches_numpy(n, L, dt, seed, B, mu):
+    """The left side of the remain-bound skip test for the current tree and every insertion of three node visits, all replicates,
+    on data whose segments wrap (heavy replicates) -- from the oracle's pattern vector of each saveCurrentTree call."""
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    ninf = c["n_inf"]
+    remain = _remain_bounds(boot, seg, bound, ninf)
+    eng = _engine(c, boot, seg, 1)
+    eng.set_remain_bounds(remain)
+    allb = np.arange(B, dtype=np.int32)
+    assert np.array_equal(eng.reps_prefix_max(-1, allb), _prefix_max_numpy(pp[:ninf], boot, seg, remain))
+    order = eng.visit_order()
+    for i in (1, n + 1, 2 * n - 2):
+        o.set_ring(c["bn"], c["bs"]); o.allocate(True); o.evaluate_full(True)
+        o.record(True)
+        o.rearrange(i, 1, 6, True, s0)
+        mps, ptn = o.saved(True)
+        vb, mp, cref, cprune = eng.scan_visits(order, i, 1, 1, 6)
+        for k in range(len(mps)):
+            want = _prefix_max_numpy(ptn[k, :ninf], boot, seg, remain)
+            assert np.array_equal(eng.reps_prefix_max(k - 1, allb), want), (i, k)
+        sub = np.array([B - 1, 0, B // 2], dtype=np.int32)                     # a short, unordered list
+        assert np.array_equal(eng.reps_prefix_max(len(mps) - 2, sub), _prefix_max_numpy(ptn[len(mps) - 1, :ninf], boot, seg, remain)[sub])
+
+
+def _run_gpu_bb_distinct(c, boot, seg, tensor, K, remain, iters=3, seed=2024, mt=6, cutoff=0.0):
+    from mpboot_b200 import synth
+    from mpboot_b200.engine import Treels
+    eng = _engine(c, boot, seg, tensor)
+    if remain is not None:
+        eng.set_remain_bounds(remain)
+    B = boot.shape[0]
+    bl = np.full(B, -float(np.iinfo(np.int64).max), dtype=np.float64)
+    bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
+    thr = np.full(B, -(2 ** 31 - 1), dtype=np.int32)
+    tl = Treels(c["n"])
+    portlib.seed_rng(seed)
+    rets, ncalls, nreps = [], 0, 0
+    for it in range(1, iters + 1):
+        bn, bs = (c["bn"], c["bs"]) if it == 1 else synth.random_tree_rings(c["n"], np.random.default_rng(5000 + it))
+        ret, bn, bs, nins, nc, nr = eng.optimize_spr_bb(bn, bs, tl.hooks(portlib.rng_fn_address()), bl, bc, bt, cutoff, 0.5, 1, mt,
+                                                        distinct=K, cur_it=it, boot_threshold=thr)
+        rets.append(ret); ncalls += nc; nreps += nr
+    top = tl.toplists(B)
+    return dict(ret=rets, draws=portlib.rng_draws(), ring=(bn, bs), state=(bl, bc, bt), ncalls=ncalls, nreps=nreps, treels=tl.logl(),
+                mats=tl.materialized(), toplists=(top[0], thr, top[1]), topiters=tl.topiters(B))
+
+
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES[:3])
+@pytest.mark.parametrize("K", [1, 3])
+def test_bb_distinct_iter_matches_oracle(n, L, dt, seed, B, mu, K, tensor):
+    """Three iterations of -bb SPR searches under -distinct_iter_top_boot K on one bookkeeping state: lists, iterations, thresholds,
+    boot_logl / counts / trees, draws, treels and materialised trees equal the oracle's -- without remain bounds and with them
+    (where the skip of replicates changes decisions, tests/test_bb_cpu.py)."""
+    from tests.test_bb_cpu import run_bb_distinct
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    for bnd in (None, bound):
+        w = run_bb_distinct(o, c, boot, seg, bnd, False, K)
+        g = _run_gpu_bb_distinct(c, boot, seg, tensor, K, None if bnd is None else _remain_bounds(boot, seg, bnd, c["n_inf"]))
+        assert g["ret"] == w["ret"] and g["draws"] == w["draws"]
+        assert np.array_equal(g["ring"][0][3:], w["ring"][0][3:]) and np.array_equal(g["ring"][1][3:], w["ring"][1][3:])
+        assert all(np.array_equal(x, y) for x, y in zip(g["state"], w["state"]))
+        assert all(np.array_equal(x, y) for x, y in zip(g["toplists"], w["toplists"])) and np.array_equal(g["topiters"], w["topiters"])
+        assert g["ncalls"] == w["counters"][0] and g["nreps"] == w["counters"][2]
+        assert np.array_equal(g["treels"], w["treels"])
+        assert np.array_equal(g["mats"][:, :3], w["mats"][:, 1:4]) and np.array_equal(g["mats"][:, 3], w["mats"][:, 4])
+
+
 def test_full_size_c2_reps_linearity_and_dot_product():
     """Full BASELINE size (C2: 200 x 100 000 patterns, B = 999 replicates in three blocks A, B, A + B): with MPBoot's own
     segmentation no 16-bit segment sum wraps, so REPS is linear in the replicate frequencies -- res(A + B) = res(A) + res(B)

@@ -34,6 +34,10 @@ CASES = {
     "mulhits_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-mulhits"]),
     "topboot_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-mulhits", "-topboot", "3"]),
     "mulhits_aa_20x600": (20, 600, synth.PLL_AA_DATA, 0.08, 13, ["-st", "AA", "-mulhits"]),
+    # -distinct_iter_top_boot K (iqtree.cpp:3587-3685) on saturated alignments (supports well below 100, so the policy shows in the
+    # outputs: they differ from the default policy's): 2 REPS segments (no segment in the skip test's range) / 5 segments
+    "distinct_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-distinct_iter_top_boot", "3"]),
+    "distinct_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-distinct_iter_top_boot", "2"]),
     # -cost (Sankoff weighted parsimony, ParsTree): transitions 1 / transversions 2; "@tstv" = a cost file written next to the alignment
     "cost_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv"]),
     # an asymmetric matrix (obeys the triangle inequality, so ParsTree::initCostMatrix leaves it alone): scores depend on the root
