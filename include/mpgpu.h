@@ -309,10 +309,11 @@ int mpgpu_reps_candidates(mpgpu_ctx *ctx, const int32_t *cand_idx, int m, int32_
  * row buffers in one piece. */
 int mpgpu_reps_candidates_device(mpgpu_ctx *ctx, const int32_t *cand_idx, int m, void **dev_res, int *pitch);
 
-/* ---- pllOptimizeSprParsimony under -bb: search + saveCurrentTree, default policy ----
+/* ---- pllOptimizeSprParsimony under -bb: search + saveCurrentTree ----
  * Replaces the pair pllOptimizeSprParsimony (sprparsimony.cpp:3244) / IQTree::saveCurrentTree
- * (iqtree.cpp:3271-3760) for maximum_parsimony && spr_parsimony with !store_candidate_trees,
- * !multiple_hits, distinct_iter_top_boot < 1, outside ratchet iterations.  Every scored
+ * (iqtree.cpp:3271-3760) for maximum_parsimony && spr_parsimony with !store_candidate_trees.  Described here for the
+ * default policy (!multiple_hits, distinct_iter_top_boot < 1, outside ratchet iterations); the other policies and
+ * ratchet iterations are selected through mpgpu_bb_state below.  Every scored
  * insertion and, once per node visit, the current tree (:2286-2289) goes through the cutoff
  * filter (:3343), is appended to treels_logl (push_tree_logl), gets its REPS vector from the
  * device and updates boot_logl / boot_counts / boot_trees exactly as :3687-3731, drawing

@@ -562,7 +562,8 @@ MPREF_API unsigned long mpref_sweep_count_insertions(mpref *h, int mintrav, int 
  * !auto_vectorize, !do_first_rell, outside ratchet iterations.  The REPS loop runs on the
  * reference's own Vec16us (load_a on 32-byte aligned buffers, as iqtree.cpp:3428); pattern
  * scores come from the reference's pllComputePatternParsimony; the skip bound is
- * pllComputeRellRemainBound (:3821-3858) over pllCalcMinParsScorePattern and ras_pars_score. */
+ * pllComputeRellRemainBound (:3821-3858) over pllCalcMinParsScorePattern and ras_pars_score.
+ * mpref_boot_set_mulhits / _topboot / _distinct / _ratchet switch on the other branches of the same function. */
 #include <map>
 #include <set>
 struct BootSim {
