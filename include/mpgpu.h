@@ -381,6 +381,13 @@ typedef struct mpgpu_bb_state {
     int32_t *top_count;                       /* [B] in/out: boot_trees_parsimony_top[sample].size() */
     int32_t *boot_threshold;                  /* [B] in/out: IQTree::boot_threshold (vector<int>, starts at -INT_MAX, iqtree.cpp:267) */
     int32_t cur_it;                           /* MPGPU_BB_DISTINCT_ITER: IQTree::curIt of this search */
+    int32_t updates_off;                      /* -min_iter1_cand in iteration 1 (params->minimize_iter1_candidates && curIt == 1,
+                                               * iqtree.cpp:3404): a call that passes the cutoff is appended to treels_logl and
+                                               * nothing else happens -- no replicate is touched, no tree materialised, no draw */
+    int32_t *boot_tree_orig_logl;             /* -cutoff_from_btrees (IQTree::boot_tree_orig_logl, vector<int> [B]) or NULL: the
+                                               * call's cur_logl is stored when a replicate accepts its tree (default :3717-3718,
+                                               * distinct-iteration :3618-3619) or, under -mulhits, raised to it (:3524-3527);
+                                               * the host derives logl_cutoff from it between searches (:1657-1661) */
 } mpgpu_bb_state;
 int mpgpu_optimize_spr_bb(mpgpu_ctx *ctx, int32_t *back_node, int32_t *back_slot, int mintrav, int maxtrav,
                           const mpgpu_bb_hooks *hooks, mpgpu_bb_state *state,

@@ -557,6 +557,8 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
     const double eps = st->ufboot_epsilon;
     int32_t tree_index = hk->push_tree_logl(hk->user, cur_logl);
     const int32_t tree_index_pushed = tree_index;         // treels_logl.size() - 1 of this call
+    if (st->updates_off) { st->n_reps++; return; }        // -min_iter1_cand, iteration 1 (iqtree.cpp:3404)
+    int32_t *const orig_logl = st->boot_tree_orig_logl;   // -cutoff_from_btrees
     bool have = false;
     const bool mulhits = st->policy == MPGPU_BB_MULHITS;
     auto one = [&](int b, int32_t res) {
@@ -590,6 +592,7 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
                     tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
                 }
                 if (rell > bl) st->boot_logl[b] = rell;
+                if (orig_logl && cur_logl > (double)orig_logl[b]) orig_logl[b] = (int32_t)cur_logl;      // :3524-3527
                 hk->mulhit(hk->user, b, tree_index, rell > bl);
             }
             return;
@@ -600,6 +603,7 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
                 tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
             }
             if (rell > bl) st->boot_counts[b] = 1;
+            if (orig_logl) orig_logl[b] = (int32_t)cur_logl;                                              // :3717-3718
             st->boot_logl[b] = std::max(bl, rell);
             st->boot_trees[b] = tree_index;
         }
@@ -630,6 +634,7 @@ static void bb_save(BBRun *bb, Ctx *c, double cur_logl, const RepsOut &ro, int c
                     have = true;
                     tree_index = hk->materialize(hk->user, c->tree.bn.data(), c->tree.bs.data(), remove_ref, insert_ref, tree_index);
                 }
+                if (orig_logl) orig_logl[b] = (int32_t)cur_logl;                               // :3618-3619
                 st->boot_trees[b] = tree_index;                                                // :3621
                 st->boot_logl[b] = std::max(st->boot_logl[b], rell);
                 st->boot_threshold[b] = hk->disthit(hk->user, b, tree_index, (int32_t)rell, st->cur_it, st->top_n, thr);   // :3624-3678
@@ -785,6 +790,9 @@ static int optimize_impl(mpgpu_ctx *c, int32_t *back_node, int32_t *back_slot, i
                     for (int b = 0; b < st->B; b++) thr[b] = st->boot_threshold[b] <= -2147483647 ? 2147483647 : -st->boot_threshold[b];
                 } else
                 for (int b = 0; b < st->B; b++) thr[b] = bb_screen_of(st->boot_logl[b], st->ufboot_epsilon);
+                if (st->updates_off && !st->ratchet) {     // -min_iter1_cand, iteration 1: the calls only extend treels_logl, no REPS vector is used
+                    ro.dense.clear(); ro.dense_off.assign(pass_cands.size(), -1); ro.orig.clear(); ro.keep_slot.clear();
+                } else
                 if (int rc = reps_run(c, pass_cands.data(), (int)pass_cands.size(), thr.data(), ro)) return rc;
             }
             prof.stop(2); prof.start();

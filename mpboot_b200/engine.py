@@ -122,7 +122,7 @@ class BBState(C.Structure):
                 ("logl_cutoff", C.c_double), ("ufboot_epsilon", C.c_double), ("n_calls", C.c_int64), ("n_reps", C.c_int64),
                 ("ratchet", C.c_int32), ("ratchet_pattern_pars", C.c_void_p), ("ratchet_last_score", C.c_int32),
                 ("policy", C.c_int32), ("top_n", C.c_int32), ("top_count", C.c_void_p), ("boot_threshold", C.c_void_p),
-                ("cur_it", C.c_int32)]
+                ("cur_it", C.c_int32), ("updates_off", C.c_int32), ("boot_tree_orig_logl", C.c_void_p)]
 
 
 class HostRng:
@@ -527,14 +527,15 @@ class Engine:
 
     def optimize_spr_bb(self, bn, bs, hooks, boot_logl, boot_counts, boot_trees, logl_cutoff=0.0, eps=0.5,
                         mintrav=1, maxtrav=6, ratchet_pattern_pars=None, mulhits=False, topboot=0, distinct=0, cur_it=1,
-                        boot_threshold=None):
+                        boot_threshold=None, updates_off=False, boot_tree_orig_logl=None):
         """pllOptimizeSprParsimony + saveCurrentTree (default policy).  hooks: BBHooks (e.g.
         Treels.hooks(rng)); boot_* arrays are updated in place.  Returns (startMP, back_node,
         back_slot, insertions scored, saveCurrentTree calls, REPS vectors used)."""
         bn = np.array(bn, dtype=np.int32, copy=True); bs = np.array(bs, dtype=np.int32, copy=True)
         assert boot_logl.dtype == np.float64 and boot_counts.dtype == np.int32 and boot_trees.dtype == np.int32
         st = BBState(len(boot_logl), boot_logl.ctypes.data, boot_counts.ctypes.data, boot_trees.ctypes.data,
-                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0, 0, None, None, int(cur_it))
+                     float(logl_cutoff), float(eps), 0, 0, 0, None, 0, 1 if mulhits else 0, 0, None, None, int(cur_it),
+                     1 if updates_off else 0, None if boot_tree_orig_logl is None else boot_tree_orig_logl.ctypes.data)
         if distinct:                                    # -distinct_iter_top_boot K: boot_threshold [B] int32 is the caller's, in/out
             assert boot_threshold is not None and boot_threshold.dtype == np.int32 and len(boot_threshold) == len(boot_logl)
             st.policy = 3; st.top_n = int(distinct); st.boot_threshold = boot_threshold.ctypes.data

@@ -383,6 +383,50 @@ def test_bb_distinct_iter_matches_oracle(n, L, dt, seed, B, mu, K, tensor):
         assert np.array_equal(g["mats"][:, :3], w["mats"][:, 1:4]) and np.array_equal(g["mats"][:, 3], w["mats"][:, 4])
 
 
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES[:3])
+def test_bb_min_iter1_cand_and_cutoff_from_btrees(n, L, dt, seed, B, mu):
+    """-min_iter1_cand in iteration 1 (state.updates_off, iqtree.cpp:3404): every call that passes the cutoff lands in treels_logl and
+    nothing else happens -- the search is the plain search (same draws, same tree), replicates untouched, nothing materialised.
+    -cutoff_from_btrees (state.boot_tree_orig_logl, :3717-3718 / :3524-3527): each replicate ends up with the score, on the original
+    alignment, of the tree it holds.  (The patched program's outputs under both options equal the stock binary's:
+    tests/test_gpu_dropin.py.)"""
+    from mpboot_b200.engine import Engine, Treels
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    full = _run_gpu_bb(c, boot, seg, 0.0, 1)
+
+    def run(**kw):
+        eng = _engine(c, boot, seg, 1)
+        bl = np.full(B, -float(np.iinfo(np.int64).max), dtype=np.float64)
+        bc = np.zeros(B, dtype=np.int32); bt = np.full(B, -1, dtype=np.int32)
+        tl = Treels(c["n"])
+        portlib.seed_rng(2024)
+        ret, bn, bs, nins, ncalls, nreps = eng.optimize_spr_bb(c["bn"], c["bs"], tl.hooks(portlib.rng_fn_address()), bl, bc, bt, 0.0, 0.5, 1, 6, **kw)
+        return dict(ret=ret, draws=portlib.rng_draws(), ring=(bn, bs), state=(bl, bc, bt), treels=tl.logl(), mats=tl.materialized(), tl=tl,
+                    ncalls=ncalls, nins=nins)
+
+    portlib.seed_rng(2024)
+    eng = Engine(); eng.load_alignment(c["codes"], c["weights"], c["datatype"])
+    plain_ret, pbn, pbs, plain_nins = eng.optimize_spr(c["bn"], c["bs"], portlib.rng_fn_address(), 1, 6)
+    plain_draws = portlib.rng_draws()
+
+    off = run(updates_off=True)
+    assert off["ret"] == plain_ret and off["draws"] == plain_draws and off["nins"] == plain_nins      # no saveCurrentTree draw
+    assert np.array_equal(off["ring"][0][3:], pbn[3:]) and np.array_equal(off["ring"][1][3:], pbs[3:])
+    assert len(off["mats"]) == 0 and (off["state"][2] == -1).all() and (off["state"][1] == 0).all()
+    assert len(off["treels"]) == off["ncalls"] > plain_nins                                # cutoff off: every call is appended (insertions + one per visit)
+    assert off["treels"].max() == -float(plain_ret)                                        # the best tree the search saw
+
+    orig = np.zeros(B, dtype=np.int32)
+    r = run(boot_tree_orig_logl=orig)
+    assert r["ret"] == full["ret"] and r["draws"] == full["draws"] and all(np.array_equal(x, y) for x, y in zip(r["state"], full["state"]))
+    assert np.array_equal(orig.astype(np.float64), r["treels"][r["state"][2]])             # cur_logl of the tree each replicate holds
+    orig2 = np.zeros(B, dtype=np.int32)
+    m = run(mulhits=True, boot_tree_orig_logl=orig2)
+    sizes, flat = m["tl"].mulhits(B)
+    best = np.array([m["treels"][flat[sizes[:b].sum(): sizes[:b + 1].sum()]].max() for b in range(B)])
+    assert (orig2 >= best).all() and np.isin(orig2.astype(np.float64), m["treels"]).all() and (orig2 < 0).all()
+
+
 def test_full_size_c2_reps_linearity_and_dot_product():
     """Full BASELINE size (C2: 200 x 100 000 patterns, B = 999 replicates in three blocks A, B, A + B): with MPBoot's own
     segmentation no 16-bit segment sum wraps, so REPS is linear in the replicate frequencies -- res(A + B) = res(A) + res(B)

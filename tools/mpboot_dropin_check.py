@@ -38,6 +38,12 @@ CASES = {
     # outputs: they differ from the default policy's): 2 REPS segments (no segment in the skip test's range) / 5 segments
     "distinct_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-distinct_iter_top_boot", "3"]),
     "distinct_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-distinct_iter_top_boot", "2"]),
+    # -cutoff_from_btrees (logl_cutoff from IQTree::boot_tree_orig_logl, iqtree.cpp:1657-1661, filled at :3524 / :3618 / :3717) under the
+    # default, the -mulhits and the distinct-iteration policy; -min_iter1_cand (iteration 1 only extends treels_logl, :3404)
+    "cutoffbt_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-cutoff_from_btrees"]),
+    "cutoffbt_mulhits_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-mulhits", "-cutoff_from_btrees"]),
+    "cutoffbt_distinct_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-distinct_iter_top_boot", "2", "-cutoff_from_btrees"]),
+    "miniter1_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-min_iter1_cand"]),
     # -cost (Sankoff weighted parsimony, ParsTree): transitions 1 / transversions 2; "@tstv" = a cost file written next to the alignment
     "cost_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv"]),
     # an asymmetric matrix (obeys the triangle inequality, so ParsTree::initCostMatrix leaves it alone): scores depend on the root
