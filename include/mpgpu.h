@@ -280,6 +280,8 @@ int mpgpu_sankoff_reps_stats(mpgpu_ctx *ctx, int64_t *tensor_chunks, int64_t *ex
 
 /* Options: "sankoff_exact" 0/1 (see mpgpu_scan_bounds);
  * "reps_tensor" 0/1 (0 = everything through the exact CUDA-core kernel; for tests);
+ * "reps_nowrap" 0/1 (-autovec, iqtree.cpp:3418-3423: the replicate scores are plain int dot products, no 16-bit segment sums and no
+ * skip test; the original_sample column of ratchet iterations keeps the segmented u16 sums of :3283-3294; Fitch scoring only);
  * "reps_timing" 0/1 (CUDA events around the largest tensor-kernel launch, read by mpgpu_reps_timing);
  * "sankoff_u32" 0/1 (-short_off, tools.cpp:2365: the reference's 32-bit Sankoff vectors -- pattern weights are not cut to 16 bits and
  * the per-segment weighted sums and node scores do not wrap at 2^16; set before mpgpu_set_cost_matrix; the u16 bound on

@@ -44,9 +44,9 @@ void free_reps(Ctx *c)
     for (void *p : ptrs) if (p) cudaFree(p);
     if (r.ev0) { cudaEventDestroy(r.ev0); cudaEventDestroy(r.ev1); }
     if (r.h_pin) cudaFreeHost(r.h_pin);
-    const bool use_tensor = r.use_tensor, timing = r.timing;
+    const bool use_tensor = r.use_tensor, timing = r.timing, nowrap = r.nowrap;
     r = Reps();
-    r.use_tensor = use_tensor; r.timing = timing;
+    r.use_tensor = use_tensor; r.timing = timing; r.nowrap = nowrap;
     c->d_row_of = nullptr; c->d_row_tasks = nullptr; c->d_rows_site = nullptr;
 }
 
@@ -419,6 +419,7 @@ static int reps_run(Ctx *c, const int32_t *cands, int m, const int32_t *thr, Rep
     out.keep_slot.assign(r.keep_on ? m : 0, -1);
     r.keep_used = 0;
     if (m == 0) return 0;
+    if (c->sk.on && r.nowrap) { set_error("option reps_nowrap (-autovec) is not available under -cost"); return 1; }
     if (c->sk.on) return sk_reps_run(c, cands, m, thr, out, device_only);
     if (int rc = refresh_tree_rows(c)) return rc;
     // rows the whole list would like to have; ensure_rows clamps to the memory budget
@@ -1113,6 +1114,7 @@ int mpgpu_set_option(mpgpu_ctx *c, const char *name, int value)
         c->reps.use_tensor = value != 0;
         return 0;
     }
+    if (!strcmp(name, "reps_nowrap")) { c->reps.nowrap = value != 0; return 0; }
     if (!strcmp(name, "sankoff_exact")) { c->sk.exact = value != 0; return 0; }
     if (!strcmp(name, "sankoff_u32")) {
         if (c->sk.on) { set_error("sankoff_u32 must be set before mpgpu_set_cost_matrix"); return 1; }

@@ -130,6 +130,7 @@ struct Reps {
     int p_lo = 0, p_hi = 0;               // patterns whose first expanded site lies in this shard's word slice
     int32_t *d_segmax = nullptr;          // [nseg] wrap check: max over replicates of the segment bound
     bool use_tensor = true;
+    bool nowrap = false;                  // option "reps_nowrap" (-autovec): the replicates' sums are plain ints, only original_sample's column keeps the 16-bit segment sums
     uint8_t *d_w8 = nullptr;              // [Bpad][Kpad] u8, K-major: the tensor kernel's B operand
     uint16_t *d_w16T = nullptr;           // [upper][Bpad] u16, pattern-major: the exact weights
     int32_t *d_seg_upper = nullptr;       // [nseg]

@@ -939,7 +939,7 @@ __global__ void k_reps_tree_row(int32_t *__restrict__ X, int plane_row0, int nbi
 
 __global__ void __launch_bounds__(256) k_reps_combine(const int32_t *__restrict__ X, int G, int Bpad, int B, int t_row,
                                                       const int2 *__restrict__ calls, int call0, int ncalls, int32_t *__restrict__ res,
-                                                      const int32_t *__restrict__ thr, int32_t *__restrict__ call_hit)
+                                                      const int32_t *__restrict__ thr, int32_t *__restrict__ call_hit, int nowrap_cols)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = call0 + blockIdx.y;                           // uniform over the block
@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(256) k_reps_combine(const int32_t *__restrict_
             int v = X[(size_t)t_row * pitch + (size_t)g * Bpad + b];
             if (cd.x >= 0) v -= X[(size_t)cd.x * pitch + (size_t)g * Bpad + b];
             if (cd.y >= 0) v += X[(size_t)cd.y * pitch + (size_t)g * Bpad + b];
-            total += g == 0 ? v : (v & 0xFFFF);
+            total += (g == 0 || b < nowrap_cols) ? v : (v & 0xFFFF);     // columns below nowrap_cols: the plain-int loop of -autovec (iqtree.cpp:3418-3423)
         }
         res[(size_t)j * Bpad + b] = total;
         hit = thr && b < B && total <= thr[b];
@@ -985,7 +985,8 @@ int launch_reps_combine(Ctx *c, int t_row, const int2 *d_calls, int ncalls, int3
     for (int done = 0; done < ncalls; done += 65535) {
         const int chunk = ncalls - done < 65535 ? ncalls - done : 65535;
         dim3 grid((r.Bpad + 255) / 256, chunk);
-        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.Buser, t_row, d_calls, done, ncalls, d_res, d_thr, d_call_hit);
+        k_reps_combine<<<grid, 256, 0, c->stream>>>(r.d_X, r.G, r.Bpad, r.Buser, t_row, d_calls, done, ncalls, d_res, d_thr, d_call_hit,
+                                                    r.nowrap ? r.Buser : 0);
         c->launches++;
         MPGPU_CUDA(cudaGetLastError());
     }

@@ -53,6 +53,31 @@ def test_reps_current_tree_and_candidates(n, L, dt, seed, B, mu, tensor):
             assert np.array_equal(got[k], portlib.reps(ptn[k, : c["n_inf"]], boot[:, : c["n_inf"]], seg)), (i, k)
 
 
+@pytest.mark.parametrize("tensor", [0, 1], ids=["exact-cuda-core", "tensor"])
+@pytest.mark.parametrize("n,L,dt,seed,B,mu", CASES[:3])
+def test_reps_nowrap_is_the_plain_int_dot_product(n, L, dt, seed, B, mu, tensor):
+    """-autovec (option reps_nowrap, iqtree.cpp:3418-3423): res = sum_ptn pattern_pars * boot_sample as plain ints -- on replicates
+    whose 16-bit segment sums do wrap, so the two semantics differ."""
+    c, o, s0, pp, seg, boot, ras, bound = bb_setup(n, L, dt, seed, B, mu)
+    ninf = c["n_inf"]
+    w = boot[:, :ninf].astype(np.int64)
+    eng = _engine(c, boot, seg, tensor)
+    wrapped = eng.reps_current_tree()
+    eng.set_option("reps_nowrap", 1)
+    plain = eng.reps_current_tree()
+    assert np.array_equal(plain, w @ pp[:ninf].astype(np.int64)) and not np.array_equal(plain, wrapped)
+    order = eng.visit_order()
+    o.set_ring(c["bn"], c["bs"]); o.allocate(True); o.evaluate_full(True)
+    o.record(True)
+    o.rearrange(n + 1, 1, 6, True, s0)
+    mps, ptn = o.saved(True)
+    vb, mp, cref, cprune = eng.scan_visits(order, n + 1, 1, 1, 6)
+    got = eng.reps_candidates(np.arange(-1, len(mp), dtype=np.int32))
+    assert np.array_equal(got, (w @ ptn[:, :ninf].astype(np.int64).T).T)
+    eng.set_option("reps_nowrap", 0)
+    assert np.array_equal(eng.reps_current_tree(), wrapped)
+
+
 def _same_as_oracle(g, w):
     assert g["ret"] == w["ret"] and g["draws"] == w["draws"]
     assert np.array_equal(g["ring"][0][3:], w["ring"][0][3:]) and np.array_equal(g["ring"][1][3:], w["ring"][1][3:])

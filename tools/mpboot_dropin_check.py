@@ -44,6 +44,8 @@ CASES = {
     "cutoffbt_mulhits_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-mulhits", "-cutoff_from_btrees"]),
     "cutoffbt_distinct_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-distinct_iter_top_boot", "2", "-cutoff_from_btrees"]),
     "miniter1_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-min_iter1_cand"]),
+    # -autovec: the unsegmented plain-int REPS loop (iqtree.cpp:3418-3423), no skip test
+    "autovec_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-autovec"]),
     # -cost (Sankoff weighted parsimony, ParsTree): transitions 1 / transversions 2; "@tstv" = a cost file written next to the alignment
     "cost_17x1998": (17, 1998, synth.PLL_DNA_DATA, 0.05, 1, ["-cost", "@tstv"]),
     # an asymmetric matrix (obeys the triangle inequality, so ParsTree::initCostMatrix leaves it alone): scores depend on the root
