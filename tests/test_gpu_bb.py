@@ -445,11 +445,16 @@ def test_bb_min_iter1_cand_and_cutoff_from_btrees(n, L, dt, seed, B, mu):
     r = run(boot_tree_orig_logl=orig)
     assert r["ret"] == full["ret"] and r["draws"] == full["draws"] and all(np.array_equal(x, y) for x, y in zip(r["state"], full["state"]))
     assert np.array_equal(orig.astype(np.float64), r["treels"][r["state"][2]])             # cur_logl of the tree each replicate holds
+    # -mulhits only ever raises the entry (:3524-3527): from the reference's initial 0 (iqtree.cpp:254) a negative score never does ...
     orig2 = np.zeros(B, dtype=np.int32)
     m = run(mulhits=True, boot_tree_orig_logl=orig2)
+    assert (orig2 == 0).all()
+    # ... from below it climbs to the best original-alignment score among the trees that ever tied or beat the replicate's best
+    orig3 = np.full(B, -10 ** 6, dtype=np.int32)
+    m = run(mulhits=True, boot_tree_orig_logl=orig3)
     sizes, flat = m["tl"].mulhits(B)
     best = np.array([m["treels"][flat[sizes[:b].sum(): sizes[:b + 1].sum()]].max() for b in range(B)])
-    assert (orig2 >= best).all() and np.isin(orig2.astype(np.float64), m["treels"]).all() and (orig2 < 0).all()
+    assert (orig3 >= best).all() and np.isin(orig3.astype(np.float64), m["treels"]).all() and (orig3 < 0).all()
 
 
 def test_full_size_c2_reps_linearity_and_dot_product():

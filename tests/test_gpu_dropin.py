@@ -29,7 +29,7 @@ RUNS = [("c1_12x300", "plain"), ("c1_12x300", "bb"), ("c1_17x1998", "plain"), ("
         ("mulhits_17x1998", "bb"), ("topboot_17x1998", "bb"), ("mulhits_aa_20x600", "bb"),
         ("distinct_20x800", "bb"), ("distinct_30x1500", "bb"),
         ("cutoffbt_30x1500", "bb"), ("cutoffbt_mulhits_20x800", "bb"), ("cutoffbt_distinct_20x800", "bb"), ("miniter1_20x800", "bb"),
-        ("autovec_30x1500", "bb"),
+        ("autovec_30x1500", "bb"), ("firstrell_30x1500", "bb"), ("firstrell_distinct_30x1500", "bb"),
         ("cost_17x1998", "plain"), ("cost_17x1998", "bb"), ("costasym_17x1998", "plain"), ("costasym_17x1998", "bb"),
         ("costu32_17x1998", "plain"), ("costu32_17x1998", "bb")]
 

@@ -44,6 +44,9 @@ CASES = {
     "cutoffbt_mulhits_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-mulhits", "-cutoff_from_btrees"]),
     "cutoffbt_distinct_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-distinct_iter_top_boot", "2", "-cutoff_from_btrees"]),
     "miniter1_20x800": (20, 800, synth.PLL_DNA_DATA, 0.25, 21, ["-min_iter1_cand"]),
+    # -do_first_rell: REPS over the first half of the patterns only (iqtree.cpp:3426-3429), alone and under the distinct-iteration policy
+    "firstrell_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-do_first_rell"]),
+    "firstrell_distinct_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-do_first_rell", "-distinct_iter_top_boot", "2"]),
     # -autovec: the unsegmented plain-int REPS loop (iqtree.cpp:3418-3423), no skip test
     "autovec_30x1500": (30, 1500, synth.PLL_DNA_DATA, 0.35, 23, ["-autovec"]),
     # -cost (Sankoff weighted parsimony, ParsTree): transitions 1 / transversions 2; "@tstv" = a cost file written next to the alignment
