@@ -641,6 +641,26 @@ struct BatchProf {
 };
 static BatchProf g_bp;
 
+// MPGPU_PROFILE=4: host timeline of mpgpu_scan_visits (the e2e sweep), averaged over the calls and printed at exit: when each
+// stage of the call was reached, in us since the call began
+struct SweepProf {
+    bool on = getenv("MPGPU_PROFILE") && atoi(getenv("MPGPU_PROFILE")) == 4;
+    static const int K = 16;
+    const char *name[K] = {nullptr};
+    double sum[K] = {0}; long cnt[K] = {0};
+    std::chrono::steady_clock::time_point t0;
+    void begin() { if (on) t0 = std::chrono::steady_clock::now(); }
+    void mark(int k, const char *what) {
+        if (!on || k >= K) return;
+        name[k] = what; sum[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); cnt[k]++;
+    }
+    ~SweepProf() {
+        if (!on) return;
+        for (int k = 0; k < K; k++) if (cnt[k]) fprintf(stderr, "[mpgpu sweep timeline] %-34s %8.1f us (n = %ld)\n", name[k], 1e6 * sum[k] / cnt[k], cnt[k]);
+    }
+};
+static SweepProf g_sw;
+
 // d_counts[0, n) = 0 before a scan.  k_publish leaves the range it read zeroed, so in the search loop this is usually
 // nothing; any other reader leaves the counters dirty and the next scan pays one memset.
 int zero_counts(Ctx *c, size_t n)
@@ -670,13 +690,23 @@ int run_scan(Ctx *c)
 // zero (the next batch needs no memset) and writes the flag word last; the host spins on the flag.
 __global__ void __launch_bounds__(512) k_publish(int32_t *__restrict__ counts, int nout, uint32_t *__restrict__ wcount, int nwc,
                                                  int32_t *__restrict__ host_counts, uint32_t *__restrict__ host_wc,
-                                                 volatile uint32_t *host_flag, uint32_t epoch)
+                                                 volatile uint32_t *host_flag, uint32_t epoch, unsigned int *ticket)
 {
-    for (int i = threadIdx.x; i < nout; i += blockDim.x) { host_counts[i] = __ldcg(counts + i); counts[i] = 0; }
-    for (int i = threadIdx.x; i < nwc; i += blockDim.x) { host_wc[i] = __ldcg(wcount + i); wcount[i] = 0; }
+    // a large read-back (a whole sweep: ~15 k counters) is spread over a few blocks -- one block's posted writes over PCIe took 19 us
+    // for 61 KB -- and the block that draws the last ticket raises the flag (every block fences its writes before it draws)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i < nout; i += nth) { host_counts[i] = __ldcg(counts + i); counts[i] = 0; }
+    for (int i = tid; i < nwc; i += nth) { host_wc[i] = __ldcg(wcount + i); wcount[i] = 0; }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) *host_flag = epoch;
+    if (threadIdx.x == 0) {
+        if (gridDim.x == 1) { *host_flag = epoch; return; }
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0;
+            __threadfence_system();
+            *host_flag = epoch;
+        }
+    }
 }
 
 static int ensure_h_counts(Ctx *c, size_t nout)
@@ -723,8 +753,11 @@ int launch_publish(Ctx *c, int nout)
     if (int rc = ensure_h_counts(c, (size_t)nout)) return rc;
     c->flag_epoch++;
     if (c->flag_epoch == 0) c->flag_epoch = 1;
-    k_publish<<<1, 512, 0, c->stream>>>(c->d_counts, nout, c->d_wcount, (int)c->wc_used, c->h_counts, c->wcount_pin.data(),
-                                        c->h_flag, c->flag_epoch);
+    if (!c->d_done) { MPGPU_CUDA(cudaMalloc((void **)&c->d_done, 64)); MPGPU_CUDA(cudaMemsetAsync(c->d_done, 0, 64, c->stream)); }
+    static const int max_blocks = getenv("MPGPU_PUBLISH_BLOCKS") ? std::max(1, atoi(getenv("MPGPU_PUBLISH_BLOCKS"))) : 16;   // tuning knob
+    const int blocks = std::max(1, std::min(max_blocks, (nout + (int)c->wc_used + 1023) / 1024));
+    k_publish<<<blocks, 512, 0, c->stream>>>(c->d_counts, nout, c->d_wcount, (int)c->wc_used, c->h_counts, c->wcount_pin.data(),
+                                             c->h_flag, c->flag_epoch, c->d_done + 1);      // (word 0 is the fused publish's ticket)
     c->launches++;
     MPGPU_CUDA(cudaGetLastError());
     if (g_bp.armed) g_bp.rec(3, c->stream);
@@ -738,6 +771,11 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
     if (pl.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
     const size_t nout = (size_t)pl.task_cap + pl.n_cand;
     static const bool no_publish = getenv("MPGPU_NO_PUBLISH") != nullptr;
+    // what does not depend on the counts goes to the caller while the device is still scoring
+    if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
+    if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
+    if (cand_prune) memcpy(cand_prune, pl.cand_prune.data(), pl.n_cand * sizeof(int32_t));
+    g_sw.mark(10, "finish: index arrays copied");
     if (c->pub_inflight) {                 // the scan's last block publishes (latency path)
         c->pub_inflight = false;
         if (g_bp.armed) g_bp.rec(3, c->stream);
@@ -751,6 +789,7 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
         MPGPU_CUDA(cudaStreamSynchronize(c->stream));
         c->counts_dirty = nout + 1;
     }
+    g_sw.mark(11, "finish: counts on the host");
     settle_views(c, true);
     if (!c->lens_valid) { set_error("view lengths not set"); return 1; }
     const size_t ntasks = pl.tasks.size();
@@ -764,9 +803,7 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
         const int ti = ctask[j];
         mp[j] = tconst[ti] + (uint32_t)base[ti] + (uint32_t)cnt[j];
     }
-    if (visit_begin) memcpy(visit_begin, pl.visit_begin.data(), pl.visit_begin.size() * sizeof(int32_t));
-    if (cand_ref) memcpy(cand_ref, pl.cand_ref.data(), pl.n_cand * sizeof(int32_t));
-    if (cand_prune) memcpy(cand_prune, pl.cand_prune.data(), pl.n_cand * sizeof(int32_t));
+    g_sw.mark(12, "finish: scores assembled");
     if (g_bp.armed && g_bp.ev[3] && cudaEventSynchronize(g_bp.ev[3]) == cudaSuccess) {
         const auto h3 = std::chrono::steady_clock::now();
         float ms;
@@ -805,6 +842,13 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
     const uint32_t vstride_vec = (uint32_t)(c->view_stride / (c->S < 4 ? c->S : 4));
     int pieces = count >= 32 ? 2 : 1;        // measured on B200 (C2 sweep, staged pieces, r02): 2: 0.248 ms, 3: 0.249, 4: 0.264, 6: 0.304, 8: 0.344 e2e (copy-engine pieces: 2: 0.267)
     if (const char *e = getenv("MPGPU_SCAN_PIECES")) { int v = atoi(e); if (v >= 1) pieces = v; }
+    // tuning knob MPGPU_SCAN_SPLITS="p1,p2,...": piece boundaries in percent of the visits (pieces = boundaries + 1), large batches only
+    static const std::vector<int> split_pct = []() {
+        std::vector<int> v;
+        if (const char *e = getenv("MPGPU_SCAN_SPLITS")) { for (const char *q = e; *q;) { v.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; } }
+        return v;
+    }();
+    if (!split_pct.empty() && count >= 32) pieces = (int)split_pct.size() + 1;
     // a small batch is latency-bound (one warp per task and chunk walks ~100 ops): cut its tasks into sub-tasks
     static const int split_depth = getenv("MPGPU_SPLIT_DEPTH") ? atoi(getenv("MPGPU_SPLIT_DEPTH")) : 3;
     static const int split_max = getenv("MPGPU_SPLIT_MAXCOUNT") ? atoi(getenv("MPGPU_SPLIT_MAXCOUNT")) : 16;
@@ -815,12 +859,20 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
     if (int rc = planner.begin(c->tree, order, first, count, mintrav, maxtrav, vstride_vec, pl, false, vstale, sd, c->ref_table.data())) return rc;
     if (int rc = reserve_plan(c)) return rc;
     if (int rc = zero_counts(c, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
+    g_sw.mark(1, "planner begun, counters zeroed");
     int v0 = 0;
     for (int k = 0; k < pieces; k++) {
         // early pieces are smaller: the device should get going as soon as possible
-        const int v1 = k == pieces - 1 ? count : std::min(count, v0 + std::max(1, (int)((long long)count * (k + 1) / (pieces * (pieces + 1) / 2))));
+        // (tuning knob MPGPU_SCAN_FIRST_PCT: share of the visits in the first of two pieces; MPGPU_SCAN_EQUAL: equal pieces)
+        static const int first_pct = getenv("MPGPU_SCAN_FIRST_PCT") ? atoi(getenv("MPGPU_SCAN_FIRST_PCT")) : 0;
+        static const bool equal_pieces = getenv("MPGPU_SCAN_EQUAL") != nullptr;
+        int v1 = k == pieces - 1 ? count : std::min(count, v0 + std::max(1, (int)((long long)count * (k + 1) / (pieces * (pieces + 1) / 2))));
+        if (k < pieces - 1 && equal_pieces) v1 = std::min(count, std::max(v0 + 1, (int)((long long)count * (k + 1) / pieces)));
+        if (k == 0 && pieces == 2 && first_pct > 0 && first_pct < 100) v1 = std::min(count - 1, std::max(1, (int)((long long)count * first_pct / 100)));
+        if (k < pieces - 1 && (int)split_pct.size() == pieces - 1) v1 = std::min(count, std::max(v0 + 1, (int)((long long)count * split_pct[k] / 100)));
         const int ops0 = pl.n_ops, task0 = (int)pl.tasks.size();
         planner.add(v0, v1);
+        if (pieces <= 4 && g_sw.on) g_sw.mark(2 + 2 * k, k == 0 ? "piece 0 enumerated" : (k == 1 ? "piece 1 enumerated" : "piece k enumerated"));
         if (sd) planner.split();
         // latency path (one piece, one shard, a small plan): the plan rides to the device with the wave launch (or a k_stage
         // launch) and the scan's last block publishes the counts -- no copy engine and no stream synchronize in the step
@@ -861,6 +913,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         if (!pl.sub_tasks.empty()) { if (int rc = launch_scan(c, (int)pl.tasks.size(), (int)pl.sub_tasks.size(), pl.max_slot)) return rc; }
         else if (int rc = launch_scan(c, task0, (int)pl.tasks.size() - task0, pl.max_slot)) return rc;
         c->pub_request = false;                 // (nothing was launched: finish_scan publishes on its own)
+        if (pieces <= 4) g_sw.mark(3 + 2 * k, k == 0 ? "piece 0 staged + launched" : (k == 1 ? "piece 1 staged + launched" : "piece k staged + launched"));
         v0 = v1;
         if (v0 >= count) break;
     }
@@ -1359,7 +1412,9 @@ int mpgpu_scan_visits(mpgpu_ctx *c, const int32_t *order, int first, int count, 
     if (c && !c->reduces()) { set_error("mpgpu_scan_visits on a sharded context needs mpgpu_set_allreduce (or use plan/launch/finish)"); return 1; }
     if (int rc = need_tree(c, true)) return rc;
     if (!order || !mp || first < 1 || count < 0 || first + count > 2 * c->n - 1) { set_error("bad visit range"); return 1; }
+    g_sw.begin();
     MPGPU_CUDA(cudaSetDevice(c->device));
+    g_sw.mark(0, "device set");
     if (int rc = scan_batch_pipelined(c, order, first, count, mintrav, maxtrav)) return rc;
     if (n_cand) *n_cand = c->plan.n_cand;
     if (c->plan.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }

@@ -344,17 +344,27 @@ class Engine:
         self._ck(self.L.mpgpu_visit_order(self.h, _p(out)))
         return out
 
-    def scan_visits(self, order, first, count, mintrav=1, maxtrav=6, capacity=None):
-        order = np.ascontiguousarray(order, dtype=np.int32)
+    def scan_visits(self, order, first, count, mintrav=1, maxtrav=6, capacity=None, reuse=False):
+        """reuse=True: the output arrays of the previous call with the same shape are written again (what a C caller does with its
+        own buffers); the returned views are then only valid until the next such call."""
+        if not (isinstance(order, np.ndarray) and order.dtype == np.int32 and order.flags.c_contiguous):
+            order = np.ascontiguousarray(order, dtype=np.int32)
         if capacity is None:
             capacity = count * (8 << min(maxtrav, 10)) + 16
-        vb = np.zeros(count + 1, dtype=np.int32)
-        mp = np.zeros(capacity, dtype=np.uint32)
-        cr = np.zeros(capacity, dtype=np.int32)
-        cp = np.zeros(capacity, dtype=np.int32)
+        key = (count, capacity)
+        if reuse and getattr(self, "_scan_out_key", None) == key:
+            vb, mp, cr, cp, ptrs = self._scan_out
+        else:
+            vb = np.zeros(count + 1, dtype=np.int32)
+            mp = np.zeros(capacity, dtype=np.uint32)
+            cr = np.zeros(capacity, dtype=np.int32)
+            cp = np.zeros(capacity, dtype=np.int32)
+            ptrs = (_p(vb), _p(mp), _p(cr), _p(cp))
+            if reuse:
+                self._scan_out_key, self._scan_out = key, (vb, mp, cr, cp, ptrs)
         nc = C.c_int()
         self._ck(self.L.mpgpu_scan_visits(self.h, _p(order), first, count, mintrav, maxtrav,
-                                          _p(vb), _p(mp), _p(cr), _p(cp), capacity, C.byref(nc)))
+                                          ptrs[0], ptrs[1], ptrs[2], ptrs[3], capacity, C.byref(nc)))
         k = nc.value
         return vb, mp[:k], cr[:k], cp[:k]
 
