@@ -649,7 +649,19 @@ struct SweepProf {
     const char *name[K] = {nullptr};
     double sum[K] = {0}; long cnt[K] = {0};
     std::chrono::steady_clock::time_point t0;
-    void begin() { if (on) t0 = std::chrono::steady_clock::now(); }
+    cudaEvent_t ev[8] = {nullptr}; const char *ename[8] = {nullptr}; double esum[8] = {0}; long ecnt[8] = {0}; int nev = 0;
+    void begin() { if (on) { t0 = std::chrono::steady_clock::now(); nev = 0; } }
+    void rec(cudaStream_t st, const char *what) {          // a device-side timestamp in stream order
+        if (!on || nev >= 8) return;
+        if (!ev[nev]) cudaEventCreate(&ev[nev]);
+        ename[nev] = what; cudaEventRecord(ev[nev], st); nev++;
+    }
+    void collect() {
+        if (!on || nev < 2) return;
+        cudaEventSynchronize(ev[nev - 1]);
+        for (int k = 1; k < nev; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[0], ev[k]) == cudaSuccess) { esum[k] += ms; ecnt[k]++; } }
+        nev = 0;
+    }
     void mark(int k, const char *what) {
         if (!on || k >= K) return;
         name[k] = what; sum[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); cnt[k]++;
@@ -657,6 +669,7 @@ struct SweepProf {
     ~SweepProf() {
         if (!on) return;
         for (int k = 0; k < K; k++) if (cnt[k]) fprintf(stderr, "[mpgpu sweep timeline] %-34s %8.1f us (n = %ld)\n", name[k], 1e6 * sum[k] / cnt[k], cnt[k]);
+        for (int k = 1; k < 8; k++) if (ecnt[k]) fprintf(stderr, "[mpgpu sweep timeline] device: %-26s %8.1f us after the first stream op (n = %ld)\n", ename[k], 1e3 * esum[k] / ecnt[k], ecnt[k]);
     }
 };
 static SweepProf g_sw;
@@ -790,6 +803,7 @@ int finish_scan(Ctx *c, int32_t *visit_begin, uint32_t *mp, int32_t *cand_ref, i
         c->counts_dirty = nout + 1;
     }
     g_sw.mark(11, "finish: counts on the host");
+    g_sw.rec(c->stream, "publish done"); g_sw.collect();
     settle_views(c, true);
     if (!c->lens_valid) { set_error("view lengths not set"); return 1; }
     const size_t ntasks = pl.tasks.size();
@@ -860,6 +874,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
     if (int rc = reserve_plan(c)) return rc;
     if (int rc = zero_counts(c, (size_t)pl.task_cap + pl.cand_ref.size() + 1)) return rc;
     g_sw.mark(1, "planner begun, counters zeroed");
+    g_sw.rec(c->stream, "start");
     int v0 = 0;
     for (int k = 0; k < pieces; k++) {
         // early pieces are smaller: the device should get going as soon as possible
@@ -913,6 +928,7 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         if (!pl.sub_tasks.empty()) { if (int rc = launch_scan(c, (int)pl.tasks.size(), (int)pl.sub_tasks.size(), pl.max_slot)) return rc; }
         else if (int rc = launch_scan(c, task0, (int)pl.tasks.size() - task0, pl.max_slot)) return rc;
         c->pub_request = false;                 // (nothing was launched: finish_scan publishes on its own)
+        if (pieces <= 4) g_sw.rec(c->stream, k == 0 ? "scan of piece 0 done" : (k == 1 ? "scan of piece 1 done" : "scan of piece k done"));
         if (pieces <= 4) g_sw.mark(3 + 2 * k, k == 0 ? "piece 0 staged + launched" : (k == 1 ? "piece 1 staged + launched" : "piece k staged + launched"));
         v0 = v1;
         if (v0 >= count) break;
