@@ -838,7 +838,7 @@ def measure_sweep(args, workload, scaling, steps, world, rank, local, stream, fl
     vb, mp, cref, cprune = eng.scan_finish(n_cand, nvis)
 
     # e2e: the reference-facing call with host buffers (plan on host, H2D, kernel, exchange, D2H, finish)
-    e2e_steps = max(3, min(steps, 10))
+    e2e_steps = max(3, steps)
     for _ in range(2):                           # untimed warm-up of the end-to-end path (page-locked buffers)
         eng.scan_visits(order, 1, nvis, 1, args.maxtrav, capacity=n_cand + 16, reuse=True)
     barrier()
@@ -969,6 +969,8 @@ def run_ours(args):
         if bb_patterns:
             line["bb_pattern_shards"] = bb_patterns
         line["e2e"]["h2d_bytes_per_step"] = int(eng.scan_plan_bytes())
+        from mpboot_b200 import engine as _engine
+        line["e2e"]["host_threads"] = int(_engine.lib().mpgpu_host_plan_threads())     # threads that enumerate the sweep's plan (MPGPU_PLAN_THREADS)
         if world == 1 and not args.no_search:
             line["search"] = bench_search(eng, case, args)
         if world == 1 and not args.no_bb:

@@ -886,7 +886,8 @@ int scan_batch_pipelined(Ctx *c, const int32_t *order, int first, int count, int
         if (k == 0 && pieces == 2 && first_pct > 0 && first_pct < 100) v1 = std::min(count - 1, std::max(1, (int)((long long)count * first_pct / 100)));
         if (k < pieces - 1 && (int)split_pct.size() == pieces - 1) v1 = std::min(count, std::max(v0 + 1, (int)((long long)count * split_pct[k] / 100)));
         const int ops0 = pl.n_ops, task0 = (int)pl.tasks.size();
-        planner.add(v0, v1);
+        if (!vstale && !sd && v1 - v0 >= 96) planner.add_parallel(v0, v1, plan_threads());     // a big piece of a big batch: several host threads
+        else planner.add(v0, v1);
         if (pieces <= 4 && g_sw.on) g_sw.mark(2 + 2 * k, k == 0 ? "piece 0 enumerated" : (k == 1 ? "piece 1 enumerated" : "piece k enumerated"));
         if (sd) planner.split();
         // latency path (one piece, one shard, a small plan): the plan rides to the device with the wave launch (or a k_stage

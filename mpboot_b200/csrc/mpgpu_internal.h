@@ -461,6 +461,10 @@ public:
               int mintrav, int maxtrav, uint32_t vstride, ScanPlan &plan, bool host_only = false,
               const uint8_t *vstale = nullptr, int split_depth = 0, ScanRef *table = nullptr);
     void add(int v0, int v1);
+    // the same result as add(v0, v1) -- byte for byte -- with the enumeration spread over `nthreads` host threads (the caller's
+    // included): every thread enumerates a range of visits into buffers of its own, then copies its share into place.  Falls
+    // back to add() for small ranges, lazy plans and plans that are split into sub-tasks.
+    void add_parallel(int v0, int v1, int nthreads);
     void finish();
     void split();
 private:
@@ -469,6 +473,7 @@ private:
     ScanPlanner(const ScanPlanner &);
     ScanPlanner &operator=(const ScanPlanner &);
 };
+int plan_threads();                     // host threads ScanPlanner::add_parallel may use (MPGPU_PLAN_THREADS; 1 = the caller alone)
 int build_scan_plan(const HostTree &t, const int32_t *order,
                     int first, int count, int mintrav, int maxtrav, uint32_t vstride_vec, ScanPlan &plan);
 void apply_spr_move(HostTree &t, int remove_ref, int insert_ref);

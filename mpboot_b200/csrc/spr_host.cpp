@@ -9,7 +9,17 @@
 #include "mpgpu_internal.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unistd.h>
 
 namespace mpgpu {
 
@@ -220,9 +230,109 @@ struct ScanPlanner::Impl {
     const int32_t *order;
     int first, mintrav, maxtrav;
     int split_depth = 0;
-    Impl(const HostTree &tt, ScanPlan &plan, uint32_t vstride, const int32_t *ord,
-         int f, int mi, int ma, const uint8_t *vstale, ScanRef *table) : b(tt, plan, vstride, vstale, table), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma) {}
+    uint32_t vstride;
+    Impl(const HostTree &tt, ScanPlan &plan, uint32_t vs, const int32_t *ord,
+         int f, int mi, int ma, const uint8_t *vstale, ScanRef *table) : b(tt, plan, vs, vstale, table), t(tt), order(ord), first(f), mintrav(mi), maxtrav(ma), vstride(vs) {}
 };
+
+// ---- host threads for the enumeration of large plans ----------------------------------------------------------------------
+// A whole sweep (C2: 398 visits, 14 476 candidates) takes one thread ~105 us to enumerate -- as long as the device needs to
+// score it -- and sits in front of the last piece's launch on the e2e path.  The visits are independent, so a few detached
+// workers enumerate ranges of them side by side.  They spin for a short while after a job (a sweep loop keeps them hot) and
+// sleep on a condition variable otherwise; the pool is created on first use, per process (a forked child gets its own), and
+// never torn down (no join at exit: the threads own nothing).
+namespace {
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+// A job is a number of independent items; every thread (the caller included) draws items from a shared counter until none is
+// left, so the caller never waits for a worker that is asleep or was descheduled -- it only waits for items already drawn.
+struct PlanJob {
+    std::atomic<int> next{0}, done{0};
+    int total = 0;
+    std::function<void(int, int)> fn;                    // (thread, item); only ever called while the caller is still inside run()
+};
+class PlanPool {
+public:
+    explicit PlanPool(int workers) : n_(workers)
+    {
+        for (int k = 0; k <= workers; k++) parts.emplace_back(new ScanPlan());
+        for (int k = 1; k <= workers; k++) std::thread([this, k]() { loop(k); }).detach();
+    }
+    int workers() const { return n_; }
+    void run(int total, const std::function<void(int, int)> &fn)
+    {
+        std::shared_ptr<PlanJob> job = std::make_shared<PlanJob>();
+        job->total = total; job->fn = fn;
+        { std::lock_guard<std::mutex> lk(m_); cur_ = job; gen_.fetch_add(1, std::memory_order_release); }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+        drain(*job, 0);
+        while (job->done.load(std::memory_order_acquire) != total) cpu_relax();
+    }
+    std::vector<std::unique_ptr<ScanPlan>> parts;        // per thread: the buffers its items are enumerated into (kept across calls)
+private:
+    static void drain(PlanJob &job, int k)
+    {
+        for (;;) {
+            const int i = job.next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= job.total) return;                  // (a late thread gets here long after run() returned: it touches the job only)
+            job.fn(k, i);
+            job.done.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void loop(int k)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            const auto t0 = std::chrono::steady_clock::now();
+            unsigned spins = 0;
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                cpu_relax();
+                if ((++spins & 255) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(500)) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    sleepers_.fetch_add(1, std::memory_order_release);
+                    cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
+                    sleepers_.fetch_sub(1, std::memory_order_release);
+                }
+            }
+            std::shared_ptr<PlanJob> job;
+            { std::lock_guard<std::mutex> lk(m_); job = cur_; seen = gen_.load(std::memory_order_acquire); }
+            if (job) drain(*job, k);
+        }
+    }
+    const int n_;
+    std::shared_ptr<PlanJob> cur_;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> sleepers_{0};
+    std::mutex m_;
+    std::condition_variable cv_;
+};
+}  // namespace
+// host threads for the enumeration of a large batch: MPGPU_PLAN_THREADS, else up to 4 when the machine has the cores to spare
+int plan_threads()
+{
+    static const int n = []() {
+        if (const char *e = getenv("MPGPU_PLAN_THREADS")) { const int v = atoi(e); return v < 1 ? 1 : (v > 8 ? 8 : v); }
+        const unsigned hc = std::thread::hardware_concurrency();
+        return hc >= 8 ? 4 : (hc >= 4 ? 2 : 1);
+    }();
+    return n;
+}
+namespace {
+PlanPool *plan_pool(int workers)
+{
+    static std::mutex mk;
+    static PlanPool *pool = nullptr;
+    static pid_t owner = 0;
+    static int size = 0;
+    std::lock_guard<std::mutex> lk(mk);
+    if (!pool || owner != getpid() || size != workers) { pool = new PlanPool(workers); owner = getpid(); size = workers; }   // (an outgrown pool is left to sleep)
+    return pool;
+}
+}  // namespace
 
 ScanPlanner::ScanPlanner() : impl(nullptr) {}
 ScanPlanner::~ScanPlanner() { delete impl; }
@@ -252,7 +362,7 @@ int ScanPlanner::begin(const HostTree &t, const int32_t *order, int first, int c
     plan.item_cap = impl->split_depth > 0 ? (size_t)plan.task_cap * (1 + ((size_t)2 << split_depth)) : (size_t)plan.task_cap;
     if (impl->split_depth > 0) { if (plan.kid_op.size() < 2 * cap1) plan.kid_op.resize(2 * cap1); b.kid_op = plan.kid_op.data(); }
     if (host_only) {
-        plan.offs_host.resize(cap + cap / 4); plan.ctl_host.resize(cap + cap / 4);
+        if (plan.offs_host.size() < cap + cap / 4) { plan.offs_host.resize(cap + cap / 4); plan.ctl_host.resize(cap + cap / 4); }   // (grow only: no refill)
     } else if (!plan.offs.reserve(cap + cap / 4) || !plan.ctl.reserve(cap + cap / 4) || !plan.tasks_pin.reserve(plan.item_cap + 16)) {
         set_error("page-locked host allocation for the scan plan failed"); return 1;
     }
@@ -320,6 +430,70 @@ void ScanPlanner::add(int v0, int v1)
             }
         }
     }
+    plan.n_cand = b.ncand; plan.n_ops = b.nops; plan.max_slot = b.max_slot;
+}
+
+void ScanPlanner::add_parallel(int v0, int v1, int nthreads)
+{
+    Builder &b = impl->b;
+    ScanPlan &plan = b.plan;
+    const int nv = v1 - v0;
+    if (nthreads > 8) nthreads = 8;
+    if (nthreads < 2 || nv < 16 * nthreads || b.lazy || b.kid_op || impl->maxtrav < impl->mintrav) { add(v0, v1); return; }
+    PlanPool *pool = plan_pool(nthreads - 1);
+    const int W = pool->workers() + 1;
+    const Impl *me = impl;
+    // the range in chunks of 16 visits; a chunk is enumerated by whichever thread draws it, into that thread's own buffers
+    // (local op, candidate and task numbers), and remembers where
+    const int CH = 16, C = (nv + CH - 1) / CH;
+    struct Chunk { int owner, ops, nops, cand, ncand, task, ntask, vis, nvis; };
+    std::vector<Chunk> chunks((size_t)C);
+    std::vector<std::unique_ptr<ScanPlanner>> sub((size_t)W);
+    pool->run(C, [&](int k, int c) {
+        ScanPlan &pp = *pool->parts[k];
+        if (!sub[k]) {
+            sub[k].reset(new ScanPlanner());
+            if (sub[k]->begin(me->t, me->order, me->first + v0, nv, me->mintrav, me->maxtrav, me->vstride, pp, true, nullptr, 0, me->b.ref_)) return;
+        }
+        Chunk &ck = chunks[c];
+        ck.owner = k; ck.ops = pp.n_ops; ck.cand = pp.n_cand; ck.task = (int)pp.tasks.size(); ck.vis = (int)pp.visit_ref.size();
+        sub[k]->add(c * CH, std::min(nv, c * CH + CH));
+        ck.nops = pp.n_ops - ck.ops; ck.ncand = pp.n_cand - ck.cand; ck.ntask = (int)pp.tasks.size() - ck.task; ck.nvis = (int)pp.visit_ref.size() - ck.vis;
+    });
+    std::vector<int> ops0((size_t)C + 1), cand0((size_t)C + 1), task0((size_t)C + 1);
+    ops0[0] = b.nops; cand0[0] = b.ncand; task0[0] = (int)plan.tasks.size();
+    for (int c = 0; c < C; c++) { ops0[c + 1] = ops0[c] + chunks[c].nops; cand0[c + 1] = cand0[c] + chunks[c].ncand; task0[c + 1] = task0[c] + chunks[c].ntask; }
+    // every chunk's streams move to their place in the plan, in visit order (control words are relative to their task: unchanged)
+    pool->run(C, [&](int, int c) {
+        const Chunk &ck = chunks[c];
+        const ScanPlan &pp = *pool->parts[ck.owner];
+        memcpy(b.offs + ops0[c], pp.offs_host.data() + ck.ops, (size_t)ck.nops * sizeof(ScanOffs));
+        memcpy(b.ctl + ops0[c], pp.ctl_host.data() + ck.ops, (size_t)ck.nops * sizeof(ScanCtl));
+        memcpy(b.cand_ref + cand0[c], pp.cand_ref.data() + ck.cand, (size_t)ck.ncand * sizeof(int32_t));
+        memcpy(b.cand_prune + cand0[c], pp.cand_prune.data() + ck.cand, (size_t)ck.ncand * sizeof(int32_t));
+        const int32_t *ct = pp.cand_task.data() + ck.cand;
+        int32_t *dst = b.cand_task + cand0[c];
+        const int shift = task0[c] - ck.task;
+        for (int j = 0; j < ck.ncand; j++) dst[j] = ct[j] + shift;
+    });
+    for (int c = 0; c < C; c++) {
+        const Chunk &ck = chunks[c];
+        const ScanPlan &pp = *pool->parts[ck.owner];
+        for (int i = 0; i < ck.ntask; i++) {
+            ScanTask tk = pp.tasks[(size_t)ck.task + i];
+            tk.op_begin += ops0[c] - ck.ops; tk.op_end += ops0[c] - ck.ops;
+            tk.base_out = task0[c] + i;
+            tk.cand_base = plan.task_cap + cand0[c] + (tk.cand_base - pp.task_cap - ck.cand);
+            plan.tasks.push_back(tk);
+        }
+        for (int i = 0; i < ck.nvis; i++) {
+            plan.visit_begin.push_back(pp.visit_begin[(size_t)ck.vis + i] - ck.cand + cand0[c]);
+            plan.visit_ref.push_back(pp.visit_ref[(size_t)ck.vis + i]);
+        }
+        plan.task_vids.insert(plan.task_vids.end(), pp.task_vids.begin() + 3 * (size_t)ck.task, pp.task_vids.begin() + 3 * (size_t)(ck.task + ck.ntask));
+    }
+    for (int k = 0; k < W; k++) if (sub[k] && pool->parts[k]->max_slot > b.max_slot) b.max_slot = pool->parts[k]->max_slot;
+    b.nops = ops0[C]; b.ncand = cand0[C];
     plan.n_cand = b.ncand; plan.n_ops = b.nops; plan.max_slot = b.max_slot;
 }
 
@@ -406,13 +580,51 @@ int mpgpu_host_enumerate(int ntaxa, const int32_t *back_node, const int32_t *bac
     static thread_local ScanPlan plan;                     // its arrays are sized to an upper bound: keep them across calls
     ScanPlanner pl;
     if (int rc = pl.begin(t, order, first, count, mintrav, maxtrav, 1u, plan, true)) return rc;
-    pl.add(0, count);
+    pl.add_parallel(0, count, plan_threads());
     pl.finish();
     if (n_cand) *n_cand = plan.n_cand;
     if (plan.n_cand > capacity) { set_error("candidate capacity too small"); return 1; }
     memcpy(visit_begin, plan.visit_begin.data(), plan.visit_begin.size() * sizeof(int32_t));
     if (cand_ref) memcpy(cand_ref, plan.cand_ref.data(), (size_t)plan.n_cand * sizeof(int32_t));
     if (cand_prune) memcpy(cand_prune, plan.cand_prune.data(), (size_t)plan.n_cand * sizeof(int32_t));
+    return 0;
+}
+
+int mpgpu_host_plan_threads(void) { return plan_threads(); }
+
+int mpgpu_host_plan_selftest(int ntaxa, const int32_t *back_node, const int32_t *back_slot, const int32_t *order, int first, int count,
+                             int mintrav, int maxtrav, int nthreads, int pieces)
+{
+    HostTree t;
+    if (int rc = host_tree_from(ntaxa, back_node, back_slot, t)) return rc;
+    if (!order || first < 1 || count < 0 || first + count > 2 * ntaxa - 1 || pieces < 1) { set_error("bad visit range"); return 1; }
+    ScanPlan a, b;
+    {
+        ScanPlanner pl;
+        if (int rc = pl.begin(t, order, first, count, mintrav, maxtrav, 7u, a, true)) return rc;
+        pl.add(0, count);
+        pl.finish();
+    }
+    {
+        ScanPlanner pl;
+        if (int rc = pl.begin(t, order, first, count, mintrav, maxtrav, 7u, b, true)) return rc;
+        int v0 = 0;
+        for (int k = 0; k < pieces; k++) {
+            const int v1 = k == pieces - 1 ? count : std::min(count, (int)((long long)count * (k + 1) / pieces));
+            pl.add_parallel(v0, v1, nthreads);
+            v0 = v1;
+        }
+        pl.finish();
+    }
+    const char *bad = nullptr;
+    if (a.n_cand != b.n_cand || a.n_ops != b.n_ops || a.max_slot != b.max_slot || a.task_cap != b.task_cap) bad = "counts";
+    else if (a.tasks.size() != b.tasks.size() || (a.tasks.size() && memcmp(a.tasks.data(), b.tasks.data(), a.tasks.size() * sizeof(ScanTask)))) bad = "tasks";
+    else if (memcmp(a.offs_host.data(), b.offs_host.data(), (size_t)a.n_ops * sizeof(ScanOffs))) bad = "view offsets";
+    else if (memcmp(a.ctl_host.data(), b.ctl_host.data(), (size_t)a.n_ops * sizeof(ScanCtl))) bad = "control words";
+    else if (memcmp(a.cand_ref.data(), b.cand_ref.data(), (size_t)a.n_cand * 4) || memcmp(a.cand_prune.data(), b.cand_prune.data(), (size_t)a.n_cand * 4) ||
+             memcmp(a.cand_task.data(), b.cand_task.data(), (size_t)a.n_cand * 4)) bad = "candidate tables";
+    else if (a.visit_begin != b.visit_begin || a.visit_ref != b.visit_ref || a.task_vids != b.task_vids) bad = "visit tables";
+    if (bad) { set_error(std::string("parallel enumeration differs from the sequential one: ") + bad); return 2; }
     return 0;
 }
 

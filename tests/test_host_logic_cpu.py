@@ -117,3 +117,29 @@ def test_apply_move_matches_oracle(n, seed):
         if moved >= 12:
             break
     assert moved >= 3
+
+
+@pytest.mark.parametrize("n,seed", [(40, 3), (200, 5), (777, 9)])
+def test_parallel_enumeration_is_the_sequential_plan(n, seed):
+    """Large batches are enumerated by several host threads (ScanPlanner::add_parallel): the scan program -- tasks, view offsets,
+    control words, candidate and visit tables -- must be the same bytes as the single-threaded one, for any thread count, piece
+    count and visit range; called repeatedly (the pool's workers sleep and wake) and from a forked child (a pool of its own)."""
+    import os
+    from mpboot_b200 import synth
+    L = engine.lib()
+    L.mpgpu_last_error.restype = C.c_char_p
+    L.mpgpu_host_plan_selftest.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6
+    bn, bs = synth.random_tree_rings(n, np.random.default_rng(seed))
+    bn = np.ascontiguousarray(bn, dtype=np.int32); bs = np.ascontiguousarray(bs, dtype=np.int32)
+    order = host_visit_order(n, bn, bs)
+    for rep in range(3):
+        for nthreads in (1, 2, 3, 4, 8):
+            for pieces in (1, 2, 3):
+                for first, count, mt in ((1, 2 * n - 2, 6), (n // 2, n, 3), (n + 1, n - 2, 8), (1, 2 * n - 2, 1)):
+                    rc = L.mpgpu_host_plan_selftest(n, _p(bn), _p(bs), _p(order), first, count, 1, mt, nthreads, pieces)
+                    assert rc == 0, (L.mpgpu_last_error().decode(), nthreads, pieces, first, count, mt)
+    pid = os.fork()
+    if pid == 0:
+        rc = L.mpgpu_host_plan_selftest(n, _p(bn), _p(bs), _p(order), 1, 2 * n - 2, 1, 6, 4, 2)
+        os._exit(0 if rc == 0 else 1)
+    assert os.waitpid(pid, 0)[1] == 0
