@@ -15,6 +15,9 @@
  *   - threading: like the reference's engine (file-scope globals, sprparsimony.cpp:127-141) a context is not re-entrant,
  *     and contexts on the SAME device must be driven from one host thread (under -cost they share one constant bank for
  *     the cost matrix, re-bound on alternating use).  One process (or thread) per GPU is the intended layout.
+ *     The library itself starts up to three detached helper threads the first time a large batch (>= 96 node visits) is
+ *     enumerated (mpgpu_host_plan_threads below; MPGPU_PLAN_THREADS=1: none); they touch host memory of the call only,
+ *     never CUDA, and sleep between batches.  A forked child gets helpers of its own.
  *   - trees travel as PLL "ring tables": nodes 1..n are tips, n+1..2n-2 inner nodes; an inner
  *     node has ring slots 0,1,2 (slot s+1 = ->next of slot s, pllrepo/src/pll.h:687-702), a
  *     tip only slot 0.  back_node[3*i+s] / back_slot[3*i+s] = node number and slot hooked to
