@@ -439,7 +439,8 @@ int mpgpu_host_enumerate(int ntaxa, const int32_t *back_node, const int32_t *bac
 int mpgpu_host_apply_spr(int ntaxa, int32_t *back_node, int32_t *back_slot, int32_t remove_ref, int32_t insert_ref);
 /* Host threads the library uses to enumerate a large batch (>= 96 node visits in one piece, outside SPR searches): the caller's plus
  * up to three detached helpers, started on first use, that sleep between batches; environment MPGPU_PLAN_THREADS=<n> (1 = none),
- * default 4 on machines with 8 or more hardware threads, 2 with 4 or more.  The result does not depend on it. */
+ * default 4 on machines with 8 or more hardware threads per process of the node (LOCAL_WORLD_SIZE, as torchrun exports it), 2 with 4
+ * or more, else 1.  The result does not depend on it. */
 int mpgpu_host_plan_threads(void);
 /* Test aid: the scan program of those visits built once by one thread and once by `nthreads` host threads in `pieces` pieces (the
  * way mpgpu_scan_visits builds a large batch); 0 <=> tasks, view offsets, control words, candidate and visit tables are the same

@@ -316,7 +316,10 @@ int plan_threads()
 {
     static const int n = []() {
         if (const char *e = getenv("MPGPU_PLAN_THREADS")) { const int v = atoi(e); return v < 1 ? 1 : (v > 8 ? 8 : v); }
-        const unsigned hc = std::thread::hardware_concurrency();
+        // one process per GPU: the processes of a node share its cores (torchrun exports LOCAL_WORLD_SIZE), and a spinning helper
+        // must not take a core another rank's calling thread needs -- at most half the hardware threads are ever used
+        unsigned hc = std::thread::hardware_concurrency();
+        if (const char *w = getenv("LOCAL_WORLD_SIZE")) { const int lw = atoi(w); if (lw > 1) hc /= (unsigned)lw; }
         return hc >= 8 ? 4 : (hc >= 4 ? 2 : 1);
     }();
     return n;
