@@ -138,7 +138,10 @@ def test_parallel_enumeration_is_the_sequential_plan(n, seed):
                 for first, count, mt in ((1, 2 * n - 2, 6), (n // 2, n, 3), (n + 1, n - 2, 8), (1, 2 * n - 2, 1)):
                     rc = L.mpgpu_host_plan_selftest(n, _p(bn), _p(bs), _p(order), first, count, 1, mt, nthreads, pieces)
                     assert rc == 0, (L.mpgpu_last_error().decode(), nthreads, pieces, first, count, mt)
-    pid = os.fork()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)      # (forking with the pool's helper threads around is the point)
+        pid = os.fork()
     if pid == 0:
         rc = L.mpgpu_host_plan_selftest(n, _p(bn), _p(bs), _p(order), 1, 2 * n - 2, 1, 6, 4, 2)
         os._exit(0 if rc == 0 else 1)
