@@ -273,6 +273,7 @@ public:
         while (job->done.load(std::memory_order_acquire) != total) cpu_relax();
     }
     std::vector<std::unique_ptr<ScanPlan>> parts;        // per thread: the buffers its items are enumerated into (kept across calls)
+    std::mutex busy;                                     // one plan at a time uses the pool (and its buffers); others enumerate alone
 private:
     static void drain(PlanJob &job, int k)
     {
@@ -328,12 +329,14 @@ namespace {
 PlanPool *plan_pool(int workers)
 {
     static std::mutex mk;
-    static PlanPool *pool = nullptr;
+    static PlanPool *pools[8] = {nullptr};               // one per size (in practice one size per process), never torn down
     static pid_t owner = 0;
-    static int size = 0;
     std::lock_guard<std::mutex> lk(mk);
-    if (!pool || owner != getpid() || size != workers) { pool = new PlanPool(workers); owner = getpid(); size = workers; }   // (an outgrown pool is left to sleep)
-    return pool;
+    if (owner != getpid()) { for (PlanPool *&p : pools) p = nullptr; owner = getpid(); }      // a forked child: the parent's helpers are not here
+    if (workers < 1) workers = 1;
+    if (workers > 7) workers = 7;
+    if (!pools[workers]) pools[workers] = new PlanPool(workers);
+    return pools[workers];
 }
 }  // namespace
 
@@ -444,6 +447,9 @@ void ScanPlanner::add_parallel(int v0, int v1, int nthreads)
     if (nthreads > 8) nthreads = 8;
     if (nthreads < 2 || nv < 16 * nthreads || b.lazy || b.kid_op || impl->maxtrav < impl->mintrav) { add(v0, v1); return; }
     PlanPool *pool = plan_pool(nthreads - 1);
+    // contexts driven from different host threads (one per GPU) share the pool: whoever finds it taken enumerates on its own
+    std::unique_lock<std::mutex> taken(pool->busy, std::try_to_lock);
+    if (!taken.owns_lock()) { add(v0, v1); return; }
     const int W = pool->workers() + 1;
     const Impl *me = impl;
     // the range in chunks of 16 visits; a chunk is enumerated by whichever thread draws it, into that thread's own buffers

@@ -26,7 +26,7 @@ static void random_tree(int n, unsigned seed, std::vector<int32_t> &bn, std::vec
     }
     bn = t.bn; bs = t.bs;
 }
-int main()
+static int run_all(int seed_off)
 {
     for (int n : {50, 200, 600}) {
         std::vector<int32_t> bn, bs, order(2 * n - 1);
@@ -39,6 +39,18 @@ int main()
                     if (rc) { printf("selftest rc=%d n=%d nt=%d pieces=%d: %s\n", rc, n, nt, pieces, mpgpu::g_err.c_str()); return 1; }
                 }
     }
+    (void)seed_off;
+    return 0;
+}
+#include <thread>
+int main()
+{
+    if (run_all(0)) return 1;
+    // two host threads (two contexts, one per GPU) enumerating at the same time: one gets the pool, the other falls back to add()
+    int rc1 = 0, rc2 = 0;
+    std::thread a([&]() { rc1 = run_all(1); }), b([&]() { rc2 = run_all(2); });
+    a.join(); b.join();
+    if (rc1 || rc2) return 1;
     printf("ok\n");
     return 0;
 }
