@@ -146,3 +146,46 @@ def test_parallel_enumeration_is_the_sequential_plan(n, seed):
         rc = L.mpgpu_host_plan_selftest(n, _p(bn), _p(bs), _p(order), 1, 2 * n - 2, 1, 6, 4, 2)
         os._exit(0 if rc == 0 else 1)
     assert os.waitpid(pid, 0)[1] == 0
+
+
+def test_disthit_hook_is_the_reference_list_update():
+    """The -distinct_iter_top_boot list update (iqtree.cpp:3624-3677) as the library's treels container implements it (the `disthit`
+    hook mpgpu_optimize_spr_bb calls on every accepted tree), against a line-by-line restatement on random call sequences: tree
+    already listed -> nothing; this iteration has an entry -> the better one stays; room left -> append; full -> the worst goes;
+    the threshold is the list's minimum."""
+    from mpboot_b200.engine import Treels, BBHooks
+    L = engine.lib()
+    rng = np.random.default_rng(77)
+    for K in (1, 2, 3, 5):
+        tl = Treels(8)
+        hk = tl.hooks(C.cast(L.mpgpu_splitmix64_double, C.c_void_p).value)
+        fn = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32)(hk.disthit)
+        B = 6
+        top = [[] for _ in range(B)]; it_of = [[] for _ in range(B)]; thr = [-(2 ** 31 - 1)] * B
+        for step in range(4000):
+            b = int(rng.integers(B)); tree = int(rng.integers(40)); cur_it = 1 + step // 400
+            # only calls the policy accepts reach the hook: rell >= threshold
+            rell = int(max(thr[b], -300) + rng.integers(0, 4)) if thr[b] > -(2 ** 31 - 1) else int(-300 + rng.integers(0, 20))
+            t = min(K, len(it_of[b]))
+            new_thr = thr[b]
+            if not any(top[b][c][0] == tree for c in range(t)):
+                c = 0
+                while c < t:
+                    if it_of[b][c] == cur_it:
+                        if rell > top[b][c][1]:
+                            top[b][c] = [tree, rell]
+                        break
+                    c += 1
+                if c == t and t < K:
+                    it_of[b].append(cur_it); top[b].append([tree, rell])
+                elif c == t and t == K:
+                    worst = min(range(t), key=lambda d: (top[b][d][1], d))
+                    top[b][worst] = [tree, rell]; it_of[b][worst] = cur_it
+                new_thr = min(e[1] for e in top[b])
+            got = fn(hk.user, b, tree, rell, cur_it, K, thr[b])
+            assert got == new_thr, (K, step)
+            thr[b] = new_thr
+        sizes, flat = tl.toplists(B)
+        assert list(sizes) == [len(x) for x in top]
+        assert flat.tolist() == [e for x in top for e in x]
+        assert tl.topiters(B).tolist() == [i for x in it_of for i in x]
